@@ -1,0 +1,159 @@
+"""Pin the oracle to the reference's own outputs (tests/golden/*.npz, made by make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cnn as ocnn
+from oracle import gradcam as ogc
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _numpy_case(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cfg = ocnn.NetConfig.numpy_flavour(tuple(int(v) for v in g["input_shape"]), 2,
+                                       [tuple(int(a) for a in r) for r in g["conv_layers"]],
+                                       [int(v) for v in g["hidden"]], float(g["alpha"]))
+    n_conv = len(cfg.conv_layers)
+    conv_idx = [2 * i for i in range(n_conv)]                       # layers index incl. pools
+    dense_idx = [2 * n_conv + j for j in range(len(cfg.hidden_units) + 1)]
+    p = ocnn.Params([g[f"W{i}"] for i in conv_idx], [g[f"b{i}"] for i in conv_idx],
+                    [g[f"W{i}"] for i in dense_idx], [g[f"b{i}"] for i in dense_idx])
+    return g, cfg, p, conv_idx, dense_idx
+
+
+@pytest.mark.parametrize("name", ["ref_numpy_small", "ref_numpy_odd", "ref_numpy_ties", "ref_numpy_k5"])
+def test_numpy_flavour_forward_and_explain(name):
+    g, cfg, p, conv_idx, dense_idx = _numpy_case(name)
+    cache = ocnn.forward(cfg, p, g["x"])
+    tol = dict(rtol=0, atol=1e-11)
+    np.testing.assert_allclose(cache.probs[0].numpy(), g["probs"], **tol)
+    assert int(cache.probs[0].argmax()) == int(g["pred_class"])
+    for bi, li in enumerate(conv_idx):
+        np.testing.assert_allclose(cache.conv_out[bi][0].numpy(), g[f"conv_out{li}"], **tol)
+        np.testing.assert_allclose(cache.pool_out[bi][0].numpy(), g[f"pool_out{li + 1}"], **tol)
+        assert np.array_equal(cache.switches[bi][0].numpy() > 0, g[f"switches{li + 1}"])
+    for j, li in enumerate(dense_idx):
+        np.testing.assert_allclose(cache.z[j][0].numpy(), g[f"z{li}"], **tol)
+    for c in (0, 1):
+        d_top = ocnn.top_gradient(cache, c, "softmax_ce")
+        cag, d_input, wg = ocnn.backward(cfg, p, cache, d_top, want_wgrads=True)
+        np.testing.assert_allclose(d_input[0].numpy(), g[f"d_input_c{c}"], **tol)
+        for bi, li in enumerate(conv_idx):
+            np.testing.assert_allclose(cag[bi][0].numpy(), g[f"conv_act_grads{li}_c{c}"], **tol)
+            np.testing.assert_allclose(wg["conv"][bi][0][0].numpy(), g[f"grad{li}_dF_c{c}"], **tol)
+            np.testing.assert_allclose(wg["conv"][bi][1][0].numpy(), g[f"grad{li}_db_conv_c{c}"], **tol)
+        for j, li in enumerate(dense_idx):
+            np.testing.assert_allclose(wg["dense"][j][0][0].numpy(), g[f"grad{li}_dW_c{c}"], **tol)
+            np.testing.assert_allclose(wg["dense"][j][1][0].numpy(), g[f"grad{li}_db_c{c}"], **tol)
+        sal, _ = ogc.saliency_map(d_input[0].numpy())
+        np.testing.assert_allclose(sal, g[f"saliency_c{c}"], **tol)
+
+
+def test_ties_fixture_really_has_ties():
+    g, cfg, p, conv_idx, _ = _numpy_case("ref_numpy_ties")
+    sw = g[f"switches{conv_idx[0] + 1}"]
+    h2, w2 = sw.shape[0] // 2, sw.shape[1] // 2
+    per_window = sw[:2 * h2, :2 * w2].reshape(h2, 2, w2, 2, -1).sum(axis=(1, 3))
+    assert per_window.max() == 4 and per_window.min() >= 1
+
+
+def _torch_case(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cfg = ocnn.NetConfig.torch_flavour(tuple(int(v) for v in g["input_shape"]), 2,
+                                       [tuple(int(a) for a in r) for r in g["conv_layers"]],
+                                       [int(v) for v in g["hidden"]], float(g["alpha"]))
+    n_conv, n_dense = len(cfg.conv_layers), len(cfg.hidden_units) + 1
+    p = ocnn.Params([g[f"sd.convs.{i}.weight"].transpose(0, 2, 3, 1) for i in range(n_conv)],
+                    [g[f"sd.convs.{i}.bias"] for i in range(n_conv)],
+                    [g[f"sd.fc.{3 * j}.weight"] for j in range(n_dense)],
+                    [g[f"sd.fc.{3 * j}.bias"] for j in range(n_dense)])
+    return g, cfg, p
+
+
+@pytest.mark.parametrize("name", ["ref_torch_small", "ref_torch_odd"])
+def test_torch_flavour_forward_and_gradients(name):
+    g, cfg, p = _torch_case(name)
+    cache = ocnn.forward(cfg, p, g["x"])                       # fp64 oracle vs fp32 reference
+    np.testing.assert_allclose(cache.logits.numpy(), g["logits"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(cache.probs.numpy(), g["probs"], rtol=0, atol=2e-6)
+    assert np.array_equal(cache.logits.argmax(dim=1).numpy(), g["pred_class"])
+    np.testing.assert_allclose(cache.conv_out[-1].permute(0, 3, 1, 2).numpy(), g["A_last"], rtol=0, atol=2e-6)
+    for c in (0, 1):
+        cag, _, _ = ocnn.backward(cfg, p, cache, ocnn.top_gradient(cache, c, "logit"))
+        for i in range(len(cfg.conv_layers)):
+            np.testing.assert_allclose(cag[i].permute(0, 3, 1, 2).numpy(), g[f"dA{i}_logit_c{c}"],
+                                       rtol=0, atol=2e-6)
+
+
+def test_state_dict_converter_roundtrip():
+    """NumPy-layout params (HWC fc1 columns) -> ADCNNM state_dict -> same function."""
+    cfg_np = ocnn.NetConfig((10, 12, 2), 2, [(3, 3), (4, 3)], [5], 0.01, 0.01, 1, "hwc", "first", "logits")
+    p = ocnn.init_params(cfg_np, seed=5, bias_std=0.1)
+    sd = ocnn.params_to_state_dict(cfg_np, p)
+    cfg_t = ocnn.NetConfig.torch_flavour((10, 12, 2), 2, [(3, 3), (4, 3)], [5])
+    p_t = ocnn.Params([sd[f"convs.{i}.weight"].numpy().transpose(0, 2, 3, 1) for i in range(2)],
+                      [sd[f"convs.{i}.bias"].numpy() for i in range(2)],
+                      [sd[f"fc.{3 * j}.weight"].numpy() for j in range(2)],
+                      [sd[f"fc.{3 * j}.bias"].numpy() for j in range(2)])
+    x = ocnn.synth_images(3, (10, 12, 2), seed=1)
+    a = ocnn.forward(cfg_np, p, x).logits.numpy()
+    b = ocnn.forward(cfg_t, p_t, x).logits.numpy()
+    np.testing.assert_allclose(a, b, rtol=0, atol=1e-6)
+
+
+def test_bilinear_equals_cv2_fixture():
+    g = np.load(os.path.join(GOLDEN, "cv2_resize.npz"))
+    i = 0
+    while f"src{i}" in g:
+        dst = g[f"dst{i}"]
+        got = ogc.bilinear_resize(g[f"src{i}"], dst.shape[0], dst.shape[1])
+        np.testing.assert_allclose(got, dst, rtol=0, atol=1.3e-7)   # <= 1 ulp at 1.0
+        i += 1
+    assert i >= 6
+
+
+def test_jet_lut_fixture():
+    lut = ogc.jet_lut_bgr()
+    assert lut.shape == (256, 3) and lut.dtype == np.uint8
+    assert lut[0].tolist() == [128, 0, 0] and lut[255].tolist() == [0, 0, 128]
+
+
+def test_tail_known_answers():
+    """Known-answer micro-tests the reference lacks."""
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((2, 4, 6, 6)).astype(np.float32)
+    # constant map: min == max => 0/(1e-7) path => all zeros
+    out = ogc.gradcam_tail(np.ones_like(A), np.ones_like(A), (12, 12))
+    assert np.all(out == 0)
+    # all-negative cam => ReLU => zeros
+    out = ogc.gradcam_tail(np.abs(A), -np.ones_like(A), (12, 12))
+    assert np.all(out == 0)
+    # generic: range [0,1], max hits ~1 after the second normalisation
+    out = ogc.gradcam_tail(A, rng.standard_normal(A.shape).astype(np.float32), (12, 12))
+    assert out.dtype == np.float32 and out.min() == 0 and abs(out.max() - 1) < 1e-5
+
+
+@pytest.mark.ref
+def test_oracle_against_live_reference():
+    """When /root/reference is present: a fresh random case straight through the reference."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("no /root/reference on this machine")
+    ref = ref_loader.load_numpy_cnn()
+    np.random.seed(99)
+    with ref_loader.silenced():
+        m = ref.CNNModel((10, 9, 2), 2, conv_layers=[(2, 3), (3, 3)], hidden_units=[4], leaky_alpha=0.1)
+    cfg = ocnn.NetConfig.numpy_flavour((10, 9, 2), 2, [(2, 3), (3, 3)], [4], 0.1)
+    p = ocnn.Params([m.layers[0]["filters"], m.layers[2]["filters"]],
+                    [m.layers[0]["biases"], m.layers[2]["biases"]],
+                    [m.layers[4]["weights"], m.layers[5]["weights"]],
+                    [m.layers[4]["biases"], m.layers[5]["biases"]])
+    x = np.random.randn(10, 9, 2)
+    with ref_loader.silenced():
+        cls, probs = m.predict(x)
+    c, pr, _ = ocnn.predict(cfg, p, x)
+    assert int(c[0]) == int(cls)
+    np.testing.assert_allclose(pr[0], probs, rtol=0, atol=1e-12)
