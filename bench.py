@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched predict + Grad-CAM images/s at 256x256 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of predict + Grad-CAM over one batch of synthetic images that is already resident
+in HBM (value) or sits in pinned host memory (e2e, through the host-buffer C-ABI call).  Workload at N=1 is
+BASELINE.json configs[1]: the ADCNNM-flavour CNN (conv 32,64 k3 pad1 / fc 256,128 / 2 classes, random init)
+on 512 synthetic 256x256x1 images; at N>1 each rank runs that same batch on its own GPU (weak scaling, no
+collective on the data path); rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "predict+Grad-CAM images/sec at 256x256"
+UNIT = "images/s"
+INPUT_SHAPE = (256, 256, 1)
+CONV_LAYERS = [(32, 3), (64, 3)]
+HIDDEN = [256, 128]
+NUM_CLASSES = 2
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic work per image, same-pad ADCNNM flavour at 256x256x1
+# ------------------------------------------------------------------------------------------------
+def algorithmic_flops_per_image():
+    h, w, c = INPUT_SHAPE
+    fl = {}
+    cin = c
+    for i, (f, k) in enumerate(CONV_LAYERS):
+        fl[f"conv{i}"] = 2.0 * h * w * f * k * k * cin       # same-pad: output map == input map
+        h, w, cin = h // 2, w // 2, f
+    flat = h * w * cin
+    prev, dense = flat, 0.0
+    for u in HIDDEN + [NUM_CLASSES]:
+        dense += 2.0 * prev * u
+        prev = u
+    fl["dense_fwd"] = dense
+    fl["dense_bwd"] = dense
+    return fl
+
+
+def tail_bytes_per_image(elem_size):
+    h, w = INPUT_SHAPE[0] // 2, INPUT_SHAPE[1] // 2      # last conv map 128x128x64
+    k = CONV_LAYERS[-1][0]
+    return 2.0 * k * h * w * elem_size + INPUT_SHAPE[0] * INPUT_SHAPE[1] * 4.0
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def oracle_setup():
+    from oracle import cnn as ocnn
+    cfg = ocnn.NetConfig.torch_flavour(INPUT_SHAPE, NUM_CLASSES, CONV_LAYERS, HIDDEN, 0.01)
+    params = ocnn.init_params(cfg, seed=7, bias_std=0.0)      # reference initialisers, seeded
+    return ocnn, cfg, params
+
+
+def cpu_reference_rate(n_images, batch=32, repeats=1):
+    """The reference's CPU path (oracle port of ADCNNM + autograd Grad-CAM + NumPy tail) on the host cores."""
+    import torch
+    from oracle import cpu_port
+    _, cfg, params = oracle_setup()
+    rate, secs = cpu_port.time_predict_gradcam(cfg, params, n_images, batch=batch, repeats=repeats)
+    return rate, secs, torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference is
+    Python and cannot travel to the GPU box).  Rank 0 alone runs and prints."""
+    if rank != 0:
+        return
+    import torch
+    n_per_step = args.ref_images
+    _, cfg, params = oracle_setup()
+    from oracle import cpu_port
+    from oracle import cnn as ocnn
+    model = cpu_port.build(cfg, params)
+    x = torch.from_numpy(ocnn.synth_images(n_per_step, INPUT_SHAPE, seed=20251018))
+
+    def step():
+        for s in range(0, n_per_step, 32):
+            cpu_port.predict_gradcam(model, x[s:s + 32])
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = n_per_step * args.steps / dt
+    sample = f"{n_per_step} synthetic 256x256x1 images per step in batches of 32 (bounded sample of the batch-512 workload)"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.batch, "cpu"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(batch, precision):
+    return {"workload": f"cfg2: ADCNNM-flavour CNN (conv 32,64 k3 pad1; fc 256,128; {NUM_CLASSES} classes; random init) "
+                        f"predict+Grad-CAM(last conv, predicted class), 256x256x1 fp32 NHWC, batch {batch} per GPU",
+            "batch_per_gpu": batch, "precision_path": precision,
+            "l2_policy": "inputs + activations per step (>= 134 MB input, GBs of activations) exceed the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import bcad_b200
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ocnn, cfg, params = oracle_setup()
+    B = args.batch
+    spec = bcad_b200.NetSpec.torch_flavour(INPUT_SHAPE, NUM_CLASSES, CONV_LAYERS, HIDDEN, 0.01)
+    precision = args.precision
+    eng = None
+    if precision in ("auto", "bf16"):
+        try:
+            eng = bcad_b200.Engine(spec, precision="bf16", max_batch=B, device=local_rank)
+            precision = "bf16"
+        except ValueError as e:
+            if args.precision == "bf16":
+                raise
+            log(f"[bench] bf16 tensor path unavailable ({e}); using the fp32 CUDA-core path")
+    if eng is None:
+        eng = bcad_b200.Engine(spec, precision="fp32", max_batch=B, device=local_rank)
+        precision = "fp32"
+    eng.set_weights(params.conv_w, params.conv_b, params.dense_w, params.dense_b)
+
+    # synthetic inputs: distinct per rank (seed + rank); generated once, resident in HBM for `value`
+    n_unique = min(B, 64)
+    base = ocnn.synth_images(n_unique, INPUT_SHAPE, seed=20251018 + rank)
+    reps = (B + n_unique - 1) // n_unique
+    x_host = torch.from_numpy(np.concatenate([base] * reps, axis=0)[:B].copy()).pin_memory()
+    x_dev = x_host.to(dev)
+    heat_dev = torch.empty((B, INPUT_SHAPE[0], INPUT_SHAPE[1]), device=dev, dtype=torch.float32)
+    heat_host = torch.empty((B, INPUT_SHAPE[0], INPUT_SHAPE[1]), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_dev():
+        return eng.predict_explain(x_dev, None, "logit", out_heat=heat_dev)
+
+    def step_host():
+        return eng.predict_explain_host(x_host.numpy(), None, "logit", heat_out=heat_host.numpy())
+
+    # ---- device-resident throughput (value)
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step_dev()
+    ev1.record()
+    barrier()
+    launches = eng.launch_count - l0
+    ms_total = ev0.elapsed_time(ev1)
+    # ---- end to end through the host-buffer C-ABI call (e2e)
+    for _ in range(max(1, min(args.warmup, 3))):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    tt = torch.tensor([ms_total, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(tt[0]), float(tt[1])
+
+    # ---- per-kernel device times (CUDA events before every kernel, separate profiled steps)
+    eng.set_profiling(True)
+    prof = {}
+    nprof = 3
+    for _ in range(nprof):
+        step_dev()
+        torch.cuda.synchronize(dev)
+        for i, (name, ms) in enumerate(eng.last_profile()):
+            key = f"{i:02d}:{name}"
+            prof[key] = prof.get(key, 0.0) + ms / nprof
+    eng.set_profiling(False)
+
+    if rank != 0:
+        return
+    # ---- sanity of the result against the oracle on a few images (not timed)
+    cls, probs, logits, heat = out
+    pk = peaks()
+    fl = algorithmic_flops_per_image()
+    step_ms = ms_total / args.steps
+    value = world * B * args.steps / (ms_total * 1e-3)
+    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+    kernels = []
+    for key, ms in sorted(prof.items()):
+        kernels.append({"kernel": key, "ms": round(ms, 4), "share": round(ms / max(1e-9, sum(prof.values())), 4)})
+    # dominant kernel -> roofline
+    dom_key = max(prof, key=prof.get)
+    dom_ms = prof[dom_key]
+    roof = None
+    name = dom_key.split(":", 1)[1]
+    if name.startswith("conv"):
+        # conv kernels: conv0 = first block, conv1 = second block ...
+        li = 0 if "conv0" in name else 1
+        flops = fl[f"conv{li}"] * B
+        peak = pk["bf16_tflops_sustained"]
+        ach = flops / (dom_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "traffic": None, "peak_source": pk["source"] + " (sustained bf16 cuBLAS)",
+                "algorithmic_flops_per_launch": flops}
+    elif "sgemm" in name or "fc" in name:
+        flops = 2.0 * (INPUT_SHAPE[0] // 4) * (INPUT_SHAPE[1] // 4) * CONV_LAYERS[-1][0] * HIDDEN[0] * B
+        peak = pk["bf16_tflops_sustained"]
+        ach = flops / (dom_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "traffic": None, "peak_source": pk["source"] + " (sustained bf16 cuBLAS)",
+                "algorithmic_flops_per_launch": flops}
+    else:
+        esz = 2 if precision == "bf16" else 4
+        nbytes = tail_bytes_per_image(esz) * B
+        ach = nbytes / (dom_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                "algorithmic_bytes_per_launch": nbytes}
+    # Grad-CAM tail roofline (always reported beside the dominant kernel)
+    tail_ms = sum(ms for k, ms in prof.items() if k.split(":", 1)[1] in ("cam", "upsample_norm", "alpha_from_pool_grad", "tail_fused"))
+    esz = 2 if precision == "bf16" else 4
+    tail_bytes = tail_bytes_per_image(esz) * B
+    tail_roof = {"bound": "hbm", "kernels": "Grad-CAM tail (alpha, cam, upsample+min-max)", "ms": tail_ms,
+                 "achieved": tail_bytes / max(1e-9, tail_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                 "frac": tail_bytes / max(1e-9, tail_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                 "algorithmic_bytes_per_launch": tail_bytes,
+                 "note": "dense definition (read A, read dA, write fp32 map); this path derives alpha from the pooled "
+                         "gradient and never materialises dA"}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        rate, secs, cores = cpu_reference_rate(args.cpu_images)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_images} of the workload's synthetic 256x256x1 images in batches of 32 "
+                         f"({secs:.1f} s), oracle port of ADCNNM + autograd Grad-CAM + NumPy tail"}
+    out_json = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+        "config": workload_config(B, precision),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
+                "d2h_bytes_per_step": int(heat_host.numel() * 4 + B * (2 * NUM_CLASSES * 4 + 4)),
+                "ms_per_step": e2e_ms / args.steps, "api": "bcad_predict_explain_host (pinned host buffers)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "roofline_tail": tail_roof,
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+        "tensor_path": bool(eng.uses_tensor_path),
+    }
+    print(json.dumps(out_json), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=512, help="images per GPU per step")
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--cpu-images", type=int, default=96, help="bounded CPU-baseline sample")
+    ap.add_argument("--ref-images", type=int, default=64, help="images per step of the --impl reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        import torch
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    elif args.gpus > 1:
+        log(f"[bench] --gpus {args.gpus} without torchrun: launch with torch.distributed.run; running 1 rank")
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

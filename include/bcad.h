@@ -1,0 +1,166 @@
+/*
+ * libbcad -- B200-native predict + Grad-CAM for the vision-xai-breast-cancer-cad hot path.
+ *
+ * Plain C ABI: opaque handle, plain pointers and sizes, int status codes (0 = ok, <0 = error,
+ * text via bcad_last_error()).  No torch types.  Device pointers are owned by the caller; the
+ * handle owns only weights and workspace.  Every entry point is re-entrant per (handle, stream).
+ *
+ * The reference has NO FFI/plugin seam: its boundary is plain Python classes
+ * and functions.  Each entry point below cites the reference Python interface it stands behind;
+ * the ctypes binding a maintainer adds is shown in INTEGRATION.md and implemented in
+ * vision-xai-breast-cancer-cad_b200/_lib.py.
+ */
+#ifndef BCAD_H
+#define BCAD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BCAD_MAX_CONV 8
+#define BCAD_MAX_DENSE 8
+
+/* status codes */
+#define BCAD_OK 0
+#define BCAD_ERR_INVALID (-1)      /* bad argument / shape / unsupported configuration (-> ValueError) */
+#define BCAD_ERR_CUDA (-2)         /* CUDA runtime error (-> RuntimeError) */
+#define BCAD_ERR_STATE (-3)        /* call order (weights not committed, no cached forward, ...) */
+#define BCAD_ERR_NOMEM (-4)
+
+/* cfg.flatten_order: how the CALLER's first dense weight matrix indexes the flattened pool output */
+#define BCAD_FLATTEN_HWC 0         /* out.flatten() of an (h,w,C) array: Classes/CNNModel.py:178 */
+#define BCAD_FLATTEN_CHW 1         /* x.reshape(B,-1) of NCHW:            ADCNNM.py:77 */
+/* cfg.pool_ties: max-pool backward when several window elements equal the maximum */
+#define BCAD_TIES_ALL 0            /* gradient duplicated to every tie: Classes/CNNModel.py:260,274-275 */
+#define BCAD_TIES_FIRST 1          /* first maximum in row-major window order: nn.MaxPool2d (ADCNNM.py:49) */
+/* cfg.head */
+#define BCAD_HEAD_SOFTMAX_CLIP 0   /* probs = softmax(clip(z,+-50)) /(sum+1e-12): Classes/CNNModel.py:203-212 */
+#define BCAD_HEAD_LOGITS 1         /* raw logits out, probs = softmax(logits): ADCNNM.py:78, app.py:593 */
+/* cfg.precision */
+#define BCAD_PREC_FP32 0           /* fp32 CUDA-core path, any shape */
+#define BCAD_PREC_BF16 1           /* bf16 tcgen05 tensor-core path (fp32 accumulate) where the shape allows */
+/* grad_mode: gradient injected at the network output for the explanation */
+#define BCAD_GRAD_LOGIT 0          /* d(logit_c): pytorch_grad_cam ClassifierOutputTarget, GRADCAM.py:64 */
+#define BCAD_GRAD_SOFTMAX_CE 1     /* probs - onehot(c): explainability.py:21-22 */
+/* bcad_get_tensor kinds (cached by the most recent forward of <= max_batch images) */
+#define BCAD_T_CONV_OUT 0          /* layer['output'] of conv block i, NHWC fp32 (Classes/CNNModel.py:169) */
+#define BCAD_T_POOL_OUT 1          /* layer['output'] of pool block i, NHWC fp32 (:174) */
+#define BCAD_T_DENSE_Z 2           /* layer['z'] of dense/output layer j (:181,194) */
+#define BCAD_T_ALPHA 3             /* Grad-CAM channel weights alpha_k of the last explain call, [B,F] */
+#define BCAD_T_CAM_LOWRES 4        /* ReLU(sum_k alpha_k A_k) before normalisation, [B,h,w] */
+
+#if defined(__GNUC__)
+#define BCAD_API __attribute__((visibility("default")))
+#else
+#define BCAD_API
+#endif
+
+typedef struct bcad_model bcad_model;
+
+typedef struct bcad_config {
+    int32_t in_h, in_w, in_c;               /* input_shape (H,W,C): Classes/CNNModel.py:68, ADCNNM.py:42 */
+    int32_t num_classes;
+    int32_t n_conv;
+    int32_t conv_filters[BCAD_MAX_CONV];    /* conv_layers[i][0] */
+    int32_t conv_ksize[BCAD_MAX_CONV];      /* conv_layers[i][1] */
+    int32_t n_hidden;
+    int32_t hidden_units[BCAD_MAX_DENSE];
+    float alpha_conv;                       /* LeakyReLU slope after convs (ADCNNM.py:76 hard-wires 0.01) */
+    float alpha_dense;                      /* LeakyReLU slope after hidden dense layers */
+    int32_t pad;                            /* zero padding per side: 0 (NumPy CNN) or 1 (ADCNNM.py:48) */
+    int32_t flatten_order;
+    int32_t pool_ties;
+    int32_t head;
+    int32_t precision;
+    int32_t max_batch;                      /* workspace is sized for this many images; larger calls are chunked */
+    int32_t keep_all_activations;           /* 1: also cache every conv block's pre-pool output (compat .layers, saliency) */
+    int32_t device;                         /* CUDA device ordinal */
+} bcad_config;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+/* CNNModel.__init__/_build_model (Classes/CNNModel.py:68-157), ADCNNM.CNNModel.__init__ (ADCNNM.py:35-70) */
+BCAD_API int bcad_create(const bcad_config* cfg, bcad_model** out);
+BCAD_API void bcad_destroy(bcad_model* m);
+/* thread-local message of the last failing call */
+BCAD_API const char* bcad_last_error(void);
+BCAD_API const char* bcad_version(void);
+
+/* ---- weights: load_weights (Classes/CNNModel.py:30-60), load_trained_model (ADCNNM.py:155-202) */
+/* filters: HOST fp32 (F,k,k,C) -- the NumPy layout (Classes/CNNModel.py:94); bias: HOST fp32 (F,) */
+BCAD_API int bcad_set_conv_weights(bcad_model* m, int conv_idx, const float* filters_fkkc, const float* bias);
+/* W: HOST fp32 (units,in); for dense_idx 0 the `in` index follows cfg.flatten_order; bias (units,).
+ * dense_idx runs over the hidden layers then the output layer (n_hidden + 1 matrices). */
+BCAD_API int bcad_set_dense_weights(bcad_model* m, int dense_idx, const float* w_units_in, const float* bias);
+/* optional inference-time BatchNorm fold (identity for reference models, README.md:87-93):
+ * w' = w*gamma/sqrt(var+eps), b' = (b-mean)*gamma/sqrt(var+eps)+beta, applied to the staged conv. */
+BCAD_API int bcad_fold_batchnorm(bcad_model* m, int conv_idx, const float* gamma, const float* beta,
+                        const float* mean, const float* var, float eps);
+/* packs / uploads everything staged so far; required before the first predict */
+BCAD_API int bcad_commit(bcad_model* m);
+
+/* ---- the hot path, DEVICE buffers ------------------------------------------------------------- */
+/* forward(x, training=False) + predict (Classes/CNNModel.py:162-198, 524-526); model(inputs) +
+ * torch.max + torch.softmax (ADCNNM.py:72-78, app.py:584-593).
+ * x_dev: fp32 NHWC [B,H,W,C].  Outputs (each may be NULL): logits/probs [B,num_classes] fp32,
+ * cls [B] int32 (first maximum).  stream: cudaStream_t (NULL = legacy default stream). */
+BCAD_API int bcad_predict(bcad_model* m, const float* x_dev, int B, float* logits_dev, float* probs_dev,
+                 int32_t* cls_dev, void* stream);
+
+/* predict + Grad-CAM on the last conv block's post-LeakyReLU output
+ * (generate_dual_class_gradcam_overlays_pytorch GRADCAM.py:31-81 with the tail of pytorch_grad_cam;
+ * ExplainableAI.generate_heatmap Classes/ExplainableAI.py:14).
+ * class_idx_dev: int32 [B] target classes or NULL = each image's predicted class (GRADCAM.py:60-61).
+ * heatmap_dev: fp32 [B,H,W] in [0,1]. */
+BCAD_API int bcad_predict_explain(bcad_model* m, const float* x_dev, int B, const int32_t* class_idx_dev,
+                         int grad_mode, float* logits_dev, float* probs_dev, int32_t* cls_dev,
+                         float* heatmap_dev, void* stream);
+
+/* compute_backprops_for_explainability (explainability.py:13-68), activation-gradient part:
+ * uses the activations cached by the preceding bcad_predict of the SAME B (<= max_batch,
+ * keep_all_activations=1 when gradients below the last conv block are wanted).
+ * conv_act_grads_dev[i]: fp32 NHWC gradient w.r.t. conv block i's post-activation output, or NULL to
+ * skip (entries below the lowest requested block are not computed); d_input_dev: fp32 [B,H,W,C] or NULL. */
+BCAD_API int bcad_explain_backward(bcad_model* m, int B, const int32_t* class_idx_dev, int grad_mode,
+                          float* const* conv_act_grads_dev, float* d_input_dev, void* stream);
+
+/* cached tensors of the most recent forward / explain (layer['output'], ['z'] ... compat) -> dst_dev */
+BCAD_API int bcad_get_tensor(bcad_model* m, int kind, int index, int B, float* dst_dev, void* stream);
+/* number of fp32 elements per image of that tensor */
+BCAD_API int64_t bcad_tensor_elems(bcad_model* m, int kind, int index);
+
+/* ---- the hot path, HOST buffers (the end-to-end call: H2D, compute, D2H, chunked and overlapped) */
+/* x_host: fp32 [B,H,W,C]; outputs host (NULL to skip); pinned memory makes the copies asynchronous. */
+BCAD_API int bcad_predict_explain_host(bcad_model* m, const float* x_host, int B, const int32_t* class_idx_host,
+                              int grad_mode, float* logits_host, float* probs_host, int32_t* cls_host,
+                              float* heatmap_host);
+
+/* ---- stand-alone Grad-CAM tail (pytorch_grad_cam BaseCAM.forward / scale_cam_image) ------------ */
+/* A, dA: [B,h,w,K] NHWC device, dtype 0 = fp32, 1 = bf16; out: fp32 [B,H,W].
+ * alpha_k = mean_hw dA_k ; cam = ReLU(sum_k alpha_k A_k) ; min-max ; bilinear (cv2.resize) ; min-max. */
+BCAD_API int bcad_gradcam_tail(const void* A_dev, const void* dA_dev, int B, int K, int h, int w, int H, int W,
+                      int dtype, float* out_dev, void* stream);
+
+/* ---- overlay stage (show_cam_on_image GRADCAM.py:67, heatmap_uint8 GRADCAM.py:70) -------------- */
+/* img01_dev: fp32 [B,H,W] grayscale in [0,1]; cam_dev: fp32 [B,H,W]; overlay_rgb_dev: u8 [B,H,W,3]
+ * (NULL to skip); heat_u8_dev: u8 [B,H,W] (NULL to skip). */
+BCAD_API int bcad_overlay(const float* img01_dev, const float* cam_dev, int B, int H, int W,
+                 uint8_t* overlay_rgb_dev, uint8_t* heat_u8_dev, void* stream);
+
+/* ---- introspection ---------------------------------------------------------------------------- */
+/* kernels launched by this handle since creation (bench.py reports the delta as gpu_launches) */
+BCAD_API int64_t bcad_launch_count(bcad_model* m);
+/* 1 when the handle runs the tcgen05 fast path for its conv/fc stack, 0 when it runs fp32 CUDA cores */
+BCAD_API int bcad_uses_tensor_path(bcad_model* m);
+/* per-kernel device times of the last DEVICE-buffer call: with bcad_set_profiling(m,1) a CUDA event is
+ * recorded on the call's stream before every kernel (and one at the end); interval i is kernel i.
+ * Off by default (the timed bench region runs with it off). */
+BCAD_API int bcad_set_profiling(bcad_model* m, int on);
+BCAD_API int bcad_profile_count(bcad_model* m);
+BCAD_API int bcad_profile_get(bcad_model* m, int i, char* name_buf, int name_cap, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BCAD_H */

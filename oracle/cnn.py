@@ -255,7 +255,7 @@ def top_gradient(cache: Cache, class_idx, mode: str) -> torch.Tensor:
     if mode == "logit":
         return onehot
     if mode == "softmax_ce":
-        return softmax_clip(cache.logits).to(cache.logits.dtype) - onehot
+        return cache.probs.to(cache.logits.dtype) - onehot     # the model's own probabilities (per head)
     raise ValueError(mode)
 
 

@@ -157,3 +157,16 @@ def test_oracle_against_live_reference():
     c, pr, _ = ocnn.predict(cfg, p, x)
     assert int(c[0]) == int(cls)
     np.testing.assert_allclose(pr[0], probs, rtol=0, atol=1e-12)
+
+
+def test_cpu_port_matches_reference_fixture():
+    """oracle.cpu_port (the timed CPU baseline) reproduces the reference ADCNNM logits and gradients."""
+    from oracle import cpu_port
+    g, cfg, p = _torch_case("ref_torch_small")
+    model = cpu_port.build(cfg, p)
+    x = torch.from_numpy(g["x"])
+    cls, logits, heat = cpu_port.predict_gradcam(model, x, class_idx=[0, 0, 0])
+    np.testing.assert_allclose(logits, g["logits"], rtol=0, atol=1e-6)
+    assert np.array_equal(cls, g["pred_class"])
+    want = ogc.gradcam_tail(g["A_last"], g["dA1_logit_c0"], (16, 16))
+    np.testing.assert_allclose(heat, want, rtol=0, atol=2e-6)

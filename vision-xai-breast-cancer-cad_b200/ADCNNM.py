@@ -1,0 +1,113 @@
+"""Drop-in for ``WebApplicationPrototype/ADCNNM.py``: the PyTorch CNN.
+
+``CNNModel`` keeps the reference's constructor, parameter names (``convs.{i}.weight/bias``,
+``fc.{0,3,6..}.weight/bias`` -- so ``load_state_dict(torch.load(...))`` of a reference checkpoint works),
+``forward(x[B,H,W,C]) -> logits`` (ADCNNM.py:72-78) and ``load_trained_model`` (ADCNNM.py:155-202).
+The modules only HOLD the parameters; ``forward`` runs in libbcad (Conv2d(padding=1) + leaky_relu(0.01) +
+MaxPool2d(2), CHW flatten handled by permuting fc1's columns at load time, Linear + LeakyReLU(alpha)).
+Inference only: the returned logits carry no autograd graph (training is SURVEY 8 row f4).
+"""
+from __future__ import annotations
+
+import json
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .engine import Engine, NetSpec
+
+
+class CNNModel(nn.Module):
+    def __init__(self, input_shape, num_classes, conv_layers=[(32, 3), (64, 3)], hidden_units=[256, 128],
+                 dropout_rate=0.3, leaky_alpha=0.01, *, precision="fp32", max_batch=64, device_index=0):
+        super().__init__()
+        H, W, C = input_shape                      # ADCNNM.py:42
+        self._spec = NetSpec.torch_flavour((H, W, C), num_classes, conv_layers, hidden_units, leaky_alpha)
+        self.convs = nn.ModuleList()
+        self.pools = nn.ModuleList()
+        in_channels = C
+        for out_channels, ksize in conv_layers:
+            self.convs.append(nn.Conv2d(in_channels, out_channels, ksize, padding=1))   # ADCNNM.py:48
+            self.pools.append(nn.MaxPool2d(2))
+            in_channels = out_channels
+        _, flatten_size = self._spec.shapes()
+        layers = []
+        in_units = flatten_size
+        for units in hidden_units:
+            layers += [nn.Linear(in_units, units), nn.LeakyReLU(leaky_alpha), nn.Dropout(dropout_rate)]
+            in_units = units
+        layers.append(nn.Linear(in_units, num_classes))
+        self.fc = nn.Sequential(*layers)
+        self._precision, self._max_batch, self._device_index = precision, max_batch, device_index
+        self._engine = None
+        self._versions = None
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _param_versions(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def sync_weights(self, force=True):
+        ver = self._param_versions()
+        if self._engine is None:
+            self._engine = Engine(self._spec, precision=self._precision, max_batch=self._max_batch,
+                                  device=self._device_index)
+            force = True
+        if force or ver != self._versions:
+            conv_w = [c.weight.detach().cpu().numpy().transpose(0, 2, 3, 1) for c in self.convs]   # (F,C,k,k)->(F,k,k,C)
+            conv_b = [c.bias.detach().cpu().numpy() for c in self.convs]
+            lin = [m for m in self.fc if isinstance(m, nn.Linear)]
+            self._engine.set_weights(conv_w, conv_b, [l.weight.detach().cpu().numpy() for l in lin],
+                                     [l.bias.detach().cpu().numpy() for l in lin])
+            self._versions = ver
+        return self._engine
+
+    @property
+    def engine(self) -> Engine:
+        return self.sync_weights(force=False)
+
+    # ------------------------------------------------------------------ forward (ADCNNM.py:72-78)
+    def forward(self, x):
+        if self.training and any(isinstance(m, nn.Dropout) and m.p > 0 for m in self.fc):
+            raise NotImplementedError("train-mode forward (dropout, autograd) is SURVEY 8 row f4; call .eval() first")
+        cls, probs, logits = self.engine.predict(x)
+        return logits.to(x.device) if isinstance(x, torch.Tensor) else logits
+
+    # ------------------------------------------------------------------ batched entry points (new)
+    def predict_batch(self, x):
+        """-> (classes int64 [B], probs [B,nc]) -- torch.max / torch.softmax of app.py:589-593."""
+        cls, probs, _ = self.engine.predict(x)
+        return cls.long(), probs
+
+    def predict_explain_batch(self, x, class_idx=None, grad_mode="logit"):
+        """-> (classes [B], logits [B,nc], Grad-CAM heatmaps fp32 [B,H,W]) on the GPU."""
+        cls, probs, logits, heat = self.engine.predict_explain(x, class_idx, grad_mode)
+        return cls.long(), logits, heat
+
+
+def train_model(*a, **k):
+    raise NotImplementedError("train_model (ADCNNM.py:86-153) is SURVEY 8 row f4, not part of this hot path")
+
+
+def load_trained_model(json_path, weight_path, **engine_kw):
+    """ADCNNM.py:155-202: JSON config + ``.pth`` state_dict -> eval-mode model (same exceptions)."""
+    with open(json_path, "r") as f:
+        config = json.load(f)
+    input_shape = tuple(config["dataset"]["input_shape"])
+    num_classes = config["dataset"]["num_classes"]
+    conv_layers = [tuple(layer) for layer in config["model"]["conv_layers"]]
+    hidden_units = config["model"]["hidden_units"]
+    dropout_rate = config["model"]["dropout_rate"]
+    model = CNNModel(input_shape=input_shape, num_classes=num_classes, conv_layers=conv_layers,
+                     hidden_units=hidden_units, dropout_rate=dropout_rate, **engine_kw)
+    try:
+        state_dict = torch.load(weight_path, map_location="cpu")
+        model.load_state_dict(state_dict)
+        model.eval()
+        model.sync_weights()
+        print(f" Model loaded successfully from '{weight_path}' on device: cuda")
+    except FileNotFoundError:
+        raise FileNotFoundError(f" Could not find weight file at '{weight_path}'")
+    except Exception as e:
+        raise RuntimeError(f" Failed to load model weights: {e}")
+    return model

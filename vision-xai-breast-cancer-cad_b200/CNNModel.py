@@ -1,0 +1,250 @@
+"""Drop-in for ``Classes/CNNModel.py`` (== WebApplicationPrototype/CNNModel.py, CNNM.py): the NumPy CNN.
+
+Same constructor, ``layers`` list-of-dicts, ``forward`` / ``predict`` / ``load_weights`` /
+``save_model`` as the reference (Classes/CNNModel.py:30-60, 67-198, 524-555) -- but ``forward`` runs
+on the GPU through libbcad instead of Python loops.  None of the reference's import-time side effects
+(stdout hijack :28, log file :10, Windows-path weight load :587) are reproduced.
+
+Added batched entry points the reference only hints at (``Classes/Model.py:43 predict_batch``):
+``predict_batch(X)`` and ``predict_explain_batch(X, class_idx=None)``.
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import Engine, NetSpec
+
+
+class _Lazy:
+    __slots__ = ("fn",)
+
+    def __init__(self, fn):
+        self.fn = fn
+
+
+class _Layer(dict):
+    """layer dict whose cached activations are fetched from the device on first access."""
+
+    def __getitem__(self, key):
+        v = dict.__getitem__(self, key)
+        if isinstance(v, _Lazy):
+            v = v.fn()
+            dict.__setitem__(self, key, v)
+        return v
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+
+def load_weights(cls, path="trained_model/cnn_model.npz"):
+    """Classes/CNNModel.py:30-60: ``.npz`` with a JSON ``config`` and ``W{i}``/``b{i}`` keyed by layer index."""
+    data = np.load(path, allow_pickle=True)
+    config = json.loads(str(data["config"]))
+    model = cls(
+        input_shape=tuple(config["input_shape"]),
+        num_classes=config["num_classes"],
+        conv_layers=config["conv_layers"],
+        hidden_units=config["hidden_units"],
+        dropout_rate=config["dropout_rate"],
+        leaky_alpha=config.get("leaky_alpha", 0.01),
+    )
+    for i, layer in enumerate(model.layers):
+        if layer["type"] == "conv":
+            layer["filters"] = data[f"W{i}"]
+            layer["biases"] = data[f"b{i}"]
+        elif layer["type"] in ["dense", "output"]:
+            layer["weights"] = data[f"W{i}"]
+            layer["biases"] = data[f"b{i}"]
+    print(f"[INFO] Model loaded from {path}")
+    return model
+
+
+class CNNModel:
+    def __init__(self, input_shape, num_classes, conv_layers=[(8, 3), (16, 3)], hidden_units=[128, 64],
+                 dropout_rate=0.3, leaky_alpha=0.01, *, precision="fp32", max_batch=32, device=0,
+                 keep_all_activations=True):
+        self.input_shape = input_shape
+        self.num_classes = num_classes
+        self.conv_layers_config = conv_layers
+        self.hidden_units = hidden_units
+        self.dropout_rate = dropout_rate
+        self.leaky_alpha = leaky_alpha
+        self.layers = []
+        self.epoch_accuracy = []
+        self._precision, self._max_batch, self._device = precision, max_batch, device
+        self._keep_all = keep_all_activations
+        self._engine = None
+        self._weights_key = None
+        self._build_model()
+
+    # ------------------------------------------------------------------ build (Classes/CNNModel.py:88-157)
+    def _build_model(self):
+        in_shape = tuple(self.input_shape)
+        for num_filters, ksize in self.conv_layers_config:
+            filters = np.random.randn(num_filters, ksize, ksize, in_shape[2]) * np.sqrt(2.0 / (ksize * ksize * in_shape[2]))
+            out_h, out_w = in_shape[0] - ksize + 1, in_shape[1] - ksize + 1
+            self.layers.append(_Layer({
+                "type": "conv", "filters": filters, "biases": np.zeros(num_filters),
+                "input_shape": in_shape, "output_shape": (out_h, out_w, num_filters),
+                "ksize": ksize, "num_filters": num_filters, "input": None, "output": None}))
+            in_shape = (out_h, out_w, num_filters)
+            pool_h, pool_w = in_shape[0] // 2, in_shape[1] // 2
+            self.layers.append(_Layer({
+                "type": "pool", "input_shape": in_shape, "output_shape": (pool_h, pool_w, in_shape[2]),
+                "input": None, "output": None, "switches": None}))
+            in_shape = (pool_h, pool_w, in_shape[2])
+        prev_units = int(np.prod(in_shape))
+        for units in self.hidden_units:
+            limit = np.sqrt(6.0 / (prev_units + units))
+            self.layers.append(_Layer({
+                "type": "dense", "weights": np.random.uniform(-limit, limit, (units, prev_units)),
+                "biases": np.zeros(units), "input_shape": (prev_units,), "input": None, "z": None,
+                "output_shape": (units,)}))
+            prev_units = units
+        limit = np.sqrt(6.0 / (prev_units + self.num_classes))
+        self.layers.append(_Layer({
+            "type": "output", "weights": np.random.uniform(-limit, limit, (self.num_classes, prev_units)),
+            "biases": np.zeros(self.num_classes), "input_shape": (prev_units,), "input": None, "z": None,
+            "output_shape": (self.num_classes,)}))
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _spec(self) -> NetSpec:
+        return NetSpec.numpy_flavour(self.input_shape, self.num_classes, self.conv_layers_config,
+                                     self.hidden_units, self.leaky_alpha)
+
+    def _conv_layers(self):
+        return [l for l in self.layers if l["type"] == "conv"]
+
+    def _dense_layers(self):
+        return [l for l in self.layers if l["type"] in ("dense", "output")]
+
+    def sync_weights(self, force=True):
+        """Upload ``layers[*]['filters'|'weights'|'biases']`` to the device.  Called automatically when a
+        weight array OBJECT is replaced (as ``load_weights`` does); call it yourself after in-place edits."""
+        convs, denses = self._conv_layers(), self._dense_layers()
+        key = tuple(id(dict.__getitem__(l, k)) for l in convs for k in ("filters", "biases")) + \
+            tuple(id(dict.__getitem__(l, k)) for l in denses for k in ("weights", "biases"))
+        if self._engine is None:
+            self._engine = Engine(self._spec(), precision=self._precision, max_batch=self._max_batch,
+                                  keep_all_activations=self._keep_all, device=self._device)
+            force = True
+        if force or key != self._weights_key:
+            self._engine.set_weights([l["filters"] for l in convs], [l["biases"] for l in convs],
+                                     [l["weights"] for l in denses], [l["biases"] for l in denses])
+            self._weights_key = key
+        return self._engine
+
+    @property
+    def engine(self) -> Engine:
+        return self.sync_weights(force=False)
+
+    # ------------------------------------------------------------------ forward / predict
+    def forward(self, x, training=True):
+        """Classes/CNNModel.py:162-198 (single sample (H,W,C) -> probs (num_classes,) float64).
+
+        Caches ``layer['input'|'output'|'switches'|'z']`` like the reference (fetched lazily from the device).
+        Training-mode dropout (:186-188) belongs to the training step, which is outside this hot path."""
+        if training and self.dropout_rate > 0.0:
+            raise NotImplementedError(
+                "forward(training=True) with dropout is the training step (SURVEY 8 f4), not built here; "
+                "call forward(x, training=False) / predict(x)")
+        x = np.asarray(x)
+        eng = self.engine
+        cls, probs, logits = eng.predict(x[None].astype(np.float32))
+        self._fill_caches(x)
+        self._last_logits = logits
+        return probs[0].double().cpu().numpy()
+
+    def _fill_caches(self, x):
+        eng = self._engine
+        ci = di = 0
+        prev_key = None
+        for idx, layer in enumerate(self.layers):
+            t = layer["type"]
+            if t == "conv":
+                layer["input"] = x if ci == 0 else _Lazy(self._getter(_lib.T_POOL_OUT, ci - 1, self.layers[idx - 1]["output_shape"]))
+                layer["output"] = _Lazy(self._getter(_lib.T_CONV_OUT, ci, layer["output_shape"]))
+            elif t == "pool":
+                layer["input"] = _Lazy(self._getter(_lib.T_CONV_OUT, ci, layer["input_shape"]))
+                layer["output"] = _Lazy(self._getter(_lib.T_POOL_OUT, ci, layer["output_shape"]))
+                layer["switches"] = _Lazy(self._switch_getter(idx))
+                ci += 1
+            else:
+                layer["z"] = _Lazy(self._getter(_lib.T_DENSE_Z, di, layer["output_shape"]))
+                layer["input"] = _Lazy(self._dense_input_getter(idx, di))
+                di += 1
+
+    def _getter(self, kind, index, shape):
+        eng = self._engine
+        return lambda: eng.get_tensor(kind, index, 1)[0].double().cpu().numpy().reshape(shape)
+
+    def _switch_getter(self, idx):
+        def fn():                                              # Classes/CNNModel.py:260 (every tie marked)
+            x, p = self.layers[idx]["input"], self.layers[idx]["output"]
+            h2, w2 = p.shape[0], p.shape[1]
+            sw = np.zeros_like(x, dtype=bool)
+            up = np.repeat(np.repeat(p, 2, axis=0), 2, axis=1)
+            sw[:2 * h2, :2 * w2] = x[:2 * h2, :2 * w2] == up
+            return sw
+        return fn
+
+    def _dense_input_getter(self, idx, di):
+        def fn():                                              # flat.copy() (Classes/CNNModel.py:179,192)
+            prev = self.layers[idx - 1]
+            if prev["type"] == "pool":
+                return prev["output"].flatten()
+            z = prev["z"]
+            return np.where(z > 0, z, self.leaky_alpha * z)
+        return fn
+
+    def _softmax(self, z):
+        """Classes/CNNModel.py:203-212 (host helper kept for explainability-style callers)."""
+        z = np.array(z, dtype=np.float64)
+        z = np.clip(z, -50.0, 50.0)
+        z = z - np.max(z)
+        exps = np.exp(z)
+        s = np.sum(exps)
+        if s == 0:
+            return np.ones_like(z) / len(z)
+        return exps / (s + 1e-12)
+
+    def predict(self, X):
+        """Classes/CNNModel.py:524-526: (argmax, probs)."""
+        probs = self.forward(X, training=False)
+        return np.argmax(probs), probs
+
+    # ------------------------------------------------------------------ batched entry points (new)
+    def predict_batch(self, X):
+        """X [B,H,W,C] -> (classes int64 [B], probs float32 [B,nc])."""
+        cls, probs, _ = self.engine.predict(np.asarray(X, dtype=np.float32))
+        return cls.cpu().numpy().astype(np.int64), probs.cpu().numpy()
+
+    def predict_explain_batch(self, X, class_idx=None, grad_mode="softmax_ce"):
+        """X [B,H,W,C] -> (classes [B], probs [B,nc], Grad-CAM heatmaps float32 [B,H,W] in [0,1])."""
+        cls, probs, _, heat = self.engine.predict_explain_host(np.asarray(X, dtype=np.float32), class_idx, grad_mode)
+        return cls.astype(np.int64), probs, heat
+
+    # ------------------------------------------------------------------ persistence (Classes/CNNModel.py:530-555)
+    def save_model(self, path="trained_model/cnn_model.npz"):
+        d = os.path.dirname(path)
+        if d:
+            os.makedirs(d, exist_ok=True)
+        config = {"input_shape": list(self.input_shape), "num_classes": self.num_classes,
+                  "conv_layers": [list(c) for c in self.conv_layers_config], "hidden_units": list(self.hidden_units),
+                  "dropout_rate": self.dropout_rate, "leaky_alpha": self.leaky_alpha}
+        weights = {}
+        for i, layer in enumerate(self.layers):
+            if layer["type"] == "conv":
+                weights[f"W{i}"], weights[f"b{i}"] = layer["filters"], layer["biases"]
+            elif layer["type"] in ["dense", "output"]:
+                weights[f"W{i}"], weights[f"b{i}"] = layer["weights"], layer["biases"]
+        np.savez(path, config=json.dumps(config), **weights)
+        print(f"[INFO] Model saved to {path}")
+
+    def train(self, *a, **k):
+        raise NotImplementedError("training (Classes/CNNModel.py:399-512) is SURVEY 8 row f4, not part of this hot path")

@@ -1,0 +1,52 @@
+// Launcher declarations shared between the kernel translation units and api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bcad {
+
+// ---------------------------------------------------------------- fp32 CUDA-core path (any shape)
+struct ConvArgs {
+    const float* x;      // [B,H,W,Cin] NHWC
+    const float* w;      // packed [k*k][Cin][CoutPad]
+    const float* bias;   // [CoutPad]
+    float* y;            // [B,Ho,Wo,Cout] post-activation, or nullptr
+    float* p;            // [B,Hp,Wp,Cout] 2x2 max-pooled, or nullptr
+    int B, H, W, Cin, Cout, CoutPad, ksize, pad, Ho, Wo, Hp, Wp;
+    float alpha;         // LeakyReLU slope (1 = identity)
+};
+int launch_conv_fp32(const ConvArgs& a, cudaStream_t s);
+
+// C[M,N] = A[M,K] * B  with B given as [N,K] (b_kmajor) or [K,N]; split-K partials in `partials`
+// ([splits][M][N]) when splits > 1, reduced (+bias, optional LeakyReLU copy) by launch_splitk_reduce.
+int sgemm_pick_splits(int M, int N, int K);
+int launch_sgemm(const float* A, const float* Bm, float* C_or_partials, int M, int N, int K,
+                 bool b_kmajor, int splits, cudaStream_t s);
+int launch_splitk_reduce(const float* partials, int splits, const float* bias, float* z, float* h,
+                         float alpha, int M, int N, cudaStream_t s);
+
+int launch_head(const float* logits, float* probs, int32_t* cls, int B, int nc, int head, cudaStream_t s);
+int launch_top_grad(const float* probs, const int32_t* cls, const int32_t* class_idx, float* d_top,
+                    int B, int nc, int grad_mode, cudaStream_t s);
+int launch_leaky_mask_mul(float* d, const float* z, float alpha, int64_t n, cudaStream_t s);
+int launch_unpool(const float* g, const float* y, float* dy, int B, int Ho, int Wo, int C, int ties,
+                  cudaStream_t s);
+// alpha partials from the pooled gradient (+ tie counts from y when ties==ALL): [B][splits][C]
+int alpha_pool_splits(int Hp);
+int launch_alpha_from_pool_grad(const float* g, const float* y, float* alpha_part, int B, int Ho, int Wo,
+                                int C, int ties, int splits, cudaStream_t s);
+// alpha partials from a dense gradient map (fp32 or bf16 NHWC): [B][splits][C]
+int launch_alpha_from_dense_grad(const void* dA, int dtype, float* alpha_part, int B, int h, int w, int C,
+                                 int splits, cudaStream_t s);
+// cam_lo[B,h,w] = ReLU(sum_k alpha_k A_k), alpha_k = inv_hw * sum_s alpha_part[b][s][k];
+// also writes alpha_out [B][C] (may be null) and per-image min/max partials mm[B][splits][2]
+int cam_splits(int h);
+int launch_cam(const void* A, int dtype, const float* alpha_part, int alpha_splits, float inv_hw,
+               float* alpha_out, float* cam_lo, float* mm, int B, int h, int w, int C, int splits,
+               cudaStream_t s);
+int launch_upsample_norm(const float* cam_lo, const float* mm, int mm_splits, float* out, int B, int h,
+                         int w, int H, int W, cudaStream_t s);
+int launch_overlay(const float* img01, const float* cam, int B, int H, int W, uint8_t* overlay_rgb,
+                   uint8_t* heat_u8, cudaStream_t s);
+
+}  // namespace bcad

@@ -1,0 +1,849 @@
+// fp32 CUDA-core kernels: the shape-generic path of libbcad (any ksize / channels / padding).
+//
+// Reference semantics implemented here (file:line under /root/reference):
+//   conv + bias + LeakyReLU (strict ">")      Classes/CNNModel.py:227-240, ADCNNM.py:48,76
+//   2x2/2 max-pool, floor dims                Classes/CNNModel.py:245-261
+//   max-pool backward, ties ALL / FIRST       Classes/CNNModel.py:263-277 / nn.MaxPool2d autograd
+//   dense  z = W.flat + b, LeakyReLU          Classes/CNNModel.py:177-189
+//   softmax(clip +-50), /(sum+1e-12)          Classes/CNNModel.py:203-212
+//   top gradient, dense backward              explainability.py:20-34
+//   Grad-CAM tail                             pytorch_grad_cam (GRADCAM.py:53,64) -- see oracle/gradcam.py
+#include "common.cuh"
+#include "kernels.h"
+#include "../../include/bcad.h"
+
+namespace bcad {
+
+// =====================================================================================================
+// direct convolution, NHWC fp32, fused bias + LeakyReLU (+ 2x2 max-pool)
+//   CTA tile 16 rows x 32 cols x 32 couts, 256 threads, thread tile 2 rows x 4 cols x 8 couts
+//   (the 2x2 pool windows are thread-local), input channels staged through smem 8 at a time.
+// =====================================================================================================
+constexpr int CT_ROWS = 16, CT_COLS = 32, CT_COUT = 32, CT_CC = 8;
+
+template <int K>
+__global__ void __launch_bounds__(256, 2) conv_fp32_kernel(ConvArgs a, int tiles_x) {
+    constexpr int PR = CT_ROWS + K - 1, PC = CT_COLS + K - 1;
+    extern __shared__ float smem[];
+    float* s_in = smem;                       // [CT_CC][PR][PC]
+    float* s_w = smem + CT_CC * PR * PC;      // [K*K][CT_CC][32]
+
+    const int tid = threadIdx.x;
+    const int cg = tid & 3;                   // cout group: couts cg*8 .. cg*8+7 of this CTA's 32
+    const int pg = tid >> 2;                  // pixel group
+    const int tx = pg & 7, ty = pg >> 3;      // 8 x 8 groups of (2 rows x 4 cols)
+    const int ox0 = (blockIdx.x % tiles_x) * CT_COLS, oy0 = (blockIdx.x / tiles_x) * CT_ROWS;
+    const int co0 = blockIdx.y * CT_COUT;
+    const int b = blockIdx.z;
+
+    float acc[2][4][8];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[r][c][j] = 0.f;
+
+    const float* xb = a.x + (size_t)b * a.H * a.W * a.Cin;
+    for (int c0 = 0; c0 < a.Cin; c0 += CT_CC) {
+        const int cc = min(CT_CC, a.Cin - c0);
+        __syncthreads();
+        for (int i = tid; i < PR * PC * cc; i += 256) {
+            const int ci = i % cc, rest = i / cc;
+            const int pc = rest % PC, pr = rest / PC;
+            const int iy = oy0 - a.pad + pr, ix = ox0 - a.pad + pc;
+            float v = 0.f;
+            if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
+                v = __ldg(xb + ((size_t)iy * a.W + ix) * a.Cin + c0 + ci);
+            s_in[(ci * PR + pr) * PC + pc] = v;
+        }
+        for (int i = tid; i < K * K * cc * 32; i += 256) {
+            const int co = i & 31, rest = i >> 5;
+            const int ci = rest % cc, tap = rest / cc;
+            s_w[(tap * CT_CC + ci) * 32 + co] =
+                __ldg(a.w + ((size_t)tap * a.Cin + c0 + ci) * a.CoutPad + co0 + co);
+        }
+        __syncthreads();
+        for (int ci = 0; ci < cc; ++ci) {
+            float win[K + 1][K + 3];
+#pragma unroll
+            for (int r = 0; r < K + 1; ++r)
+#pragma unroll
+                for (int c = 0; c < K + 3; ++c)
+                    win[r][c] = s_in[(ci * PR + ty * 2 + r) * PC + tx * 4 + c];
+#pragma unroll
+            for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx) {
+                    const float4* wp =
+                        reinterpret_cast<const float4*>(s_w + ((ky * K + kx) * CT_CC + ci) * 32 + cg * 8);
+                    const float4 w0 = wp[0], w1 = wp[1];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float v = win[r + ky][c + kx];
+                            acc[r][c][0] = fmaf(v, w0.x, acc[r][c][0]);
+                            acc[r][c][1] = fmaf(v, w0.y, acc[r][c][1]);
+                            acc[r][c][2] = fmaf(v, w0.z, acc[r][c][2]);
+                            acc[r][c][3] = fmaf(v, w0.w, acc[r][c][3]);
+                            acc[r][c][4] = fmaf(v, w1.x, acc[r][c][4]);
+                            acc[r][c][5] = fmaf(v, w1.y, acc[r][c][5]);
+                            acc[r][c][6] = fmaf(v, w1.z, acc[r][c][6]);
+                            acc[r][c][7] = fmaf(v, w1.w, acc[r][c][7]);
+                        }
+                }
+        }
+    }
+
+    // ---- epilogue: bias + LeakyReLU, store y, thread-local 2x2 max-pool, store p
+    const int cbase = co0 + cg * 8;
+    float bias[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bias[j] = __ldg(a.bias + cbase + j);
+    const bool vec = (a.Cout % 4 == 0) && (cbase + 8 <= a.Cout);
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[r][c][j] = leaky(acc[r][c][j] + bias[j], a.alpha);
+            const int oy = oy0 + ty * 2 + r, ox = ox0 + tx * 4 + c;
+            if (a.y != nullptr && oy < a.Ho && ox < a.Wo) {
+                float* dst = a.y + (((size_t)b * a.Ho + oy) * a.Wo + ox) * a.Cout + cbase;
+                if (vec) {
+                    reinterpret_cast<float4*>(dst)[0] = make_float4(acc[r][c][0], acc[r][c][1], acc[r][c][2], acc[r][c][3]);
+                    reinterpret_cast<float4*>(dst)[1] = make_float4(acc[r][c][4], acc[r][c][5], acc[r][c][6], acc[r][c][7]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (cbase + j < a.Cout) dst[j] = acc[r][c][j];
+                }
+            }
+        }
+    if (a.p != nullptr) {
+        const int py = (oy0 >> 1) + ty;
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+            const int px = (ox0 >> 1) + tx * 2 + c2;
+            if (py < a.Hp && px < a.Wp) {
+                float m[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    m[j] = fmaxf(fmaxf(acc[0][2 * c2][j], acc[0][2 * c2 + 1][j]),
+                                 fmaxf(acc[1][2 * c2][j], acc[1][2 * c2 + 1][j]));
+                float* dst = a.p + (((size_t)b * a.Hp + py) * a.Wp + px) * a.Cout + cbase;
+                if (vec) {
+                    reinterpret_cast<float4*>(dst)[0] = make_float4(m[0], m[1], m[2], m[3]);
+                    reinterpret_cast<float4*>(dst)[1] = make_float4(m[4], m[5], m[6], m[7]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (cbase + j < a.Cout) dst[j] = m[j];
+                }
+            }
+        }
+    }
+}
+
+template <int K>
+static int launch_conv_k(const ConvArgs& a, cudaStream_t s) {
+    constexpr int PR = CT_ROWS + K - 1, PC = CT_COLS + K - 1;
+    const size_t smem = (size_t)(CT_CC * PR * PC + K * K * CT_CC * 32) * sizeof(float);
+    if (smem > 48 * 1024)   // per-device attribute; cheap enough to set on every launch of the large-k variants
+        BCAD_CUDA_CHECK(cudaFuncSetAttribute(conv_fp32_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles_x = cdiv(a.Wo, CT_COLS), tiles_y = cdiv(a.Ho, CT_ROWS);
+    dim3 grid(tiles_x * tiles_y, a.CoutPad / CT_COUT, a.B);
+    conv_fp32_kernel<K><<<grid, 256, smem, s>>>(a, tiles_x);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+int launch_conv_fp32(const ConvArgs& a, cudaStream_t s) {
+    BCAD_REQUIRE(a.B <= 65535, "conv: batch chunk %d exceeds 65535", a.B);
+    switch (a.ksize) {
+        case 1: return launch_conv_k<1>(a, s);
+        case 2: return launch_conv_k<2>(a, s);
+        case 3: return launch_conv_k<3>(a, s);
+        case 4: return launch_conv_k<4>(a, s);
+        case 5: return launch_conv_k<5>(a, s);
+        case 6: return launch_conv_k<6>(a, s);
+        case 7: return launch_conv_k<7>(a, s);
+        default:
+            set_error("conv: ksize %d not supported (1..7)", a.ksize);
+            return BCAD_ERR_INVALID;
+    }
+}
+
+// =====================================================================================================
+// SGEMM  C[M,N] = A[M,K] * B   (A row-major K-contiguous; B as [N,K] or [K,N]), split-K partials
+//   128 x 128 x 8 tiles, 256 threads, 8x8 register tile split 4+4 so smem reads are conflict-free
+// =====================================================================================================
+constexpr int GM = 128, GN = 128, GK = 8, GLD = 132;
+
+template <bool B_KMAJOR>
+__global__ void __launch_bounds__(256, 2)
+sgemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ C, int M, int N,
+             int K, int k_per_split) {
+    __shared__ __align__(16) float As[GK][GLD];
+    __shared__ __align__(16) float Bs[GK][GLD];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+    const int kbeg = blockIdx.z * k_per_split, kend = min(K, kbeg + k_per_split);
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    // K-major tile loader: 128 rows x 8 k; thread -> row tid/2, k-quad (tid&1)*4
+    const int lrow = tid >> 1, lkq = (tid & 1) * 4;
+    // N-major B loader: 8 k x 128 n; thread -> k tid/32, n-quad (tid&31)*4
+    const int bk = tid >> 5, bnq = (tid & 31) * 4;
+    const bool kvec = (K % 4 == 0), nvec = (N % 4 == 0);
+
+    auto load_kmajor = [&](const float* P, int rows, int r0, int k0, float (&v)[4]) {
+        const int r = r0 + lrow, k = k0 + lkq;
+        v[0] = v[1] = v[2] = v[3] = 0.f;
+        if (r < rows) {
+            const float* src = P + (size_t)r * K + k;
+            if (kvec && k + 4 <= kend) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (k + j < kend) v[j] = __ldg(src + j);
+            }
+        }
+    };
+    auto load_nmajor = [&](int k0, float (&v)[4]) {
+        const int k = k0 + bk, n = n0 + bnq;
+        v[0] = v[1] = v[2] = v[3] = 0.f;
+        if (k < kend) {
+            const float* src = Bm + (size_t)k * N + n;
+            if (nvec && n + 4 <= N) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (n + j < N) v[j] = __ldg(src + j);
+            }
+        }
+    };
+
+    float ra[4], rb[4];
+    if (kbeg < kend) {
+        load_kmajor(A, M, m0, kbeg, ra);
+        if (B_KMAJOR) load_kmajor(Bm, N, n0, kbeg, rb); else load_nmajor(kbeg, rb);
+    }
+    for (int k0 = kbeg; k0 < kend; k0 += GK) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) As[lkq + j][lrow] = ra[j];
+        if (B_KMAJOR) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Bs[lkq + j][lrow] = rb[j];
+        } else {
+            *reinterpret_cast<float4*>(&Bs[bk][bnq]) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+        }
+        __syncthreads();
+        if (k0 + GK < kend) {   // prefetch the next tile into registers while computing this one
+            load_kmajor(A, M, m0, k0 + GK, ra);
+            if (B_KMAJOR) load_kmajor(Bm, N, n0, k0 + GK, rb); else load_nmajor(k0 + GK, rb);
+        }
+#pragma unroll
+        for (int kk = 0; kk < GK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 4 + 64]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4 + 64]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+    }
+    float* Cz = C + (size_t)blockIdx.z * M * N;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + ty * 4 + (i & 3) + (i >> 2) * 64;
+        if (m >= M) continue;
+#pragma unroll
+        for (int jh = 0; jh < 2; ++jh) {
+            const int n = n0 + tx * 4 + jh * 64;
+            float* dst = Cz + (size_t)m * N + n;
+            if (nvec && n + 4 <= N) {
+                *reinterpret_cast<float4*>(dst) = make_float4(acc[i][jh * 4], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (n + j < N) dst[j] = acc[i][jh * 4 + j];
+            }
+        }
+    }
+}
+
+int sgemm_pick_splits(int M, int N, int K) {
+    const int tiles = cdiv(M, GM) * cdiv(N, GN);
+    int splits = 1;
+    if (tiles < 296 && K >= 512) {
+        splits = cdiv(296, tiles);
+        const int max_splits = K / 256;
+        if (splits > max_splits) splits = max_splits;
+        if (splits < 1) splits = 1;
+    }
+    return splits;
+}
+
+int launch_sgemm(const float* A, const float* Bm, float* C, int M, int N, int K, bool b_kmajor, int splits,
+                 cudaStream_t s) {
+    int kps = cdiv(cdiv(K, splits), GK) * GK;
+    dim3 grid(cdiv(N, GN), cdiv(M, GM), splits);
+    BCAD_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "sgemm: grid too large (M=%d splits=%d)", M, splits);
+    if (b_kmajor) sgemm_kernel<true><<<grid, 256, 0, s>>>(A, Bm, C, M, N, K, kps);
+    else sgemm_kernel<false><<<grid, 256, 0, s>>>(A, Bm, C, M, N, K, kps);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+// z[m,n] = sum_s partial[s][m][n] + bias[n] (fixed order => run-to-run bit-stable); h = LeakyReLU(z)
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, const float* __restrict__ bias,
+                                     float* __restrict__ z, float* __restrict__ h, float alpha, int M, int N) {
+    const size_t total = (size_t)M * N;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        float v = 0.f;
+        for (int s = 0; s < splits; ++s) v += part[(size_t)s * total + i];
+        if (bias != nullptr) v += __ldg(bias + (i % N));
+        if (z != nullptr) z[i] = v;
+        if (h != nullptr) h[i] = leaky(v, alpha);
+    }
+}
+
+int launch_splitk_reduce(const float* part, int splits, const float* bias, float* z, float* h, float alpha,
+                         int M, int N, cudaStream_t s) {
+    const size_t total = (size_t)M * N;
+    const int blocks = (int)min((size_t)4096, (total + 255) / 256);
+    splitk_reduce_kernel<<<blocks, 256, 0, s>>>(part, splits, bias, z, h, alpha, M, N);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+// =====================================================================================================
+// head: probabilities + class; top gradient; LeakyReLU' mask
+// =====================================================================================================
+__global__ void head_kernel(const float* __restrict__ logits, float* __restrict__ probs, int32_t* __restrict__ cls,
+                            int B, int nc, int head) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float* z = logits + (size_t)b * nc;
+    // double arithmetic: the NumPy reference's softmax is float64 (Classes/CNNModel.py:205)
+    double zmax = -1e300;
+    for (int c = 0; c < nc; ++c) {
+        double v = (double)z[c];
+        if (head == BCAD_HEAD_SOFTMAX_CLIP) v = fmin(fmax(v, -50.0), 50.0);
+        zmax = fmax(zmax, v);
+    }
+    double sum = 0.0;
+    for (int c = 0; c < nc; ++c) {
+        double v = (double)z[c];
+        if (head == BCAD_HEAD_SOFTMAX_CLIP) v = fmin(fmax(v, -50.0), 50.0);
+        sum += exp(v - zmax);
+    }
+    int best = 0;
+    double best_v = -1e300;
+    for (int c = 0; c < nc; ++c) {
+        double v = (double)z[c];
+        if (head == BCAD_HEAD_SOFTMAX_CLIP) v = fmin(fmax(v, -50.0), 50.0);
+        double p = (head == BCAD_HEAD_SOFTMAX_CLIP) ? exp(v - zmax) / (sum + 1e-12) : exp(v - zmax) / sum;
+        if (probs != nullptr) probs[(size_t)b * nc + c] = (float)p;
+        // NumPy flavour: argmax(probs) (Classes/CNNModel.py:526); torch flavour: max(logits) (app.py:589)
+        const double score = (head == BCAD_HEAD_SOFTMAX_CLIP) ? p : (double)z[c];
+        if (score > best_v) { best_v = score; best = c; }
+    }
+    if (cls != nullptr) cls[b] = best;
+}
+
+int launch_head(const float* logits, float* probs, int32_t* cls, int B, int nc, int head, cudaStream_t s) {
+    head_kernel<<<cdiv(B, 128), 128, 0, s>>>(logits, probs, cls, B, nc, head);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+__global__ void top_grad_kernel(const float* __restrict__ probs, const int32_t* __restrict__ cls,
+                                const int32_t* __restrict__ class_idx, float* __restrict__ d_top, int B, int nc,
+                                int grad_mode) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * nc) return;
+    const int b = i / nc, c = i % nc;
+    const int target = class_idx != nullptr ? class_idx[b] : cls[b];
+    const float onehot = (c == target) ? 1.f : 0.f;
+    d_top[i] = (grad_mode == BCAD_GRAD_LOGIT) ? onehot : probs[i] - onehot;
+}
+
+int launch_top_grad(const float* probs, const int32_t* cls, const int32_t* class_idx, float* d_top, int B, int nc,
+                    int grad_mode, cudaStream_t s) {
+    top_grad_kernel<<<cdiv(B * nc, 256), 256, 0, s>>>(probs, cls, class_idx, d_top, B, nc, grad_mode);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+__global__ void leaky_mask_mul_kernel(float* __restrict__ d, const float* __restrict__ z, float alpha, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        d[i] *= (z[i] > 0.f ? 1.f : alpha);
+}
+
+int launch_leaky_mask_mul(float* d, const float* z, float alpha, int64_t n, cudaStream_t s) {
+    const int blocks = (int)min((int64_t)148 * 16, (n + 255) / 256);
+    leaky_mask_mul_kernel<<<blocks, 256, 0, s>>>(d, z, alpha, (size_t)n);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+// =====================================================================================================
+// max-pool backward: dy[window] = g * switch(window)
+// =====================================================================================================
+__global__ void unpool_kernel(const float* __restrict__ g, const float* __restrict__ y, float* __restrict__ dy,
+                              int B, int Ho, int Wo, int C, int ties) {
+    const int Hp = Ho / 2, Wp = Wo / 2;
+    const int Hc = (Ho + 1) / 2, Wc = (Wo + 1) / 2;          // windows incl. the dropped odd row/col
+    const size_t total = (size_t)B * Hc * Wc * C;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        size_t r = i / C;
+        const int wx = (int)(r % Wc); r /= Wc;
+        const int wy = (int)(r % Hc);
+        const int b = (int)(r / Hc);
+        const size_t ybase = ((size_t)b * Ho) * Wo * C + c;
+        if (wy < Hp && wx < Wp) {
+            const float gv = g[(((size_t)b * Hp + wy) * Wp + wx) * C + c];
+            float v[4];
+            size_t idx[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                idx[q] = ybase + ((size_t)(2 * wy + (q >> 1)) * Wo + (2 * wx + (q & 1))) * C;
+                v[q] = y[idx[q]];
+            }
+            const float m = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
+            bool taken = false;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                bool sw = (v[q] == m);
+                if (ties == BCAD_TIES_FIRST) { sw = sw && !taken; taken = taken || sw; }
+                dy[idx[q]] = sw ? gv : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int yy = 2 * wy + (q >> 1), xx = 2 * wx + (q & 1);
+                if (yy < Ho && xx < Wo) dy[ybase + ((size_t)yy * Wo + xx) * C] = 0.f;
+            }
+        }
+    }
+}
+
+int launch_unpool(const float* g, const float* y, float* dy, int B, int Ho, int Wo, int C, int ties, cudaStream_t s) {
+    const size_t total = (size_t)B * ((Ho + 1) / 2) * ((Wo + 1) / 2) * C;
+    const int blocks = (int)min((size_t)148 * 32, (total + 255) / 256);
+    unpool_kernel<<<blocks, 256, 0, s>>>(g, y, dy, B, Ho, Wo, C, ties);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+// =====================================================================================================
+// Grad-CAM channel weights without materialising dA:
+//   alpha_k * (h*w) = sum over pool windows of g[window,k] * (#elements the gradient is routed to)
+//   (#routed = 1 for TIES_FIRST, number of maxima for TIES_ALL)
+// grid (splits, B); block 256 = CL channel lanes x (256/CL) pixel lanes
+// =====================================================================================================
+__global__ void alpha_from_pool_grad_kernel(const float* __restrict__ g, const float* __restrict__ y,
+                                            float* __restrict__ alpha_part, int Ho, int Wo, int C, int ties,
+                                            int CL) {
+    extern __shared__ float red[];                     // [256/CL][CL]
+    const int Hp = Ho / 2, Wp = Wo / 2;
+    const int b = blockIdx.y, split = blockIdx.x, splits = gridDim.x;
+    const int cl = threadIdx.x % CL, pl = threadIdx.x / CL, PL = blockDim.x / CL;
+    const int rows_per = cdiv(Hp, splits);
+    const int r0 = split * rows_per, r1 = min(Hp, r0 + rows_per);
+    for (int cb = 0; cb < C; cb += CL) {               // uniform trip count (barriers inside)
+        const int c = cb + cl;
+        float acc = 0.f;
+        for (int wy = r0; wy < r1 && c < C; ++wy)
+            for (int wx = pl; wx < Wp; wx += PL) {
+                float gv = g[(((size_t)b * Hp + wy) * Wp + wx) * C + c];
+                if (ties == BCAD_TIES_ALL) {
+                    const float* yp = y + (((size_t)b * Ho + 2 * wy) * Wo + 2 * wx) * C + c;
+                    const float v0 = yp[0], v1 = yp[C], v2 = yp[(size_t)Wo * C], v3 = yp[(size_t)Wo * C + C];
+                    const float m = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+                    const int cnt = (v0 == m) + (v1 == m) + (v2 == m) + (v3 == m);
+                    gv *= (float)cnt;
+                }
+                acc += gv;
+            }
+        red[pl * CL + cl] = acc;
+        __syncthreads();
+        if (pl == 0 && c < C) {
+            float t = 0.f;
+            for (int q = 0; q < PL; ++q) t += red[q * CL + cl];
+            alpha_part[((size_t)b * splits + split) * C + c] = t;
+        }
+        __syncthreads();
+    }
+}
+
+int alpha_pool_splits(int Hp) { return Hp >= 32 ? 4 : 1; }
+
+static int pick_channel_lanes(int C) {
+    int cl = 1;
+    while (cl < C && cl < 64) cl <<= 1;
+    return cl;
+}
+
+int launch_alpha_from_pool_grad(const float* g, const float* y, float* alpha_part, int B, int Ho, int Wo, int C,
+                                int ties, int splits, cudaStream_t s) {
+    const int CL = pick_channel_lanes(C);
+    dim3 grid(splits, B);
+    alpha_from_pool_grad_kernel<<<grid, 256, 256 * sizeof(float), s>>>(g, y, alpha_part, Ho, Wo, C, ties, CL);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+// alpha partials from a dense gradient map dA [B,h,w,C] (fp32 or bf16): plain per-channel sums
+template <typename T>
+__global__ void alpha_from_dense_grad_kernel(const T* __restrict__ dA, float* __restrict__ alpha_part, int h, int w,
+                                             int C, int CL) {
+    extern __shared__ float red[];
+    const int b = blockIdx.y, split = blockIdx.x, splits = gridDim.x;
+    const int cl = threadIdx.x % CL, pl = threadIdx.x / CL, PL = blockDim.x / CL;
+    const int npix = h * w;
+    const int per = cdiv(npix, splits);
+    const int p0 = split * per, p1 = min(npix, p0 + per);
+    const T* base = dA + (size_t)b * npix * C;
+    for (int cb = 0; cb < C; cb += CL) {               // uniform trip count (barriers inside)
+        const int c = cb + cl;
+        float acc = 0.f;
+        for (int p = p0 + pl; p < p1 && c < C; p += PL) {
+            if constexpr (sizeof(T) == 4) acc += base[(size_t)p * C + c];
+            else acc += __bfloat162float(base[(size_t)p * C + c]);
+        }
+        red[pl * CL + cl] = acc;
+        __syncthreads();
+        if (pl == 0 && c < C) {
+            float t = 0.f;
+            for (int q = 0; q < PL; ++q) t += red[q * CL + cl];
+            alpha_part[((size_t)b * splits + split) * C + c] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// vectorised variant: C % 4 == 0 (fp32) / C % 8 == 0 (bf16), 128-bit streaming loads
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+alpha_from_dense_grad_vec_kernel(const void* __restrict__ dA, float* __restrict__ alpha_part, int h, int w, int C) {
+    constexpr int EPV = BF16 ? 8 : 4;                  // elements per 16-byte vector
+    extern __shared__ float red[];                     // [256][EPV]
+    const int b = blockIdx.y, split = blockIdx.x, splits = gridDim.x;
+    const int npix = h * w;
+    const int per = cdiv(npix, splits);
+    const int p0 = split * per, p1 = min(npix, p0 + per);
+    const int vpp = C / EPV;                           // vectors per pixel
+    const size_t v0 = (size_t)p0 * vpp, v1 = (size_t)p1 * vpp;
+    // thread t always sees the same channel group when 256 % vpp == 0; otherwise use the generic kernel
+    const uint4* base = reinterpret_cast<const uint4*>(dA) + (size_t)b * npix * vpp;
+    float acc[EPV];
+#pragma unroll
+    for (int j = 0; j < EPV; ++j) acc[j] = 0.f;
+    for (size_t v = v0 + threadIdx.x; v < v1; v += 256) {
+        const uint4 q = ldg_stream_u4(base + v);
+        if constexpr (BF16) {
+            acc[0] += bf16lo(q.x); acc[1] += bf16hi(q.x); acc[2] += bf16lo(q.y); acc[3] += bf16hi(q.y);
+            acc[4] += bf16lo(q.z); acc[5] += bf16hi(q.z); acc[6] += bf16lo(q.w); acc[7] += bf16hi(q.w);
+        } else {
+            acc[0] += __uint_as_float(q.x); acc[1] += __uint_as_float(q.y);
+            acc[2] += __uint_as_float(q.z); acc[3] += __uint_as_float(q.w);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < EPV; ++j) red[threadIdx.x * EPV + j] = acc[j];
+    __syncthreads();
+    // channel c is held by threads t with (v0 + t) % vpp == c / EPV
+    for (int c = threadIdx.x; c < C; c += 256) {
+        const int grp = c / EPV, j = c % EPV;
+        const int first = (int)((grp + vpp - (v0 % vpp)) % vpp);
+        float t = 0.f;
+        for (int q = first; q < 256; q += vpp) t += red[q * EPV + j];
+        alpha_part[((size_t)b * splits + split) * C + c] = t;
+    }
+}
+
+int launch_alpha_from_dense_grad(const void* dA, int dtype, float* alpha_part, int B, int h, int w, int C, int splits,
+                                 cudaStream_t s) {
+    dim3 grid(splits, B);
+    const int epv = dtype == 1 ? 8 : 4;
+    if (C % epv == 0 && 256 % (C / epv) == 0) {
+        if (dtype == 1) alpha_from_dense_grad_vec_kernel<true><<<grid, 256, 256 * 8 * sizeof(float), s>>>(dA, alpha_part, h, w, C);
+        else alpha_from_dense_grad_vec_kernel<false><<<grid, 256, 256 * 4 * sizeof(float), s>>>(dA, alpha_part, h, w, C);
+    } else {
+        const int CL = pick_channel_lanes(C);
+        if (dtype == 1)
+            alpha_from_dense_grad_kernel<__nv_bfloat16><<<grid, 256, 256 * sizeof(float), s>>>(
+                reinterpret_cast<const __nv_bfloat16*>(dA), alpha_part, h, w, C, CL);
+        else
+            alpha_from_dense_grad_kernel<float><<<grid, 256, 256 * sizeof(float), s>>>(
+                reinterpret_cast<const float*>(dA), alpha_part, h, w, C, CL);
+    }
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+// =====================================================================================================
+// cam_lo = ReLU(sum_k alpha_k A_k)  + per-CTA min/max partials
+// grid (splits, B), 256 threads; LP lanes cooperate on one pixel with 128-bit loads
+// =====================================================================================================
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+cam_kernel(const void* __restrict__ A, const float* __restrict__ alpha_part, int alpha_splits, float inv_hw,
+           float* __restrict__ alpha_out, float* __restrict__ cam_lo, float* __restrict__ mm, int h, int w, int C,
+           int LP, int vec) {
+    extern __shared__ float s_alpha[];                 // [C] then [16] reduction scratch
+    __shared__ float s_min[8], s_max[8];
+    const int b = blockIdx.y, split = blockIdx.x, splits = gridDim.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float t = 0.f;
+        for (int q = 0; q < alpha_splits; ++q) t += alpha_part[((size_t)b * alpha_splits + q) * C + c];
+        t *= inv_hw;
+        s_alpha[c] = t;
+        if (alpha_out != nullptr && split == 0) alpha_out[(size_t)b * C + c] = t;
+    }
+    __syncthreads();
+    const int npix = h * w;
+    const int per = cdiv(npix, splits);
+    const int p0 = split * per, p1 = min(npix, p0 + per);
+    float vmin = 3.4e38f, vmax = -3.4e38f;
+    if (vec) {
+        constexpr int EPV = BF16 ? 8 : 4;
+        const int vpp = C / EPV;
+        const int sub = threadIdx.x % LP, grp = threadIdx.x / LP, G = blockDim.x / LP;
+        const uint4* base = reinterpret_cast<const uint4*>(A) + (size_t)b * npix * vpp;
+        const int iters = cdiv_dev(p1 - p0, G);
+        for (int it = 0; it < iters; ++it) {               // uniform trip count (shuffles inside)
+            const int p = p0 + it * G + grp;
+            float acc = 0.f;
+            const bool live = p < p1;
+            if (live)
+                for (int v = sub; v < vpp; v += LP) {
+                    const uint4 q = ldg_stream_u4(base + (size_t)p * vpp + v);
+                    const float* al = s_alpha + v * EPV;
+                    if constexpr (BF16) {
+                        acc = fmaf(bf16lo(q.x), al[0], acc); acc = fmaf(bf16hi(q.x), al[1], acc);
+                        acc = fmaf(bf16lo(q.y), al[2], acc); acc = fmaf(bf16hi(q.y), al[3], acc);
+                        acc = fmaf(bf16lo(q.z), al[4], acc); acc = fmaf(bf16hi(q.z), al[5], acc);
+                        acc = fmaf(bf16lo(q.w), al[6], acc); acc = fmaf(bf16hi(q.w), al[7], acc);
+                    } else {
+                        acc = fmaf(__uint_as_float(q.x), al[0], acc); acc = fmaf(__uint_as_float(q.y), al[1], acc);
+                        acc = fmaf(__uint_as_float(q.z), al[2], acc); acc = fmaf(__uint_as_float(q.w), al[3], acc);
+                    }
+                }
+            for (int o = LP >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (live && sub == 0) {
+                acc = fmaxf(acc, 0.f);
+                cam_lo[(size_t)b * npix + p] = acc;
+                vmin = fminf(vmin, acc);
+                vmax = fmaxf(vmax, acc);
+            }
+        }
+    } else {
+        for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+            float acc = 0.f;
+            for (int c = 0; c < C; ++c) {
+                float a;
+                if (BF16) a = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(A)[((size_t)b * npix + p) * C + c]);
+                else a = reinterpret_cast<const float*>(A)[((size_t)b * npix + p) * C + c];
+                acc = fmaf(a, s_alpha[c], acc);
+            }
+            acc = fmaxf(acc, 0.f);
+            cam_lo[(size_t)b * npix + p] = acc;
+            vmin = fminf(vmin, acc);
+            vmax = fmaxf(vmax, acc);
+        }
+    }
+    vmin = warp_min(vmin);
+    vmax = warp_max(vmax);
+    if ((threadIdx.x & 31) == 0) { s_min[threadIdx.x >> 5] = vmin; s_max[threadIdx.x >> 5] = vmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < 8; ++q) { vmin = fminf(vmin, s_min[q]); vmax = fmaxf(vmax, s_max[q]); }
+        mm[((size_t)b * splits + split) * 2 + 0] = vmin;
+        mm[((size_t)b * splits + split) * 2 + 1] = vmax;
+    }
+}
+
+int cam_splits(int h) { return h >= 64 ? 8 : (h >= 16 ? 2 : 1); }
+
+int launch_cam(const void* A, int dtype, const float* alpha_part, int alpha_splits, float inv_hw, float* alpha_out,
+               float* cam_lo, float* mm, int B, int h, int w, int C, int splits, cudaStream_t s) {
+    const int epv = dtype == 1 ? 8 : 4;
+    const int vec = (C % epv == 0) ? 1 : 0;
+    int LP = 1;
+    if (vec) { while (LP < C / epv && LP < 32) LP <<= 1; }
+    dim3 grid(splits, B);
+    const size_t smem = (size_t)C * sizeof(float);
+    if (dtype == 1) cam_kernel<true><<<grid, 256, smem, s>>>(A, alpha_part, alpha_splits, inv_hw, alpha_out, cam_lo, mm, h, w, C, LP, vec);
+    else cam_kernel<false><<<grid, 256, smem, s>>>(A, alpha_part, alpha_splits, inv_hw, alpha_out, cam_lo, mm, h, w, C, LP, vec);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+// =====================================================================================================
+// min-max -> bilinear (cv2.resize INTER_LINEAR) -> min-max.  One CTA per image; the low-res map
+// lives in shared memory (falls back to global/L2 reads when it does not fit).
+// =====================================================================================================
+constexpr int UP_THREADS = 1024;
+
+__device__ __forceinline__ void block_minmax(float& vmin, float& vmax, float* s_red) {
+    vmin = warp_min(vmin);
+    vmax = warp_max(vmax);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5] = vmin; s_red[32 + (threadIdx.x >> 5)] = vmax; }
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    vmin = s_red[0];
+    vmax = s_red[32];
+    for (int q = 1; q < nw; ++q) { vmin = fminf(vmin, s_red[q]); vmax = fmaxf(vmax, s_red[32 + q]); }
+}
+
+__global__ void __launch_bounds__(UP_THREADS)
+upsample_norm_kernel(const float* __restrict__ cam_lo, const float* __restrict__ mm, int mm_splits,
+                     float* __restrict__ out, int h, int w, int H, int W, int lo_in_smem) {
+    extern __shared__ float sm[];
+    __shared__ float s_red[64];
+    // layout: x0[W] x1[W] fx[W] y0[H] y1[H] fy[H] (ints stored as float bits) then the low-res map
+    int* s_x0 = reinterpret_cast<int*>(sm);
+    int* s_x1 = s_x0 + W;
+    float* s_fx = sm + 2 * W;
+    int* s_y0 = reinterpret_cast<int*>(sm + 3 * W);
+    int* s_y1 = s_y0 + H;
+    float* s_fy = sm + 3 * W + 2 * H;
+    float* s_lo = sm + 3 * W + 3 * H;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    // coordinate tables: source coordinate in double, weight = float(frac) (oracle/gradcam.py, pinned to cv2)
+    for (int d = tid; d < W + H; d += blockDim.x) {
+        const bool isx = d < W;
+        const int dd = isx ? d : d - W;
+        const int ns = isx ? w : h, nd = isx ? W : H;
+        const double sc = ((double)dd + 0.5) * ((double)ns / (double)nd) - 0.5;
+        int i0 = (int)floor(sc);
+        float f = (float)(sc - (double)i0);
+        if (i0 < 0) { i0 = 0; f = 0.f; }
+        if (i0 >= ns - 1) { i0 = ns - 1; f = 0.f; }
+        const int i1 = min(i0 + 1, ns - 1);
+        if (isx) { s_x0[dd] = i0; s_x1[dd] = i1; s_fx[dd] = f; }
+        else { s_y0[dd] = i0; s_y1[dd] = i1; s_fy[dd] = f; }
+    }
+    float mn = 3.4e38f, mx = -3.4e38f;
+    for (int q = 0; q < mm_splits; ++q) {
+        mn = fminf(mn, mm[((size_t)b * mm_splits + q) * 2]);
+        mx = fmaxf(mx, mm[((size_t)b * mm_splits + q) * 2 + 1]);
+    }
+    const float denom = 1e-7f + (mx - mn);
+    const float* lo = cam_lo + (size_t)b * h * w;
+    if (lo_in_smem) {
+        for (int i = tid; i < h * w; i += blockDim.x) s_lo[i] = (lo[i] - mn) / denom;
+    }
+    __syncthreads();
+    auto sample = [&](int oy, int ox) -> float {
+        const int x0 = s_x0[ox], x1 = s_x1[ox], y0 = s_y0[oy], y1 = s_y1[oy];
+        const float fx = s_fx[ox], fy = s_fy[oy];
+        float a00, a01, a10, a11;
+        if (lo_in_smem) {
+            a00 = s_lo[y0 * w + x0]; a01 = s_lo[y0 * w + x1]; a10 = s_lo[y1 * w + x0]; a11 = s_lo[y1 * w + x1];
+        } else {
+            a00 = (lo[y0 * w + x0] - mn) / denom; a01 = (lo[y0 * w + x1] - mn) / denom;
+            a10 = (lo[y1 * w + x0] - mn) / denom; a11 = (lo[y1 * w + x1] - mn) / denom;
+        }
+        const float top = a00 * (1.f - fx) + a01 * fx;       // horizontal pass first (OpenCV HResize)
+        const float bot = a10 * (1.f - fx) + a11 * fx;
+        return top * (1.f - fy) + bot * fy;
+    };
+    float vmin = 3.4e38f, vmax = -3.4e38f;
+    const int npix = H * W;
+    for (int i = tid; i < npix; i += blockDim.x) {
+        const float v = sample(i / W, i % W);
+        vmin = fminf(vmin, v);
+        vmax = fmaxf(vmax, v);
+    }
+    block_minmax(vmin, vmax, s_red);
+    const float denom2 = 1e-7f + (vmax - vmin);
+    float* ob = out + (size_t)b * npix;
+    for (int i = tid; i < npix; i += blockDim.x) ob[i] = (sample(i / W, i % W) - vmin) / denom2;
+}
+
+int launch_upsample_norm(const float* cam_lo, const float* mm, int mm_splits, float* out, int B, int h, int w, int H,
+                         int W, cudaStream_t s) {
+    size_t smem = (size_t)(3 * W + 3 * H) * sizeof(float);
+    const size_t lo_bytes = (size_t)h * w * sizeof(float);
+    int lo_in_smem = 0;
+    if (smem + lo_bytes <= 200 * 1024) { smem += lo_bytes; lo_in_smem = 1; }
+    BCAD_REQUIRE(smem <= 200 * 1024, "upsample: output %dx%d too large for the coordinate tables", H, W);
+    if (smem > 48 * 1024)
+        BCAD_CUDA_CHECK(cudaFuncSetAttribute(upsample_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    upsample_norm_kernel<<<B, UP_THREADS, smem, s>>>(cam_lo, mm, mm_splits, out, h, w, H, W, lo_in_smem);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+// =====================================================================================================
+// overlay: show_cam_on_image (JET LUT, 0.5/0.5 blend, /max, u8) + heatmap_uint8 (truncation)
+// =====================================================================================================
+__constant__ uint8_t c_jet_bgr[256 * 3] = {
+#include "jet_lut.inc"
+};
+
+__global__ void __launch_bounds__(1024)
+overlay_kernel(const float* __restrict__ img01, const float* __restrict__ cam, int H, int W,
+               uint8_t* __restrict__ overlay_rgb, uint8_t* __restrict__ heat_u8) {
+    __shared__ float s_red[64];
+    const int b = blockIdx.x, npix = H * W;
+    const float* ib = img01 + (size_t)b * npix;
+    const float* cb = cam + (size_t)b * npix;
+    float vmax = -3.4e38f, vmin = 0.f;
+    for (int i = threadIdx.x; i < npix; i += blockDim.x) {
+        const float cv = cb[i];
+        const int li = (int)(uint8_t)(int)(255.f * cv);          // np.uint8(255*cam): truncation
+        if (heat_u8 != nullptr) heat_u8[(size_t)b * npix + i] = (uint8_t)(int)(cv * 255.f);
+        const float g = ib[i];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float heat = (float)c_jet_bgr[li * 3 + (2 - ch)] / 255.f;     // BGR -> RGB
+            vmax = fmaxf(vmax, 0.5f * heat + 0.5f * g);
+        }
+    }
+    if (overlay_rgb == nullptr) return;
+    block_minmax(vmin, vmax, s_red);
+    for (int i = threadIdx.x; i < npix; i += blockDim.x) {
+        const int li = (int)(uint8_t)(int)(255.f * cb[i]);
+        const float g = ib[i];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float heat = (float)c_jet_bgr[li * 3 + (2 - ch)] / 255.f;
+            const float o = (0.5f * heat + 0.5f * g) / vmax;
+            overlay_rgb[((size_t)b * npix + i) * 3 + ch] = (uint8_t)(int)(255.f * o);
+        }
+    }
+}
+
+int launch_overlay(const float* img01, const float* cam, int B, int H, int W, uint8_t* overlay_rgb, uint8_t* heat_u8,
+                   cudaStream_t s) {
+    overlay_kernel<<<B, 1024, 0, s>>>(img01, cam, H, W, overlay_rgb, heat_u8);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+}  // namespace bcad

@@ -1,0 +1,97 @@
+// The model handle behind bcad_model (weights, workspace, transfer pipeline).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <vector>
+
+#include "../../include/bcad.h"
+
+namespace bcad {
+
+struct ConvLayer {
+    int Cin = 0, Cout = 0, CoutPad = 0, k = 0;
+    int H = 0, W = 0, Ho = 0, Wo = 0, Hp = 0, Wp = 0;
+    std::vector<float> h_w, h_b;      // staged host weights: (F,k,k,C) and (F,)
+    float* d_w = nullptr;             // fp32 packed [k*k][Cin][CoutPad]
+    float* d_b = nullptr;             // [CoutPad]
+    float* d_w_dgrad = nullptr;       // fp32 packed flipped filters for the input gradient
+    float* d_zero_bias = nullptr;
+    float* y = nullptr;               // cached post-activation output (fp32 path), NHWC
+    float* p = nullptr;               // cached pooled output (fp32 path), NHWC
+    float* dz = nullptr;              // explain_backward scratch
+    float* gp = nullptr;              // gradient w.r.t. this block's pooled output (explain_backward)
+};
+
+struct DenseLayer {
+    int in = 0, out = 0, splits = 1;
+    std::vector<float> h_w, h_b;      // (out,in) with `in` in device (NHWC) order, (out,)
+    float* d_w = nullptr;
+    float* d_b = nullptr;
+    float* z = nullptr;               // pre-activation [B,out]
+    float* h = nullptr;               // LeakyReLU(z); reused as d(h) then dz by the backward
+};
+
+struct Xfer {                          // host-buffer pipeline (bcad_predict_explain_host)
+    bool inited = false;
+    int chunk = 0;
+    cudaStream_t s_in = nullptr, s_compute = nullptr, s_out = nullptr;
+    cudaEvent_t in_done[2] = {nullptr, nullptr}, compute_done[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
+    float* x[2] = {nullptr, nullptr};
+    float* heat[2] = {nullptr, nullptr};
+    float* logits[2] = {nullptr, nullptr};
+    float* probs[2] = {nullptr, nullptr};
+    int32_t* cls[2] = {nullptr, nullptr};
+    int32_t* cidx[2] = {nullptr, nullptr};
+};
+
+struct TensorPath;                     // tensor_path.cu
+
+struct Model {
+    bcad_config cfg;
+    std::vector<ConvLayer> conv;
+    std::vector<DenseLayer> dense;
+    int64_t flat = 0;
+    bool committed = false, ws_ready = false, tensor_path = false, profiling = false;
+    int cached_B = 0;
+    int64_t launches = 0;
+    size_t ws_bytes = 0;
+    std::mutex mu;
+    std::vector<void*> allocs;
+    // shared workspace
+    float* partials = nullptr;
+    float* probs = nullptr;
+    int32_t* cls = nullptr;
+    float* d_top = nullptr;
+    float* g_flat = nullptr;
+    float* alpha_part = nullptr;
+    float* alpha = nullptr;
+    float* cam_lo = nullptr;
+    float* mm = nullptr;
+    int alpha_splits = 1, cam_splits = 1;
+    cudaEvent_t call_done = nullptr;
+    std::vector<cudaEvent_t> prof_pool;   // profiling marks of the last call: event i precedes kernel i
+    std::vector<const char*> prof_names;
+    int prof_n = 0;
+    Xfer xfer;
+    TensorPath* tp = nullptr;
+
+    int alloc(void** p, size_t bytes);
+    void free_all();
+    int mark(const char* name, cudaStream_t s);
+};
+
+// dense backward shared by both paths: d_top -> ... -> dz of dense[0] (left in dense[0].h) and, when
+// g_flat != nullptr, on to the flattened pool output
+int dense_backward(Model* m, int n, const int32_t* class_idx, int grad_mode, float* g_flat, cudaStream_t s);
+
+// ---- tensor (tcgen05) path, tensor_path.cu
+int tensor_path_supported(const Model& m);          // BCAD_OK or BCAD_ERR_INVALID (+ message)
+int tensor_path_commit(Model& m);
+int tensor_forward_chunk(Model& m, const float* x, int n, cudaStream_t s);
+int tensor_explain_chunk(Model& m, int n, const int32_t* class_idx, int grad_mode, float* heat, cudaStream_t s);
+int tensor_get_activation(Model& m, int kind, int index, int B, float* dst, cudaStream_t s);
+void tensor_path_destroy(Model& m);
+
+}  // namespace bcad

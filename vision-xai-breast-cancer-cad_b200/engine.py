@@ -1,0 +1,363 @@
+"""Host-side engine over the libbcad handle: batched predict / predict+Grad-CAM, sharding.
+
+PyTorch is used only to own device memory and streams; every computation happens inside
+libbcad.so (hand-written sm_100a CUDA) through the C-ABI in include/bcad.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+@dataclass
+class NetSpec:
+    """Constructor arguments of the reference CNNs + the flavour switches."""
+    input_shape: Tuple[int, int, int]
+    num_classes: int
+    conv_layers: Sequence[Tuple[int, int]]
+    hidden_units: Sequence[int]
+    alpha_conv: float = 0.01
+    alpha_dense: float = 0.01
+    pad: int = 0
+    flatten: str = "hwc"
+    pool_ties: str = "dup"
+    head: str = "softmax"
+
+    @staticmethod
+    def numpy_flavour(input_shape, num_classes, conv_layers, hidden_units, leaky_alpha=0.01):
+        """Classes/CNNModel.py:68 -- valid conv, HWC flatten, tie-duplicating pool, softmax head."""
+        return NetSpec(tuple(input_shape), int(num_classes), [tuple(map(int, c)) for c in conv_layers],
+                       [int(u) for u in hidden_units], float(leaky_alpha), float(leaky_alpha), 0, "hwc", "dup", "softmax")
+
+    @staticmethod
+    def torch_flavour(input_shape, num_classes, conv_layers, hidden_units, leaky_alpha=0.01):
+        """ADCNNM.py:35-78 -- Conv2d(padding=1), F.leaky_relu default slope on convs, CHW flatten, logits."""
+        return NetSpec(tuple(input_shape), int(num_classes), [tuple(map(int, c)) for c in conv_layers],
+                       [int(u) for u in hidden_units], 0.01, float(leaky_alpha), 1, "chw", "first", "logits")
+
+    def shapes(self):
+        h, w, c = self.input_shape
+        out = []
+        for f, k in self.conv_layers:
+            ch, cw = h + 2 * self.pad - k + 1, w + 2 * self.pad - k + 1
+            out.append(((ch, cw, f), (ch // 2, cw // 2, f)))
+            h, w, c = ch // 2, cw // 2, f
+        return out, h * w * c
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        return C.c_void_p(t.data_ptr())
+    if isinstance(t, np.ndarray):
+        return C.c_void_p(t.ctypes.data)
+    raise TypeError(type(t))
+
+
+def _f32c(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a), dtype=np.float32)
+
+
+class Engine:
+    """One libbcad handle on one GPU."""
+
+    def __init__(self, spec: NetSpec, precision: str = "fp32", max_batch: int = 64,
+                 keep_all_activations: bool = False, device: int = 0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("libbcad needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.spec = spec
+        self.device = int(device)
+        self.precision = precision
+        self.max_batch = int(max_batch)
+        cfg = _lib.Config()
+        cfg.in_h, cfg.in_w, cfg.in_c = spec.input_shape
+        cfg.num_classes = spec.num_classes
+        if len(spec.conv_layers) > _lib.MAX_CONV or len(spec.hidden_units) >= _lib.MAX_DENSE:
+            raise ValueError("too many layers")
+        cfg.n_conv = len(spec.conv_layers)
+        for i, (f, k) in enumerate(spec.conv_layers):
+            cfg.conv_filters[i], cfg.conv_ksize[i] = int(f), int(k)
+        cfg.n_hidden = len(spec.hidden_units)
+        for j, u in enumerate(spec.hidden_units):
+            cfg.hidden_units[j] = int(u)
+        cfg.alpha_conv, cfg.alpha_dense = spec.alpha_conv, spec.alpha_dense
+        cfg.pad = spec.pad
+        cfg.flatten_order = _lib.FLATTEN[spec.flatten]
+        cfg.pool_ties = _lib.TIES[spec.pool_ties]
+        cfg.head = _lib.HEAD[spec.head]
+        cfg.precision = _lib.PRECISION[precision]
+        cfg.max_batch = self.max_batch
+        cfg.keep_all_activations = 1 if keep_all_activations else 0
+        cfg.device = self.device
+        self._h = C.c_void_p()
+        _lib.check(self.lib.bcad_create(C.byref(cfg), C.byref(self._h)))
+        self._committed = False
+        self.tdev = torch.device("cuda", self.device)
+
+    # ------------------------------------------------------------------ lifetime / weights
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.bcad_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_weights(self, conv_w, conv_b, dense_w, dense_b, batchnorm=None):
+        """conv_w[i]: (F,k,k,C); dense_w[j]: (units,in) with fc1 columns in spec.flatten order."""
+        for i, (w, b) in enumerate(zip(conv_w, conv_b)):
+            f, k = self.spec.conv_layers[i]
+            w = _f32c(w)
+            if w.shape[0] != f or w.shape[1] != k or w.shape[2] != k:
+                raise ValueError(f"conv {i}: filters shape {w.shape} does not match ({f},{k},{k},C)")
+            b = _f32c(b)
+            _lib.check(self.lib.bcad_set_conv_weights(self._h, i, _ptr(w), _ptr(b)))
+            if batchnorm and batchnorm.get(i) is not None:
+                g, bt, mu, var, eps = batchnorm[i]
+                _lib.check(self.lib.bcad_fold_batchnorm(self._h, i, _ptr(_f32c(g)), _ptr(_f32c(bt)),
+                                                        _ptr(_f32c(mu)), _ptr(_f32c(var)), float(eps)))
+        _, prev = self.spec.shapes()
+        units = list(self.spec.hidden_units) + [self.spec.num_classes]
+        if len(dense_w) != len(units):
+            raise ValueError(f"expected {len(units)} dense matrices, got {len(dense_w)}")
+        for j, (w, b) in enumerate(zip(dense_w, dense_b)):
+            w = _f32c(w)
+            if w.shape != (units[j], prev):
+                raise ValueError(f"dense {j}: weights shape {w.shape} does not match {(units[j], prev)}")
+            _lib.check(self.lib.bcad_set_dense_weights(self._h, j, _ptr(w), _ptr(_f32c(b))))
+            prev = units[j]
+        _lib.check(self.lib.bcad_commit(self._h))
+        self._committed = True
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.tdev).cuda_stream)
+
+    def _as_device_input(self, x) -> torch.Tensor:
+        h, w, c = self.spec.input_shape
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        if x.dim() == 3:
+            x = x[None]
+        if tuple(x.shape[1:]) != (h, w, c):
+            raise ValueError(f"input shape {tuple(x.shape)} does not match [B,{h},{w},{c}]")
+        return x.to(device=self.tdev, dtype=torch.float32, non_blocking=True).contiguous()
+
+    @property
+    def uses_tensor_path(self) -> bool:
+        return bool(self.lib.bcad_uses_tensor_path(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.bcad_launch_count(self._h))
+
+    def set_profiling(self, on: bool):
+        _lib.check(self.lib.bcad_set_profiling(self._h, 1 if on else 0))
+
+    def last_profile(self):
+        """[(kernel name, ms)] of the last device-buffer call (needs set_profiling(True) before it)."""
+        n = int(self.lib.bcad_profile_count(self._h))
+        out = []
+        for i in range(n):
+            buf = C.create_string_buffer(64)
+            ms = C.c_float()
+            _lib.check(self.lib.bcad_profile_get(self._h, i, buf, 64, C.byref(ms)))
+            out.append((buf.value.decode(), float(ms.value)))
+        return out
+
+    # ------------------------------------------------------------------ hot path, device tensors
+    def predict(self, x):
+        """-> (cls int32 [B], probs fp32 [B,nc], logits fp32 [B,nc]) as CUDA tensors."""
+        x = self._as_device_input(x)
+        B, nc = x.shape[0], self.spec.num_classes
+        with torch.cuda.device(self.tdev):
+            logits = torch.empty((B, nc), device=self.tdev, dtype=torch.float32)
+            probs = torch.empty((B, nc), device=self.tdev, dtype=torch.float32)
+            cls = torch.empty((B,), device=self.tdev, dtype=torch.int32)
+            _lib.check(self.lib.bcad_predict(self._h, _ptr(x), B, _ptr(logits), _ptr(probs), _ptr(cls), self._stream()))
+        return cls, probs, logits
+
+    def predict_explain(self, x, class_idx=None, grad_mode: str = "logit", out_heat: Optional[torch.Tensor] = None):
+        """-> (cls, probs, logits, heatmaps fp32 [B,H,W]) as CUDA tensors."""
+        x = self._as_device_input(x)
+        B, nc = x.shape[0], self.spec.num_classes
+        h, w, _ = self.spec.input_shape
+        with torch.cuda.device(self.tdev):
+            logits = torch.empty((B, nc), device=self.tdev, dtype=torch.float32)
+            probs = torch.empty((B, nc), device=self.tdev, dtype=torch.float32)
+            cls = torch.empty((B,), device=self.tdev, dtype=torch.int32)
+            heat = out_heat if out_heat is not None else torch.empty((B, h, w), device=self.tdev, dtype=torch.float32)
+            ci = self._class_idx(class_idx, B)
+            _lib.check(self.lib.bcad_predict_explain(self._h, _ptr(x), B, _ptr(ci), _lib.GRAD_MODE[grad_mode],
+                                                     _ptr(logits), _ptr(probs), _ptr(cls), _ptr(heat), self._stream()))
+        return cls, probs, logits, heat
+
+    def _class_idx(self, class_idx, B):
+        if class_idx is None:
+            return None
+        ci = torch.as_tensor(class_idx, dtype=torch.int32).reshape(-1)
+        if ci.numel() == 1:
+            ci = ci.expand(B)
+        if ci.numel() != B:
+            raise ValueError(f"class_idx has {ci.numel()} entries for a batch of {B}")
+        if int(ci.min()) < 0 or int(ci.max()) >= self.spec.num_classes:
+            raise ValueError("class_idx out of range")
+        return ci.to(self.tdev).contiguous()
+
+    def explain_backward(self, B: int, class_idx, grad_mode: str = "softmax_ce",
+                         want_conv: Sequence[int] = (), want_input: bool = False):
+        """After predict() of the same B: ({conv_block: dA [B,h,w,F]}, d_input [B,H,W,C] | None)."""
+        shapes, _ = self.spec.shapes()
+        n_conv = len(shapes)
+        with torch.cuda.device(self.tdev):
+            ptrs = (C.c_void_p * n_conv)()
+            outs = {}
+            for i in want_conv:
+                ch, cw, f = shapes[i][0]
+                outs[i] = torch.empty((B, ch, cw, f), device=self.tdev, dtype=torch.float32)
+                ptrs[i] = outs[i].data_ptr()
+            d_in = None
+            if want_input:
+                d_in = torch.empty((B,) + tuple(self.spec.input_shape), device=self.tdev, dtype=torch.float32)
+            ci = self._class_idx(class_idx, B)
+            _lib.check(self.lib.bcad_explain_backward(self._h, B, _ptr(ci), _lib.GRAD_MODE[grad_mode],
+                                                      ptrs, _ptr(d_in), self._stream()))
+        return outs, d_in
+
+    def get_tensor(self, kind: int, index: int, B: int) -> torch.Tensor:
+        per = int(self.lib.bcad_tensor_elems(self._h, kind, index))
+        if per <= 0:
+            raise ValueError(f"no such tensor ({kind},{index})")
+        with torch.cuda.device(self.tdev):
+            out = torch.empty((B, per), device=self.tdev, dtype=torch.float32)
+            _lib.check(self.lib.bcad_get_tensor(self._h, kind, index, B, _ptr(out), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ hot path, host buffers (end to end)
+    def predict_explain_host(self, x: np.ndarray, class_idx: Optional[np.ndarray] = None, grad_mode: str = "logit",
+                             heat_out: Optional[np.ndarray] = None, want_heat: bool = True):
+        """x: float32 [B,H,W,C] host array (pinned memory makes the copies asynchronous).
+        -> (cls int32 [B], probs [B,nc], logits [B,nc], heat [B,H,W]) as host arrays."""
+        h, w, c = self.spec.input_shape
+        if x.dtype != np.float32 or not x.flags["C_CONTIGUOUS"]:
+            x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim == 3:
+            x = x[None]
+        if x.shape[1:] != (h, w, c):
+            raise ValueError(f"input shape {x.shape} does not match [B,{h},{w},{c}]")
+        B, nc = x.shape[0], self.spec.num_classes
+        logits = np.empty((B, nc), np.float32)
+        probs = np.empty((B, nc), np.float32)
+        cls = np.empty((B,), np.int32)
+        heat = None
+        if want_heat:
+            heat = heat_out if heat_out is not None else np.empty((B, h, w), np.float32)
+        ci = None
+        if class_idx is not None:
+            ci = np.ascontiguousarray(np.broadcast_to(np.asarray(class_idx, dtype=np.int32).reshape(-1), (B,)))
+        _lib.check(self.lib.bcad_predict_explain_host(self._h, _ptr(x), B, _ptr(ci), _lib.GRAD_MODE[grad_mode],
+                                                      _ptr(logits), _ptr(probs), _ptr(cls), _ptr(heat)))
+        return cls, probs, logits, heat
+
+
+def gradcam_tail(A: torch.Tensor, dA: torch.Tensor, out_hw: Tuple[int, int]) -> torch.Tensor:
+    """Stand-alone Grad-CAM tail on NHWC CUDA tensors [B,h,w,K] (fp32 or bf16) -> fp32 [B,H,W]."""
+    lib = _lib.load()
+    if A.shape != dA.shape or A.dtype != dA.dtype or A.dim() != 4:
+        raise ValueError("A and dA must be NHWC tensors of the same shape and dtype")
+    if A.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("fp32 or bf16 only")
+    A, dA = A.contiguous(), dA.contiguous()
+    B, h, w, K = A.shape
+    H, W = out_hw
+    out = torch.empty((B, H, W), device=A.device, dtype=torch.float32)
+    with torch.cuda.device(A.device):
+        _lib.check(lib.bcad_gradcam_tail(_ptr(A), _ptr(dA), B, K, h, w, H, W, 0 if A.dtype == torch.float32 else 1,
+                                         _ptr(out), C.c_void_p(torch.cuda.current_stream(A.device).cuda_stream)))
+    return out
+
+
+def overlay(img01: torch.Tensor, cam: torch.Tensor, want_overlay=True, want_heat_u8=True):
+    """show_cam_on_image + heatmap_uint8 (GRADCAM.py:67,70) on CUDA tensors [B,H,W] -> (u8 [B,H,W,3], u8 [B,H,W])."""
+    lib = _lib.load()
+    img01 = img01.to(torch.float32).contiguous()
+    cam = cam.to(torch.float32).contiguous()
+    B, H, W = cam.shape
+    ov = torch.empty((B, H, W, 3), device=cam.device, dtype=torch.uint8) if want_overlay else None
+    hu = torch.empty((B, H, W), device=cam.device, dtype=torch.uint8) if want_heat_u8 else None
+    with torch.cuda.device(cam.device):
+        _lib.check(lib.bcad_overlay(_ptr(img01), _ptr(cam), B, H, W, _ptr(ov), _ptr(hu),
+                                    C.c_void_p(torch.cuda.current_stream(cam.device).cuda_stream)))
+    return ov, hu
+
+
+# --------------------------------------------------------------------------------------------------
+# batch sharding: contiguous split, replicated weights, no collective on this path
+# --------------------------------------------------------------------------------------------------
+def shard_bounds(n: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous near-equal split of n images over `world` ranks: [(start, stop)] (empty shards allowed)."""
+    base, rem = divmod(n, world)
+    out, s = [], 0
+    for r in range(world):
+        e = s + base + (1 if r < rem else 0)
+        out.append((s, e))
+        s = e
+    return out
+
+
+class ShardedEngine:
+    """Single-process driver over several GPUs of one box: one Engine + one host thread per GPU."""
+
+    def __init__(self, spec: NetSpec, devices: Sequence[int], **kw):
+        self.engines = [Engine(spec, device=d, **kw) for d in devices]
+        self.spec = spec
+
+    def set_weights(self, *a, **k):
+        for e in self.engines:
+            e.set_weights(*a, **k)
+
+    def predict_explain_host(self, x: np.ndarray, class_idx=None, grad_mode="logit"):
+        B = x.shape[0]
+        h, w, _ = self.spec.input_shape
+        nc = self.spec.num_classes
+        cls = np.empty((B,), np.int32)
+        probs = np.empty((B, nc), np.float32)
+        logits = np.empty((B, nc), np.float32)
+        heat = np.empty((B, h, w), np.float32)
+        errs = []
+
+        def work(e, s, t):
+            try:
+                if t <= s:
+                    return
+                ci = None if class_idx is None else np.broadcast_to(np.asarray(class_idx, np.int32).reshape(-1), (B,))[s:t]
+                c, p, l, hm = e.predict_explain_host(x[s:t], ci, grad_mode, heat_out=heat[s:t])
+                cls[s:t], probs[s:t], logits[s:t] = c, p, l
+            except Exception as ex:  # surfaced after join
+                errs.append(ex)
+
+        ths = [threading.Thread(target=work, args=(e, s, t))
+               for e, (s, t) in zip(self.engines, shard_bounds(B, len(self.engines)))]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        if errs:
+            raise errs[0]
+        return cls, probs, logits, heat
+
+    def close(self):
+        for e in self.engines:
+            e.close()
