@@ -160,6 +160,13 @@ BCAD_API int bcad_set_profiling(bcad_model* m, int on);
 BCAD_API int bcad_profile_count(bcad_model* m);
 BCAD_API int bcad_profile_get(bcad_model* m, int i, char* name_buf, int name_cap, float* ms);
 
+/* ---- diagnostics ------------------------------------------------------------------------------ */
+/* One 128 x N x (16*steps) tcgen05 UMMA problem on caller-provided shared-memory operand images and descriptor
+ * fields; used by tests/test_gpu_sm100.py to pin the descriptor conventions the tensor path relies on.
+ * params_host: int32 {N, steps, a_lbo, a_sbo, a_layout, b_lbo, b_sbo, b_layout, a_koff[64], b_koff[64]}. */
+BCAD_API int bcad_selftest_umma(const void* a_img_dev, int a_bytes, const void* b_img_dev, int b_bytes,
+                       const int32_t* params_host, float* d_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,13 +52,38 @@ def load_torch_golden(name):
     return g, cfg, p
 
 
-def oracle_heatmaps(cfg, params, x, class_idx, grad_mode):
-    """Oracle predict + Grad-CAM at the last conv block (float64 net, float32 tail as pytorch_grad_cam)."""
+def _switches_from(A_nhwc: np.ndarray, ties: str) -> np.ndarray:
+    """Pool switches (float mask) of an activation map, per the flavour's tie rule."""
+    import torch
+    _, sw = ocnn._pool_with_switches(torch.as_tensor(A_nhwc).permute(0, 3, 1, 2), ties)
+    return sw.permute(0, 2, 3, 1).numpy()
+
+
+def near_tie_windows(A_nhwc: np.ndarray, rel=1e-6) -> np.ndarray:
+    """[B,h2,w2,C] bool: pool windows holding a value within `rel` (relative) of the maximum without
+    being equal to it -- a float32 computation may legitimately see an exact tie there (or break one)."""
+    b, h, w, c = A_nhwc.shape
+    h2, w2 = h // 2, w // 2
+    win = A_nhwc[:, :2 * h2, :2 * w2].reshape(b, h2, 2, w2, 2, c).transpose(0, 1, 3, 5, 2, 4).reshape(b, h2, w2, c, 4)
+    mx = win.max(axis=-1, keepdims=True)
+    gap = mx - win
+    return ((gap > 0) & (gap < rel * np.maximum(np.abs(mx), 1e-30))).any(axis=-1)
+
+
+def oracle_heatmaps(cfg, params, x, class_idx, grad_mode, A_for_ties=None):
+    """Oracle predict + Grad-CAM at the last conv block (float64 net, float32 tail as pytorch_grad_cam).
+
+    A_for_ties: optional [B,h,w,F] activation map whose EXACT-EQUALITY structure decides the pool switches of
+    the last block (the tie rule compares floats for equality, so it can only be reproduced bit-for-bit at the
+    precision the activations were computed in; see DESIGN.md "tie semantics")."""
+    import torch
     from oracle import gradcam as ogc
     cache = ocnn.forward(cfg, params, x)
     score = cache.probs if cfg.head == "softmax" else cache.logits
     cls = score.argmax(dim=-1).numpy()
     ci = cls if class_idx is None else class_idx
+    if A_for_ties is not None:
+        cache.switches[-1] = torch.as_tensor(_switches_from(A_for_ties, cfg.pool_ties)).to(cache.logits.dtype)
     cag, _, _ = ocnn.backward(cfg, params, cache, ocnn.top_gradient(cache, ci, grad_mode), through_input=False)
     last = len(cfg.conv_layers) - 1
     A = cache.conv_out[last].numpy().astype(np.float32)

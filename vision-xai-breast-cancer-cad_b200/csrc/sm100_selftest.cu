@@ -1,0 +1,83 @@
+// Self-test harness for the tcgen05 building blocks: runs ONE 128 x N x (16*steps) UMMA problem whose operand
+// images (exact shared-memory byte layouts) and descriptor fields come from the caller, so tests/ can pin the
+// descriptor conventions (no-swizzle core matrices, 16-byte shifted starts, SW128 K-advance) against a matmul.
+#include "../../include/bcad.h"
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace bcad {
+
+struct SelftestParams {
+    int N, steps;
+    int a_lbo, a_sbo, a_layout, b_lbo, b_sbo, b_layout;
+    int a_koff[64], b_koff[64];
+};
+
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_kernel(const uint4* __restrict__ a_img, int a_bytes, const uint4* __restrict__ b_img, int b_bytes,
+                     SelftestParams p, float* __restrict__ D) {
+    using namespace sm100;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    uint8_t* sa = smem;
+    uint8_t* sb = smem + ((a_bytes + 1023) / 1024) * 1024;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < a_bytes / 16; i += 128) reinterpret_cast<uint4*>(sa)[i] = a_img[i];
+    for (int i = tid; i < b_bytes / 16; i += 128) reinterpret_cast<uint4*>(sb)[i] = b_img[i];
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(&tmem_base, 256);
+        tmem_relinquish();
+    }
+    fence_proxy_async();           // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base;
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, p.N);
+        for (int k = 0; k < p.steps; ++k) {
+            const uint64_t ad = make_smem_desc(smem_u32(sa) + p.a_koff[k], p.a_lbo, p.a_sbo, p.a_layout);
+            const uint64_t bd = make_smem_desc(smem_u32(sb) + p.b_koff[k], p.b_lbo, p.b_sbo, p.b_layout);
+            umma_bf16(tmem, ad, bd, idesc, k > 0 ? 1u : 0u);
+        }
+        umma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < p.N; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        const int row = warp * 32 + (tid & 31);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (c0 + j < p.N) D[(size_t)row * p.N + c0 + j] = v[j];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace bcad
+
+extern "C" int bcad_selftest_umma(const void* a_img_dev, int a_bytes, const void* b_img_dev, int b_bytes,
+                                  const int32_t* params_host, float* d_dev, void* stream) {
+    using namespace bcad;
+    BCAD_REQUIRE(a_img_dev && b_img_dev && params_host && d_dev, "selftest: null argument");
+    BCAD_REQUIRE(a_bytes % 16 == 0 && b_bytes % 16 == 0, "selftest: images must be multiples of 16 bytes");
+    SelftestParams p;
+    memcpy(&p, params_host, sizeof(p));
+    BCAD_REQUIRE(p.N >= 16 && p.N <= 256 && p.N % 16 == 0 && p.steps >= 1 && p.steps <= 64, "selftest: bad N/steps");
+    const size_t smem = ((size_t)(a_bytes + 1023) / 1024) * 1024 + b_bytes + 1024;
+    BCAD_REQUIRE(smem <= 200 * 1024, "selftest: operand images too large");
+    BCAD_CUDA_CHECK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(a_img_dev), a_bytes,
+                                                                 reinterpret_cast<const uint4*>(b_img_dev), b_bytes, p, d_dev);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
