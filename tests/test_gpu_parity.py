@@ -83,7 +83,8 @@ def test_predict_explain_vs_oracle(flavour, shape, convs, hidden, B, kind, grad_
     cfg = mk(shape, 2, convs, hidden, 0.01)
     p = ocnn.init_params(cfg, seed=7, bias_std=0.05)
     x = ocnn.synth_images(B, shape, seed=123, kind=kind)
-    eng = engine_from(cfg, p, max_batch=4)                       # B > max_batch for some cases => chunking
+    eng = engine_from(cfg, p, max_batch=8)
+    eng_chunked = engine_from(cfg, p, max_batch=4)               # B > max_batch for some cases => chunking
     from bcad_b200 import _lib
     from util import _switches_from, near_tie_windows
     last = len(convs) - 1
@@ -91,10 +92,8 @@ def test_predict_explain_vs_oracle(flavour, shape, convs, hidden, B, kind, grad_
         cls, probs, logits, heat = eng.predict_explain(x, class_idx, grad_mode)
         # The pool-tie rule compares activations for exact equality: take the equality structure from the
         # device's own fp32 activations (last chunk is cached) and everything else from the float64 oracle.
-        nb = B % 4 or 4
-        A_dev = _np(eng.get_tensor(_lib.T_CONV_OUT, last, nb)).reshape(nb, *cfg.shapes()[0][last][0])
+        A_ties = _np(eng.get_tensor(_lib.T_CONV_OUT, last, B)).reshape(B, *cfg.shapes()[0][last][0])
         o_cls, cache, A, dA, o_heat = oracle_heatmaps(cfg, p, x, class_idx, grad_mode)
-        A_ties = np.concatenate([A[:B - nb], A_dev]) if nb < B else A_dev
         sw_dev, sw_or = _switches_from(A_ties, cfg.pool_ties), cache.switches[-1].numpy()
         if not np.array_equal(sw_dev, sw_or):
             # differences are only allowed where float64 itself sees a near-tie (gap < 1e-6 relative)
@@ -106,6 +105,11 @@ def test_predict_explain_vs_oracle(flavour, shape, convs, hidden, B, kind, grad_
         np.testing.assert_allclose(_np(logits), cache.logits.numpy(), rtol=0, atol=FP32_TOL)
         np.testing.assert_allclose(_np(probs), cache.probs.numpy(), rtol=0, atol=FP32_TOL)
         np.testing.assert_allclose(_np(heat), o_heat, rtol=0, atol=FP32_TOL)
+        c2, p2, l2, h2 = eng_chunked.predict_explain(x, class_idx, grad_mode)      # chunked == unchunked
+        assert np.array_equal(_np(c2), _np(cls))
+        np.testing.assert_allclose(_np(l2), _np(logits), rtol=0, atol=1e-5)
+        np.testing.assert_allclose(_np(h2), _np(heat), rtol=0, atol=1e-5)
+    eng_chunked.close()
     # host-buffer C-ABI call == device-buffer call
     h_cls, h_probs, h_logits, h_heat = eng.predict_explain_host(x, None, grad_mode)
     cls, probs, logits, heat = eng.predict_explain(x, None, grad_mode)

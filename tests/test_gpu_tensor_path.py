@@ -1,0 +1,114 @@
+"""bf16 tcgen05 path vs the float64 oracle.  Tolerance (north_star): logits / normalised heatmaps max-abs <= 1e-2;
+classes identical wherever the oracle's logit margin exceeds the bf16 error bound."""
+import numpy as np
+import pytest
+import torch
+
+from util import engine_from, oracle_heatmaps, ocnn
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 1e-2
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _check(cfg, p, x, eng, B):
+    from bcad_b200 import _lib
+    assert eng.uses_tensor_path
+    for class_idx, mode in ((None, "logit"), (np.arange(B) % 2, "softmax_ce")):
+        cls, probs, logits, heat = eng.predict_explain(x, class_idx, mode)
+        o_cls, cache, A, dA, o_heat = oracle_heatmaps(cfg, p, x, class_idx, mode)
+        lg = cache.logits.numpy()
+        err_l = np.abs(_np(logits) - lg).max()
+        scale = max(1.0, np.abs(lg).max())
+        assert err_l <= BF16_TOL * scale, f"logits err {err_l} (scale {scale})"
+        margin = np.abs(lg[:, 0] - lg[:, 1])
+        safe = margin > 4 * BF16_TOL * scale
+        assert np.array_equal(_np(cls)[safe], o_cls[safe])
+        err_h = np.abs(_np(heat) - o_heat).max(axis=(1, 2))
+        assert err_h.max() <= BF16_TOL, f"heatmap err per image {err_h}"
+    return err_l, err_h.max()
+
+
+def test_tensor_path_intermediates_small():
+    """Stage-by-stage: pooled conv0 (bf16), target activations A, fc1 pre-activations."""
+    from bcad_b200 import _lib
+    cfg = ocnn.NetConfig.torch_flavour((64, 64, 1), 2, [(32, 3), (64, 3)], [64, 32], 0.01)
+    p = ocnn.init_params(cfg, seed=7, bias_std=0.05)
+    x = ocnn.synth_images(5, (64, 64, 1), seed=1)
+    eng = engine_from(cfg, p, precision="bf16", max_batch=8)
+    cls, probs, logits = eng.predict(x)
+    cache = ocnn.forward(cfg, p, x)
+    p1 = _np(eng.get_tensor(_lib.T_POOL_OUT, 0, 5)).reshape(5, 32, 32, 32)
+    want = cache.pool_out[0].numpy()
+    assert np.abs(p1 - want).max() <= 2e-2 * max(1.0, np.abs(want).max()), "conv0+pool (bf16 store)"
+    A = _np(eng.get_tensor(_lib.T_CONV_OUT, 1, 5)).reshape(5, 32, 32, 64)
+    want = cache.conv_out[1].numpy()
+    assert np.abs(A - want).max() <= 3e-2 * max(1.0, np.abs(want).max()), "conv1 implicit GEMM"
+    z1 = _np(eng.get_tensor(_lib.T_DENSE_Z, 0, 5))
+    want = cache.z[0].numpy()
+    assert np.abs(z1 - want).max() <= 3e-2 * max(1.0, np.abs(want).max()), "fc1 split-K GEMM"
+    np.testing.assert_allclose(_np(logits), cache.logits.numpy(), rtol=0, atol=BF16_TOL * max(1.0, np.abs(cache.logits.numpy()).max()))
+    eng.close()
+
+
+@pytest.mark.parametrize("shape,convs,hidden,B,mb", [
+    ((64, 64, 1), [(32, 3), (64, 3)], [64, 32], 5, 8),
+    ((48, 40, 1), [(16, 3), (64, 3)], [32], 7, 4),            # chunked, Cin=16, one hidden layer
+    ((32, 32, 1), [(64, 3), (64, 3)], [256, 128], 3, 4),      # Cin=64
+    ((32, 32, 1), [(32, 3), (64, 3)], [48, 16], 140, 256),    # two fc1 M tiles (B > 128)
+])
+def test_tensor_path_torch_flavour(shape, convs, hidden, B, mb):
+    cfg = ocnn.NetConfig.torch_flavour(shape, 2, convs, hidden, 0.01)
+    p = ocnn.init_params(cfg, seed=7, bias_std=0.05)
+    x = ocnn.synth_images(B, shape, seed=11)
+    eng = engine_from(cfg, p, precision="bf16", max_batch=mb)
+    _check(cfg, p, x, eng, B)
+    eng.close()
+
+
+def test_tensor_path_valid_conv_odd_sizes():
+    """pad=0 (valid) with odd maps: 61 -> 59 -> 29 -> 27 -> 13; first-index pooling, softmax head, HWC flatten."""
+    cfg = ocnn.NetConfig((61, 61, 1), 2, [(32, 3), (64, 3)], [32], 0.01, 0.01, 0, "hwc", "first", "softmax")
+    p = ocnn.init_params(cfg, seed=5, bias_std=0.05)
+    x = ocnn.synth_images(4, (61, 61, 1), seed=3)
+    eng = engine_from(cfg, p, precision="bf16", max_batch=4)
+    _check(cfg, p, x, eng, 4)
+    eng.close()
+
+
+def test_tensor_path_rejects_unsupported_shapes():
+    import bcad_b200
+    from util import spec_from_cfg
+    cfg = ocnn.NetConfig.numpy_flavour((32, 32, 1), 2, [(32, 3), (64, 3)], [32])        # tie-duplicating pool
+    with pytest.raises(ValueError, match="TIES_FIRST"):
+        bcad_b200.Engine(spec_from_cfg(cfg), precision="bf16")
+    cfg = ocnn.NetConfig.torch_flavour((32, 32, 3), 2, [(32, 3), (64, 3)], [32])
+    with pytest.raises(ValueError):
+        bcad_b200.Engine(spec_from_cfg(cfg), precision="bf16")
+
+
+def test_tensor_path_full_size_canonical():
+    """BASELINE cfg2 network at 256x256x1: oracle parity on a few images + batch-slice / host-call properties."""
+    cfg = ocnn.NetConfig.torch_flavour((256, 256, 1), 2, [(32, 3), (64, 3)], [256, 128], 0.01)
+    p = ocnn.init_params(cfg, seed=7, bias_std=0.0)
+    x = ocnn.synth_images(10, (256, 256, 1), seed=20251018)
+    eng = engine_from(cfg, p, precision="bf16", max_batch=16)
+    _check(cfg, p, x[:4], eng, 4)
+    cls, probs, logits, heat = eng.predict_explain(x, None, "logit")
+    h = _np(heat)
+    assert h.min() >= 0.0 and h.max() <= 1.0 and np.all(h.reshape(10, -1).max(axis=1) > 0.999)
+    c1, p1, l1, h1 = eng.predict_explain(x[7:8], None, "logit")
+    assert np.array_equal(_np(h1)[0], h[7]) and np.array_equal(_np(l1)[0], _np(logits)[7])      # batch-of-1 == slice
+    hc, hp, hl, hh = eng.predict_explain_host(x, None, "logit")
+    assert np.array_equal(hh, h) and np.array_equal(hc, _np(cls))
+    # fp32 path of the same model agrees within the bf16 tolerance
+    eng32 = engine_from(cfg, p, precision="fp32", max_batch=16)
+    c32, p32, l32, h32 = eng32.predict_explain(x, None, "logit")
+    assert np.abs(_np(l32) - _np(logits)).max() <= BF16_TOL * max(1.0, float(l32.abs().max()))
+    assert np.abs(_np(h32) - h).max() <= BF16_TOL
+    eng.close()
+    eng32.close()

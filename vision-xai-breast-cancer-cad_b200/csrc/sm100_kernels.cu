@@ -1,0 +1,564 @@
+// bf16 tensor-core path (sm_100a): tcgen05.mma with TMEM accumulators, operands staged in shared memory by
+// the bulk-copy (TMA) engine, warp-specialised persistent kernels.
+//
+// Device-internal layouts (all ours, chosen so every transfer is a contiguous bulk copy and every UMMA operand
+// is a canonical K-major image with no data reshuffling):
+//   "C8 planar" activations   X[b][y][c/8][x][8] bf16   -- one (row, channel-octet) plane is x-contiguous 16 B items
+//   conv weights image        [tap*(Cin/8)+chunk][cout][8] bf16  -- no-swizzle core matrices (8 couts x 16 B)
+//   fc1 A tiles (pooled act.) [b/128][pooled pixel][b%128][128 B, 16 B chunks XOR (row&7)]  -- SW128 K-major
+//   fc1 W tiles               [pooled pixel][unit][128 B, chunks XOR (unit&7)]               -- SW128 K-major
+//
+// Reference semantics: conv+bias+LeakyReLU+2x2 max-pool (Classes/CNNModel.py:227-261, ADCNNM.py:48,76),
+// dense z = W.flat + b (Classes/CNNModel.py:180); Grad-CAM channel reduction (pytorch_grad_cam, GRADCAM.py:64).
+#include "../../include/bcad.h"
+#include "common.cuh"
+#include "sm100.cuh"
+#include "sm100_kernels.h"
+
+namespace bcad {
+
+using namespace sm100;
+
+// =====================================================================================================
+// first conv block (Cin = 1, 3x3): CUDA cores, fused bias + LeakyReLU + 2x2 max-pool, bf16 C8-planar out.
+// K = 9 is too skinny for the tensor core; the block is ~6 % of the network's MACs.
+// block = 2 pooled rows x 128 pooled columns; thread = one pooled pixel, loops over channel octets.
+// =====================================================================================================
+template <int COUT>
+__global__ void __launch_bounds__(256)
+conv_first_pool_kernel(const float* __restrict__ x, const float* __restrict__ w /*[9][COUT]*/,
+                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W, int pad, int Hp,
+                       int Wp, float alpha) {
+    __shared__ __align__(16) float s_w[9 * COUT];
+    __shared__ float s_b[COUT];
+    for (int i = threadIdx.x; i < 9 * COUT; i += 256) s_w[i] = w[i];
+    for (int i = threadIdx.x; i < COUT; i += 256) s_b[i] = bias[i];
+    __syncthreads();
+    const int b = blockIdx.z;
+    const int px = blockIdx.x * 128 + (threadIdx.x & 127);
+    const int py = blockIdx.y * 2 + (threadIdx.x >> 7);
+    if (px >= Wp || py >= Hp) return;
+    const float* xb = x + (size_t)b * H * W;
+    float in[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int iy = 2 * py - pad + r;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int ix = 2 * px - pad + c;
+            in[r][c] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xb + (size_t)iy * W + ix) : 0.f;
+        }
+    }
+#pragma unroll 1
+    for (int oc = 0; oc < COUT / 8; ++oc) {
+        float acc[4][8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float4 w0 = *reinterpret_cast<const float4*>(&s_w[(ky * 3 + kx) * COUT + oc * 8]);
+                const float4 w1 = *reinterpret_cast<const float4*>(&s_w[(ky * 3 + kx) * COUT + oc * 8 + 4]);
+                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float v = in[(q >> 1) + ky][(q & 1) + kx];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[q][j] = fmaf(v, wv[j], acc[q][j]);
+                }
+            }
+        // max-pool commutes with the monotone bias + LeakyReLU (alpha >= 0): pool first, activate once
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            float m0 = fmaxf(fmaxf(acc[0][j], acc[1][j]), fmaxf(acc[2][j], acc[3][j])) + s_b[oc * 8 + j];
+            float m1 = fmaxf(fmaxf(acc[0][j + 1], acc[1][j + 1]), fmaxf(acc[2][j + 1], acc[3][j + 1])) + s_b[oc * 8 + j + 1];
+            pk[j >> 1] = pack_bf16(leaky(m0, alpha), leaky(m1, alpha));
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out) + (((size_t)b * Hp + py) * (COUT / 8) + oc) * Wp + px;
+        *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
+int launch_conv_first_pool(const float* x, const float* w9c, const float* bias, __nv_bfloat16* out, int B, int H, int W,
+                           int pad, int Cout, float alpha, cudaStream_t s) {
+    const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2, Hp = Ho / 2, Wp = Wo / 2;
+    dim3 grid(cdiv(Wp, 128), cdiv(Hp, 2), B);
+    switch (Cout) {
+        case 16: conv_first_pool_kernel<16><<<grid, 256, 0, s>>>(x, w9c, bias, out, H, W, pad, Hp, Wp, alpha); break;
+        case 32: conv_first_pool_kernel<32><<<grid, 256, 0, s>>>(x, w9c, bias, out, H, W, pad, Hp, Wp, alpha); break;
+        case 64: conv_first_pool_kernel<64><<<grid, 256, 0, s>>>(x, w9c, bias, out, H, W, pad, Hp, Wp, alpha); break;
+        default: set_error("conv_first_pool: Cout %d not supported (16/32/64)", Cout); return BCAD_ERR_INVALID;
+    }
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+// =====================================================================================================
+// 3x3 convolution as implicit GEMM on tcgen05 (Cin in {16,32,64}, Cout = 64, map width <= 128)
+//
+//   M = 128 consecutive pixels of one output row, N = Cout, K = 9 taps x Cin.
+//   Input rows live in a shared-memory ring in C8-planar order (pixels 16 B apart), so the A operand of tap
+//   (dy,dx) is just the ring row (y+dy) with the descriptor start address advanced by dx*16 bytes: no im2col
+//   copy, every input row is fetched from L2/HBM exactly once per band.  Zero padding = two halo pixel slots
+//   that are never written + a permanently-zero row slot.
+//   Output rows are produced in pairs so the 2x2 max-pool happens in the epilogue (vertical max in registers,
+//   horizontal max with one shuffle); accumulators are double-buffered in TMEM so the epilogue of pair p
+//   overlaps the MMAs of pair p+1.
+//   Warp roles: 0 = bulk-copy producer, 1 = MMA issuer, 2..5 = epilogue (TMEM lane quadrant = warp % 4).
+// =====================================================================================================
+constexpr int IG_XP = 136;            // pixel slots per ring row (>= 128 + 2 halo, multiple of 8)
+constexpr int IG_STAGES = 4;          // ring stages of 2 input rows
+constexpr int IG_THREADS = 192;
+
+template <int CIN, int COUT>
+struct IgemmSmem {
+    static constexpr int CHUNKS = CIN / 8;
+    static constexpr int LBO = IG_XP * 16;                 // bytes between channel octets of one row
+    static constexpr int ROWB = CHUNKS * LBO;              // bytes per ring row
+    static constexpr int WBYTES = 9 * CHUNKS * COUT * 16;  // weight image
+    static constexpr int OFF_W = 0;
+    static constexpr int OFF_ZERO = OFF_W + WBYTES;
+    static constexpr int OFF_RING = OFF_ZERO + ROWB;
+    static constexpr int OFF_BIAS = OFF_RING + IG_STAGES * 2 * ROWB;
+    static constexpr int OFF_BAR = OFF_BIAS + COUT * 4;
+    static constexpr int TOTAL = OFF_BAR + 256;
+};
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) {
+    using L = IgemmSmem<CIN, COUT>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* s_w = smem + L::OFF_W;
+    uint8_t* s_zero = smem + L::OFF_ZERO;
+    uint8_t* s_ring = smem + L::OFF_RING;
+    float* s_bias = reinterpret_cast<float*>(smem + L::OFF_BIAS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+    uint64_t* full = bars;                       // [IG_STAGES] producer -> MMA
+    uint64_t* empty = bars + IG_STAGES;          // [IG_STAGES] MMA -> producer
+    uint64_t* tfull = bars + 2 * IG_STAGES;      // [2] MMA -> epilogue
+    uint64_t* tempty = bars + 2 * IG_STAGES + 2; // [2] epilogue -> MMA
+    uint64_t* wbar = bars + 2 * IG_STAGES + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * IG_STAGES + 5);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // ---- one-time setup: zero the halo slots + zero row, barriers, TMEM
+    for (int i = tid; i < (L::ROWB * (1 + IG_STAGES * 2)) / 16; i += IG_THREADS)
+        reinterpret_cast<uint4*>(s_zero)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < COUT; i += IG_THREADS) s_bias[i] = a.bias[i];
+    if (tid == 0) {
+        for (int i = 0; i < IG_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        mbar_init(wbar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(tmem_slot, 256);
+        tmem_relinquish();
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int n_items = a.B * a.bands;
+    const int in_row_elems = L::CHUNKS * a.W * 8;          // bf16 elements per input row (all channel octets)
+
+    if (warp == 0) {
+        // ================================ producer ================================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(wbar, L::WBYTES);
+            for (int off = 0; off < L::WBYTES; off += 16384)
+                bulk_g2s(s_w + off, a.w_img + off, min(16384, L::WBYTES - off), wbar);
+            uint32_t g = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int b = item / a.bands, band = item % a.bands;
+                const int y0 = band * a.band_rows;
+                const int nrows = min(a.band_rows, a.Ho - y0);
+                const int nstages = (nrows + 1) / 2 + 1;
+                const __nv_bfloat16* inb = a.in + (size_t)b * a.H * in_row_elems;
+                for (int q = 0; q < nstages; ++q, ++g) {
+                    const uint32_t slot = g % IG_STAGES;
+                    if (g >= IG_STAGES) mbar_wait(&empty[slot], ((g / IG_STAGES) - 1) & 1);
+                    uint32_t bytes = 0;
+                    for (int r = 0; r < 2; ++r) {
+                        const int in_row = y0 - a.pad + 2 * q + r;
+                        if (in_row >= 0 && in_row < a.H) bytes += L::CHUNKS * a.W * 16;
+                    }
+                    if (bytes) mbar_arrive_expect_tx(&full[slot], bytes);
+                    else mbar_arrive(&full[slot]);
+                    for (int r = 0; r < 2; ++r) {
+                        const int in_row = y0 - a.pad + 2 * q + r;
+                        if (in_row < 0 || in_row >= a.H) continue;
+                        uint8_t* dst = s_ring + (slot * 2 + r) * L::ROWB + a.pad * 16;
+                        const __nv_bfloat16* src = inb + (size_t)in_row * in_row_elems;
+                        for (int c = 0; c < L::CHUNKS; ++c)
+                            bulk_g2s(dst + c * L::LBO, src + (size_t)c * a.W * 8, a.W * 16, &full[slot]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, COUT);
+            mbar_wait(wbar, 0);
+            uint32_t g = 0, acc_it = 0;
+            const uint32_t w_base = smem_u32(s_w), zero_base = smem_u32(s_zero), ring_base = smem_u32(s_ring);
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int band = item % a.bands;
+                const int y0 = band * a.band_rows;
+                const int nrows = min(a.band_rows, a.Ho - y0);
+                const int npairs = (nrows + 1) / 2;
+                for (int p = 0; p < npairs; ++p, ++g, ++acc_it) {
+                    if (p == 0) mbar_wait(&full[g % IG_STAGES], (g / IG_STAGES) & 1);
+                    mbar_wait(&full[(g + 1) % IG_STAGES], ((g + 1) / IG_STAGES) & 1);
+                    const uint32_t j = acc_it & 1;
+                    if (acc_it >= 2) mbar_wait(&tempty[j], ((acc_it >> 1) - 1) & 1);
+                    tc_fence_after();
+                    for (int r = 0; r < 2; ++r) {
+                        if (2 * p + r >= nrows) break;
+                        const uint32_t d_tmem = tmem + j * (2 * COUT) + r * COUT;
+                        uint32_t acc = 0;
+                        for (int dy = 0; dy < 3; ++dy) {
+                            const int i = 2 * p + r + dy;                    // band-local input row
+                            const int in_row = y0 - a.pad + i;
+                            uint32_t row_base;
+                            if (in_row < 0 || in_row >= a.H) row_base = zero_base;
+                            else row_base = ring_base + (((g + (i >> 1) - p) % IG_STAGES) * 2 + (i & 1)) * L::ROWB;
+#pragma unroll
+                            for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                                for (int ks = 0; ks < CIN / 16; ++ks) {
+                                    const uint64_t ad = make_smem_desc(row_base + ks * 2 * L::LBO + dx * 16, L::LBO, 128, LAYOUT_NONE);
+                                    const uint64_t bd = make_smem_desc(w_base + ((dy * 3 + dx) * L::CHUNKS + 2 * ks) * (COUT * 16),
+                                                                       COUT * 16, 128, LAYOUT_NONE);
+                                    umma_bf16(d_tmem, ad, bd, idesc, acc);
+                                    acc = 1;
+                                }
+                        }
+                    }
+                    umma_commit(&empty[g % IG_STAGES]);      // stage p is dead once these MMAs retire
+                    umma_commit(&tfull[j]);
+                }
+                umma_commit(&empty[g % IG_STAGES]);          // the band's last stage
+                ++g;
+            }
+        }
+    } else {
+        // ================================ epilogue (4 warps) ================================
+        const int quad = warp & 3;
+        const int x = quad * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+        uint32_t acc_it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int b = item / a.bands, band = item % a.bands;
+            const int y0 = band * a.band_rows;
+            const int nrows = min(a.band_rows, a.Ho - y0);
+            const int npairs = (nrows + 1) / 2;
+            for (int p = 0; p < npairs; ++p, ++acc_it) {
+                const uint32_t j = acc_it & 1;
+                mbar_wait(&tfull[j], (acc_it >> 1) & 1);
+                tc_fence_after();
+                const int t0 = y0 + 2 * p;
+                const bool has1 = (2 * p + 1 < nrows);
+                const int py = t0 >> 1, px = x >> 1;
+                const bool pool_ok = has1 && py < a.Hp && px < a.Wp && !(x & 1);
+#pragma unroll 1
+                for (int half = 0; half < COUT / 32; ++half) {
+                    float v0[32], v1[32];
+                    tmem_ld32(tmem + lane_off + j * (2 * COUT) + half * 32, v0);
+                    tmem_ld32(tmem + lane_off + j * (2 * COUT) + COUT + half * 32, v1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        const float bq = s_bias[half * 32 + q];
+                        v0[q] = leaky(v0[q] + bq, a.alpha);
+                        v1[q] = leaky(v1[q] + bq, a.alpha);
+                    }
+                    if (a.act != nullptr && x < a.Wo) {
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {
+                            const int chunk = half * 4 + cc;
+                            uint4* d0 = reinterpret_cast<uint4*>(a.act) + (((size_t)b * a.Ho + t0) * (COUT / 8) + chunk) * a.Wo + x;
+                            *d0 = make_uint4(pack_bf16(v0[cc * 8], v0[cc * 8 + 1]), pack_bf16(v0[cc * 8 + 2], v0[cc * 8 + 3]),
+                                             pack_bf16(v0[cc * 8 + 4], v0[cc * 8 + 5]), pack_bf16(v0[cc * 8 + 6], v0[cc * 8 + 7]));
+                            if (has1) {
+                                uint4* d1 = d0 + (size_t)(COUT / 8) * a.Wo;
+                                *d1 = make_uint4(pack_bf16(v1[cc * 8], v1[cc * 8 + 1]), pack_bf16(v1[cc * 8 + 2], v1[cc * 8 + 3]),
+                                                 pack_bf16(v1[cc * 8 + 4], v1[cc * 8 + 5]), pack_bf16(v1[cc * 8 + 6], v1[cc * 8 + 7]));
+                            }
+                        }
+                    }
+                    // 2x2 max-pool: vertical in registers, horizontal with the neighbouring lane
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        const float m = fmaxf(v0[q], v1[q]);
+                        v0[q] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                    }
+                    if (pool_ok) {
+                        if (a.pool_fc != nullptr) {
+                            // fc1 A-operand tile: [b/128][pooled pixel][b%128][128 B], chunk index XOR (row & 7)
+                            const int row = b & 127;
+                            uint8_t* base = a.pool_fc + ((((size_t)(b >> 7) * a.Hp * a.Wp) + (size_t)py * a.Wp + px) * 128 + row) * 128;
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc) {
+                                const int chunk = (half * 4 + cc) ^ (row & 7);
+                                *reinterpret_cast<uint4*>(base + chunk * 16) =
+                                    make_uint4(pack_bf16(v0[cc * 8], v0[cc * 8 + 1]), pack_bf16(v0[cc * 8 + 2], v0[cc * 8 + 3]),
+                                               pack_bf16(v0[cc * 8 + 4], v0[cc * 8 + 5]), pack_bf16(v0[cc * 8 + 6], v0[cc * 8 + 7]));
+                            }
+                        }
+                        if (a.pool_c8 != nullptr) {
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc) {
+                                const int chunk = half * 4 + cc;
+                                uint4* d = reinterpret_cast<uint4*>(a.pool_c8) + (((size_t)b * a.Hp + py) * (COUT / 8) + chunk) * a.Wp + px;
+                                *d = make_uint4(pack_bf16(v0[cc * 8], v0[cc * 8 + 1]), pack_bf16(v0[cc * 8 + 2], v0[cc * 8 + 3]),
+                                                pack_bf16(v0[cc * 8 + 4], v0[cc * 8 + 5]), pack_bf16(v0[cc * 8 + 6], v0[cc * 8 + 7]));
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[j]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+template <int CIN, int COUT>
+static int launch_igemm_t(const IgemmArgs& a, int sms, cudaStream_t s) {
+    using L = IgemmSmem<CIN, COUT>;
+    BCAD_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    const int items = a.B * a.bands;
+    const int grid = items < sms ? items : sms;
+    conv_igemm_kernel<CIN, COUT><<<grid, IG_THREADS, L::TOTAL, s>>>(a);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+int launch_conv_igemm(const IgemmArgs& a, int Cin, int Cout, int sms, cudaStream_t s) {
+    BCAD_REQUIRE(a.W <= 128 && a.Wo <= 128, "conv_igemm: map width %d > 128", a.W);
+    BCAD_REQUIRE(a.band_rows % 2 == 0, "conv_igemm: band_rows must be even");
+    if (Cout == 64) {
+        if (Cin == 16) return launch_igemm_t<16, 64>(a, sms, s);
+        if (Cin == 32) return launch_igemm_t<32, 64>(a, sms, s);
+        if (Cin == 64) return launch_igemm_t<64, 64>(a, sms, s);
+    }
+    set_error("conv_igemm: Cin=%d Cout=%d not supported (Cin 16/32/64, Cout 64)", Cin, Cout);
+    return BCAD_ERR_INVALID;
+}
+
+// =====================================================================================================
+// fc1 as a split-K GEMM on tcgen05:  partial[split][m][n] = sum_{k in split} A[m][k] W[n][k]
+//   CTA tile 128 (images) x N (units, <= 256) x 64 (one pooled pixel's channels) per k-block; both operands
+//   arrive as ready-made SW128 tiles via one bulk copy each; 4-stage ring; warp roles as above.
+// =====================================================================================================
+constexpr int FC_STAGES = 4;
+constexpr int FC_THREADS = 192;
+
+__global__ void __launch_bounds__(FC_THREADS, 1) fc_splitk_kernel(FcArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // dynamic smem base is 1024-aligned by declaration; SW128 tiles need it
+    uint8_t* smem = smem_raw;
+    const int a_tile = 128 * 128, w_tile = a.N * 128, stage_bytes = a_tile + w_tile;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FC_STAGES * stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + FC_STAGES;
+    uint64_t* done = bars + 2 * FC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * FC_STAGES + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < FC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(tmem_slot, 256);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int split = blockIdx.x, mt = blockIdx.y;
+    const int kb0 = split * a.kb_per_split, kb1 = min(a.nkb, kb0 + a.kb_per_split);
+    const int nk = kb1 - kb0;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < nk; ++i) {
+                const int st = i % FC_STAGES;
+                if (i >= FC_STAGES) mbar_wait(&empty[st], ((i / FC_STAGES) - 1) & 1);
+                mbar_arrive_expect_tx(&full[st], stage_bytes);
+                uint8_t* sa = smem + st * stage_bytes;
+                bulk_g2s(sa, a.a_tiles + ((size_t)mt * a.nkb + kb0 + i) * a_tile, a_tile, &full[st]);
+                const uint8_t* wsrc = a.w_tiles + (size_t)(kb0 + i) * w_tile;
+                for (int off = 0; off < w_tile; off += 16384)
+                    bulk_g2s(sa + a_tile + off, wsrc + off, min(16384, w_tile - off), &full[st]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, a.N);
+            for (int i = 0; i < nk; ++i) {
+                const int st = i % FC_STAGES;
+                mbar_wait(&full[st], (i / FC_STAGES) & 1);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + st * stage_bytes), sw = sa + a_tile;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t ad = make_smem_desc(sa + k * 32, 16, 1024, LAYOUT_SW128);
+                    const uint64_t bd = make_smem_desc(sw + k * 32, 16, 1024, LAYOUT_SW128);
+                    umma_bf16(tmem, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty[st]);
+            }
+            umma_commit(done);
+        }
+    } else {
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        float* dst = a.partials + ((size_t)split * a.m_pad + (size_t)mt * 128 + row) * a.N;
+        if (nk > 0) {
+            mbar_wait(done, 0);
+            tc_fence_after();
+            for (int c0 = 0; c0 < a.N; c0 += 32) {
+                float v[32];
+                tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 32; q += 4)
+                    *reinterpret_cast<float4*>(dst + c0 + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+            }
+        } else {
+            for (int c0 = 0; c0 < a.N; c0 += 4) *reinterpret_cast<float4*>(dst + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+int launch_fc_splitk(const FcArgs& a, cudaStream_t s) {
+    BCAD_REQUIRE(a.N % 16 == 0 && a.N >= 16 && a.N <= 256, "fc_splitk: N=%d must be a multiple of 16 in 16..256", a.N);
+    const int stage_bytes = 128 * 128 + a.N * 128;
+    const int smem = FC_STAGES * stage_bytes + 256;
+    BCAD_CUDA_CHECK(cudaFuncSetAttribute(fc_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    dim3 grid(a.splits, a.m_tiles);
+    fc_splitk_kernel<<<grid, FC_THREADS, smem, s>>>(a);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+// z[m][n] = sum_s partial[s][m][n] + bias[n] (fixed order), h = LeakyReLU(z); partial rows padded to m_pad
+__global__ void fc_reduce_kernel(const float* __restrict__ part, int splits, size_t ld_split, const float* __restrict__ bias,
+                                 float* __restrict__ z, float* __restrict__ h, float alpha, int M, int N) {
+    const size_t total = (size_t)M * N;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        float v = 0.f;
+        for (int s = 0; s < splits; ++s) v += part[(size_t)s * ld_split + i];
+        v += __ldg(bias + (i % N));
+        z[i] = v;
+        if (h != nullptr) h[i] = leaky(v, alpha);
+    }
+}
+
+int launch_fc_reduce(const float* part, int splits, size_t ld_split, const float* bias, float* z, float* h, float alpha,
+                     int M, int N, cudaStream_t s) {
+    const size_t total = (size_t)M * N;
+    const int blocks = (int)min((size_t)2048, (total + 255) / 256);
+    fc_reduce_kernel<<<blocks, 256, 0, s>>>(part, splits, ld_split, bias, z, h, alpha, M, N);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+// =====================================================================================================
+// Grad-CAM channel reduction on C8-planar bf16 activations: cam = ReLU(sum_k alpha_k A_k) + min/max partials
+// grid (splits, B), 256 threads, thread = pixel; every load is a coalesced 16 B per lane.
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+cam_c8_kernel(const __nv_bfloat16* __restrict__ A, const float* __restrict__ alpha_raw, float scale,
+              float* __restrict__ alpha_out, float* __restrict__ cam_lo, float* __restrict__ mm, int h, int w, int C) {
+    extern __shared__ float s_alpha[];
+    __shared__ float s_min[8], s_max[8];
+    const int b = blockIdx.y, split = blockIdx.x, splits = gridDim.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float t = alpha_raw[(size_t)b * C + c] * scale;
+        s_alpha[c] = t;
+        if (alpha_out != nullptr && split == 0) alpha_out[(size_t)b * C + c] = t;
+    }
+    __syncthreads();
+    const int rows_per = cdiv(h, splits);
+    const int y0 = split * rows_per, y1 = min(h, y0 + rows_per);
+    const int chunks = C / 8;
+    float vmin = 3.4e38f, vmax = -3.4e38f;
+    const uint4* base = reinterpret_cast<const uint4*>(A) + (size_t)b * h * chunks * w;
+    const int npix = (y1 - y0) * w;
+    for (int i = threadIdx.x; i < npix; i += blockDim.x) {
+        const int y = y0 + i / w, x = i % w;
+        float acc = 0.f;
+        const uint4* p = base + ((size_t)y * chunks) * w + x;
+        for (int c = 0; c < chunks; ++c) {
+            const uint4 q = ldg_stream_u4(p + (size_t)c * w);
+            const float* al = s_alpha + c * 8;
+            acc = fmaf(bf16lo(q.x), al[0], acc); acc = fmaf(bf16hi(q.x), al[1], acc);
+            acc = fmaf(bf16lo(q.y), al[2], acc); acc = fmaf(bf16hi(q.y), al[3], acc);
+            acc = fmaf(bf16lo(q.z), al[4], acc); acc = fmaf(bf16hi(q.z), al[5], acc);
+            acc = fmaf(bf16lo(q.w), al[6], acc); acc = fmaf(bf16hi(q.w), al[7], acc);
+        }
+        acc = fmaxf(acc, 0.f);
+        cam_lo[((size_t)b * h + y) * w + x] = acc;
+        vmin = fminf(vmin, acc);
+        vmax = fmaxf(vmax, acc);
+    }
+    vmin = warp_min(vmin);
+    vmax = warp_max(vmax);
+    if ((threadIdx.x & 31) == 0) { s_min[threadIdx.x >> 5] = vmin; s_max[threadIdx.x >> 5] = vmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < 8; ++q) { vmin = fminf(vmin, s_min[q]); vmax = fmaxf(vmax, s_max[q]); }
+        mm[((size_t)b * splits + split) * 2 + 0] = vmin;
+        mm[((size_t)b * splits + split) * 2 + 1] = vmax;
+    }
+}
+
+int launch_cam_c8(const __nv_bfloat16* A, const float* alpha_raw, float scale, float* alpha_out, float* cam_lo, float* mm,
+                  int B, int h, int w, int C, int splits, cudaStream_t s) {
+    dim3 grid(splits, B);
+    cam_c8_kernel<<<grid, 256, C * sizeof(float), s>>>(A, alpha_raw, scale, alpha_out, cam_lo, mm, h, w, C);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+// C8-planar bf16 [B][h][C/8][w][8] -> NHWC fp32 (compat / inspection only)
+__global__ void c8_to_nhwc_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int h, int w, int C, size_t total) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        size_t r = i / C;
+        const int x = (int)(r % w); r /= w;
+        const int y = (int)(r % h);
+        const size_t b = r / h;
+        dst[i] = __bfloat162float(src[((((b * h + y) * (C / 8) + (c >> 3)) * w + x) << 3) + (c & 7)]);
+    }
+}
+
+int launch_c8_to_nhwc(const __nv_bfloat16* src, float* dst, int B, int h, int w, int C, cudaStream_t s) {
+    const size_t total = (size_t)B * h * w * C;
+    const int blocks = (int)min((size_t)148 * 16, (total + 255) / 256);
+    c8_to_nhwc_kernel<<<blocks, 256, 0, s>>>(src, dst, h, w, C, total);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+}  // namespace bcad

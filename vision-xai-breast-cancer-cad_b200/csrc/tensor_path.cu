@@ -1,17 +1,218 @@
-// bf16 tcgen05 path -- placeholder until the sm_100a kernels land (create() with BCAD_PREC_BF16 is refused).
+// Orchestration of the bf16 tcgen05 path: eligibility, weight packing, per-chunk forward and explain.
+//
+// Pipeline per chunk of n images (n <= max_batch):
+//   conv_first_pool  (CUDA cores, Cin=1)      x fp32 NHWC          -> P1 bf16 C8-planar
+//   conv_igemm       (tcgen05)                P1                   -> A (target activations, bf16 C8-planar)
+//                                                                     + pooled map as fc1 A-operand tiles
+//   fc_splitk        (tcgen05) + fc_reduce    tiles x W1 tiles     -> z1, h1            (fp32)
+//   remaining dense layers, head              (small fp32 kernels shared with the fp32 path)
+//   explain: top gradient -> dense backward to dz1 -> alpha = dz1 . S / (h w)  with S[u][k] = sum_pixels W1[u][pixel,k]
+//            (exact for first-index pooling: the un-pooled gradient of a window sums to the pooled gradient, so the
+//             dense gradient map dA never has to exist -- SURVEY P8), cam_c8 -> upsample_norm.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/bcad.h"
 #include "common.cuh"
+#include "kernels.h"
 #include "model.h"
+#include "sm100_kernels.h"
 
 namespace bcad {
 
-int tensor_path_supported(const Model&) {
-    set_error("precision=BF16: the tcgen05 path is not built into this libbcad yet; use BCAD_PREC_FP32");
-    return BCAD_ERR_INVALID;
+struct TensorPath {
+    int sms = 148;
+    float* d_w0 = nullptr;          // first conv weights [9][Cout0] fp32
+    float* d_b0 = nullptr;
+    uint8_t* d_w1_img = nullptr;    // igemm weight image
+    float* d_b1 = nullptr;
+    uint8_t* d_fc_w = nullptr;      // fc1 W tiles
+    float* d_S = nullptr;           // [units][Cout] fp32: per-channel column sums of fc1 (alpha shortcut)
+    __nv_bfloat16* p1 = nullptr;    // conv0 pooled, C8 planar
+    __nv_bfloat16* act = nullptr;   // conv1 output, C8 planar
+    uint8_t* fc_a = nullptr;        // pooled conv1 as fc1 A tiles
+    float* fc_part = nullptr;
+    float* alpha_raw = nullptr;     // [B][Cout] = dz1 . S
+    int fc_splits = 1, kb_per_split = 1, m_pad = 128;
+};
+
+#define TP_TRY(expr) do { int _rc = (expr); if (_rc != BCAD_OK) return _rc; } while (0)
+#define TP_LAUNCH(m, name, expr) do { int _rc = (m).mark(name, s); if (_rc == BCAD_OK) _rc = (expr); if (_rc != BCAD_OK) return _rc; (m).launches += 1; } while (0)
+
+static uint16_t f2bf(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
+    u += 0x7fffu + ((u >> 16) & 1);                                            // round to nearest even
+    return (uint16_t)(u >> 16);
 }
-int tensor_path_commit(Model&) { return BCAD_ERR_STATE; }
-int tensor_forward_chunk(Model&, const float*, int, cudaStream_t) { return BCAD_ERR_STATE; }
-int tensor_explain_chunk(Model&, int, const int32_t*, int, float*, cudaStream_t) { return BCAD_ERR_STATE; }
-int tensor_get_activation(Model&, int, int, int, float*, cudaStream_t) { return BCAD_ERR_STATE; }
-void tensor_path_destroy(Model&) {}
+
+int tensor_path_supported(const Model& m) {
+    const bcad_config& c = m.cfg;
+    BCAD_REQUIRE(m.conv.size() == 2, "precision=BF16: the tensor path covers 2 conv blocks (got %zu); use BCAD_PREC_FP32", m.conv.size());
+    const ConvLayer& c0 = m.conv[0];
+    const ConvLayer& c1 = m.conv[1];
+    BCAD_REQUIRE(c0.Cin == 1 && c0.k == 3 && (c0.Cout == 16 || c0.Cout == 32 || c0.Cout == 64),
+                 "precision=BF16: first conv block must be 1 -> 16/32/64 channels, 3x3 (got %d -> %d, k=%d)", c0.Cin, c0.Cout, c0.k);
+    BCAD_REQUIRE(c1.k == 3 && c1.Cout == 64, "precision=BF16: second conv block must be 3x3 with 64 filters (got k=%d, %d)", c1.k, c1.Cout);
+    BCAD_REQUIRE(c1.W <= 128, "precision=BF16: second conv block input width %d > 128", c1.W);
+    BCAD_REQUIRE(c.pad == 0 || c.pad == 1, "precision=BF16: pad must be 0 or 1");
+    BCAD_REQUIRE(c.pool_ties == BCAD_TIES_FIRST,
+                 "precision=BF16: the alpha shortcut needs first-index pooling (TIES_FIRST); the tie-duplicating NumPy flavour runs on BCAD_PREC_FP32");
+    const int units = m.dense[0].out;
+    BCAD_REQUIRE(units % 16 == 0 && units <= 256, "precision=BF16: first dense layer must have a multiple of 16 units <= 256 (got %d)", units);
+    return BCAD_OK;
+}
+
+int tensor_path_commit(Model& m) {
+    if (m.tp == nullptr) m.tp = new TensorPath();
+    TensorPath& t = *m.tp;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&t.sms, cudaDevAttrMultiProcessorCount, dev);
+    const ConvLayer& c0 = m.conv[0];
+    const ConvLayer& c1 = m.conv[1];
+    DenseLayer& d0 = m.dense[0];
+    const int mb = m.cfg.max_batch;
+    // ---- conv0: [9][Cout] fp32
+    {
+        std::vector<float> w((size_t)9 * c0.Cout);
+        for (int f = 0; f < c0.Cout; ++f)
+            for (int tap = 0; tap < 9; ++tap) w[(size_t)tap * c0.Cout + f] = c0.h_w[(size_t)f * 9 + tap];
+        if (!t.d_w0) TP_TRY(m.alloc((void**)&t.d_w0, w.size() * 4));
+        if (!t.d_b0) TP_TRY(m.alloc((void**)&t.d_b0, c0.Cout * 4));
+        BCAD_CUDA_CHECK(cudaMemcpy(t.d_w0, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+        BCAD_CUDA_CHECK(cudaMemcpy(t.d_b0, c0.h_b.data(), c0.Cout * 4, cudaMemcpyHostToDevice));
+    }
+    // ---- conv1 weight image: [tap*(Cin/8)+chunk][cout][8] bf16
+    {
+        const int chunks = c1.Cin / 8;
+        std::vector<uint16_t> img((size_t)9 * chunks * c1.Cout * 8);
+        for (int tap = 0; tap < 9; ++tap)
+            for (int ch = 0; ch < chunks; ++ch)
+                for (int f = 0; f < c1.Cout; ++f)
+                    for (int e = 0; e < 8; ++e)
+                        img[(((size_t)tap * chunks + ch) * c1.Cout + f) * 8 + e] =
+                            f2bf(c1.h_w[((size_t)f * 9 + tap) * c1.Cin + ch * 8 + e]);
+        if (!t.d_w1_img) TP_TRY(m.alloc((void**)&t.d_w1_img, img.size() * 2));
+        if (!t.d_b1) TP_TRY(m.alloc((void**)&t.d_b1, c1.Cout * 4));
+        BCAD_CUDA_CHECK(cudaMemcpy(t.d_w1_img, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+        BCAD_CUDA_CHECK(cudaMemcpy(t.d_b1, c1.h_b.data(), c1.Cout * 4, cudaMemcpyHostToDevice));
+    }
+    // ---- fc1: SW128 tiles [pixel][unit][128 B]; K index inside a tile = channel; S = per-channel column sums
+    {
+        const int npix = c1.Hp * c1.Wp, N = d0.out, C = c1.Cout;
+        std::vector<uint16_t> tiles((size_t)npix * N * 64);
+        std::vector<double> S((size_t)N * C, 0.0);
+        for (int u = 0; u < N; ++u) {
+            const float* row = d0.h_w.data() + (size_t)u * d0.in;          // device (NHWC) column order: pixel*C + c
+            for (int pp = 0; pp < npix; ++pp) {
+                uint16_t* dst = tiles.data() + ((size_t)pp * N + u) * 64;
+                for (int cidx = 0; cidx < C; ++cidx) {
+                    const float v = row[(size_t)pp * C + cidx];
+                    const int chunk = (cidx >> 3) ^ (u & 7);
+                    const uint16_t q = f2bf(v);
+                    dst[chunk * 8 + (cidx & 7)] = q;
+                    uint32_t bits = (uint32_t)q << 16;                     // S uses the bf16-rounded weights the GEMM sees
+                    float vq;
+                    memcpy(&vq, &bits, 4);
+                    S[(size_t)u * C + cidx] += vq;
+                }
+            }
+        }
+        std::vector<float> Sf(S.begin(), S.end());
+        if (!t.d_fc_w) TP_TRY(m.alloc((void**)&t.d_fc_w, tiles.size() * 2));
+        if (!t.d_S) TP_TRY(m.alloc((void**)&t.d_S, Sf.size() * 4));
+        BCAD_CUDA_CHECK(cudaMemcpy(t.d_fc_w, tiles.data(), tiles.size() * 2, cudaMemcpyHostToDevice));
+        BCAD_CUDA_CHECK(cudaMemcpy(t.d_S, Sf.data(), Sf.size() * 4, cudaMemcpyHostToDevice));
+    }
+    // ---- workspace
+    if (t.p1 == nullptr) {
+        t.m_pad = cdiv(mb, 128) * 128;
+        const int npix = c1.Hp * c1.Wp;
+        const int m_tiles = t.m_pad / 128;
+        int splits = cdiv(t.sms, m_tiles);
+        if (splits > npix) splits = npix;
+        t.kb_per_split = cdiv(npix, splits);
+        t.fc_splits = cdiv(npix, t.kb_per_split);
+        TP_TRY(m.alloc((void**)&t.p1, (size_t)mb * c0.Hp * c0.Wp * c0.Cout * 2));
+        TP_TRY(m.alloc((void**)&t.act, (size_t)mb * c1.Ho * c1.Wo * c1.Cout * 2));
+        TP_TRY(m.alloc((void**)&t.fc_a, (size_t)t.m_pad * npix * 128));
+        BCAD_CUDA_CHECK(cudaMemset(t.fc_a, 0, (size_t)t.m_pad * npix * 128));     // padding rows: finite zeros
+        TP_TRY(m.alloc((void**)&t.fc_part, (size_t)t.fc_splits * t.m_pad * d0.out * 4));
+        TP_TRY(m.alloc((void**)&t.alpha_raw, (size_t)mb * c1.Cout * 4));
+    }
+    return BCAD_OK;
+}
+
+void tensor_path_destroy(Model& m) {
+    delete m.tp;
+    m.tp = nullptr;
+}
+
+int tensor_forward_chunk(Model& m, const float* x, int n, cudaStream_t s) {
+    TensorPath& t = *m.tp;
+    const ConvLayer& c0 = m.conv[0];
+    const ConvLayer& c1 = m.conv[1];
+    TP_LAUNCH(m, "conv0_first_pool", launch_conv_first_pool(x, t.d_w0, t.d_b0, t.p1, n, c0.H, c0.W, m.cfg.pad, c0.Cout, m.cfg.alpha_conv, s));
+    IgemmArgs a;
+    a.in = t.p1; a.w_img = t.d_w1_img; a.bias = t.d_b1; a.act = t.act; a.pool_fc = t.fc_a; a.pool_c8 = nullptr;
+    a.B = n; a.H = c1.H; a.W = c1.W; a.Ho = c1.Ho; a.Wo = c1.Wo; a.Hp = c1.Hp; a.Wp = c1.Wp; a.pad = m.cfg.pad;
+    a.band_rows = 64;
+    if (a.band_rows > c1.Ho) a.band_rows = cdiv(c1.Ho, 2) * 2;
+    a.bands = cdiv(c1.Ho, a.band_rows);
+    a.alpha = m.cfg.alpha_conv;
+    TP_LAUNCH(m, "conv1_igemm_tcgen05", launch_conv_igemm(a, c1.Cin, c1.Cout, t.sms, s));
+    // fc1
+    DenseLayer& d0 = m.dense[0];
+    FcArgs f;
+    f.a_tiles = t.fc_a; f.w_tiles = t.d_fc_w; f.partials = t.fc_part;
+    f.N = d0.out; f.nkb = c1.Hp * c1.Wp; f.kb_per_split = t.kb_per_split; f.splits = t.fc_splits;
+    f.m_tiles = cdiv(n, 128); f.m_pad = t.m_pad;
+    TP_LAUNCH(m, "fc1_splitk_tcgen05", launch_fc_splitk(f, s));
+    const bool only = (m.dense.size() == 1);
+    TP_LAUNCH(m, "fc1_reduce", launch_fc_reduce(t.fc_part, t.fc_splits, (size_t)t.m_pad * d0.out, d0.d_b, d0.z, only ? nullptr : d0.h,
+                                                m.cfg.alpha_dense, n, d0.out, s));
+    // remaining (small) dense layers on the shared fp32 kernels
+    const float* in = d0.h;
+    for (size_t j = 1; j < m.dense.size(); ++j) {
+        DenseLayer& D = m.dense[j];
+        const bool last = (j + 1 == m.dense.size());
+        const int splits = std::min(D.splits, sgemm_pick_splits(n, D.out, D.in));
+        TP_LAUNCH(m, "sgemm", launch_sgemm(in, D.d_w, m.partials, n, D.out, D.in, true, splits, s));
+        TP_LAUNCH(m, "splitk_reduce", launch_splitk_reduce(m.partials, splits, D.d_b, D.z, last ? nullptr : D.h, m.cfg.alpha_dense, n, D.out, s));
+        in = D.h;
+    }
+    return BCAD_OK;
+}
+
+int tensor_explain_chunk(Model& m, int n, const int32_t* class_idx, int grad_mode, float* heat, cudaStream_t s) {
+    TensorPath& t = *m.tp;
+    const ConvLayer& T = m.conv.back();
+    // dense backward down to dz1 (left in dense[0].h); no fc1 dgrad GEMM, no dA
+    TP_TRY(dense_backward(&m, n, class_idx, grad_mode, nullptr, s));
+    const float* dz1 = (m.dense.size() > 1) ? m.dense[0].h : m.d_top;
+    TP_LAUNCH(m, "alpha_shortcut_sgemm", launch_sgemm(dz1, t.d_S, t.alpha_raw, n, T.Cout, m.dense[0].out, false, 1, s));
+    const float inv_hw = 1.0f / ((float)T.Ho * (float)T.Wo);
+    TP_LAUNCH(m, "cam_c8", launch_cam_c8(t.act, t.alpha_raw, inv_hw, m.alpha, m.cam_lo, m.mm, n, T.Ho, T.Wo, T.Cout, m.cam_splits, s));
+    TP_LAUNCH(m, "upsample_norm", launch_upsample_norm(m.cam_lo, m.mm, m.cam_splits, heat, n, T.Ho, T.Wo, m.cfg.in_h, m.cfg.in_w, s));
+    return BCAD_OK;
+}
+
+int tensor_get_activation(Model& m, int kind, int index, int B, float* dst, cudaStream_t s) {
+    TensorPath& t = *m.tp;
+    if (kind == BCAD_T_CONV_OUT && index == 1) {
+        const ConvLayer& L = m.conv[1];
+        return launch_c8_to_nhwc(t.act, dst, B, L.Ho, L.Wo, L.Cout, s);
+    }
+    if (kind == BCAD_T_POOL_OUT && index == 0) {
+        const ConvLayer& L = m.conv[0];
+        return launch_c8_to_nhwc(t.p1, dst, B, L.Hp, L.Wp, L.Cout, s);
+    }
+    set_error("get_tensor: the tensor path does not materialise tensor (%d,%d); use BCAD_PREC_FP32 for full activation caches", kind, index);
+    return BCAD_ERR_STATE;
+}
 
 }  // namespace bcad

@@ -125,18 +125,20 @@ class Engine:
             b = _f32c(b)
             _lib.check(self.lib.bcad_set_conv_weights(self._h, i, _ptr(w), _ptr(b)))
             if batchnorm and batchnorm.get(i) is not None:
-                g, bt, mu, var, eps = batchnorm[i]
-                _lib.check(self.lib.bcad_fold_batchnorm(self._h, i, _ptr(_f32c(g)), _ptr(_f32c(bt)),
-                                                        _ptr(_f32c(mu)), _ptr(_f32c(var)), float(eps)))
+                # keep the converted arrays alive across the call (ctypes only sees raw addresses)
+                bn = [_f32c(v) for v in batchnorm[i][:4]]
+                _lib.check(self.lib.bcad_fold_batchnorm(self._h, i, _ptr(bn[0]), _ptr(bn[1]), _ptr(bn[2]), _ptr(bn[3]),
+                                                        float(batchnorm[i][4])))
         _, prev = self.spec.shapes()
         units = list(self.spec.hidden_units) + [self.spec.num_classes]
         if len(dense_w) != len(units):
             raise ValueError(f"expected {len(units)} dense matrices, got {len(dense_w)}")
         for j, (w, b) in enumerate(zip(dense_w, dense_b)):
             w = _f32c(w)
+            b = _f32c(b)
             if w.shape != (units[j], prev):
                 raise ValueError(f"dense {j}: weights shape {w.shape} does not match {(units[j], prev)}")
-            _lib.check(self.lib.bcad_set_dense_weights(self._h, j, _ptr(w), _ptr(_f32c(b))))
+            _lib.check(self.lib.bcad_set_dense_weights(self._h, j, _ptr(w), _ptr(b)))
             prev = units[j]
         _lib.check(self.lib.bcad_commit(self._h))
         self._committed = True
