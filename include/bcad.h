@@ -40,7 +40,7 @@ extern "C" {
 #define BCAD_HEAD_LOGITS 1         /* raw logits out, probs = softmax(logits): ADCNNM.py:78, app.py:593 */
 /* cfg.precision */
 #define BCAD_PREC_FP32 0           /* fp32 CUDA-core path, any shape */
-#define BCAD_PREC_BF16 1           /* bf16 tcgen05 tensor-core path (fp32 accumulate) where the shape allows */
+#define BCAD_PREC_F16 1            /* 16-bit tcgen05 tensor-core path (fp16 operands, fp32 accumulate) where the shape allows */
 /* grad_mode: gradient injected at the network output for the explanation */
 #define BCAD_GRAD_LOGIT 0          /* d(logit_c): pytorch_grad_cam ClassifierOutputTarget, GRADCAM.py:64 */
 #define BCAD_GRAD_SOFTMAX_CE 1     /* probs - onehot(c): explainability.py:21-22 */

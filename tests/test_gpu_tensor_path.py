@@ -8,7 +8,7 @@ from util import engine_from, oracle_heatmaps, ocnn
 
 pytestmark = pytest.mark.gpu
 
-BF16_TOL = 1e-2
+F16_TOL = 1e-2
 
 
 def _np(t):
@@ -24,12 +24,12 @@ def _check(cfg, p, x, eng, B):
         lg = cache.logits.numpy()
         err_l = np.abs(_np(logits) - lg).max()
         scale = max(1.0, np.abs(lg).max())
-        assert err_l <= BF16_TOL * scale, f"logits err {err_l} (scale {scale})"
+        assert err_l <= F16_TOL * scale, f"logits err {err_l} (scale {scale})"
         margin = np.abs(lg[:, 0] - lg[:, 1])
-        safe = margin > 4 * BF16_TOL * scale
+        safe = margin > 4 * F16_TOL * scale
         assert np.array_equal(_np(cls)[safe], o_cls[safe])
         err_h = np.abs(_np(heat) - o_heat).max(axis=(1, 2))
-        assert err_h.max() <= BF16_TOL, f"heatmap err per image {err_h}"
+        assert err_h.max() <= F16_TOL, f"heatmap err per image {err_h}"
     return err_l, err_h.max()
 
 
@@ -39,7 +39,7 @@ def test_tensor_path_intermediates_small():
     cfg = ocnn.NetConfig.torch_flavour((64, 64, 1), 2, [(32, 3), (64, 3)], [64, 32], 0.01)
     p = ocnn.init_params(cfg, seed=7, bias_std=0.05)
     x = ocnn.synth_images(5, (64, 64, 1), seed=1)
-    eng = engine_from(cfg, p, precision="bf16", max_batch=8)
+    eng = engine_from(cfg, p, precision="fp16", max_batch=8)
     cls, probs, logits = eng.predict(x)
     cache = ocnn.forward(cfg, p, x)
     p1 = _np(eng.get_tensor(_lib.T_POOL_OUT, 0, 5)).reshape(5, 32, 32, 32)
@@ -51,7 +51,7 @@ def test_tensor_path_intermediates_small():
     z1 = _np(eng.get_tensor(_lib.T_DENSE_Z, 0, 5))
     want = cache.z[0].numpy()
     assert np.abs(z1 - want).max() <= 3e-2 * max(1.0, np.abs(want).max()), "fc1 split-K GEMM"
-    np.testing.assert_allclose(_np(logits), cache.logits.numpy(), rtol=0, atol=BF16_TOL * max(1.0, np.abs(cache.logits.numpy()).max()))
+    np.testing.assert_allclose(_np(logits), cache.logits.numpy(), rtol=0, atol=F16_TOL * max(1.0, np.abs(cache.logits.numpy()).max()))
     eng.close()
 
 
@@ -65,7 +65,7 @@ def test_tensor_path_torch_flavour(shape, convs, hidden, B, mb):
     cfg = ocnn.NetConfig.torch_flavour(shape, 2, convs, hidden, 0.01)
     p = ocnn.init_params(cfg, seed=7, bias_std=0.05)
     x = ocnn.synth_images(B, shape, seed=11)
-    eng = engine_from(cfg, p, precision="bf16", max_batch=mb)
+    eng = engine_from(cfg, p, precision="fp16", max_batch=mb)
     _check(cfg, p, x, eng, B)
     eng.close()
 
@@ -75,7 +75,7 @@ def test_tensor_path_valid_conv_odd_sizes():
     cfg = ocnn.NetConfig((61, 61, 1), 2, [(32, 3), (64, 3)], [32], 0.01, 0.01, 0, "hwc", "first", "softmax")
     p = ocnn.init_params(cfg, seed=5, bias_std=0.05)
     x = ocnn.synth_images(4, (61, 61, 1), seed=3)
-    eng = engine_from(cfg, p, precision="bf16", max_batch=4)
+    eng = engine_from(cfg, p, precision="fp16", max_batch=4)
     _check(cfg, p, x, eng, 4)
     eng.close()
 
@@ -85,10 +85,10 @@ def test_tensor_path_rejects_unsupported_shapes():
     from util import spec_from_cfg
     cfg = ocnn.NetConfig.numpy_flavour((32, 32, 1), 2, [(32, 3), (64, 3)], [32])        # tie-duplicating pool
     with pytest.raises(ValueError, match="TIES_FIRST"):
-        bcad_b200.Engine(spec_from_cfg(cfg), precision="bf16")
+        bcad_b200.Engine(spec_from_cfg(cfg), precision="fp16")
     cfg = ocnn.NetConfig.torch_flavour((32, 32, 3), 2, [(32, 3), (64, 3)], [32])
     with pytest.raises(ValueError):
-        bcad_b200.Engine(spec_from_cfg(cfg), precision="bf16")
+        bcad_b200.Engine(spec_from_cfg(cfg), precision="fp16")
 
 
 def test_tensor_path_full_size_canonical():
@@ -96,7 +96,7 @@ def test_tensor_path_full_size_canonical():
     cfg = ocnn.NetConfig.torch_flavour((256, 256, 1), 2, [(32, 3), (64, 3)], [256, 128], 0.01)
     p = ocnn.init_params(cfg, seed=7, bias_std=0.0)
     x = ocnn.synth_images(10, (256, 256, 1), seed=20251018)
-    eng = engine_from(cfg, p, precision="bf16", max_batch=16)
+    eng = engine_from(cfg, p, precision="fp16", max_batch=16)
     _check(cfg, p, x[:4], eng, 4)
     cls, probs, logits, heat = eng.predict_explain(x, None, "logit")
     h = _np(heat)
@@ -108,7 +108,7 @@ def test_tensor_path_full_size_canonical():
     # fp32 path of the same model agrees within the bf16 tolerance
     eng32 = engine_from(cfg, p, precision="fp32", max_batch=16)
     c32, p32, l32, h32 = eng32.predict_explain(x, None, "logit")
-    assert np.abs(_np(l32) - _np(logits)).max() <= BF16_TOL * max(1.0, float(l32.abs().max()))
-    assert np.abs(_np(h32) - h).max() <= BF16_TOL
+    assert np.abs(_np(l32) - _np(logits)).max() <= F16_TOL * max(1.0, float(l32.abs().max()))
+    assert np.abs(_np(h32) - h).max() <= F16_TOL
     eng.close()
     eng32.close()

@@ -1,10 +1,10 @@
-// bf16 tensor-core path (sm_100a): tcgen05.mma with TMEM accumulators, operands staged in shared memory by
+// 16-bit tensor-core path (sm_100a; fp16 operands, fp32 accumulation): tcgen05.mma with TMEM accumulators, operands staged in shared memory by
 // the bulk-copy (TMA) engine, warp-specialised persistent kernels.
 //
 // Device-internal layouts (all ours, chosen so every transfer is a contiguous bulk copy and every UMMA operand
 // is a canonical K-major image with no data reshuffling):
-//   "C8 planar" activations   X[b][y][c/8][x][8] bf16   -- one (row, channel-octet) plane is x-contiguous 16 B items
-//   conv weights image        [tap*(Cin/8)+chunk][cout][8] bf16  -- no-swizzle core matrices (8 couts x 16 B)
+//   "C8 planar" activations   X[b][y][c/8][x][8] fp16   -- one (row, channel-octet) plane is x-contiguous 16 B items
+//   conv weights image        [tap*(Cin/8)+chunk][cout][8] fp16  -- no-swizzle core matrices (8 couts x 16 B)
 //   fc1 A tiles (pooled act.) [b/128][pooled pixel][b%128][128 B, 16 B chunks XOR (row&7)]  -- SW128 K-major
 //   fc1 W tiles               [pooled pixel][unit][128 B, chunks XOR (unit&7)]               -- SW128 K-major
 //
@@ -20,14 +20,14 @@ namespace bcad {
 using namespace sm100;
 
 // =====================================================================================================
-// first conv block (Cin = 1, 3x3): CUDA cores, fused bias + LeakyReLU + 2x2 max-pool, bf16 C8-planar out.
+// first conv block (Cin = 1, 3x3): CUDA cores, fused bias + LeakyReLU + 2x2 max-pool, fp16 C8-planar out.
 // K = 9 is too skinny for the tensor core; the block is ~6 % of the network's MACs.
 // block = 2 pooled rows x 128 pooled columns; thread = one pooled pixel, loops over channel octets.
 // =====================================================================================================
 template <int COUT>
 __global__ void __launch_bounds__(256)
 conv_first_pool_kernel(const float* __restrict__ x, const float* __restrict__ w /*[9][COUT]*/,
-                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W, int pad, int Hp,
+                       const float* __restrict__ bias, __half* __restrict__ out, int H, int W, int pad, int Hp,
                        int Wp, float alpha) {
     __shared__ __align__(16) float s_w[9 * COUT];
     __shared__ float s_b[COUT];
@@ -76,14 +76,14 @@ conv_first_pool_kernel(const float* __restrict__ x, const float* __restrict__ w 
         for (int j = 0; j < 8; j += 2) {
             float m0 = fmaxf(fmaxf(acc[0][j], acc[1][j]), fmaxf(acc[2][j], acc[3][j])) + s_b[oc * 8 + j];
             float m1 = fmaxf(fmaxf(acc[0][j + 1], acc[1][j + 1]), fmaxf(acc[2][j + 1], acc[3][j + 1])) + s_b[oc * 8 + j + 1];
-            pk[j >> 1] = pack_bf16(leaky(m0, alpha), leaky(m1, alpha));
+            pk[j >> 1] = pack_f16(leaky(m0, alpha), leaky(m1, alpha));
         }
         uint4* dst = reinterpret_cast<uint4*>(out) + (((size_t)b * Hp + py) * (COUT / 8) + oc) * Wp + px;
         *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
 }
 
-int launch_conv_first_pool(const float* x, const float* w9c, const float* bias, __nv_bfloat16* out, int B, int H, int W,
+int launch_conv_first_pool(const float* x, const float* w9c, const float* bias, __half* out, int B, int H, int W,
                            int pad, int Cout, float alpha, cudaStream_t s) {
     const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2, Hp = Ho / 2, Wp = Wo / 2;
     dim3 grid(cdiv(Wp, 128), cdiv(Hp, 2), B);
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
     const uint32_t tmem = *tmem_slot;
 
     const int n_items = a.B * a.bands;
-    const int in_row_elems = L::CHUNKS * a.W * 8;          // bf16 elements per input row (all channel octets)
+    const int in_row_elems = L::CHUNKS * a.W * 8;          // fp16 elements per input row (all channel octets)
 
     if (warp == 0) {
         // ================================ producer ================================
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
                 const int y0 = band * a.band_rows;
                 const int nrows = min(a.band_rows, a.Ho - y0);
                 const int nstages = (nrows + 1) / 2 + 1;
-                const __nv_bfloat16* inb = a.in + (size_t)b * a.H * in_row_elems;
+                const __half* inb = a.in + (size_t)b * a.H * in_row_elems;
                 for (int q = 0; q < nstages; ++q, ++g) {
                     const uint32_t slot = g % IG_STAGES;
                     if (g >= IG_STAGES) mbar_wait(&empty[slot], ((g / IG_STAGES) - 1) & 1);
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
                         const int in_row = y0 - a.pad + 2 * q + r;
                         if (in_row < 0 || in_row >= a.H) continue;
                         uint8_t* dst = s_ring + (slot * 2 + r) * L::ROWB + a.pad * 16;
-                        const __nv_bfloat16* src = inb + (size_t)in_row * in_row_elems;
+                        const __half* src = inb + (size_t)in_row * in_row_elems;
                         for (int c = 0; c < L::CHUNKS; ++c)
                             bulk_g2s(dst + c * L::LBO, src + (size_t)c * a.W * 8, a.W * 16, &full[slot]);
                     }
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(128, COUT);
+            constexpr uint32_t idesc = make_idesc_f16(128, COUT);
             mbar_wait(wbar, 0);
             uint32_t g = 0, acc_it = 0;
             const uint32_t w_base = smem_u32(s_w), zero_base = smem_u32(s_zero), ring_base = smem_u32(s_ring);
@@ -286,12 +286,12 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
                         for (int cc = 0; cc < 4; ++cc) {
                             const int chunk = half * 4 + cc;
                             uint4* d0 = reinterpret_cast<uint4*>(a.act) + (((size_t)b * a.Ho + t0) * (COUT / 8) + chunk) * a.Wo + x;
-                            *d0 = make_uint4(pack_bf16(v0[cc * 8], v0[cc * 8 + 1]), pack_bf16(v0[cc * 8 + 2], v0[cc * 8 + 3]),
-                                             pack_bf16(v0[cc * 8 + 4], v0[cc * 8 + 5]), pack_bf16(v0[cc * 8 + 6], v0[cc * 8 + 7]));
+                            *d0 = make_uint4(pack_f16(v0[cc * 8], v0[cc * 8 + 1]), pack_f16(v0[cc * 8 + 2], v0[cc * 8 + 3]),
+                                             pack_f16(v0[cc * 8 + 4], v0[cc * 8 + 5]), pack_f16(v0[cc * 8 + 6], v0[cc * 8 + 7]));
                             if (has1) {
                                 uint4* d1 = d0 + (size_t)(COUT / 8) * a.Wo;
-                                *d1 = make_uint4(pack_bf16(v1[cc * 8], v1[cc * 8 + 1]), pack_bf16(v1[cc * 8 + 2], v1[cc * 8 + 3]),
-                                                 pack_bf16(v1[cc * 8 + 4], v1[cc * 8 + 5]), pack_bf16(v1[cc * 8 + 6], v1[cc * 8 + 7]));
+                                *d1 = make_uint4(pack_f16(v1[cc * 8], v1[cc * 8 + 1]), pack_f16(v1[cc * 8 + 2], v1[cc * 8 + 3]),
+                                                 pack_f16(v1[cc * 8 + 4], v1[cc * 8 + 5]), pack_f16(v1[cc * 8 + 6], v1[cc * 8 + 7]));
                             }
                         }
                     }
@@ -310,8 +310,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
                             for (int cc = 0; cc < 4; ++cc) {
                                 const int chunk = (half * 4 + cc) ^ (row & 7);
                                 *reinterpret_cast<uint4*>(base + chunk * 16) =
-                                    make_uint4(pack_bf16(v0[cc * 8], v0[cc * 8 + 1]), pack_bf16(v0[cc * 8 + 2], v0[cc * 8 + 3]),
-                                               pack_bf16(v0[cc * 8 + 4], v0[cc * 8 + 5]), pack_bf16(v0[cc * 8 + 6], v0[cc * 8 + 7]));
+                                    make_uint4(pack_f16(v0[cc * 8], v0[cc * 8 + 1]), pack_f16(v0[cc * 8 + 2], v0[cc * 8 + 3]),
+                                               pack_f16(v0[cc * 8 + 4], v0[cc * 8 + 5]), pack_f16(v0[cc * 8 + 6], v0[cc * 8 + 7]));
                             }
                         }
                         if (a.pool_c8 != nullptr) {
@@ -319,8 +319,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
                             for (int cc = 0; cc < 4; ++cc) {
                                 const int chunk = half * 4 + cc;
                                 uint4* d = reinterpret_cast<uint4*>(a.pool_c8) + (((size_t)b * a.Hp + py) * (COUT / 8) + chunk) * a.Wp + px;
-                                *d = make_uint4(pack_bf16(v0[cc * 8], v0[cc * 8 + 1]), pack_bf16(v0[cc * 8 + 2], v0[cc * 8 + 3]),
-                                                pack_bf16(v0[cc * 8 + 4], v0[cc * 8 + 5]), pack_bf16(v0[cc * 8 + 6], v0[cc * 8 + 7]));
+                                *d = make_uint4(pack_f16(v0[cc * 8], v0[cc * 8 + 1]), pack_f16(v0[cc * 8 + 2], v0[cc * 8 + 3]),
+                                                pack_f16(v0[cc * 8 + 4], v0[cc * 8 + 5]), pack_f16(v0[cc * 8 + 6], v0[cc * 8 + 7]));
                             }
                         }
                     }
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_splitk_kernel(FcArgs a) {
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, a.N);
+            const uint32_t idesc = make_idesc_f16(128, a.N);
             for (int i = 0; i < nk; ++i) {
                 const int st = i % FC_STAGES;
                 mbar_wait(&full[st], (i / FC_STAGES) & 1);
@@ -439,7 +439,8 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_splitk_kernel(FcArgs a) {
                 tmem_ld_wait();
 #pragma unroll
                 for (int q = 0; q < 32; q += 4)
-                    *reinterpret_cast<float4*>(dst + c0 + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+                    if (c0 + q < a.N)   // N is a multiple of 16, not necessarily of 32
+                        *reinterpret_cast<float4*>(dst + c0 + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
             }
         } else {
             for (int c0 = 0; c0 < a.N; c0 += 4) *reinterpret_cast<float4*>(dst + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -484,11 +485,11 @@ int launch_fc_reduce(const float* part, int splits, size_t ld_split, const float
 }
 
 // =====================================================================================================
-// Grad-CAM channel reduction on C8-planar bf16 activations: cam = ReLU(sum_k alpha_k A_k) + min/max partials
+// Grad-CAM channel reduction on C8-planar fp16 activations: cam = ReLU(sum_k alpha_k A_k) + min/max partials
 // grid (splits, B), 256 threads, thread = pixel; every load is a coalesced 16 B per lane.
 // =====================================================================================================
 __global__ void __launch_bounds__(256)
-cam_c8_kernel(const __nv_bfloat16* __restrict__ A, const float* __restrict__ alpha_raw, float scale,
+cam_c8_kernel(const __half* __restrict__ A, const float* __restrict__ alpha_raw, float scale,
               float* __restrict__ alpha_out, float* __restrict__ cam_lo, float* __restrict__ mm, int h, int w, int C) {
     extern __shared__ float s_alpha[];
     __shared__ float s_min[8], s_max[8];
@@ -512,10 +513,11 @@ cam_c8_kernel(const __nv_bfloat16* __restrict__ A, const float* __restrict__ alp
         for (int c = 0; c < chunks; ++c) {
             const uint4 q = ldg_stream_u4(p + (size_t)c * w);
             const float* al = s_alpha + c * 8;
-            acc = fmaf(bf16lo(q.x), al[0], acc); acc = fmaf(bf16hi(q.x), al[1], acc);
-            acc = fmaf(bf16lo(q.y), al[2], acc); acc = fmaf(bf16hi(q.y), al[3], acc);
-            acc = fmaf(bf16lo(q.z), al[4], acc); acc = fmaf(bf16hi(q.z), al[5], acc);
-            acc = fmaf(bf16lo(q.w), al[6], acc); acc = fmaf(bf16hi(q.w), al[7], acc);
+            const float2 f0 = unpack_f16(q.x), f1 = unpack_f16(q.y), f2 = unpack_f16(q.z), f3 = unpack_f16(q.w);
+            acc = fmaf(f0.x, al[0], acc); acc = fmaf(f0.y, al[1], acc);
+            acc = fmaf(f1.x, al[2], acc); acc = fmaf(f1.y, al[3], acc);
+            acc = fmaf(f2.x, al[4], acc); acc = fmaf(f2.y, al[5], acc);
+            acc = fmaf(f3.x, al[6], acc); acc = fmaf(f3.y, al[7], acc);
         }
         acc = fmaxf(acc, 0.f);
         cam_lo[((size_t)b * h + y) * w + x] = acc;
@@ -533,7 +535,7 @@ cam_c8_kernel(const __nv_bfloat16* __restrict__ A, const float* __restrict__ alp
     }
 }
 
-int launch_cam_c8(const __nv_bfloat16* A, const float* alpha_raw, float scale, float* alpha_out, float* cam_lo, float* mm,
+int launch_cam_c8(const __half* A, const float* alpha_raw, float scale, float* alpha_out, float* cam_lo, float* mm,
                   int B, int h, int w, int C, int splits, cudaStream_t s) {
     dim3 grid(splits, B);
     cam_c8_kernel<<<grid, 256, C * sizeof(float), s>>>(A, alpha_raw, scale, alpha_out, cam_lo, mm, h, w, C);
@@ -541,19 +543,19 @@ int launch_cam_c8(const __nv_bfloat16* A, const float* alpha_raw, float scale, f
     return BCAD_OK;
 }
 
-// C8-planar bf16 [B][h][C/8][w][8] -> NHWC fp32 (compat / inspection only)
-__global__ void c8_to_nhwc_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int h, int w, int C, size_t total) {
+// C8-planar fp16 [B][h][C/8][w][8] -> NHWC fp32 (compat / inspection only)
+__global__ void c8_to_nhwc_kernel(const __half* __restrict__ src, float* __restrict__ dst, int h, int w, int C, size_t total) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % C);
         size_t r = i / C;
         const int x = (int)(r % w); r /= w;
         const int y = (int)(r % h);
         const size_t b = r / h;
-        dst[i] = __bfloat162float(src[((((b * h + y) * (C / 8) + (c >> 3)) * w + x) << 3) + (c & 7)]);
+        dst[i] = __half2float(src[((((b * h + y) * (C / 8) + (c >> 3)) * w + x) << 3) + (c & 7)]);
     }
 }
 
-int launch_c8_to_nhwc(const __nv_bfloat16* src, float* dst, int B, int h, int w, int C, cudaStream_t s) {
+int launch_c8_to_nhwc(const __half* src, float* dst, int B, int h, int w, int C, cudaStream_t s) {
     const size_t total = (size_t)B * h * w * C;
     const int blocks = (int)min((size_t)148 * 16, (total + 255) / 256);
     c8_to_nhwc_kernel<<<blocks, 256, 0, s>>>(src, dst, h, w, C, total);

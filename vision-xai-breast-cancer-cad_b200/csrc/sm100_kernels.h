@@ -1,21 +1,21 @@
-// Launchers of the bf16 tensor path (sm100_kernels.cu).
+// Launchers of the 16-bit (fp16 operand) tensor path (sm100_kernels.cu).
 #pragma once
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace bcad {
 
-int launch_conv_first_pool(const float* x, const float* w9c, const float* bias, __nv_bfloat16* out, int B, int H, int W,
+int launch_conv_first_pool(const float* x, const float* w9c, const float* bias, __half* out, int B, int H, int W,
                            int pad, int Cout, float alpha, cudaStream_t s);
 
 struct IgemmArgs {
-    const __nv_bfloat16* in;      // C8 planar [B][H][Cin/8][W][8]
+    const __half* in;      // C8 planar [B][H][Cin/8][W][8]
     const uint8_t* w_img;         // [9*(Cin/8)][Cout][16 B]
     const float* bias;            // [Cout]
-    __nv_bfloat16* act;           // C8 planar [B][Ho][Cout/8][Wo][8] post-activation, or nullptr
+    __half* act;           // C8 planar [B][Ho][Cout/8][Wo][8] post-activation, or nullptr
     uint8_t* pool_fc;             // pooled output as fc1 A tiles, or nullptr
-    __nv_bfloat16* pool_c8;       // pooled output C8 planar [B][Hp][Cout/8][Wp][8], or nullptr
+    __half* pool_c8;       // pooled output C8 planar [B][Hp][Cout/8][Wp][8], or nullptr
     int B, H, W, Ho, Wo, Hp, Wp, pad;
     int bands, band_rows;         // work items per image; output rows per item (even)
     float alpha;
@@ -32,8 +32,8 @@ int launch_fc_splitk(const FcArgs& a, cudaStream_t s);
 int launch_fc_reduce(const float* part, int splits, size_t ld_split, const float* bias, float* z, float* h, float alpha,
                      int M, int N, cudaStream_t s);
 
-int launch_cam_c8(const __nv_bfloat16* A, const float* alpha_raw, float scale, float* alpha_out, float* cam_lo, float* mm,
+int launch_cam_c8(const __half* A, const float* alpha_raw, float scale, float* alpha_out, float* cam_lo, float* mm,
                   int B, int h, int w, int C, int splits, cudaStream_t s);
-int launch_c8_to_nhwc(const __nv_bfloat16* src, float* dst, int B, int h, int w, int C, cudaStream_t s);
+int launch_c8_to_nhwc(const __half* src, float* dst, int B, int h, int w, int C, cudaStream_t s);
 
 }  // namespace bcad

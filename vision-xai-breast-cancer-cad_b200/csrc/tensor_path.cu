@@ -1,8 +1,8 @@
-// Orchestration of the bf16 tcgen05 path: eligibility, weight packing, per-chunk forward and explain.
+// Orchestration of the 16-bit tcgen05 path (fp16 operands, fp32 accumulation): eligibility, weight packing, per-chunk forward and explain.
 //
 // Pipeline per chunk of n images (n <= max_batch):
-//   conv_first_pool  (CUDA cores, Cin=1)      x fp32 NHWC          -> P1 bf16 C8-planar
-//   conv_igemm       (tcgen05)                P1                   -> A (target activations, bf16 C8-planar)
+//   conv_first_pool  (CUDA cores, Cin=1)      x fp32 NHWC          -> P1 fp16 C8-planar
+//   conv_igemm       (tcgen05)                P1                   -> A (target activations, fp16 C8-planar)
 //                                                                     + pooled map as fc1 A-operand tiles
 //   fc_splitk        (tcgen05) + fc_reduce    tiles x W1 tiles     -> z1, h1            (fp32)
 //   remaining dense layers, head              (small fp32 kernels shared with the fp32 path)
@@ -18,6 +18,8 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "model.h"
+#include <cuda_fp16.h>
+
 #include "sm100_kernels.h"
 
 namespace bcad {
@@ -26,12 +28,12 @@ struct TensorPath {
     int sms = 148;
     float* d_w0 = nullptr;          // first conv weights [9][Cout0] fp32
     float* d_b0 = nullptr;
-    uint8_t* d_w1_img = nullptr;    // igemm weight image
+    uint8_t* d_w1_img = nullptr;    // igemm weight image (fp16)
     float* d_b1 = nullptr;
     uint8_t* d_fc_w = nullptr;      // fc1 W tiles
     float* d_S = nullptr;           // [units][Cout] fp32: per-channel column sums of fc1 (alpha shortcut)
-    __nv_bfloat16* p1 = nullptr;    // conv0 pooled, C8 planar
-    __nv_bfloat16* act = nullptr;   // conv1 output, C8 planar
+    __half* p1 = nullptr;    // conv0 pooled, C8 planar
+    __half* act = nullptr;   // conv1 output, C8 planar
     uint8_t* fc_a = nullptr;        // pooled conv1 as fc1 A tiles
     float* fc_part = nullptr;
     float* alpha_raw = nullptr;     // [B][Cout] = dz1 . S
@@ -41,28 +43,32 @@ struct TensorPath {
 #define TP_TRY(expr) do { int _rc = (expr); if (_rc != BCAD_OK) return _rc; } while (0)
 #define TP_LAUNCH(m, name, expr) do { int _rc = (m).mark(name, s); if (_rc == BCAD_OK) _rc = (expr); if (_rc != BCAD_OK) return _rc; (m).launches += 1; } while (0)
 
-static uint16_t f2bf(float f) {
-    uint32_t u;
-    memcpy(&u, &f, 4);
-    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
-    u += 0x7fffu + ((u >> 16) & 1);                                            // round to nearest even
-    return (uint16_t)(u >> 16);
+static uint16_t f2h(float f) {                  // round-to-nearest-even fp32 -> fp16 bits (host)
+    const __half h = __float2half_rn(f);
+    uint16_t q;
+    memcpy(&q, &h, 2);
+    return q;
+}
+static float h2f(uint16_t q) {
+    __half h;
+    memcpy(&h, &q, 2);
+    return __half2float(h);
 }
 
 int tensor_path_supported(const Model& m) {
     const bcad_config& c = m.cfg;
-    BCAD_REQUIRE(m.conv.size() == 2, "precision=BF16: the tensor path covers 2 conv blocks (got %zu); use BCAD_PREC_FP32", m.conv.size());
+    BCAD_REQUIRE(m.conv.size() == 2, "precision=F16: the tensor path covers 2 conv blocks (got %zu); use BCAD_PREC_FP32", m.conv.size());
     const ConvLayer& c0 = m.conv[0];
     const ConvLayer& c1 = m.conv[1];
     BCAD_REQUIRE(c0.Cin == 1 && c0.k == 3 && (c0.Cout == 16 || c0.Cout == 32 || c0.Cout == 64),
-                 "precision=BF16: first conv block must be 1 -> 16/32/64 channels, 3x3 (got %d -> %d, k=%d)", c0.Cin, c0.Cout, c0.k);
-    BCAD_REQUIRE(c1.k == 3 && c1.Cout == 64, "precision=BF16: second conv block must be 3x3 with 64 filters (got k=%d, %d)", c1.k, c1.Cout);
-    BCAD_REQUIRE(c1.W <= 128, "precision=BF16: second conv block input width %d > 128", c1.W);
-    BCAD_REQUIRE(c.pad == 0 || c.pad == 1, "precision=BF16: pad must be 0 or 1");
+                 "precision=F16: first conv block must be 1 -> 16/32/64 channels, 3x3 (got %d -> %d, k=%d)", c0.Cin, c0.Cout, c0.k);
+    BCAD_REQUIRE(c1.k == 3 && c1.Cout == 64, "precision=F16: second conv block must be 3x3 with 64 filters (got k=%d, %d)", c1.k, c1.Cout);
+    BCAD_REQUIRE(c1.W <= 128, "precision=F16: second conv block input width %d > 128", c1.W);
+    BCAD_REQUIRE(c.pad == 0 || c.pad == 1, "precision=F16: pad must be 0 or 1");
     BCAD_REQUIRE(c.pool_ties == BCAD_TIES_FIRST,
-                 "precision=BF16: the alpha shortcut needs first-index pooling (TIES_FIRST); the tie-duplicating NumPy flavour runs on BCAD_PREC_FP32");
+                 "precision=F16: the alpha shortcut needs first-index pooling (TIES_FIRST); the tie-duplicating NumPy flavour runs on BCAD_PREC_FP32");
     const int units = m.dense[0].out;
-    BCAD_REQUIRE(units % 16 == 0 && units <= 256, "precision=BF16: first dense layer must have a multiple of 16 units <= 256 (got %d)", units);
+    BCAD_REQUIRE(units % 16 == 0 && units <= 256, "precision=F16: first dense layer must have a multiple of 16 units <= 256 (got %d)", units);
     return BCAD_OK;
 }
 
@@ -86,7 +92,7 @@ int tensor_path_commit(Model& m) {
         BCAD_CUDA_CHECK(cudaMemcpy(t.d_w0, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
         BCAD_CUDA_CHECK(cudaMemcpy(t.d_b0, c0.h_b.data(), c0.Cout * 4, cudaMemcpyHostToDevice));
     }
-    // ---- conv1 weight image: [tap*(Cin/8)+chunk][cout][8] bf16
+    // ---- conv1 weight image: [tap*(Cin/8)+chunk][cout][8] fp16
     {
         const int chunks = c1.Cin / 8;
         std::vector<uint16_t> img((size_t)9 * chunks * c1.Cout * 8);
@@ -95,7 +101,7 @@ int tensor_path_commit(Model& m) {
                 for (int f = 0; f < c1.Cout; ++f)
                     for (int e = 0; e < 8; ++e)
                         img[(((size_t)tap * chunks + ch) * c1.Cout + f) * 8 + e] =
-                            f2bf(c1.h_w[((size_t)f * 9 + tap) * c1.Cin + ch * 8 + e]);
+                            f2h(c1.h_w[((size_t)f * 9 + tap) * c1.Cin + ch * 8 + e]);
         if (!t.d_w1_img) TP_TRY(m.alloc((void**)&t.d_w1_img, img.size() * 2));
         if (!t.d_b1) TP_TRY(m.alloc((void**)&t.d_b1, c1.Cout * 4));
         BCAD_CUDA_CHECK(cudaMemcpy(t.d_w1_img, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
@@ -113,12 +119,9 @@ int tensor_path_commit(Model& m) {
                 for (int cidx = 0; cidx < C; ++cidx) {
                     const float v = row[(size_t)pp * C + cidx];
                     const int chunk = (cidx >> 3) ^ (u & 7);
-                    const uint16_t q = f2bf(v);
+                    const uint16_t q = f2h(v);
                     dst[chunk * 8 + (cidx & 7)] = q;
-                    uint32_t bits = (uint32_t)q << 16;                     // S uses the bf16-rounded weights the GEMM sees
-                    float vq;
-                    memcpy(&vq, &bits, 4);
-                    S[(size_t)u * C + cidx] += vq;
+                    S[(size_t)u * C + cidx] += h2f(q);                    // S uses the fp16-rounded weights the GEMM sees
                 }
             }
         }
