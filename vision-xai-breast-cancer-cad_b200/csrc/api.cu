@@ -326,6 +326,7 @@ int bcad_commit(bcad_model* mm) {
         BCAD_TRY(m->alloc((void**)&m->probs, (size_t)mb * m->cfg.num_classes * sizeof(float)));
         BCAD_TRY(m->alloc((void**)&m->cls, (size_t)mb * sizeof(int32_t)));
         BCAD_TRY(m->alloc((void**)&m->d_top, (size_t)mb * m->cfg.num_classes * sizeof(float)));
+        m->fused_head = fused_head_ok(m);
         if (!m->tensor_path) BCAD_TRY(m->alloc((void**)&m->g_flat, (size_t)mb * m->flat * sizeof(float)));
         const ConvLayer& T = m->conv.back();
         m->alpha_splits = alpha_pool_splits(T.Hp);
@@ -351,20 +352,36 @@ namespace bcad {
 // -----------------------------------------------------------------------------------------------------
 // fp32 path: one chunk (n <= max_batch) forward, activations cached in the workspace
 // -----------------------------------------------------------------------------------------------------
-static int dense_forward_fp32(Model* m, const float* flat_in, int n, cudaStream_t s) {
-    const float* in = flat_in;
-    for (size_t j = 0; j < m->dense.size(); ++j) {
-        DenseLayer& D = m->dense[j];
-        const bool last = (j + 1 == m->dense.size());
-        const int splits = std::min(D.splits, sgemm_pick_splits(n, D.out, D.in));
-        BCAD_LAUNCH(m, "sgemm", launch_sgemm(in, D.d_w, m->partials, n, D.out, D.in, true, splits, s));
-        BCAD_LAUNCH(m, "splitk_reduce", launch_splitk_reduce(m->partials, splits, D.d_b, D.z, last ? nullptr : D.h, m->cfg.alpha_dense, n, D.out, s));
-        in = D.h;
+bool fused_head_ok(const Model* m) {
+    size_t total = 0, mx = 0;
+    for (const DenseLayer& D : m->dense) { total += D.out; mx = std::max(mx, (size_t)D.out); }
+    return (total + 2 * mx) * sizeof(float) <= 40 * 1024 && m->dense.size() <= 8;
+}
+
+// One launch for everything after the fc1 GEMM (see dense_head_kernel).
+int launch_fused_head(Model* m, int n, const float* fc1_part, int splits, size_t ld, bool explain, const int32_t* class_idx,
+                      int grad_mode, float* dz1, const float* S, int C, float* alpha_raw, cudaStream_t s) {
+    HeadArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_dense = (int)m->dense.size();
+    a.max_size = 0;
+    for (int j = 0; j < a.n_dense; ++j) {
+        a.sizes[j] = m->dense[j].out;
+        a.max_size = std::max(a.max_size, m->dense[j].out);
+        a.W[j] = m->dense[j].d_w;
+        a.bias[j] = m->dense[j].d_b;
+        a.z[j] = m->dense[j].z;
     }
+    a.fc1_part = fc1_part; a.fc1_splits = splits; a.fc1_ld = ld;
+    a.alpha = m->cfg.alpha_dense; a.head = m->cfg.head; a.probs = m->probs; a.cls = m->cls;
+    a.explain = explain ? 1 : 0; a.class_idx = class_idx; a.grad_mode = grad_mode;
+    a.dz1 = dz1; a.S = S; a.C = C; a.alpha_raw = alpha_raw;
+    BCAD_LAUNCH(m, "dense_head_fused", launch_dense_head(a, n, s));
     return BCAD_OK;
 }
 
-static int forward_chunk_fp32(Model* m, const float* x, int n, cudaStream_t s) {
+static int forward_chunk_fp32(Model* m, const float* x, int n, bool explain, const int32_t* class_idx, int grad_mode,
+                              cudaStream_t s) {
     const float* in = x;
     for (size_t i = 0; i < m->conv.size(); ++i) {
         ConvLayer& L = m->conv[i];
@@ -376,7 +393,27 @@ static int forward_chunk_fp32(Model* m, const float* x, int n, cudaStream_t s) {
         BCAD_LAUNCH(m, i == 0 ? "conv0_fp32" : (i == 1 ? "conv1_fp32" : "convN_fp32"), launch_conv_fp32(a, s));
         in = L.p;
     }
-    BCAD_TRY(dense_forward_fp32(m, in, n, s));
+    // fc1 as a split-K SGEMM, then either the fused head or the layer-by-layer chain
+    DenseLayer& D0 = m->dense[0];
+    const int splits0 = std::min(D0.splits, sgemm_pick_splits(n, D0.out, D0.in));
+    BCAD_LAUNCH(m, "fc1_sgemm", launch_sgemm(in, D0.d_w, m->partials, n, D0.out, D0.in, true, splits0, s));
+    if (m->fused_head) {
+        BCAD_TRY(launch_fused_head(m, n, m->partials, splits0, (size_t)n * D0.out, explain, class_idx, grad_mode,
+                                   explain ? D0.h : nullptr, nullptr, 0, nullptr, s));
+        return BCAD_OK;
+    }
+    const bool only = (m->dense.size() == 1);
+    BCAD_LAUNCH(m, "splitk_reduce", launch_splitk_reduce(m->partials, splits0, D0.d_b, D0.z, only ? nullptr : D0.h, m->cfg.alpha_dense, n, D0.out, s));
+    in = D0.h;
+    for (size_t j = 1; j < m->dense.size(); ++j) {
+        DenseLayer& D = m->dense[j];
+        const bool last = (j + 1 == m->dense.size());
+        const int splits = std::min(D.splits, sgemm_pick_splits(n, D.out, D.in));
+        BCAD_LAUNCH(m, "sgemm", launch_sgemm(in, D.d_w, m->partials, n, D.out, D.in, true, splits, s));
+        BCAD_LAUNCH(m, "splitk_reduce", launch_splitk_reduce(m->partials, splits, D.d_b, D.z, last ? nullptr : D.h, m->cfg.alpha_dense, n, D.out, s));
+        in = D.h;
+    }
+    BCAD_LAUNCH(m, "head", launch_head(m->dense.back().z, m->probs, m->cls, n, m->cfg.num_classes, m->cfg.head, s));
     return BCAD_OK;
 }
 
@@ -411,7 +448,14 @@ static int tail_chunk(Model* m, const void* A, int a_dtype, int n, float* heat, 
 
 static int explain_chunk_fp32(Model* m, int n, const int32_t* class_idx, int grad_mode, float* heat, cudaStream_t s) {
     const ConvLayer& T = m->conv.back();
-    BCAD_TRY(dense_backward(m, n, class_idx, grad_mode, m->g_flat, s));
+    if (m->fused_head) {
+        // dz1 was left in dense[0].h by the fused head: only the fc1 input gradient remains
+        DenseLayer& D0 = m->dense[0];
+        const float* dz1 = (m->dense.size() > 1) ? D0.h : D0.h;
+        BCAD_LAUNCH(m, "fc1_dgrad_sgemm", launch_sgemm(dz1, D0.d_w, m->g_flat, n, D0.in, D0.out, false, 1, s));
+    } else {
+        BCAD_TRY(dense_backward(m, n, class_idx, grad_mode, m->g_flat, s));
+    }
     BCAD_LAUNCH(m, "alpha_from_pool_grad", launch_alpha_from_pool_grad(m->g_flat, T.y, m->alpha_part, n, T.Ho, T.Wo, T.Cout, m->cfg.pool_ties,
                                                m->alpha_splits, s));
     BCAD_TRY(tail_chunk(m, T.y, 0, n, heat, s));
@@ -435,14 +479,13 @@ static int run(Model* m, const float* x, int B, const int32_t* class_idx, int gr
     for (int b0 = 0; b0 < B; b0 += mb) {
         const int n = std::min(mb, B - b0);
         const float* xc = x + (size_t)b0 * img;
-        if (m->tensor_path) BCAD_TRY(tensor_forward_chunk(*m, xc, n, s));
-        else BCAD_TRY(forward_chunk_fp32(m, xc, n, s));
-        BCAD_LAUNCH(m, "head", launch_head(m->dense.back().z, m->probs, m->cls, n, nc, m->cfg.head, s));
+        const int32_t* ci = (explain && class_idx) ? class_idx + b0 : nullptr;
+        if (m->tensor_path) BCAD_TRY(tensor_forward_chunk(*m, xc, n, explain, ci, grad_mode, s));
+        else BCAD_TRY(forward_chunk_fp32(m, xc, n, explain, ci, grad_mode, s));
         if (logits) BCAD_CUDA_CHECK(cudaMemcpyAsync(logits + (size_t)b0 * nc, m->dense.back().z, (size_t)n * nc * sizeof(float), cudaMemcpyDeviceToDevice, s));
         if (probs) BCAD_CUDA_CHECK(cudaMemcpyAsync(probs + (size_t)b0 * nc, m->probs, (size_t)n * nc * sizeof(float), cudaMemcpyDeviceToDevice, s));
         if (cls) BCAD_CUDA_CHECK(cudaMemcpyAsync(cls + b0, m->cls, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
         if (explain) {
-            const int32_t* ci = class_idx ? class_idx + b0 : nullptr;
             if (m->tensor_path) BCAD_TRY(tensor_explain_chunk(*m, n, ci, grad_mode, heat + (size_t)b0 * hm, s));
             else BCAD_TRY(explain_chunk_fp32(m, n, ci, grad_mode, heat + (size_t)b0 * hm, s));
         }

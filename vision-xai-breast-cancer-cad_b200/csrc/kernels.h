@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/bcad.h"
+
 namespace bcad {
 
 // ---------------------------------------------------------------- fp32 CUDA-core path (any shape)
@@ -48,5 +50,30 @@ int launch_upsample_norm(const float* cam_lo, const float* mm, int mm_splits, fl
                          int w, int H, int W, cudaStream_t s);
 int launch_overlay(const float* img01, const float* cam, int B, int H, int W, uint8_t* overlay_rgb,
                    uint8_t* heat_u8, cudaStream_t s);
+
+// fused dense head: fc1 split-K reduce -> remaining dense layers -> probs/class -> (explain) backward to dz1 + alpha
+struct HeadArgs {
+    int n_dense;                  // dense layers incl. the output layer; layer 0 comes as split-K partials
+    int sizes[8];                 // output size of every dense layer (sizes[n_dense-1] = num_classes)
+    int max_size;
+    const float* W[8];            // (out,in) fp32 of layers 1.. (W[0] unused)
+    const float* bias[8];
+    float* z[8];                  // pre-activations [B][size] (kept for layer['z'] compat)
+    const float* fc1_part;        // [splits][ld] partial sums of layer 0, row b at b*sizes[0]
+    int fc1_splits;
+    size_t fc1_ld;
+    float alpha;
+    int head;
+    float* probs;
+    int32_t* cls;
+    int explain;
+    const int32_t* class_idx;     // nullable = predicted class
+    int grad_mode;
+    float* dz1;                   // [B][sizes[0]] out, nullable
+    const float* S;               // [sizes[0]][C] fp32, nullable
+    int C;
+    float* alpha_raw;             // [B][C]
+};
+int launch_dense_head(const HeadArgs& a, int B, cudaStream_t s);
 
 }  // namespace bcad

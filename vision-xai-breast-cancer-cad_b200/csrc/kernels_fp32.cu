@@ -785,10 +785,86 @@ upsample_norm_kernel(const float* __restrict__ cam_lo, const float* __restrict__
     for (int i = tid; i < npix; i += blockDim.x) ob[i] = (sample(i / W, i % W) - vmin) / denom2;
 }
 
+// Separable variant (the common case: everything fits in shared memory): the horizontally interpolated rows are
+// built once (h x W floats, exactly OpenCV's HResize-then-VResize order), every output sample is then two
+// shared-memory reads and one lerp; both min-max passes run over that.
+__global__ void __launch_bounds__(UP_THREADS)
+upsample_norm_sep_kernel(const float* __restrict__ cam_lo, const float* __restrict__ mm, int mm_splits,
+                         float* __restrict__ out, int h, int w, int H, int W) {
+    extern __shared__ float sm[];
+    __shared__ float s_red[64];
+    int* s_x0 = reinterpret_cast<int*>(sm);
+    int* s_x1 = s_x0 + W;
+    float* s_fx = sm + 2 * W;
+    int* s_y0 = reinterpret_cast<int*>(sm + 3 * W);
+    int* s_y1 = s_y0 + H;
+    float* s_fy = sm + 3 * W + 2 * H;
+    float* s_lo = sm + 3 * W + 3 * H;          // [h][w] normalised low-res map
+    float* s_hr = s_lo + h * w;                // [h][W] horizontally interpolated rows
+    const int b = blockIdx.x, tid = threadIdx.x;
+    for (int d = tid; d < W + H; d += blockDim.x) {
+        const bool isx = d < W;
+        const int dd = isx ? d : d - W;
+        const int ns = isx ? w : h, nd = isx ? W : H;
+        const double sc = ((double)dd + 0.5) * ((double)ns / (double)nd) - 0.5;
+        int i0 = (int)floor(sc);
+        float f = (float)(sc - (double)i0);
+        if (i0 < 0) { i0 = 0; f = 0.f; }
+        if (i0 >= ns - 1) { i0 = ns - 1; f = 0.f; }
+        const int i1 = min(i0 + 1, ns - 1);
+        if (isx) { s_x0[dd] = i0; s_x1[dd] = i1; s_fx[dd] = f; }
+        else { s_y0[dd] = i0 * W; s_y1[dd] = i1 * W; s_fy[dd] = f; }
+    }
+    float mn = 3.4e38f, mx = -3.4e38f;
+    for (int q = 0; q < mm_splits; ++q) {
+        mn = fminf(mn, mm[((size_t)b * mm_splits + q) * 2]);
+        mx = fmaxf(mx, mm[((size_t)b * mm_splits + q) * 2 + 1]);
+    }
+    const float denom = 1e-7f + (mx - mn);
+    const float* lo = cam_lo + (size_t)b * h * w;
+    for (int i = tid; i < h * w; i += blockDim.x) s_lo[i] = (lo[i] - mn) / denom;
+    __syncthreads();
+    for (int i = tid; i < h * W; i += blockDim.x) {
+        const int y = i / W, ox = i - y * W;
+        const float fx = s_fx[ox];
+        s_hr[i] = s_lo[y * w + s_x0[ox]] * (1.f - fx) + s_lo[y * w + s_x1[ox]] * fx;
+    }
+    __syncthreads();
+    float vmin = 3.4e38f, vmax = -3.4e38f;
+    const int npix = H * W;
+    for (int i = tid; i < npix; i += blockDim.x) {
+        const int oy = i / W, ox = i - oy * W;
+        const float fy = s_fy[oy];
+        const float v = s_hr[s_y0[oy] + ox] * (1.f - fy) + s_hr[s_y1[oy] + ox] * fy;
+        vmin = fminf(vmin, v);
+        vmax = fmaxf(vmax, v);
+    }
+    block_minmax(vmin, vmax, s_red);
+    const float inv = 1.f / (1e-7f + (vmax - vmin));
+    const float denom2 = 1e-7f + (vmax - vmin);
+    float* ob = out + (size_t)b * npix;
+    (void)inv;
+    for (int i = tid; i < npix; i += blockDim.x) {
+        const int oy = i / W, ox = i - oy * W;
+        const float fy = s_fy[oy];
+        const float v = s_hr[s_y0[oy] + ox] * (1.f - fy) + s_hr[s_y1[oy] + ox] * fy;
+        ob[i] = (v - vmin) / denom2;
+    }
+}
+
 int launch_upsample_norm(const float* cam_lo, const float* mm, int mm_splits, float* out, int B, int h, int w, int H,
                          int W, cudaStream_t s) {
-    size_t smem = (size_t)(3 * W + 3 * H) * sizeof(float);
-    const size_t lo_bytes = (size_t)h * w * sizeof(float);
+    const size_t tables = (size_t)(3 * W + 3 * H) * sizeof(float);
+    const size_t lo_bytes = (size_t)h * w * sizeof(float), hr_bytes = (size_t)h * W * sizeof(float);
+    if (tables + lo_bytes + hr_bytes <= 220 * 1024) {
+        const size_t smem = tables + lo_bytes + hr_bytes;
+        if (smem > 48 * 1024)
+            BCAD_CUDA_CHECK(cudaFuncSetAttribute(upsample_norm_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        upsample_norm_sep_kernel<<<B, UP_THREADS, smem, s>>>(cam_lo, mm, mm_splits, out, h, w, H, W);
+        BCAD_CUDA_CHECK(cudaGetLastError());
+        return BCAD_OK;
+    }
+    size_t smem = tables;
     int lo_in_smem = 0;
     if (smem + lo_bytes <= 200 * 1024) { smem += lo_bytes; lo_in_smem = 1; }
     BCAD_REQUIRE(smem <= 200 * 1024, "upsample: output %dx%d too large for the coordinate tables", H, W);
@@ -842,6 +918,124 @@ overlay_kernel(const float* __restrict__ img01, const float* __restrict__ cam, i
 int launch_overlay(const float* img01, const float* cam, int B, int H, int W, uint8_t* overlay_rgb, uint8_t* heat_u8,
                    cudaStream_t s) {
     overlay_kernel<<<B, 1024, 0, s>>>(img01, cam, H, W, overlay_rgb, heat_u8);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+// =====================================================================================================
+// fused dense head (one CTA per image): fc1 split-K reduce + bias + LeakyReLU, the remaining dense layers,
+// probabilities / class, and -- when explaining -- the top gradient and the dense backward down to dz1
+// plus the Grad-CAM channel weights through the alpha shortcut  alpha_raw[k] = sum_u dz1[u] S[u][k].
+// Replaces ~12 tiny launches of the layer-by-layer path (explainability.py:20-34, Classes/CNNModel.py:177-212).
+// =====================================================================================================
+__global__ void __launch_bounds__(256) dense_head_kernel(HeadArgs a) {
+    extern __shared__ float sh[];                 // z of every layer, then activations / gradients scratch
+    __shared__ int s_cls;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int off[BCAD_MAX_DENSE + 1];
+    off[0] = 0;
+    for (int j = 0; j < a.n_dense; ++j) off[j + 1] = off[j] + a.sizes[j];
+    float* s_z = sh;                              // [sum sizes]
+    float* s_v = sh + off[a.n_dense];             // activation vector of the current layer (max size)
+    float* s_g = s_v + a.max_size;                // gradient vector (max size)
+    // ---- layer 0: reduce the split-K partials in a fixed order
+    const int n0 = a.sizes[0];
+    for (int u = tid; u < n0; u += 256) {
+        float v = 0.f;
+        for (int sidx = 0; sidx < a.fc1_splits; ++sidx) v += a.fc1_part[(size_t)sidx * a.fc1_ld + (size_t)b * n0 + u];
+        v += __ldg(a.bias[0] + u);
+        s_z[u] = v;
+        a.z[0][(size_t)b * n0 + u] = v;
+        s_v[u] = (a.n_dense > 1) ? leaky(v, a.alpha) : v;
+    }
+    __syncthreads();
+    // ---- layers 1..: one warp per output row, lanes across the input (coalesced weight reads)
+    for (int j = 1; j < a.n_dense; ++j) {
+        const int nin = a.sizes[j - 1], nout = a.sizes[j];
+        const float* Wj = a.W[j];
+        for (int v = warp; v < nout; v += 8) {
+            float acc = 0.f;
+            for (int u = lane; u < nin; u += 32) acc = fmaf(__ldg(Wj + (size_t)v * nin + u), s_v[u], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) {
+                acc += __ldg(a.bias[j] + v);
+                s_z[off[j] + v] = acc;
+                a.z[j][(size_t)b * nout + v] = acc;
+            }
+        }
+        __syncthreads();
+        for (int v = tid; v < nout; v += 256) s_v[v] = (j + 1 < a.n_dense) ? leaky(s_z[off[j] + v], a.alpha) : s_z[off[j] + v];
+        __syncthreads();
+    }
+    // ---- probabilities + class (float64 like the NumPy reference)
+    const int nc = a.sizes[a.n_dense - 1];
+    const float* logit = s_z + off[a.n_dense - 1];
+    if (tid == 0) {
+        double zmax = -1e300;
+        for (int c = 0; c < nc; ++c) {
+            double v = (double)logit[c];
+            if (a.head == BCAD_HEAD_SOFTMAX_CLIP) v = fmin(fmax(v, -50.0), 50.0);
+            zmax = fmax(zmax, v);
+        }
+        double sum = 0.0;
+        for (int c = 0; c < nc; ++c) {
+            double v = (double)logit[c];
+            if (a.head == BCAD_HEAD_SOFTMAX_CLIP) v = fmin(fmax(v, -50.0), 50.0);
+            sum += exp(v - zmax);
+        }
+        int best = 0;
+        double best_v = -1e300;
+        for (int c = 0; c < nc; ++c) {
+            double v = (double)logit[c];
+            if (a.head == BCAD_HEAD_SOFTMAX_CLIP) v = fmin(fmax(v, -50.0), 50.0);
+            const double p = (a.head == BCAD_HEAD_SOFTMAX_CLIP) ? exp(v - zmax) / (sum + 1e-12) : exp(v - zmax) / sum;
+            a.probs[(size_t)b * nc + c] = (float)p;
+            s_g[c] = (float)p;
+            const double score = (a.head == BCAD_HEAD_SOFTMAX_CLIP) ? p : (double)logit[c];
+            if (score > best_v) { best_v = score; best = c; }
+        }
+        a.cls[b] = best;
+        s_cls = best;
+    }
+    __syncthreads();
+    if (!a.explain) return;
+    // ---- top gradient (explainability.py:21-22 / GRADCAM.py:64)
+    const int target = a.class_idx != nullptr ? a.class_idx[b] : s_cls;
+    for (int c = tid; c < nc; c += 256) {
+        const float onehot = (c == target) ? 1.f : 0.f;
+        s_g[c] = (a.grad_mode == BCAD_GRAD_LOGIT) ? onehot : s_g[c] - onehot;
+    }
+    __syncthreads();
+    // ---- backward: d(h_{j-1}) = W_j^T dz_j, dz_{j-1} = d(h_{j-1}) * LeakyReLU'(z_{j-1})
+    for (int j = a.n_dense - 1; j >= 1; --j) {
+        const int nin = a.sizes[j - 1], nout = a.sizes[j];
+        const float* Wj = a.W[j];
+        for (int u = tid; u < nin; u += 256) {
+            float acc = 0.f;
+            for (int v = 0; v < nout; ++v) acc = fmaf(__ldg(Wj + (size_t)v * nin + u), s_g[v], acc);   // coalesced over u
+            s_v[u] = acc * (s_z[off[j - 1] + u] > 0.f ? 1.f : a.alpha);
+        }
+        __syncthreads();
+        for (int u = tid; u < nin; u += 256) s_g[u] = s_v[u];
+        __syncthreads();
+    }
+    // s_g now holds dz of layer 0 (dz1)
+    if (a.dz1 != nullptr)
+        for (int u = tid; u < n0; u += 256) a.dz1[(size_t)b * n0 + u] = s_g[u];
+    if (a.S != nullptr)
+        for (int k = tid; k < a.C; k += 256) {
+            float acc = 0.f;
+            for (int u = 0; u < n0; ++u) acc = fmaf(s_g[u], __ldg(a.S + (size_t)u * a.C + k), acc);
+            a.alpha_raw[(size_t)b * a.C + k] = acc;
+        }
+}
+
+int launch_dense_head(const HeadArgs& a, int B, cudaStream_t s) {
+    int total = 0;
+    for (int j = 0; j < a.n_dense; ++j) total += a.sizes[j];
+    const size_t smem = (size_t)(total + 2 * a.max_size) * sizeof(float);
+    BCAD_REQUIRE(smem <= 48 * 1024, "dense head: layer sizes too large for the fused kernel (%zu bytes)", smem);
+    dense_head_kernel<<<B, 256, smem, s>>>(a);
     BCAD_CUDA_CHECK(cudaGetLastError());
     return BCAD_OK;
 }

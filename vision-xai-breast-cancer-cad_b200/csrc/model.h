@@ -53,7 +53,7 @@ struct Model {
     std::vector<ConvLayer> conv;
     std::vector<DenseLayer> dense;
     int64_t flat = 0;
-    bool committed = false, ws_ready = false, tensor_path = false, profiling = false;
+    bool committed = false, ws_ready = false, tensor_path = false, profiling = false, fused_head = false;
     int cached_B = 0;
     int64_t launches = 0;
     size_t ws_bytes = 0;
@@ -86,10 +86,15 @@ struct Model {
 // g_flat != nullptr, on to the flattened pool output
 int dense_backward(Model* m, int n, const int32_t* class_idx, int grad_mode, float* g_flat, cudaStream_t s);
 
+bool fused_head_ok(const Model* m);
+// everything after the fc1 GEMM in one launch (dense_head_kernel); dz1 / S / alpha_raw are optional outputs
+int launch_fused_head(Model* m, int n, const float* fc1_part, int splits, size_t ld, bool explain, const int32_t* class_idx,
+                      int grad_mode, float* dz1, const float* S, int C, float* alpha_raw, cudaStream_t s);
+
 // ---- tensor (tcgen05) path, tensor_path.cu
 int tensor_path_supported(const Model& m);          // BCAD_OK or BCAD_ERR_INVALID (+ message)
 int tensor_path_commit(Model& m);
-int tensor_forward_chunk(Model& m, const float* x, int n, cudaStream_t s);
+int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const int32_t* class_idx, int grad_mode, cudaStream_t s);
 int tensor_explain_chunk(Model& m, int n, const int32_t* class_idx, int grad_mode, float* heat, cudaStream_t s);
 int tensor_get_activation(Model& m, int kind, int index, int B, float* dst, cudaStream_t s);
 void tensor_path_destroy(Model& m);

@@ -155,7 +155,7 @@ void tensor_path_destroy(Model& m) {
     m.tp = nullptr;
 }
 
-int tensor_forward_chunk(Model& m, const float* x, int n, cudaStream_t s) {
+int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const int32_t* class_idx, int grad_mode, cudaStream_t s) {
     TensorPath& t = *m.tp;
     const ConvLayer& c0 = m.conv[0];
     const ConvLayer& c1 = m.conv[1];
@@ -175,10 +175,14 @@ int tensor_forward_chunk(Model& m, const float* x, int n, cudaStream_t s) {
     f.N = d0.out; f.nkb = c1.Hp * c1.Wp; f.kb_per_split = t.kb_per_split; f.splits = t.fc_splits;
     f.m_tiles = cdiv(n, 128); f.m_pad = t.m_pad;
     TP_LAUNCH(m, "fc1_splitk_tcgen05", launch_fc_splitk(f, s));
+    if (m.fused_head) {
+        // reduce + dense tail + class + (explain) backward to dz1 + alpha shortcut, one launch
+        return launch_fused_head(&m, n, t.fc_part, t.fc_splits, (size_t)t.m_pad * d0.out, explain, class_idx, grad_mode,
+                                 nullptr, t.d_S, c1.Cout, t.alpha_raw, s);
+    }
     const bool only = (m.dense.size() == 1);
     TP_LAUNCH(m, "fc1_reduce", launch_fc_reduce(t.fc_part, t.fc_splits, (size_t)t.m_pad * d0.out, d0.d_b, d0.z, only ? nullptr : d0.h,
                                                 m.cfg.alpha_dense, n, d0.out, s));
-    // remaining (small) dense layers on the shared fp32 kernels
     const float* in = d0.h;
     for (size_t j = 1; j < m.dense.size(); ++j) {
         DenseLayer& D = m.dense[j];
@@ -188,16 +192,19 @@ int tensor_forward_chunk(Model& m, const float* x, int n, cudaStream_t s) {
         TP_LAUNCH(m, "splitk_reduce", launch_splitk_reduce(m.partials, splits, D.d_b, D.z, last ? nullptr : D.h, m.cfg.alpha_dense, n, D.out, s));
         in = D.h;
     }
+    TP_LAUNCH(m, "head", launch_head(m.dense.back().z, m.probs, m.cls, n, m.cfg.num_classes, m.cfg.head, s));
     return BCAD_OK;
 }
 
 int tensor_explain_chunk(Model& m, int n, const int32_t* class_idx, int grad_mode, float* heat, cudaStream_t s) {
     TensorPath& t = *m.tp;
     const ConvLayer& T = m.conv.back();
-    // dense backward down to dz1 (left in dense[0].h); no fc1 dgrad GEMM, no dA
-    TP_TRY(dense_backward(&m, n, class_idx, grad_mode, nullptr, s));
-    const float* dz1 = (m.dense.size() > 1) ? m.dense[0].h : m.d_top;
-    TP_LAUNCH(m, "alpha_shortcut_sgemm", launch_sgemm(dz1, t.d_S, t.alpha_raw, n, T.Cout, m.dense[0].out, false, 1, s));
+    if (!m.fused_head) {
+        // dense backward down to dz1 (left in dense[0].h); no fc1 dgrad GEMM, no dA
+        TP_TRY(dense_backward(&m, n, class_idx, grad_mode, nullptr, s));
+        const float* dz1 = (m.dense.size() > 1) ? m.dense[0].h : m.d_top;
+        TP_LAUNCH(m, "alpha_shortcut_sgemm", launch_sgemm(dz1, t.d_S, t.alpha_raw, n, T.Cout, m.dense[0].out, false, 1, s));
+    }
     const float inv_hw = 1.0f / ((float)T.Ho * (float)T.Wo);
     TP_LAUNCH(m, "cam_c8", launch_cam_c8(t.act, t.alpha_raw, inv_hw, m.alpha, m.cam_lo, m.mm, n, T.Ho, T.Wo, T.Cout, m.cam_splits, s));
     TP_LAUNCH(m, "upsample_norm", launch_upsample_norm(m.cam_lo, m.mm, m.cam_splits, heat, n, T.Ho, T.Wo, m.cfg.in_h, m.cfg.in_w, s));
