@@ -108,11 +108,12 @@ int launch_conv_first_pool(const float* x, const float* w9c, const float* bias, 
 //   Output rows are produced in pairs so the 2x2 max-pool happens in the epilogue (vertical max in registers,
 //   horizontal max with one shuffle); accumulators are double-buffered in TMEM so the epilogue of pair p
 //   overlaps the MMAs of pair p+1.
-//   Warp roles: 0 = bulk-copy producer, 1 = MMA issuer, 2..5 = epilogue (TMEM lane quadrant = warp % 4).
+//   Warp roles: 0 = bulk-copy producer, 1 = MMA issuer, 2..9 = epilogue (TMEM lane quadrant = warp % 4; the two
+//   warps of a quadrant split the channels, so every scheduler has two epilogue warps to hide latency).
 // =====================================================================================================
 constexpr int IG_XP = 136;            // pixel slots per ring row (>= 128 + 2 halo, multiple of 8)
 constexpr int IG_STAGES = 4;          // ring stages of 2 input rows
-constexpr int IG_THREADS = 192;
+constexpr int IG_THREADS = 320;         // producer warp, MMA warp, 8 epilogue warps (2 per scheduler)
 
 template <int CIN, int COUT>
 struct IgemmSmem {
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
     for (int i = tid; i < COUT; i += IG_THREADS) s_bias[i] = a.bias[i];
     if (tid == 0) {
         for (int i = 0; i < IG_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
         mbar_init(wbar, 1);
         fence_barrier_init();
     }
@@ -251,8 +252,10 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
             }
         }
     } else {
-        // ================================ epilogue (4 warps) ================================
+        // ================================ epilogue (8 warps) ================================
         const int quad = warp & 3;
+        const int half0 = (warp - 2) >> 2;              // which 32-channel half this warp owns
+        const bool max_form = a.alpha <= 1.f;           // LeakyReLU(v) = max(v, alpha v) for 0 <= alpha <= 1
         const int x = quad * 32 + lane;
         const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
         uint32_t acc_it = 0;
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
                 const int py = t0 >> 1, px = x >> 1;
                 const bool pool_ok = has1 && py < a.Hp && px < a.Wp && !(x & 1);
 #pragma unroll 1
-                for (int half = 0; half < COUT / 32; ++half) {
+                for (int half = half0; half < COUT / 32; half += 2) {
                     float v0[32], v1[32];
                     tmem_ld32(tmem + lane_off + j * (2 * COUT) + half * 32, v0);
                     tmem_ld32(tmem + lane_off + j * (2 * COUT) + COUT + half * 32, v1);
@@ -278,8 +281,9 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
 #pragma unroll
                     for (int q = 0; q < 32; ++q) {
                         const float bq = s_bias[half * 32 + q];
-                        v0[q] = leaky(v0[q] + bq, a.alpha);
-                        v1[q] = leaky(v1[q] + bq, a.alpha);
+                        const float t0v = v0[q] + bq, t1v = v1[q] + bq;
+                        v0[q] = max_form ? fmaxf(t0v, a.alpha * t0v) : leaky(t0v, a.alpha);
+                        v1[q] = max_form ? fmaxf(t1v, a.alpha * t1v) : leaky(t1v, a.alpha);
                     }
                     if (a.act != nullptr && x < a.Wo) {
 #pragma unroll
