@@ -59,6 +59,8 @@ void Model::free_all() {
         cudaStreamDestroy(xfer.s_in);
         cudaStreamDestroy(xfer.s_compute);
         cudaStreamDestroy(xfer.s_out);
+        if (xfer.h_small) cudaFreeHost(xfer.h_small);
+        xfer.h_small = nullptr;
         xfer.inited = false;
     }
     for (cudaEvent_t e : prof_pool) cudaEventDestroy(e);
@@ -656,6 +658,18 @@ int bcad_predict_explain_host(bcad_model* mm, const float* x_host, int B, const 
             X.inited = true;
         }
     }
+    // small outputs go through pinned staging sized for the whole call
+    const size_t per_img = (size_t)(2 * nc) * sizeof(float) + sizeof(int32_t);
+    if (X.h_small_bytes < per_img * B) {
+        if (X.h_small) cudaFreeHost(X.h_small);
+        X.h_small = nullptr;
+        X.h_small_bytes = 0;
+        BCAD_CUDA_CHECK(cudaMallocHost(&X.h_small, per_img * B));
+        X.h_small_bytes = per_img * B;
+    }
+    float* st_logits = reinterpret_cast<float*>(X.h_small);
+    float* st_probs = st_logits + (size_t)B * nc;
+    int32_t* st_cls = reinterpret_cast<int32_t*>(st_probs + (size_t)B * nc);
     const int nchunks = cdiv(B, X.chunk);
     for (int c = 0; c < nchunks; ++c) {
         const int slot = c & 1, b0 = c * X.chunk, n = std::min(X.chunk, B - b0);
@@ -675,13 +689,16 @@ int bcad_predict_explain_host(bcad_model* mm, const float* x_host, int B, const 
         BCAD_CUDA_CHECK(cudaEventRecord(X.compute_done[slot], X.s_compute));
         BCAD_CUDA_CHECK(cudaStreamWaitEvent(X.s_out, X.compute_done[slot], 0));
         if (heat_host) BCAD_CUDA_CHECK(cudaMemcpyAsync(heat_host + (size_t)b0 * hm, X.heat[slot], (size_t)n * hm * sizeof(float), cudaMemcpyDeviceToHost, X.s_out));
-        if (logits_host) BCAD_CUDA_CHECK(cudaMemcpyAsync(logits_host + (size_t)b0 * nc, X.logits[slot], (size_t)n * nc * sizeof(float), cudaMemcpyDeviceToHost, X.s_out));
-        if (probs_host) BCAD_CUDA_CHECK(cudaMemcpyAsync(probs_host + (size_t)b0 * nc, X.probs[slot], (size_t)n * nc * sizeof(float), cudaMemcpyDeviceToHost, X.s_out));
-        if (cls_host) BCAD_CUDA_CHECK(cudaMemcpyAsync(cls_host + b0, X.cls[slot], (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, X.s_out));
+        BCAD_CUDA_CHECK(cudaMemcpyAsync(st_logits + (size_t)b0 * nc, X.logits[slot], (size_t)n * nc * sizeof(float), cudaMemcpyDeviceToHost, X.s_out));
+        BCAD_CUDA_CHECK(cudaMemcpyAsync(st_probs + (size_t)b0 * nc, X.probs[slot], (size_t)n * nc * sizeof(float), cudaMemcpyDeviceToHost, X.s_out));
+        BCAD_CUDA_CHECK(cudaMemcpyAsync(st_cls + b0, X.cls[slot], (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, X.s_out));
         BCAD_CUDA_CHECK(cudaEventRecord(X.out_done[slot], X.s_out));
     }
     BCAD_CUDA_CHECK(cudaStreamSynchronize(X.s_out));
     BCAD_CUDA_CHECK(cudaStreamSynchronize(X.s_compute));
+    if (logits_host) memcpy(logits_host, st_logits, (size_t)B * nc * sizeof(float));
+    if (probs_host) memcpy(probs_host, st_probs, (size_t)B * nc * sizeof(float));
+    if (cls_host) memcpy(cls_host, st_cls, (size_t)B * sizeof(int32_t));
     return BCAD_OK;
 }
 

@@ -44,6 +44,10 @@ struct Xfer {                          // host-buffer pipeline (bcad_predict_exp
     float* probs[2] = {nullptr, nullptr};
     int32_t* cls[2] = {nullptr, nullptr};
     int32_t* cidx[2] = {nullptr, nullptr};
+    // pinned host staging for the small per-image outputs (user arrays may be pageable: a pageable D2H would
+    // block the host and serialise the chunk pipeline)
+    void* h_small = nullptr;
+    size_t h_small_bytes = 0;
 };
 
 struct TensorPath;                     // tensor_path.cu

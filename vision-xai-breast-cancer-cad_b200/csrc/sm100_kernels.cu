@@ -112,7 +112,7 @@ int launch_conv_first_pool(const float* x, const float* w9c, const float* bias, 
 //   warps of a quadrant split the channels, so every scheduler has two epilogue warps to hide latency).
 // =====================================================================================================
 constexpr int IG_XP = 136;            // pixel slots per ring row (>= 128 + 2 halo, multiple of 8)
-constexpr int IG_STAGES = 4;          // ring stages of 2 input rows
+constexpr int IG_STAGES = 4;          // ring stages of 2 input rows (power of two)
 constexpr int IG_THREADS = 320;         // producer warp, MMA warp, 8 epilogue warps (2 per scheduler)
 
 template <int CIN, int COUT>
@@ -222,23 +222,30 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
                     const uint32_t j = acc_it & 1;
                     if (acc_it >= 2) mbar_wait(&tempty[j], ((acc_it >> 1) - 1) & 1);
                     tc_fence_after();
+                    // descriptor templates: only the 14-bit start-address field changes between MMAs, and all the
+                    // per-tap offsets are compile-time constants after unrolling (the single issuing thread must
+                    // spend fewer cycles per MMA than the tensor core does: 32)
+                    constexpr uint64_t a_tmpl = ((uint64_t)(L::LBO >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
+                    constexpr uint64_t b_tmpl = ((uint64_t)((COUT * 16) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
+                    const uint64_t b_desc0 = b_tmpl | (uint64_t)((w_base & 0x3FFFFu) >> 4);
                     for (int r = 0; r < 2; ++r) {
                         if (2 * p + r >= nrows) break;
                         const uint32_t d_tmem = tmem + j * (2 * COUT) + r * COUT;
                         uint32_t acc = 0;
+#pragma unroll
                         for (int dy = 0; dy < 3; ++dy) {
                             const int i = 2 * p + r + dy;                    // band-local input row
                             const int in_row = y0 - a.pad + i;
                             uint32_t row_base;
                             if (in_row < 0 || in_row >= a.H) row_base = zero_base;
-                            else row_base = ring_base + (((g + (i >> 1) - p) % IG_STAGES) * 2 + (i & 1)) * L::ROWB;
+                            else row_base = ring_base + ((((g + (i >> 1) - p) & (IG_STAGES - 1)) << 1) + (i & 1)) * L::ROWB;
+                            const uint64_t a_desc0 = a_tmpl | (uint64_t)((row_base & 0x3FFFFu) >> 4);
 #pragma unroll
                             for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
                                 for (int ks = 0; ks < CIN / 16; ++ks) {
-                                    const uint64_t ad = make_smem_desc(row_base + ks * 2 * L::LBO + dx * 16, L::LBO, 128, LAYOUT_NONE);
-                                    const uint64_t bd = make_smem_desc(w_base + ((dy * 3 + dx) * L::CHUNKS + 2 * ks) * (COUT * 16),
-                                                                       COUT * 16, 128, LAYOUT_NONE);
+                                    const uint64_t ad = a_desc0 + (uint64_t)((ks * 2 * L::LBO + dx * 16) >> 4);
+                                    const uint64_t bd = b_desc0 + (uint64_t)((((dy * 3 + dx) * L::CHUNKS + 2 * ks) * (COUT * 16)) >> 4);
                                     umma_bf16(d_tmem, ad, bd, idesc, acc);
                                     acc = 1;
                                 }
