@@ -98,6 +98,163 @@ int launch_conv_first_pool(const float* x, const float* w9c, const float* bias, 
 }
 
 // =====================================================================================================
+// first conv block on the tensor core.  K = 9 taps is padded to 32 and the spare slots buy fp32-grade accuracy
+// for free: with x = x_hi + x_lo and w = w_hi + w_lo (fp16 pairs),
+//     A row = [x_hi(9) | x_lo(9) | x_hi(9) | 1 | 1 | 0 0 0],   B row = [w_hi(9) | w_hi(9) | w_lo(9) | b_hi | b_lo | 0 0 0]
+// gives x_hi w_hi + x_lo w_hi + x_hi w_lo + b (every product exact in the fp32 accumulator; the dropped x_lo w_lo
+// term is 2^-22 relative).  One CTA tile = 128 pooled pixels of one pooled row; the four members of each 2x2 pool
+// window are four accumulators of the SAME TMEM lane, so pooling is three max ops per channel with no shuffles.
+// The CUDA-core work left is the im2col row build (16 STS.128 / thread) and the pooled epilogue: ~4x fewer
+// instructions than 1152 FFMAs per pooled pixel.  128-thread CTAs, 4 per SM (TMEM 4 x 128 columns).
+// =====================================================================================================
+template <int COUT>
+__global__ void __launch_bounds__(128, 4)
+conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_img /*[4][COUT][16 B]*/,
+                     __half* __restrict__ out, int B, int H, int W, int pad, int Hp, int Wp, float alpha) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* s_a = smem;                          // 4 classes x [4 chunks][128 rows][16 B] = 32 KB
+    uint8_t* s_b = smem + 4 * 8192;               // [4 chunks][COUT][16 B]
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (4 * COUT * 16) / 16; i += 128) reinterpret_cast<uint4*>(s_b)[i] = reinterpret_cast<const uint4*>(w_img)[i];
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(&tmem_slot, 4 * COUT);
+        tmem_relinquish();
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    constexpr uint32_t idesc = make_idesc_f16(128, COUT);
+    constexpr uint64_t a_tmpl = ((uint64_t)(2048 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
+    constexpr uint64_t b_tmpl = ((uint64_t)((COUT * 16) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
+    const uint64_t a_desc0 = a_tmpl | (uint64_t)((smem_u32(s_a) & 0x3FFFFu) >> 4);
+    const uint64_t b_desc0 = b_tmpl | (uint64_t)((smem_u32(s_b) & 0x3FFFFu) >> 4);
+    const bool max_form = alpha <= 1.f;
+    const int xtiles = cdiv(Wp, 128);
+    const int n_tiles = B * Hp * xtiles;
+    const __half one = __float2half(1.f), zero = __float2half(0.f);
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int xt = tile % xtiles;
+        const int py = (tile / xtiles) % Hp;
+        const int b = tile / (xtiles * Hp);
+        const int px = xt * 128 + tid;
+        // ---- im2col rows of this thread's 2x2 pool window: 4 x 4 input patch, split hi/lo
+        __half hi[16], lo[16];
+        const float* xb = x + (size_t)b * H * W;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int iy = 2 * py - pad + r;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int ix = 2 * px - pad + c;
+                const float v = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xb + (size_t)iy * W + ix) : 0.f;
+                const __half h = __float2half_rn(v);
+                hi[r * 4 + c] = h;
+                lo[r * 4 + c] = __float2half_rn(v - __half2float(h));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {               // class q = (row parity, col parity) of the pool window
+            const int qr = q >> 1, qc = q & 1;
+            __half row[32];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int pi = (qr + t / 3) * 4 + (qc + t % 3);
+                row[t] = hi[pi];
+                row[9 + t] = lo[pi];
+                row[18 + t] = hi[pi];
+            }
+            row[27] = one; row[28] = one; row[29] = zero; row[30] = zero; row[31] = zero;
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                uint4 v;
+                v.x = (uint32_t)__half_as_ushort(row[ch * 8 + 0]) | ((uint32_t)__half_as_ushort(row[ch * 8 + 1]) << 16);
+                v.y = (uint32_t)__half_as_ushort(row[ch * 8 + 2]) | ((uint32_t)__half_as_ushort(row[ch * 8 + 3]) << 16);
+                v.z = (uint32_t)__half_as_ushort(row[ch * 8 + 4]) | ((uint32_t)__half_as_ushort(row[ch * 8 + 5]) << 16);
+                v.w = (uint32_t)__half_as_ushort(row[ch * 8 + 6]) | ((uint32_t)__half_as_ushort(row[ch * 8 + 7]) << 16);
+                *reinterpret_cast<uint4*>(s_a + q * 8192 + ch * 2048 + tid * 16) = v;
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+                    umma_bf16(tmem + q * COUT, a_desc0 + (uint64_t)((q * 8192 + ks * 4096) >> 4),
+                              b_desc0 + (uint64_t)((ks * 2 * COUT * 16) >> 4), idesc, ks);
+            umma_commit(&bar);
+        }
+        mbar_wait(&bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        // ---- epilogue: pool (3 max), LeakyReLU once, fp16 C8-planar store
+#pragma unroll 1
+        for (int c0 = 0; c0 < COUT; c0 += 16) {
+            float v0[16], v1[16], v2[16], v3[16];
+            tmem_ld16(tmem + lane_off + 0 * COUT + c0, v0);
+            tmem_ld16(tmem + lane_off + 1 * COUT + c0, v1);
+            tmem_ld16(tmem + lane_off + 2 * COUT + c0, v2);
+            tmem_ld16(tmem + lane_off + 3 * COUT + c0, v3);
+            tmem_ld_wait();
+            if (px < Wp) {
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {
+                        const int k0 = cc * 8 + e;
+                        float m0 = fmaxf(fmaxf(v0[k0], v1[k0]), fmaxf(v2[k0], v3[k0]));
+                        float m1 = fmaxf(fmaxf(v0[k0 + 1], v1[k0 + 1]), fmaxf(v2[k0 + 1], v3[k0 + 1]));
+                        m0 = max_form ? fmaxf(m0, alpha * m0) : leaky(m0, alpha);
+                        m1 = max_form ? fmaxf(m1, alpha * m1) : leaky(m1, alpha);
+                        pk[e >> 1] = pack_f16(m0, m1);
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(out) + (((size_t)b * Hp + py) * (COUT / 8) + (c0 / 8 + cc)) * Wp + px;
+                    *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();                            // TMEM + im2col buffer are reused by the next tile
+    }
+    if (warp == 0) tmem_dealloc(tmem, 4 * COUT);
+}
+
+int launch_conv_first_tc(const float* x, const uint8_t* w_img, __half* out, int B, int H, int W, int pad, int Cout,
+                         float alpha, int sms, cudaStream_t s) {
+    const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2, Hp = Ho / 2, Wp = Wo / 2;
+    const int n_tiles = B * Hp * cdiv(Wp, 128);
+    const int smem = 4 * 8192 + 4 * Cout * 16;
+    const int per_sm = Cout <= 32 ? 4 : 2;          // TMEM: 4*Cout columns per CTA
+    const int grid = n_tiles < sms * per_sm ? n_tiles : sms * per_sm;
+    switch (Cout) {
+        case 32:
+            BCAD_CUDA_CHECK(cudaFuncSetAttribute(conv_first_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            conv_first_tc_kernel<32><<<grid, 128, smem, s>>>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha);
+            break;
+        case 64:
+            BCAD_CUDA_CHECK(cudaFuncSetAttribute(conv_first_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            conv_first_tc_kernel<64><<<grid, 128, smem, s>>>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha);
+            break;
+        default: set_error("conv_first_tc: Cout %d not supported (32/64)", Cout); return BCAD_ERR_INVALID;
+    }
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+// =====================================================================================================
 // 3x3 convolution as implicit GEMM on tcgen05 (Cin in {16,32,64}, Cout = 64, map width <= 128)
 //
 //   M = 128 consecutive pixels of one output row, N = Cout, K = 9 taps x Cin.

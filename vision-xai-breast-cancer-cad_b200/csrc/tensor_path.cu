@@ -10,6 +10,7 @@
 //            (exact for first-index pooling: the un-pooled gradient of a window sums to the pooled gradient, so the
 //             dense gradient map dA never has to exist -- SURVEY P8), cam_c8 -> upsample_norm.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -28,6 +29,7 @@ struct TensorPath {
     int sms = 148;
     float* d_w0 = nullptr;          // first conv weights [9][Cout0] fp32
     float* d_b0 = nullptr;
+    uint8_t* d_w0_img = nullptr;    // tensor-core first conv: [4][Cout0][8] fp16 (hi/lo split weights + bias)
     uint8_t* d_w1_img = nullptr;    // igemm weight image (fp16)
     float* d_b1 = nullptr;
     uint8_t* d_fc_w = nullptr;      // fc1 W tiles
@@ -91,6 +93,25 @@ int tensor_path_commit(Model& m) {
         if (!t.d_b0) TP_TRY(m.alloc((void**)&t.d_b0, c0.Cout * 4));
         BCAD_CUDA_CHECK(cudaMemcpy(t.d_w0, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
         BCAD_CUDA_CHECK(cudaMemcpy(t.d_b0, c0.h_b.data(), c0.Cout * 4, cudaMemcpyHostToDevice));
+    }
+    // ---- conv0 tensor-core image: K = 32 slots per filter: [w_hi(9) | w_hi(9) | w_lo(9) | b_hi | b_lo | 0 0 0]
+    if (c0.Cout == 32 || c0.Cout == 64) {
+        std::vector<uint16_t> img((size_t)4 * c0.Cout * 8, 0);
+        auto put = [&](int f, int k, float v) { img[((size_t)(k >> 3) * c0.Cout + f) * 8 + (k & 7)] = f2h(v); };
+        for (int f = 0; f < c0.Cout; ++f) {
+            for (int tap = 0; tap < 9; ++tap) {
+                const float w = c0.h_w[(size_t)f * 9 + tap];
+                const float whi = h2f(f2h(w));
+                put(f, tap, whi);
+                put(f, 9 + tap, whi);
+                put(f, 18 + tap, w - whi);
+            }
+            const float bhi = h2f(f2h(c0.h_b[f]));
+            put(f, 27, bhi);
+            put(f, 28, c0.h_b[f] - bhi);
+        }
+        if (!t.d_w0_img) TP_TRY(m.alloc((void**)&t.d_w0_img, img.size() * 2));
+        BCAD_CUDA_CHECK(cudaMemcpy(t.d_w0_img, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
     }
     // ---- conv1 weight image: [tap*(Cin/8)+chunk][cout][8] fp16
     {
@@ -159,7 +180,10 @@ int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const in
     TensorPath& t = *m.tp;
     const ConvLayer& c0 = m.conv[0];
     const ConvLayer& c1 = m.conv[1];
-    TP_LAUNCH(m, "conv0_first_pool", launch_conv_first_pool(x, t.d_w0, t.d_b0, t.p1, n, c0.H, c0.W, m.cfg.pad, c0.Cout, m.cfg.alpha_conv, s));
+    if (t.d_w0_img != nullptr && getenv("BCAD_CONV0_CUDA_CORES") == nullptr)
+        TP_LAUNCH(m, "conv0_first_tcgen05", launch_conv_first_tc(x, t.d_w0_img, t.p1, n, c0.H, c0.W, m.cfg.pad, c0.Cout, m.cfg.alpha_conv, t.sms, s));
+    else
+        TP_LAUNCH(m, "conv0_first_pool", launch_conv_first_pool(x, t.d_w0, t.d_b0, t.p1, n, c0.H, c0.W, m.cfg.pad, c0.Cout, m.cfg.alpha_conv, s));
     IgemmArgs a;
     a.in = t.p1; a.w_img = t.d_w1_img; a.bias = t.d_b1; a.act = t.act; a.pool_fc = t.fc_a; a.pool_c8 = nullptr;
     a.B = n; a.H = c1.H; a.W = c1.W; a.Ho = c1.Ho; a.Wo = c1.Wo; a.Hp = c1.Hp; a.Wp = c1.Wp; a.pad = m.cfg.pad;
@@ -167,6 +191,11 @@ int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const in
     if (a.band_rows > c1.Ho) a.band_rows = cdiv(c1.Ho, 2) * 2;
     a.bands = cdiv(c1.Ho, a.band_rows);
     a.alpha = m.cfg.alpha_conv;
+    if (const char* dbg = getenv("BCAD_DEBUG_SKIP_STORES")) {      // timing experiments only (results are garbage)
+        const int v = atoi(dbg);
+        if (v & 1) a.act = nullptr;
+        if (v & 2) a.pool_fc = nullptr;
+    }
     TP_LAUNCH(m, "conv1_igemm_tcgen05", launch_conv_igemm(a, c1.Cin, c1.Cout, t.sms, s));
     // fc1
     DenseLayer& d0 = m.dense[0];
