@@ -824,31 +824,43 @@ upsample_norm_sep_kernel(const float* __restrict__ cam_lo, const float* __restri
     const float* lo = cam_lo + (size_t)b * h * w;
     for (int i = tid; i < h * w; i += blockDim.x) s_lo[i] = (lo[i] - mn) / denom;
     __syncthreads();
-    for (int i = tid; i < h * W; i += blockDim.x) {
-        const int y = i / W, ox = i - y * W;
-        const float fx = s_fx[ox];
-        s_hr[i] = s_lo[y * w + s_x0[ox]] * (1.f - fx) + s_lo[y * w + s_x1[ox]] * fx;
+    // (row, column) of element tid + k*blockDim advance incrementally: no integer division in the hot loops
+    const int step_x = (int)blockDim.x % W, step_y = (int)blockDim.x / W;
+    {
+        int y = tid / W, ox = tid - y * W;
+        for (int i = tid; i < h * W; i += blockDim.x) {
+            const float fx = s_fx[ox];
+            s_hr[i] = s_lo[y * w + s_x0[ox]] * (1.f - fx) + s_lo[y * w + s_x1[ox]] * fx;
+            ox += step_x; y += step_y;
+            if (ox >= W) { ox -= W; ++y; }
+        }
     }
     __syncthreads();
     float vmin = 3.4e38f, vmax = -3.4e38f;
     const int npix = H * W;
-    for (int i = tid; i < npix; i += blockDim.x) {
-        const int oy = i / W, ox = i - oy * W;
-        const float fy = s_fy[oy];
-        const float v = s_hr[s_y0[oy] + ox] * (1.f - fy) + s_hr[s_y1[oy] + ox] * fy;
-        vmin = fminf(vmin, v);
-        vmax = fmaxf(vmax, v);
+    {
+        int oy = tid / W, ox = tid - oy * W;
+        for (int i = tid; i < npix; i += blockDim.x) {
+            const float fy = s_fy[oy];
+            const float v = s_hr[s_y0[oy] + ox] * (1.f - fy) + s_hr[s_y1[oy] + ox] * fy;
+            vmin = fminf(vmin, v);
+            vmax = fmaxf(vmax, v);
+            ox += step_x; oy += step_y;
+            if (ox >= W) { ox -= W; ++oy; }
+        }
     }
     block_minmax(vmin, vmax, s_red);
-    const float inv = 1.f / (1e-7f + (vmax - vmin));
     const float denom2 = 1e-7f + (vmax - vmin);
     float* ob = out + (size_t)b * npix;
-    (void)inv;
-    for (int i = tid; i < npix; i += blockDim.x) {
-        const int oy = i / W, ox = i - oy * W;
-        const float fy = s_fy[oy];
-        const float v = s_hr[s_y0[oy] + ox] * (1.f - fy) + s_hr[s_y1[oy] + ox] * fy;
-        ob[i] = (v - vmin) / denom2;
+    {
+        int oy = tid / W, ox = tid - oy * W;
+        for (int i = tid; i < npix; i += blockDim.x) {
+            const float fy = s_fy[oy];
+            const float v = s_hr[s_y0[oy] + ox] * (1.f - fy) + s_hr[s_y1[oy] + ox] * fy;
+            ob[i] = (v - vmin) / denom2;
+            ox += step_x; oy += step_y;
+            if (ox >= W) { ox -= W; ++oy; }
+        }
     }
 }
 

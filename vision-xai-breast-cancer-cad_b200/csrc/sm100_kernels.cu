@@ -19,6 +19,8 @@ namespace bcad {
 
 using namespace sm100;
 
+__device__ __forceinline__ uint32_t h2u(const __half2& h) { return *reinterpret_cast<const uint32_t*>(&h); }
+
 // =====================================================================================================
 // first conv block (Cin = 1, 3x3): CUDA cores, fused bias + LeakyReLU + 2x2 max-pool, fp16 C8-planar out.
 // K = 9 is too skinny for the tensor core; the block is ~6 % of the network's MACs.
@@ -278,11 +280,13 @@ struct IgemmSmem {
     static constexpr int LBO = IG_XP * 16;                 // bytes between channel octets of one row
     static constexpr int ROWB = CHUNKS * LBO;              // bytes per ring row
     static constexpr int WBYTES = 9 * CHUNKS * COUT * 16;  // weight image
-    static constexpr int OFF_W = 0;
-    static constexpr int OFF_ZERO = OFF_W + WBYTES;
+    static constexpr int BIAS_TILE = 2 * COUT * 16;         // B operand of the bias K-step: rows {b_hi, b_lo, 0...}
+    static constexpr int ONES_TILE = 2 * 128 * 16;          // A operand of the bias K-step: rows {1, 1, 0...}
+    static constexpr int OFF_W = 0;                         // weight image followed by the bias tile (one bulk copy)
+    static constexpr int OFF_ONES = OFF_W + WBYTES + BIAS_TILE;
+    static constexpr int OFF_ZERO = OFF_ONES + ONES_TILE;
     static constexpr int OFF_RING = OFF_ZERO + ROWB;
-    static constexpr int OFF_BIAS = OFF_RING + IG_STAGES * 2 * ROWB;
-    static constexpr int OFF_BAR = OFF_BIAS + COUT * 4;
+    static constexpr int OFF_BAR = OFF_RING + IG_STAGES * 2 * ROWB;
     static constexpr int TOTAL = OFF_BAR + 256;
 };
 
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
     uint8_t* s_w = smem + L::OFF_W;
     uint8_t* s_zero = smem + L::OFF_ZERO;
     uint8_t* s_ring = smem + L::OFF_RING;
-    float* s_bias = reinterpret_cast<float*>(smem + L::OFF_BIAS);
+    uint8_t* s_ones = smem + L::OFF_ONES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
     uint64_t* full = bars;                       // [IG_STAGES] producer -> MMA
     uint64_t* empty = bars + IG_STAGES;          // [IG_STAGES] MMA -> producer
@@ -307,7 +311,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
     // ---- one-time setup: zero the halo slots + zero row, barriers, TMEM
     for (int i = tid; i < (L::ROWB * (1 + IG_STAGES * 2)) / 16; i += IG_THREADS)
         reinterpret_cast<uint4*>(s_zero)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < COUT; i += IG_THREADS) s_bias[i] = a.bias[i];
+    for (int i = tid; i < L::ONES_TILE / 16; i += IG_THREADS)      // chunk 0: halves {1,1,0,0,0,0,0,0}; chunk 1: zeros
+        reinterpret_cast<uint4*>(s_ones)[i] = (i < 128) ? make_uint4(0x3C003C00u, 0, 0, 0) : make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         for (int i = 0; i < IG_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
@@ -330,9 +335,10 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
     if (warp == 0) {
         // ================================ producer ================================
         if (lane == 0) {
-            mbar_arrive_expect_tx(wbar, L::WBYTES);
-            for (int off = 0; off < L::WBYTES; off += 16384)
-                bulk_g2s(s_w + off, a.w_img + off, min(16384, L::WBYTES - off), wbar);
+            constexpr int WB = L::WBYTES + L::BIAS_TILE;
+            mbar_arrive_expect_tx(wbar, WB);
+            for (int off = 0; off < WB; off += 16384)
+                bulk_g2s(s_w + off, a.w_img + off, min(16384, WB - off), wbar);
             uint32_t g = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int b = item / a.bands, band = item % a.bands;
@@ -385,10 +391,14 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
                     constexpr uint64_t a_tmpl = ((uint64_t)(L::LBO >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
                     constexpr uint64_t b_tmpl = ((uint64_t)((COUT * 16) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
                     const uint64_t b_desc0 = b_tmpl | (uint64_t)((w_base & 0x3FFFFu) >> 4);
+                    constexpr uint64_t ones_tmpl = ((uint64_t)((128 * 16) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
+                    const uint64_t ones_desc = ones_tmpl | (uint64_t)((smem_u32(s_ones) & 0x3FFFFu) >> 4);
                     for (int r = 0; r < 2; ++r) {
                         if (2 * p + r >= nrows) break;
                         const uint32_t d_tmem = tmem + j * (2 * COUT) + r * COUT;
-                        uint32_t acc = 0;
+                        // bias K-step: D = ones x {b_hi, b_lo} (initialises the accumulator with the fp32-exact bias)
+                        umma_bf16(d_tmem, ones_desc, b_desc0 + (uint64_t)(L::WBYTES >> 4), idesc, 0u);
+                        uint32_t acc = 1;
 #pragma unroll
                         for (int dy = 0; dy < 3; ++dy) {
                             const int i = 2 * p + r + dy;                    // band-local input row
@@ -419,7 +429,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
         // ================================ epilogue (8 warps) ================================
         const int quad = warp & 3;
         const int half0 = (warp - 2) >> 2;              // which 32-channel half this warp owns
-        const bool max_form = a.alpha <= 1.f;           // LeakyReLU(v) = max(v, alpha v) for 0 <= alpha <= 1
+        const __half2 alpha2 = __float2half2_rn(a.alpha);
         const int x = quad * 32 + lane;
         const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
         uint32_t acc_it = 0;
@@ -442,32 +452,34 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
                     tmem_ld32(tmem + lane_off + j * (2 * COUT) + half * 32, v0);
                     tmem_ld32(tmem + lane_off + j * (2 * COUT) + COUT + half * 32, v1);
                     tmem_ld_wait();
+                    // the bias is already in the accumulator; round to fp16 once, then LeakyReLU and the pool run on
+                    // packed half2 (max commutes with the rounding; LeakyReLU(v) = max(v, alpha v), 0 <= alpha <= 1)
+                    __half2 a0[16], a1[16];
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) {
-                        const float bq = s_bias[half * 32 + q];
-                        const float t0v = v0[q] + bq, t1v = v1[q] + bq;
-                        v0[q] = max_form ? fmaxf(t0v, a.alpha * t0v) : leaky(t0v, a.alpha);
-                        v1[q] = max_form ? fmaxf(t1v, a.alpha * t1v) : leaky(t1v, a.alpha);
+                    for (int q = 0; q < 16; ++q) {
+                        const __half2 h0 = __floats2half2_rn(v0[2 * q], v0[2 * q + 1]);
+                        const __half2 h1 = __floats2half2_rn(v1[2 * q], v1[2 * q + 1]);
+                        a0[q] = __hmax2(h0, __hmul2(h0, alpha2));
+                        a1[q] = __hmax2(h1, __hmul2(h1, alpha2));
                     }
                     if (a.act != nullptr && x < a.Wo) {
 #pragma unroll
                         for (int cc = 0; cc < 4; ++cc) {
                             const int chunk = half * 4 + cc;
                             uint4* d0 = reinterpret_cast<uint4*>(a.act) + (((size_t)b * a.Ho + t0) * (COUT / 8) + chunk) * a.Wo + x;
-                            *d0 = make_uint4(pack_f16(v0[cc * 8], v0[cc * 8 + 1]), pack_f16(v0[cc * 8 + 2], v0[cc * 8 + 3]),
-                                             pack_f16(v0[cc * 8 + 4], v0[cc * 8 + 5]), pack_f16(v0[cc * 8 + 6], v0[cc * 8 + 7]));
+                            *d0 = make_uint4(h2u(a0[cc * 4]), h2u(a0[cc * 4 + 1]), h2u(a0[cc * 4 + 2]), h2u(a0[cc * 4 + 3]));
                             if (has1) {
                                 uint4* d1 = d0 + (size_t)(COUT / 8) * a.Wo;
-                                *d1 = make_uint4(pack_f16(v1[cc * 8], v1[cc * 8 + 1]), pack_f16(v1[cc * 8 + 2], v1[cc * 8 + 3]),
-                                                 pack_f16(v1[cc * 8 + 4], v1[cc * 8 + 5]), pack_f16(v1[cc * 8 + 6], v1[cc * 8 + 7]));
+                                *d1 = make_uint4(h2u(a1[cc * 4]), h2u(a1[cc * 4 + 1]), h2u(a1[cc * 4 + 2]), h2u(a1[cc * 4 + 3]));
                             }
                         }
                     }
                     // 2x2 max-pool: vertical in registers, horizontal with the neighbouring lane
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) {
-                        const float m = fmaxf(v0[q], v1[q]);
-                        v0[q] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                    for (int q = 0; q < 16; ++q) {
+                        const __half2 m = __hmax2(a0[q], a1[q]);
+                        const uint32_t o = __shfl_xor_sync(0xffffffffu, h2u(m), 1);
+                        a0[q] = __hmax2(m, *reinterpret_cast<const __half2*>(&o));
                     }
                     if (pool_ok) {
                         if (a.pool_fc != nullptr) {
@@ -478,8 +490,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
                             for (int cc = 0; cc < 4; ++cc) {
                                 const int chunk = (half * 4 + cc) ^ (row & 7);
                                 *reinterpret_cast<uint4*>(base + chunk * 16) =
-                                    make_uint4(pack_f16(v0[cc * 8], v0[cc * 8 + 1]), pack_f16(v0[cc * 8 + 2], v0[cc * 8 + 3]),
-                                               pack_f16(v0[cc * 8 + 4], v0[cc * 8 + 5]), pack_f16(v0[cc * 8 + 6], v0[cc * 8 + 7]));
+                                    make_uint4(h2u(a0[cc * 4]), h2u(a0[cc * 4 + 1]), h2u(a0[cc * 4 + 2]), h2u(a0[cc * 4 + 3]));
                             }
                         }
                         if (a.pool_c8 != nullptr) {
@@ -487,8 +498,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
                             for (int cc = 0; cc < 4; ++cc) {
                                 const int chunk = half * 4 + cc;
                                 uint4* d = reinterpret_cast<uint4*>(a.pool_c8) + (((size_t)b * a.Hp + py) * (COUT / 8) + chunk) * a.Wp + px;
-                                *d = make_uint4(pack_f16(v0[cc * 8], v0[cc * 8 + 1]), pack_f16(v0[cc * 8 + 2], v0[cc * 8 + 3]),
-                                                pack_f16(v0[cc * 8 + 4], v0[cc * 8 + 5]), pack_f16(v0[cc * 8 + 6], v0[cc * 8 + 7]));
+                                *d = make_uint4(h2u(a0[cc * 4]), h2u(a0[cc * 4 + 1]), h2u(a0[cc * 4 + 2]), h2u(a0[cc * 4 + 3]));
                             }
                         }
                     }

@@ -15,8 +15,7 @@ int launch_conv_first_tc(const float* x, const uint8_t* w_img, __half* out, int 
 
 struct IgemmArgs {
     const __half* in;      // C8 planar [B][H][Cin/8][W][8]
-    const uint8_t* w_img;         // [9*(Cin/8)][Cout][16 B]
-    const float* bias;            // [Cout]
+    const uint8_t* w_img;         // [9*(Cin/8)][Cout][16 B] weights, then the bias tile [2][Cout][16 B] rows {b_hi, b_lo, 0..}
     __half* act;           // C8 planar [B][Ho][Cout/8][Wo][8] post-activation, or nullptr
     uint8_t* pool_fc;             // pooled output as fc1 A tiles, or nullptr
     __half* pool_c8;       // pooled output C8 planar [B][Hp][Cout/8][Wp][8], or nullptr

@@ -67,6 +67,7 @@ int tensor_path_supported(const Model& m) {
     BCAD_REQUIRE(c1.k == 3 && c1.Cout == 64, "precision=F16: second conv block must be 3x3 with 64 filters (got k=%d, %d)", c1.k, c1.Cout);
     BCAD_REQUIRE(c1.W <= 128, "precision=F16: second conv block input width %d > 128", c1.W);
     BCAD_REQUIRE(c.pad == 0 || c.pad == 1, "precision=F16: pad must be 0 or 1");
+    BCAD_REQUIRE(c.alpha_conv <= 1.f, "precision=F16: conv LeakyReLU slope must be <= 1 (max(v, alpha v) form)");
     BCAD_REQUIRE(c.pool_ties == BCAD_TIES_FIRST,
                  "precision=F16: the alpha shortcut needs first-index pooling (TIES_FIRST); the tie-duplicating NumPy flavour runs on BCAD_PREC_FP32");
     const int units = m.dense[0].out;
@@ -116,17 +117,21 @@ int tensor_path_commit(Model& m) {
     // ---- conv1 weight image: [tap*(Cin/8)+chunk][cout][8] fp16
     {
         const int chunks = c1.Cin / 8;
-        std::vector<uint16_t> img((size_t)9 * chunks * c1.Cout * 8);
+        const size_t wel = (size_t)9 * chunks * c1.Cout * 8;
+        std::vector<uint16_t> img(wel + (size_t)2 * c1.Cout * 8, 0);      // + bias tile [2 chunks][Cout][8]
         for (int tap = 0; tap < 9; ++tap)
             for (int ch = 0; ch < chunks; ++ch)
                 for (int f = 0; f < c1.Cout; ++f)
                     for (int e = 0; e < 8; ++e)
                         img[(((size_t)tap * chunks + ch) * c1.Cout + f) * 8 + e] =
                             f2h(c1.h_w[((size_t)f * 9 + tap) * c1.Cin + ch * 8 + e]);
+        for (int f = 0; f < c1.Cout; ++f) {                                 // bias K-step rows: {b_hi, b_lo, 0 ...}
+            const float bhi = h2f(f2h(c1.h_b[f]));
+            img[wel + (size_t)f * 8 + 0] = f2h(bhi);
+            img[wel + (size_t)f * 8 + 1] = f2h(c1.h_b[f] - bhi);
+        }
         if (!t.d_w1_img) TP_TRY(m.alloc((void**)&t.d_w1_img, img.size() * 2));
-        if (!t.d_b1) TP_TRY(m.alloc((void**)&t.d_b1, c1.Cout * 4));
         BCAD_CUDA_CHECK(cudaMemcpy(t.d_w1_img, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
-        BCAD_CUDA_CHECK(cudaMemcpy(t.d_b1, c1.h_b.data(), c1.Cout * 4, cudaMemcpyHostToDevice));
     }
     // ---- fc1: SW128 tiles [pixel][unit][128 B]; K index inside a tile = channel; S = per-channel column sums
     {
@@ -185,7 +190,7 @@ int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const in
     else
         TP_LAUNCH(m, "conv0_first_pool", launch_conv_first_pool(x, t.d_w0, t.d_b0, t.p1, n, c0.H, c0.W, m.cfg.pad, c0.Cout, m.cfg.alpha_conv, s));
     IgemmArgs a;
-    a.in = t.p1; a.w_img = t.d_w1_img; a.bias = t.d_b1; a.act = t.act; a.pool_fc = t.fc_a; a.pool_c8 = nullptr;
+    a.in = t.p1; a.w_img = t.d_w1_img; a.act = t.act; a.pool_fc = t.fc_a; a.pool_c8 = nullptr;
     a.B = n; a.H = c1.H; a.W = c1.W; a.Ho = c1.Ho; a.Wo = c1.Wo; a.Hp = c1.Hp; a.Wp = c1.Wp; a.pad = m.cfg.pad;
     a.band_rows = 64;
     if (a.band_rows > c1.Ho) a.band_rows = cdiv(c1.Ho, 2) * 2;
