@@ -144,25 +144,45 @@ conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_
     const int n_tiles = B * Hp * xtiles;
     const __half one = __float2half(1.f), zero = __float2half(0.f);
     uint32_t phase = 0;
+    // input patch of a tile: 4 x 4 fp32 values per thread (zero outside the image); the loads of tile t+1 are
+    // issued before the epilogue of tile t so their latency hides behind it
+    auto load_patch = [&](int tile, float (&v)[16]) {
+        const int xt = tile % xtiles;
+        const int py = (tile / xtiles) % Hp;
+        const int b = tile / (xtiles * Hp);
+        const int px = xt * 128 + tid;
+        const float* xb = x + (size_t)b * H * W;
+        const int iy0 = 2 * py - pad, ix0 = 2 * px - pad;
+        if (iy0 >= 0 && iy0 + 3 < H && ix0 >= 0 && ix0 + 3 < W) {
+            const float* p0 = xb + (size_t)iy0 * W + ix0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) v[r * 4 + c] = __ldg(p0 + (size_t)r * W + c);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int iy = iy0 + r, ix = ix0 + c;
+                    v[r * 4 + c] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xb + (size_t)iy * W + ix) : 0.f;
+                }
+        }
+    };
+    float patch[16];
+    if ((int)blockIdx.x < n_tiles) load_patch(blockIdx.x, patch);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int xt = tile % xtiles;
         const int py = (tile / xtiles) % Hp;
         const int b = tile / (xtiles * Hp);
         const int px = xt * 128 + tid;
-        // ---- im2col rows of this thread's 2x2 pool window: 4 x 4 input patch, split hi/lo
+        // ---- im2col rows of this thread's 2x2 pool window, split hi/lo
         __half hi[16], lo[16];
-        const float* xb = x + (size_t)b * H * W;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int iy = 2 * py - pad + r;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int ix = 2 * px - pad + c;
-                const float v = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xb + (size_t)iy * W + ix) : 0.f;
-                const __half h = __float2half_rn(v);
-                hi[r * 4 + c] = h;
-                lo[r * 4 + c] = __float2half_rn(v - __half2float(h));
-            }
+        for (int e = 0; e < 16; ++e) {
+            const __half h = __float2half_rn(patch[e]);
+            hi[e] = h;
+            lo[e] = __float2half_rn(patch[e] - __half2float(h));
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {               // class q = (row parity, col parity) of the pool window
@@ -198,6 +218,7 @@ conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_
                               b_desc0 + (uint64_t)((ks * 2 * COUT * 16) >> 4), idesc, ks);
             umma_commit(&bar);
         }
+        if (tile + (int)gridDim.x < n_tiles) load_patch(tile + gridDim.x, patch);     // prefetch the next tile's inputs
         mbar_wait(&bar, phase);
         phase ^= 1;
         tc_fence_after();
@@ -271,11 +292,12 @@ int launch_conv_first_tc(const float* x, const uint8_t* w_img, __half* out, int 
 //   warps of a quadrant split the channels, so every scheduler has two epilogue warps to hide latency).
 // =====================================================================================================
 constexpr int IG_XP = 136;            // pixel slots per ring row (>= 128 + 2 halo, multiple of 8)
-constexpr int IG_STAGES = 4;          // ring stages of 2 input rows (power of two)
+constexpr int ig_stages(int cin) { return cin >= 64 ? 3 : 4; }   // ring stages of 2 input rows (smem budget)
 constexpr int IG_THREADS = 320;         // producer warp, MMA warp, 8 epilogue warps (2 per scheduler)
 
 template <int CIN, int COUT>
 struct IgemmSmem {
+    static constexpr int STAGES = ig_stages(CIN);
     static constexpr int CHUNKS = CIN / 8;
     static constexpr int LBO = IG_XP * 16;                 // bytes between channel octets of one row
     static constexpr int ROWB = CHUNKS * LBO;              // bytes per ring row
@@ -286,13 +308,14 @@ struct IgemmSmem {
     static constexpr int OFF_ONES = OFF_W + WBYTES + BIAS_TILE;
     static constexpr int OFF_ZERO = OFF_ONES + ONES_TILE;
     static constexpr int OFF_RING = OFF_ZERO + ROWB;
-    static constexpr int OFF_BAR = OFF_RING + IG_STAGES * 2 * ROWB;
+    static constexpr int OFF_BAR = OFF_RING + STAGES * 2 * ROWB;
     static constexpr int TOTAL = OFF_BAR + 256;
 };
 
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) {
     using L = IgemmSmem<CIN, COUT>;
+    constexpr int IG_STAGES = L::STAGES;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* s_w = smem + L::OFF_W;
     uint8_t* s_zero = smem + L::OFF_ZERO;
@@ -394,7 +417,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
                     constexpr uint64_t ones_tmpl = ((uint64_t)((128 * 16) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
                     const uint64_t ones_desc = ones_tmpl | (uint64_t)((smem_u32(s_ones) & 0x3FFFFu) >> 4);
                     for (int r = 0; r < 2; ++r) {
-                        if (2 * p + r >= nrows) break;
+                        if (2 * p + r >= nrows || (a.debug & 8)) break;     // debug bit 3: timing experiment without MMAs
                         const uint32_t d_tmem = tmem + j * (2 * COUT) + r * COUT;
                         // bias K-step: D = ones x {b_hi, b_lo} (initialises the accumulator with the fp32-exact bias)
                         umma_bf16(d_tmem, ones_desc, b_desc0 + (uint64_t)(L::WBYTES >> 4), idesc, 0u);
@@ -405,7 +428,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
                             const int in_row = y0 - a.pad + i;
                             uint32_t row_base;
                             if (in_row < 0 || in_row >= a.H) row_base = zero_base;
-                            else row_base = ring_base + ((((g + (i >> 1) - p) & (IG_STAGES - 1)) << 1) + (i & 1)) * L::ROWB;
+                            else row_base = ring_base + ((((g + (i >> 1) - p) % IG_STAGES) << 1) + (i & 1)) * L::ROWB;
                             const uint64_t a_desc0 = a_tmpl | (uint64_t)((row_base & 0x3FFFFu) >> 4);
 #pragma unroll
                             for (int dx = 0; dx < 3; ++dx)
@@ -442,6 +465,12 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
                 const uint32_t j = acc_it & 1;
                 mbar_wait(&tfull[j], (acc_it >> 1) & 1);
                 tc_fence_after();
+                if (a.debug & 4) {                         // timing experiment: epilogue does nothing
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[j]);
+                    continue;
+                }
                 const int t0 = y0 + 2 * p;
                 const bool has1 = (2 * p + 1 < nrows);
                 const int py = t0 >> 1, px = x >> 1;

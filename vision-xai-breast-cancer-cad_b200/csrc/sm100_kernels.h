@@ -22,6 +22,7 @@ struct IgemmArgs {
     int B, H, W, Ho, Wo, Hp, Wp, pad;
     int bands, band_rows;         // work items per image; output rows per item (even)
     float alpha;
+    int debug;                    // timing experiments only: 1 no act store, 2 no pool store, 4 empty epilogue, 8 no MMA
 };
 int launch_conv_igemm(const IgemmArgs& a, int Cin, int Cout, int sms, cudaStream_t s);
 

@@ -196,10 +196,11 @@ int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const in
     if (a.band_rows > c1.Ho) a.band_rows = cdiv(c1.Ho, 2) * 2;
     a.bands = cdiv(c1.Ho, a.band_rows);
     a.alpha = m.cfg.alpha_conv;
+    a.debug = 0;
     if (const char* dbg = getenv("BCAD_DEBUG_SKIP_STORES")) {      // timing experiments only (results are garbage)
-        const int v = atoi(dbg);
-        if (v & 1) a.act = nullptr;
-        if (v & 2) a.pool_fc = nullptr;
+        a.debug = atoi(dbg);
+        if (a.debug & 1) a.act = nullptr;
+        if (a.debug & 2) a.pool_fc = nullptr;
     }
     TP_LAUNCH(m, "conv1_igemm_tcgen05", launch_conv_igemm(a, c1.Cin, c1.Cout, t.sms, s));
     // fc1
