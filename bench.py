@@ -84,7 +84,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.idx), "-lms", "25"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -353,7 +353,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="images per GPU per step")

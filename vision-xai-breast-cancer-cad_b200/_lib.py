@@ -60,6 +60,7 @@ _SIGNATURES = {
     "bcad_uses_tensor_path": (C.c_int, [_P]),
     "bcad_set_profiling": (C.c_int, [_P, C.c_int]),
     "bcad_selftest_umma": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, _P]),
+    "bcad_selftest_umma_bench": (C.c_int, [_P, _P, _P]),
     "bcad_profile_count": (C.c_int, [_P]),
     "bcad_profile_get": (C.c_int, [_P, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_float)]),
 }

@@ -1,6 +1,7 @@
 // libbcad C-ABI: model handle, weight packing, and the predict / predict+Grad-CAM drivers.
 // Reference interfaces behind each entry point are cited in include/bcad.h.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -636,7 +637,10 @@ int bcad_predict_explain_host(bcad_model* mm, const float* x_host, int B, const 
     Xfer& X = m->xfer;
     const int nc = m->cfg.num_classes;
     const size_t img = (size_t)m->cfg.in_h * m->cfg.in_w * m->cfg.in_c, hm = (size_t)m->cfg.in_h * m->cfg.in_w;
-    const int chunk = std::min(m->cfg.max_batch, std::max(1, m->cfg.max_batch >= 256 ? m->cfg.max_batch / 4 : m->cfg.max_batch));
+    // transfer/compute chunk: small enough that the PCIe pipeline fills quickly (the link, ~52 GB/s per direction, is the
+    // end-to-end bound), large enough to keep the kernels efficient.  BCAD_HOST_CHUNK overrides (tuning).
+    int chunk = std::min(m->cfg.max_batch, 64);
+    if (const char* e = getenv("BCAD_HOST_CHUNK")) chunk = std::max(1, std::min(m->cfg.max_batch, atoi(e)));
     {
         std::lock_guard<std::mutex> lock(m->mu);
         if (!X.inited) {

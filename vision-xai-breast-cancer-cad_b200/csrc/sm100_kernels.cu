@@ -102,7 +102,7 @@ int launch_conv_first_pool(const float* x, const float* w9c, const float* bias, 
 // =====================================================================================================
 // first conv block on the tensor core.  K = 9 taps is padded to 32 and the spare slots buy fp32-grade accuracy
 // for free: with x = x_hi + x_lo and w = w_hi + w_lo (fp16 pairs),
-//     A row = [x_hi(9) | x_lo(9) | x_hi(9) | 1 | 1 | 0 0 0],   B row = [w_hi(9) | w_hi(9) | w_lo(9) | b_hi | b_lo | 0 0 0]
+//     A row = [x_hi(9) 1 | x_lo(9) 1 | x_hi(9) 0 0 0],   B row = [w_hi(9) b_hi | w_hi(9) b_lo | w_lo(9) 0 0 0]
 // gives x_hi w_hi + x_lo w_hi + x_hi w_lo + b (every product exact in the fp32 accumulator; the dropped x_lo w_lo
 // term is 2^-22 relative).  One CTA tile = 128 pooled pixels of one pooled row; the four members of each 2x2 pool
 // window are four accumulators of the SAME TMEM lane, so pooling is three max ops per channel with no shuffles.
@@ -142,7 +142,6 @@ conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_
     const bool max_form = alpha <= 1.f;
     const int xtiles = cdiv(Wp, 128);
     const int n_tiles = B * Hp * xtiles;
-    const __half one = __float2half(1.f), zero = __float2half(0.f);
     uint32_t phase = 0;
     // input patch of a tile: 4 x 4 fp32 values per thread (zero outside the image); the loads of tile t+1 are
     // issued before the epilogue of tile t so their latency hides behind it
@@ -176,35 +175,33 @@ conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_
         const int py = (tile / xtiles) % Hp;
         const int b = tile / (xtiles * Hp);
         const int px = xt * 128 + tid;
-        // ---- im2col rows of this thread's 2x2 pool window, split hi/lo
-        __half hi[16], lo[16];
+        // ---- im2col rows of this thread's 2x2 pool window.  K slots (matching the weight image):
+        //      [x(9) 1 | x_lo(9) 1 | x(9) 0 0 0]  -- cvt.rn.f16x2 turns an fp32 pair straight into one packed word
+        float lo[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            const __half h = __float2half_rn(patch[e]);
-            hi[e] = h;
-            lo[e] = __float2half_rn(patch[e] - __half2float(h));
-        }
+        for (int e = 0; e < 16; ++e) lo[e] = patch[e] - __half2float(__float2half_rn(patch[e]));
 #pragma unroll
         for (int q = 0; q < 4; ++q) {               // class q = (row parity, col parity) of the pool window
             const int qr = q >> 1, qc = q & 1;
-            __half row[32];
+            float xt[9], lt[9];
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
                 const int pi = (qr + t / 3) * 4 + (qc + t % 3);
-                row[t] = hi[pi];
-                row[9 + t] = lo[pi];
-                row[18 + t] = hi[pi];
+                xt[t] = patch[pi];
+                lt[t] = lo[pi];
             }
-            row[27] = one; row[28] = one; row[29] = zero; row[30] = zero; row[31] = zero;
+            uint32_t wd[16];
+            wd[0] = pack_f16(xt[0], xt[1]); wd[1] = pack_f16(xt[2], xt[3]); wd[2] = pack_f16(xt[4], xt[5]); wd[3] = pack_f16(xt[6], xt[7]);
+            wd[4] = pack_f16(xt[8], 1.f);
+            wd[5] = pack_f16(lt[0], lt[1]); wd[6] = pack_f16(lt[2], lt[3]); wd[7] = pack_f16(lt[4], lt[5]); wd[8] = pack_f16(lt[6], lt[7]);
+            wd[9] = pack_f16(lt[8], 1.f);
+            wd[10] = wd[0]; wd[11] = wd[1]; wd[12] = wd[2]; wd[13] = wd[3];
+            wd[14] = wd[4] & 0x0000ffffu;           // (x8, 0)
+            wd[15] = 0u;
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                uint4 v;
-                v.x = (uint32_t)__half_as_ushort(row[ch * 8 + 0]) | ((uint32_t)__half_as_ushort(row[ch * 8 + 1]) << 16);
-                v.y = (uint32_t)__half_as_ushort(row[ch * 8 + 2]) | ((uint32_t)__half_as_ushort(row[ch * 8 + 3]) << 16);
-                v.z = (uint32_t)__half_as_ushort(row[ch * 8 + 4]) | ((uint32_t)__half_as_ushort(row[ch * 8 + 5]) << 16);
-                v.w = (uint32_t)__half_as_ushort(row[ch * 8 + 6]) | ((uint32_t)__half_as_ushort(row[ch * 8 + 7]) << 16);
-                *reinterpret_cast<uint4*>(s_a + q * 8192 + ch * 2048 + tid * 16) = v;
-            }
+            for (int ch = 0; ch < 4; ++ch)
+                *reinterpret_cast<uint4*>(s_a + q * 8192 + ch * 2048 + tid * 16) =
+                    make_uint4(wd[ch * 4], wd[ch * 4 + 1], wd[ch * 4 + 2], wd[ch * 4 + 3]);
         }
         fence_proxy_async();
         __syncthreads();

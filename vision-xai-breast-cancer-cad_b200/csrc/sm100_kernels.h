@@ -9,7 +9,7 @@ namespace bcad {
 int launch_conv_first_pool(const float* x, const float* w9c, const float* bias, __half* out, int B, int H, int W,
                            int pad, int Cout, float alpha, cudaStream_t s);
 
-// tensor-core first conv: w_img = [4 chunks][Cout][8 halves] rows [w_hi(9) | w_hi(9) | w_lo(9) | b_hi | b_lo | 0 0 0]
+// tensor-core first conv: w_img = [4 chunks][Cout][8 halves] rows [w_hi(9) b_hi | w_hi(9) b_lo | w_lo(9) 0 0 0]
 int launch_conv_first_tc(const float* x, const uint8_t* w_img, __half* out, int B, int H, int W, int pad, int Cout,
                          float alpha, int sms, cudaStream_t s);
 

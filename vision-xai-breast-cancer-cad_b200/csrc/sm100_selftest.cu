@@ -63,7 +63,79 @@ umma_selftest_kernel(const uint4* __restrict__ a_img, int a_bytes, const uint4* 
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+// ---- micro-benchmarks (design evidence, not product): cycles for `reps` back-to-back UMMAs on fixed smem operands,
+// and for `reps` TMEM->register loads by `nwarps` warps.  out[0] = MMA cycles, out[1] = TMEM-load cycles.
+__global__ void __launch_bounds__(256, 1)
+umma_bench_kernel(int N, int a_layout, int b_layout, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int reps, int ld_warps,
+                  int ld_x16, long long* __restrict__ out) {
+    using namespace sm100;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (64 * 1024) / 16; i += 256) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x3C003C00u, 0x3C003C00u, 0, 0);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(&tmem_base, 512);
+        tmem_relinquish();
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base;
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc_f16(128, N);
+        const uint64_t ad = make_smem_desc(smem_u32(smem), a_lbo, a_sbo, a_layout);
+        const uint64_t bd = make_smem_desc(smem_u32(smem) + 32768, b_lbo, b_sbo, b_layout);
+        const long long t0 = clock64();
+        for (int k = 0; k < reps; ++k) umma_bf16(tmem, ad, bd, idesc, 1u);
+        umma_commit(&bar);
+        mbar_wait(&bar, 0);
+        out[0] = clock64() - t0;
+    }
+    __syncthreads();
+    tc_fence_after();
+    if (warp < ld_warps) {
+        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+        float acc = 0.f;
+        const long long t0 = clock64();
+        for (int k = 0; k < reps; ++k) {
+            if (ld_x16) {
+                float v[16];
+                tmem_ld16(tmem + lane_off + ((k * 16) & 255), v);
+                tmem_ld_wait();
+                acc += v[0] + v[15];
+            } else {
+                float v[32];
+                tmem_ld32(tmem + lane_off + ((k * 32) & 255), v);
+                tmem_ld_wait();
+                acc += v[0] + v[31];
+            }
+        }
+        const long long dt = clock64() - t0;
+        if (tid == 0) out[1] = dt;
+        if (acc == 123.456f) out[2] = 1;      // keep the loads alive
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace bcad
+
+extern "C" int bcad_selftest_umma_bench(const int32_t* p /*N,a_layout,b_layout,a_lbo,a_sbo,b_lbo,b_sbo,reps,ld_warps,ld_x16*/,
+                                        long long* out_dev, void* stream) {
+    using namespace bcad;
+    BCAD_REQUIRE(p && out_dev, "selftest bench: null argument");
+    BCAD_CUDA_CHECK(cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    umma_bench_kernel<<<1, 256, 64 * 1024, (cudaStream_t)stream>>>(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8], p[9], out_dev);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
 
 extern "C" int bcad_selftest_umma(const void* a_img_dev, int a_bytes, const void* b_img_dev, int b_bytes,
                                   const int32_t* params_host, float* d_dev, void* stream) {

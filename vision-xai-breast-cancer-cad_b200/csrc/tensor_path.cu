@@ -95,7 +95,7 @@ int tensor_path_commit(Model& m) {
         BCAD_CUDA_CHECK(cudaMemcpy(t.d_w0, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
         BCAD_CUDA_CHECK(cudaMemcpy(t.d_b0, c0.h_b.data(), c0.Cout * 4, cudaMemcpyHostToDevice));
     }
-    // ---- conv0 tensor-core image: K = 32 slots per filter: [w_hi(9) | w_hi(9) | w_lo(9) | b_hi | b_lo | 0 0 0]
+    // ---- conv0 tensor-core image: K = 32 slots per filter: [w_hi(9) b_hi | w_hi(9) b_lo | w_lo(9) 0 0 0]
     if (c0.Cout == 32 || c0.Cout == 64) {
         std::vector<uint16_t> img((size_t)4 * c0.Cout * 8, 0);
         auto put = [&](int f, int k, float v) { img[((size_t)(k >> 3) * c0.Cout + f) * 8 + (k & 7)] = f2h(v); };
@@ -104,12 +104,12 @@ int tensor_path_commit(Model& m) {
                 const float w = c0.h_w[(size_t)f * 9 + tap];
                 const float whi = h2f(f2h(w));
                 put(f, tap, whi);
-                put(f, 9 + tap, whi);
-                put(f, 18 + tap, w - whi);
+                put(f, 10 + tap, whi);
+                put(f, 20 + tap, w - whi);
             }
             const float bhi = h2f(f2h(c0.h_b[f]));
-            put(f, 27, bhi);
-            put(f, 28, c0.h_b[f] - bhi);
+            put(f, 9, bhi);
+            put(f, 19, c0.h_b[f] - bhi);
         }
         if (!t.d_w0_img) TP_TRY(m.alloc((void**)&t.d_w0_img, img.size() * 2));
         BCAD_CUDA_CHECK(cudaMemcpy(t.d_w0_img, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
