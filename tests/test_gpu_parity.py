@@ -213,3 +213,24 @@ def test_batchnorm_fold_identity_and_affine():
                      p.dense_w, p.dense_b)
     np.testing.assert_allclose(_np(logits), ocnn.forward(cfg, p2, x).logits.numpy(), rtol=0, atol=FP32_TOL)
     eng.close()
+
+
+def test_sharded_engine_equals_single_gpu():
+    """Batch sharding over the GPUs of the box: N-GPU result == 1-GPU result on the concatenated batch."""
+    import bcad_b200
+    from util import spec_from_cfg
+    ngpu = torch.cuda.device_count()
+    devices = list(range(min(ngpu, 4))) if ngpu > 1 else [0, 0]       # one GPU: two handles on it still exercise the split
+    cfg = ocnn.NetConfig.torch_flavour((32, 32, 1), 2, [(8, 3), (16, 3)], [16], 0.01)
+    p = ocnn.init_params(cfg, seed=2, bias_std=0.05)
+    x = ocnn.synth_images(11, (32, 32, 1), seed=8)
+    sh = bcad_b200.ShardedEngine(spec_from_cfg(cfg), devices, max_batch=4)
+    sh.set_weights(p.conv_w, p.conv_b, p.dense_w, p.dense_b)
+    cls, probs, logits, heat = sh.predict_explain_host(x, None, "logit")
+    one = engine_from(cfg, p, max_batch=16)
+    c1, p1, l1, h1 = one.predict_explain_host(x, None, "logit")
+    assert np.array_equal(cls, c1)
+    np.testing.assert_allclose(logits, l1, rtol=0, atol=1e-5)
+    np.testing.assert_allclose(heat, h1, rtol=0, atol=1e-5)
+    sh.close()
+    one.close()
