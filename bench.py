@@ -129,10 +129,22 @@ def oracle_setup():
     return ocnn, cfg, params
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline is meant to use every host core."""
+    import torch
+    n = os.cpu_count() or 1
+    try:
+        torch.set_num_threads(n)
+    except Exception:
+        pass
+    return torch.get_num_threads()
+
+
 def cpu_reference_rate(n_images, batch=32, repeats=1):
     """The reference's CPU path (oracle port of ADCNNM + autograd Grad-CAM + NumPy tail) on the host cores."""
     import torch
     from oracle import cpu_port
+    use_all_host_threads()
     _, cfg, params = oracle_setup()
     rate, secs = cpu_port.time_predict_gradcam(cfg, params, n_images, batch=batch, repeats=repeats)
     return rate, secs, torch.get_num_threads()
@@ -144,6 +156,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import torch
+    use_all_host_threads()
     n_per_step = args.ref_images
     _, cfg, params = oracle_setup()
     from oracle import cpu_port
