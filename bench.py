@@ -185,7 +185,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def workload_config(batch, precision):
@@ -360,10 +360,32 @@ def run_ours(args, rank, world, local_rank):
         "cpu_baseline": cpu,
         "tensor_path": bool(eng.uses_tensor_path),
     }
-    print(json.dumps(out_json), flush=True)
+    emit(out_json)
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Rank 0 must print exactly ONE JSON line: route everything else that lands on fd 1 (NCCL's version banner,
+    library chatter) to stderr and keep a private handle for the result line."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
