@@ -128,3 +128,42 @@ def test_tensor_path_full_size_canonical():
     assert np.abs(_np(h32) - h).max() <= F16_TOL
     eng.close()
     eng32.close()
+
+
+X3_LOGIT_TOL = 2e-4      # fp16x3: hi+lo split operands, fp32 accumulation -> fp32-grade
+X3_HEAT_TOL = 5e-4
+
+
+@pytest.mark.parametrize("shape,hidden,B,mb,pad", [
+    ((64, 64, 1), [64, 32], 6, 8, 1),
+    ((61, 61, 1), [32], 4, 4, 0),
+    ((32, 32, 1), [48, 16], 140, 256, 1),
+    ((256, 256, 1), [256, 128], 6, 8, 1),
+])
+def test_fp16x3_path_is_fp32_grade(shape, hidden, B, mb, pad):
+    """Split-operand tensor path (3 MMAs per product): logits within 2e-4, heat-maps within 5e-4 of the float64 oracle."""
+    from bcad_b200 import _lib
+    if pad == 1:
+        cfg = ocnn.NetConfig.torch_flavour(shape, 2, [(32, 3), (64, 3)], hidden, 0.01)
+    else:
+        cfg = ocnn.NetConfig(shape, 2, [(32, 3), (64, 3)], hidden, 0.01, 0.01, 0, "hwc", "first", "softmax")
+    p = ocnn.init_params(cfg, seed=7, bias_std=0.05)
+    x = ocnn.synth_images(B, shape, seed=21)
+    eng = engine_from(cfg, p, precision="fp16x3", max_batch=mb)
+    assert eng.uses_tensor_path
+    cls, probs, logits, heat = eng.predict_explain(x, None, "logit")
+    o_cls, cache, A, dA, o_heat = oracle_heatmaps(cfg, p, x, None, "logit")
+    lg = cache.logits.numpy()
+    scale = max(1.0, np.abs(lg).max())
+    err_l = np.abs(_np(logits) - lg).max()
+    assert err_l <= X3_LOGIT_TOL * scale, f"logits err {err_l}"
+    assert np.array_equal(_np(cls), o_cls)
+    if B <= mb:
+        last = len(cfg.conv_layers) - 1
+        A_dev = _np(eng.get_tensor(_lib.T_CONV_OUT, last, B)).reshape(A.shape)
+        assert np.abs(A_dev - A).max() <= 1e-4 * max(1.0, np.abs(A).max()), "conv1 activations"
+    flipped = _kink_flips(eng, cache, B) if B <= mb else np.zeros(B, bool)
+    err_h = np.abs(_np(heat) - o_heat).max(axis=(1, 2))
+    assert flipped.sum() <= max(1, B // 50)
+    assert err_h[~flipped].max(initial=0.0) <= X3_HEAT_TOL, f"heatmap err {err_h}"
+    eng.close()

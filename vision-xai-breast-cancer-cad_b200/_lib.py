@@ -17,7 +17,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, -1, -2, -3, -4
 FLATTEN = {"hwc": 0, "chw": 1}
 TIES = {"dup": 0, "all": 0, "first": 1}
 HEAD = {"softmax": 0, "logits": 1}
-PRECISION = {"fp32": 0, "fp16": 1}
+PRECISION = {"fp32": 0, "fp16": 1, "fp16x3": 2}
 GRAD_MODE = {"logit": 0, "softmax_ce": 1}
 T_CONV_OUT, T_POOL_OUT, T_DENSE_Z, T_ALPHA, T_CAM_LOWRES = 0, 1, 2, 3, 4
 

@@ -108,7 +108,7 @@ static int validate(const bcad_config& c) {
     BCAD_REQUIRE(c.flatten_order == BCAD_FLATTEN_HWC || c.flatten_order == BCAD_FLATTEN_CHW, "bad flatten_order %d", c.flatten_order);
     BCAD_REQUIRE(c.pool_ties == BCAD_TIES_ALL || c.pool_ties == BCAD_TIES_FIRST, "bad pool_ties %d", c.pool_ties);
     BCAD_REQUIRE(c.head == BCAD_HEAD_SOFTMAX_CLIP || c.head == BCAD_HEAD_LOGITS, "bad head %d", c.head);
-    BCAD_REQUIRE(c.precision == BCAD_PREC_FP32 || c.precision == BCAD_PREC_F16, "bad precision %d", c.precision);
+    BCAD_REQUIRE(c.precision == BCAD_PREC_FP32 || c.precision == BCAD_PREC_F16 || c.precision == BCAD_PREC_F16X3, "bad precision %d", c.precision);
     BCAD_REQUIRE(c.max_batch >= 1 && c.max_batch <= 65535, "max_batch %d out of range 1..65535", c.max_batch);
     BCAD_REQUIRE(c.alpha_conv >= 0.f && c.alpha_dense >= 0.f, "negative LeakyReLU slope is not supported (pool/activation fusion assumes a monotone activation)");
     return BCAD_OK;
@@ -175,7 +175,7 @@ int bcad_create(const bcad_config* cfg, bcad_model** out) {
         m->dense.push_back(D);
         prev = D.out;
     }
-    if (cfg->precision == BCAD_PREC_F16) {
+    if (cfg->precision == BCAD_PREC_F16 || cfg->precision == BCAD_PREC_F16X3) {
         int rc = tensor_path_supported(*m);
         if (rc != BCAD_OK) {
             delete m;

@@ -20,6 +20,7 @@ namespace bcad {
 using namespace sm100;
 
 __device__ __forceinline__ uint32_t h2u(const __half2& h) { return *reinterpret_cast<const uint32_t*>(&h); }
+__device__ __forceinline__ __half2 u2h(uint32_t v) { return *reinterpret_cast<const __half2*>(&v); }
 
 // =====================================================================================================
 // first conv block (Cin = 1, 3x3): CUDA cores, fused bias + LeakyReLU + 2x2 max-pool, fp16 C8-planar out.
@@ -109,7 +110,7 @@ int launch_conv_first_pool(const float* x, const float* w9c, const float* bias, 
 // The CUDA-core work left is the im2col row build (16 STS.128 / thread) and the pooled epilogue: ~4x fewer
 // instructions than 1152 FFMAs per pooled pixel.  128-thread CTAs, 4 per SM (TMEM 4 x 128 columns).
 // =====================================================================================================
-template <int COUT>
+template <int COUT, bool SPLIT>
 __global__ void __launch_bounds__(128, 4)
 conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_img /*[4][COUT][16 B]*/,
                      __half* __restrict__ out, int B, int H, int W, int pad, int Hp, int Wp, float alpha) {
@@ -241,8 +242,33 @@ conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_
                         m1 = max_form ? fmaxf(m1, alpha * m1) : leaky(m1, alpha);
                         pk[e >> 1] = pack_f16(m0, m1);
                     }
-                    uint4* dst = reinterpret_cast<uint4*>(out) + (((size_t)b * Hp + py) * (COUT / 8) + (c0 / 8 + cc)) * Wp + px;
-                    *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    if constexpr (!SPLIT) {
+                        uint4* dst = reinterpret_cast<uint4*>(out) + (((size_t)b * Hp + py) * (COUT / 8) + (c0 / 8 + cc)) * Wp + px;
+                        *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+                if constexpr (SPLIT) {
+                    // fp16x3 mode: the pooled fp32 value goes out as hi + lo halves, as 2*COUT "virtual" channels
+                    // (octets [hi 0..COUT/8) | lo 0..COUT/8)) of one C8-planar tensor
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        uint32_t ph[4], pl[4];
+#pragma unroll
+                        for (int e = 0; e < 8; e += 2) {
+                            const int k0 = cc * 8 + e;
+                            float m0 = fmaxf(fmaxf(v0[k0], v1[k0]), fmaxf(v2[k0], v3[k0]));
+                            float m1 = fmaxf(fmaxf(v0[k0 + 1], v1[k0 + 1]), fmaxf(v2[k0 + 1], v3[k0 + 1]));
+                            m0 = max_form ? fmaxf(m0, alpha * m0) : leaky(m0, alpha);
+                            m1 = max_form ? fmaxf(m1, alpha * m1) : leaky(m1, alpha);
+                            const __half2 h = __floats2half2_rn(m0, m1);
+                            const float2 hf = __half22float2(h);
+                            ph[e >> 1] = h2u(h);
+                            pl[e >> 1] = pack_f16(m0 - hf.x, m1 - hf.y);
+                        }
+                        uint4* dh = reinterpret_cast<uint4*>(out) + (((size_t)b * Hp + py) * (2 * COUT / 8) + (c0 / 8 + cc)) * Wp + px;
+                        *dh = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                        *(dh + (size_t)(COUT / 8) * Wp) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                    }
                 }
             }
         }
@@ -252,26 +278,27 @@ conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_
     if (warp == 0) tmem_dealloc(tmem, 4 * COUT);
 }
 
+template <int COUT, bool SPLIT>
+static int launch_conv_first_tc_t(const float* x, const uint8_t* w_img, __half* out, int B, int H, int W, int pad, int Hp,
+                                  int Wp, float alpha, int grid, int smem, cudaStream_t s) {
+    BCAD_CUDA_CHECK(cudaFuncSetAttribute(conv_first_tc_kernel<COUT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    conv_first_tc_kernel<COUT, SPLIT><<<grid, 128, smem, s>>>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
 int launch_conv_first_tc(const float* x, const uint8_t* w_img, __half* out, int B, int H, int W, int pad, int Cout,
-                         float alpha, int sms, cudaStream_t s) {
+                         float alpha, bool split_hi_lo, int sms, cudaStream_t s) {
     const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2, Hp = Ho / 2, Wp = Wo / 2;
     const int n_tiles = B * Hp * cdiv(Wp, 128);
     const int smem = 4 * 8192 + 4 * Cout * 16;
     const int per_sm = Cout <= 32 ? 4 : 2;          // TMEM: 4*Cout columns per CTA
     const int grid = n_tiles < sms * per_sm ? n_tiles : sms * per_sm;
-    switch (Cout) {
-        case 32:
-            BCAD_CUDA_CHECK(cudaFuncSetAttribute(conv_first_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            conv_first_tc_kernel<32><<<grid, 128, smem, s>>>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha);
-            break;
-        case 64:
-            BCAD_CUDA_CHECK(cudaFuncSetAttribute(conv_first_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            conv_first_tc_kernel<64><<<grid, 128, smem, s>>>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha);
-            break;
-        default: set_error("conv_first_tc: Cout %d not supported (32/64)", Cout); return BCAD_ERR_INVALID;
-    }
-    BCAD_CUDA_CHECK(cudaGetLastError());
-    return BCAD_OK;
+    if (Cout == 32 && !split_hi_lo) return launch_conv_first_tc_t<32, false>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s);
+    if (Cout == 32 && split_hi_lo) return launch_conv_first_tc_t<32, true>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s);
+    if (Cout == 64 && !split_hi_lo) return launch_conv_first_tc_t<64, false>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s);
+    set_error("conv_first_tc: Cout %d (split=%d) not supported", Cout, (int)split_hi_lo);
+    return BCAD_ERR_INVALID;
 }
 
 // =====================================================================================================
@@ -309,7 +336,7 @@ struct IgemmSmem {
     static constexpr int TOTAL = OFF_BAR + 256;
 };
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, bool X3>
 __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) {
     using L = IgemmSmem<CIN, COUT>;
     constexpr int IG_STAGES = L::STAGES;
@@ -428,14 +455,32 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
                             else row_base = ring_base + ((((g + (i >> 1) - p) % IG_STAGES) << 1) + (i & 1)) * L::ROWB;
                             const uint64_t a_desc0 = a_tmpl | (uint64_t)((row_base & 0x3FFFFu) >> 4);
 #pragma unroll
-                            for (int dx = 0; dx < 3; ++dx)
+                            for (int dx = 0; dx < 3; ++dx) {
+                                if constexpr (!X3) {
 #pragma unroll
-                                for (int ks = 0; ks < CIN / 16; ++ks) {
-                                    const uint64_t ad = a_desc0 + (uint64_t)((ks * 2 * L::LBO + dx * 16) >> 4);
-                                    const uint64_t bd = b_desc0 + (uint64_t)((((dy * 3 + dx) * L::CHUNKS + 2 * ks) * (COUT * 16)) >> 4);
-                                    umma_bf16(d_tmem, ad, bd, idesc, acc);
-                                    acc = 1;
+                                    for (int ks = 0; ks < CIN / 16; ++ks) {
+                                        const uint64_t ad = a_desc0 + (uint64_t)((ks * 2 * L::LBO + dx * 16) >> 4);
+                                        const uint64_t bd = b_desc0 + (uint64_t)((((dy * 3 + dx) * L::CHUNKS + 2 * ks) * (COUT * 16)) >> 4);
+                                        umma_bf16(d_tmem, ad, bd, idesc, acc);
+                                        acc = 1;
+                                    }
+                                } else {
+                                    // fp16x3: input octets [x_hi (H) | x_lo (H)], weight octets per tap [w_hi (H) | w_lo (H)], H = CIN/16:
+                                    //   x_hi.w_hi + x_lo.w_hi + x_hi.w_lo   (x_lo.w_lo ~ 2^-22 is dropped)
+                                    constexpr int HP = CIN / 32;               // octet PAIRS per half
+#pragma unroll
+                                    for (int g3 = 0; g3 < 3; ++g3)
+#pragma unroll
+                                        for (int kp = 0; kp < HP; ++kp) {
+                                            const int a_pair = (g3 == 1 ? HP : 0) + kp;         // x_hi, x_lo, x_hi
+                                            const int b_pair = (g3 == 2 ? HP : 0) + kp;         // w_hi, w_hi, w_lo
+                                            const uint64_t ad = a_desc0 + (uint64_t)((a_pair * 2 * L::LBO + dx * 16) >> 4);
+                                            const uint64_t bd = b_desc0 + (uint64_t)((((dy * 3 + dx) * L::CHUNKS + 2 * b_pair) * (COUT * 16)) >> 4);
+                                            umma_bf16(d_tmem, ad, bd, idesc, acc);
+                                            acc = 1;
+                                        }
                                 }
+                            }
                         }
                     }
                     umma_commit(&empty[g % IG_STAGES]);      // stage p is dead once these MMAs retire
@@ -472,6 +517,58 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
                 const bool has1 = (2 * p + 1 < nrows);
                 const int py = t0 >> 1, px = x >> 1;
                 const bool pool_ok = has1 && py < a.Hp && px < a.Wp && !(x & 1);
+                if constexpr (X3) {
+                    // fp16x3 epilogue: everything stays fp32 until the final hi/lo split
+#pragma unroll 1
+                    for (int half = half0; half < COUT / 32; half += 2) {
+#pragma unroll 1
+                        for (int sub = 0; sub < 2; ++sub) {                  // 16 channels at a time (register budget)
+                            const int cbase = half * 32 + sub * 16;
+                            float v0[16], v1[16];
+                            tmem_ld16(tmem + lane_off + j * (2 * COUT) + cbase, v0);
+                            tmem_ld16(tmem + lane_off + j * (2 * COUT) + COUT + cbase, v1);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) {
+                                v0[q] = fmaxf(v0[q], a.alpha * v0[q]);
+                                v1[q] = fmaxf(v1[q], a.alpha * v1[q]);
+                            }
+                            auto split_store = [&](uint4* dst_hi, size_t lo_off, const float* v) {
+                                const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+                                const __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+                                const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
+                                *dst_hi = make_uint4(h2u(h0), h2u(h1), h2u(h2), h2u(h3));
+                                *(dst_hi + lo_off) = make_uint4(pack_f16(v[0] - f0.x, v[1] - f0.y), pack_f16(v[2] - f1.x, v[3] - f1.y),
+                                                                pack_f16(v[4] - f2.x, v[5] - f2.y), pack_f16(v[6] - f3.x, v[7] - f3.y));
+                            };
+                            if (a.act != nullptr && x < a.Wo) {
+#pragma unroll
+                                for (int cc = 0; cc < 2; ++cc) {
+                                    const int chunk = cbase / 8 + cc;
+                                    // activations: 2*COUT virtual channels, octets [hi | lo]
+                                    uint4* d0 = reinterpret_cast<uint4*>(a.act) + (((size_t)b * a.Ho + t0) * (2 * COUT / 8) + chunk) * a.Wo + x;
+                                    split_store(d0, (size_t)(COUT / 8) * a.Wo, v0 + cc * 8);
+                                    if (has1) split_store(d0 + (size_t)(2 * COUT / 8) * a.Wo, (size_t)(COUT / 8) * a.Wo, v1 + cc * 8);
+                                }
+                            }
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) {
+                                const float mv = fmaxf(v0[q], v1[q]);
+                                v0[q] = fmaxf(mv, __shfl_xor_sync(0xffffffffu, mv, 1));
+                            }
+                            if (pool_ok && a.pool_fc != nullptr) {
+                                // fc1 A tiles: [b/128][pooled pixel][hi|lo][b%128][128 B swizzled]
+                                const int row = b & 127;
+                                uint8_t* base = a.pool_fc + (((((size_t)(b >> 7) * a.Hp * a.Wp) + (size_t)py * a.Wp + px) * 2) * 128 + row) * 128;
+#pragma unroll
+                                for (int cc = 0; cc < 2; ++cc) {
+                                    const int chunk = (cbase / 8 + cc) ^ (row & 7);
+                                    split_store(reinterpret_cast<uint4*>(base + chunk * 16), (size_t)(128 * 128) / 16, v0 + cc * 8);
+                                }
+                            }
+                        }
+                    }
+                } else
 #pragma unroll 1
                 for (int half = half0; half < COUT / 32; half += 2) {
                     float v0[32], v1[32];
@@ -540,26 +637,28 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, bool X3>
 static int launch_igemm_t(const IgemmArgs& a, int sms, cudaStream_t s) {
     using L = IgemmSmem<CIN, COUT>;
-    BCAD_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    BCAD_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<CIN, COUT, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     const int items = a.B * a.bands;
     const int grid = items < sms ? items : sms;
-    conv_igemm_kernel<CIN, COUT><<<grid, IG_THREADS, L::TOTAL, s>>>(a);
+    conv_igemm_kernel<CIN, COUT, X3><<<grid, IG_THREADS, L::TOTAL, s>>>(a);
     BCAD_CUDA_CHECK(cudaGetLastError());
     return BCAD_OK;
 }
 
-int launch_conv_igemm(const IgemmArgs& a, int Cin, int Cout, int sms, cudaStream_t s) {
+// Cin counts the channels the kernel sees: in fp16x3 mode that is 2 x the layer's channels (hi and lo octets)
+int launch_conv_igemm(const IgemmArgs& a, int Cin, int Cout, bool x3, int sms, cudaStream_t s) {
     BCAD_REQUIRE(a.W <= 128 && a.Wo <= 128, "conv_igemm: map width %d > 128", a.W);
     BCAD_REQUIRE(a.band_rows % 2 == 0, "conv_igemm: band_rows must be even");
-    if (Cout == 64) {
-        if (Cin == 16) return launch_igemm_t<16, 64>(a, sms, s);
-        if (Cin == 32) return launch_igemm_t<32, 64>(a, sms, s);
-        if (Cin == 64) return launch_igemm_t<64, 64>(a, sms, s);
+    if (Cout == 64 && !x3) {
+        if (Cin == 16) return launch_igemm_t<16, 64, false>(a, sms, s);
+        if (Cin == 32) return launch_igemm_t<32, 64, false>(a, sms, s);
+        if (Cin == 64) return launch_igemm_t<64, 64, false>(a, sms, s);
     }
-    set_error("conv_igemm: Cin=%d Cout=%d not supported (Cin 16/32/64, Cout 64)", Cin, Cout);
+    if (Cout == 64 && x3 && Cin == 64) return launch_igemm_t<64, 64, true>(a, sms, s);
+    set_error("conv_igemm: Cin=%d Cout=%d x3=%d not supported", Cin, Cout, (int)x3);
     return BCAD_ERR_INVALID;
 }
 
@@ -575,8 +674,11 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_splitk_kernel(FcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem base is 1024-aligned by declaration; SW128 tiles need it
     uint8_t* smem = smem_raw;
-    const int a_tile = 128 * 128, w_tile = a.N * 128, stage_bytes = a_tile + w_tile;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FC_STAGES * stage_bytes);
+    const int a_tile = 128 * 128, w_tile = a.N * 128;
+    const int nparts = a.x3 ? 2 : 1;                       // fp16x3: hi and lo tiles of both operands
+    const int stage_bytes = nparts * (a_tile + w_tile);
+    const int nst = a.x3 ? 2 : FC_STAGES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nst * stage_bytes);
     uint64_t* full = bars;
     uint64_t* empty = bars + FC_STAGES;
     uint64_t* done = bars + 2 * FC_STAGES;
@@ -602,29 +704,35 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_splitk_kernel(FcArgs a) {
     if (warp == 0) {
         if (lane == 0) {
             for (int i = 0; i < nk; ++i) {
-                const int st = i % FC_STAGES;
-                if (i >= FC_STAGES) mbar_wait(&empty[st], ((i / FC_STAGES) - 1) & 1);
+                const int st = i % nst;
+                if (i >= nst) mbar_wait(&empty[st], ((i / nst) - 1) & 1);
                 mbar_arrive_expect_tx(&full[st], stage_bytes);
                 uint8_t* sa = smem + st * stage_bytes;
-                bulk_g2s(sa, a.a_tiles + ((size_t)mt * a.nkb + kb0 + i) * a_tile, a_tile, &full[st]);
-                const uint8_t* wsrc = a.w_tiles + (size_t)(kb0 + i) * w_tile;
-                for (int off = 0; off < w_tile; off += 16384)
-                    bulk_g2s(sa + a_tile + off, wsrc + off, min(16384, w_tile - off), &full[st]);
+                const uint8_t* asrc = a.a_tiles + ((size_t)mt * a.nkb + kb0 + i) * (size_t)(nparts * a_tile);
+                for (int off = 0; off < nparts * a_tile; off += 16384) bulk_g2s(sa + off, asrc + off, 16384, &full[st]);
+                const uint8_t* wsrc = a.w_tiles + (size_t)(kb0 + i) * (size_t)(nparts * w_tile);
+                for (int off = 0; off < nparts * w_tile; off += 16384)
+                    bulk_g2s(sa + nparts * a_tile + off, wsrc + off, min(16384, nparts * w_tile - off), &full[st]);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc_f16(128, a.N);
             for (int i = 0; i < nk; ++i) {
-                const int st = i % FC_STAGES;
-                mbar_wait(&full[st], (i / FC_STAGES) & 1);
+                const int st = i % nst;
+                mbar_wait(&full[st], (i / nst) & 1);
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + st * stage_bytes), sw = sa + a_tile;
+                const uint32_t sa = smem_u32(smem + st * stage_bytes), sw = sa + nparts * a_tile;
+                // x3: A_hi.W_hi + A_lo.W_hi + A_hi.W_lo
+                const int ngroups = a.x3 ? 3 : 1;
+                for (int g3 = 0; g3 < ngroups; ++g3) {
+                    const uint32_t sa_g = sa + (g3 == 1 ? a_tile : 0), sw_g = sw + (g3 == 2 ? w_tile : 0);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint64_t ad = make_smem_desc(sa + k * 32, 16, 1024, LAYOUT_SW128);
-                    const uint64_t bd = make_smem_desc(sw + k * 32, 16, 1024, LAYOUT_SW128);
-                    umma_bf16(tmem, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t ad = make_smem_desc(sa_g + k * 32, 16, 1024, LAYOUT_SW128);
+                        const uint64_t bd = make_smem_desc(sw_g + k * 32, 16, 1024, LAYOUT_SW128);
+                        umma_bf16(tmem, ad, bd, idesc, (i > 0 || k > 0 || g3 > 0) ? 1u : 0u);
+                    }
                 }
                 umma_commit(&empty[st]);
             }
@@ -657,8 +765,8 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_splitk_kernel(FcArgs a) {
 
 int launch_fc_splitk(const FcArgs& a, cudaStream_t s) {
     BCAD_REQUIRE(a.N % 16 == 0 && a.N >= 16 && a.N <= 256, "fc_splitk: N=%d must be a multiple of 16 in 16..256", a.N);
-    const int stage_bytes = 128 * 128 + a.N * 128;
-    const int smem = FC_STAGES * stage_bytes + 256;
+    const int stage_bytes = (a.x3 ? 2 : 1) * (128 * 128 + a.N * 128);
+    const int smem = (a.x3 ? 2 : FC_STAGES) * stage_bytes + 256;
     BCAD_CUDA_CHECK(cudaFuncSetAttribute(fc_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     dim3 grid(a.splits, a.m_tiles);
     fc_splitk_kernel<<<grid, FC_THREADS, smem, s>>>(a);
@@ -692,6 +800,7 @@ int launch_fc_reduce(const float* part, int splits, size_t ld_split, const float
 // Grad-CAM channel reduction on C8-planar fp16 activations: cam = ReLU(sum_k alpha_k A_k) + min/max partials
 // grid (splits, B), 256 threads, thread = pixel; every load is a coalesced 16 B per lane.
 // =====================================================================================================
+template <bool X3>
 __global__ void __launch_bounds__(256)
 cam_c8_kernel(const __half* __restrict__ A, const float* __restrict__ alpha_raw, float scale,
               float* __restrict__ alpha_out, float* __restrict__ cam_lo, float* __restrict__ mm, int h, int w, int C) {
@@ -707,17 +816,23 @@ cam_c8_kernel(const __half* __restrict__ A, const float* __restrict__ alpha_raw,
     const int rows_per = cdiv(h, splits);
     const int y0 = split * rows_per, y1 = min(h, y0 + rows_per);
     const int chunks = C / 8;
+    const int planes = X3 ? 2 * chunks : chunks;          // fp16x3: octets [hi | lo]
     float vmin = 3.4e38f, vmax = -3.4e38f;
-    const uint4* base = reinterpret_cast<const uint4*>(A) + (size_t)b * h * chunks * w;
+    const uint4* base = reinterpret_cast<const uint4*>(A) + (size_t)b * h * planes * w;
     const int npix = (y1 - y0) * w;
     for (int i = threadIdx.x; i < npix; i += blockDim.x) {
         const int y = y0 + i / w, x = i % w;
         float acc = 0.f;
-        const uint4* p = base + ((size_t)y * chunks) * w + x;
+        const uint4* p = base + ((size_t)y * planes) * w + x;
         for (int c = 0; c < chunks; ++c) {
             const uint4 q = ldg_stream_u4(p + (size_t)c * w);
             const float* al = s_alpha + c * 8;
-            const float2 f0 = unpack_f16(q.x), f1 = unpack_f16(q.y), f2 = unpack_f16(q.z), f3 = unpack_f16(q.w);
+            float2 f0 = unpack_f16(q.x), f1 = unpack_f16(q.y), f2 = unpack_f16(q.z), f3 = unpack_f16(q.w);
+            if constexpr (X3) {
+                const uint4 ql = ldg_stream_u4(p + (size_t)(chunks + c) * w);
+                const float2 g0 = unpack_f16(ql.x), g1 = unpack_f16(ql.y), g2 = unpack_f16(ql.z), g3 = unpack_f16(ql.w);
+                f0.x += g0.x; f0.y += g0.y; f1.x += g1.x; f1.y += g1.y; f2.x += g2.x; f2.y += g2.y; f3.x += g3.x; f3.y += g3.y;
+            }
             acc = fmaf(f0.x, al[0], acc); acc = fmaf(f0.y, al[1], acc);
             acc = fmaf(f1.x, al[2], acc); acc = fmaf(f1.y, al[3], acc);
             acc = fmaf(f2.x, al[4], acc); acc = fmaf(f2.y, al[5], acc);
@@ -740,29 +855,35 @@ cam_c8_kernel(const __half* __restrict__ A, const float* __restrict__ alpha_raw,
 }
 
 int launch_cam_c8(const __half* A, const float* alpha_raw, float scale, float* alpha_out, float* cam_lo, float* mm,
-                  int B, int h, int w, int C, int splits, cudaStream_t s) {
+                  int B, int h, int w, int C, int splits, bool x3, cudaStream_t s) {
     dim3 grid(splits, B);
-    cam_c8_kernel<<<grid, 256, C * sizeof(float), s>>>(A, alpha_raw, scale, alpha_out, cam_lo, mm, h, w, C);
+    if (x3) cam_c8_kernel<true><<<grid, 256, C * sizeof(float), s>>>(A, alpha_raw, scale, alpha_out, cam_lo, mm, h, w, C);
+    else cam_c8_kernel<false><<<grid, 256, C * sizeof(float), s>>>(A, alpha_raw, scale, alpha_out, cam_lo, mm, h, w, C);
     BCAD_CUDA_CHECK(cudaGetLastError());
     return BCAD_OK;
 }
 
 // C8-planar fp16 [B][h][C/8][w][8] -> NHWC fp32 (compat / inspection only)
-__global__ void c8_to_nhwc_kernel(const __half* __restrict__ src, float* __restrict__ dst, int h, int w, int C, size_t total) {
+__global__ void c8_to_nhwc_kernel(const __half* __restrict__ src, float* __restrict__ dst, int h, int w, int C, int x3,
+                                  size_t total) {
+    const int planes = (x3 ? 2 : 1) * (C / 8);
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % C);
         size_t r = i / C;
         const int x = (int)(r % w); r /= w;
         const int y = (int)(r % h);
         const size_t b = r / h;
-        dst[i] = __half2float(src[((((b * h + y) * (C / 8) + (c >> 3)) * w + x) << 3) + (c & 7)]);
+        const size_t row = (b * h + y) * planes;
+        float v = __half2float(src[(((row + (c >> 3)) * w + x) << 3) + (c & 7)]);
+        if (x3) v += __half2float(src[(((row + (C / 8) + (c >> 3)) * w + x) << 3) + (c & 7)]);
+        dst[i] = v;
     }
 }
 
-int launch_c8_to_nhwc(const __half* src, float* dst, int B, int h, int w, int C, cudaStream_t s) {
+int launch_c8_to_nhwc(const __half* src, float* dst, int B, int h, int w, int C, bool x3, cudaStream_t s) {
     const size_t total = (size_t)B * h * w * C;
     const int blocks = (int)min((size_t)148 * 16, (total + 255) / 256);
-    c8_to_nhwc_kernel<<<blocks, 256, 0, s>>>(src, dst, h, w, C, total);
+    c8_to_nhwc_kernel<<<blocks, 256, 0, s>>>(src, dst, h, w, C, x3 ? 1 : 0, total);
     BCAD_CUDA_CHECK(cudaGetLastError());
     return BCAD_OK;
 }

@@ -11,7 +11,7 @@ int launch_conv_first_pool(const float* x, const float* w9c, const float* bias, 
 
 // tensor-core first conv: w_img = [4 chunks][Cout][8 halves] rows [w_hi(9) b_hi | w_hi(9) b_lo | w_lo(9) 0 0 0]
 int launch_conv_first_tc(const float* x, const uint8_t* w_img, __half* out, int B, int H, int W, int pad, int Cout,
-                         float alpha, int sms, cudaStream_t s);
+                         float alpha, bool split_hi_lo, int sms, cudaStream_t s);
 
 struct IgemmArgs {
     const __half* in;      // C8 planar [B][H][Cin/8][W][8]
@@ -24,20 +24,21 @@ struct IgemmArgs {
     float alpha;
     int debug;                    // timing experiments only: 1 no act store, 2 no pool store, 4 empty epilogue, 8 no MMA
 };
-int launch_conv_igemm(const IgemmArgs& a, int Cin, int Cout, int sms, cudaStream_t s);
+int launch_conv_igemm(const IgemmArgs& a, int Cin, int Cout, bool x3, int sms, cudaStream_t s);
 
 struct FcArgs {
     const uint8_t* a_tiles;       // [m_tiles][nkb][128][128 B] SW128
     const uint8_t* w_tiles;       // [nkb][N][128 B] SW128
     float* partials;              // [splits][m_pad][N]
     int N, nkb, kb_per_split, splits, m_tiles, m_pad;
+    int x3;                       // fp16x3: tiles come as [hi][lo] pairs; A_hi.W_hi + A_lo.W_hi + A_hi.W_lo
 };
 int launch_fc_splitk(const FcArgs& a, cudaStream_t s);
 int launch_fc_reduce(const float* part, int splits, size_t ld_split, const float* bias, float* z, float* h, float alpha,
                      int M, int N, cudaStream_t s);
 
 int launch_cam_c8(const __half* A, const float* alpha_raw, float scale, float* alpha_out, float* cam_lo, float* mm,
-                  int B, int h, int w, int C, int splits, cudaStream_t s);
-int launch_c8_to_nhwc(const __half* src, float* dst, int B, int h, int w, int C, cudaStream_t s);
+                  int B, int h, int w, int C, int splits, bool x3, cudaStream_t s);
+int launch_c8_to_nhwc(const __half* src, float* dst, int B, int h, int w, int C, bool x3, cudaStream_t s);
 
 }  // namespace bcad

@@ -40,6 +40,7 @@ struct TensorPath {
     float* fc_part = nullptr;
     float* alpha_raw = nullptr;     // [B][Cout] = dz1 . S
     int fc_splits = 1, kb_per_split = 1, m_pad = 128;
+    bool x3 = false;                // fp16x3: hi/lo split operands everywhere (fp32-grade)
 };
 
 #define TP_TRY(expr) do { int _rc = (expr); if (_rc != BCAD_OK) return _rc; } while (0)
@@ -70,6 +71,8 @@ int tensor_path_supported(const Model& m) {
     BCAD_REQUIRE(c.alpha_conv <= 1.f, "precision=F16: conv LeakyReLU slope must be <= 1 (max(v, alpha v) form)");
     BCAD_REQUIRE(c.pool_ties == BCAD_TIES_FIRST,
                  "precision=F16: the alpha shortcut needs first-index pooling (TIES_FIRST); the tie-duplicating NumPy flavour runs on BCAD_PREC_FP32");
+    if (c.precision == BCAD_PREC_F16X3)
+        BCAD_REQUIRE(c0.Cout == 32, "precision=F16X3: the split-operand path needs 32 first-block filters (got %d)", c0.Cout);
     const int units = m.dense[0].out;
     BCAD_REQUIRE(units % 16 == 0 && units <= 256, "precision=F16: first dense layer must have a multiple of 16 units <= 256 (got %d)", units);
     return BCAD_OK;
@@ -78,6 +81,7 @@ int tensor_path_supported(const Model& m) {
 int tensor_path_commit(Model& m) {
     if (m.tp == nullptr) m.tp = new TensorPath();
     TensorPath& t = *m.tp;
+    t.x3 = (m.cfg.precision == BCAD_PREC_F16X3);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&t.sms, cudaDevAttrMultiProcessorCount, dev);
@@ -117,14 +121,18 @@ int tensor_path_commit(Model& m) {
     // ---- conv1 weight image: [tap*(Cin/8)+chunk][cout][8] fp16
     {
         const int chunks = c1.Cin / 8;
-        const size_t wel = (size_t)9 * chunks * c1.Cout * 8;
-        std::vector<uint16_t> img(wel + (size_t)2 * c1.Cout * 8, 0);      // + bias tile [2 chunks][Cout][8]
+        const int vch = t.x3 ? 2 * chunks : chunks;                          // x3: octets [w_hi | w_lo] per tap
+        const size_t wel = (size_t)9 * vch * c1.Cout * 8;
+        std::vector<uint16_t> img(wel + (size_t)2 * c1.Cout * 8, 0);         // + bias tile [2 chunks][Cout][8]
         for (int tap = 0; tap < 9; ++tap)
             for (int ch = 0; ch < chunks; ++ch)
                 for (int f = 0; f < c1.Cout; ++f)
-                    for (int e = 0; e < 8; ++e)
-                        img[(((size_t)tap * chunks + ch) * c1.Cout + f) * 8 + e] =
-                            f2h(c1.h_w[((size_t)f * 9 + tap) * c1.Cin + ch * 8 + e]);
+                    for (int e = 0; e < 8; ++e) {
+                        const float w = c1.h_w[((size_t)f * 9 + tap) * c1.Cin + ch * 8 + e];
+                        const uint16_t q = f2h(w);
+                        img[(((size_t)tap * vch + ch) * c1.Cout + f) * 8 + e] = q;
+                        if (t.x3) img[(((size_t)tap * vch + chunks + ch) * c1.Cout + f) * 8 + e] = f2h(w - h2f(q));
+                    }
         for (int f = 0; f < c1.Cout; ++f) {                                 // bias K-step rows: {b_hi, b_lo, 0 ...}
             const float bhi = h2f(f2h(c1.h_b[f]));
             img[wel + (size_t)f * 8 + 0] = f2h(bhi);
@@ -136,18 +144,24 @@ int tensor_path_commit(Model& m) {
     // ---- fc1: SW128 tiles [pixel][unit][128 B]; K index inside a tile = channel; S = per-channel column sums
     {
         const int npix = c1.Hp * c1.Wp, N = d0.out, C = c1.Cout;
-        std::vector<uint16_t> tiles((size_t)npix * N * 64);
+        const int parts = t.x3 ? 2 : 1;                                      // x3: [pixel][hi|lo][unit][64]
+        std::vector<uint16_t> tiles((size_t)npix * parts * N * 64);
         std::vector<double> S((size_t)N * C, 0.0);
         for (int u = 0; u < N; ++u) {
             const float* row = d0.h_w.data() + (size_t)u * d0.in;          // device (NHWC) column order: pixel*C + c
             for (int pp = 0; pp < npix; ++pp) {
-                uint16_t* dst = tiles.data() + ((size_t)pp * N + u) * 64;
+                uint16_t* dst = tiles.data() + (((size_t)pp * parts) * N + u) * 64;
                 for (int cidx = 0; cidx < C; ++cidx) {
                     const float v = row[(size_t)pp * C + cidx];
                     const int chunk = (cidx >> 3) ^ (u & 7);
                     const uint16_t q = f2h(v);
                     dst[chunk * 8 + (cidx & 7)] = q;
-                    S[(size_t)u * C + cidx] += h2f(q);                    // S uses the fp16-rounded weights the GEMM sees
+                    if (t.x3) {
+                        dst[(size_t)N * 64 + chunk * 8 + (cidx & 7)] = f2h(v - h2f(q));
+                        S[(size_t)u * C + cidx] += v;                        // the GEMM sees (almost) the fp32 weight
+                    } else {
+                        S[(size_t)u * C + cidx] += h2f(q);                   // S uses the fp16-rounded weights the GEMM sees
+                    }
                 }
             }
         }
@@ -166,10 +180,11 @@ int tensor_path_commit(Model& m) {
         if (splits > npix) splits = npix;
         t.kb_per_split = cdiv(npix, splits);
         t.fc_splits = cdiv(npix, t.kb_per_split);
-        TP_TRY(m.alloc((void**)&t.p1, (size_t)mb * c0.Hp * c0.Wp * c0.Cout * 2));
-        TP_TRY(m.alloc((void**)&t.act, (size_t)mb * c1.Ho * c1.Wo * c1.Cout * 2));
-        TP_TRY(m.alloc((void**)&t.fc_a, (size_t)t.m_pad * npix * 128));
-        BCAD_CUDA_CHECK(cudaMemset(t.fc_a, 0, (size_t)t.m_pad * npix * 128));     // padding rows: finite zeros
+        const size_t parts = t.x3 ? 2 : 1;
+        TP_TRY(m.alloc((void**)&t.p1, parts * mb * c0.Hp * c0.Wp * c0.Cout * 2));
+        TP_TRY(m.alloc((void**)&t.act, parts * mb * c1.Ho * c1.Wo * c1.Cout * 2));
+        TP_TRY(m.alloc((void**)&t.fc_a, parts * t.m_pad * npix * 128));
+        BCAD_CUDA_CHECK(cudaMemset(t.fc_a, 0, parts * t.m_pad * npix * 128));     // padding rows: finite zeros
         TP_TRY(m.alloc((void**)&t.fc_part, (size_t)t.fc_splits * t.m_pad * d0.out * 4));
         TP_TRY(m.alloc((void**)&t.alpha_raw, (size_t)mb * c1.Cout * 4));
     }
@@ -185,8 +200,8 @@ int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const in
     TensorPath& t = *m.tp;
     const ConvLayer& c0 = m.conv[0];
     const ConvLayer& c1 = m.conv[1];
-    if (t.d_w0_img != nullptr && getenv("BCAD_CONV0_CUDA_CORES") == nullptr)
-        TP_LAUNCH(m, "conv0_first_tcgen05", launch_conv_first_tc(x, t.d_w0_img, t.p1, n, c0.H, c0.W, m.cfg.pad, c0.Cout, m.cfg.alpha_conv, t.sms, s));
+    if (t.d_w0_img != nullptr && (t.x3 || getenv("BCAD_CONV0_CUDA_CORES") == nullptr))
+        TP_LAUNCH(m, "conv0_first_tcgen05", launch_conv_first_tc(x, t.d_w0_img, t.p1, n, c0.H, c0.W, m.cfg.pad, c0.Cout, m.cfg.alpha_conv, t.x3, t.sms, s));
     else
         TP_LAUNCH(m, "conv0_first_pool", launch_conv_first_pool(x, t.d_w0, t.d_b0, t.p1, n, c0.H, c0.W, m.cfg.pad, c0.Cout, m.cfg.alpha_conv, s));
     IgemmArgs a;
@@ -202,13 +217,13 @@ int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const in
         if (a.debug & 1) a.act = nullptr;
         if (a.debug & 2) a.pool_fc = nullptr;
     }
-    TP_LAUNCH(m, "conv1_igemm_tcgen05", launch_conv_igemm(a, c1.Cin, c1.Cout, t.sms, s));
+    TP_LAUNCH(m, "conv1_igemm_tcgen05", launch_conv_igemm(a, t.x3 ? 2 * c1.Cin : c1.Cin, c1.Cout, t.x3, t.sms, s));
     // fc1
     DenseLayer& d0 = m.dense[0];
     FcArgs f;
     f.a_tiles = t.fc_a; f.w_tiles = t.d_fc_w; f.partials = t.fc_part;
     f.N = d0.out; f.nkb = c1.Hp * c1.Wp; f.kb_per_split = t.kb_per_split; f.splits = t.fc_splits;
-    f.m_tiles = cdiv(n, 128); f.m_pad = t.m_pad;
+    f.m_tiles = cdiv(n, 128); f.m_pad = t.m_pad; f.x3 = t.x3 ? 1 : 0;
     TP_LAUNCH(m, "fc1_splitk_tcgen05", launch_fc_splitk(f, s));
     if (m.fused_head) {
         // reduce + dense tail + class + (explain) backward to dz1 + alpha shortcut, one launch
@@ -241,7 +256,7 @@ int tensor_explain_chunk(Model& m, int n, const int32_t* class_idx, int grad_mod
         TP_LAUNCH(m, "alpha_shortcut_sgemm", launch_sgemm(dz1, t.d_S, t.alpha_raw, n, T.Cout, m.dense[0].out, false, 1, s));
     }
     const float inv_hw = 1.0f / ((float)T.Ho * (float)T.Wo);
-    TP_LAUNCH(m, "cam_c8", launch_cam_c8(t.act, t.alpha_raw, inv_hw, m.alpha, m.cam_lo, m.mm, n, T.Ho, T.Wo, T.Cout, m.cam_splits, s));
+    TP_LAUNCH(m, "cam_c8", launch_cam_c8(t.act, t.alpha_raw, inv_hw, m.alpha, m.cam_lo, m.mm, n, T.Ho, T.Wo, T.Cout, m.cam_splits, t.x3, s));
     TP_LAUNCH(m, "upsample_norm", launch_upsample_norm(m.cam_lo, m.mm, m.cam_splits, heat, n, T.Ho, T.Wo, m.cfg.in_h, m.cfg.in_w, s));
     return BCAD_OK;
 }
@@ -250,11 +265,11 @@ int tensor_get_activation(Model& m, int kind, int index, int B, float* dst, cuda
     TensorPath& t = *m.tp;
     if (kind == BCAD_T_CONV_OUT && index == 1) {
         const ConvLayer& L = m.conv[1];
-        return launch_c8_to_nhwc(t.act, dst, B, L.Ho, L.Wo, L.Cout, s);
+        return launch_c8_to_nhwc(t.act, dst, B, L.Ho, L.Wo, L.Cout, t.x3, s);
     }
     if (kind == BCAD_T_POOL_OUT && index == 0) {
         const ConvLayer& L = m.conv[0];
-        return launch_c8_to_nhwc(t.p1, dst, B, L.Hp, L.Wp, L.Cout, s);
+        return launch_c8_to_nhwc(t.p1, dst, B, L.Hp, L.Wp, L.Cout, t.x3, s);
     }
     set_error("get_tensor: the tensor path does not materialise tensor (%d,%d); use BCAD_PREC_FP32 for full activation caches", kind, index);
     return BCAD_ERR_STATE;
