@@ -208,12 +208,13 @@ def run_ours(args, rank, world, local_rank):
     spec = bcad_b200.NetSpec.torch_flavour(INPUT_SHAPE, NUM_CLASSES, CONV_LAYERS, HIDDEN, 0.01)
     precision = args.precision
     eng = None
-    if precision in ("auto", "fp16"):
+    if precision in ("auto", "fp16", "fp16x3"):
+        want = "fp16" if precision == "auto" else precision
         try:
-            eng = bcad_b200.Engine(spec, precision="fp16", max_batch=B, device=local_rank)
-            precision = "fp16"
+            eng = bcad_b200.Engine(spec, precision=want, max_batch=B, device=local_rank)
+            precision = want
         except ValueError as e:
-            if args.precision == "fp16":
+            if args.precision != "auto":
                 raise
             log(f"[bench] fp16 tensor path unavailable ({e}); using the fp32 CUDA-core path")
     if eng is None:
@@ -321,15 +322,15 @@ def run_ours(args, rank, world, local_rank):
                 "frac": ach / peak, "traffic": None, "peak_source": pk["source"] + " (sustained bf16 cuBLAS)",
                 "algorithmic_flops_per_launch": flops}
     else:
-        esz = 2 if precision == "fp16" else 4
+        esz = 2 if precision.startswith("fp16") else 4
         nbytes = tail_bytes_per_image(esz) * B
         ach = nbytes / (dom_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
                 "algorithmic_bytes_per_launch": nbytes}
     # Grad-CAM tail roofline (always reported beside the dominant kernel)
-    tail_ms = sum(ms for k, ms in prof.items() if k.split(":", 1)[1] in ("cam", "upsample_norm", "alpha_from_pool_grad", "tail_fused"))
-    esz = 2 if precision == "fp16" else 4
+    tail_ms = sum(ms for k, ms in prof.items() if k.split(":", 1)[1] in ("cam", "cam_c8", "upsample_norm", "alpha_from_pool_grad", "tail_fused"))
+    esz = 2 if precision.startswith("fp16") else 4
     tail_bytes = tail_bytes_per_image(esz) * B
     tail_roof = {"bound": "hbm", "kernels": "Grad-CAM tail (alpha, cam, upsample+min-max)", "ms": tail_ms,
                  "achieved": tail_bytes / max(1e-9, tail_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
@@ -347,7 +348,7 @@ def run_ours(args, rank, world, local_rank):
     out_json = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16" if precision == "fp16" else "f32", "data": "synthetic",
+        "dtype": {"fp16": "f16", "fp16x3": "f16x3 (hi+lo split, fp32-grade)"}.get(precision, "f32"), "data": "synthetic",
         "config": workload_config(B, precision),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
                 "d2h_bytes_per_step": int(heat_host.numel() * 4 + B * (2 * NUM_CLASSES * 4 + 4)),
@@ -392,7 +393,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="images per GPU per step")
-    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "fp16"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "fp16", "fp16x3"])
     ap.add_argument("--cpu-images", type=int, default=96, help="bounded CPU-baseline sample")
     ap.add_argument("--ref-images", type=int, default=64, help="images per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -9,13 +9,14 @@ from bcad_b200 import _lib
 from oracle import cnn as ocnn
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+FAST = sys.argv[2] if len(sys.argv) > 2 else "fp16"
 shape = (256, 256, 1)
 cfg = ocnn.NetConfig.torch_flavour(shape, 2, [(32, 3), (64, 3)], [256, 128], 0.01)
 p = ocnn.init_params(cfg, seed=7)
 x = ocnn.synth_images(N, shape, seed=20251018)
 spec = bcad_b200.NetSpec.torch_flavour(shape, 2, [(32, 3), (64, 3)], [256, 128], 0.01)
 res = {}
-for prec in ("fp32", "fp16"):
+for prec in ("fp32", FAST):
     e = bcad_b200.Engine(spec, precision=prec, max_batch=N)
     e.set_weights(p.conv_w, p.conv_b, p.dense_w, p.dense_b)
     cls, probs, logits, heat = e.predict_explain(x, None, "logit")
@@ -29,10 +30,10 @@ for prec in ("fp32", "fp16"):
         rng_ = cam.amax(dim=(1, 2)) - cam.amin(dim=(1, 2))
         kappa = (nrm / rng_.clamp_min(1e-30)).cpu().numpy()
     e.close()
-err = np.abs(res["fp16"][2] - res["fp32"][2]).reshape(N, -1).max(1)
+err = np.abs(res[FAST][2] - res["fp32"][2]).reshape(N, -1).max(1)
 margin = np.abs(res["fp32"][1][:, 0] - res["fp32"][1][:, 1])
-lerr = np.abs(res["fp16"][1] - res["fp32"][1]).max(1)
-flips = int((res["fp16"][0] != res["fp32"][0]).sum())
+lerr = np.abs(res[FAST][1] - res["fp32"][1]).max(1)
+flips = int((res[FAST][0] != res["fp32"][0]).sum())
 order = np.argsort(-err)
 print("N", N, "class flips", flips, "min margin", margin.min(), "max logit err", lerr.max())
 print("heat err: median %.4f p90 %.4f p99 %.4f max %.4f ; >1e-2: %d" % (np.median(err), np.quantile(err, .9), np.quantile(err, .99), err.max(), (err > 1e-2).sum()))
