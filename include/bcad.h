@@ -169,7 +169,7 @@ BCAD_API int bcad_selftest_umma(const void* a_img_dev, int a_bytes, const void* 
                        const int32_t* params_host, float* d_dev, void* stream);
 
 /* Micro-benchmark behind DESIGN.md's operand-layout choices: cycles of `reps` back-to-back 128xNx16 UMMAs and of
- * `reps` TMEM loads.  p = {N, a_layout, b_layout, a_lbo, a_sbo, b_lbo, b_sbo, reps, ld_warps, ld_x16}; out_dev: int64[3]. */
+ * `reps` TMEM loads.  p = {N, a_layout, b_layout, a_lbo, a_sbo, b_lbo, b_sbo, reps, ld_warps, ld_x16, a_off, alternate}; out_dev: int64[3]. */
 BCAD_API int bcad_selftest_umma_bench(const int32_t* p, long long* out_dev, void* stream);
 
 #ifdef __cplusplus

@@ -5,8 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bcad_b200
 lib = bcad_b200._lib.load()
 out = torch.zeros(3, dtype=torch.int64, device="cuda")
-def run(N, al, bl, albo, asbo, blbo, bsbo, reps=2000, ldw=4, x16=0):
-    p = np.array([N, al, bl, albo, asbo, blbo, bsbo, reps, ldw, x16], np.int32)
+def run(N, al, bl, albo, asbo, blbo, bsbo, reps=2000, ldw=4, x16=0, a_off=0, alt=0):
+    p = np.array([N, al, bl, albo, asbo, blbo, bsbo, reps, ldw, x16, a_off, alt], np.int32)
     bcad_b200._lib.check(lib.bcad_selftest_umma_bench(C.c_void_p(p.ctypes.data), C.c_void_p(out.data_ptr()), None))
     torch.cuda.synchronize()
     o = out.cpu().numpy()
@@ -17,7 +17,11 @@ for N in (64, 128, 256):
     c = run(N, 0, 2, 2176, 128, 16, 1024)
     d = run(N, 4, 4, 16, 512, 16, 512)
     print(f"N={N}: cycles/MMA  A,B no-swizzle {a[0]:.1f} | A,B SW128 {b[0]:.1f} | A none, B SW128 {c[0]:.1f} | A,B SW64 {d[0]:.1f}")
-for ldw in (1, 4, 8):
+for a_off in (0, 16, 32, 64):
+    for alt in (0, 1):
+        r = run(64, 0, 0, 2176, 128, 1024, 128, 2000, 4, 0, a_off, alt)
+        print(f"N=64 no-swizzle, A start +{a_off} B, alternate operands={alt}: {r[0]:.1f} cycles/MMA")
+for ldw in (1,):
     for x16 in (0, 1):
         r = run(64, 2, 2, 16, 1024, 16, 1024, 2000, ldw, x16)
         print(f"tmem ld: {ldw} warps, x{16 if x16 else 32}: {r[1]:.1f} cycles per load per warp")

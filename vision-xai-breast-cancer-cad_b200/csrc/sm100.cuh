@@ -79,6 +79,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     return d;
 }
 
+// 64-bit descriptor from separately tracked halves: only the low word (start address) changes between MMAs, so
+// per-MMA descriptor arithmetic stays a single 32-bit add
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+
 // instruction descriptor, kind::f16: bf16 x bf16 -> fp32, both operands K-major
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4)                 // D format  = F32
@@ -98,6 +106,23 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Predicated forms for warp-uniform issue loops: every lane runs the loop (so the compiler keeps the descriptors
+// in uniform registers and emits a plain predicated UTCHMMA, no per-thread serialisation), one elected lane issues.
+__device__ __forceinline__ void umma_f16_if(bool leader, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"((uint32_t)leader)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_if(bool leader, uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"((uint32_t)leader)
         : "memory");
 }
 // arrive on an mbarrier when every previously issued tcgen05.mma of this thread has completed

@@ -416,7 +416,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
+        {   // warp-uniform loop; one elected lane issues the MMAs and commits
+            const bool leader = elect_one();
             constexpr uint32_t idesc = make_idesc_f16(128, COUT);
             mbar_wait(wbar, 0);
             uint32_t g = 0, acc_it = 0;
@@ -435,17 +436,16 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
                     // descriptor templates: only the 14-bit start-address field changes between MMAs, and all the
                     // per-tap offsets are compile-time constants after unrolling (the single issuing thread must
                     // spend fewer cycles per MMA than the tensor core does: 32)
-                    constexpr uint64_t a_tmpl = ((uint64_t)(L::LBO >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
-                    constexpr uint64_t b_tmpl = ((uint64_t)((COUT * 16) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
-                    const uint64_t b_desc0 = b_tmpl | (uint64_t)((w_base & 0x3FFFFu) >> 4);
-                    constexpr uint64_t ones_tmpl = ((uint64_t)((128 * 16) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
-                    const uint64_t ones_desc = ones_tmpl | (uint64_t)((smem_u32(s_ones) & 0x3FFFFu) >> 4);
+                    constexpr uint32_t d_hi = (uint32_t)(128 >> 4) | (1u << 14);            // SBO = 128 B, descriptor version 1
+                    constexpr uint32_t a_lo_t = (uint32_t)(L::LBO >> 4) << 16;              // LBO = octet pitch of a ring row
+                    constexpr uint32_t b_lo_t = (uint32_t)((COUT * 16) >> 4) << 16;
+                    const uint32_t b_lo0 = b_lo_t | ((w_base & 0x3FFFFu) >> 4);
+                    const uint32_t ones_lo = ((uint32_t)((128 * 16) >> 4) << 16) | ((smem_u32(s_ones) & 0x3FFFFu) >> 4);
                     for (int r = 0; r < 2; ++r) {
                         if (2 * p + r >= nrows || (a.debug & 8)) break;     // debug bit 3: timing experiment without MMAs
                         const uint32_t d_tmem = tmem + j * (2 * COUT) + r * COUT;
                         // bias K-step: D = ones x {b_hi, b_lo} (initialises the accumulator with the fp32-exact bias)
-                        umma_bf16(d_tmem, ones_desc, b_desc0 + (uint64_t)(L::WBYTES >> 4), idesc, 0u);
-                        uint32_t acc = 1;
+                        umma_f16_if(leader, d_tmem, desc64(ones_lo, d_hi), desc64(b_lo0 + (uint32_t)(L::WBYTES >> 4), d_hi), idesc, 0u);
 #pragma unroll
                         for (int dy = 0; dy < 3; ++dy) {
                             const int i = 2 * p + r + dy;                    // band-local input row
@@ -453,17 +453,15 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
                             uint32_t row_base;
                             if (in_row < 0 || in_row >= a.H) row_base = zero_base;
                             else row_base = ring_base + ((((g + (i >> 1) - p) % IG_STAGES) << 1) + (i & 1)) * L::ROWB;
-                            const uint64_t a_desc0 = a_tmpl | (uint64_t)((row_base & 0x3FFFFu) >> 4);
+                            const uint32_t a_lo0 = a_lo_t | ((row_base & 0x3FFFFu) >> 4);
 #pragma unroll
                             for (int dx = 0; dx < 3; ++dx) {
                                 if constexpr (!X3) {
 #pragma unroll
-                                    for (int ks = 0; ks < CIN / 16; ++ks) {
-                                        const uint64_t ad = a_desc0 + (uint64_t)((ks * 2 * L::LBO + dx * 16) >> 4);
-                                        const uint64_t bd = b_desc0 + (uint64_t)((((dy * 3 + dx) * L::CHUNKS + 2 * ks) * (COUT * 16)) >> 4);
-                                        umma_bf16(d_tmem, ad, bd, idesc, acc);
-                                        acc = 1;
-                                    }
+                                    for (int ks = 0; ks < CIN / 16; ++ks)
+                                        umma_f16_if(leader, d_tmem, desc64(a_lo0 + (uint32_t)((ks * 2 * L::LBO + dx * 16) >> 4), d_hi),
+                                                  desc64(b_lo0 + (uint32_t)((((dy * 3 + dx) * L::CHUNKS + 2 * ks) * (COUT * 16)) >> 4), d_hi),
+                                                  idesc, 1u);
                                 } else {
                                     // fp16x3: input octets [x_hi (H) | x_lo (H)], weight octets per tap [w_hi (H) | w_lo (H)], H = CIN/16:
                                     //   x_hi.w_hi + x_lo.w_hi + x_hi.w_lo   (x_lo.w_lo ~ 2^-22 is dropped)
@@ -474,19 +472,18 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
                                         for (int kp = 0; kp < HP; ++kp) {
                                             const int a_pair = (g3 == 1 ? HP : 0) + kp;         // x_hi, x_lo, x_hi
                                             const int b_pair = (g3 == 2 ? HP : 0) + kp;         // w_hi, w_hi, w_lo
-                                            const uint64_t ad = a_desc0 + (uint64_t)((a_pair * 2 * L::LBO + dx * 16) >> 4);
-                                            const uint64_t bd = b_desc0 + (uint64_t)((((dy * 3 + dx) * L::CHUNKS + 2 * b_pair) * (COUT * 16)) >> 4);
-                                            umma_bf16(d_tmem, ad, bd, idesc, acc);
-                                            acc = 1;
+                                            umma_f16_if(leader, d_tmem, desc64(a_lo0 + (uint32_t)((a_pair * 2 * L::LBO + dx * 16) >> 4), d_hi),
+                                                      desc64(b_lo0 + (uint32_t)((((dy * 3 + dx) * L::CHUNKS + 2 * b_pair) * (COUT * 16)) >> 4), d_hi),
+                                                      idesc, 1u);
                                         }
                                 }
                             }
                         }
                     }
-                    umma_commit(&empty[g % IG_STAGES]);      // stage p is dead once these MMAs retire
-                    umma_commit(&tfull[j]);
+                    umma_commit_if(leader, &empty[g % IG_STAGES]);      // stage p is dead once these MMAs retire
+                    umma_commit_if(leader, &tfull[j]);
                 }
-                umma_commit(&empty[g % IG_STAGES]);          // the band's last stage
+                umma_commit_if(leader, &empty[g % IG_STAGES]);          // the band's last stage
                 ++g;
             }
         }

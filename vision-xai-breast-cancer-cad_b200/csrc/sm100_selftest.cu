@@ -67,7 +67,7 @@ umma_selftest_kernel(const uint4* __restrict__ a_img, int a_bytes, const uint4* 
 // and for `reps` TMEM->register loads by `nwarps` warps.  out[0] = MMA cycles, out[1] = TMEM-load cycles.
 __global__ void __launch_bounds__(256, 1)
 umma_bench_kernel(int N, int a_layout, int b_layout, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int reps, int ld_warps,
-                  int ld_x16, long long* __restrict__ out) {
+                  int ld_x16, int a_off, int alternate, long long* __restrict__ out) {
     using namespace sm100;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
@@ -89,10 +89,15 @@ umma_bench_kernel(int N, int a_layout, int b_layout, int a_lbo, int a_sbo, int b
     const uint32_t tmem = tmem_base;
     if (tid == 0) {
         const uint32_t idesc = make_idesc_f16(128, N);
-        const uint64_t ad = make_smem_desc(smem_u32(smem), a_lbo, a_sbo, a_layout);
+        const uint64_t ad = make_smem_desc(smem_u32(smem) + a_off, a_lbo, a_sbo, a_layout);
+        const uint64_t ad2 = make_smem_desc(smem_u32(smem) + a_off + (alternate ? 4096 : 0), a_lbo, a_sbo, a_layout);
         const uint64_t bd = make_smem_desc(smem_u32(smem) + 32768, b_lbo, b_sbo, b_layout);
+        const uint64_t bd2 = make_smem_desc(smem_u32(smem) + 32768 + (alternate ? 2048 : 0), b_lbo, b_sbo, b_layout);
         const long long t0 = clock64();
-        for (int k = 0; k < reps; ++k) umma_bf16(tmem, ad, bd, idesc, 1u);
+        for (int k = 0; k < reps; k += 2) {
+            umma_bf16(tmem, ad, bd, idesc, 1u);
+            umma_bf16(tmem, ad2, bd2, idesc, 1u);
+        }
         umma_commit(&bar);
         mbar_wait(&bar, 0);
         out[0] = clock64() - t0;
@@ -127,12 +132,12 @@ umma_bench_kernel(int N, int a_layout, int b_layout, int a_lbo, int a_sbo, int b
 
 }  // namespace bcad
 
-extern "C" int bcad_selftest_umma_bench(const int32_t* p /*N,a_layout,b_layout,a_lbo,a_sbo,b_lbo,b_sbo,reps,ld_warps,ld_x16*/,
+extern "C" int bcad_selftest_umma_bench(const int32_t* p /*N,a_layout,b_layout,a_lbo,a_sbo,b_lbo,b_sbo,reps,ld_warps,ld_x16,a_off,alternate*/,
                                         long long* out_dev, void* stream) {
     using namespace bcad;
     BCAD_REQUIRE(p && out_dev, "selftest bench: null argument");
     BCAD_CUDA_CHECK(cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    umma_bench_kernel<<<1, 256, 64 * 1024, (cudaStream_t)stream>>>(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8], p[9], out_dev);
+    umma_bench_kernel<<<1, 256, 64 * 1024, (cudaStream_t)stream>>>(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8], p[9], p[10], p[11], out_dev);
     BCAD_CUDA_CHECK(cudaGetLastError());
     return BCAD_OK;
 }
