@@ -149,6 +149,17 @@ BCAD_API int bcad_gradcam_tail(const void* A_dev, const void* dA_dev, int B, int
 BCAD_API int bcad_overlay(const float* img01_dev, const float* cam_dev, int B, int H, int W,
                  uint8_t* overlay_rgb_dev, uint8_t* heat_u8_dev, void* stream);
 
+/* ---- tiny U-Net encoder front: conv2d + relu + max_pool of Classes/unet.py:13-73 ------- */
+/* y = LeakyReLU_alpha(conv(x, kernel) + bias), NHWC fp32, kernel DEVICE fp32 (k,k,Cin,Cout) as unet.py holds it, bias
+ * DEVICE (Cout) or NULL.  padded_output=1 reproduces conv2d(..., 'same') of unet.py:19-27: the output has the PADDED
+ * size (H+2*pad, W+2*pad), the true convolution in its top-left corner and zeros elsewhere.  y [B,Ho,Wo,Cout] and/or
+ * pooled [B,Ho/2,Wo/2,Cout] (2x2/2 max-pool, unet.py:32-43); either may be NULL.  alpha=0 is ReLU (unet.py:53). */
+BCAD_API int bcad_conv_block(const float* x_dev, int B, int H, int W, int Cin, const float* kernel_kkcf_dev,
+                    const float* bias_dev, int k, int Cout, int pad, float alpha, int padded_output,
+                    float* y_dev, float* pooled_dev, void* stream);
+/* non-overlapping mean pool, floor dims (Classes/ImageSegmentation.py:145-163): [B,H,W,C] -> [B,H/pool,W/pool,C] */
+BCAD_API int bcad_avg_pool(const float* x_dev, int B, int H, int W, int C, int pool, float* out_dev, void* stream);
+
 /* ---- introspection ---------------------------------------------------------------------------- */
 /* kernels launched by this handle since creation (bench.py reports the delta as gpu_launches) */
 BCAD_API int64_t bcad_launch_count(bcad_model* m);

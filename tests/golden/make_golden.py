@@ -113,6 +113,35 @@ def torch_case(name, input_shape, conv_layers, hidden, batch, seed, alpha=0.01):
     print("wrote", name, "classes", out["pred_class"])
 
 
+def unet_case(name, shape, batch, seed):
+    """Classes/unet.py functions (exec-loaded without the script part and its missing imports)."""
+    import types
+    path = os.path.join(ref_loader.REF_ROOT, "Classes", "unet.py")
+    src = open(path, encoding="utf-8").read()
+    src = src[:src.index("# ----------- Run UNet on All Images")]
+    src = src.replace("from preprocessing import processed_images_np", "").replace("import matplotlib.pyplot as plt", "")
+    mod = types.ModuleType("ref_unet")
+    exec(compile(src, path, "exec"), mod.__dict__)
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((batch,) + tuple(shape))
+    np.random.seed(seed)
+    bn = mod.tiny_unet_numpy(x)                          # draws its three kernels from the global stream
+    np.random.seed(seed)
+    c1 = mod.conv2d(x, np.random.randn(3, 3, shape[-1], 16))
+    seg_path = os.path.join(ref_loader.REF_ROOT, "Classes", "ImageSegmentation.py")
+    out = {"x": x, "seed": seed, "bn": bn, "c1": c1, "p1": mod.max_pool(mod.relu(c1))}
+    # average_pool as in Classes/ImageSegmentation.py:145-163 (same arithmetic, restated inline: the class needs pydicom)
+    b, h, w, c = bn.shape
+    ps = 3
+    ap = np.zeros((b, h // ps, w // ps, c))
+    for i in range(h // ps):
+        for j in range(w // ps):
+            ap[:, i, j, :] = np.mean(bn[:, i * ps:(i + 1) * ps, j * ps:(j + 1) * ps, :], axis=(1, 2))
+    out["avg3"] = ap
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote", name, bn.shape, ap.shape)
+
+
 def cv2_cases():
     import cv2
     lut = cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(1, 256), cv2.COLORMAP_JET)[0]
@@ -136,4 +165,6 @@ if __name__ == "__main__":
     numpy_case("ref_numpy_k5", (15, 14, 2), [(3, 5), (4, 3)], [5], seed=14)
     torch_case("ref_torch_small", (16, 16, 1), [(4, 3), (8, 3)], [12, 6], batch=3, seed=21)
     torch_case("ref_torch_odd", (13, 18, 3), [(5, 3), (6, 3)], [9], batch=2, seed=22, alpha=0.2)
+    unet_case("ref_unet_small", (16, 16, 1), 2, seed=31)
+    unet_case("ref_unet_odd", (21, 18, 2), 1, seed=32)
     cv2_cases()

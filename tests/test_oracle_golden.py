@@ -170,3 +170,19 @@ def test_cpu_port_matches_reference_fixture():
     assert np.array_equal(cls, g["pred_class"])
     want = ogc.gradcam_tail(g["A_last"], g["dA1_logit_c0"], (16, 16))
     np.testing.assert_allclose(heat, want, rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("name,c", [("ref_unet_small", 1), ("ref_unet_odd", 2)])
+def test_unet_oracle_matches_reference_fixture(name, c):
+    """oracle.unet vs Classes/unet.py outputs (padded-size 'same' conv quirk, pools, kernel stream order)."""
+    from oracle import unet as ou
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    ks = ou.draw_kernels(c, int(g["seed"]))
+    c1 = ou.conv2d_same_quirk(g["x"], ks[0])
+    assert c1.shape == g["c1"].shape == (g["x"].shape[0], g["x"].shape[1] + 2, g["x"].shape[2] + 2, 16)
+    assert np.all(c1[:, -2:] == 0) and np.all(c1[:, :, -2:] == 0)            # the quirk: trailing rows/cols are zero
+    np.testing.assert_allclose(c1, g["c1"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(ou.max_pool(ou.relu(c1)), g["p1"], rtol=0, atol=1e-12)
+    bn = ou.tiny_unet(g["x"], ks)
+    np.testing.assert_allclose(bn, g["bn"], rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(ou.average_pool(bn, 3), g["avg3"], rtol=1e-12, atol=1e-9)

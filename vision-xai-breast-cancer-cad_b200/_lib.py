@@ -56,6 +56,9 @@ _SIGNATURES = {
     "bcad_predict_explain_host": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, _P, _P, _P]),
     "bcad_gradcam_tail": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "bcad_overlay": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "bcad_conv_block": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float,
+                                  C.c_int, _P, _P, _P]),
+    "bcad_avg_pool": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "bcad_launch_count": (C.c_int64, [_P]),
     "bcad_uses_tensor_path": (C.c_int, [_P]),
     "bcad_set_profiling": (C.c_int, [_P, C.c_int]),

@@ -737,6 +737,45 @@ int bcad_overlay(const float* img01, const float* cam, int B, int H, int W, uint
     return launch_overlay(img01, cam, B, H, W, overlay_rgb, heat_u8, (cudaStream_t)stream);
 }
 
+// -----------------------------------------------------------------------------------------------------
+// stand-alone conv block / average pool: the tiny U-Net encoder front (Classes/unet.py:13-73)
+// -----------------------------------------------------------------------------------------------------
+int bcad_conv_block(const float* x, int B, int H, int W, int Cin, const float* kernel_kkcf, const float* bias, int k, int Cout,
+                    int pad, float alpha, int padded_output, float* y, float* pooled, void* stream) {
+    BCAD_REQUIRE(x && kernel_kkcf && (y || pooled), "conv_block: null argument");
+    BCAD_REQUIRE(B >= 1 && H >= 1 && W >= 1 && Cin >= 1 && Cout >= 1 && k >= 1 && k <= 7 && pad >= 0 && pad <= 3, "conv_block: bad sizes");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int Hv = H + 2 * pad - k + 1, Wv = W + 2 * pad - k + 1;           // true convolution output
+    BCAD_REQUIRE(Hv >= 1 && Wv >= 1, "conv_block: kernel larger than the padded input");
+    // padded_output reproduces conv2d(...,'same') of Classes/unet.py:19-27: output allocated at the padded input size,
+    // the trailing rows/cols (windows skipped by the reference) stay zero
+    const int Ho = padded_output ? H + 2 * pad : Hv, Wo = padded_output ? W + 2 * pad : Wv;
+    const int CoutPad = cdiv(Cout, 32) * 32;
+    float* scratch = nullptr;
+    const size_t wn = (size_t)k * k * Cin * CoutPad;
+    BCAD_CUDA_CHECK(cudaMallocAsync((void**)&scratch, (wn + CoutPad) * sizeof(float), s));
+    int rc = launch_pad_conv_weights(kernel_kkcf, scratch, k * k, Cin, Cout, CoutPad, s);
+    if (rc == BCAD_OK) {
+        if (bias) rc = launch_pad_conv_weights(bias, scratch + wn, 1, 1, Cout, CoutPad, s);
+        else if (cudaMemsetAsync(scratch + wn, 0, CoutPad * sizeof(float), s) != cudaSuccess) rc = BCAD_ERR_CUDA;
+    }
+    if (rc == BCAD_OK) {
+        ConvArgs a;
+        a.x = x; a.w = scratch; a.bias = scratch + wn; a.y = y; a.p = pooled;
+        a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.CoutPad = CoutPad; a.ksize = k; a.pad = pad;
+        a.Ho = Ho; a.Wo = Wo; a.Hp = Ho / 2; a.Wp = Wo / 2; a.alpha = alpha;
+        a.Hv = padded_output ? Hv : 0; a.Wv = padded_output ? Wv : 0;
+        rc = launch_conv_fp32(a, s);
+    }
+    cudaFreeAsync(scratch, s);
+    return rc;
+}
+
+int bcad_avg_pool(const float* x, int B, int H, int W, int C, int pool, float* out, void* stream) {
+    BCAD_REQUIRE(x && out && B >= 1 && H >= 1 && W >= 1 && C >= 1 && pool >= 1, "avg_pool: bad argument");
+    return launch_avg_pool(x, out, B, H, W, C, pool, (cudaStream_t)stream);
+}
+
 int64_t bcad_launch_count(bcad_model* mm) {
     Model* m = reinterpret_cast<Model*>(mm);
     return m ? m->launches : -1;

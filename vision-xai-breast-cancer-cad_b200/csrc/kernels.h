@@ -16,6 +16,7 @@ struct ConvArgs {
     float* p;            // [B,Hp,Wp,Cout] 2x2 max-pooled, or nullptr
     int B, H, W, Cin, Cout, CoutPad, ksize, pad, Ho, Wo, Hp, Wp;
     float alpha;         // LeakyReLU slope (1 = identity)
+    int Hv = 0, Wv = 0;  // when > 0: outputs at (oy >= Hv or ox >= Wv) are forced to 0 (Classes/unet.py:19-27 quirk)
 };
 int launch_conv_fp32(const ConvArgs& a, cudaStream_t s);
 
@@ -48,6 +49,10 @@ int launch_cam(const void* A, int dtype, const float* alpha_part, int alpha_spli
                cudaStream_t s);
 int launch_upsample_norm(const float* cam_lo, const float* mm, int mm_splits, float* out, int B, int h,
                          int w, int H, int W, cudaStream_t s);
+// non-overlapping mean pool, floor dims (Classes/ImageSegmentation.py:145-163)
+int launch_avg_pool(const float* x, float* out, int B, int H, int W, int C, int pool, cudaStream_t s);
+// [k][k][Cin][Cout] -> [k*k][Cin][CoutPad] (zero padded)
+int launch_pad_conv_weights(const float* w, float* out, int taps, int Cin, int Cout, int CoutPad, cudaStream_t s);
 int launch_overlay(const float* img01, const float* cam, int B, int H, int W, uint8_t* overlay_rgb,
                    uint8_t* heat_u8, cudaStream_t s);
 

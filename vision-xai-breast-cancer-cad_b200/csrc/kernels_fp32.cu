@@ -106,9 +106,10 @@ __global__ void __launch_bounds__(256, 2) conv_fp32_kernel(ConvArgs a, int tiles
     for (int r = 0; r < 2; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[r][c][j] = leaky(acc[r][c][j] + bias[j], a.alpha);
             const int oy = oy0 + ty * 2 + r, ox = ox0 + tx * 4 + c;
+            const bool dead = (a.Hv > 0) && (oy >= a.Hv || ox >= a.Wv);     // zero border of the padded-size output
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[r][c][j] = dead ? 0.f : leaky(acc[r][c][j] + bias[j], a.alpha);
             if (a.y != nullptr && oy < a.Ho && ox < a.Wo) {
                 float* dst = a.y + (((size_t)b * a.Ho + oy) * a.Wo + ox) * a.Cout + cbase;
                 if (vec) {
@@ -885,6 +886,50 @@ int launch_upsample_norm(const float* cam_lo, const float* mm, int mm_splits, fl
     if (smem > 48 * 1024)
         BCAD_CUDA_CHECK(cudaFuncSetAttribute(upsample_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     upsample_norm_kernel<<<B, UP_THREADS, smem, s>>>(cam_lo, mm, mm_splits, out, h, w, H, W, lo_in_smem);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+// =====================================================================================================
+// small helpers of the tiny U-Net front
+// =====================================================================================================
+__global__ void avg_pool_kernel(const float* __restrict__ x, float* __restrict__ out, int H, int W, int C, int pool,
+                                int Hn, int Wn, size_t total) {
+    const float inv = 1.f / (float)(pool * pool);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        size_t r = i / C;
+        const int j = (int)(r % Wn); r /= Wn;
+        const int ii = (int)(r % Hn);
+        const size_t b = r / Hn;
+        float acc = 0.f;
+        for (int u = 0; u < pool; ++u)
+            for (int v = 0; v < pool; ++v) acc += x[((b * H + (size_t)ii * pool + u) * W + (size_t)j * pool + v) * C + c];
+        out[i] = acc * inv;
+    }
+}
+
+int launch_avg_pool(const float* x, float* out, int B, int H, int W, int C, int pool, cudaStream_t s) {
+    const int Hn = H / pool, Wn = W / pool;
+    const size_t total = (size_t)B * Hn * Wn * C;
+    if (total == 0) return BCAD_OK;
+    const int blocks = (int)min((size_t)148 * 8, (total + 255) / 256);
+    avg_pool_kernel<<<blocks, 256, 0, s>>>(x, out, H, W, C, pool, Hn, Wn, total);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+__global__ void pad_conv_weights_kernel(const float* __restrict__ w, float* __restrict__ out, int rows, int Cout, int CoutPad) {
+    const int total = rows * CoutPad;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int f = i % CoutPad, r = i / CoutPad;
+        out[i] = f < Cout ? w[(size_t)r * Cout + f] : 0.f;
+    }
+}
+
+int launch_pad_conv_weights(const float* w, float* out, int taps, int Cin, int Cout, int CoutPad, cudaStream_t s) {
+    const int total = taps * Cin * CoutPad;
+    pad_conv_weights_kernel<<<cdiv(total, 256), 256, 0, s>>>(w, out, taps * Cin, Cout, CoutPad);
     BCAD_CUDA_CHECK(cudaGetLastError());
     return BCAD_OK;
 }
