@@ -206,15 +206,16 @@ conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_
         }
         fence_proxy_async();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {                            // warp-uniform; one elected lane issues (plain predicated UTCHMMA)
+            const bool leader = elect_one();
             tc_fence_after();
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks)
-                    umma_bf16(tmem + q * COUT, a_desc0 + (uint64_t)((q * 8192 + ks * 4096) >> 4),
-                              b_desc0 + (uint64_t)((ks * 2 * COUT * 16) >> 4), idesc, ks);
-            umma_commit(&bar);
+                    umma_f16_if(leader, tmem + q * COUT, a_desc0 + (uint64_t)((q * 8192 + ks * 4096) >> 4),
+                                b_desc0 + (uint64_t)((ks * 2 * COUT * 16) >> 4), idesc, ks);
+            umma_commit_if(leader, &bar);
         }
         if (tile + (int)gridDim.x < n_tiles) load_patch(tile + gridDim.x, patch);     // prefetch the next tile's inputs
         mbar_wait(&bar, phase);
@@ -333,7 +334,11 @@ struct IgemmSmem {
     static constexpr int OFF_ZERO = OFF_ONES + ONES_TILE;
     static constexpr int OFF_RING = OFF_ZERO + ROWB;
     static constexpr int OFF_BAR = OFF_RING + STAGES * 2 * ROWB;
-    static constexpr int TOTAL = OFF_BAR + 256;
+    // activation staging for bulk (TMA) stores: 2 accumulator buffers x 2 rows x (COUT/8) octets x 128 px x 16 B
+    static constexpr bool STAGED = (CIN <= 32);
+    static constexpr int STAGE_BYTES = 2 * (COUT / 8) * 128 * 16;
+    static constexpr int OFF_STAGE = OFF_BAR + 256;
+    static constexpr int TOTAL = OFF_STAGE + (STAGED ? 2 * STAGE_BYTES : 0);
 };
 
 template <int CIN, int COUT, bool X3>
@@ -345,6 +350,9 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
     uint8_t* s_zero = smem + L::OFF_ZERO;
     uint8_t* s_ring = smem + L::OFF_RING;
     uint8_t* s_ones = smem + L::OFF_ONES;
+    uint8_t* s_stage = smem + L::OFF_STAGE;
+    constexpr bool STAGED = L::STAGED && !X3;
+    (void)s_stage;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
     uint64_t* full = bars;                       // [IG_STAGES] producer -> MMA
     uint64_t* empty = bars + IG_STAGES;          // [IG_STAGES] MMA -> producer
@@ -565,7 +573,12 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
                             }
                         }
                     }
-                } else
+                } else {
+                if constexpr (STAGED) {
+                    // staging buffer j was last read by the bulk stores issued two pairs ago
+                    if (tid == 64) bulk_wait_read<1>();
+                    named_bar_sync(1, 256);
+                }
 #pragma unroll 1
                 for (int half = half0; half < COUT / 32; half += 2) {
                     float v0[32], v1[32];
@@ -582,7 +595,21 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
                         a0[q] = __hmax2(h0, __hmul2(h0, alpha2));
                         a1[q] = __hmax2(h1, __hmul2(h1, alpha2));
                     }
-                    if (a.act != nullptr && x < a.Wo) {
+                    if constexpr (STAGED) {
+                        // activations go to a shared-memory image of the two output rows ([row][octet][x][16 B], exactly
+                        // their global layout) and leave with two bulk (TMA) stores per pair: 16 STS instead of 16 STG
+                        if (a.act != nullptr && x < a.Wo) {
+                            uint8_t* st = s_stage + j * L::STAGE_BYTES;
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc) {
+                                const int chunk = half * 4 + cc;
+                                *reinterpret_cast<uint4*>(st + ((size_t)chunk * a.Wo + x) * 16) =
+                                    make_uint4(h2u(a0[cc * 4]), h2u(a0[cc * 4 + 1]), h2u(a0[cc * 4 + 2]), h2u(a0[cc * 4 + 3]));
+                                *reinterpret_cast<uint4*>(st + ((size_t)((COUT / 8) + chunk) * a.Wo + x) * 16) =
+                                    make_uint4(h2u(a1[cc * 4]), h2u(a1[cc * 4 + 1]), h2u(a1[cc * 4 + 2]), h2u(a1[cc * 4 + 3]));
+                            }
+                        }
+                    } else if (a.act != nullptr && x < a.Wo) {
 #pragma unroll
                         for (int cc = 0; cc < 4; ++cc) {
                             const int chunk = half * 4 + cc;
@@ -623,12 +650,28 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
                         }
                     }
                 }
+                if constexpr (!X3 && STAGED) {
+                    if (a.act != nullptr) {
+                        fence_proxy_async();                       // staged rows -> visible to the bulk-copy engine
+                        named_bar_sync(1, 256);
+                        if (tid == 64) {
+                            const size_t row_bytes = (size_t)(COUT / 8) * a.Wo * 16;
+                            uint8_t* gdst = reinterpret_cast<uint8_t*>(a.act) + ((size_t)b * a.Ho + t0) * row_bytes;
+                            const uint8_t* st = s_stage + j * L::STAGE_BYTES;
+                            bulk_s2g(gdst, st, (uint32_t)row_bytes);
+                            if (has1) bulk_s2g(gdst + row_bytes, st + row_bytes, (uint32_t)row_bytes);
+                            bulk_commit();
+                        }
+                    }
+                }
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[j]);
             }
         }
     }
+    if (STAGED && tid == 64) bulk_wait<0>();         // staged rows must be read out before the CTA's smem goes away
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 256);
