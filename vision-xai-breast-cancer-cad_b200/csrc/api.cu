@@ -674,9 +674,26 @@ int bcad_predict_explain_host(bcad_model* mm, const float* x_host, int B, const 
     float* st_logits = reinterpret_cast<float*>(X.h_small);
     float* st_probs = st_logits + (size_t)B * nc;
     int32_t* st_cls = reinterpret_cast<int32_t*>(st_probs + (size_t)B * nc);
-    const int nchunks = cdiv(B, X.chunk);
-    for (int c = 0; c < nchunks; ++c) {
-        const int slot = c & 1, b0 = c * X.chunk, n = std::min(X.chunk, B - b0);
+    // chunk schedule: ramp up and down (C/4, C/2, C, ..., C, C/2, C/4) so the un-overlapped head (first H2D + compute) and
+    // tail (last D2H) of the pipeline are short; the steady state runs H2D, compute and D2H of three chunks concurrently
+    std::vector<int> sizes;
+    {
+        const int C0 = X.chunk;
+        int left = B;
+        std::vector<int> head, tail;
+        if (B >= 4 * C0 && C0 >= 8) {
+            head = {C0 / 4, C0 / 2};
+            tail = {C0 / 2, C0 / 4};
+        }
+        for (int v : head) { sizes.push_back(v); left -= v; }
+        int tail_sum = 0;
+        for (int v : tail) tail_sum += v;
+        while (left - tail_sum > 0) { const int v = std::min(C0, left - tail_sum); sizes.push_back(v); left -= v; }
+        for (int v : tail) { sizes.push_back(v); left -= v; }
+    }
+    int b0 = 0;
+    for (int c = 0; c < (int)sizes.size(); b0 += sizes[c], ++c) {
+        const int slot = c & 1, n = sizes[c];
         // slot reuse: its previous D2H (chunk c-2) must have drained before we overwrite its buffers
         if (c >= 2) {
             BCAD_CUDA_CHECK(cudaStreamWaitEvent(X.s_in, X.compute_done[slot], 0));
