@@ -108,15 +108,15 @@ int launch_conv_first_pool(const float* x, const float* w9c, const float* bias, 
 // term is 2^-22 relative).  One CTA tile = 128 pooled pixels of one pooled row; the four members of each 2x2 pool
 // window are four accumulators of the SAME TMEM lane, so pooling is three max ops per channel with no shuffles.
 // The CUDA-core work left is the im2col row build (16 STS.128 / thread) and the pooled epilogue: ~4x fewer
-// instructions than 1152 FFMAs per pooled pixel.  128-thread CTAs, 4 per SM (TMEM 4 x 128 columns).
+// instructions than 1152 FFMAs per pooled pixel.  128-thread CTAs, 3 per SM, im2col image double-buffered.
 // =====================================================================================================
 template <int COUT, bool SPLIT>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, 3)
 conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_img /*[4][COUT][16 B]*/,
                      __half* __restrict__ out, int B, int H, int W, int pad, int Hp, int Wp, float alpha) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* s_a = smem;                          // 4 classes x [4 chunks][128 rows][16 B] = 32 KB
-    uint8_t* s_b = smem + 4 * 8192;               // [4 chunks][COUT][16 B]
+    uint8_t* s_a = smem;                          // 2 buffers x 4 classes x [4 chunks][128 rows][16 B] = 2 x 32 KB
+    uint8_t* s_b = smem + 2 * 32768;              // [4 chunks][COUT][16 B]
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -169,14 +169,10 @@ conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_
                 }
         }
     };
-    float patch[16];
-    if ((int)blockIdx.x < n_tiles) load_patch(blockIdx.x, patch);
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int xt = tile % xtiles;
-        const int py = (tile / xtiles) % Hp;
-        const int b = tile / (xtiles * Hp);
-        const int px = xt * 128 + tid;
-        // ---- im2col rows of this thread's 2x2 pool window.  K slots (matching the weight image):
+    // Software pipeline over tiles: the im2col image is double-buffered, so the rows of tile t+1 are built while the
+    // MMAs of tile t run; one __syncthreads per tile.
+    auto build = [&](int buf, const float (&patch)[16]) {
+        // im2col rows of this thread's 2x2 pool window.  K slots (matching the weight image):
         //      [x(9) 1 | x_lo(9) 1 | x(9) 0 0 0]  -- cvt.rn.f16x2 turns an fp32 pair straight into one packed word
         float lo[16];
 #pragma unroll
@@ -201,11 +197,11 @@ conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_
             wd[15] = 0u;
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch)
-                *reinterpret_cast<uint4*>(s_a + q * 8192 + ch * 2048 + tid * 16) =
+                *reinterpret_cast<uint4*>(s_a + buf * 32768 + q * 8192 + ch * 2048 + tid * 16) =
                     make_uint4(wd[ch * 4], wd[ch * 4 + 1], wd[ch * 4 + 2], wd[ch * 4 + 3]);
         }
-        fence_proxy_async();
-        __syncthreads();
+    };
+    auto issue = [&](int buf) {
         if (warp == 0) {                            // warp-uniform; one elected lane issues (plain predicated UTCHMMA)
             const bool leader = elect_one();
             tc_fence_after();
@@ -213,14 +209,16 @@ conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_
             for (int q = 0; q < 4; ++q)
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks)
-                    umma_f16_if(leader, tmem + q * COUT, a_desc0 + (uint64_t)((q * 8192 + ks * 4096) >> 4),
+                    umma_f16_if(leader, tmem + q * COUT, a_desc0 + (uint64_t)((buf * 32768 + q * 8192 + ks * 4096) >> 4),
                                 b_desc0 + (uint64_t)((ks * 2 * COUT * 16) >> 4), idesc, ks);
             umma_commit_if(leader, &bar);
         }
-        if (tile + (int)gridDim.x < n_tiles) load_patch(tile + gridDim.x, patch);     // prefetch the next tile's inputs
-        mbar_wait(&bar, phase);
-        phase ^= 1;
-        tc_fence_after();
+    };
+    auto epilogue = [&](int tile) {
+        const int xt = tile % xtiles;
+        const int py = (tile / xtiles) % Hp;
+        const int b = tile / (xtiles * Hp);
+        const int px = xt * 128 + tid;
         // ---- epilogue: pool (3 max), LeakyReLU once, fp16 C8-planar store
 #pragma unroll 1
         for (int c0 = 0; c0 < COUT; c0 += 16) {
@@ -273,8 +271,32 @@ conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_
                 }
             }
         }
+    };
+    const int G = gridDim.x;
+    float patch[16];
+    int tile = blockIdx.x;
+    if (tile < n_tiles) {
+        load_patch(tile, patch);
+        build(0, patch);
+        fence_proxy_async();
+        if (tile + G < n_tiles) load_patch(tile + G, patch);
+        __syncthreads();
+        issue(0);
+    }
+    for (int it = 0; tile < n_tiles; tile += G, ++it) {
+        const int next = tile + G;
+        if (next < n_tiles) {
+            build((it + 1) & 1, patch);             // overlaps the MMAs of this tile
+            fence_proxy_async();
+            if (next + G < n_tiles) load_patch(next + G, patch);     // inputs of tile t+2
+        }
+        mbar_wait(&bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        epilogue(tile);
         tc_fence_before();
-        __syncthreads();                            // TMEM + im2col buffer are reused by the next tile
+        __syncthreads();                            // next image fully built; TMEM drained
+        if (next < n_tiles) issue((it + 1) & 1);
     }
     if (warp == 0) tmem_dealloc(tmem, 4 * COUT);
 }
@@ -292,8 +314,8 @@ int launch_conv_first_tc(const float* x, const uint8_t* w_img, __half* out, int 
                          float alpha, bool split_hi_lo, int sms, cudaStream_t s) {
     const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2, Hp = Ho / 2, Wp = Wo / 2;
     const int n_tiles = B * Hp * cdiv(Wp, 128);
-    const int smem = 4 * 8192 + 4 * Cout * 16;
-    const int per_sm = Cout <= 32 ? 4 : 2;          // TMEM: 4*Cout columns per CTA
+    const int smem = 2 * 32768 + 4 * Cout * 16;
+    const int per_sm = Cout <= 32 ? 3 : 2;          // smem: 66 KB per CTA; TMEM: 4*Cout columns per CTA
     const int grid = n_tiles < sms * per_sm ? n_tiles : sms * per_sm;
     if (Cout == 32 && !split_hi_lo) return launch_conv_first_tc_t<32, false>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s);
     if (Cout == 32 && split_hi_lo) return launch_conv_first_tc_t<32, true>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s);
