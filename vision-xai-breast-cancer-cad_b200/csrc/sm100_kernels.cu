@@ -146,11 +146,20 @@ conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_
     uint32_t phase = 0;
     // input patch of a tile: 4 x 4 fp32 values per thread (zero outside the image); the loads of tile t+1 are
     // issued before the epilogue of tile t so their latency hides behind it
-    auto load_patch = [&](int tile, float (&v)[16]) {
-        const int xt = tile % xtiles;
-        const int py = (tile / xtiles) % Hp;
-        const int b = tile / (xtiles * Hp);
-        const int px = xt * 128 + tid;
+    // tile coordinates (image, pooled row, x tile) advance by gridDim.x tiles per iteration without divisions
+    struct TileC { int b, py, xt; };
+    const int G = gridDim.x;
+    const int g_xt = G % xtiles, g_py = (G / xtiles) % Hp, g_b = G / (xtiles * Hp);
+    auto advance = [&](TileC& t) {
+        t.xt += g_xt;
+        if (t.xt >= xtiles) { t.xt -= xtiles; ++t.py; }
+        t.py += g_py;
+        if (t.py >= Hp) { t.py -= Hp; ++t.b; }
+        t.b += g_b;
+    };
+    auto load_patch = [&](const TileC& t, float (&v)[16]) {
+        const int py = t.py, b = t.b;
+        const int px = t.xt * 128 + tid;
         const float* xb = x + (size_t)b * H * W;
         const int iy0 = 2 * py - pad, ix0 = 2 * px - pad;
         if (iy0 >= 0 && iy0 + 3 < H && ix0 >= 0 && ix0 + 3 < W) {
@@ -214,11 +223,9 @@ conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_
             umma_commit_if(leader, &bar);
         }
     };
-    auto epilogue = [&](int tile) {
-        const int xt = tile % xtiles;
-        const int py = (tile / xtiles) % Hp;
-        const int b = tile / (xtiles * Hp);
-        const int px = xt * 128 + tid;
+    auto epilogue = [&](const TileC& t) {
+        const int py = t.py, b = t.b;
+        const int px = t.xt * 128 + tid;
         // ---- epilogue: pool (3 max), LeakyReLU once, fp16 C8-planar store
 #pragma unroll 1
         for (int c0 = 0; c0 < COUT; c0 += 16) {
@@ -272,14 +279,16 @@ conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_
             }
         }
     };
-    const int G = gridDim.x;
     float patch[16];
     int tile = blockIdx.x;
+    TileC cur{tile / (xtiles * Hp), (tile / xtiles) % Hp, tile % xtiles};
+    TileC nxt = cur;                                 // coordinates of the tile whose inputs `patch` holds
     if (tile < n_tiles) {
-        load_patch(tile, patch);
+        load_patch(cur, patch);
         build(0, patch);
         fence_proxy_async();
-        if (tile + G < n_tiles) load_patch(tile + G, patch);
+        advance(nxt);
+        if (tile + G < n_tiles) load_patch(nxt, patch);
         __syncthreads();
         issue(0);
     }
@@ -288,12 +297,14 @@ conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_
         if (next < n_tiles) {
             build((it + 1) & 1, patch);             // overlaps the MMAs of this tile
             fence_proxy_async();
-            if (next + G < n_tiles) load_patch(next + G, patch);     // inputs of tile t+2
+            advance(nxt);
+            if (next + G < n_tiles) load_patch(nxt, patch);          // inputs of tile t+2
         }
         mbar_wait(&bar, phase);
         phase ^= 1;
         tc_fence_after();
-        epilogue(tile);
+        epilogue(cur);
+        advance(cur);
         tc_fence_before();
         __syncthreads();                            // next image fully built; TMEM drained
         if (next < n_tiles) issue((it + 1) & 1);
