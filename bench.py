@@ -290,8 +290,22 @@ def run_ours(args, rank, world, local_rank):
 
     if rank != 0:
         return
-    # ---- sanity of the result against the oracle on a few images (not timed)
+    # ---- sanity of the result against the oracle on a few images (not timed): a fast wrong answer is not a result
     cls, probs, logits, heat = out
+    check = None
+    if not args.no_check:
+        from oracle import gradcam as ogc
+        k = 4
+        xs = x_host[:k].numpy()
+        cache = ocnn.forward(cfg, params, xs)
+        o_cls = cache.logits.argmax(dim=-1).numpy()
+        cag, _, _ = ocnn.backward(cfg, params, cache, ocnn.top_gradient(cache, o_cls, "logit"), through_input=False)
+        o_heat = ogc.gradcam_tail_nhwc(cache.conv_out[-1].numpy().astype(np.float32), cag[1].numpy().astype(np.float32), INPUT_SHAPE[:2])
+        d_heat = heat[:k].float().cpu().numpy()
+        check = {"images": k, "vs": "float64 oracle (oracle/cnn.py + oracle/gradcam.py)",
+                 "classes_equal": bool(np.array_equal(cls[:k].cpu().numpy(), o_cls)),
+                 "max_logit_err": float(np.abs(logits[:k].cpu().numpy() - cache.logits.numpy()).max()),
+                 "heat_err_per_image": [float(v) for v in np.abs(d_heat - o_heat).reshape(k, -1).max(axis=1)]}
     pk = peaks()
     fl = algorithmic_flops_per_image()
     step_ms = ms_total / args.steps
@@ -359,6 +373,7 @@ def run_ours(args, rank, world, local_rank):
         "roofline_tail": tail_roof,
         "kernels": kernels,
         "cpu_baseline": cpu,
+        "check": check,
         "tensor_path": bool(eng.uses_tensor_path),
     }
     emit(out_json)
@@ -397,6 +412,7 @@ def main():
     ap.add_argument("--cpu-images", type=int, default=96, help="bounded CPU-baseline sample")
     ap.add_argument("--ref-images", type=int, default=64, help="images per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="skip the (untimed) oracle check of the first images")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
