@@ -23,17 +23,27 @@ def short(name):
 
 
 def main():
-    tag, launches, reps = sys.argv[1], sys.argv[2], sys.argv[3:]
+    args = sys.argv[1:]
+    first = None
+    if args[0] == "--first":
+        first = int(args[1]); args = args[2:]
+    tag, launches, reps = args[0], args[1], args[2:]
     root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'profiles')
     # ---- launch list
     lines = [l for l in open(launches) if l.startswith('"')]
     agg = collections.OrderedDict()
+    n = 0
     for row in csv.DictReader(io.StringIO(''.join(lines))):
         if row.get('Metric Name') == 'gpu__time_duration.sum':
+            if first is not None and n >= first:
+                break
+            n += 1
             agg.setdefault(short(row['Kernel Name']), []).append(float(row['Metric Value'].replace(',', '')))
     tot = sum(sum(v) for v in agg.values())
     out = [f"# ncu launch list ({os.path.basename(launches)}): gpu__time_duration.sum per kernel\n\n",
-           "Cold-cache, serialised launches under ncu: compare SHARES with bench.py's `kernels[].share`, not absolutes.\n\n",
+           "Cold-cache, serialised launches under ncu: compare SHARES with bench.py's `kernels[].share`, not absolutes.\n",
+           (f"Only the first {first} launches = the device-resident batch-512 steps (warm-up + timed); the rest of the CSV are the "
+            "64-image chunk launches of the host-buffer (e2e) pipeline, whose proportions differ.\n\n" if first else "\n"),
            "| kernel | launches | avg us | share of all profiled time |\n|---|---|---|---|\n"]
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         out.append(f"| {k} | {len(v)} | {sum(v) / len(v) / 1e3:.1f} | {sum(v) / tot:.3f} |\n")
