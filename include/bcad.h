@@ -160,6 +160,25 @@ BCAD_API int bcad_conv_block(const float* x_dev, int B, int H, int W, int Cin, c
 /* non-overlapping mean pool, floor dims (Classes/ImageSegmentation.py:145-163): [B,H,W,C] -> [B,H/pool,W/pool,C] */
 BCAD_API int bcad_avg_pool(const float* x_dev, int B, int H, int W, int C, int pool, float* out_dev, void* stream);
 
+/* ---- training step (BASELINE config 5): fp32 path, keep_all_activations=1 ------------------------ */
+/* Flat gradient vector: per conv block [W packed (k*k,Cin,CoutPad) | b (CoutPad)], then per dense layer [W (out,in) | b (out)]
+ * -- the layouts the device weights live in, so the optimiser and an all-reduce can treat it as one opaque fp32 buffer. */
+BCAD_API int64_t bcad_grad_elems(bcad_model* m);
+BCAD_API int bcad_grad_layout(bcad_model* m, int is_dense, int index, int64_t* w_off, int64_t* w_elems, int64_t* b_off,
+                     int64_t* b_elems);
+/* Gradients of the MEAN softmax cross-entropy over the B images of the preceding bcad_predict(x, B) w.r.t. every weight and
+ * bias (_compute_sample_grads summed and divided by n: Classes/CNNModel.py:282-355, 459-464; nn.CrossEntropyLoss
+ * ADCNNM.py:89).  labels_dev: int32 [B]; grads_dev: fp32 [bcad_grad_elems]; loss_dev: fp32 [B] per-sample loss or NULL. */
+BCAD_API int bcad_train_backward(bcad_model* m, const float* x_dev, const int32_t* labels_dev, int B, float* grads_dev,
+                        float* loss_dev, void* stream);
+/* opt 0: w -= lr * clip(g), per-tensor L2-norm clipping at max_norm (Classes/CNNModel.py:217-222, 372-394; 0 = no clip);
+ * opt 1: Adam(lr, b1, b2, eps) as torch.optim.Adam (ADCNNM.py:88).  grads_dev usually comes back from an all-reduce. */
+BCAD_API int bcad_apply_update(bcad_model* m, const float* grads_dev, int opt, float lr, float max_norm, float b1, float b2,
+                      float eps, void* stream);
+/* current weights in the caller's layouts: filters (F,k,k,C) + bias; dense (units,in) in cfg.flatten_order + bias (HOST) */
+BCAD_API int bcad_get_conv_weights(bcad_model* m, int conv_idx, float* filters_fkkc_host, float* bias_host);
+BCAD_API int bcad_get_dense_weights(bcad_model* m, int dense_idx, float* w_units_in_host, float* bias_host);
+
 /* ---- introspection ---------------------------------------------------------------------------- */
 /* kernels launched by this handle since creation (bench.py reports the delta as gpu_launches) */
 BCAD_API int64_t bcad_launch_count(bcad_model* m);

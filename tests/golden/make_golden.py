@@ -113,6 +113,58 @@ def torch_case(name, input_shape, conv_layers, hidden, batch, seed, alpha=0.01):
     print("wrote", name, "classes", out["pred_class"])
 
 
+def train_case(name, input_shape, conv_layers, hidden, seed, n=3, lr=0.05):
+    """Reference _compute_sample_grads over n samples, averaged as train() does (:438-464), then _apply_grads (:372-394)."""
+    ref = ref_loader.load_numpy_cnn()
+    rng = np.random.default_rng(seed)
+    np.random.seed(seed)
+    with ref_loader.silenced():
+        m = ref.CNNModel(input_shape, 2, conv_layers=conv_layers, hidden_units=hidden, dropout_rate=0.0, leaky_alpha=0.01)
+    for layer in m.layers:
+        if "biases" in layer:
+            layer["biases"] = rng.normal(0, 0.1, layer["biases"].shape)
+    X = rng.standard_normal((n,) + tuple(input_shape)) * 3.0        # large inputs => some gradient norms exceed the clip
+    labels = rng.integers(0, 2, n)
+    out = {"X": X, "labels": labels, "lr": lr, "input_shape": np.array(input_shape), "conv_layers": np.array(conv_layers),
+           "hidden": np.array(hidden)}
+    for i, layer in enumerate(m.layers):
+        if layer["type"] == "conv":
+            out[f"W{i}"], out[f"b{i}"] = layer["filters"].copy(), layer["biases"].copy()
+        elif layer["type"] in ("dense", "output"):
+            out[f"W{i}"], out[f"b{i}"] = layer["weights"].copy(), layer["biases"].copy()
+    acc = [None] * len(m.layers)
+    losses = []
+    for x, y in zip(X, labels):
+        onehot = np.eye(2)[y]
+        with ref_loader.silenced():
+            probs = m.forward(x, training=True)              # dropout_rate = 0: no randomness
+            losses.append(m.cross_entropy(probs, onehot))
+            sg = m._compute_sample_grads(onehot)
+        for idx, g in enumerate(sg):
+            if g is None:
+                continue
+            if acc[idx] is None:
+                acc[idx] = {k: np.zeros_like(v) for k, v in g.items()}
+            for k in g:
+                acc[idx][k] += g[k]
+    for idx, g in enumerate(acc):
+        if g is None:
+            continue
+        for k in g:
+            g[k] = g[k] / float(n)
+            out[f"grad{idx}_{k}"] = g[k]
+    with ref_loader.silenced():
+        m._apply_grads(acc, lr)
+    for i, layer in enumerate(m.layers):
+        if layer["type"] == "conv":
+            out[f"newW{i}"], out[f"newb{i}"] = layer["filters"], layer["biases"]
+        elif layer["type"] in ("dense", "output"):
+            out[f"newW{i}"], out[f"newb{i}"] = layer["weights"], layer["biases"]
+    out["losses"] = np.array(losses)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote", name, "losses", losses)
+
+
 def unet_case(name, shape, batch, seed):
     """Classes/unet.py functions (exec-loaded without the script part and its missing imports)."""
     import types
@@ -165,6 +217,7 @@ if __name__ == "__main__":
     numpy_case("ref_numpy_k5", (15, 14, 2), [(3, 5), (4, 3)], [5], seed=14)
     torch_case("ref_torch_small", (16, 16, 1), [(4, 3), (8, 3)], [12, 6], batch=3, seed=21)
     torch_case("ref_torch_odd", (13, 18, 3), [(5, 3), (6, 3)], [9], batch=2, seed=22, alpha=0.2)
+    train_case("ref_numpy_train", (12, 12, 2), [(3, 3), (4, 3)], [6, 5], seed=41)
     unet_case("ref_unet_small", (16, 16, 1), 2, seed=31)
     unet_case("ref_unet_odd", (21, 18, 2), 1, seed=32)
     cv2_cases()

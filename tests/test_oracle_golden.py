@@ -186,3 +186,23 @@ def test_unet_oracle_matches_reference_fixture(name, c):
     bn = ou.tiny_unet(g["x"], ks)
     np.testing.assert_allclose(bn, g["bn"], rtol=1e-12, atol=1e-9)
     np.testing.assert_allclose(ou.average_pool(bn, 3), g["avg3"], rtol=1e-12, atol=1e-9)
+
+
+def test_training_oracle_matches_reference_fixture():
+    """oracle.train (mean gradients, SGD + per-tensor clip) vs the reference's _compute_sample_grads / _apply_grads."""
+    from oracle import train as otr
+    g = np.load(os.path.join(GOLDEN, "ref_numpy_train.npz"))
+    cfg = ocnn.NetConfig.numpy_flavour((12, 12, 2), 2, [(3, 3), (4, 3)], [6, 5], 0.01)
+    p = ocnn.Params([g["W0"], g["W2"]], [g["b0"], g["b2"]], [g["W4"], g["W5"], g["W6"]], [g["b4"], g["b5"], g["b6"]])
+    gr, loss = otr.mean_grads(cfg, p, g["X"], g["labels"])
+    np.testing.assert_allclose(loss, g["losses"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(gr["conv_w"][0], g["grad0_dF"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(gr["conv_w"][1], g["grad2_dF"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(gr["conv_b"][1], g["grad2_db_conv"], rtol=0, atol=1e-12)
+    for j, li in enumerate((4, 5, 6)):
+        np.testing.assert_allclose(gr["dense_w"][j], g[f"grad{li}_dW"], rtol=0, atol=1e-12)
+    assert max(np.linalg.norm(x) for x in gr["conv_w"] + gr["dense_w"]) > 5.0          # the clip branch is exercised
+    newp = otr.sgd_clip_step(p, gr, float(g["lr"]))
+    np.testing.assert_allclose(newp.conv_w[1], g["newW2"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(newp.dense_w[0], g["newW4"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(newp.dense_b[2], g["newb6"], rtol=0, atol=1e-12)

@@ -55,3 +55,27 @@ def test_world2_sharded_equals_single(tmp_path, n):
     want = _per_image_fn(x)
     assert torch.equal(got["full"], want)
     assert float(got["tmax"]) == 2.0
+
+
+def _ar_worker(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from bcad_b200.training import allreduce_mean_
+    torch.manual_seed(rank)
+    g = torch.randn(1000)
+    mine = g.clone()
+    allreduce_mean_(g, slice(100, 900))                  # fc1-weight bucket first, then the two small ones
+    gathered = [torch.zeros(1000) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    if rank == 0:
+        torch.save({"avg": g, "want": sum(gathered) / world}, out_path)
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_mean_world2(tmp_path):
+    """The training step's only collective: bucketed all-reduce + /world == mean of the ranks' gradient vectors."""
+    out = str(tmp_path / "ar.pt")
+    mp.spawn(_ar_worker, args=(2, 29500 + (os.getpid() % 2000) + 17, out), nprocs=2, join=True)
+    got = torch.load(out)
+    assert torch.allclose(got["avg"], got["want"], atol=1e-6)

@@ -11,6 +11,8 @@ Modules mirror the reference files they stand in for:
 ``explainability``     WebApplicationPrototype/explainability.py
 ``GRADCAM``            WebApplicationPrototype/GRADCAM.py
 ``ExplainableAI``      Classes/ExplainableAI.py
+``unet``               Classes/unet.py layer functions (tiny U-Net encoder front)
+``training``           data-parallel training step (wgrad kernels + one gradient all-reduce)
 ``engine``             batched / sharded driver over the libbcad C-ABI (include/bcad.h)
 =====================  ===========================================================
 

@@ -24,18 +24,6 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) {
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-        else prev = -1;
-    }
-    ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
-
 int Model::alloc(void** p, size_t bytes) {
     if (bytes == 0) bytes = 16;
     cudaError_t e = cudaMalloc(p, bytes);

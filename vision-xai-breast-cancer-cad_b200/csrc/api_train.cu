@@ -1,0 +1,257 @@
+// C-ABI of the training step (BASELINE config 5): gradients of the mean softmax cross-entropy over a
+// batch w.r.t. every weight and bias, optimiser updates on the device weights, weight read-back.
+// Reference: Classes/CNNModel.py:282-355 (_compute_sample_grads), :372-394 (_apply_grads), :399-512 (train);
+// ADCNNM.py:86-153 (Adam + CrossEntropyLoss).  fp32 path only; dropout is not applied (train with dropout_rate=0 or
+// accept eval-mode activations).
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "../../include/bcad.h"
+#include "common.cuh"
+#include "kernels.h"
+#include "model.h"
+
+namespace bcad {
+
+#define TR_TRY(expr) do { int _rc = (expr); if (_rc != BCAD_OK) return _rc; } while (0)
+#define TR_LAUNCH(m, name, expr) do { int _rc = (m)->mark(name, s); if (_rc == BCAD_OK) _rc = (expr); if (_rc != BCAD_OK) return _rc; (m)->launches += 1; } while (0)
+
+static int ensure_train_state(Model* m) {
+    TrainState& T = m->train;
+    if (T.ready) return BCAD_OK;
+    size_t off = 0;
+    for (const ConvLayer& L : m->conv) {
+        T.conv_w_off.push_back(off); off += (size_t)L.k * L.k * L.Cin * L.CoutPad;
+        T.conv_b_off.push_back(off); off += (size_t)L.CoutPad;
+    }
+    for (const DenseLayer& D : m->dense) {
+        T.dense_w_off.push_back(off); off += (size_t)D.out * D.in;
+        T.dense_b_off.push_back(off); off += (size_t)D.out;
+    }
+    T.total = off;
+    const int mb = m->cfg.max_batch;
+    int max_out = 1;
+    for (DenseLayer& D : m->dense) {
+        float* p = nullptr;
+        TR_TRY(m->alloc((void**)&p, (size_t)mb * D.out * sizeof(float)));
+        T.dense_dz.push_back(p);
+        max_out = std::max(max_out, D.out);
+    }
+    TR_TRY(m->alloc((void**)&T.hbuf, (size_t)mb * max_out * sizeof(float)));
+    size_t pw = 0, pb = 0;
+    for (const ConvLayer& L : m->conv) {
+        // any B <= max_batch launches at most max(max_ctas, B) CTAs (conv_wgrad_band_rows)
+        const size_t ncta = (size_t)std::max(T.max_ctas, mb);
+        pw = std::max(pw, ncta * (size_t)L.k * L.k * L.Cin * L.CoutPad);
+        pb = std::max(pb, ncta * (size_t)L.CoutPad);
+    }
+    TR_TRY(m->alloc((void**)&T.part_w, pw * sizeof(float)));
+    TR_TRY(m->alloc((void**)&T.part_b, pb * sizeof(float)));
+    TR_TRY(m->alloc((void**)&T.norms, 2 * (m->conv.size() + m->dense.size()) * sizeof(float)));
+    T.ready = true;
+    return BCAD_OK;
+}
+
+}  // namespace bcad
+
+using namespace bcad;
+
+extern "C" {
+
+int64_t bcad_grad_elems(bcad_model* mm) {
+    Model* m = reinterpret_cast<Model*>(mm);
+    if (!m) return -1;
+    int64_t n = 0;
+    for (const ConvLayer& L : m->conv) n += (int64_t)L.k * L.k * L.Cin * L.CoutPad + L.CoutPad;
+    for (const DenseLayer& D : m->dense) n += (int64_t)D.out * D.in + D.out;
+    return n;
+}
+
+int bcad_grad_layout(bcad_model* mm, int is_dense, int index, int64_t* w_off, int64_t* w_elems, int64_t* b_off, int64_t* b_elems) {
+    Model* m = reinterpret_cast<Model*>(mm);
+    BCAD_REQUIRE(m && w_off && w_elems && b_off && b_elems, "grad_layout: null argument");
+    int64_t off = 0;
+    for (size_t i = 0; i < m->conv.size(); ++i) {
+        const ConvLayer& L = m->conv[i];
+        const int64_t we = (int64_t)L.k * L.k * L.Cin * L.CoutPad, be = L.CoutPad;
+        if (!is_dense && (int)i == index) { *w_off = off; *w_elems = we; *b_off = off + we; *b_elems = be; return BCAD_OK; }
+        off += we + be;
+    }
+    for (size_t j = 0; j < m->dense.size(); ++j) {
+        const DenseLayer& D = m->dense[j];
+        const int64_t we = (int64_t)D.out * D.in, be = D.out;
+        if (is_dense && (int)j == index) { *w_off = off; *w_elems = we; *b_off = off + we; *b_elems = be; return BCAD_OK; }
+        off += we + be;
+    }
+    set_error("grad_layout: no such layer (%d,%d)", is_dense, index);
+    return BCAD_ERR_INVALID;
+}
+
+// Gradients of the MEAN cross-entropy over the B images of the preceding bcad_predict (same x, same B, fp32 path,
+// keep_all_activations=1).  grads_dev: fp32 [bcad_grad_elems]; loss_dev: fp32 [B] per-sample losses (may be NULL).
+int bcad_train_backward(bcad_model* mm, const float* x, const int32_t* labels, int B, float* grads, float* loss, void* stream) {
+    Model* m = reinterpret_cast<Model*>(mm);
+    BCAD_REQUIRE(m && x && labels && grads, "train_backward: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (m->tensor_path) { set_error("training runs on the fp32 path: create the model with BCAD_PREC_FP32"); return BCAD_ERR_INVALID; }
+    if (!m->committed || m->cached_B != B) {
+        set_error("train_backward needs the activations of a preceding bcad_predict with the same B=%d (cached %d)", B, m->cached_B);
+        return BCAD_ERR_STATE;
+    }
+    for (size_t i = 0; i < m->conv.size(); ++i)
+        if (m->conv[i].y == nullptr) { set_error("training needs keep_all_activations=1"); return BCAD_ERR_STATE; }
+    DeviceGuard g(m->cfg.device);
+    std::lock_guard<std::mutex> lock(m->mu);
+    TR_TRY(ensure_train_state(m));
+    TrainState& T = m->train;
+    BCAD_CUDA_CHECK(cudaStreamWaitEvent(s, m->call_done, 0));
+    const int nc = m->cfg.num_classes, nd = (int)m->dense.size(), nconv = (int)m->conv.size();
+    float* loss_buf = loss ? loss : T.hbuf;                  // scratch when the caller does not want the losses
+    TR_LAUNCH(m, "ce_loss_topgrad", launch_ce_loss_topgrad(m->probs, labels, loss_buf, T.dense_dz[nd - 1], B, nc, s));
+    // ---- dense layers, last to first
+    for (int j = nd - 1; j >= 0; --j) {
+        DenseLayer& D = m->dense[j];
+        const float* in_j;
+        if (j == 0) in_j = m->conv.back().p;
+        else {
+            TR_LAUNCH(m, "leaky_from_z", launch_leaky_from_z(m->dense[j - 1].z, T.hbuf, m->cfg.alpha_dense, (int64_t)B * m->dense[j - 1].out, s));
+            in_j = T.hbuf;
+        }
+        TR_LAUNCH(m, "dense_wgrad", launch_sgemm_tn(T.dense_dz[j], in_j, grads + T.dense_w_off[j], D.out, D.in, B, s));
+        TR_LAUNCH(m, "dense_bgrad", launch_colsum(T.dense_dz[j], grads + T.dense_b_off[j], B, D.out, s));
+        float* dst = (j > 0) ? T.dense_dz[j - 1] : m->g_flat;
+        TR_LAUNCH(m, "dense_dgrad", launch_sgemm(T.dense_dz[j], D.d_w, dst, B, D.in, D.out, false, 1, s));
+        if (j > 0) TR_LAUNCH(m, "leaky_mask_mul", launch_leaky_mask_mul(dst, m->dense[j - 1].z, m->cfg.alpha_dense, (int64_t)B * m->dense[j - 1].out, s));
+    }
+    // ---- conv blocks, last to first
+    const float* gp = m->g_flat;
+    for (int i = nconv - 1; i >= 0; --i) {
+        ConvLayer& L = m->conv[i];
+        const size_t elems = (size_t)B * L.Ho * L.Wo * L.Cout;
+        if (L.dz == nullptr) TR_TRY(m->alloc((void**)&L.dz, (size_t)m->cfg.max_batch * L.Ho * L.Wo * L.Cout * sizeof(float)));
+        TR_LAUNCH(m, "unpool", launch_unpool(gp, L.y, L.dz, B, L.Ho, L.Wo, L.Cout, m->cfg.pool_ties, s));
+        TR_LAUNCH(m, "leaky_mask_mul", launch_leaky_mask_mul(L.dz, L.y, m->cfg.alpha_conv, (int64_t)elems, s));
+        const float* in_i = (i == 0) ? x : m->conv[i - 1].p;
+        const int rows = conv_wgrad_band_rows(B, L.Ho, T.max_ctas);
+        TR_LAUNCH(m, "conv_wgrad", launch_conv_wgrad(L.dz, in_i, T.part_w, T.part_b, grads + T.conv_w_off[i], grads + T.conv_b_off[i], B, L.H, L.W,
+                                                    L.Cin, L.Cout, L.CoutPad, L.k, m->cfg.pad, L.Ho, L.Wo, rows, s));
+        m->launches += 2;                                    // the two partial reductions
+        if (i > 0) {
+            ConvLayer& P = m->conv[i - 1];
+            if (P.gp == nullptr) TR_TRY(m->alloc((void**)&P.gp, (size_t)m->cfg.max_batch * P.Hp * P.Wp * P.Cout * sizeof(float)));
+            ConvArgs a;
+            a.x = L.dz; a.w = L.d_w_dgrad; a.bias = L.d_zero_bias; a.y = P.gp; a.p = nullptr;
+            a.B = B; a.H = L.Ho; a.W = L.Wo; a.Cin = L.Cout; a.Cout = L.Cin; a.CoutPad = cdiv(L.Cin, 32) * 32;
+            a.ksize = L.k; a.pad = L.k - 1 - m->cfg.pad; a.Ho = L.H; a.Wo = L.W; a.Hp = 0; a.Wp = 0; a.alpha = 1.f;
+            TR_LAUNCH(m, "conv_dgrad", launch_conv_fp32(a, s));
+            gp = P.gp;
+        }
+    }
+    BCAD_CUDA_CHECK(cudaEventRecord(m->call_done, s));
+    return BCAD_OK;
+}
+
+// optimiser step on the device weights.  opt: 0 = SGD with per-tensor L2-norm clipping at max_norm (0 = no clipping)
+// (Classes/CNNModel.py:372-394), 1 = Adam (b1, b2, eps; torch.optim.Adam, ADCNNM.py:88).
+int bcad_apply_update(bcad_model* mm, const float* grads, int opt, float lr, float max_norm, float b1, float b2, float eps, void* stream) {
+    Model* m = reinterpret_cast<Model*>(mm);
+    BCAD_REQUIRE(m && grads, "apply_update: null argument");
+    BCAD_REQUIRE(opt == 0 || opt == 1, "apply_update: opt must be 0 (SGD+clip) or 1 (Adam)");
+    if (m->tensor_path) { set_error("training runs on the fp32 path"); return BCAD_ERR_INVALID; }
+    if (!m->committed) { set_error("weights not committed"); return BCAD_ERR_STATE; }
+    cudaStream_t s = (cudaStream_t)stream;
+    DeviceGuard g(m->cfg.device);
+    std::lock_guard<std::mutex> lock(m->mu);
+    TR_TRY(ensure_train_state(m));
+    TrainState& T = m->train;
+    BCAD_CUDA_CHECK(cudaStreamWaitEvent(s, m->call_done, 0));
+    if (opt == 1 && T.adam_m == nullptr) {
+        TR_TRY(m->alloc((void**)&T.adam_m, T.total * sizeof(float)));
+        TR_TRY(m->alloc((void**)&T.adam_v, T.total * sizeof(float)));
+        BCAD_CUDA_CHECK(cudaMemsetAsync(T.adam_m, 0, T.total * sizeof(float), s));
+        BCAD_CUDA_CHECK(cudaMemsetAsync(T.adam_v, 0, T.total * sizeof(float), s));
+    }
+    if (opt == 1) ++T.adam_step;
+    int tix = 0;
+    auto step = [&](float* w, size_t off, size_t n) -> int {
+        if (opt == 0) {
+            TR_LAUNCH(m, "l2norm", launch_l2norm(grads + off, n, T.norms + tix, s));
+            TR_LAUNCH(m, "sgd_clip_update", launch_sgd_clip_update(w, grads + off, T.norms + tix, lr, max_norm, n, s));
+        } else {
+            TR_LAUNCH(m, "adam_update", launch_adam_update(w, grads + off, T.adam_m + off, T.adam_v + off, lr, b1, b2, eps, T.adam_step, n, s));
+        }
+        ++tix;
+        return BCAD_OK;
+    };
+    for (size_t i = 0; i < m->conv.size(); ++i) {
+        ConvLayer& L = m->conv[i];
+        TR_TRY(step(L.d_w, T.conv_w_off[i], (size_t)L.k * L.k * L.Cin * L.CoutPad));
+        TR_TRY(step(L.d_b, T.conv_b_off[i], (size_t)L.CoutPad));
+        TR_LAUNCH(m, "repack_dgrad", launch_repack_dgrad(L.d_w, L.d_w_dgrad, L.k, L.Cin, L.Cout, L.CoutPad, cdiv(L.Cin, 32) * 32, s));
+    }
+    for (size_t j = 0; j < m->dense.size(); ++j) {
+        DenseLayer& D = m->dense[j];
+        TR_TRY(step(D.d_w, T.dense_w_off[j], (size_t)D.out * D.in));
+        TR_TRY(step(D.d_b, T.dense_b_off[j], (size_t)D.out));
+    }
+    m->cached_B = 0;                                         // cached activations no longer match the weights
+    BCAD_CUDA_CHECK(cudaEventRecord(m->call_done, s));
+    return BCAD_OK;
+}
+
+// weights back in the caller's layouts (save_model Classes/CNNModel.py:530-555; state_dict ADCNNM.py:150)
+int bcad_get_conv_weights(bcad_model* mm, int i, float* filters_fkkc, float* bias) {
+    Model* m = reinterpret_cast<Model*>(mm);
+    BCAD_REQUIRE(m && filters_fkkc, "get_conv_weights: null argument");
+    BCAD_REQUIRE(i >= 0 && i < (int)m->conv.size(), "conv index %d out of range", i);
+    if (!m->committed) { set_error("weights not committed"); return BCAD_ERR_STATE; }
+    DeviceGuard g(m->cfg.device);
+    ConvLayer& L = m->conv[i];
+    BCAD_CUDA_CHECK(cudaDeviceSynchronize());
+    std::vector<float> pk((size_t)L.k * L.k * L.Cin * L.CoutPad), pb(L.CoutPad);
+    BCAD_CUDA_CHECK(cudaMemcpy(pk.data(), L.d_w, pk.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    BCAD_CUDA_CHECK(cudaMemcpy(pb.data(), L.d_b, pb.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int f = 0; f < L.Cout; ++f) {
+        if (bias) bias[f] = pb[f];
+        L.h_b[f] = pb[f];
+        for (int t = 0; t < L.k * L.k; ++t)
+            for (int c = 0; c < L.Cin; ++c) {
+                const float v = pk[((size_t)t * L.Cin + c) * L.CoutPad + f];
+                filters_fkkc[((size_t)f * L.k * L.k + t) * L.Cin + c] = v;
+                L.h_w[((size_t)f * L.k * L.k + t) * L.Cin + c] = v;
+            }
+    }
+    return BCAD_OK;
+}
+
+int bcad_get_dense_weights(bcad_model* mm, int j, float* w, float* bias) {
+    Model* m = reinterpret_cast<Model*>(mm);
+    BCAD_REQUIRE(m && w, "get_dense_weights: null argument");
+    BCAD_REQUIRE(j >= 0 && j < (int)m->dense.size(), "dense index %d out of range", j);
+    if (!m->committed) { set_error("weights not committed"); return BCAD_ERR_STATE; }
+    DeviceGuard g(m->cfg.device);
+    DenseLayer& D = m->dense[j];
+    if (D.d_w == nullptr) { set_error("dense %d has no fp32 device weights (tensor path)", j); return BCAD_ERR_STATE; }
+    BCAD_CUDA_CHECK(cudaDeviceSynchronize());
+    BCAD_CUDA_CHECK(cudaMemcpy(D.h_w.data(), D.d_w, D.h_w.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    BCAD_CUDA_CHECK(cudaMemcpy(D.h_b.data(), D.d_b, D.h_b.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    if (bias) memcpy(bias, D.h_b.data(), D.h_b.size() * sizeof(float));
+    if (j == 0 && m->cfg.flatten_order == BCAD_FLATTEN_CHW) {
+        const ConvLayer& L = m->conv.back();
+        const int C = L.Cout, H = L.Hp, W = L.Wp;
+        for (int u = 0; u < D.out; ++u) {
+            const float* src = D.h_w.data() + (size_t)u * D.in;
+            float* dst = w + (size_t)u * D.in;
+            for (int c = 0; c < C; ++c)
+                for (int y = 0; y < H; ++y)
+                    for (int x = 0; x < W; ++x) dst[((size_t)c * H + y) * W + x] = src[((size_t)y * W + x) * C + c];
+        }
+    } else {
+        memcpy(w, D.h_w.data(), D.h_w.size() * sizeof(float));
+    }
+    return BCAD_OK;
+}
+
+}  // extern "C"

@@ -56,6 +56,20 @@ int launch_pad_conv_weights(const float* w, float* out, int taps, int Cin, int C
 int launch_overlay(const float* img01, const float* cam, int B, int H, int W, uint8_t* overlay_rgb,
                    uint8_t* heat_u8, cudaStream_t s);
 
+// ---------------------------------------------------------------- training step (kernels_train.cu)
+int launch_ce_loss_topgrad(const float* probs, const int32_t* labels, float* loss, float* dz, int B, int nc, cudaStream_t s);
+int launch_leaky_from_z(const float* z, float* h, float alpha, int64_t n, cudaStream_t s);
+int launch_sgemm_tn(const float* A, const float* Bm, float* C, int M, int N, int K, cudaStream_t s);
+int launch_colsum(const float* A, float* out, int K, int N, cudaStream_t s);
+int conv_wgrad_band_rows(int B, int Ho, int max_ctas);
+int launch_conv_wgrad(const float* dz, const float* in, float* part_w, float* part_b, float* dw, float* db, int B, int H, int W,
+                      int Cin, int Cout, int CoutPad, int k, int pad, int Ho, int Wo, int band_rows, cudaStream_t s);
+int launch_repack_dgrad(const float* w, float* dk, int k, int Cin, int Cout, int CoutPad, int CinPad, cudaStream_t s);
+int launch_l2norm(const float* g, size_t n, float* out, cudaStream_t s);
+int launch_sgd_clip_update(float* w, const float* g, const float* norm, float lr, float max_norm, size_t n, cudaStream_t s);
+int launch_adam_update(float* w, const float* g, float* m1, float* m2, float lr, float b1, float b2, float eps, int step, size_t n,
+                       cudaStream_t s);
+
 // fused dense head: fc1 split-K reduce -> remaining dense layers -> probs/class -> (explain) backward to dz1 + alpha
 struct HeadArgs {
     int n_dense;                  // dense layers incl. the output layer; layer 0 comes as split-K partials

@@ -10,6 +10,18 @@
 
 namespace bcad {
 
+struct DeviceGuard {                   // make the handle's device current for the duration of a call
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 struct ConvLayer {
     int Cin = 0, Cout = 0, CoutPad = 0, k = 0;
     int H = 0, W = 0, Ho = 0, Wo = 0, Hp = 0, Wp = 0;
@@ -50,6 +62,21 @@ struct Xfer {                          // host-buffer pipeline (bcad_predict_exp
     size_t h_small_bytes = 0;
 };
 
+struct TrainState {                     // row f4: buffers of the training step (allocated on first use)
+    bool ready = false;
+    std::vector<size_t> conv_w_off, conv_b_off, dense_w_off, dense_b_off;   // offsets into the flat gradient vector
+    size_t total = 0;
+    std::vector<float*> dense_dz;       // dz of every dense layer [max_batch][out]
+    float* hbuf = nullptr;              // LeakyReLU(z) of the layer feeding the current wgrad
+    float* part_w = nullptr;            // conv wgrad per-CTA partials
+    float* part_b = nullptr;
+    float* norms = nullptr;             // one L2 norm per tensor
+    float* adam_m = nullptr;
+    float* adam_v = nullptr;
+    int adam_step = 0;
+    int max_ctas = 2048;
+};
+
 struct TensorPath;                     // tensor_path.cu
 
 struct Model {
@@ -79,6 +106,7 @@ struct Model {
     std::vector<const char*> prof_names;
     int prof_n = 0;
     Xfer xfer;
+    TrainState train;
     TensorPath* tp = nullptr;
 
     int alloc(void** p, size_t bytes);

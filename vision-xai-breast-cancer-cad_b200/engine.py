@@ -247,6 +247,79 @@ class Engine:
             _lib.check(self.lib.bcad_get_tensor(self._h, kind, index, B, _ptr(out), self._stream()))
         return out
 
+    # ------------------------------------------------------------------ training step
+    def grad_elems(self) -> int:
+        return int(self.lib.bcad_grad_elems(self._h))
+
+    def grad_layout(self, is_dense: bool, index: int):
+        vals = [C.c_int64() for _ in range(4)]
+        _lib.check(self.lib.bcad_grad_layout(self._h, 1 if is_dense else 0, index, *[C.byref(v) for v in vals]))
+        return tuple(int(v.value) for v in vals)          # (w_off, w_elems, b_off, b_elems)
+
+    def train_backward(self, x: torch.Tensor, labels, grads: Optional[torch.Tensor] = None):
+        """After ``predict(x)`` of the same batch (fp32 engine, keep_all_activations=True):
+        -> (flat gradient of the MEAN cross-entropy [grad_elems], per-sample loss [B]) as CUDA tensors."""
+        x = self._as_device_input(x)
+        B = x.shape[0]
+        lab = torch.as_tensor(labels, dtype=torch.int32).reshape(-1).to(self.tdev).contiguous()
+        if lab.numel() != B:
+            raise ValueError("one label per image")
+        with torch.cuda.device(self.tdev):
+            if grads is None:
+                grads = torch.empty((self.grad_elems(),), device=self.tdev, dtype=torch.float32)
+            loss = torch.empty((B,), device=self.tdev, dtype=torch.float32)
+            _lib.check(self.lib.bcad_train_backward(self._h, _ptr(x), _ptr(lab), B, _ptr(grads), _ptr(loss), self._stream()))
+        return grads, loss
+
+    def apply_update(self, grads: torch.Tensor, opt: str = "sgd_clip", lr: float = 0.01, max_norm: float = 5.0,
+                     betas=(0.9, 0.999), eps: float = 1e-8):
+        """opt "sgd_clip": Classes/CNNModel.py:372-394; opt "adam": torch.optim.Adam as ADCNNM.py:88."""
+        code = {"sgd_clip": 0, "sgd": 0, "adam": 1}[opt]
+        with torch.cuda.device(self.tdev):
+            _lib.check(self.lib.bcad_apply_update(self._h, _ptr(grads), code, float(lr), float(max_norm if opt != "sgd" else 0.0),
+                                                  float(betas[0]), float(betas[1]), float(eps), self._stream()))
+
+    def get_weights(self):
+        """Current device weights in the reference layouts: ([F,k,k,C]), ([F]), ([units,in] fc1 in spec.flatten order), ([units])."""
+        conv_w, conv_b, dense_w, dense_b = [], [], [], []
+        cin = self.spec.input_shape[2]
+        for i, (f, k) in enumerate(self.spec.conv_layers):
+            w, b = np.empty((f, k, k, cin), np.float32), np.empty((f,), np.float32)
+            _lib.check(self.lib.bcad_get_conv_weights(self._h, i, _ptr(w), _ptr(b)))
+            conv_w.append(w); conv_b.append(b)
+            cin = f
+        _, prev = self.spec.shapes()
+        for j, u in enumerate(list(self.spec.hidden_units) + [self.spec.num_classes]):
+            w, b = np.empty((u, prev), np.float32), np.empty((u,), np.float32)
+            _lib.check(self.lib.bcad_get_dense_weights(self._h, j, _ptr(w), _ptr(b)))
+            dense_w.append(w); dense_b.append(b)
+            prev = u
+        return conv_w, conv_b, dense_w, dense_b
+
+    def unpack_grads(self, grads: torch.Tensor):
+        """Flat device-layout gradient -> reference layouts (dict like oracle.train.mean_grads)."""
+        g = grads.detach().cpu().numpy()
+        out = {"conv_w": [], "conv_b": [], "dense_w": [], "dense_b": []}
+        cin = self.spec.input_shape[2]
+        shapes, prev = self.spec.shapes()
+        for i, (f, k) in enumerate(self.spec.conv_layers):
+            wo, we, bo, be = self.grad_layout(False, i)
+            cpad = be
+            pk = g[wo:wo + we].reshape(k * k, cin, cpad)[:, :, :f]                      # [tap][c][f]
+            out["conv_w"].append(np.ascontiguousarray(pk.transpose(2, 0, 1)).reshape(f, k, k, cin))
+            out["conv_b"].append(g[bo:bo + f].copy())
+            cin = f
+        ph, pw, pc = shapes[-1][1]
+        for j, u in enumerate(list(self.spec.hidden_units) + [self.spec.num_classes]):
+            wo, we, bo, be = self.grad_layout(True, j)
+            w = g[wo:wo + we].reshape(u, prev)
+            if j == 0 and self.spec.flatten == "chw":                                   # device order is (h,w,c)
+                w = w.reshape(u, ph, pw, pc).transpose(0, 3, 1, 2).reshape(u, -1)
+            out["dense_w"].append(np.ascontiguousarray(w))
+            out["dense_b"].append(g[bo:bo + be].copy())
+            prev = u
+        return out
+
     # ------------------------------------------------------------------ hot path, host buffers (end to end)
     def predict_explain_host(self, x: np.ndarray, class_idx: Optional[np.ndarray] = None, grad_mode: str = "logit",
                              heat_out: Optional[np.ndarray] = None, want_heat: bool = True):
