@@ -162,7 +162,8 @@ BCAD_API int bcad_avg_pool(const float* x_dev, int B, int H, int W, int C, int p
 
 /* ---- training step (BASELINE config 5): fp32 path, keep_all_activations=1 ------------------------ */
 /* Flat gradient vector: per conv block [W packed (k*k,Cin,CoutPad) | b (CoutPad)], then per dense layer [W (out,in) | b (out)]
- * -- the layouts the device weights live in, so the optimiser and an all-reduce can treat it as one opaque fp32 buffer. */
+ * -- the layouts the device weights live in, every tensor starting on a 128-byte boundary (bcad_grad_layout gives the
+ * offsets; the gaps are never read), so the optimiser and an all-reduce can treat it as one opaque fp32 buffer. */
 BCAD_API int64_t bcad_grad_elems(bcad_model* m);
 BCAD_API int bcad_grad_layout(bcad_model* m, int is_dense, int index, int64_t* w_off, int64_t* w_elems, int64_t* b_off,
                      int64_t* b_elems);
@@ -171,6 +172,13 @@ BCAD_API int bcad_grad_layout(bcad_model* m, int is_dense, int index, int64_t* w
  * ADCNNM.py:89).  labels_dev: int32 [B]; grads_dev: fp32 [bcad_grad_elems]; loss_dev: fp32 [B] per-sample loss or NULL. */
 BCAD_API int bcad_train_backward(bcad_model* m, const float* x_dev, const int32_t* labels_dev, int B, float* grads_dev,
                         float* loss_dev, void* stream);
+/* Dropout multipliers for the next forwards of exactly B images (B <= max_batch): masks[b][sum of hidden units] (host or
+ * device pointer), hidden layers in order, each value 0 or 1/(1-rate) -- Classes/CNNModel.py:186-188, nn.Dropout of
+ * ADCNNM.py:62.  The caller draws them.  NULL or B = 0 switches dropout off.  bcad_train_backward feeds the dropped
+ * activations to the weight gradients; mask_backward = 1 also masks the back-propagated gradient (autograd, ADCNNM.py),
+ * 0 leaves it unmasked as the NumPy reference's backward does (Classes/CNNModel.py:307-316). */
+BCAD_API int bcad_set_dropout_masks(bcad_model* m, const float* masks, int B, int mask_backward, void* stream);
+
 /* opt 0: w -= lr * clip(g), per-tensor L2-norm clipping at max_norm (Classes/CNNModel.py:217-222, 372-394; 0 = no clip);
  * opt 1: Adam(lr, b1, b2, eps) as torch.optim.Adam (ADCNNM.py:88).  grads_dev usually comes back from an all-reduce. */
 BCAD_API int bcad_apply_update(bcad_model* m, const float* grads_dev, int opt, float lr, float max_norm, float b1, float b2,

@@ -188,6 +188,7 @@ class Cache:
     z: List[torch.Tensor] = field(default_factory=list)          # pre-activations, last = logits
     logits: Optional[torch.Tensor] = None
     probs: Optional[torch.Tensor] = None
+    dropout: Optional[list] = None                               # per hidden layer [B,units] multipliers (training)
 
 
 def _pool_with_switches(y_nchw: torch.Tensor, ties: str):
@@ -207,8 +208,11 @@ def _pool_with_switches(y_nchw: torch.Tensor, ties: str):
     return p, sw
 
 
-def forward(cfg: NetConfig, params: Params, x, dtype=torch.float64) -> Cache:
-    """Batched forward with the reference's caches (Classes/CNNModel.py:162-198)."""
+def forward(cfg: NetConfig, params: Params, x, dtype=torch.float64, dropout=None) -> Cache:
+    """Batched forward with the reference's caches (Classes/CNNModel.py:162-198).
+
+    dropout: training mode only -- one [B,units] multiplier array (0 or 1/(1-rate)) per hidden dense layer, applied after
+    the activation (Classes/CNNModel.py:186-188 / nn.Dropout)."""
     x = torch.as_tensor(np.asarray(x)).to(dtype)
     if x.dim() == 3:
         x = x[None]
@@ -231,6 +235,9 @@ def forward(cfg: NetConfig, params: Params, x, dtype=torch.float64) -> Cache:
         z = flat @ torch.as_tensor(w).to(dtype).T + torch.as_tensor(b).to(dtype)
         cache.z.append(z)
         flat = _leaky(z, cfg.alpha_dense) if j < n_dense - 1 else z
+        if dropout is not None and j < n_dense - 1:
+            flat = flat * torch.as_tensor(dropout[j]).to(dtype)
+    cache.dropout = dropout
     cache.logits = cache.z[-1]
     cache.probs = softmax_clip(cache.logits) if cfg.head == "softmax" else torch.softmax(cache.logits, dim=-1)
     return cache
@@ -260,7 +267,7 @@ def top_gradient(cache: Cache, class_idx, mode: str) -> torch.Tensor:
 
 
 def backward(cfg: NetConfig, params: Params, cache: Cache, d_top: torch.Tensor,
-             through_input: bool = True, want_wgrads: bool = False):
+             through_input: bool = True, want_wgrads: bool = False, dropout_in_backward: bool = True):
     """explainability.py:13-68 batched.
 
     Returns (conv_act_grads {conv_block: [B,h,w,F]}, d_input [B,H,W,C] or None, wgrads or None).
@@ -274,6 +281,10 @@ def backward(cfg: NetConfig, params: Params, cache: Cache, d_top: torch.Tensor,
     for j in reversed(range(n_dense)):
         w = torch.as_tensor(params.dense_w[j]).to(dtype)
         if j < n_dense - 1:
+            # autograd masks the gradient with the dropout multipliers; the NumPy reference's _compute_sample_grads does
+            # NOT (Classes/CNNModel.py:307-316 uses d_out as is) -- dropout_in_backward=False restates that
+            if cache.dropout is not None and dropout_in_backward:
+                d = d * torch.as_tensor(cache.dropout[j]).to(dtype)
             d = d * _dleaky(cache.z[j], cfg.alpha_dense)                            # :28-29
         if want_wgrads:
             wgrads["dense"][j] = (d[:, :, None] * cache.dense_in[j][:, None, :], d.clone())   # per-sample outer

@@ -13,12 +13,16 @@ import torch
 from . import cnn as ocnn
 
 
-def mean_grads(cfg, params, x, labels):
-    """{'conv_w': [(F,k,k,C)], 'conv_b': [(F,)], 'dense_w': [(out,in)], 'dense_b': [(out,)]}, loss per sample."""
-    cache = ocnn.forward(cfg, params, x)
+def mean_grads(cfg, params, x, labels, dropout=None, dropout_in_backward=True):
+    """{'conv_w': [(F,k,k,C)], 'conv_b': [(F,)], 'dense_w': [(out,in)], 'dense_b': [(out,)]}, loss per sample.
+
+    dropout: per hidden layer [B,units] multipliers; dropout_in_backward=False is the NumPy reference (its backward ignores
+    the mask, Classes/CNNModel.py:307-316), True is autograd (ADCNNM.py)."""
+    cache = ocnn.forward(cfg, params, x, dropout=dropout)
     labels = np.asarray(labels)
     d_top = ocnn.top_gradient(cache, labels, "softmax_ce")
-    _, _, wg = ocnn.backward(cfg, params, cache, d_top, through_input=True, want_wgrads=True)
+    _, _, wg = ocnn.backward(cfg, params, cache, d_top, through_input=True, want_wgrads=True,
+                              dropout_in_backward=dropout_in_backward)
     out = {"conv_w": [w[0].mean(dim=0).numpy() for w in wg["conv"]], "conv_b": [w[1].mean(dim=0).numpy() for w in wg["conv"]],
            "dense_w": [w[0].mean(dim=0).numpy() for w in wg["dense"]], "dense_b": [w[1].mean(dim=0).numpy() for w in wg["dense"]]}
     p = cache.probs.numpy()

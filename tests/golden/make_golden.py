@@ -113,13 +113,13 @@ def torch_case(name, input_shape, conv_layers, hidden, batch, seed, alpha=0.01):
     print("wrote", name, "classes", out["pred_class"])
 
 
-def train_case(name, input_shape, conv_layers, hidden, seed, n=3, lr=0.05):
+def train_case(name, input_shape, conv_layers, hidden, seed, n=3, lr=0.05, dropout_rate=0.0):
     """Reference _compute_sample_grads over n samples, averaged as train() does (:438-464), then _apply_grads (:372-394)."""
     ref = ref_loader.load_numpy_cnn()
     rng = np.random.default_rng(seed)
     np.random.seed(seed)
     with ref_loader.silenced():
-        m = ref.CNNModel(input_shape, 2, conv_layers=conv_layers, hidden_units=hidden, dropout_rate=0.0, leaky_alpha=0.01)
+        m = ref.CNNModel(input_shape, 2, conv_layers=conv_layers, hidden_units=hidden, dropout_rate=dropout_rate, leaky_alpha=0.01)
     for layer in m.layers:
         if "biases" in layer:
             layer["biases"] = rng.normal(0, 0.1, layer["biases"].shape)
@@ -134,10 +134,17 @@ def train_case(name, input_shape, conv_layers, hidden, seed, n=3, lr=0.05):
             out[f"W{i}"], out[f"b{i}"] = layer["weights"].copy(), layer["biases"].copy()
     acc = [None] * len(m.layers)
     losses = []
-    for x, y in zip(X, labels):
+    masks = []
+    for si, (x, y) in enumerate(zip(X, labels)):
         onehot = np.eye(2)[y]
+        if dropout_rate > 0.0:
+            # the reference draws np.random.rand(units) per hidden layer, in order (:186-188): replay the stream to record
+            # the multipliers it is about to use
+            np.random.seed(seed * 100 + si)
+            masks.append(np.concatenate([(np.random.rand(u) > dropout_rate).astype(np.float32) / (1.0 - dropout_rate) for u in hidden]))
+            np.random.seed(seed * 100 + si)
         with ref_loader.silenced():
-            probs = m.forward(x, training=True)              # dropout_rate = 0: no randomness
+            probs = m.forward(x, training=True)
             losses.append(m.cross_entropy(probs, onehot))
             sg = m._compute_sample_grads(onehot)
         for idx, g in enumerate(sg):
@@ -161,6 +168,9 @@ def train_case(name, input_shape, conv_layers, hidden, seed, n=3, lr=0.05):
         elif layer["type"] in ("dense", "output"):
             out[f"newW{i}"], out[f"newb{i}"] = layer["weights"], layer["biases"]
     out["losses"] = np.array(losses)
+    if masks:
+        out["dropout_masks"] = np.stack(masks)
+        out["dropout_rate"] = dropout_rate
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     print("wrote", name, "losses", losses)
 
@@ -218,6 +228,7 @@ if __name__ == "__main__":
     torch_case("ref_torch_small", (16, 16, 1), [(4, 3), (8, 3)], [12, 6], batch=3, seed=21)
     torch_case("ref_torch_odd", (13, 18, 3), [(5, 3), (6, 3)], [9], batch=2, seed=22, alpha=0.2)
     train_case("ref_numpy_train", (12, 12, 2), [(3, 3), (4, 3)], [6, 5], seed=41)
+    train_case("ref_numpy_train_dropout", (12, 12, 2), [(3, 3), (4, 3)], [8, 6], seed=42, n=4, dropout_rate=0.4)
     unet_case("ref_unet_small", (16, 16, 1), 2, seed=31)
     unet_case("ref_unet_odd", (21, 18, 2), 1, seed=32)
     cv2_cases()

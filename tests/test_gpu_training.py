@@ -108,3 +108,123 @@ def test_data_parallel_equals_full_batch():
     avg = (halves[0] + halves[1]) / 2
     assert float((avg - g_full).abs().max()) <= 1e-6 * max(1.0, float(g_full.abs().max()))
     full.close()
+
+
+def test_dropout_masks_numpy_reference_semantics():
+    """Reference forward(training=True) with dropout 0.4 + _compute_sample_grads (whose backward ignores the mask)."""
+    g = np.load(os.path.join(GOLDEN, "ref_numpy_train_dropout.npz"))
+    cfg = ocnn.NetConfig.numpy_flavour((12, 12, 2), 2, [(3, 3), (4, 3)], [8, 6], 0.01)
+    p = ocnn.Params([g["W0"], g["W2"]], [g["b0"], g["b2"]], [g["W4"], g["W5"], g["W6"]], [g["b4"], g["b5"], g["b6"]])
+    eng = engine_from(cfg, p, max_batch=4, keep_all_activations=True)
+    x = torch.from_numpy(g["X"].astype(np.float32)).cuda()
+    eng.set_dropout_masks(g["dropout_masks"], mask_backward=False)
+    eng.predict(x)
+    grads, loss = eng.train_backward(x, g["labels"])
+    _cmp(loss.cpu().numpy(), g["losses"], 1e-5, "loss")
+    u = eng.unpack_grads(grads)
+    _cmp(u["conv_w"][0], g["grad0_dF"], 1e-5, "dF0")
+    _cmp(u["conv_w"][1], g["grad2_dF"], 1e-5, "dF2")
+    for j, li in enumerate((4, 5, 6)):
+        _cmp(u["dense_w"][j], g[f"grad{li}_dW"], 1e-5, f"dW{li}")
+        _cmp(u["dense_b"][j], g[f"grad{li}_db"], 1e-5, f"db{li}")
+    # a forward of another batch size must refuse the stale masks; clearing them restores inference
+    with pytest.raises(RuntimeError):
+        eng.predict(x[:2])
+    eng.set_dropout_masks(None)
+    _, probs, _ = eng.predict(x)
+    _cmp(probs.cpu().numpy(), ocnn.forward(cfg, p, g["X"]).probs.numpy(), 1e-5, "inference after clearing")
+    eng.close()
+
+
+def test_dropout_masks_autograd_semantics():
+    from oracle import train as otr
+    cfg = ocnn.NetConfig.torch_flavour((16, 20, 1), 2, [(4, 3), (8, 3)], [12, 10], 0.01)
+    p = ocnn.init_params(cfg, seed=5, bias_std=0.05)
+    x = ocnn.synth_images(6, (16, 20, 1), seed=6)
+    labels = np.array([0, 1, 0, 1, 1, 0])
+    rng = np.random.default_rng(0)
+    mk = (rng.random((6, 22)) >= 0.3).astype(np.float32) / 0.7
+    eng = engine_from(cfg, p, max_batch=6, keep_all_activations=True)
+    eng.set_dropout_masks(mk, mask_backward=True)
+    xd = torch.from_numpy(x).cuda()
+    eng.predict(xd)
+    grads, loss = eng.train_backward(xd, labels)
+    want, wloss = otr.mean_grads(cfg, p, x, labels, dropout=[mk[:, :12], mk[:, 12:]], dropout_in_backward=True)
+    u = eng.unpack_grads(grads)
+    for k in ("conv_w", "conv_b", "dense_w", "dense_b"):
+        for a, b in zip(u[k], want[k]):
+            _cmp(a, b, 1e-4, k)
+    _cmp(loss.cpu().numpy(), wloss, 1e-5, "loss")
+    eng.close()
+
+
+def _toy_dataset(n, shape, seed):
+    """Two classes told apart by which half of the image is bright."""
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n,) + shape).astype(np.float32) * 0.3
+    y = rng.integers(0, 2, n)
+    for i in range(n):
+        if y[i]:
+            X[i, : shape[0] // 2] += 1.5
+        else:
+            X[i, shape[0] // 2:] += 1.5
+    return X, y
+
+
+def test_numpy_mirror_train_batch_matches_oracle_and_train_learns(capsys):
+    from bcad_b200.CNNModel import CNNModel
+    from oracle import train as otr
+    shape = (16, 16, 1)
+    X, y = _toy_dataset(24, shape, 1)
+    Y = np.eye(2)[y]
+    np.random.seed(7)
+    m = CNNModel(shape, 2, conv_layers=[(4, 3), (6, 3)], hidden_units=[10, 8], dropout_rate=0.25, max_batch=8)
+    cfg = ocnn.NetConfig.numpy_flavour(shape, 2, [(4, 3), (6, 3)], [10, 8], 0.01)
+    p0 = ocnn.Params([l["filters"].copy() for l in m._conv_layers()], [l["biases"].copy() for l in m._conv_layers()],
+                     [l["weights"].copy() for l in m._dense_layers()], [l["biases"].copy() for l in m._dense_layers()])
+    # one batch: the mirror draws the dropout multipliers from np.random in the reference's order
+    np.random.seed(99)
+    mk = np.stack([np.concatenate([(np.random.rand(u) > 0.25).astype(np.float32) / 0.75 for u in (10, 8)]) for _ in range(8)])
+    np.random.seed(99)
+    loss_sum = m.train_batch(X[:8], Y[:8], lr=0.05)
+    want, wloss = otr.mean_grads(cfg, p0, X[:8], y[:8], dropout=[mk[:, :10], mk[:, 10:]], dropout_in_backward=False)
+    p1 = otr.sgd_clip_step(p0, want, 0.05)
+    assert abs(loss_sum - wloss.sum()) < 1e-4 * max(1.0, wloss.sum())
+    m._pull_weights()
+    for l, w in zip(m._conv_layers(), p1.conv_w):
+        _cmp(l["filters"], w, 1e-5, "filters after one batch")
+    for l, w in zip(m._dense_layers(), p1.dense_w):
+        _cmp(l["weights"], w, 1e-5, "weights after one batch")
+    # the whole loop: learns the toy problem, restores the best weights, keeps layers[] in sync with the device
+    m.train(X, Y, X, Y, epochs=12, lr=0.05, batch_size=8)
+    out = capsys.readouterr().out
+    assert "[TRAIN] Best accuracy" in out
+    acc = m.get_training_metrics(X, Y, verbose=False)
+    assert acc >= 0.9 and abs(acc - max(m.epoch_accuracy)) < 1e-9
+    cw, _, dw, _ = m.engine.get_weights()
+    _cmp(cw[0], m._conv_layers()[0]["filters"], 1e-6, "layers[] == device")
+    _cmp(dw[0], m._dense_layers()[0]["weights"], 1e-6, "layers[] == device")
+
+
+def test_torch_mirror_train_model(tmp_path):
+    from bcad_b200 import ADCNNM as A
+    shape = (16, 16, 1)
+    X, y = _toy_dataset(32, shape, 2)
+    Xt, yt = torch.from_numpy(X), torch.from_numpy(y).long()
+    loader = [(Xt[i:i + 8], yt[i:i + 8]) for i in range(0, 32, 8)]
+    torch.manual_seed(0)
+    m = A.CNNModel(shape, 2, conv_layers=[(4, 3), (8, 3)], hidden_units=[16, 8], dropout_rate=0.2)
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    path = str(tmp_path / "best.pth")
+    hist, best = A.train_model(m, loader, loader, epochs=15, lr=5e-3, save_path=path)
+    assert len(hist) == 15 and hist[-1]["loss"] < hist[0]["loss"] and best >= 0.9
+    after = m.state_dict()
+    assert any(not torch.equal(before[k], after[k]) for k in before)          # parameters came back from the device
+    m.eval()
+    lg = m(Xt)                                                                # uses the trained device weights
+    assert float((lg.argmax(1).cpu() == yt).float().mean()) >= 0.9
+    saved = torch.load(path)
+    assert set(saved) == set(after)
+    m2 = A.CNNModel(shape, 2, conv_layers=[(4, 3), (8, 3)], hidden_units=[16, 8], dropout_rate=0.2).eval()
+    m2.load_state_dict(saved)
+    assert float((m2(Xt).argmax(1).cpu() == yt).float().mean()) >= 0.9

@@ -5,7 +5,8 @@
 ``forward(x[B,H,W,C]) -> logits`` (ADCNNM.py:72-78) and ``load_trained_model`` (ADCNNM.py:155-202).
 The modules only HOLD the parameters; ``forward`` runs in libbcad (Conv2d(padding=1) + leaky_relu(0.01) +
 MaxPool2d(2), CHW flatten handled by permuting fc1's columns at load time, Linear + LeakyReLU(alpha)).
-Inference only: the returned logits carry no autograd graph (training is SURVEY 8 row f4).
+``forward`` returns logits without an autograd graph; training goes through ``train_model`` (forward, backward and
+Adam all on the device).
 """
 from __future__ import annotations
 
@@ -69,7 +70,8 @@ class CNNModel(nn.Module):
     # ------------------------------------------------------------------ forward (ADCNNM.py:72-78)
     def forward(self, x):
         if self.training and any(isinstance(m, nn.Dropout) and m.p > 0 for m in self.fc):
-            raise NotImplementedError("train-mode forward (dropout, autograd) is SURVEY 8 row f4; call .eval() first")
+            raise NotImplementedError("train-mode forward (dropout, autograd graph) is not offered: train with train_model(), "
+                                      "or call .eval() first")
         cls, probs, logits = self.engine.predict(x)
         return logits.to(x.device) if isinstance(x, torch.Tensor) else logits
 
@@ -85,8 +87,82 @@ class CNNModel(nn.Module):
         return cls.long(), logits, heat
 
 
-def train_model(*a, **k):
-    raise NotImplementedError("train_model (ADCNNM.py:86-153) is SURVEY 8 row f4, not part of this hot path")
+def _pull_into_modules(model):
+    """Device weights -> the nn.Parameters (state_dict layout), without triggering a re-upload."""
+    cw, cb, dw, db = model._engine.get_weights()
+    lin = [m for m in model.fc if isinstance(m, nn.Linear)]
+    with torch.no_grad():
+        for c, w, b in zip(model.convs, cw, cb):
+            c.weight.copy_(torch.from_numpy(np.ascontiguousarray(w.transpose(0, 3, 1, 2))))
+            c.bias.copy_(torch.from_numpy(b))
+        for l, w, b in zip(lin, dw, db):
+            l.weight.copy_(torch.from_numpy(w))
+            l.bias.copy_(torch.from_numpy(b))
+    model._versions = model._param_versions()
+
+
+def train_model(model, train_loader, test_loader, epochs=10, lr=0.001, device="cuda",
+                save_path="trained_model/cnn_model_Advanced.pth"):
+    """ADCNNM.py:86-153 on the device: Adam(lr) on the mean cross-entropy, nn.Dropout after every hidden layer, validation
+    accuracy per epoch, best state_dict saved to ``save_path`` -> (history, best_val_acc).
+
+    Forward, backward and the Adam update all run in libbcad; under an initialised torch.distributed group each rank
+    feeds its own loader shard and the flat gradient is averaged with one bucketed all-reduce per step."""
+    import os
+
+    from .training import DataParallelTrainer
+    first = next(iter(train_loader))[0]
+    bs = int(first.shape[0])
+    eng = model._engine
+    if eng is None or eng.uses_tensor_path or not eng.keep_all_activations or eng.max_batch < bs:
+        if eng is not None:
+            eng.close()
+        model._engine = Engine(model._spec, precision="fp32", max_batch=max(bs, model._max_batch), keep_all_activations=True,
+                               device=model._device_index)
+        model._versions = None
+    eng = model.sync_weights(force=False)
+    trainer = DataParallelTrainer(eng, opt="adam", lr=lr)
+    rates = [m.p for m in model.fc if isinstance(m, nn.Dropout)]
+    units = list(model._spec.hidden_units)
+    best_val_acc, history = 0.0, []
+    for epoch in range(epochs):
+        model.train()
+        total_loss, correct, total = 0.0, 0, 0
+        for X, y in train_loader:
+            n = int(X.shape[0])
+            if any(r > 0 for r in rates):
+                mk = torch.cat([(torch.rand(n, u, device=eng.tdev) >= r).float() / (1.0 - r) for u, r in zip(units, rates)], dim=1)
+                eng.set_dropout_masks(mk, mask_backward=True)
+            try:
+                loss = trainer.step(X, y)
+                cls = trainer.last_classes
+            finally:
+                eng.set_dropout_masks(None)
+            total_loss += float(loss.mean())
+            correct += int((cls.cpu() == torch.as_tensor(y).cpu().int()).sum())
+            total += n
+        train_acc = correct / max(1, total)
+        avg_loss = total_loss / max(1, len(train_loader))
+        print(f"[EPOCH {epoch+1}] Loss={avg_loss:.4f}, Acc={train_acc:.4f}")
+        model.eval()
+        val_correct, val_total = 0, 0
+        for X, y in test_loader:
+            cls, _, _ = eng.predict(X)
+            val_correct += int((cls.cpu() == torch.as_tensor(y).cpu().int()).sum())
+            val_total += int(X.shape[0])
+        val_acc = val_correct / max(1, val_total)
+        print(f"[VAL] Acc={val_acc:.4f}")
+        history.append({"epoch": epoch + 1, "loss": avg_loss, "val_acc": val_acc})
+        if val_acc > best_val_acc:
+            best_val_acc = val_acc
+            _pull_into_modules(model)
+            d = os.path.dirname(save_path)
+            if d:
+                os.makedirs(d, exist_ok=True)
+            torch.save(model.state_dict(), save_path)
+            print(f" Saved best model at epoch {epoch+1} with val_acc={val_acc:.4f}")
+    _pull_into_modules(model)
+    return history, best_val_acc
 
 
 def load_trained_model(json_path, weight_path, **engine_kw):

@@ -148,11 +148,11 @@ class CNNModel:
         """Classes/CNNModel.py:162-198 (single sample (H,W,C) -> probs (num_classes,) float64).
 
         Caches ``layer['input'|'output'|'switches'|'z']`` like the reference (fetched lazily from the device).
-        Training-mode dropout (:186-188) belongs to the training step, which is outside this hot path."""
+        Training-mode dropout (:186-188) is applied inside ``train_batch`` (masks drawn from np.random in the reference's order)."""
         if training and self.dropout_rate > 0.0:
             raise NotImplementedError(
-                "forward(training=True) with dropout is the training step (SURVEY 8 f4), not built here; "
-                "call forward(x, training=False) / predict(x)")
+                "forward(training=True) with dropout is part of the device training step: use train() / train_batch(); "
+                "for inference call forward(x, training=False) / predict(x)")
         x = np.asarray(x)
         eng = self.engine
         cls, probs, logits = eng.predict(x[None].astype(np.float32))
@@ -246,5 +246,110 @@ class CNNModel:
         np.savez(path, config=json.dumps(config), **weights)
         print(f"[INFO] Model saved to {path}")
 
-    def train(self, *a, **k):
-        raise NotImplementedError("training (Classes/CNNModel.py:399-512) is SURVEY 8 row f4, not part of this hot path")
+    # ------------------------------------------------------------------ training (Classes/CNNModel.py:399-512)
+    def _training_engine(self, batch_size):
+        """The handle the training step runs on: fp32, every activation kept, max_batch >= batch_size."""
+        eng = self._engine
+        if eng is None or eng.uses_tensor_path or not eng.keep_all_activations or eng.max_batch < batch_size:
+            if eng is not None:
+                eng.close()
+            self._engine, self._precision, self._keep_all = None, "fp32", True
+            self._max_batch = max(self._max_batch, int(batch_size))
+        return self.sync_weights(force=False)
+
+    def _pull_weights(self):
+        """Device weights -> ``layers[*]`` (float64 arrays like the reference's), without triggering a re-upload."""
+        cw, cb, dw, db = self._engine.get_weights()
+        for l, w, b in zip(self._conv_layers(), cw, cb):
+            l["filters"], l["biases"] = w.astype(np.float64), b.astype(np.float64)
+        for l, w, b in zip(self._dense_layers(), dw, db):
+            l["weights"], l["biases"] = w.astype(np.float64), b.astype(np.float64)
+        convs, denses = self._conv_layers(), self._dense_layers()
+        self._weights_key = tuple(id(dict.__getitem__(l, k)) for l in convs for k in ("filters", "biases")) + \
+            tuple(id(dict.__getitem__(l, k)) for l in denses for k in ("weights", "biases"))
+
+    def _draw_dropout(self, n_samples):
+        """The multipliers the reference would draw for n samples: np.random.rand(units) per hidden layer, sample by
+        sample (Classes/CNNModel.py:186-188) -- same global stream, same order."""
+        rows = []
+        for _ in range(n_samples):
+            rows.append(np.concatenate([(np.random.rand(u) > self.dropout_rate).astype(np.float32) / (1.0 - self.dropout_rate)
+                                        for u in self.hidden_units]))
+        return np.stack(rows)
+
+    def train_batch(self, X_batch, y_batch, lr):
+        """One mini-batch of ``train``: averaged gradients (:438-464) + ``_apply_grads`` (:372-394) on the device.
+        Under an initialised torch.distributed group the gradients are averaged over the ranks first.  -> summed loss."""
+        from .training import allreduce_mean_
+        X_batch = np.asarray(X_batch, dtype=np.float32)
+        y_batch = np.asarray(y_batch)
+        labels = y_batch.argmax(axis=1) if y_batch.ndim == 2 else y_batch
+        eng = self._training_engine(len(X_batch))
+        drop = self.dropout_rate > 0.0 and len(self.hidden_units) > 0
+        if drop:
+            eng.set_dropout_masks(self._draw_dropout(len(X_batch)), mask_backward=False)
+        try:
+            eng.predict(X_batch)
+            grads, loss = eng.train_backward(X_batch, labels)
+        finally:
+            if drop:
+                eng.set_dropout_masks(None)
+        allreduce_mean_(grads)
+        eng.apply_update(grads, "sgd_clip", lr=lr, max_norm=5.0)
+        return float(loss.sum())
+
+    def train(self, X, y_onehot, X_test, y_test, epochs=10, lr=0.01, batch_size=8, eval_every_batch=True):
+        """Same loop as the reference: shuffle per epoch (np.random), one clipped-SGD update per mini-batch of averaged
+        gradients, test accuracy after every batch, lr *= 0.98 per epoch, best-accuracy weights restored at the end.
+        ``y_onehot`` one-hot rows (the reference's cross_entropy / probs - y_true)."""
+        X, y_onehot = np.asarray(X), np.asarray(y_onehot)
+        dataset_size = len(X)
+        best_acc, best_weights = 0.0, None
+        print("[Training Params] :")
+        print("       Learning Rate:", lr)
+        print("       Drop Out Rate:", self.dropout_rate)
+        print("       Num Epochs:", epochs)
+        print("       Batch size:", batch_size)
+        self._training_engine(batch_size)
+        for epoch in range(epochs):
+            indices = np.arange(dataset_size)
+            np.random.shuffle(indices)
+            X_shuf, y_shuf = X[indices], y_onehot[indices]
+            accuracy, total_loss = 0, 0.0
+            for i in range(0, dataset_size, batch_size):
+                xb, yb = X_shuf[i:i + batch_size], y_shuf[i:i + batch_size]
+                batch_loss = self.train_batch(xb, yb, lr)
+                total_loss += batch_loss
+                if eval_every_batch or i + batch_size >= dataset_size:
+                    accuracy = self.get_training_metrics(X_test, y_test, verbose=False)
+                print(f"[EPOCH {epoch+1}/{epochs}, BATCH {i//batch_size+1}] BatchLoss={batch_loss/ max(1, len(xb)):.4f}  Accuracy={accuracy}")
+            self._pull_weights()
+            print(f"\n[EPOCH {epoch+1}] Loss={total_loss / dataset_size:.4f}, Acc={accuracy:.4f}")
+            self.epoch_accuracy.append(accuracy)
+            if accuracy > best_acc:
+                best_acc = accuracy
+                best_weights = [{k: np.copy(dict.__getitem__(l, k)) for k in ("weights", "biases", "filters") if k in l}
+                                for l in self.layers]
+            lr *= 0.98
+        print(f"[TRAIN] Best accuracy: {best_acc:.4f}")
+        if best_weights is not None:
+            for layer, saved in zip(self.layers, best_weights):
+                for key in saved:
+                    layer[key] = saved[key]
+            self.sync_weights(force=True)
+
+    def get_training_metrics(self, X_test, Y_test, verbose=True):
+        """Accuracy of ``predict`` over a test set (Classes/CNNModel.py:560-585; the reference reads undefined globals for
+        the labels -- here they come from ``Y_test``: one-hot rows or integer labels)."""
+        Y_test = np.asarray(Y_test)
+        y_true = Y_test.argmax(axis=1) if Y_test.ndim == 2 else Y_test
+        y_pred, _ = self.predict_batch(np.asarray(X_test, dtype=np.float32))
+        y_pred = np.asarray(y_pred)
+        acc = float((y_pred == y_true).mean())
+        if verbose:
+            print(f"\n[Test Accuracy] {acc:.4f}")
+            cm = np.zeros((self.num_classes, self.num_classes), dtype=np.int64)
+            np.add.at(cm, (y_true, y_pred), 1)
+            print("\nConfusion Matrix:")
+            print(cm)
+        return acc

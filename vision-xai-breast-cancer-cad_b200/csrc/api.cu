@@ -388,13 +388,19 @@ static int forward_chunk_fp32(Model* m, const float* x, int n, bool explain, con
     DenseLayer& D0 = m->dense[0];
     const int splits0 = std::min(D0.splits, sgemm_pick_splits(n, D0.out, D0.in));
     BCAD_LAUNCH(m, "fc1_sgemm", launch_sgemm(in, D0.d_w, m->partials, n, D0.out, D0.in, true, splits0, s));
-    if (m->fused_head) {
+    const float* drop = m->train.drop_B ? m->train.drop : nullptr;   // training forward: dropout after every hidden layer
+    if (drop && m->train.drop_B != n) {
+        set_error("dropout masks are set for a batch of %d, this forward has %d images (clear them with bcad_set_dropout_masks(m, NULL, 0))", m->train.drop_B, n);
+        return BCAD_ERR_STATE;
+    }
+    if (m->fused_head && !drop) {
         BCAD_TRY(launch_fused_head(m, n, m->partials, splits0, (size_t)n * D0.out, explain, class_idx, grad_mode,
                                    explain ? D0.h : nullptr, nullptr, 0, nullptr, s));
         return BCAD_OK;
     }
     const bool only = (m->dense.size() == 1);
     BCAD_LAUNCH(m, "splitk_reduce", launch_splitk_reduce(m->partials, splits0, D0.d_b, D0.z, only ? nullptr : D0.h, m->cfg.alpha_dense, n, D0.out, s));
+    if (drop && !only) BCAD_LAUNCH(m, "dropout", launch_mul_mask(D0.h, drop + m->train.drop_off[0], n, D0.out, m->train.drop_ld, s));
     in = D0.h;
     for (size_t j = 1; j < m->dense.size(); ++j) {
         DenseLayer& D = m->dense[j];
@@ -402,6 +408,7 @@ static int forward_chunk_fp32(Model* m, const float* x, int n, bool explain, con
         const int splits = std::min(D.splits, sgemm_pick_splits(n, D.out, D.in));
         BCAD_LAUNCH(m, "sgemm", launch_sgemm(in, D.d_w, m->partials, n, D.out, D.in, true, splits, s));
         BCAD_LAUNCH(m, "splitk_reduce", launch_splitk_reduce(m->partials, splits, D.d_b, D.z, last ? nullptr : D.h, m->cfg.alpha_dense, n, D.out, s));
+        if (drop && !last) BCAD_LAUNCH(m, "dropout", launch_mul_mask(D.h, drop + m->train.drop_off[j], n, D.out, m->train.drop_ld, s));
         in = D.h;
     }
     BCAD_LAUNCH(m, "head", launch_head(m->dense.back().z, m->probs, m->cls, n, m->cfg.num_classes, m->cfg.head, s));
@@ -459,6 +466,7 @@ static int run(Model* m, const float* x, int B, const int32_t* class_idx, int gr
     BCAD_REQUIRE(B >= 1, "batch must be >= 1, got %d", B);
     BCAD_REQUIRE(grad_mode == BCAD_GRAD_LOGIT || grad_mode == BCAD_GRAD_SOFTMAX_CE, "bad grad_mode %d", grad_mode);
     BCAD_REQUIRE(!explain || heat, "heatmap output pointer is null");
+    BCAD_REQUIRE(!(explain && m->train.drop_B), "explanations are an inference call: clear the dropout masks first");
     if (!m->committed) { set_error("weights not committed: call bcad_commit first"); return BCAD_ERR_STATE; }
     DeviceGuard g(m->cfg.device);
     std::lock_guard<std::mutex> lock(m->mu);

@@ -18,19 +18,30 @@ namespace bcad {
 #define TR_TRY(expr) do { int _rc = (expr); if (_rc != BCAD_OK) return _rc; } while (0)
 #define TR_LAUNCH(m, name, expr) do { int _rc = (m)->mark(name, s); if (_rc == BCAD_OK) _rc = (expr); if (_rc != BCAD_OK) return _rc; (m)->launches += 1; } while (0)
 
+// the one definition of the flat gradient layout: every tensor starts 128-byte aligned (vector stores in the wgrad kernels)
+struct GradLayout { std::vector<size_t> conv_w, conv_b, dense_w, dense_b; size_t total = 0; };
+static GradLayout grad_layout_of(const Model* m) {
+    GradLayout g;
+    size_t off = 0;
+    auto pad32 = [](size_t n) { return (n + 31) / 32 * 32; };
+    for (const ConvLayer& L : m->conv) {
+        g.conv_w.push_back(off); off += pad32((size_t)L.k * L.k * L.Cin * L.CoutPad);
+        g.conv_b.push_back(off); off += pad32((size_t)L.CoutPad);
+    }
+    for (const DenseLayer& D : m->dense) {
+        g.dense_w.push_back(off); off += pad32((size_t)D.out * D.in);
+        g.dense_b.push_back(off); off += pad32((size_t)D.out);
+    }
+    g.total = off;
+    return g;
+}
+
 static int ensure_train_state(Model* m) {
     TrainState& T = m->train;
     if (T.ready) return BCAD_OK;
-    size_t off = 0;
-    for (const ConvLayer& L : m->conv) {
-        T.conv_w_off.push_back(off); off += (size_t)L.k * L.k * L.Cin * L.CoutPad;
-        T.conv_b_off.push_back(off); off += (size_t)L.CoutPad;
-    }
-    for (const DenseLayer& D : m->dense) {
-        T.dense_w_off.push_back(off); off += (size_t)D.out * D.in;
-        T.dense_b_off.push_back(off); off += (size_t)D.out;
-    }
-    T.total = off;
+    const GradLayout gl = grad_layout_of(m);
+    T.conv_w_off = gl.conv_w; T.conv_b_off = gl.conv_b; T.dense_w_off = gl.dense_w; T.dense_b_off = gl.dense_b;
+    T.total = gl.total;
     const int mb = m->cfg.max_batch;
     int max_out = 1;
     for (DenseLayer& D : m->dense) {
@@ -63,27 +74,24 @@ extern "C" {
 int64_t bcad_grad_elems(bcad_model* mm) {
     Model* m = reinterpret_cast<Model*>(mm);
     if (!m) return -1;
-    int64_t n = 0;
-    for (const ConvLayer& L : m->conv) n += (int64_t)L.k * L.k * L.Cin * L.CoutPad + L.CoutPad;
-    for (const DenseLayer& D : m->dense) n += (int64_t)D.out * D.in + D.out;
-    return n;
+    return (int64_t)grad_layout_of(m).total;
 }
 
 int bcad_grad_layout(bcad_model* mm, int is_dense, int index, int64_t* w_off, int64_t* w_elems, int64_t* b_off, int64_t* b_elems) {
     Model* m = reinterpret_cast<Model*>(mm);
     BCAD_REQUIRE(m && w_off && w_elems && b_off && b_elems, "grad_layout: null argument");
-    int64_t off = 0;
-    for (size_t i = 0; i < m->conv.size(); ++i) {
-        const ConvLayer& L = m->conv[i];
-        const int64_t we = (int64_t)L.k * L.k * L.Cin * L.CoutPad, be = L.CoutPad;
-        if (!is_dense && (int)i == index) { *w_off = off; *w_elems = we; *b_off = off + we; *b_elems = be; return BCAD_OK; }
-        off += we + be;
+    const GradLayout gl = grad_layout_of(m);
+    if (!is_dense && index >= 0 && index < (int)m->conv.size()) {
+        const ConvLayer& L = m->conv[index];
+        *w_off = (int64_t)gl.conv_w[index]; *w_elems = (int64_t)L.k * L.k * L.Cin * L.CoutPad;
+        *b_off = (int64_t)gl.conv_b[index]; *b_elems = L.CoutPad;
+        return BCAD_OK;
     }
-    for (size_t j = 0; j < m->dense.size(); ++j) {
-        const DenseLayer& D = m->dense[j];
-        const int64_t we = (int64_t)D.out * D.in, be = D.out;
-        if (is_dense && (int)j == index) { *w_off = off; *w_elems = we; *b_off = off + we; *b_elems = be; return BCAD_OK; }
-        off += we + be;
+    if (is_dense && index >= 0 && index < (int)m->dense.size()) {
+        const DenseLayer& D = m->dense[index];
+        *w_off = (int64_t)gl.dense_w[index]; *w_elems = (int64_t)D.out * D.in;
+        *b_off = (int64_t)gl.dense_b[index]; *b_elems = D.out;
+        return BCAD_OK;
     }
     set_error("grad_layout: no such layer (%d,%d)", is_dense, index);
     return BCAD_ERR_INVALID;
@@ -117,12 +125,14 @@ int bcad_train_backward(bcad_model* mm, const float* x, const int32_t* labels, i
         if (j == 0) in_j = m->conv.back().p;
         else {
             TR_LAUNCH(m, "leaky_from_z", launch_leaky_from_z(m->dense[j - 1].z, T.hbuf, m->cfg.alpha_dense, (int64_t)B * m->dense[j - 1].out, s));
+            if (T.drop_B) TR_LAUNCH(m, "dropout", launch_mul_mask(T.hbuf, T.drop + T.drop_off[j - 1], B, m->dense[j - 1].out, T.drop_ld, s));
             in_j = T.hbuf;
         }
         TR_LAUNCH(m, "dense_wgrad", launch_sgemm_tn(T.dense_dz[j], in_j, grads + T.dense_w_off[j], D.out, D.in, B, s));
         TR_LAUNCH(m, "dense_bgrad", launch_colsum(T.dense_dz[j], grads + T.dense_b_off[j], B, D.out, s));
         float* dst = (j > 0) ? T.dense_dz[j - 1] : m->g_flat;
         TR_LAUNCH(m, "dense_dgrad", launch_sgemm(T.dense_dz[j], D.d_w, dst, B, D.in, D.out, false, 1, s));
+        if (j > 0 && T.drop_B && T.drop_backward) TR_LAUNCH(m, "dropout", launch_mul_mask(dst, T.drop + T.drop_off[j - 1], B, m->dense[j - 1].out, T.drop_ld, s));
         if (j > 0) TR_LAUNCH(m, "leaky_mask_mul", launch_leaky_mask_mul(dst, m->dense[j - 1].z, m->cfg.alpha_dense, (int64_t)B * m->dense[j - 1].out, s));
     }
     // ---- conv blocks, last to first
@@ -150,6 +160,37 @@ int bcad_train_backward(bcad_model* mm, const float* x, const int32_t* labels, i
         }
     }
     BCAD_CUDA_CHECK(cudaEventRecord(m->call_done, s));
+    return BCAD_OK;
+}
+
+// Dropout multipliers for the NEXT forwards of exactly B images (B <= max_batch): masks[b][sum of hidden units], hidden
+// layers in order, each value 0 or 1/(1-rate) (Classes/CNNModel.py:186-188; nn.Dropout ADCNNM.py:62).  The caller draws them
+// (the NumPy mirror replays np.random in the reference's order).  NULL / B = 0 switches dropout off again.
+// mask_backward: 1 = the gradient is masked too (autograd, ADCNNM.py); 0 = the NumPy reference, whose backward uses d_out as
+// is (Classes/CNNModel.py:307-316).
+int bcad_set_dropout_masks(bcad_model* mm, const float* masks, int B, int mask_backward, void* stream) {
+    Model* m = reinterpret_cast<Model*>(mm);
+    BCAD_REQUIRE(m, "null model");
+    if (m->tensor_path) { set_error("training runs on the fp32 path"); return BCAD_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    DeviceGuard g(m->cfg.device);
+    std::lock_guard<std::mutex> lock(m->mu);
+    TrainState& T = m->train;
+    if (masks == nullptr || B == 0) { T.drop_B = 0; return BCAD_OK; }
+    BCAD_REQUIRE(B >= 1 && B <= m->cfg.max_batch, "dropout masks: B=%d must be within max_batch=%d", B, m->cfg.max_batch);
+    BCAD_REQUIRE(m->dense.size() > 1, "the network has no hidden dense layer to drop");
+    if (T.drop == nullptr) {
+        T.drop_off.clear();
+        T.drop_ld = 0;
+        for (size_t j = 0; j + 1 < m->dense.size(); ++j) { T.drop_off.push_back(T.drop_ld); T.drop_ld += m->dense[j].out; }
+        TR_TRY(m->alloc((void**)&T.drop, (size_t)m->cfg.max_batch * T.drop_ld * sizeof(float)));
+    }
+    BCAD_CUDA_CHECK(cudaStreamWaitEvent(s, m->call_done, 0));
+    BCAD_CUDA_CHECK(cudaMemcpyAsync(T.drop, masks, (size_t)B * T.drop_ld * sizeof(float), cudaMemcpyDefault, s));
+    BCAD_CUDA_CHECK(cudaEventRecord(m->call_done, s));
+    T.drop_B = B;
+    T.drop_backward = (mask_backward != 0);
+    m->cached_B = 0;
     return BCAD_OK;
 }
 

@@ -39,6 +39,22 @@ int launch_leaky_from_z(const float* z, float* h, float alpha, int64_t n, cudaSt
     return BCAD_OK;
 }
 
+// h[b][u] (*)= mask[b][off + u]: dropout multipliers (0 or 1/(1-p)) of one hidden layer, rows of length ld in `mask`
+__global__ void mul_mask_kernel(float* __restrict__ h, const float* __restrict__ mask, int units, int ld, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / units;
+        h[i] *= mask[b * ld + (i - b * units)];
+    }
+}
+
+int launch_mul_mask(float* h, const float* mask, int B, int units, int ld, cudaStream_t s) {
+    const int64_t n = (int64_t)B * units;
+    const int blocks = (int)min((int64_t)148 * 8, (n + 255) / 256);
+    mul_mask_kernel<<<blocks, 256, 0, s>>>(h, mask, units, ld, (size_t)n);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
 // C[M][N] = sum_k A[k][M] * B[k][N]  (dense weight gradient dW = dz^T . input; K = batch)
 __global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
                                                        float* __restrict__ C, int M, int N, int K) {

@@ -74,6 +74,10 @@ struct TrainState {                     // row f4: buffers of the training step 
     float* adam_m = nullptr;
     float* adam_v = nullptr;
     int adam_step = 0;
+    float* drop = nullptr;              // dropout multipliers [max_batch][drop_ld] (bcad_set_dropout_masks), drop_B = 0: off
+    int drop_B = 0, drop_ld = 0;
+    bool drop_backward = true;          // mask the gradient too (autograd); false = the NumPy reference's backward
+    std::vector<int> drop_off;          // column offset of every hidden layer in a mask row
     int max_ctas = 2048;
 };
 

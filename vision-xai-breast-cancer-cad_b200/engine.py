@@ -78,6 +78,7 @@ class Engine:
         self.device = int(device)
         self.precision = precision
         self.max_batch = int(max_batch)
+        self.keep_all_activations = bool(keep_all_activations)
         cfg = _lib.Config()
         cfg.in_h, cfg.in_w, cfg.in_c = spec.input_shape
         cfg.num_classes = spec.num_classes
@@ -266,10 +267,23 @@ class Engine:
             raise ValueError("one label per image")
         with torch.cuda.device(self.tdev):
             if grads is None:
-                grads = torch.empty((self.grad_elems(),), device=self.tdev, dtype=torch.float32)
+                grads = torch.zeros((self.grad_elems(),), device=self.tdev, dtype=torch.float32)   # gaps between tensors stay 0
             loss = torch.empty((B,), device=self.tdev, dtype=torch.float32)
             _lib.check(self.lib.bcad_train_backward(self._h, _ptr(x), _ptr(lab), B, _ptr(grads), _ptr(loss), self._stream()))
         return grads, loss
+
+    def set_dropout_masks(self, masks, mask_backward: bool = True):
+        """masks [B, sum(hidden_units)] multipliers (0 or 1/(1-rate)) for the next forwards of exactly B images; None = off.
+        mask_backward=False restates the NumPy reference, whose backward ignores the mask (Classes/CNNModel.py:307-316)."""
+        if masks is None:
+            _lib.check(self.lib.bcad_set_dropout_masks(self._h, None, 0, 1, self._stream()))
+            return
+        mk = torch.as_tensor(masks, dtype=torch.float32).to(self.tdev).contiguous()
+        if mk.dim() != 2 or mk.shape[1] != sum(self.spec.hidden_units):
+            raise ValueError(f"dropout masks must be [B, {sum(self.spec.hidden_units)}], got {tuple(mk.shape)}")
+        with torch.cuda.device(self.tdev):
+            _lib.check(self.lib.bcad_set_dropout_masks(self._h, _ptr(mk), mk.shape[0], 1 if mask_backward else 0, self._stream()))
+            torch.cuda.current_stream(self.tdev).synchronize()      # mk may be freed on return
 
     def apply_update(self, grads: torch.Tensor, opt: str = "sgd_clip", lr: float = 0.01, max_norm: float = 5.0,
                      betas=(0.9, 0.999), eps: float = 1e-8):

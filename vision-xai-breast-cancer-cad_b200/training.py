@@ -44,12 +44,13 @@ class DataParallelTrainer:
         wo, we, _, _ = engine.grad_layout(True, 0)
         self._big = slice(wo, wo + we)
         self._grads = None
+        self.last_classes = None
 
     def step(self, x: torch.Tensor, labels) -> torch.Tensor:
         """One optimiser step on this rank's shard; returns the per-sample losses of the shard (CUDA tensor)."""
         eng = self.engine
         x = eng._as_device_input(x)
-        eng.predict(x)                                           # forward, activations cached in the handle
+        self.last_classes, _, _ = eng.predict(x)                 # forward, activations cached in the handle
         self._grads, loss = eng.train_backward(x, labels, self._grads)
         allreduce_mean_(self._grads, self._big)
         eng.apply_update(self._grads, self.opt, self.lr, self.max_norm, self.betas, self.eps)
