@@ -393,6 +393,98 @@ def run_ours(args, rank, world, local_rank):
     emit(out_json)
 
 
+def run_train(args, rank, world, local_rank):
+    """Secondary line (SURVEY 8 row f4 / BASELINE config 5): data-parallel training step, images/s.  fp32 forward +
+    backward + weight gradients in libbcad, ONE bucketed NCCL all-reduce of the flat gradient, Adam on the device."""
+    import torch
+    import torch.distributed as dist
+    import bcad_b200
+    from bcad_b200.training import DataParallelTrainer
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ocnn, cfg, params = oracle_setup()
+    B = args.train_batch
+    spec = bcad_b200.NetSpec.torch_flavour(INPUT_SHAPE, NUM_CLASSES, CONV_LAYERS, HIDDEN, 0.01)
+    eng = bcad_b200.Engine(spec, precision="fp32", max_batch=B, keep_all_activations=True, device=local_rank)
+    eng.set_weights(params.conv_w, params.conv_b, params.dense_w, params.dense_b)
+    tr = DataParallelTrainer(eng, opt="adam", lr=1e-4)
+    x_host = torch.from_numpy(ocnn.synth_images(B, INPUT_SHAPE, seed=777 + rank)).pin_memory()
+    y_host = torch.from_numpy((np.arange(B) % 2).astype(np.int32)).pin_memory()
+    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        tr.step(x_dev, y_dev)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        loss = tr.step(x_dev, y_dev)
+    ev1.record()
+    barrier()
+    launches = eng.launch_count - l0
+    ms_total = ev0.elapsed_time(ev1)
+    # end to end: inputs and labels from pinned host memory, the step's mean loss read back (2 untimed steps first: torch
+    # loads its reduction kernel lazily)
+    def step_e2e():
+        loss = tr.step(x_host.to(dev, non_blocking=True), y_host.to(dev, non_blocking=True))
+        return float(loss.mean())
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        mean_loss = step_e2e()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    tt = torch.tensor([ms_total, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(tt[0]), float(tt[1])
+    eng.set_profiling(True)
+    prof = {}
+    eng.predict(x_dev)
+    torch.cuda.synchronize(dev)
+    for i, (name, ms) in enumerate(eng.last_profile()):
+        prof[f"fwd{i:02d}:{name}"] = ms
+    g, _ = eng.train_backward(x_dev, y_dev)
+    torch.cuda.synchronize(dev)
+    for i, (name, ms) in enumerate(eng.last_profile()):
+        prof[f"bwd{i:02d}:{name}"] = ms
+    eng.apply_update(g, "adam", lr=0.0)
+    torch.cuda.synchronize(dev)
+    for i, (name, ms) in enumerate(eng.last_profile()):
+        prof[f"upd{i:02d}:{name}"] = prof.get(f"upd{i:02d}:{name}", 0.0) + ms
+    eng.set_profiling(False)
+    if rank != 0:
+        return
+    tot = max(1e-9, sum(prof.values()))
+    kernels = [{"kernel": k, "ms": round(v, 4), "share": round(v / tot, 4)} for k, v in sorted(prof.items()) if v / tot >= 0.005]
+    grad_bytes = eng.grad_elems() * 4
+    emit({
+        "metric": "training throughput (forward + backward + gradient all-reduce + Adam), images/s", "value": world * B * args.steps / (ms_total * 1e-3),
+        "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"train: ADCNNM-flavour CNN {INPUT_SHAPE} conv{CONV_LAYERS} fc{HIDDEN}, {B} images/GPU/step, Adam, "
+                               f"one {grad_bytes / 1e6:.0f} MB gradient all-reduce per step (secondary line, BASELINE config 5)",
+                   "images_per_gpu": B, "l2": "activations >> 126 MB L2 per step"},
+        "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + B * 4),
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "last_mean_loss": mean_loss},
+        "gpu_launches": int(launches), "clocks": clocks, "kernels": kernels, "grad_bytes": grad_bytes,
+    })
+
+
 _JSON_FD = None
 
 
@@ -425,6 +517,9 @@ def main():
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "fp16", "fp16x3"])
     ap.add_argument("--cpu-images", type=int, default=96, help="bounded CPU-baseline sample")
     ap.add_argument("--ref-images", type=int, default=64, help="images per step of the --impl reference arm")
+    ap.add_argument("--workload", default="explain", choices=["explain", "train"],
+                    help="explain = the headline path (predict + Grad-CAM); train = the secondary training-step line")
+    ap.add_argument("--train-batch", type=int, default=64, help="images per GPU per training step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the (untimed) oracle check of the first images")
     args = ap.parse_args()
@@ -445,7 +540,7 @@ def main():
     elif args.gpus > 1:
         log(f"[bench] --gpus {args.gpus} without torchrun: launch with torch.distributed.run; running 1 rank")
     try:
-        run_ours(args, rank, world, local_rank)
+        (run_train if args.workload == "train" else run_ours)(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -228,3 +228,15 @@ def test_torch_mirror_train_model(tmp_path):
     m2 = A.CNNModel(shape, 2, conv_layers=[(4, 3), (8, 3)], hidden_units=[16, 8], dropout_rate=0.2).eval()
     m2.load_state_dict(saved)
     assert float((m2(Xt).argmax(1).cpu() == yt).float().mean()) >= 0.9
+
+
+def test_nccl_data_parallel_step_matches_full_batch():
+    """2 ranks over NCCL (needs 2 GPUs; the driver's 1-GPU run skips it -- the gloo test covers the collective on CPU)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29611", os.path.join(root, "tools", "train_dp_check.py")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "DP-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -206,3 +206,19 @@ def test_training_oracle_matches_reference_fixture():
     np.testing.assert_allclose(newp.conv_w[1], g["newW2"], rtol=0, atol=1e-12)
     np.testing.assert_allclose(newp.dense_w[0], g["newW4"], rtol=0, atol=1e-12)
     np.testing.assert_allclose(newp.dense_b[2], g["newb6"], rtol=0, atol=1e-12)
+
+
+def test_training_oracle_dropout_matches_reference_fixture():
+    """forward(training=True) with dropout + _compute_sample_grads: the reference's backward does NOT mask the gradient."""
+    from oracle import train as otr
+    g = np.load(os.path.join(GOLDEN, "ref_numpy_train_dropout.npz"))
+    cfg = ocnn.NetConfig.numpy_flavour((12, 12, 2), 2, [(3, 3), (4, 3)], [8, 6], 0.01)
+    p = ocnn.Params([g["W0"], g["W2"]], [g["b0"], g["b2"]], [g["W4"], g["W5"], g["W6"]], [g["b4"], g["b5"], g["b6"]])
+    mk = g["dropout_masks"]
+    gr, loss = otr.mean_grads(cfg, p, g["X"], g["labels"], dropout=[mk[:, :8], mk[:, 8:]], dropout_in_backward=False)
+    np.testing.assert_allclose(loss, g["losses"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(gr["conv_w"][0], g["grad0_dF"], rtol=0, atol=1e-12)
+    for j, li in enumerate((4, 5, 6)):
+        np.testing.assert_allclose(gr["dense_w"][j], g[f"grad{li}_dW"], rtol=0, atol=1e-12)
+    masked, _ = otr.mean_grads(cfg, p, g["X"], g["labels"], dropout=[mk[:, :8], mk[:, 8:]], dropout_in_backward=True)
+    assert np.abs(masked["dense_w"][0] - g["grad4_dW"]).max() > 1e-3       # the autograd rule is a different function

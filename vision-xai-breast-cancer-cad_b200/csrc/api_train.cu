@@ -116,6 +116,7 @@ int bcad_train_backward(bcad_model* mm, const float* x, const int32_t* labels, i
     TrainState& T = m->train;
     BCAD_CUDA_CHECK(cudaStreamWaitEvent(s, m->call_done, 0));
     const int nc = m->cfg.num_classes, nd = (int)m->dense.size(), nconv = (int)m->conv.size();
+    m->prof_n = 0;
     float* loss_buf = loss ? loss : T.hbuf;                  // scratch when the caller does not want the losses
     TR_LAUNCH(m, "ce_loss_topgrad", launch_ce_loss_topgrad(m->probs, labels, loss_buf, T.dense_dz[nd - 1], B, nc, s));
     // ---- dense layers, last to first
@@ -159,6 +160,7 @@ int bcad_train_backward(bcad_model* mm, const float* x, const int32_t* labels, i
             gp = P.gp;
         }
     }
+    TR_TRY(m->mark("end", s));
     BCAD_CUDA_CHECK(cudaEventRecord(m->call_done, s));
     return BCAD_OK;
 }
@@ -215,6 +217,7 @@ int bcad_apply_update(bcad_model* mm, const float* grads, int opt, float lr, flo
         BCAD_CUDA_CHECK(cudaMemsetAsync(T.adam_v, 0, T.total * sizeof(float), s));
     }
     if (opt == 1) ++T.adam_step;
+    m->prof_n = 0;
     int tix = 0;
     auto step = [&](float* w, size_t off, size_t n) -> int {
         if (opt == 0) {
@@ -238,6 +241,7 @@ int bcad_apply_update(bcad_model* mm, const float* grads, int opt, float lr, flo
         TR_TRY(step(D.d_b, T.dense_b_off[j], (size_t)D.out));
     }
     m->cached_B = 0;                                         // cached activations no longer match the weights
+    TR_TRY(m->mark("end", s));
     BCAD_CUDA_CHECK(cudaEventRecord(m->call_done, s));
     return BCAD_OK;
 }

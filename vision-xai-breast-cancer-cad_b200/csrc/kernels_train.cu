@@ -193,6 +193,83 @@ conv_wgrad_kernel(const float* __restrict__ dz, const float* __restrict__ in, fl
     }
 }
 
+
+// First-layer variant (Cin <= 4): with so few input channels the (filters x channels) thread map above leaves most of the
+// CTA idle, so here thread = (8 filters, one PIXEL lane): dz is read straight from global (the NG threads of a pixel cover
+// its CoutPad floats contiguously), the K*K input taps come through L1, and the pixel lanes are summed at the end --
+// shuffles inside a warp, then a fixed-order pass over the 8 warps in shared memory (deterministic).
+template <int K>
+__global__ void __launch_bounds__(256)
+conv_wgrad_smallcin_kernel(const float* __restrict__ dz, const float* __restrict__ in, float* __restrict__ part_w,
+                           float* __restrict__ part_b, int H, int W, int Cin, int Cout, int CoutPad, int pad, int Ho, int Wo,
+                           int band_rows, int bands) {
+    __shared__ float red[8][8][33];                             // [warp][filter in group][cg (<= 32)], +1 pad; one tap at a time
+    const int NG = CoutPad / 8, PL = 256 / NG;                  // filter groups (<= 32), pixel lanes
+    const int tid = threadIdx.x, cg = tid % NG, pl = tid / NG, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.x / bands, band = blockIdx.x % bands;
+    const int y0 = band * band_rows, y1 = min(Ho, y0 + band_rows);
+    const size_t wsz = (size_t)K * K * Cin * CoutPad;
+    float* pw = part_w + (size_t)blockIdx.x * wsz;
+    const bool vec = (Cout % 8 == 0);
+    for (int c = 0; c < Cin; ++c) {
+        float acc[K * K + 1][8];                                // last row: the bias gradient (c == 0 only)
+#pragma unroll
+        for (int t = 0; t <= K * K; ++t)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+        for (int y = y0; y < y1; ++y)
+            for (int x = pl; x < Wo; x += PL) {
+                float dv[8];
+                const float* dp = dz + (((size_t)b * Ho + y) * Wo + x) * Cout + cg * 8;
+                if (vec && cg * 8 < Cout) {
+                    const float4 d0 = __ldg(reinterpret_cast<const float4*>(dp)), d1 = __ldg(reinterpret_cast<const float4*>(dp) + 1);
+                    dv[0] = d0.x; dv[1] = d0.y; dv[2] = d0.z; dv[3] = d0.w; dv[4] = d1.x; dv[5] = d1.y; dv[6] = d1.z; dv[7] = d1.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dv[j] = (cg * 8 + j < Cout) ? __ldg(dp + j) : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[K * K][j] += dv[j];
+#pragma unroll
+                for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < K; ++kx) {
+                        const int iy = y + ky - pad, ix = x + kx - pad;
+                        const float xv = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(in + (((size_t)b * H + iy) * W + ix) * Cin + c) : 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[ky * K + kx][j] = fmaf(xv, dv[j], acc[ky * K + kx][j]);
+                    }
+            }
+        // sum the pixel lanes: lanes of a warp that share cg differ by multiples of NG
+        const int nval = (c == 0) ? K * K + 1 : K * K;
+#pragma unroll
+        for (int t = 0; t <= K * K; ++t)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float v = acc[t][j];
+                for (int o = NG; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                acc[t][j] = v;
+            }
+#pragma unroll
+        for (int t = 0; t <= K * K; ++t) {
+            if (t >= nval) break;
+            __syncthreads();
+            if (lane < NG)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) red[warp][j][lane] = acc[t][j];
+            __syncthreads();
+            if (tid < 8 * NG) {
+                const int g = tid % NG, j = tid / NG;
+                float v = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) v += red[w][j][g];
+                if (t < K * K) pw[((size_t)t * Cin + c) * CoutPad + g * 8 + j] = v;
+                else part_b[(size_t)blockIdx.x * CoutPad + g * 8 + j] = v;
+            }
+        }
+    }
+}
+
 // out[i] = sum_p part[p][i]  (fixed order)
 __global__ void reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int nparts, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -218,7 +295,11 @@ int launch_conv_wgrad(const float* dz, const float* in, float* part_w, float* pa
     const int NG = CoutPad / 8, CL = 256 / NG;
     const int ncta = B * bands;
     const size_t smem = (size_t)(32 * CoutPad + k * (32 + k - 1) * CL) * sizeof(float);
-    if (k == 1) conv_wgrad_kernel<1><<<ncta, 256, smem, s>>>(dz, in, part_w, part_b, H, W, Cin, Cout, CoutPad, pad, Ho, Wo, band_rows, bands);
+    if (Cin <= 4) {                                           // first layer: pixel-parallel variant
+        if (k == 1) conv_wgrad_smallcin_kernel<1><<<ncta, 256, 0, s>>>(dz, in, part_w, part_b, H, W, Cin, Cout, CoutPad, pad, Ho, Wo, band_rows, bands);
+        else if (k == 2) conv_wgrad_smallcin_kernel<2><<<ncta, 256, 0, s>>>(dz, in, part_w, part_b, H, W, Cin, Cout, CoutPad, pad, Ho, Wo, band_rows, bands);
+        else conv_wgrad_smallcin_kernel<3><<<ncta, 256, 0, s>>>(dz, in, part_w, part_b, H, W, Cin, Cout, CoutPad, pad, Ho, Wo, band_rows, bands);
+    } else if (k == 1) conv_wgrad_kernel<1><<<ncta, 256, smem, s>>>(dz, in, part_w, part_b, H, W, Cin, Cout, CoutPad, pad, Ho, Wo, band_rows, bands);
     else if (k == 2) conv_wgrad_kernel<2><<<ncta, 256, smem, s>>>(dz, in, part_w, part_b, H, W, Cin, Cout, CoutPad, pad, Ho, Wo, band_rows, bands);
     else conv_wgrad_kernel<3><<<ncta, 256, smem, s>>>(dz, in, part_w, part_b, H, W, Cin, Cout, CoutPad, pad, Ho, Wo, band_rows, bands);
     BCAD_CUDA_CHECK(cudaGetLastError());
