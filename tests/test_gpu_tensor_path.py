@@ -10,6 +10,8 @@ from util import engine_from, oracle_heatmaps, ocnn
 pytestmark = pytest.mark.gpu
 
 F16_TOL = 1e-2
+X3_LOGIT_TOL = 2e-4      # fp16x3: hi+lo split operands, fp32 accumulation -> fp32-grade
+X3_HEAT_TOL = 5e-4
 
 
 def _np(t):
@@ -86,6 +88,31 @@ def test_tensor_path_torch_flavour(shape, convs, hidden, B, mb):
     eng.close()
 
 
+@pytest.mark.parametrize("shape,pad,precision", [
+    ((40, 300, 1), 1, "fp16"),        # second block 150 px wide: segments of 128 + 22
+    ((24, 520, 1), 1, "fp16"),        # 260 px: 128 + 128 + 4
+    ((30, 301, 1), 0, "fp16"),        # valid conv: 299 -> 149 -> 147
+    ((24, 520, 1), 1, "fp16x3"),
+])
+def test_tensor_path_wide_maps(shape, pad, precision):
+    """Maps wider than one 128-pixel MMA tile: the implicit GEMM walks 128-pixel segments of a row (halo slots re-zeroed)."""
+    cfg = ocnn.NetConfig(shape, 2, [(32, 3), (64, 3)], [32, 16], 0.01, 0.01, pad, "chw", "first", "logits")
+    p = ocnn.init_params(cfg, seed=9, bias_std=0.05)
+    x = ocnn.synth_images(6, shape, seed=4)
+    eng = engine_from(cfg, p, precision=precision, max_batch=8)
+    if precision == "fp16":
+        _check(cfg, p, x, eng, 6)
+    else:
+        cls, probs, logits, heat = eng.predict_explain(x, None, "logit")
+        o_cls, cache, A, dA, o_heat = oracle_heatmaps(cfg, p, x, None, "logit")
+        lg = cache.logits.numpy()
+        assert np.abs(_np(logits) - lg).max() <= X3_LOGIT_TOL * max(1.0, np.abs(lg).max())
+        flipped = _kink_flips(eng, cache, 6)
+        assert flipped.sum() <= 1
+        assert np.abs(_np(heat) - o_heat).max(axis=(1, 2))[~flipped].max(initial=0.0) <= X3_HEAT_TOL
+    eng.close()
+
+
 def test_tensor_path_valid_conv_odd_sizes():
     """pad=0 (valid) with odd maps: 61 -> 59 -> 29 -> 27 -> 13; first-index pooling, softmax head, HWC flatten."""
     cfg = ocnn.NetConfig((61, 61, 1), 2, [(32, 3), (64, 3)], [32], 0.01, 0.01, 0, "hwc", "first", "softmax")
@@ -130,8 +157,6 @@ def test_tensor_path_full_size_canonical():
     eng32.close()
 
 
-X3_LOGIT_TOL = 2e-4      # fp16x3: hi+lo split operands, fp32 accumulation -> fp32-grade
-X3_HEAT_TOL = 5e-4
 
 
 @pytest.mark.parametrize("shape,hidden,B,mb,pad", [

@@ -417,41 +417,62 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    const int n_items = a.B * a.bands;
+    const int per_img = a.bands * a.xsegs;
+    const int n_items = a.B * per_img;
     const int in_row_elems = L::CHUNKS * a.W * 8;          // fp16 elements per input row (all channel octets)
 
     if (warp == 0) {
         // ================================ producer ================================
-        if (lane == 0) {
+        // (whole warp: lane 0 issues the bulk copies, the lanes zero the halo slots a segment leaves unwritten)
+        {
             constexpr int WB = L::WBYTES + L::BIAS_TILE;
-            mbar_arrive_expect_tx(wbar, WB);
-            for (int off = 0; off < WB; off += 16384)
-                bulk_g2s(s_w + off, a.w_img + off, min(16384, WB - off), wbar);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(wbar, WB);
+                for (int off = 0; off < WB; off += 16384)
+                    bulk_g2s(s_w + off, a.w_img + off, min(16384, WB - off), wbar);
+            }
             uint32_t g = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int b = item / a.bands, band = item % a.bands;
+                const int b = item / per_img, rem = item % per_img;
+                const int band = rem / a.xsegs, x0 = (rem % a.xsegs) * 128;
                 const int y0 = band * a.band_rows;
                 const int nrows = min(a.band_rows, a.Ho - y0);
                 const int nstages = (nrows + 1) / 2 + 1;
-                const __half* inb = a.in + (size_t)b * a.H * in_row_elems;
+                // ring slot s holds input pixel x0 - pad + s; slots outside the image stay (or are made) zero
+                const int s_lo = max(0, a.pad - x0), s_hi = min(130, a.W - x0 + a.pad);
+                const bool zero_hi = (a.xsegs > 1) && (s_hi < 130);       // only a multi-segment map can leave stale pixels there
+                const bool zero_lo = (a.xsegs > 1) && (s_lo > 0);
+                const __half* inb = a.in + (size_t)b * a.H * in_row_elems + (size_t)(x0 - a.pad + s_lo) * 8;
                 for (int q = 0; q < nstages; ++q, ++g) {
                     const uint32_t slot = g % IG_STAGES;
                     if (g >= IG_STAGES) mbar_wait(&empty[slot], ((g / IG_STAGES) - 1) & 1);
-                    uint32_t bytes = 0;
-                    for (int r = 0; r < 2; ++r) {
-                        const int in_row = y0 - a.pad + 2 * q + r;
-                        if (in_row >= 0 && in_row < a.H) bytes += L::CHUNKS * a.W * 16;
+                    if (zero_hi || zero_lo) {
+                        for (int i = lane; i < 2 * L::CHUNKS; i += 32) {
+                            uint8_t* rowp = s_ring + (slot * 2 + (i / L::CHUNKS)) * L::ROWB + (i % L::CHUNKS) * L::LBO;
+                            if (zero_lo) *reinterpret_cast<uint4*>(rowp) = make_uint4(0, 0, 0, 0);
+                            if (zero_hi) *reinterpret_cast<uint4*>(rowp + s_hi * 16) = make_uint4(0, 0, 0, 0);
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
                     }
-                    if (bytes) mbar_arrive_expect_tx(&full[slot], bytes);
-                    else mbar_arrive(&full[slot]);
-                    for (int r = 0; r < 2; ++r) {
-                        const int in_row = y0 - a.pad + 2 * q + r;
-                        if (in_row < 0 || in_row >= a.H) continue;
-                        uint8_t* dst = s_ring + (slot * 2 + r) * L::ROWB + a.pad * 16;
-                        const __half* src = inb + (size_t)in_row * in_row_elems;
-                        for (int c = 0; c < L::CHUNKS; ++c)
-                            bulk_g2s(dst + c * L::LBO, src + (size_t)c * a.W * 8, a.W * 16, &full[slot]);
+                    if (lane == 0) {
+                        uint32_t bytes = 0;
+                        for (int r = 0; r < 2; ++r) {
+                            const int in_row = y0 - a.pad + 2 * q + r;
+                            if (in_row >= 0 && in_row < a.H) bytes += L::CHUNKS * (s_hi - s_lo) * 16;
+                        }
+                        if (bytes) mbar_arrive_expect_tx(&full[slot], bytes);
+                        else mbar_arrive(&full[slot]);
+                        for (int r = 0; r < 2; ++r) {
+                            const int in_row = y0 - a.pad + 2 * q + r;
+                            if (in_row < 0 || in_row >= a.H) continue;
+                            uint8_t* dst = s_ring + (slot * 2 + r) * L::ROWB + s_lo * 16;
+                            const __half* src = inb + (size_t)in_row * in_row_elems;
+                            for (int c = 0; c < L::CHUNKS; ++c)
+                                bulk_g2s(dst + c * L::LBO, src + (size_t)c * a.W * 8, (s_hi - s_lo) * 16, &full[slot]);
+                        }
                     }
+                    __syncwarp();
                 }
             }
         }
@@ -464,7 +485,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
             uint32_t g = 0, acc_it = 0;
             const uint32_t w_base = smem_u32(s_w), zero_base = smem_u32(s_zero), ring_base = smem_u32(s_ring);
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int band = item % a.bands;
+                const int band = (item % per_img) / a.xsegs;
                 const int y0 = band * a.band_rows;
                 const int nrows = min(a.band_rows, a.Ho - y0);
                 const int npairs = (nrows + 1) / 2;
@@ -533,11 +554,12 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
         const int quad = warp & 3;
         const int half0 = (warp - 2) >> 2;              // which 32-channel half this warp owns
         const __half2 alpha2 = __float2half2_rn(a.alpha);
-        const int x = quad * 32 + lane;
         const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
         uint32_t acc_it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int b = item / a.bands, band = item % a.bands;
+            const int b = item / per_img, rem = item % per_img;
+            const int band = rem / a.xsegs;
+            const int x = (rem % a.xsegs) * 128 + quad * 32 + lane;          // output pixel of this TMEM lane
             const int y0 = band * a.band_rows;
             const int nrows = min(a.band_rows, a.Ho - y0);
             const int npairs = (nrows + 1) / 2;
@@ -714,7 +736,7 @@ template <int CIN, int COUT, bool X3>
 static int launch_igemm_t(const IgemmArgs& a, int sms, cudaStream_t s) {
     using L = IgemmSmem<CIN, COUT>;
     BCAD_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<CIN, COUT, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    const int items = a.B * a.bands;
+    const int items = a.B * a.bands * a.xsegs;
     const int grid = items < sms ? items : sms;
     conv_igemm_kernel<CIN, COUT, X3><<<grid, IG_THREADS, L::TOTAL, s>>>(a);
     BCAD_CUDA_CHECK(cudaGetLastError());
@@ -723,7 +745,7 @@ static int launch_igemm_t(const IgemmArgs& a, int sms, cudaStream_t s) {
 
 // Cin counts the channels the kernel sees: in fp16x3 mode that is 2 x the layer's channels (hi and lo octets)
 int launch_conv_igemm(const IgemmArgs& a, int Cin, int Cout, bool x3, int sms, cudaStream_t s) {
-    BCAD_REQUIRE(a.W <= 128 && a.Wo <= 128, "conv_igemm: map width %d > 128", a.W);
+    BCAD_REQUIRE(a.xsegs == cdiv(a.Wo, 128), "conv_igemm: xsegs must be ceil(Wo/128)");
     BCAD_REQUIRE(a.band_rows % 2 == 0, "conv_igemm: band_rows must be even");
     if (Cout == 64 && !x3) {
         if (Cin == 16) return launch_igemm_t<16, 64, false>(a, sms, s);

@@ -20,7 +20,8 @@ struct IgemmArgs {
     uint8_t* pool_fc;             // pooled output as fc1 A tiles, or nullptr
     __half* pool_c8;       // pooled output C8 planar [B][Hp][Cout/8][Wp][8], or nullptr
     int B, H, W, Ho, Wo, Hp, Wp, pad;
-    int bands, band_rows;         // work items per image; output rows per item (even)
+    int bands, band_rows;         // row bands per image; output rows per band (even)
+    int xsegs;                    // 128-pixel segments per row: work item = (image, band, segment)
     float alpha;
     int debug;                    // timing experiments only: 1 no act store, 2 no pool store, 4 empty epilogue, 8 no MMA
 };

@@ -66,7 +66,6 @@ int tensor_path_supported(const Model& m) {
     BCAD_REQUIRE(c0.Cin == 1 && c0.k == 3 && (c0.Cout == 16 || c0.Cout == 32 || c0.Cout == 64),
                  "precision=F16: first conv block must be 1 -> 16/32/64 channels, 3x3 (got %d -> %d, k=%d)", c0.Cin, c0.Cout, c0.k);
     BCAD_REQUIRE(c1.k == 3 && c1.Cout == 64, "precision=F16: second conv block must be 3x3 with 64 filters (got k=%d, %d)", c1.k, c1.Cout);
-    BCAD_REQUIRE(c1.W <= 128, "precision=F16: second conv block input width %d > 128", c1.W);
     BCAD_REQUIRE(c.pad == 0 || c.pad == 1, "precision=F16: pad must be 0 or 1");
     BCAD_REQUIRE(c.alpha_conv <= 1.f, "precision=F16: conv LeakyReLU slope must be <= 1 (max(v, alpha v) form)");
     BCAD_REQUIRE(c.pool_ties == BCAD_TIES_FIRST,
@@ -210,6 +209,7 @@ int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const in
     a.band_rows = 64;
     if (a.band_rows > c1.Ho) a.band_rows = cdiv(c1.Ho, 2) * 2;
     a.bands = cdiv(c1.Ho, a.band_rows);
+    a.xsegs = cdiv(c1.Wo, 128);
     a.alpha = m.cfg.alpha_conv;
     a.debug = 0;
     if (const char* dbg = getenv("BCAD_DEBUG_SKIP_STORES")) {      // timing experiments only (results are garbage)
