@@ -67,7 +67,7 @@ def algorithmic_flops_per_image():
 
 
 def tail_bytes_per_image(elem_size):
-    h, w = INPUT_SHAPE[0] // 2, INPUT_SHAPE[1] // 2      # last conv map 128x128x64
+    h, w = INPUT_SHAPE[0] // 2, INPUT_SHAPE[1] // 2      # last conv map (128x128x64 at 256x256)
     k = CONV_LAYERS[-1][0]
     return 2.0 * k * h * w * elem_size + INPUT_SHAPE[0] * INPUT_SHAPE[1] * 4.0
 
@@ -175,7 +175,7 @@ def run_reference(args, rank, world):
         step()
     dt = time.perf_counter() - t0
     value = n_per_step * args.steps / dt
-    sample = f"{n_per_step} synthetic 256x256x1 images per step in batches of 32 (bounded sample of the batch-512 workload)"
+    sample = f"{n_per_step} synthetic {'x'.join(map(str, INPUT_SHAPE))} images per step in batches of 32 (bounded sample of the batch-512 workload)"
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -189,8 +189,10 @@ def run_reference(args, rank, world):
 
 
 def workload_config(batch, precision):
-    return {"workload": f"cfg2: ADCNNM-flavour CNN (conv 32,64 k3 pad1; fc 256,128; {NUM_CLASSES} classes; random init) "
-                        f"predict+Grad-CAM(last conv, predicted class), 256x256x1 fp32 NHWC, batch {batch} per GPU",
+    h, w, c = INPUT_SHAPE
+    tag = "cfg2" if INPUT_SHAPE == (256, 256, 1) else "secondary shape (SURVEY 8d)"
+    return {"workload": f"{tag}: ADCNNM-flavour CNN (conv 32,64 k3 pad1; fc 256,128; {NUM_CLASSES} classes; random init) "
+                        f"predict+Grad-CAM(last conv, predicted class), {h}x{w}x{c} fp32 NHWC, batch {batch} per GPU",
             "batch_per_gpu": batch, "precision_path": precision,
             "l2_policy": "inputs + activations per step (>= 134 MB input, GBs of activations) exceed the 126 MB L2"}
 
@@ -359,7 +361,7 @@ def run_ours(args, rank, world, local_rank):
                                       "note": "SURVEY 8d dense figure (read A, read dA, write fp32 map); this path derives alpha "
                                               "from dz1 and never materialises dA, so it moves fewer bytes than that"}}
     traffic_file = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if roof is not None and os.path.exists(traffic_file) and B == 512:
+    if roof is not None and os.path.exists(traffic_file) and B == 512 and INPUT_SHAPE == (256, 256, 1):
         tr = json.load(open(traffic_file))
         for kname, nbytes in tr.items():
             if kname.split("<")[0] in {"conv_igemm_kernel": "conv1_igemm_tcgen05", "conv_first_tc_kernel": "conv0_first_tcgen05"} and \
@@ -371,7 +373,7 @@ def run_ours(args, rank, world, local_rank):
     if not args.no_cpu_baseline:
         rate, secs, cores = cpu_reference_rate(args.cpu_images)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_images} of the workload's synthetic 256x256x1 images in batches of 32 "
+               "sample": f"{args.cpu_images} of the workload's synthetic {'x'.join(map(str, INPUT_SHAPE))} images in batches of 32 "
                          f"({secs:.1f} s), oracle port of ADCNNM + autograd Grad-CAM + NumPy tail"}
     out_json = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -520,9 +522,14 @@ def main():
     ap.add_argument("--workload", default="explain", choices=["explain", "train"],
                     help="explain = the headline path (predict + Grad-CAM); train = the secondary training-step line")
     ap.add_argument("--train-batch", type=int, default=64, help="images per GPU per training step")
+    ap.add_argument("--input-shape", default=None, help="H,W,C of a SECONDARY shape (SURVEY 8d: 256,256,64 or 64,256,256); "
+                                                        "the headline line uses the default 256,256,1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the (untimed) oracle check of the first images")
     args = ap.parse_args()
+    if args.input_shape:
+        global INPUT_SHAPE
+        INPUT_SHAPE = tuple(int(v) for v in args.input_shape.split(","))
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))

@@ -113,6 +113,35 @@ def test_tensor_path_wide_maps(shape, pad, precision):
     eng.close()
 
 
+@pytest.mark.parametrize("shape,convs,pad,B", [
+    ((32, 40, 3), [(32, 3), (64, 3)], 1, 5),      # RGB-like: 3 channels padded to one 16-channel group
+    ((24, 24, 64), [(32, 3), (64, 3)], 1, 4),     # one 64-channel group ("(H,W,64)" bottleneck features)
+    ((16, 48, 256), [(32, 3), (64, 3)], 1, 3),    # 4 groups of 64 accumulate in TMEM (the deployed 256-channel model)
+    ((20, 20, 48), [(32, 3), (64, 3)], 1, 4),     # 3 groups of 16
+    ((24, 24, 32), [(64, 3), (64, 3)], 1, 4),     # 64 first-block filters: bands of 4 rows
+    ((16, 16, 96), [(64, 3), (64, 3)], 1, 3),     # 64 filters, 3 groups of 32
+    ((12, 300, 32), [(32, 3), (64, 3)], 1, 3),    # wide map: 3 segments in the first block, 2 in the second
+    ((21, 23, 16), [(32, 3), (64, 3)], 0, 4),     # valid conv, odd sizes
+    ((38, 20, 64), [(32, 3), (64, 3)], 1, 150),   # many bands per image and more items than SMs
+])
+def test_tensor_path_multichannel_first_block(shape, convs, pad, B):
+    """Multi-channel inputs: fp32 NHWC -> fp16 C8-planar, first block as a channel-grouped implicit GEMM (sm100_wide.cu)."""
+    cfg = ocnn.NetConfig(shape, 2, convs, [32, 16], 0.01, 0.01, pad, "chw", "first", "logits")
+    p = ocnn.init_params(cfg, seed=13, bias_std=0.05)
+    x = ocnn.synth_images(B, shape, seed=8)
+    eng = engine_from(cfg, p, precision="fp16", max_batch=max(8, B))
+    from bcad_b200 import _lib
+    k = min(4, B)
+    cache = ocnn.forward(cfg, p, x[:k])
+    eng.predict(x[:k])
+    h1, w1 = cache.pool_out[0].shape[1:3]
+    p1 = _np(eng.get_tensor(_lib.T_POOL_OUT, 0, k)).reshape(k, h1, w1, convs[0][0])
+    want = cache.pool_out[0].numpy()
+    assert np.abs(p1 - want).max() <= 1e-2 * max(1.0, np.abs(want).max()), "first block (fp16 operands, fp32 accumulate)"
+    _check(cfg, p, x, eng, B)
+    eng.close()
+
+
 def test_tensor_path_valid_conv_odd_sizes():
     """pad=0 (valid) with odd maps: 61 -> 59 -> 29 -> 27 -> 13; first-index pooling, softmax head, HWC flatten."""
     cfg = ocnn.NetConfig((61, 61, 1), 2, [(32, 3), (64, 3)], [32], 0.01, 0.01, 0, "hwc", "first", "softmax")
@@ -130,7 +159,10 @@ def test_tensor_path_rejects_unsupported_shapes():
     with pytest.raises(ValueError, match="TIES_FIRST"):
         bcad_b200.Engine(spec_from_cfg(cfg), precision="fp16")
     cfg = ocnn.NetConfig.torch_flavour((32, 32, 3), 2, [(32, 3), (64, 3)], [32])
-    with pytest.raises(ValueError):
+    with pytest.raises(ValueError, match="single-channel"):
+        bcad_b200.Engine(spec_from_cfg(cfg), precision="fp16x3")
+    cfg = ocnn.NetConfig.torch_flavour((32, 32, 3), 2, [(16, 3), (64, 3)], [32])
+    with pytest.raises(ValueError, match="32 or 64 filters"):
         bcad_b200.Engine(spec_from_cfg(cfg), precision="fp16")
 
 

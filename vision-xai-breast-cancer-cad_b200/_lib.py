@@ -88,11 +88,12 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("BCAD_LIB", LIB_PATH)       # developer override: an experimental build of the same ABI
+    if not os.path.exists(path):
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python vision-xai-breast-cancer-cad_b200/build.py` "
+            f"{path} is missing: build it with `python vision-xai-breast-cancer-cad_b200/build.py` "
             "(or __graft_entry__.build()). This package has no CPU / PyTorch fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)            # AttributeError if the .so does not export it
         fn.restype = res

@@ -349,8 +349,11 @@ int launch_conv_first_tc(const float* x, const uint8_t* w_img, __half* out, int 
 //   Warp roles: 0 = bulk-copy producer, 1 = MMA issuer, 2..9 = epilogue (TMEM lane quadrant = warp % 4; the two
 //   warps of a quadrant split the channels, so every scheduler has two epilogue warps to hide latency).
 // =====================================================================================================
+#ifndef IG_STAGES_SMALL
+#define IG_STAGES_SMALL 4
+#endif
 constexpr int IG_XP = 136;            // pixel slots per ring row (>= 128 + 2 halo, multiple of 8)
-constexpr int ig_stages(int cin) { return cin >= 64 ? 3 : 4; }   // ring stages of 2 input rows (smem budget)
+constexpr int ig_stages(int cin) { return cin >= 64 ? 3 : IG_STAGES_SMALL; }   // ring stages of 2 input rows (smem budget)
 constexpr int IG_THREADS = 320;         // producer warp, MMA warp, 8 epilogue warps (2 per scheduler)
 
 template <int CIN, int COUT>

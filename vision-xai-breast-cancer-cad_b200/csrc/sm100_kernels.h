@@ -27,6 +27,21 @@ struct IgemmArgs {
 };
 int launch_conv_igemm(const IgemmArgs& a, int Cin, int Cout, bool x3, int sms, cudaStream_t s);
 
+// first conv block with many input channels (sm100_wide.cu)
+struct WideArgs {
+    const __half* in;             // C8 planar [B][H][CinPad/8][W][8]
+    const uint8_t* w_img;         // [G][9*(KC/8)][Cout][16 B] per channel group, then the bias tile [2][Cout][16 B]
+    __half* pool_c8;              // pooled output C8 planar [B][Hp][Cout/8][Wp][8]
+    int B, H, W, Ho, Wo, Hp, Wp, pad;
+    int G;                        // channel groups of KC = conv_wide_group_channels(CinPad, Cout) channels
+    int ybands, xsegs;            // bands of 256/Cout output rows, 128-pixel segments: work item = (image, band, segment)
+    float alpha;
+};
+int conv_wide_group_channels(int CinPad, int Cout);
+int conv_wide_rows_per_band(int Cout);
+int launch_conv_wide(const WideArgs& a, int CinPad, int Cout, int sms, cudaStream_t s);
+int launch_nhwc_to_c8(const float* x, __half* out, int B, int H, int W, int C, int CinPad, cudaStream_t s);
+
 struct FcArgs {
     const uint8_t* a_tiles;       // [m_tiles][nkb][128][128 B] SW128
     const uint8_t* w_tiles;       // [nkb][N][128 B] SW128

@@ -41,6 +41,10 @@ struct TensorPath {
     float* alpha_raw = nullptr;     // [B][Cout] = dz1 . S
     int fc_splits = 1, kb_per_split = 1, m_pad = 128;
     bool x3 = false;                // fp16x3: hi/lo split operands everywhere (fp32-grade)
+    bool wide = false;              // first block has Cin > 1: nhwc_to_c8 + conv_wide (sm100_wide.cu)
+    int cin_pad = 0, kc = 0, groups = 0;
+    uint8_t* d_w0_wide = nullptr;   // [G][9*(KC/8)][Cout0][16 B] + bias tile
+    __half* x_c8 = nullptr;         // the input converted to C8-planar fp16
 };
 
 #define TP_TRY(expr) do { int _rc = (expr); if (_rc != BCAD_OK) return _rc; } while (0)
@@ -63,15 +67,20 @@ int tensor_path_supported(const Model& m) {
     BCAD_REQUIRE(m.conv.size() == 2, "precision=F16: the tensor path covers 2 conv blocks (got %zu); use BCAD_PREC_FP32", m.conv.size());
     const ConvLayer& c0 = m.conv[0];
     const ConvLayer& c1 = m.conv[1];
-    BCAD_REQUIRE(c0.Cin == 1 && c0.k == 3 && (c0.Cout == 16 || c0.Cout == 32 || c0.Cout == 64),
-                 "precision=F16: first conv block must be 1 -> 16/32/64 channels, 3x3 (got %d -> %d, k=%d)", c0.Cin, c0.Cout, c0.k);
+    BCAD_REQUIRE(c0.k == 3 && (c0.Cout == 16 || c0.Cout == 32 || c0.Cout == 64),
+                 "precision=F16: first conv block must be 3x3 with 16/32/64 filters (got %d, k=%d)", c0.Cout, c0.k);
+    if (c0.Cin > 1) {
+        BCAD_REQUIRE(c0.Cout == 32 || c0.Cout == 64, "precision=F16: a multi-channel first conv block needs 32 or 64 filters (got %d)", c0.Cout);
+        BCAD_REQUIRE(c0.Cin <= 1024, "precision=F16: first conv block with %d input channels (max 1024)", c0.Cin);
+        BCAD_REQUIRE(c.precision != BCAD_PREC_F16X3, "precision=F16X3 covers single-channel inputs; use BCAD_PREC_F16 or BCAD_PREC_FP32 for %d channels", c0.Cin);
+    }
     BCAD_REQUIRE(c1.k == 3 && c1.Cout == 64, "precision=F16: second conv block must be 3x3 with 64 filters (got k=%d, %d)", c1.k, c1.Cout);
     BCAD_REQUIRE(c.pad == 0 || c.pad == 1, "precision=F16: pad must be 0 or 1");
     BCAD_REQUIRE(c.alpha_conv <= 1.f, "precision=F16: conv LeakyReLU slope must be <= 1 (max(v, alpha v) form)");
     BCAD_REQUIRE(c.pool_ties == BCAD_TIES_FIRST,
                  "precision=F16: the alpha shortcut needs first-index pooling (TIES_FIRST); the tie-duplicating NumPy flavour runs on BCAD_PREC_FP32");
     if (c.precision == BCAD_PREC_F16X3)
-        BCAD_REQUIRE(c0.Cout == 32, "precision=F16X3: the split-operand path needs 32 first-block filters (got %d)", c0.Cout);
+        BCAD_REQUIRE(c0.Cin == 1 && c0.Cout == 32, "precision=F16X3: the split-operand path needs 32 first-block filters (got %d)", c0.Cout);
     const int units = m.dense[0].out;
     BCAD_REQUIRE(units % 16 == 0 && units <= 256, "precision=F16: first dense layer must have a multiple of 16 units <= 256 (got %d)", units);
     return BCAD_OK;
@@ -88,8 +97,35 @@ int tensor_path_commit(Model& m) {
     const ConvLayer& c1 = m.conv[1];
     DenseLayer& d0 = m.dense[0];
     const int mb = m.cfg.max_batch;
+    t.wide = (c0.Cin > 1);
+    if (t.wide) {
+        // ---- multi-channel first block: per channel group [tap][octet][Cout][8] fp16, then the bias tile
+        t.cin_pad = cdiv(c0.Cin, 16) * 16;
+        t.kc = conv_wide_group_channels(t.cin_pad, c0.Cout);
+        t.groups = t.cin_pad / t.kc;
+        const int chunks = t.kc / 8;
+        const size_t wg = (size_t)9 * chunks * c0.Cout * 8;                   // halves per group
+        std::vector<uint16_t> img(wg * t.groups + (size_t)2 * c0.Cout * 8, 0);
+        for (int g = 0; g < t.groups; ++g)
+            for (int tap = 0; tap < 9; ++tap)
+                for (int ch = 0; ch < chunks; ++ch)
+                    for (int f = 0; f < c0.Cout; ++f)
+                        for (int e = 0; e < 8; ++e) {
+                            const int cidx = g * t.kc + ch * 8 + e;
+                            if (cidx < c0.Cin)
+                                img[g * wg + (((size_t)tap * chunks + ch) * c0.Cout + f) * 8 + e] = f2h(c0.h_w[((size_t)f * 9 + tap) * c0.Cin + cidx]);
+                        }
+        for (int f = 0; f < c0.Cout; ++f) {
+            const float bhi = h2f(f2h(c0.h_b[f]));
+            img[wg * t.groups + (size_t)f * 8 + 0] = f2h(bhi);
+            img[wg * t.groups + (size_t)f * 8 + 1] = f2h(c0.h_b[f] - bhi);
+        }
+        if (!t.d_w0_wide) TP_TRY(m.alloc((void**)&t.d_w0_wide, img.size() * 2));
+        BCAD_CUDA_CHECK(cudaMemcpy(t.d_w0_wide, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+        if (!t.x_c8) TP_TRY(m.alloc((void**)&t.x_c8, (size_t)mb * c0.H * c0.W * t.cin_pad * 2));
+    }
     // ---- conv0: [9][Cout] fp32
-    {
+    if (!t.wide) {
         std::vector<float> w((size_t)9 * c0.Cout);
         for (int f = 0; f < c0.Cout; ++f)
             for (int tap = 0; tap < 9; ++tap) w[(size_t)tap * c0.Cout + f] = c0.h_w[(size_t)f * 9 + tap];
@@ -99,7 +135,7 @@ int tensor_path_commit(Model& m) {
         BCAD_CUDA_CHECK(cudaMemcpy(t.d_b0, c0.h_b.data(), c0.Cout * 4, cudaMemcpyHostToDevice));
     }
     // ---- conv0 tensor-core image: K = 32 slots per filter: [w_hi(9) b_hi | w_hi(9) b_lo | w_lo(9) 0 0 0]
-    if (c0.Cout == 32 || c0.Cout == 64) {
+    if (!t.wide && (c0.Cout == 32 || c0.Cout == 64)) {
         std::vector<uint16_t> img((size_t)4 * c0.Cout * 8, 0);
         auto put = [&](int f, int k, float v) { img[((size_t)(k >> 3) * c0.Cout + f) * 8 + (k & 7)] = f2h(v); };
         for (int f = 0; f < c0.Cout; ++f) {
@@ -199,7 +235,15 @@ int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const in
     TensorPath& t = *m.tp;
     const ConvLayer& c0 = m.conv[0];
     const ConvLayer& c1 = m.conv[1];
-    if (t.d_w0_img != nullptr && (t.x3 || getenv("BCAD_CONV0_CUDA_CORES") == nullptr))
+    if (t.wide) {
+        TP_LAUNCH(m, "input_to_c8", launch_nhwc_to_c8(x, t.x_c8, n, c0.H, c0.W, c0.Cin, t.cin_pad, s));
+        WideArgs w;
+        w.in = t.x_c8; w.w_img = t.d_w0_wide; w.pool_c8 = t.p1;
+        w.B = n; w.H = c0.H; w.W = c0.W; w.Ho = c0.Ho; w.Wo = c0.Wo; w.Hp = c0.Hp; w.Wp = c0.Wp; w.pad = m.cfg.pad;
+        w.G = t.groups; w.ybands = cdiv(c0.Ho, conv_wide_rows_per_band(c0.Cout)); w.xsegs = cdiv(c0.Wo, 128);
+        w.alpha = m.cfg.alpha_conv;
+        TP_LAUNCH(m, "conv0_wide_tcgen05", launch_conv_wide(w, t.cin_pad, c0.Cout, t.sms, s));
+    } else if (t.d_w0_img != nullptr && (t.x3 || getenv("BCAD_CONV0_CUDA_CORES") == nullptr))
         TP_LAUNCH(m, "conv0_first_tcgen05", launch_conv_first_tc(x, t.d_w0_img, t.p1, n, c0.H, c0.W, m.cfg.pad, c0.Cout, m.cfg.alpha_conv, t.x3, t.sms, s));
     else
         TP_LAUNCH(m, "conv0_first_pool", launch_conv_first_pool(x, t.d_w0, t.d_b0, t.p1, n, c0.H, c0.W, m.cfg.pad, c0.Cout, m.cfg.alpha_conv, s));
