@@ -10,6 +10,8 @@
 //
 // Reference semantics: conv+bias+LeakyReLU+2x2 max-pool (Classes/CNNModel.py:227-261, ADCNNM.py:48,76),
 // dense z = W.flat + b (Classes/CNNModel.py:180); Grad-CAM channel reduction (pytorch_grad_cam, GRADCAM.py:64).
+#include <stdlib.h>
+
 #include "../../include/bcad.h"
 #include "common.cuh"
 #include "sm100.cuh"
@@ -110,13 +112,13 @@ int launch_conv_first_pool(const float* x, const float* w9c, const float* bias, 
 // The CUDA-core work left is the im2col row build (16 STS.128 / thread) and the pooled epilogue: ~4x fewer
 // instructions than 1152 FFMAs per pooled pixel.  128-thread CTAs, 3 per SM, im2col image double-buffered.
 // =====================================================================================================
-template <int COUT, bool SPLIT>
-__global__ void __launch_bounds__(128, 3)
+template <int COUT, bool SPLIT, bool DBUF>
+__global__ void __launch_bounds__(128, DBUF ? 3 : 4)
 conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_img /*[4][COUT][16 B]*/,
                      __half* __restrict__ out, int B, int H, int W, int pad, int Hp, int Wp, float alpha) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* s_a = smem;                          // 2 buffers x 4 classes x [4 chunks][128 rows][16 B] = 2 x 32 KB
-    uint8_t* s_b = smem + 2 * 32768;              // [4 chunks][COUT][16 B]
+    uint8_t* s_a = smem;                          // (DBUF ? 2 : 1) buffers x 4 classes x [4 chunks][128 rows][16 B] = 32 KB each
+    uint8_t* s_b = smem + (DBUF ? 2 : 1) * 32768;  // [4 chunks][COUT][16 B]
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -294,29 +296,42 @@ conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_
     }
     for (int it = 0; tile < n_tiles; tile += G, ++it) {
         const int next = tile + G;
-        if (next < n_tiles) {
-            build((it + 1) & 1, patch);             // overlaps the MMAs of this tile
-            fence_proxy_async();
-            advance(nxt);
-            if (next + G < n_tiles) load_patch(nxt, patch);          // inputs of tile t+2
+        if constexpr (DBUF) {
+            if (next < n_tiles) {
+                build((it + 1) & 1, patch);             // overlaps the MMAs of this tile
+                fence_proxy_async();
+                advance(nxt);
+                if (next + G < n_tiles) load_patch(nxt, patch);          // inputs of tile t+2
+            }
+            mbar_wait(&bar, phase);
+            phase ^= 1;
+            tc_fence_after();
+        } else {
+            // one im2col buffer (a 4th CTA per SM instead): it is free again once this tile's MMAs have retired
+            mbar_wait(&bar, phase);
+            phase ^= 1;
+            tc_fence_after();
+            if (next < n_tiles) {
+                build(0, patch);
+                fence_proxy_async();
+                advance(nxt);
+                if (next + G < n_tiles) load_patch(nxt, patch);
+            }
         }
-        mbar_wait(&bar, phase);
-        phase ^= 1;
-        tc_fence_after();
         epilogue(cur);
         advance(cur);
         tc_fence_before();
         __syncthreads();                            // next image fully built; TMEM drained
-        if (next < n_tiles) issue((it + 1) & 1);
+        if (next < n_tiles) issue(DBUF ? ((it + 1) & 1) : 0);
     }
     if (warp == 0) tmem_dealloc(tmem, 4 * COUT);
 }
 
-template <int COUT, bool SPLIT>
+template <int COUT, bool SPLIT, bool DBUF = true>
 static int launch_conv_first_tc_t(const float* x, const uint8_t* w_img, __half* out, int B, int H, int W, int pad, int Hp,
                                   int Wp, float alpha, int grid, int smem, cudaStream_t s) {
-    BCAD_CUDA_CHECK(cudaFuncSetAttribute(conv_first_tc_kernel<COUT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    conv_first_tc_kernel<COUT, SPLIT><<<grid, 128, smem, s>>>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha);
+    BCAD_CUDA_CHECK(cudaFuncSetAttribute(conv_first_tc_kernel<COUT, SPLIT, DBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    conv_first_tc_kernel<COUT, SPLIT, DBUF><<<grid, 128, smem, s>>>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha);
     BCAD_CUDA_CHECK(cudaGetLastError());
     return BCAD_OK;
 }
@@ -325,9 +340,11 @@ int launch_conv_first_tc(const float* x, const uint8_t* w_img, __half* out, int 
                          float alpha, bool split_hi_lo, int sms, cudaStream_t s) {
     const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2, Hp = Ho / 2, Wp = Wo / 2;
     const int n_tiles = B * Hp * cdiv(Wp, 128);
-    const int smem = 2 * 32768 + 4 * Cout * 16;
-    const int per_sm = Cout <= 32 ? 3 : 2;          // smem: 66 KB per CTA; TMEM: 4*Cout columns per CTA
+    const bool single = (Cout == 32 && !split_hi_lo && getenv("BCAD_CONV0_SINGLE") != nullptr);   // experiment
+    const int smem = (single ? 1 : 2) * 32768 + 4 * Cout * 16;
+    const int per_sm = Cout <= 32 ? (single ? 4 : 3) : 2;          // smem: 66 KB per CTA; TMEM: 4*Cout columns per CTA
     const int grid = n_tiles < sms * per_sm ? n_tiles : sms * per_sm;
+    if (single) return launch_conv_first_tc_t<32, false, false>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s);
     if (Cout == 32 && !split_hi_lo) return launch_conv_first_tc_t<32, false>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s);
     if (Cout == 32 && split_hi_lo) return launch_conv_first_tc_t<32, true>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s);
     if (Cout == 64 && !split_hi_lo) return launch_conv_first_tc_t<64, false>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s);
