@@ -337,6 +337,13 @@ def run_ours(args, rank, world, local_rank):
         roof = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": None, "peak_source": pk["source"] + " (sustained bf16 cuBLAS)",
                 "algorithmic_flops_per_launch": flops}
+    elif name == "input_to_c8":
+        h, w, c = INPUT_SHAPE
+        nbytes = float(h * w * (c * 4 + ((c + 15) // 16 * 16) * 2)) * B      # fp32 NHWC read + fp16 C8-planar write
+        ach = nbytes / (dom_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                "algorithmic_bytes_per_launch": nbytes}
     else:
         esz = 2 if precision.startswith("fp16") else 4
         nbytes = tail_bytes_per_image(esz) * B

@@ -110,7 +110,8 @@ int launch_conv_first_pool(const float* x, const float* w9c, const float* bias, 
 // term is 2^-22 relative).  One CTA tile = 128 pooled pixels of one pooled row; the four members of each 2x2 pool
 // window are four accumulators of the SAME TMEM lane, so pooling is three max ops per channel with no shuffles.
 // The CUDA-core work left is the im2col row build (16 STS.128 / thread) and the pooled epilogue: ~4x fewer
-// instructions than 1152 FFMAs per pooled pixel.  128-thread CTAs, 3 per SM, im2col image double-buffered.
+// instructions than 1152 FFMAs per pooled pixel.  128-thread CTAs; DBUF: im2col image double-buffered, 3 CTAs per SM;
+// !DBUF: one image, 4 CTAs per SM.
 // =====================================================================================================
 template <int COUT, bool SPLIT, bool DBUF>
 __global__ void __launch_bounds__(128, DBUF ? 3 : 4)
@@ -340,12 +341,13 @@ int launch_conv_first_tc(const float* x, const uint8_t* w_img, __half* out, int 
                          float alpha, bool split_hi_lo, int sms, cudaStream_t s) {
     const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2, Hp = Ho / 2, Wp = Wo / 2;
     const int n_tiles = B * Hp * cdiv(Wp, 128);
-    const bool single = (Cout == 32 && !split_hi_lo && getenv("BCAD_CONV0_SINGLE") != nullptr);   // experiment
+    // 32 filters, fp16 mode: ONE im2col buffer and a 4th CTA per SM (TMEM allows 4 x 128 columns) measured 2.6 % faster than
+    // double-buffering with 3 CTAs (0.254 vs 0.261 ms at 512 x 256x256)
+    const bool single = (Cout == 32 && !split_hi_lo);
     const int smem = (single ? 1 : 2) * 32768 + 4 * Cout * 16;
     const int per_sm = Cout <= 32 ? (single ? 4 : 3) : 2;          // smem: 66 KB per CTA; TMEM: 4*Cout columns per CTA
     const int grid = n_tiles < sms * per_sm ? n_tiles : sms * per_sm;
     if (single) return launch_conv_first_tc_t<32, false, false>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s);
-    if (Cout == 32 && !split_hi_lo) return launch_conv_first_tc_t<32, false>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s);
     if (Cout == 32 && split_hi_lo) return launch_conv_first_tc_t<32, true>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s);
     if (Cout == 64 && !split_hi_lo) return launch_conv_first_tc_t<64, false>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s);
     set_error("conv_first_tc: Cout %d (split=%d) not supported", Cout, (int)split_hi_lo);

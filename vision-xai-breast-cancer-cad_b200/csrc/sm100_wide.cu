@@ -12,8 +12,6 @@
 //                   (+ 2 halo rows), the weights come from L2.
 //   Output: pooled map, C8-planar fp16 -- the input layout of conv_igemm (sm100_kernels.cu).
 // Reference semantics: Conv2d(padding=1) / valid conv + bias + LeakyReLU + MaxPool2d(2) (ADCNNM.py:48,76; Classes/CNNModel.py:227-261).
-#include <stdlib.h>
-
 #include "../../include/bcad.h"
 #include "common.cuh"
 #include "sm100.cuh"
@@ -62,7 +60,11 @@ int launch_nhwc_to_c8(const float* x, __half* out, int B, int H, int W, int C, i
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int WD_XP = 136;              // pixel slots per ring row (128 + 2 halo, multiple of 8)
 constexpr int WD_THREADS = 320;         // producer warp, MMA warp, 8 epilogue warps
-constexpr int wd_stages(int kc) { return kc >= 64 ? 3 : 8; }   // ring stages of 2 input rows (deep prefetch: a stage is ~1 us of MMA work)
+// ring stages of 2 input rows.  Deep prefetch: a stage is ~1 us of MMA work (groups of 64 channels with a 3-stage ring measured
+// 9 % slower).  Measured and dropped: reading the caller's fp32 NHWC directly (converter warps, cp.async staging) -- a channel
+// group is then a 128-byte piece of every pixel record, and that strided HBM pattern cost as much as the separate streaming
+// conversion pass saves (1.03 ms vs 0.54 + 0.475 ms at 128 x 256x256x64).
+constexpr int wd_stages(int) { return 8; }
 
 template <int KC, int COUT>
 struct WideSmem {
@@ -323,7 +325,6 @@ static int launch_wide_t(const WideArgs& a, int sms, cudaStream_t s) {
 }
 
 int conv_wide_group_channels(int CinPad, int Cout) {
-    if (getenv("BCAD_WIDE_KC64") != nullptr && Cout == 32 && CinPad % 64 == 0) return 64;   // experiment: 3-stage ring of 64-channel rows
     if (CinPad % 32 == 0) return 32;
     return 16;
 }
@@ -335,7 +336,6 @@ int launch_conv_wide(const WideArgs& a, int CinPad, int Cout, int sms, cudaStrea
     BCAD_REQUIRE(CinPad % 16 == 0 && a.G * KC == CinPad, "conv_wide: %d channels in %d groups of %d", CinPad, a.G, KC);
     BCAD_REQUIRE(a.xsegs == cdiv(a.Wo, 128) && a.ybands == cdiv(a.Ho, conv_wide_rows_per_band(Cout)), "conv_wide: bad tiling");
     if (Cout == 32) {
-        if (KC == 64) return launch_wide_t<64, 32>(a, sms, s);
         if (KC == 32) return launch_wide_t<32, 32>(a, sms, s);
         return launch_wide_t<16, 32>(a, sms, s);
     }
