@@ -988,19 +988,21 @@ int launch_overlay(const float* img01, const float* cam, int B, int H, int W, ui
 // Replaces ~12 tiny launches of the layer-by-layer path (explainability.py:20-34, Classes/CNNModel.py:177-212).
 // =====================================================================================================
 __global__ void __launch_bounds__(256) dense_head_kernel(HeadArgs a) {
-    extern __shared__ float sh[];                 // z of every layer, then activations / gradients scratch
+    extern __shared__ __align__(16) float sh[];   // z of every layer, then activations / gradients scratch
     __shared__ int s_cls;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int off[BCAD_MAX_DENSE + 1];
     off[0] = 0;
     for (int j = 0; j < a.n_dense; ++j) off[j + 1] = off[j] + a.sizes[j];
     float* s_z = sh;                              // [sum sizes]
-    float* s_v = sh + off[a.n_dense];             // activation vector of the current layer (max size)
+    float* s_v = sh + ((off[a.n_dense] + 3) & ~3); // activation vector of the current layer (max size), 16-byte aligned
     float* s_g = s_v + a.max_size;                // gradient vector (max size)
     // ---- layer 0: reduce the split-K partials in a fixed order
     const int n0 = a.sizes[0];
     for (int u = tid; u < n0; u += 256) {
         float v = 0.f;
+        // fixed summation order; unrolled so that 8 partial loads are in flight (the kernel is a chain of L2 latencies)
+#pragma unroll 8
         for (int sidx = 0; sidx < a.fc1_splits; ++sidx) v += a.fc1_part[(size_t)sidx * a.fc1_ld + (size_t)b * n0 + u];
         v += __ldg(a.bias[0] + u);
         s_z[u] = v;
@@ -1012,14 +1014,37 @@ __global__ void __launch_bounds__(256) dense_head_kernel(HeadArgs a) {
     for (int j = 1; j < a.n_dense; ++j) {
         const int nin = a.sizes[j - 1], nout = a.sizes[j];
         const float* Wj = a.W[j];
-        for (int v = warp; v < nout; v += 8) {
-            float acc = 0.f;
-            for (int u = lane; u < nin; u += 32) acc = fmaf(__ldg(Wj + (size_t)v * nin + u), s_v[u], acc);
-            acc = warp_sum(acc);
-            if (lane == 0) {
-                acc += __ldg(a.bias[j] + v);
-                s_z[off[j] + v] = acc;
-                a.z[j][(size_t)b * nout + v] = acc;
+        // four output rows at a time per warp (independent weight loads in flight); 16-byte loads when the row length allows
+        const bool vec4 = (nin % 4 == 0);
+        for (int v0 = warp * 4; v0 < nout; v0 += 32) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            if (vec4) {
+                for (int u = lane * 4; u < nin; u += 128) {
+                    const float4 x = *reinterpret_cast<const float4*>(s_v + u);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        if (v0 + r < nout) {
+                            const float4 w = __ldg(reinterpret_cast<const float4*>(Wj + (size_t)(v0 + r) * nin + u));
+                            acc[r] = fmaf(w.x, x.x, fmaf(w.y, x.y, fmaf(w.z, x.z, fmaf(w.w, x.w, acc[r]))));
+                        }
+                }
+            } else {
+                for (int u = lane; u < nin; u += 32) {
+                    const float x = s_v[u];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        if (v0 + r < nout) acc[r] = fmaf(__ldg(Wj + (size_t)(v0 + r) * nin + u), x, acc[r]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float t = warp_sum(acc[r]);
+                if (lane == 0 && v0 + r < nout) {
+                    const int v = v0 + r;
+                    const float zz = t + __ldg(a.bias[j] + v);
+                    s_z[off[j] + v] = zz;
+                    a.z[j][(size_t)b * nout + v] = zz;
+                }
             }
         }
         __syncthreads();
@@ -1069,10 +1094,39 @@ __global__ void __launch_bounds__(256) dense_head_kernel(HeadArgs a) {
     for (int j = a.n_dense - 1; j >= 1; --j) {
         const int nin = a.sizes[j - 1], nout = a.sizes[j];
         const float* Wj = a.W[j];
-        for (int u = tid; u < nin; u += 256) {
-            float acc = 0.f;
-            for (int v = 0; v < nout; ++v) acc = fmaf(__ldg(Wj + (size_t)v * nin + u), s_g[v], acc);   // coalesced over u
-            s_v[u] = acc * (s_z[off[j - 1] + u] > 0.f ? 1.f : a.alpha);
+        if (nin == 256 && nout % 4 == 0) {
+            // 64 column quads x 4 slices of the rows: 16-byte weight loads, partial sums combined in a fixed order
+            const int uq = (tid & 63) * 4, part = tid >> 6, per = nout / 4;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int v = part * per; v < (part + 1) * per; ++v) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(Wj + (size_t)v * nin + uq));
+                const float gv = s_g[v];
+                acc.x = fmaf(w.x, gv, acc.x); acc.y = fmaf(w.y, gv, acc.y); acc.z = fmaf(w.z, gv, acc.z); acc.w = fmaf(w.w, gv, acc.w);
+            }
+            __syncthreads();                               // s_g fully read
+            float* s_p = s_v;                              // [4][256] partials need 4 * nin floats: s_v + s_g hold 2 * max_size
+            if (part < 2) *reinterpret_cast<float4*>(s_p + part * 256 + uq) = acc;
+            __syncthreads();
+            if (part >= 2) {
+                float4 t = *reinterpret_cast<const float4*>(s_p + (part - 2) * 256 + uq);
+                t.x += acc.x; t.y += acc.y; t.z += acc.z; t.w += acc.w;
+                *reinterpret_cast<float4*>(s_p + (part - 2) * 256 + uq) = t;
+            }
+            __syncthreads();
+            {
+                const int u = tid;
+                const float t = s_p[u] + s_p[256 + u];
+                __syncthreads();
+                s_v[u] = t * (s_z[off[j - 1] + u] > 0.f ? 1.f : a.alpha);
+            }
+        } else {
+            for (int u = tid; u < nin; u += 256) {
+                float acc = 0.f;
+#pragma unroll 8
+                for (int v = 0; v < nout; ++v) acc = fmaf(__ldg(Wj + (size_t)v * nin + u), s_g[v], acc);   // coalesced over u
+                s_v[u] = acc * (s_z[off[j - 1] + u] > 0.f ? 1.f : a.alpha);
+            }
         }
         __syncthreads();
         for (int u = tid; u < nin; u += 256) s_g[u] = s_v[u];
@@ -1081,18 +1135,45 @@ __global__ void __launch_bounds__(256) dense_head_kernel(HeadArgs a) {
     // s_g now holds dz of layer 0 (dz1)
     if (a.dz1 != nullptr)
         for (int u = tid; u < n0; u += 256) a.dz1[(size_t)b * n0 + u] = s_g[u];
-    if (a.S != nullptr)
-        for (int k = tid; k < a.C; k += 256) {
-            float acc = 0.f;
-            for (int u = 0; u < n0; ++u) acc = fmaf(s_g[u], __ldg(a.S + (size_t)u * a.C + k), acc);
-            a.alpha_raw[(size_t)b * a.C + k] = acc;
+    if (a.S != nullptr) {
+        // alpha_raw[k] = sum_u dz1[u] S[u][k]: the u range is cut into `parts` slices so that all 256 threads work
+        // (C is 64 on the tensor path); partial sums are combined in a fixed order
+        if (a.C == 64 && n0 % 16 == 0 && a.max_size >= 256) {
+            // 16 channel quads x 16 slices of u: 16-byte loads of S; the two slices of a warp meet by shuffle, the 8 warps in smem
+            const int kq = (tid & 15) * 4, part = tid >> 4, per = n0 / 16;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int u = part * per; u < (part + 1) * per; ++u) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(a.S + (size_t)u * 64 + kq));
+                const float gv = s_g[u];
+                acc.x = fmaf(w.x, gv, acc.x); acc.y = fmaf(w.y, gv, acc.y); acc.z = fmaf(w.z, gv, acc.z); acc.w = fmaf(w.w, gv, acc.w);
+            }
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
+            __syncthreads();                               // every thread has finished reading s_g
+            if (lane < 16) *reinterpret_cast<float4*>(s_v + warp * 64 + kq) = acc;      // [8 warps][64]: 512 floats of scratch
+            __syncthreads();
+            if (tid < 64) {
+                float t = 0.f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) t += s_v[q * 64 + tid];
+                a.alpha_raw[(size_t)b * 64 + tid] = t;
+            }
+        } else {
+            for (int k = tid; k < a.C; k += 256) {
+                float acc = 0.f;
+#pragma unroll 8
+                for (int u = 0; u < n0; ++u) acc = fmaf(s_g[u], __ldg(a.S + (size_t)u * a.C + k), acc);
+                a.alpha_raw[(size_t)b * a.C + k] = acc;
+            }
         }
+    }
 }
 
 int launch_dense_head(const HeadArgs& a, int B, cudaStream_t s) {
     int total = 0;
     for (int j = 0; j < a.n_dense; ++j) total += a.sizes[j];
-    const size_t smem = (size_t)(total + 2 * a.max_size) * sizeof(float);
+    const size_t smem = (size_t)(total + 4 + 2 * a.max_size) * sizeof(float);
     BCAD_REQUIRE(smem <= 48 * 1024, "dense head: layer sizes too large for the fused kernel (%zu bytes)", smem);
     dense_head_kernel<<<B, 256, smem, s>>>(a);
     BCAD_CUDA_CHECK(cudaGetLastError());
