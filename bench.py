@@ -370,11 +370,13 @@ def run_ours(args, rank, world, local_rank):
     traffic_file = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if roof is not None and os.path.exists(traffic_file) and B == 512 and INPUT_SHAPE == (256, 256, 1):
         tr = json.load(open(traffic_file))
-        for kname, nbytes in tr.items():
-            if kname.split("<")[0] in {"conv_igemm_kernel": "conv1_igemm_tcgen05", "conv_first_tc_kernel": "conv0_first_tcgen05"} and \
-                    {"conv_igemm_kernel": "conv1_igemm_tcgen05", "conv_first_tc_kernel": "conv0_first_tcgen05"}[kname.split("<")[0]] == roof["kernel"]:
-                roof["traffic"] = nbytes
-                roof["traffic_source"] = "profiles/r01_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, per launch)"
+        x3 = precision == "fp16x3"
+        ncu_name = {"conv1_igemm_tcgen05": "conv_igemm_kernel<64, 64, 1>" if x3 else "conv_igemm_kernel<32, 64, 0>",
+                    "conv0_first_tcgen05": None if x3 else "conv_first_tc_kernel<32, 0>"}.get(roof["kernel"])
+        if ncu_name in tr:
+            roof["traffic"] = tr[ncu_name]
+            roof["traffic_source"] = (f"profiles/r01_traffic.json [{ncu_name}] (ncu --set full, dram__bytes_read.sum + "
+                                      "dram__bytes_write.sum, per launch)")
 
     cpu = None
     if not args.no_cpu_baseline:

@@ -300,6 +300,10 @@ int tensor_explain_chunk(Model& m, int n, const int32_t* class_idx, int grad_mod
         TP_LAUNCH(m, "alpha_shortcut_sgemm", launch_sgemm(dz1, t.d_S, t.alpha_raw, n, T.Cout, m.dense[0].out, false, 1, s));
     }
     const float inv_hw = 1.0f / ((float)T.Ho * (float)T.Wo);
+    if (tail_fused_supported(T.Ho, T.Wo, m.cfg.in_h, m.cfg.in_w, T.Cout) && getenv("BCAD_TAIL_TWO_KERNELS") == nullptr) {
+        TP_LAUNCH(m, "tail_fused", launch_tail_fused(t.act, t.alpha_raw, inv_hw, m.alpha, heat, n, T.Ho, T.Wo, m.cfg.in_h, m.cfg.in_w, T.Cout, t.x3, s));
+        return BCAD_OK;
+    }
     TP_LAUNCH(m, "cam_c8", launch_cam_c8(t.act, t.alpha_raw, inv_hw, m.alpha, m.cam_lo, m.mm, n, T.Ho, T.Wo, T.Cout, m.cam_splits, t.x3, s));
     TP_LAUNCH(m, "upsample_norm", launch_upsample_norm(m.cam_lo, m.mm, m.cam_splits, heat, n, T.Ho, T.Wo, m.cfg.in_h, m.cfg.in_w, s));
     return BCAD_OK;
