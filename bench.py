@@ -526,7 +526,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="images per GPU per step")
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "fp16", "fp16x3"])
-    ap.add_argument("--cpu-images", type=int, default=96, help="bounded CPU-baseline sample")
+    ap.add_argument("--cpu-images", type=int, default=1024, help="bounded CPU-baseline sample (~10 s of CPU work on 16 cores)")
     ap.add_argument("--ref-images", type=int, default=64, help="images per step of the --impl reference arm")
     ap.add_argument("--workload", default="explain", choices=["explain", "train"],
                     help="explain = the headline path (predict + Grad-CAM); train = the secondary training-step line")

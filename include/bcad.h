@@ -160,6 +160,12 @@ BCAD_API int bcad_conv_block(const float* x_dev, int B, int H, int W, int Cin, c
 /* non-overlapping mean pool, floor dims (Classes/ImageSegmentation.py:145-163): [B,H,W,C] -> [B,H/pool,W/pool,C] */
 BCAD_API int bcad_avg_pool(const float* x_dev, int B, int H, int W, int C, int pool, float* out_dev, void* stream);
 
+/* ---- feeding producer of the basic classifier (app.py:466-489 process_bottleneck_features) ----------------------------- */
+/* feat_dev: fp32 [B][C][H][W] (layout 0) or [B][H][W][C] (layout 1) -> cv2.resize(.., (out_w, out_h), INTER_LINEAR) ->
+ * out_dev fp32 [B][out_h][out_w][C].  Bit-exact with OpenCV 4.13's float paths (> 4 channels: float32 coordinates). */
+BCAD_API int bcad_bottleneck_resize(const float* feat_dev, int B, int C, int H, int W, int layout, int out_h, int out_w,
+                           float* out_dev, void* stream);
+
 /* ---- training step (BASELINE config 5): fp32 path, keep_all_activations=1 ------------------------ */
 /* Flat gradient vector: per conv block [W packed (k*k,Cin,CoutPad) | b (CoutPad)], then per dense layer [W (out,in) | b (out)]
  * -- the layouts the device weights live in, every tensor starting on a 128-byte boundary (bcad_grad_layout gives the

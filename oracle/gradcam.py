@@ -31,8 +31,13 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def bilinear_resize(src: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
-    """``cv2.resize(src.astype(float32), (out_w, out_h), interpolation=INTER_LINEAR)``.
+def bilinear_resize(src: np.ndarray, out_h: int, out_w: int, coords_f32: bool = False) -> np.ndarray:
+    """``cv2.resize(src.astype(float32), (out_w, out_h), interpolation=INTER_LINEAR)`` over the last two axes.
+
+    coords_f32: OpenCV 4.13 has two float32 code paths (measured, tests/golden/ref_bottleneck.npz + cv2_resize.npz):
+    images with <= 4 channels keep the source coordinate in double (default here: the Grad-CAM map is 1 channel); images with
+    more channels (the 64-channel bottleneck features of app.py:466-489) use the classic loop
+    ``fx = (float)((dx+0.5)*scale - 0.5); sx = cvFloor(fx); fx -= sx`` -- coordinate and weight in float32.
 
     Half-pixel centres ``s = (d+0.5)*(n_src/n_dst) - 0.5`` in double; ``i0=floor(s)``; weight =
     float32(s - i0); indices clamped to [0, n-1] with weight 0 (border replicate); separable; float32.
@@ -46,8 +51,10 @@ def bilinear_resize(src: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
         # fractional part rounded to float32 (measured against cv2: <= 1 ulp for every size tried;
         # float32 coordinates are 1.6e-6 off for non-power-of-two scales).
         s = (np.arange(n_dst, dtype=np.float64) + 0.5) * (np.float64(n_src) / np.float64(n_dst)) - 0.5
+        if coords_f32:
+            s = s.astype(np.float32)
         i0 = np.floor(s).astype(np.int64)
-        f = (s - i0).astype(np.float32)
+        f = (s - i0.astype(s.dtype)).astype(np.float32)
         # OpenCV: if i0 < 0 -> i0 = 0, f = 0 ; if i0 >= n-1 -> i0 = n-1, f = 0
         lo = i0 < 0
         hi = i0 >= n_src - 1
@@ -63,6 +70,15 @@ def bilinear_resize(src: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
     rows = rows.astype(np.float32)
     out = rows[..., y0, :] * (one - fy)[:, None] + rows[..., y1, :] * fy[:, None]
     return out.astype(np.float32)
+
+
+def process_bottleneck_features(feat, resize_shape=(32, 32)) -> np.ndarray:
+    """app.py:466-489: a [C,H,W] feature map (tensor, or ndarray with shape[0] < shape[2]) -> HWC, then
+    ``cv2.resize(feat, resize_shape, INTER_LINEAR)`` (dsize = (width, height)) -> float32 [h, w, C]."""
+    feat = np.asarray(feat, dtype=np.float32)
+    chw = feat if feat.shape[0] < feat.shape[2] else feat.transpose(2, 0, 1)
+    ow, oh = resize_shape
+    return np.ascontiguousarray(bilinear_resize(chw, oh, ow, coords_f32=chw.shape[0] > 4).transpose(1, 2, 0))
 
 
 def gradcam_tail(A: np.ndarray, dA: np.ndarray, out_hw, resize=bilinear_resize) -> np.ndarray:

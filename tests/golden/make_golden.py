@@ -204,6 +204,29 @@ def unet_case(name, shape, batch, seed):
     print("wrote", name, bn.shape, ap.shape)
 
 
+def bottleneck_case():
+    """process_bottleneck_features (WebApplicationPrototype/app.py:466-489), exec-loaded alone (app.py needs flask)."""
+    import types
+    import cv2
+    path = os.path.join(ref_loader.REF_ROOT, "WebApplicationPrototype", "app.py")
+    src = open(path, encoding="utf-8").read()
+    a = src.index("def process_bottleneck_features")
+    b = src.index("@app.route('/classify'")
+    mod = types.ModuleType("ref_app_slice")
+    mod.__dict__.update({"torch": torch, "np": np, "cv2": cv2})
+    exec(compile(src[a:b], path, "exec"), mod.__dict__)
+    rng = np.random.default_rng(51)
+    out = {}
+    f0 = rng.standard_normal((8, 64, 64)).astype(np.float32)                 # CHW tensor, scale 8 like 256 -> 32
+    out["feat0"], out["out0"] = f0, mod.process_bottleneck_features(torch.from_numpy(f0), resize_shape=(8, 8))
+    f1 = rng.standard_normal((5, 37, 50)).astype(np.float32)                 # CHW ndarray (shape[0] < shape[2]), odd sizes
+    out["feat1"], out["out1"] = f1, mod.process_bottleneck_features(f1, resize_shape=(11, 7))   # cv2 dsize = (width, height)
+    f2 = rng.standard_normal((20, 24, 6)).astype(np.float32)                 # already HWC (shape[0] >= shape[2]): resized as is
+    out["feat2"], out["out2"] = f2, mod.process_bottleneck_features(f2, resize_shape=(9, 10))
+    np.savez_compressed(os.path.join(HERE, "ref_bottleneck.npz"), **out)
+    print("wrote ref_bottleneck", out["out0"].shape, out["out1"].shape, out["out2"].shape)
+
+
 def cv2_cases():
     import cv2
     lut = cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(1, 256), cv2.COLORMAP_JET)[0]
@@ -231,4 +254,5 @@ if __name__ == "__main__":
     train_case("ref_numpy_train_dropout", (12, 12, 2), [(3, 3), (4, 3)], [8, 6], seed=42, n=4, dropout_rate=0.4)
     unet_case("ref_unet_small", (16, 16, 1), 2, seed=31)
     unet_case("ref_unet_odd", (21, 18, 2), 1, seed=32)
+    bottleneck_case()
     cv2_cases()

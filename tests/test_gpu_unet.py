@@ -54,3 +54,29 @@ def test_unet_front_feeds_the_cnn_full_size():
     assert np.abs(logits.cpu().numpy() - cache.logits.numpy()).max() <= 1e-4 * max(1.0, np.abs(cache.logits.numpy()).max())
     assert np.abs(heat.cpu().numpy() - o_heat).max() <= 1e-4
     eng.close()
+
+
+def test_process_bottleneck_features_matches_reference():
+    """app.py:466-489 outputs recorded from the reference (tests/golden/ref_bottleneck.npz): bit-exact."""
+    import os
+    import numpy as np
+    import torch
+    from util import GOLDEN
+    from bcad_b200 import bottleneck as bn
+    g = np.load(os.path.join(GOLDEN, "ref_bottleneck.npz"))
+    got0 = bn.process_bottleneck_features(torch.from_numpy(g["feat0"]), resize_shape=(8, 8))        # tensor: [C,H,W]
+    got1 = bn.process_bottleneck_features(g["feat1"], resize_shape=(11, 7))                         # ndarray CHW, odd sizes
+    got2 = bn.process_bottleneck_features(g["feat2"], resize_shape=(9, 10))                         # ndarray already HWC
+    for got, want in ((got0, g["out0"]), (got1, g["out1"]), (got2, g["out2"])):
+        assert got.shape == want.shape and got.dtype == np.float32
+        assert np.array_equal(got, want), float(np.abs(got - want).max())
+    # <= 4 channels take OpenCV's double-coordinate path (the Grad-CAM map's): checked against the oracle
+    from oracle import gradcam as ogc
+    rng = np.random.default_rng(5)
+    f = rng.standard_normal((3, 41, 29)).astype(np.float32)
+    want = ogc.process_bottleneck_features(f, (13, 17))
+    assert np.abs(bn.process_bottleneck_features(f, (13, 17)) - want).max() <= 1e-6
+    # batched entry point, 64 channels, 256 -> 32 like the app
+    fb = rng.standard_normal((2, 64, 256, 256)).astype(np.float32)
+    out = bn.resize_batch(fb, (32, 32)).cpu().numpy()
+    assert np.array_equal(out[1], ogc.process_bottleneck_features(fb[1], (32, 32)))

@@ -222,3 +222,12 @@ def test_training_oracle_dropout_matches_reference_fixture():
         np.testing.assert_allclose(gr["dense_w"][j], g[f"grad{li}_dW"], rtol=0, atol=1e-12)
     masked, _ = otr.mean_grads(cfg, p, g["X"], g["labels"], dropout=[mk[:, :8], mk[:, 8:]], dropout_in_backward=True)
     assert np.abs(masked["dense_w"][0] - g["grad4_dW"]).max() > 1e-3       # the autograd rule is a different function
+
+
+def test_bottleneck_resize_oracle_matches_reference_fixture():
+    """oracle.gradcam.process_bottleneck_features vs the reference's app.py:466-489 (cv2's > 4-channel float32-coordinate path
+    and the <= 4-channel double-coordinate path are different arithmetic; both pinned)."""
+    from oracle import gradcam as ogc
+    g = np.load(os.path.join(GOLDEN, "ref_bottleneck.npz"))
+    for i, rs in enumerate([(8, 8), (11, 7), (9, 10)]):
+        assert np.array_equal(ogc.process_bottleneck_features(g[f"feat{i}"], rs), g[f"out{i}"])

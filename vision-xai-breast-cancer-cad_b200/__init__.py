@@ -12,6 +12,7 @@ Modules mirror the reference files they stand in for:
 ``GRADCAM``            WebApplicationPrototype/GRADCAM.py
 ``ExplainableAI``      Classes/ExplainableAI.py
 ``unet``               Classes/unet.py layer functions (tiny U-Net encoder front)
+``bottleneck``         app.py:466-489 ``process_bottleneck_features`` (CHW -> HWC + cv2 bilinear resize)
 ``training``           data-parallel training step (wgrad kernels + one gradient all-reduce)
 ``engine``             batched / sharded driver over the libbcad C-ABI (include/bcad.h)
 =====================  ===========================================================

@@ -790,6 +790,13 @@ int bcad_conv_block(const float* x, int B, int H, int W, int Cin, const float* k
     return rc;
 }
 
+int bcad_bottleneck_resize(const float* feat_dev, int B, int C, int H, int W, int layout, int out_h, int out_w, float* out_dev, void* stream) {
+    BCAD_REQUIRE(feat_dev && out_dev, "bottleneck_resize: null pointer");
+    BCAD_REQUIRE(B >= 1 && C >= 1 && H >= 1 && W >= 1 && out_h >= 1 && out_w >= 1, "bottleneck_resize: bad shape");
+    BCAD_REQUIRE(layout == 0 || layout == 1, "bottleneck_resize: layout must be 0 (CHW) or 1 (HWC)");
+    return launch_bottleneck_resize(feat_dev, out_dev, B, C, H, W, layout == 0 ? 1 : 0, out_h, out_w, (cudaStream_t)stream);
+}
+
 int bcad_avg_pool(const float* x, int B, int H, int W, int C, int pool, float* out, void* stream) {
     BCAD_REQUIRE(x && out && B >= 1 && H >= 1 && W >= 1 && C >= 1 && pool >= 1, "avg_pool: bad argument");
     return launch_avg_pool(x, out, B, H, W, C, pool, (cudaStream_t)stream);

@@ -982,6 +982,59 @@ int launch_overlay(const float* img01, const float* cam, int B, int H, int W, ui
 }
 
 // =====================================================================================================
+// process_bottleneck_features (app.py:466-489): [C,H,W] (or [H,W,C]) -> cv2.resize(INTER_LINEAR) -> [h,w,C].
+// OpenCV's > 4-channel float path: source coordinate and weight in float32 (fx = (float)((dx+0.5)*scale-0.5); sx = floor;
+// fx -= sx), horizontal pass then vertical, no FMA contraction (bit-exact against tests/golden/ref_bottleneck.npz);
+// <= 4 channels: coordinate in double, weight = float(frac) as in the Grad-CAM tail.  thread = one output element, channel
+// fastest so the HWC stores are coalesced (only 4 source pixels per output are ever read: the pass is tiny).
+// =====================================================================================================
+__global__ void __launch_bounds__(256) bottleneck_resize_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int H,
+                                                                int W, int chw, int oh, int ow, size_t total) {
+    const bool f32c = C > 4;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        size_t r = i / C;
+        const int ox = (int)(r % ow);
+        r /= ow;
+        const int oy = (int)(r % oh);
+        const size_t b = r / oh;
+        auto coord = [&](int d, int ns, int nd, int& i0, int& i1, float& f) {
+            const double sd = ((double)d + 0.5) * ((double)ns / (double)nd) - 0.5;
+            if (f32c) {
+                const float sf = (float)sd;
+                const float fl = floorf(sf);
+                i0 = (int)fl;
+                f = __fsub_rn(sf, fl);
+            } else {
+                i0 = (int)floor(sd);
+                f = (float)(sd - (double)i0);
+            }
+            if (i0 < 0) { i0 = 0; f = 0.f; }
+            if (i0 >= ns - 1) { i0 = ns - 1; f = 0.f; }
+            i1 = min(i0 + 1, ns - 1);
+        };
+        int x0, x1, y0, y1;
+        float fx, fy;
+        coord(ox, W, ow, x0, x1, fx);
+        coord(oy, H, oh, y0, y1, fy);
+        const float* sb = src + b * (size_t)C * H * W;
+        auto at = [&](int y, int x) { return chw ? __ldg(sb + ((size_t)c * H + y) * W + x) : __ldg(sb + ((size_t)y * W + x) * C + c); };
+        const float gx = __fsub_rn(1.f, fx), gy = __fsub_rn(1.f, fy);
+        const float top = __fadd_rn(__fmul_rn(at(y0, x0), gx), __fmul_rn(at(y0, x1), fx));
+        const float bot = __fadd_rn(__fmul_rn(at(y1, x0), gx), __fmul_rn(at(y1, x1), fx));
+        dst[i] = __fadd_rn(__fmul_rn(top, gy), __fmul_rn(bot, fy));
+    }
+}
+
+int launch_bottleneck_resize(const float* src, float* dst, int B, int C, int H, int W, int chw, int oh, int ow, cudaStream_t s) {
+    const size_t total = (size_t)B * oh * ow * C;
+    const int blocks = (int)std::min<size_t>((size_t)148 * 8, (total + 255) / 256);
+    bottleneck_resize_kernel<<<blocks, 256, 0, s>>>(src, dst, C, H, W, chw, oh, ow, total);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+// =====================================================================================================
 // fused dense head (one CTA per image): fc1 split-K reduce + bias + LeakyReLU, the remaining dense layers,
 // probabilities / class, and -- when explaining -- the top gradient and the dense backward down to dz1
 // plus the Grad-CAM channel weights through the alpha shortcut  alpha_raw[k] = sum_u dz1[u] S[u][k].
