@@ -323,8 +323,11 @@ def run_ours(args, rank, world, local_rank):
     name = dom_key.split(":", 1)[1]
     if name.startswith("conv"):
         # conv kernels: conv0 = first block, conv1 = second block ...
-        li = 0 if "conv0" in name else 1
-        flops = fl[f"conv{li}"] * B
+        if name.startswith("conv01"):                     # both conv blocks in one kernel
+            flops = (fl["conv0"] + fl["conv1"]) * B
+        else:
+            li = 0 if "conv0" in name else 1
+            flops = fl[f"conv{li}"] * B
         peak = pk["bf16_tflops_sustained"]
         ach = flops / (dom_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
@@ -371,7 +374,7 @@ def run_ours(args, rank, world, local_rank):
     if roof is not None and os.path.exists(traffic_file) and B == 512 and INPUT_SHAPE == (256, 256, 1):
         tr = json.load(open(traffic_file))
         x3 = precision == "fp16x3"                       # the committed capture is of the fp16 mode
-        ncu_name = None if x3 else {"conv1_igemm_tcgen05": "conv_igemm_kernel<32, 64, 0>",
+        ncu_name = None if x3 else {"conv1_igemm_tcgen05": "conv_igemm_kernel<32, 64, 0>", "conv01_fused_tcgen05": "conv_fused_kernel",
                                     "conv0_first_tcgen05": "conv_first_tc_kernel<32, 0, 0>"}.get(roof["kernel"])
         if ncu_name in tr:
             roof["traffic"] = tr[ncu_name]

@@ -57,7 +57,7 @@ def test_tensor_path_intermediates_small():
     cfg = ocnn.NetConfig.torch_flavour((64, 64, 1), 2, [(32, 3), (64, 3)], [64, 32], 0.01)
     p = ocnn.init_params(cfg, seed=7, bias_std=0.05)
     x = ocnn.synth_images(5, (64, 64, 1), seed=1)
-    eng = engine_from(cfg, p, precision="fp16", max_batch=8)
+    eng = engine_from(cfg, p, precision="fp16", max_batch=8, keep_all_activations=True)   # the fused conv kernel writes P1 out only then
     cls, probs, logits = eng.predict(x)
     cache = ocnn.forward(cfg, p, x)
     p1 = _np(eng.get_tensor(_lib.T_POOL_OUT, 0, 5)).reshape(5, 32, 32, 32)
@@ -140,6 +140,32 @@ def test_tensor_path_multichannel_first_block(shape, convs, pad, B):
     assert np.abs(p1 - want).max() <= 1e-2 * max(1.0, np.abs(want).max()), "first block (fp16 operands, fp32 accumulate)"
     _check(cfg, p, x, eng, B)
     eng.close()
+
+
+def test_fused_and_two_kernel_conv_paths_agree(monkeypatch):
+    """The fused two-block kernel (default) and the conv0 + conv1 kernels compute the same network: logits and heat-maps agree
+    to fp16 rounding of the pooled first-block map (max-then-round vs round-then-max, LeakyReLU in half2), and the fused
+    path keeps that map on chip unless keep_all_activations is set."""
+    from bcad_b200 import _lib
+    cfg = ocnn.NetConfig.torch_flavour((96, 80, 1), 2, [(32, 3), (64, 3)], [64, 32], 0.01)
+    p = ocnn.init_params(cfg, seed=21, bias_std=0.05)
+    x = ocnn.synth_images(9, (96, 80, 1), seed=2)
+    eng = engine_from(cfg, p, precision="fp16", max_batch=16)
+    c1, p1, l1, h1 = eng.predict_explain(x, None, "logit")
+    with pytest.raises(RuntimeError, match="on chip"):
+        eng.get_tensor(_lib.T_POOL_OUT, 0, 9)
+    monkeypatch.setenv("BCAD_TWO_CONV_KERNELS", "1")
+    c2, p2, l2, h2 = eng.predict_explain(x, None, "logit")
+    pool_two = _np(eng.get_tensor(_lib.T_POOL_OUT, 0, 9))
+    monkeypatch.delenv("BCAD_TWO_CONV_KERNELS")
+    assert np.abs(_np(l1) - _np(l2)).max() <= 2e-3 * max(1.0, float(l2.abs().max()))
+    assert np.abs(_np(h1) - _np(h2)).max() <= 5e-3
+    eng.close()
+    engk = engine_from(cfg, p, precision="fp16", max_batch=16, keep_all_activations=True)
+    engk.predict(x)
+    pool_fused = _np(engk.get_tensor(_lib.T_POOL_OUT, 0, 9))
+    assert np.abs(pool_fused - pool_two).max() <= 2e-3 * max(1.0, np.abs(pool_two).max())
+    engk.close()
 
 
 def test_tensor_path_valid_conv_odd_sizes():

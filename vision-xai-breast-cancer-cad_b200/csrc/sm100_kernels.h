@@ -42,6 +42,24 @@ int conv_wide_rows_per_band(int Cout);
 int launch_conv_wide(const WideArgs& a, int CinPad, int Cout, int sms, cudaStream_t s);
 int launch_nhwc_to_c8(const float* x, __half* out, int B, int H, int W, int C, int CinPad, cudaStream_t s);
 
+// both conv blocks in one persistent kernel (sm100_fused.cu): Cin = 1 -> 32 -> 64 filters, fp16 mode, maps up to 128 px wide
+struct FusedArgs {
+    const float* x;               // fp32 [B][H][W]
+    const uint8_t* w0_img;        // first-block image [4 chunks][32][16 B] (as launch_conv_first_tc)
+    const uint8_t* w1_img;        // second-block weight image + bias tile (as IgemmArgs::w_img)
+    __half* act;                  // second-block activations, C8 planar, or nullptr
+    uint8_t* pool_fc;             // pooled second-block output as fc1 A tiles, or nullptr
+    __half* p1_out;               // optional copy of the pooled first-block output (C8 planar), nullptr = stays on chip
+    int B, H, W;                  // input
+    int H1, W1;                   // pooled first-block map = second-block input
+    int Ho, Wo, Hp, Wp, pad;      // second-block output / pooled dims
+    int bands, band_rows;
+    float alpha;
+    int debug;                    // timing experiments only: 1 no activation store, 2 no fc1-tile store, 16 first-block teams idle
+};
+bool conv_fused_supported(int Cin, int C0, int C1, int W1, int Wo1, bool x3);
+int launch_conv_fused(const FusedArgs& a, int sms, cudaStream_t s);
+
 struct FcArgs {
     const uint8_t* a_tiles;       // [m_tiles][nkb][128][128 B] SW128
     const uint8_t* w_tiles;       // [nkb][N][128 B] SW128

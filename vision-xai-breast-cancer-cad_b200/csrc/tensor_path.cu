@@ -41,6 +41,7 @@ struct TensorPath {
     float* alpha_raw = nullptr;     // [B][Cout] = dz1 . S
     int fc_splits = 1, kb_per_split = 1, m_pad = 128;
     bool x3 = false;                // fp16x3: hi/lo split operands everywhere (fp32-grade)
+    bool p1_valid = true;           // the last forward wrote the pooled first-block map to HBM (the fused kernel only does with keep_all_activations)
     bool wide = false;              // first block has Cin > 1: nhwc_to_c8 + conv_wide (sm100_wide.cu)
     int cin_pad = 0, kc = 0, groups = 0;
     uint8_t* d_w0_wide = nullptr;   // [G][9*(KC/8)][Cout0][16 B] + bias tile
@@ -235,6 +236,30 @@ int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const in
     TensorPath& t = *m.tp;
     const ConvLayer& c0 = m.conv[0];
     const ConvLayer& c1 = m.conv[1];
+    // both conv blocks in one persistent kernel when the shape allows (0.52 vs 0.25 + 0.35 ms at 512 x 256x256x1);
+    // BCAD_TWO_CONV_KERNELS=1 forces the two-kernel path (profiling comparisons)
+    const bool fuse = !t.wide && t.d_w0_img != nullptr && conv_fused_supported(c0.Cin, c0.Cout, c1.Cout, c1.W, c1.Wo, t.x3) &&
+                      getenv("BCAD_TWO_CONV_KERNELS") == nullptr;
+    if (fuse) {
+        FusedArgs f;
+        f.x = x; f.w0_img = t.d_w0_img; f.w1_img = t.d_w1_img; f.act = t.act; f.pool_fc = t.fc_a;
+        f.p1_out = m.cfg.keep_all_activations ? t.p1 : nullptr;          // the pooled first-block map normally never leaves the SM
+        t.p1_valid = (f.p1_out != nullptr);
+        f.B = n; f.H = c0.H; f.W = c0.W; f.H1 = c1.H; f.W1 = c1.W; f.Ho = c1.Ho; f.Wo = c1.Wo; f.Hp = c1.Hp; f.Wp = c1.Wp;
+        f.pad = m.cfg.pad;
+        f.band_rows = 64;
+        if (f.band_rows > c1.Ho) f.band_rows = cdiv(c1.Ho, 2) * 2;
+        f.bands = cdiv(c1.Ho, f.band_rows);
+        f.alpha = m.cfg.alpha_conv;
+        f.debug = 0;
+        if (const char* dbg = getenv("BCAD_DEBUG_SKIP_STORES")) {      // timing experiments only (results are garbage)
+            f.debug = atoi(dbg);
+            if (f.debug & 1) f.act = nullptr;
+            if (f.debug & 2) f.pool_fc = nullptr;
+        }
+        TP_LAUNCH(m, "conv01_fused_tcgen05", launch_conv_fused(f, t.sms, s));
+    } else {
+    t.p1_valid = true;
     if (t.wide) {
         TP_LAUNCH(m, "input_to_c8", launch_nhwc_to_c8(x, t.x_c8, n, c0.H, c0.W, c0.Cin, t.cin_pad, s));
         WideArgs w;
@@ -262,6 +287,7 @@ int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const in
         if (a.debug & 2) a.pool_fc = nullptr;
     }
     TP_LAUNCH(m, "conv1_igemm_tcgen05", launch_conv_igemm(a, t.x3 ? 2 * c1.Cin : c1.Cin, c1.Cout, t.x3, t.sms, s));
+    }
     // fc1
     DenseLayer& d0 = m.dense[0];
     FcArgs f;
@@ -316,6 +342,10 @@ int tensor_get_activation(Model& m, int kind, int index, int B, float* dst, cuda
         return launch_c8_to_nhwc(t.act, dst, B, L.Ho, L.Wo, L.Cout, t.x3, s);
     }
     if (kind == BCAD_T_POOL_OUT && index == 0) {
+        if (!t.p1_valid) {
+            set_error("get_tensor: the fused conv kernel keeps the pooled first-block map on chip; create the model with keep_all_activations=1 to have it written out");
+            return BCAD_ERR_STATE;
+        }
         const ConvLayer& L = m.conv[0];
         return launch_c8_to_nhwc(t.p1, dst, B, L.Hp, L.Wp, L.Cout, t.x3, s);
     }
