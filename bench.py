@@ -370,7 +370,7 @@ def run_ours(args, rank, world, local_rank):
                                       "equivalent_GBps": dense_bytes / max(1e-9, tail_ms * 1e-3) / 1e9,
                                       "note": "SURVEY 8d dense figure (read A, read dA, write fp32 map); this path derives alpha "
                                               "from dz1 and never materialises dA, so it moves fewer bytes than that"}}
-    traffic_file = os.path.join(ROOT, "profiles", "r01b_traffic.json")
+    traffic_file = os.path.join(ROOT, "profiles", "r01c_traffic.json")
     if roof is not None and os.path.exists(traffic_file) and B == 512 and INPUT_SHAPE == (256, 256, 1):
         tr = json.load(open(traffic_file))
         x3 = precision == "fp16x3"                       # the committed capture is of the fp16 mode
@@ -378,7 +378,7 @@ def run_ours(args, rank, world, local_rank):
                                     "conv0_first_tcgen05": "conv_first_tc_kernel<32, 0, 0>"}.get(roof["kernel"])
         if ncu_name in tr:
             roof["traffic"] = tr[ncu_name]
-            roof["traffic_source"] = (f"profiles/r01b_traffic.json [{ncu_name}] (ncu --set full, dram__bytes_read.sum + "
+            roof["traffic_source"] = (f"profiles/r01c_traffic.json [{ncu_name}] (ncu --set full, dram__bytes_read.sum + "
                                       "dram__bytes_write.sum, per launch)")
 
     cpu = None
