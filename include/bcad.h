@@ -76,7 +76,9 @@ typedef struct bcad_config {
     int32_t head;
     int32_t precision;
     int32_t max_batch;                      /* workspace is sized for this many images; larger calls are chunked */
-    int32_t keep_all_activations;           /* 1: also cache every conv block's pre-pool output (compat .layers, saliency) */
+    int32_t keep_all_activations;           /* 1: also cache every conv block's pre-pool output (compat .layers, saliency);
+                                             *    on the 16-bit path: also write out the pooled first-block map, which the fused
+                                             *    conv kernel otherwise keeps on chip (bcad_get_tensor(BCAD_T_POOL_OUT, 0)) */
     int32_t device;                         /* CUDA device ordinal */
 } bcad_config;
 
