@@ -138,6 +138,11 @@ BCAD_API int64_t bcad_tensor_elems(bcad_model* m, int kind, int index);
 BCAD_API int bcad_predict_explain_host(bcad_model* m, const float* x_host, int B, const int32_t* class_idx_host,
                               int grad_mode, float* logits_host, float* probs_host, int32_t* cls_host,
                               float* heatmap_host);
+/* Same call, heat-maps as heatmap_uint8 = (cam * 255).astype(uint8) (GRADCAM.py:70, truncating) [B,H,W]: the caller that
+ * only writes PNGs (app.py:715,750) gets a quarter of the device->host bytes (the call is PCIe-bound). */
+BCAD_API int bcad_predict_explain_host_u8(bcad_model* m, const float* x_host, int B, const int32_t* class_idx_host_or_null,
+                                 int grad_mode, float* logits_host, float* probs_host, int32_t* cls_host,
+                                 uint8_t* heat_u8_host);
 
 /* ---- stand-alone Grad-CAM tail (pytorch_grad_cam BaseCAM.forward / scale_cam_image) ------------ */
 /* A, dA: [B,h,w,K] NHWC device, dtype 0 = fp32, 1 = bf16; out: fp32 [B,H,W].

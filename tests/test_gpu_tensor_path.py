@@ -168,6 +168,21 @@ def test_fused_and_two_kernel_conv_paths_agree(monkeypatch):
     engk.close()
 
 
+def test_host_call_u8_heatmaps_are_truncated_float_maps():
+    """bcad_predict_explain_host_u8: heatmap_uint8 = (cam * 255).astype(uint8) of the float32 map (GRADCAM.py:70), chunked."""
+    cfg = ocnn.NetConfig.torch_flavour((64, 48, 1), 2, [(32, 3), (64, 3)], [32, 16], 0.01)
+    p = ocnn.init_params(cfg, seed=3, bias_std=0.05)
+    x = ocnn.synth_images(70, (64, 48, 1), seed=12)                     # > one 64-image host chunk
+    for precision in ("fp16", "fp32"):
+        eng = engine_from(cfg, p, precision=precision, max_batch=64)
+        c32, p32, l32, h32 = eng.predict_explain_host(x, None, "logit")
+        c8, p8, l8, h8 = eng.predict_explain_host(x, None, "logit", heat_dtype=np.uint8)
+        assert h8.dtype == np.uint8 and h8.shape == h32.shape
+        assert np.array_equal(h8, (h32 * np.float32(255)).astype(np.uint8))
+        assert np.array_equal(c8, c32) and np.array_equal(l8, l32)
+        eng.close()
+
+
 def test_tensor_path_valid_conv_odd_sizes():
     """pad=0 (valid) with odd maps: 61 -> 59 -> 29 -> 27 -> 13; first-index pooling, softmax head, HWC flatten."""
     cfg = ocnn.NetConfig((61, 61, 1), 2, [(32, 3), (64, 3)], [32], 0.01, 0.01, 0, "hwc", "first", "softmax")

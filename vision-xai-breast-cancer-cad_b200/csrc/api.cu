@@ -623,8 +623,8 @@ int bcad_get_tensor(bcad_model* mm, int kind, int index, int B, float* dst, void
 // -----------------------------------------------------------------------------------------------------
 // host-buffer end-to-end call: H2D / compute / D2H in chunks on three streams, double-buffered
 // -----------------------------------------------------------------------------------------------------
-int bcad_predict_explain_host(bcad_model* mm, const float* x_host, int B, const int32_t* class_idx_host, int grad_mode,
-                              float* logits_host, float* probs_host, int32_t* cls_host, float* heat_host) {
+static int predict_explain_host_impl(bcad_model* mm, const float* x_host, int B, const int32_t* class_idx_host, int grad_mode,
+                                     float* logits_host, float* probs_host, int32_t* cls_host, float* heat_host, uint8_t* heat_u8_host) {
     Model* m = reinterpret_cast<Model*>(mm);
     BCAD_REQUIRE(m && x_host, "predict_explain_host: null argument");
     BCAD_REQUIRE(B >= 1, "batch must be >= 1, got %d", B);
@@ -657,6 +657,8 @@ int bcad_predict_explain_host(bcad_model* mm, const float* x_host, int B, const 
             X.chunk = chunk;
             X.inited = true;
         }
+        if (heat_u8_host != nullptr && X.heat8[0] == nullptr)
+            for (int i = 0; i < 2; ++i) BCAD_TRY(m->alloc((void**)&X.heat8[i], (size_t)X.chunk * hm));
     }
     // small outputs go through pinned staging sized for the whole call
     const size_t per_img = (size_t)(2 * nc) * sizeof(float) + sizeof(int32_t);
@@ -706,12 +708,15 @@ int bcad_predict_explain_host(bcad_model* mm, const float* x_host, int B, const 
             BCAD_CUDA_CHECK(cudaMemcpyAsync(X.cidx[slot], class_idx_host + b0, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, X.s_in));
         BCAD_CUDA_CHECK(cudaEventRecord(X.in_done[slot], X.s_in));
         BCAD_CUDA_CHECK(cudaStreamWaitEvent(X.s_compute, X.in_done[slot], 0));
-        int rc = run(m, X.x[slot], n, class_idx_host ? X.cidx[slot] : nullptr, grad_mode, heat_host != nullptr, X.logits[slot],
+        const bool want_heat = (heat_host != nullptr || heat_u8_host != nullptr);
+        int rc = run(m, X.x[slot], n, class_idx_host ? X.cidx[slot] : nullptr, grad_mode, want_heat, X.logits[slot],
                      X.probs[slot], X.cls[slot], X.heat[slot], X.s_compute);
+        if (rc == BCAD_OK && heat_u8_host != nullptr) rc = launch_heat_to_u8(X.heat[slot], X.heat8[slot], (size_t)n * hm, X.s_compute);
         if (rc != BCAD_OK) { cudaDeviceSynchronize(); return rc; }
         BCAD_CUDA_CHECK(cudaEventRecord(X.compute_done[slot], X.s_compute));
         BCAD_CUDA_CHECK(cudaStreamWaitEvent(X.s_out, X.compute_done[slot], 0));
         if (heat_host) BCAD_CUDA_CHECK(cudaMemcpyAsync(heat_host + (size_t)b0 * hm, X.heat[slot], (size_t)n * hm * sizeof(float), cudaMemcpyDeviceToHost, X.s_out));
+        if (heat_u8_host) BCAD_CUDA_CHECK(cudaMemcpyAsync(heat_u8_host + (size_t)b0 * hm, X.heat8[slot], (size_t)n * hm, cudaMemcpyDeviceToHost, X.s_out));
         BCAD_CUDA_CHECK(cudaMemcpyAsync(st_logits + (size_t)b0 * nc, X.logits[slot], (size_t)n * nc * sizeof(float), cudaMemcpyDeviceToHost, X.s_out));
         BCAD_CUDA_CHECK(cudaMemcpyAsync(st_probs + (size_t)b0 * nc, X.probs[slot], (size_t)n * nc * sizeof(float), cudaMemcpyDeviceToHost, X.s_out));
         BCAD_CUDA_CHECK(cudaMemcpyAsync(st_cls + b0, X.cls[slot], (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, X.s_out));
@@ -723,6 +728,17 @@ int bcad_predict_explain_host(bcad_model* mm, const float* x_host, int B, const 
     if (probs_host) memcpy(probs_host, st_probs, (size_t)B * nc * sizeof(float));
     if (cls_host) memcpy(cls_host, st_cls, (size_t)B * sizeof(int32_t));
     return BCAD_OK;
+}
+
+int bcad_predict_explain_host(bcad_model* mm, const float* x_host, int B, const int32_t* class_idx_host, int grad_mode,
+                              float* logits_host, float* probs_host, int32_t* cls_host, float* heat_host) {
+    return predict_explain_host_impl(mm, x_host, B, class_idx_host, grad_mode, logits_host, probs_host, cls_host, heat_host, nullptr);
+}
+
+int bcad_predict_explain_host_u8(bcad_model* mm, const float* x_host, int B, const int32_t* class_idx_host, int grad_mode,
+                                 float* logits_host, float* probs_host, int32_t* cls_host, uint8_t* heat_u8_host) {
+    BCAD_REQUIRE(heat_u8_host, "predict_explain_host_u8: null heat-map pointer");
+    return predict_explain_host_impl(mm, x_host, B, class_idx_host, grad_mode, logits_host, probs_host, cls_host, nullptr, heat_u8_host);
 }
 
 // -----------------------------------------------------------------------------------------------------

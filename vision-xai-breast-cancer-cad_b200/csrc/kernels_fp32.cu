@@ -974,6 +974,26 @@ overlay_kernel(const float* __restrict__ img01, const float* __restrict__ cam, i
     }
 }
 
+// heatmap_uint8 = (cam * 255).astype(np.uint8)  (GRADCAM.py:70: truncation), 4 pixels per thread
+__global__ void __launch_bounds__(256) heat_to_u8_kernel(const float* __restrict__ cam, uint8_t* __restrict__ out, size_t n) {
+    const size_t n4 = n / 4;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = ldg_stream(reinterpret_cast<const float4*>(cam) + i);
+        uchar4 o;
+        o.x = (uint8_t)(int)(v.x * 255.f); o.y = (uint8_t)(int)(v.y * 255.f); o.z = (uint8_t)(int)(v.z * 255.f); o.w = (uint8_t)(int)(v.w * 255.f);
+        reinterpret_cast<uchar4*>(out)[i] = o;
+    }
+    for (size_t i = n4 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (uint8_t)(int)(cam[i] * 255.f);
+}
+
+int launch_heat_to_u8(const float* cam, uint8_t* out, size_t n, cudaStream_t s) {
+    const int blocks = (int)std::min<size_t>((size_t)148 * 8, (n / 4 + 255) / 256 + 1);
+    heat_to_u8_kernel<<<blocks, 256, 0, s>>>(cam, out, n);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
 int launch_overlay(const float* img01, const float* cam, int B, int H, int W, uint8_t* overlay_rgb, uint8_t* heat_u8,
                    cudaStream_t s) {
     overlay_kernel<<<B, 1024, 0, s>>>(img01, cam, H, W, overlay_rgb, heat_u8);

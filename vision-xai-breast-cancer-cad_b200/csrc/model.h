@@ -52,6 +52,7 @@ struct Xfer {                          // host-buffer pipeline (bcad_predict_exp
     cudaEvent_t in_done[2] = {nullptr, nullptr}, compute_done[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
     float* x[2] = {nullptr, nullptr};
     float* heat[2] = {nullptr, nullptr};
+    uint8_t* heat8[2] = {nullptr, nullptr};   // u8 heat-maps of a chunk (bcad_predict_explain_host_u8), allocated on first use
     float* logits[2] = {nullptr, nullptr};
     float* probs[2] = {nullptr, nullptr};
     int32_t* cls[2] = {nullptr, nullptr};

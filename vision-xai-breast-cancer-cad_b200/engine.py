@@ -336,9 +336,12 @@ class Engine:
 
     # ------------------------------------------------------------------ hot path, host buffers (end to end)
     def predict_explain_host(self, x: np.ndarray, class_idx: Optional[np.ndarray] = None, grad_mode: str = "logit",
-                             heat_out: Optional[np.ndarray] = None, want_heat: bool = True):
+                             heat_out: Optional[np.ndarray] = None, want_heat: bool = True, heat_dtype=np.float32):
         """x: float32 [B,H,W,C] host array (pinned memory makes the copies asynchronous).
-        -> (cls int32 [B], probs [B,nc], logits [B,nc], heat [B,H,W]) as host arrays."""
+        -> (cls int32 [B], probs [B,nc], logits [B,nc], heat [B,H,W]) as host arrays.
+        heat_dtype=np.uint8 returns ``heatmap_uint8 = (cam * 255).astype(uint8)`` (GRADCAM.py:70) instead of the float32 map:
+        a quarter of the device->host bytes of a PCIe-bound call."""
+        u8 = np.dtype(heat_dtype) == np.uint8
         h, w, c = self.spec.input_shape
         if x.dtype != np.float32 or not x.flags["C_CONTIGUOUS"]:
             x = np.ascontiguousarray(x, dtype=np.float32)
@@ -352,12 +355,14 @@ class Engine:
         cls = np.empty((B,), np.int32)
         heat = None
         if want_heat:
-            heat = heat_out if heat_out is not None else np.empty((B, h, w), np.float32)
+            heat = heat_out if heat_out is not None else np.empty((B, h, w), np.uint8 if u8 else np.float32)
+            if heat.dtype != (np.uint8 if u8 else np.float32) or not heat.flags["C_CONTIGUOUS"]:
+                raise ValueError("heat_out must be a C-contiguous array of heat_dtype")
         ci = None
         if class_idx is not None:
             ci = np.ascontiguousarray(np.broadcast_to(np.asarray(class_idx, dtype=np.int32).reshape(-1), (B,)))
-        _lib.check(self.lib.bcad_predict_explain_host(self._h, _ptr(x), B, _ptr(ci), _lib.GRAD_MODE[grad_mode],
-                                                      _ptr(logits), _ptr(probs), _ptr(cls), _ptr(heat)))
+        fn = self.lib.bcad_predict_explain_host_u8 if (u8 and want_heat) else self.lib.bcad_predict_explain_host
+        _lib.check(fn(self._h, _ptr(x), B, _ptr(ci), _lib.GRAD_MODE[grad_mode], _ptr(logits), _ptr(probs), _ptr(cls), _ptr(heat)))
         return cls, probs, logits, heat
 
 
