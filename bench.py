@@ -129,9 +129,38 @@ def oracle_setup():
     return ocnn, cfg, params
 
 
+_ALL_CPUS = None
+
+
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this rank's host thread (and therefore its pinned staging buffers, first-touched next) to the CPUs NVML reports as
+    local to the GPU: with several ranks per node the host<->device copies of the e2e leg stay off the inter-socket link."""
+    global _ALL_CPUS
+    try:
+        import pynvml
+        if _ALL_CPUS is None:
+            _ALL_CPUS = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1} & _ALL_CPUS
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception as e:                                  # affinity is an optimisation, never a requirement
+        log(f"[bench] NUMA binding skipped: {e}")
+    return None
+
+
 def use_all_host_threads():
     """torchrun exports OMP_NUM_THREADS=1; the CPU baseline is meant to use every host core."""
     import torch
+    if _ALL_CPUS is not None:
+        try:
+            os.sched_setaffinity(0, _ALL_CPUS)
+        except Exception:
+            pass
     n = os.cpu_count() or 1
     try:
         torch.set_num_threads(n)
@@ -205,6 +234,8 @@ def run_ours(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        bind_to_gpu_numa_node(local_rank)
     ocnn, cfg, params = oracle_setup()
     B = args.batch
     spec = bcad_b200.NetSpec.torch_flavour(INPUT_SHAPE, NUM_CLASSES, CONV_LAYERS, HIDDEN, 0.01)
