@@ -122,10 +122,42 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+# synthetic workload -- generated HERE, not by oracle/: the product arm never touches the oracle except for the
+# untimed `check` below (the checker) and the cpu_baseline leg
+# ------------------------------------------------------------------------------------------------
+def synth_weights(seed=7):
+    """Random-init weights of the ADCNNM-flavour network with the reference's own initialisers (He-normal conv
+    Classes/CNNModel.py:94, Glorot-uniform dense :131-132, zero biases), seeded.  Layouts: conv (F,k,k,C), dense (units, C*H*W)."""
+    rng = np.random.default_rng(seed)
+    conv_w, conv_b, dense_w, dense_b = [], [], [], []
+    h, w, c = INPUT_SHAPE
+    for f, k in CONV_LAYERS:
+        conv_w.append(rng.standard_normal((f, k, k, c)) * np.sqrt(2.0 / (k * k * c)))
+        conv_b.append(np.zeros(f))
+        h, w, c = h // 2, w // 2, f                           # same-pad conv + 2x2 pool
+    prev = h * w * c
+    for units in HIDDEN + [NUM_CLASSES]:
+        lim = np.sqrt(6.0 / (prev + units))
+        dense_w.append(rng.uniform(-lim, lim, (units, prev)))
+        dense_b.append(np.zeros(units))
+        prev = units
+    return conv_w, conv_b, dense_w, dense_b
+
+
+def synth_images(n, shape, seed):
+    """Per-image standardised float32 [n,H,W,C] (the reference normalises its inputs: Classes/ImageSegmentation.py:229-232)."""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n,) + tuple(shape)).astype(np.float32)
+    mean = x.mean(axis=(1, 2, 3), keepdims=True)
+    std = x.std(axis=(1, 2, 3), keepdims=True)
+    return ((x - mean) / std).astype(np.float32)
+
+
 def oracle_setup():
+    """Checker / CPU-baseline legs only: the oracle's view (config + Params) of the same synthetic weights."""
     from oracle import cnn as ocnn
     cfg = ocnn.NetConfig.torch_flavour(INPUT_SHAPE, NUM_CLASSES, CONV_LAYERS, HIDDEN, 0.01)
-    params = ocnn.init_params(cfg, seed=7, bias_std=0.0)      # reference initialisers, seeded
+    params = ocnn.Params(*synth_weights())
     return ocnn, cfg, params
 
 
@@ -191,7 +223,7 @@ def run_reference(args, rank, world):
     from oracle import cpu_port
     from oracle import cnn as ocnn
     model = cpu_port.build(cfg, params)
-    x = torch.from_numpy(ocnn.synth_images(n_per_step, INPUT_SHAPE, seed=20251018))
+    x = torch.from_numpy(synth_images(n_per_step, INPUT_SHAPE, seed=20251018))
 
     def step():
         for s in range(0, n_per_step, 32):
@@ -236,7 +268,7 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         bind_to_gpu_numa_node(local_rank)
-    ocnn, cfg, params = oracle_setup()
+    conv_w, conv_b, dense_w, dense_b = synth_weights()
     B = args.batch
     spec = bcad_b200.NetSpec.torch_flavour(INPUT_SHAPE, NUM_CLASSES, CONV_LAYERS, HIDDEN, 0.01)
     precision = args.precision
@@ -253,11 +285,11 @@ def run_ours(args, rank, world, local_rank):
     if eng is None:
         eng = bcad_b200.Engine(spec, precision="fp32", max_batch=B, device=local_rank)
         precision = "fp32"
-    eng.set_weights(params.conv_w, params.conv_b, params.dense_w, params.dense_b)
+    eng.set_weights(conv_w, conv_b, dense_w, dense_b)
 
     # synthetic inputs: distinct per rank (seed + rank); generated once, resident in HBM for `value`
     n_unique = min(B, 64)
-    base = ocnn.synth_images(n_unique, INPUT_SHAPE, seed=20251018 + rank)
+    base = synth_images(n_unique, INPUT_SHAPE, seed=20251018 + rank)
     reps = (B + n_unique - 1) // n_unique
     x_host = torch.from_numpy(np.concatenate([base] * reps, axis=0)[:B].copy()).pin_memory()
     x_dev = x_host.to(dev)
@@ -341,6 +373,7 @@ def run_ours(args, rank, world, local_rank):
     check = None
     if not args.no_check:
         from oracle import gradcam as ogc
+        ocnn, cfg, params = oracle_setup()
         k = 4
         xs = x_host[:k].numpy()
         cache = ocnn.forward(cfg, params, xs)
@@ -465,13 +498,12 @@ def run_train(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    ocnn, cfg, params = oracle_setup()
     B = args.train_batch
     spec = bcad_b200.NetSpec.torch_flavour(INPUT_SHAPE, NUM_CLASSES, CONV_LAYERS, HIDDEN, 0.01)
     eng = bcad_b200.Engine(spec, precision="fp32", max_batch=B, keep_all_activations=True, device=local_rank)
-    eng.set_weights(params.conv_w, params.conv_b, params.dense_w, params.dense_b)
+    eng.set_weights(*synth_weights())
     tr = DataParallelTrainer(eng, opt="adam", lr=1e-4)
-    x_host = torch.from_numpy(ocnn.synth_images(B, INPUT_SHAPE, seed=777 + rank)).pin_memory()
+    x_host = torch.from_numpy(synth_images(B, INPUT_SHAPE, seed=777 + rank)).pin_memory()
     y_host = torch.from_numpy((np.arange(B) % 2).astype(np.int32)).pin_memory()
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
 
