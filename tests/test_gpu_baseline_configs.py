@@ -1,0 +1,93 @@
+"""The BASELINE.json configurations that are parity cases rather than bench lines, at their full sizes, through
+size-independent properties (+ the oracle on a few images).
+
+cfg 1: 245 synthetic 256x256 images in batches of 32 (7 x 32 + 21: a ragged last batch)
+cfg 3: U-Net front -> CNN -> Grad-CAM -> overlay   (the shape flow is in test_gpu_unet.py; here the overlay stage is added)
+cfg 4: 8192 images, sharded / chunked
+"""
+import numpy as np
+import pytest
+import torch
+
+from util import engine_from, oracle_heatmaps, ocnn
+
+pytestmark = pytest.mark.gpu
+
+
+def _canonical():
+    cfg = ocnn.NetConfig.torch_flavour((256, 256, 1), 2, [(32, 3), (64, 3)], [256, 128], 0.01)
+    return cfg, ocnn.init_params(cfg, seed=7, bias_std=0.0)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp16", 1e-2), ("fp32", 1e-4)])
+def test_cfg1_245_images_in_batches_of_32(precision, tol):
+    cfg, p = _canonical()
+    x = ocnn.synth_images(245, (256, 256, 1), seed=20251018)
+    eng32 = engine_from(cfg, p, precision=precision, max_batch=32)          # 7 x 32 + 21
+    cls, probs, logits, heat = eng32.predict_explain(x, None, "logit")
+    cls, logits, heat = cls.cpu().numpy(), logits.cpu().numpy(), heat.cpu().numpy()
+    assert heat.shape == (245, 256, 256) and np.isfinite(heat).all() and heat.min() >= 0.0 and heat.max() <= 1.0
+    assert np.all(heat.reshape(245, -1).max(axis=1) > 0.999)               # every map is min-max normalised
+    # batching must not matter: the ragged 21-image batch and a single image, run on their own, reproduce their slices bit for bit
+    c21, p21, l21, h21 = eng32.predict_explain(x[224:], None, "logit")
+    assert np.array_equal(cls[224:], c21.cpu().numpy()) and np.array_equal(logits[224:], l21.cpu().numpy())
+    assert np.array_equal(heat[224:], h21.cpu().numpy())
+    c1, p1, l1, h1 = eng32.predict_explain(x[100:101], None, "logit")
+    assert np.array_equal(logits[100:101], l1.cpu().numpy()) and np.array_equal(heat[100:101], h1.cpu().numpy())
+    # a handle with another max_batch splits fc1's K range differently (another fixed summation order): equal to rounding
+    eng_big = engine_from(cfg, p, precision=precision, max_batch=256)
+    c2, p2, l2, h2 = eng_big.predict_explain(x, None, "logit")
+    assert np.abs(logits - l2.cpu().numpy()).max() <= 2e-5 * max(1.0, np.abs(logits).max())
+    big_err = np.abs(heat - h2.cpu().numpy()).reshape(245, -1).max(axis=1)
+    assert np.sort(big_err)[:-3].max() <= 1e-4, np.sort(big_err)[-5:]       # (a rounding-level logit change can flip a LeakyReLU kink)
+    # the ragged tail against the oracle (images 224..244 live in the 21-image batch)
+    idx = np.array([0, 31, 32, 224, 244])
+    o_cls, cache, A, dA, o_heat = oracle_heatmaps(cfg, p, x[idx], None, "logit")
+    lg = cache.logits.numpy()
+    assert np.abs(logits[idx] - lg).max() <= tol * max(1.0, np.abs(lg).max())
+    margin = np.abs(lg[:, 0] - lg[:, 1])
+    safe = margin > 4 * tol * max(1.0, np.abs(lg).max())
+    assert np.array_equal(cls[idx][safe], o_cls[safe])
+    err = np.abs(heat[idx] - o_heat).reshape(len(idx), -1).max(axis=1)
+    assert np.sort(err)[:-1].max() <= tol, err                              # at most one LeakyReLU-kink image (DESIGN: 16-bit caveat)
+    eng32.close()
+    eng_big.close()
+
+
+def test_cfg4_8192_images_chunked_host_call():
+    """8192 images through the host-buffer call (64-image transfer chunks, max_batch 512): 128 copies of 64 distinct images --
+    every copy must reproduce the first bit for bit, whatever chunk / position it lands in, and match a 64-image call."""
+    cfg, p = _canonical()
+    base = ocnn.synth_images(64, (256, 256, 1), seed=99)
+    x = np.ascontiguousarray(np.broadcast_to(base[None], (128, 64, 256, 256, 1)).reshape(8192, 256, 256, 1))
+    eng = engine_from(cfg, p, precision="fp16", max_batch=512)
+    cls, probs, logits, heat = eng.predict_explain_host(x, None, "logit", heat_dtype=np.uint8)
+    ref_c, ref_p, ref_l, ref_h = eng.predict_explain_host(base, None, "logit", heat_dtype=np.uint8)
+    assert np.array_equal(cls.reshape(128, 64), np.broadcast_to(ref_c, (128, 64)))
+    assert np.array_equal(logits.reshape(128, 64, 2), np.broadcast_to(ref_l, (128, 64, 2)))
+    assert np.array_equal(heat.reshape(128, 64, 256, 256), np.broadcast_to(ref_h, (128, 64, 256, 256)))
+    # and the device-buffer call over 512-image chunks agrees with the host call
+    xd = torch.from_numpy(x[:1024]).cuda()
+    c2, p2, l2, h2 = eng.predict_explain(xd, None, "logit")
+    assert np.array_equal(c2.cpu().numpy(), cls[:1024]) and np.array_equal(l2.cpu().numpy(), logits[:1024])
+    assert np.array_equal((h2 * 255).to(torch.uint8).cpu().numpy(), heat[:1024])
+    eng.close()
+
+
+def test_cfg3_overlay_stage_after_gradcam():
+    """show_cam_on_image + heatmap_uint8 on the Grad-CAM maps of the canonical network vs the oracle (GRADCAM.py:67,70)."""
+    import bcad_b200
+    from oracle import gradcam as ogc
+    cfg, p = _canonical()
+    x = ocnn.synth_images(4, (256, 256, 1), seed=3)
+    eng = engine_from(cfg, p, precision="fp32", max_batch=4)
+    cls, probs, logits, heat = eng.predict_explain(x, None, "logit")
+    img01 = torch.from_numpy((x[..., 0] - x.min()) / (x.max() - x.min())).cuda()            # grey image in [0,1]
+    ov, hu = bcad_b200.overlay(img01, heat)
+    heat_np, img_np = heat.cpu().numpy(), img01.cpu().numpy()
+    for i in range(4):
+        want_ov = ogc.show_cam_on_image(np.repeat(img_np[i][..., None], 3, axis=-1), heat_np[i])
+        diff = np.abs(ov[i].cpu().numpy().astype(np.int16) - want_ov.astype(np.int16))
+        assert diff.max() <= 1 and (diff > 0).mean() < 0.01                  # +-1 only at float32 rounding boundaries
+        assert np.array_equal(hu[i].cpu().numpy(), ogc.heatmap_u8(heat_np[i]))
+    eng.close()
