@@ -410,6 +410,10 @@ def run_ours(args, rank, world, local_rank):
         roof = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": None, "peak_source": pk["source"] + " (sustained bf16 cuBLAS)",
                 "algorithmic_flops_per_launch": flops}
+        if name.startswith("conv01"):
+            roof["note"] = ("both conv blocks in ONE kernel: FLOPs of block 1 (K = 9 taps, CUDA-core-bound im2col) + block 2 over the kernel's "
+                            "time; as two kernels (BCAD_TWO_CONV_KERNELS=1) block 2 alone reaches 0.64 of peak, both together 0.40 "
+                            "(profiles/r01b_bench_1gpu.json)")
     elif "sgemm" in name or "fc" in name:
         flops = 2.0 * (INPUT_SHAPE[0] // 4) * (INPUT_SHAPE[1] // 4) * CONV_LAYERS[-1][0] * HIDDEN[0] * B
         peak = pk["bf16_tflops_sustained"]
