@@ -31,6 +31,7 @@ INPUT_SHAPE = (256, 256, 1)
 CONV_LAYERS = [(32, 3), (64, 3)]
 HIDDEN = [256, 128]
 NUM_CLASSES = 2
+FLAVOUR = "torch"          # "numpy": the reference's NumPy CNN (valid conv, HWC flatten, tie-duplicating pool, softmax) -- secondary line
 
 
 def log(*a):
@@ -54,7 +55,9 @@ def algorithmic_flops_per_image():
     fl = {}
     cin = c
     for i, (f, k) in enumerate(CONV_LAYERS):
-        fl[f"conv{i}"] = 2.0 * h * w * f * k * k * cin       # same-pad: output map == input map
+        if FLAVOUR == "numpy":
+            h, w = h - k + 1, w - k + 1                       # valid conv
+        fl[f"conv{i}"] = 2.0 * h * w * f * k * k * cin       # (same-pad: output map == input map)
         h, w, cin = h // 2, w // 2, f
     flat = h * w * cin
     prev, dense = flat, 0.0
@@ -134,7 +137,9 @@ def synth_weights(seed=7):
     for f, k in CONV_LAYERS:
         conv_w.append(rng.standard_normal((f, k, k, c)) * np.sqrt(2.0 / (k * k * c)))
         conv_b.append(np.zeros(f))
-        h, w, c = h // 2, w // 2, f                           # same-pad conv + 2x2 pool
+        if FLAVOUR == "numpy":
+            h, w = h - k + 1, w - k + 1                       # valid conv
+        h, w, c = h // 2, w // 2, f                           # (same-pad conv for the torch flavour) + 2x2 pool
     prev = h * w * c
     for units in HIDDEN + [NUM_CLASSES]:
         lim = np.sqrt(6.0 / (prev + units))
@@ -156,7 +161,8 @@ def synth_images(n, shape, seed):
 def oracle_setup():
     """Checker / CPU-baseline legs only: the oracle's view (config + Params) of the same synthetic weights."""
     from oracle import cnn as ocnn
-    cfg = ocnn.NetConfig.torch_flavour(INPUT_SHAPE, NUM_CLASSES, CONV_LAYERS, HIDDEN, 0.01)
+    mk = ocnn.NetConfig.numpy_flavour if FLAVOUR == "numpy" else ocnn.NetConfig.torch_flavour
+    cfg = mk(INPUT_SHAPE, NUM_CLASSES, CONV_LAYERS, HIDDEN, 0.01)
     params = ocnn.Params(*synth_weights())
     return ocnn, cfg, params
 
@@ -252,6 +258,11 @@ def run_reference(args, rank, world):
 def workload_config(batch, precision):
     h, w, c = INPUT_SHAPE
     tag = "cfg2" if INPUT_SHAPE == (256, 256, 1) else "secondary shape (SURVEY 8d)"
+    if FLAVOUR == "numpy":
+        return {"workload": f"secondary line: NumPy-flavour CNN of Classes/CNNModel.py (conv 32,64 k3 valid; HWC flatten; tie-duplicating "
+                            f"pool; softmax head; fc 256,128; random init) predict+Grad-CAM(last conv, predicted class, softmax-CE top "
+                            f"gradient), {h}x{w}x{c} fp32 NHWC, batch {batch} per GPU",
+                "batch_per_gpu": batch, "precision_path": precision, "l2_policy": "inputs + activations per step exceed the 126 MB L2"}
     return {"workload": f"{tag}: ADCNNM-flavour CNN (conv 32,64 k3 pad1; fc 256,128; {NUM_CLASSES} classes; random init) "
                         f"predict+Grad-CAM(last conv, predicted class), {h}x{w}x{c} fp32 NHWC, batch {batch} per GPU",
             "batch_per_gpu": batch, "precision_path": precision,
@@ -270,11 +281,12 @@ def run_ours(args, rank, world, local_rank):
         bind_to_gpu_numa_node(local_rank)
     conv_w, conv_b, dense_w, dense_b = synth_weights()
     B = args.batch
-    spec = bcad_b200.NetSpec.torch_flavour(INPUT_SHAPE, NUM_CLASSES, CONV_LAYERS, HIDDEN, 0.01)
+    mk_spec = bcad_b200.NetSpec.numpy_flavour if FLAVOUR == "numpy" else bcad_b200.NetSpec.torch_flavour
+    spec = mk_spec(INPUT_SHAPE, NUM_CLASSES, CONV_LAYERS, HIDDEN, 0.01)
     precision = args.precision
     eng = None
     if precision in ("auto", "fp16", "fp16x3"):
-        want = "fp16" if precision == "auto" else precision
+        want = ("fp16x3" if FLAVOUR == "numpy" else "fp16") if precision == "auto" else precision
         try:
             eng = bcad_b200.Engine(spec, precision=want, max_batch=B, device=local_rank)
             precision = want
@@ -296,21 +308,23 @@ def run_ours(args, rank, world, local_rank):
     heat_dev = torch.empty((B, INPUT_SHAPE[0], INPUT_SHAPE[1]), device=dev, dtype=torch.float32)
     heat_host = torch.empty((B, INPUT_SHAPE[0], INPUT_SHAPE[1]), dtype=torch.float32).pin_memory()
 
+    GRAD = "softmax_ce" if FLAVOUR == "numpy" else "logit"       # the top gradient each reference API uses
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
     def step_dev():
-        return eng.predict_explain(x_dev, None, "logit", out_heat=heat_dev)
+        return eng.predict_explain(x_dev, None, GRAD, out_heat=heat_dev)
 
     def step_host():
-        return eng.predict_explain_host(x_host.numpy(), None, "logit", heat_out=heat_host.numpy())
+        return eng.predict_explain_host(x_host.numpy(), None, GRAD, heat_out=heat_host.numpy())
 
     heat8_host = torch.empty((B, INPUT_SHAPE[0], INPUT_SHAPE[1]), dtype=torch.uint8).pin_memory()
 
     def step_host_u8():      # same call, heat-maps as heatmap_uint8 (GRADCAM.py:70): informational, NOT the headline e2e
-        return eng.predict_explain_host(x_host.numpy(), None, "logit", heat_out=heat8_host.numpy(), heat_dtype=np.uint8)
+        return eng.predict_explain_host(x_host.numpy(), None, GRAD, heat_out=heat8_host.numpy(), heat_dtype=np.uint8)
 
     # ---- device-resident throughput (value)
     for _ in range(args.warmup):
@@ -378,7 +392,9 @@ def run_ours(args, rank, world, local_rank):
         xs = x_host[:k].numpy()
         cache = ocnn.forward(cfg, params, xs)
         o_cls = cache.logits.argmax(dim=-1).numpy()
-        cag, _, _ = ocnn.backward(cfg, params, cache, ocnn.top_gradient(cache, o_cls, "logit"), through_input=False)
+        score = cache.probs if cfg.head == "softmax" else cache.logits
+        o_cls = score.argmax(dim=-1).numpy()
+        cag, _, _ = ocnn.backward(cfg, params, cache, ocnn.top_gradient(cache, o_cls, GRAD), through_input=False)
         o_heat = ogc.gradcam_tail_nhwc(cache.conv_out[-1].numpy().astype(np.float32), cag[1].numpy().astype(np.float32), INPUT_SHAPE[:2])
         d_heat = heat[:k].float().cpu().numpy()
         check = {"images": k, "vs": "float64 oracle (oracle/cnn.py + oracle/gradcam.py)",
@@ -618,11 +634,15 @@ def main():
     ap.add_argument("--workload", default="explain", choices=["explain", "train"],
                     help="explain = the headline path (predict + Grad-CAM); train = the secondary training-step line")
     ap.add_argument("--train-batch", type=int, default=64, help="images per GPU per training step")
+    ap.add_argument("--flavour", default="torch", choices=["torch", "numpy"],
+                    help="numpy = SECONDARY line on the reference's NumPy CNN (tie-duplicating pool): fp16x3 tensor path + fp32 tail")
     ap.add_argument("--input-shape", default=None, help="H,W,C of a SECONDARY shape (SURVEY 8d: 256,256,64 or 64,256,256); "
                                                         "the headline line uses the default 256,256,1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the (untimed) oracle check of the first images")
     args = ap.parse_args()
+    global FLAVOUR
+    FLAVOUR = args.flavour
     if args.input_shape:
         global INPUT_SHAPE
         INPUT_SHAPE = tuple(int(v) for v in args.input_shape.split(","))

@@ -41,7 +41,8 @@ extern "C" {
 /* cfg.precision */
 #define BCAD_PREC_FP32 0           /* fp32 CUDA-core path, any shape */
 #define BCAD_PREC_F16 1            /* 16-bit tcgen05 tensor-core path (fp16 operands, fp32 accumulate) where the shape allows */
-#define BCAD_PREC_F16X3 2          /* tensor-core path with hi+lo fp16 split operands (3 MMAs per product): fp32-grade results */
+#define BCAD_PREC_F16X3 2          /* tensor-core path with hi+lo fp16 split operands (3 MMAs per product): fp32-grade results;
+                                    * the only tensor mode that accepts BCAD_TIES_ALL (the rule compares activations for equality) */
 /* grad_mode: gradient injected at the network output for the explanation */
 #define BCAD_GRAD_LOGIT 0          /* d(logit_c): pytorch_grad_cam ClassifierOutputTarget, GRADCAM.py:64 */
 #define BCAD_GRAD_SOFTMAX_CE 1     /* probs - onehot(c): explainability.py:21-22 */

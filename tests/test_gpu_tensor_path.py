@@ -196,7 +196,7 @@ def test_tensor_path_valid_conv_odd_sizes():
 def test_tensor_path_rejects_unsupported_shapes():
     import bcad_b200
     from util import spec_from_cfg
-    cfg = ocnn.NetConfig.numpy_flavour((32, 32, 1), 2, [(32, 3), (64, 3)], [32])        # tie-duplicating pool
+    cfg = ocnn.NetConfig.numpy_flavour((32, 32, 1), 2, [(32, 3), (64, 3)], [32])        # tie-duplicating pool: fp16x3 or fp32 only
     with pytest.raises(ValueError, match="TIES_FIRST"):
         bcad_b200.Engine(spec_from_cfg(cfg), precision="fp16")
     cfg = ocnn.NetConfig.torch_flavour((32, 32, 3), 2, [(32, 3), (64, 3)], [32])
@@ -264,4 +264,40 @@ def test_fp16x3_path_is_fp32_grade(shape, hidden, B, mb, pad):
     err_h = np.abs(_np(heat) - o_heat).max(axis=(1, 2))
     assert flipped.sum() <= max(1, B // 50)
     assert err_h[~flipped].max(initial=0.0) <= X3_HEAT_TOL, f"heatmap err {err_h}"
+    eng.close()
+
+
+@pytest.mark.parametrize("shape,hidden,B,kind", [
+    ((64, 64, 1), [64, 32], 6, "gauss"),
+    ((61, 57, 1), [32], 5, "gauss"),
+    ((48, 48, 1), [48, 16], 6, "mammo"),          # exact-zero background: real pool ties
+])
+def test_numpy_flavour_on_the_split_operand_tensor_path(shape, hidden, B, kind):
+    """The tie-duplicating NumPy CNN (valid conv, HWC flatten, softmax head) with precision fp16x3: convs / fc1 on tcgen05 with
+    fp32-grade activations, Grad-CAM weights from the dense pooled gradient with tie counts (fp32 tail).  Same tie-aware
+    comparison as the fp32 path's test (the rule compares activations for equality)."""
+    from bcad_b200 import _lib
+    from util import _switches_from, near_tie_windows
+    cfg = ocnn.NetConfig.numpy_flavour(shape, 2, [(32, 3), (64, 3)], hidden, 0.01)
+    p = ocnn.init_params(cfg, seed=11, bias_std=0.05)
+    x = ocnn.synth_images(B, shape, seed=31, kind=kind)
+    eng = engine_from(cfg, p, precision="fp16x3", max_batch=8)
+    assert eng.uses_tensor_path
+    for class_idx, mode in ((None, "softmax_ce"), (np.arange(B) % 2, "logit")):
+        cls, probs, logits, heat = eng.predict_explain(x, class_idx, mode)
+        A_ties = _np(eng.get_tensor(_lib.T_CONV_OUT, 1, B)).reshape(B, *cfg.shapes()[0][1][0])
+        o_cls, cache, A, dA, o_heat = oracle_heatmaps(cfg, p, x, class_idx, mode)
+        sw_dev, sw_or = _switches_from(A_ties, cfg.pool_ties), cache.switches[-1].numpy()
+        if not np.array_equal(sw_dev, sw_or):
+            h2, w2 = A.shape[1] // 2, A.shape[2] // 2
+            diff_win = (sw_dev != sw_or)[:, :2 * h2, :2 * w2].reshape(B, h2, 2, w2, 2, -1).any(axis=(2, 4))
+            assert np.all(near_tie_windows(cache.conv_out[1].numpy(), rel=1e-5)[diff_win]), "tie structure differs beyond fp32-grade rounding"
+            o_cls, cache, A, dA, o_heat = oracle_heatmaps(cfg, p, x, class_idx, mode, A_for_ties=A_ties)
+        lg = cache.logits.numpy()
+        assert np.array_equal(_np(cls), o_cls)
+        assert np.abs(_np(logits) - lg).max() <= X3_LOGIT_TOL * max(1.0, np.abs(lg).max())
+        assert np.abs(_np(probs) - cache.probs.numpy()).max() <= X3_LOGIT_TOL
+        flipped = _kink_flips(eng, cache, B)
+        assert flipped.sum() <= 1
+        assert np.abs(_np(heat) - o_heat).max(axis=(1, 2))[~flipped].max(initial=0.0) <= X3_HEAT_TOL
     eng.close()

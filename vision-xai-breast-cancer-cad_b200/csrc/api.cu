@@ -291,7 +291,9 @@ int bcad_commit(bcad_model* mm) {
     }
     for (size_t j = 0; j < m->dense.size(); ++j) {
         DenseLayer& D = m->dense[j];
-        if (!(m->tensor_path && j == 0))   // the tensor path keeps fc1 in bf16 only (126-134 MB instead of 3x that)
+        // the tensor path keeps fc1 as 16-bit tiles only (126-134 MB instead of 3x that) -- unless the tie-duplicating pool rule
+        // is on: its Grad-CAM weights need the dense pooled gradient, i.e. the fp32 fc1 input-gradient GEMM
+        if (!(m->tensor_path && j == 0 && m->cfg.pool_ties == BCAD_TIES_FIRST))
             BCAD_TRY(upload(m, &D.d_w, D.h_w));
         BCAD_TRY(upload(m, &D.d_b, D.h_b));
     }
@@ -318,7 +320,7 @@ int bcad_commit(bcad_model* mm) {
         BCAD_TRY(m->alloc((void**)&m->cls, (size_t)mb * sizeof(int32_t)));
         BCAD_TRY(m->alloc((void**)&m->d_top, (size_t)mb * m->cfg.num_classes * sizeof(float)));
         m->fused_head = fused_head_ok(m);
-        if (!m->tensor_path) BCAD_TRY(m->alloc((void**)&m->g_flat, (size_t)mb * m->flat * sizeof(float)));
+        if (!m->tensor_path || m->cfg.pool_ties != BCAD_TIES_FIRST) BCAD_TRY(m->alloc((void**)&m->g_flat, (size_t)mb * m->flat * sizeof(float)));
         const ConvLayer& T = m->conv.back();
         m->alpha_splits = alpha_pool_splits(T.Hp);
         m->cam_splits = cam_splits(T.Ho);

@@ -980,27 +980,91 @@ int launch_cam_c8(const __half* A, const float* alpha_raw, float scale, float* a
     return BCAD_OK;
 }
 
-// C8-planar fp16 [B][h][C/8][w][8] -> NHWC fp32 (compat / inspection only)
-__global__ void c8_to_nhwc_kernel(const __half* __restrict__ src, float* __restrict__ dst, int h, int w, int C, int x3,
-                                  size_t total) {
-    const int planes = (x3 ? 2 : 1) * (C / 8);
+// Grad-CAM channel weights under the tie-duplicating pool rule, straight from the split (hi + lo) C8-planar activations:
+//   alpha_raw[b][k] = sum over pool windows of g[b, window, k] * (number of window elements equal to the window maximum)
+// (Classes/CNNModel.py:260,274-275: every tie receives the gradient; the dense map dA never exists).  g: fp32 NHWC pooled
+// gradient [B][Hp][Wp][C].  One CTA per image, warp = channel octet (C = 64: 8 warps), lanes across windows; the activation value
+// is hi + lo in fp32 -- the same number c8_to_nhwc_kernel reports, so the equality structure is the one the tests see.
+__global__ void __launch_bounds__(256) alpha_ties_c8_kernel(const __half* __restrict__ A, const float* __restrict__ g,
+                                                            float* __restrict__ alpha_raw, int h, int w, int C) {
+    const int octets = C / 8, planes = 2 * octets;
+    const int Hp = h / 2, Wp = w / 2;
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint4* base = reinterpret_cast<const uint4*>(A) + (size_t)b * h * planes * w;
+    const float* gb = g + (size_t)b * Hp * Wp * C;
+    for (int o = warp; o < octets; o += nwarps) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int wy = 0; wy < Hp; ++wy)
+            for (int wx = lane; wx < Wp; wx += 32) {
+                float v[4][8];
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int cx = 0; cx < 2; ++cx) {
+                        const uint4* p = base + ((size_t)(2 * wy + r) * planes + o) * w + 2 * wx + cx;
+                        const uint4 qh = ldg_stream_u4(p), ql = ldg_stream_u4(p + (size_t)octets * w);
+                        const float2 h0 = unpack_f16(qh.x), h1 = unpack_f16(qh.y), h2 = unpack_f16(qh.z), h3 = unpack_f16(qh.w);
+                        const float2 l0 = unpack_f16(ql.x), l1 = unpack_f16(ql.y), l2 = unpack_f16(ql.z), l3 = unpack_f16(ql.w);
+                        float* d = v[r * 2 + cx];
+                        d[0] = h0.x + l0.x; d[1] = h0.y + l0.y; d[2] = h1.x + l1.x; d[3] = h1.y + l1.y;
+                        d[4] = h2.x + l2.x; d[5] = h2.y + l2.y; d[6] = h3.x + l3.x; d[7] = h3.y + l3.y;
+                    }
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gb + ((size_t)wy * Wp + wx) * C + o * 8));
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gb + ((size_t)wy * Wp + wx) * C + o * 8) + 1);
+                const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float m = fmaxf(fmaxf(v[0][j], v[1][j]), fmaxf(v[2][j], v[3][j]));
+                    const int cnt = (v[0][j] == m) + (v[1][j] == m) + (v[2][j] == m) + (v[3][j] == m);
+                    acc[j] = fmaf(gv[j], (float)cnt, acc[j]);
+                }
+            }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float t = warp_sum(acc[j]);
+            if (lane == 0) alpha_raw[(size_t)b * C + o * 8 + j] = t;
+        }
+    }
+}
+
+int launch_alpha_ties_c8(const __half* A, const float* g, float* alpha_raw, int B, int h, int w, int C, cudaStream_t s) {
+    BCAD_REQUIRE(C % 8 == 0, "alpha_ties_c8: channel count %d", C);
+    alpha_ties_c8_kernel<<<B, 256, 0, s>>>(A, g, alpha_raw, h, w, C);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+// C8-planar fp16 [B][h][C/8][w][8] (fp16x3: octets [hi | lo]) -> NHWC fp32.  thread = (pixel, channel octet), octet fastest: a
+// warp writes 1 KB of contiguous output and reads 64 contiguous bytes from each plane (inspection calls and the fp32 tail of the
+// tie-duplicating mode)
+__global__ void __launch_bounds__(256) c8_to_nhwc_kernel(const __half* __restrict__ src, float* __restrict__ dst, int w, int C, int x3,
+                                                         size_t rows) {
+    const int octets = C / 8, planes = (x3 ? 2 : 1) * octets;
+    const size_t per_row = (size_t)octets * w, total = rows * per_row;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        size_t r = i / C;
-        const int x = (int)(r % w); r /= w;
-        const int y = (int)(r % h);
-        const size_t b = r / h;
-        const size_t row = (b * h + y) * planes;
-        float v = __half2float(src[(((row + (c >> 3)) * w + x) << 3) + (c & 7)]);
-        if (x3) v += __half2float(src[(((row + (C / 8) + (c >> 3)) * w + x) << 3) + (c & 7)]);
-        dst[i] = v;
+        const size_t row = i / per_row;
+        const int rem = (int)(i - row * per_row);
+        const int x = rem / octets, o = rem - x * octets;          // octet fastest: a warp writes 1 KB of contiguous NHWC floats
+        const uint4* base = reinterpret_cast<const uint4*>(src) + (row * planes) * w;
+        const uint4 q = ldg_stream_u4(base + (size_t)o * w + x);
+        float2 f0 = unpack_f16(q.x), f1 = unpack_f16(q.y), f2 = unpack_f16(q.z), f3 = unpack_f16(q.w);
+        if (x3) {
+            const uint4 ql = ldg_stream_u4(base + (size_t)(octets + o) * w + x);
+            const float2 g0 = unpack_f16(ql.x), g1 = unpack_f16(ql.y), g2 = unpack_f16(ql.z), g3 = unpack_f16(ql.w);
+            f0.x += g0.x; f0.y += g0.y; f1.x += g1.x; f1.y += g1.y; f2.x += g2.x; f2.y += g2.y; f3.x += g3.x; f3.y += g3.y;
+        }
+        float4* out = reinterpret_cast<float4*>(dst + (row * w + x) * C + o * 8);
+        out[0] = make_float4(f0.x, f0.y, f1.x, f1.y);
+        out[1] = make_float4(f2.x, f2.y, f3.x, f3.y);
     }
 }
 
 int launch_c8_to_nhwc(const __half* src, float* dst, int B, int h, int w, int C, bool x3, cudaStream_t s) {
-    const size_t total = (size_t)B * h * w * C;
+    const size_t total = (size_t)B * h * w * (C / 8);
     const int blocks = (int)min((size_t)148 * 16, (total + 255) / 256);
-    c8_to_nhwc_kernel<<<blocks, 256, 0, s>>>(src, dst, h, w, C, x3 ? 1 : 0, total);
+    c8_to_nhwc_kernel<<<blocks, 256, 0, s>>>(src, dst, w, C, x3 ? 1 : 0, (size_t)B * h);
     BCAD_CUDA_CHECK(cudaGetLastError());
     return BCAD_OK;
 }

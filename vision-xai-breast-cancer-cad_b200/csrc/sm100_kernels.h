@@ -77,6 +77,8 @@ int launch_cam_c8(const __half* A, const float* alpha_raw, float scale, float* a
 bool tail_fused_supported(int h, int w, int H, int W, int C);
 int launch_tail_fused(const __half* A, const float* alpha_raw, float scale, float* alpha_out, float* out, int B, int h, int w,
                       int H, int W, int C, bool x3, cudaStream_t s);
+// tie-duplicating rule on the fp16x3 path: alpha_raw[b][k] = sum_windows g * (#maxima in the window), A = split C8-planar activations
+int launch_alpha_ties_c8(const __half* A, const float* g_pool, float* alpha_raw, int B, int h, int w, int C, cudaStream_t s);
 int launch_c8_to_nhwc(const __half* src, float* dst, int B, int h, int w, int C, bool x3, cudaStream_t s);
 
 }  // namespace bcad

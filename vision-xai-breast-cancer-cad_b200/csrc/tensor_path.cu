@@ -78,8 +78,13 @@ int tensor_path_supported(const Model& m) {
     BCAD_REQUIRE(c1.k == 3 && c1.Cout == 64, "precision=F16: second conv block must be 3x3 with 64 filters (got k=%d, %d)", c1.k, c1.Cout);
     BCAD_REQUIRE(c.pad == 0 || c.pad == 1, "precision=F16: pad must be 0 or 1");
     BCAD_REQUIRE(c.alpha_conv <= 1.f, "precision=F16: conv LeakyReLU slope must be <= 1 (max(v, alpha v) form)");
-    BCAD_REQUIRE(c.pool_ties == BCAD_TIES_FIRST,
-                 "precision=F16: the alpha shortcut needs first-index pooling (TIES_FIRST); the tie-duplicating NumPy flavour runs on BCAD_PREC_FP32");
+    // tie-duplicating pool rule (the NumPy CNN): the Grad-CAM weights need per-window tie counts, taken from activations that
+    // must be fp32-grade (the rule compares for equality) -> only the split-operand mode, with an fp32 tail
+    BCAD_REQUIRE(c.pool_ties == BCAD_TIES_FIRST || c.precision == BCAD_PREC_F16X3,
+                 "precision=F16: the alpha shortcut needs first-index pooling (TIES_FIRST); the tie-duplicating NumPy flavour runs on "
+                 "BCAD_PREC_F16X3 or BCAD_PREC_FP32");
+    BCAD_REQUIRE(c.pool_ties == BCAD_TIES_FIRST || m.dense.size() > 1,
+                 "precision=F16X3 with the tie-duplicating rule needs at least one hidden dense layer");
     if (c.precision == BCAD_PREC_F16X3)
         BCAD_REQUIRE(c0.Cin == 1 && c0.Cout == 32, "precision=F16X3: the split-operand path needs 32 first-block filters (got %d)", c0.Cout);
     const int units = m.dense[0].out;
@@ -297,6 +302,9 @@ int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const in
     TP_LAUNCH(m, "fc1_splitk_tcgen05", launch_fc_splitk(f, s));
     if (m.fused_head) {
         // reduce + dense tail + class + (explain) backward to dz1 + alpha shortcut, one launch
+        if (m.cfg.pool_ties != BCAD_TIES_FIRST)              // dz1 stays in dense[0].h for the fp32 tail; no alpha shortcut
+            return launch_fused_head(&m, n, t.fc_part, t.fc_splits, (size_t)t.m_pad * d0.out, explain, class_idx, grad_mode,
+                                     explain ? d0.h : nullptr, nullptr, 0, nullptr, s);
         return launch_fused_head(&m, n, t.fc_part, t.fc_splits, (size_t)t.m_pad * d0.out, explain, class_idx, grad_mode,
                                  nullptr, t.d_S, c1.Cout, t.alpha_raw, s);
     }
@@ -319,6 +327,14 @@ int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const in
 int tensor_explain_chunk(Model& m, int n, const int32_t* class_idx, int grad_mode, float* heat, cudaStream_t s) {
     TensorPath& t = *m.tp;
     const ConvLayer& T = m.conv.back();
+    if (m.cfg.pool_ties != BCAD_TIES_FIRST) {
+        // tie-duplicating rule (the NumPy CNN): no alpha shortcut -- dz1 -> dense pooled gradient (fp32 GEMM with the fp32 fc1
+        // weights) -> alpha with per-window tie counts read from the split activations; alpha_raw then feeds the usual tail
+        if (!m.fused_head) TP_TRY(dense_backward(&m, n, class_idx, grad_mode, nullptr, s));          // leaves dz1 in dense[0].h
+        DenseLayer& D0 = m.dense[0];
+        TP_LAUNCH(m, "fc1_dgrad_sgemm", launch_sgemm(D0.h, D0.d_w, m.g_flat, n, D0.in, D0.out, false, 1, s));
+        TP_LAUNCH(m, "alpha_ties_c8", launch_alpha_ties_c8(t.act, m.g_flat, t.alpha_raw, n, T.Ho, T.Wo, T.Cout, s));
+    } else
     if (!m.fused_head) {
         // dense backward down to dz1 (left in dense[0].h); no fc1 dgrad GEMM, no dA
         TP_TRY(dense_backward(&m, n, class_idx, grad_mode, nullptr, s));
