@@ -34,12 +34,15 @@ def test_cfg1_245_images_in_batches_of_32(precision, tol):
     assert np.array_equal(heat[224:], h21.cpu().numpy())
     c1, p1, l1, h1 = eng32.predict_explain(x[100:101], None, "logit")
     assert np.array_equal(logits[100:101], l1.cpu().numpy()) and np.array_equal(heat[100:101], h1.cpu().numpy())
-    # a handle with another max_batch splits fc1's K range differently (another fixed summation order): equal to rounding
+    # a handle with another max_batch splits fc1's K range differently (another fixed summation order), and in the 16-bit mode a
+    # handle sized for 256 images runs the fused conv kernel while one sized for 32 runs the two conv kernels (the pooled
+    # first-block map is rounded to fp16 at a different point): equal to the rounding of the mode
     eng_big = engine_from(cfg, p, precision=precision, max_batch=256)
     c2, p2, l2, h2 = eng_big.predict_explain(x, None, "logit")
-    assert np.abs(logits - l2.cpu().numpy()).max() <= 2e-5 * max(1.0, np.abs(logits).max())
+    rnd = 2e-3 if precision == "fp16" else 2e-5
+    assert np.abs(logits - l2.cpu().numpy()).max() <= rnd * max(1.0, np.abs(logits).max())
     big_err = np.abs(heat - h2.cpu().numpy()).reshape(245, -1).max(axis=1)
-    assert np.sort(big_err)[:-3].max() <= 1e-4, np.sort(big_err)[-5:]       # (a rounding-level logit change can flip a LeakyReLU kink)
+    assert np.sort(big_err)[:-3].max() <= 5 * rnd, np.sort(big_err)[-5:]    # (a rounding-level logit change can flip a LeakyReLU kink)
     # the ragged tail against the oracle (images 224..244 live in the 21-image batch)
     idx = np.array([0, 31, 32, 224, 244])
     o_cls, cache, A, dA, o_heat = oracle_heatmaps(cfg, p, x[idx], None, "logit")

@@ -151,9 +151,11 @@ def test_fused_and_two_kernel_conv_paths_agree(monkeypatch):
     p = ocnn.init_params(cfg, seed=21, bias_std=0.05)
     x = ocnn.synth_images(9, (96, 80, 1), seed=2)
     eng = engine_from(cfg, p, precision="fp16", max_batch=16)
+    monkeypatch.setenv("BCAD_FUSED_CONV", "1")                  # (small calls use the two kernels unless forced)
     c1, p1, l1, h1 = eng.predict_explain(x, None, "logit")
     with pytest.raises(RuntimeError, match="on chip"):
         eng.get_tensor(_lib.T_POOL_OUT, 0, 9)
+    monkeypatch.delenv("BCAD_FUSED_CONV")
     monkeypatch.setenv("BCAD_TWO_CONV_KERNELS", "1")
     c2, p2, l2, h2 = eng.predict_explain(x, None, "logit")
     pool_two = _np(eng.get_tensor(_lib.T_POOL_OUT, 0, 9))
@@ -162,6 +164,7 @@ def test_fused_and_two_kernel_conv_paths_agree(monkeypatch):
     assert np.abs(_np(h1) - _np(h2)).max() <= 5e-3
     eng.close()
     engk = engine_from(cfg, p, precision="fp16", max_batch=16, keep_all_activations=True)
+    monkeypatch.setenv("BCAD_FUSED_CONV", "1")
     engk.predict(x)
     pool_fused = _np(engk.get_tensor(_lib.T_POOL_OUT, 0, 9))
     assert np.abs(pool_fused - pool_two).max() <= 2e-3 * max(1.0, np.abs(pool_two).max())
@@ -181,6 +184,23 @@ def test_host_call_u8_heatmaps_are_truncated_float_maps():
         assert np.array_equal(h8, (h32 * np.float32(255)).astype(np.uint8))
         assert np.array_equal(c8, c32) and np.array_equal(l8, l32)
         eng.close()
+
+
+@pytest.mark.parametrize("shape,pad,hidden,B", [
+    ((64, 64, 1), 1, [64, 32], 5),
+    ((61, 61, 1), 0, [32], 4),               # valid conv, odd maps: 61 -> 59 -> 29 -> 27 -> 13
+    ((256, 256, 1), 1, [256, 128], 3),       # canonical shape: two 64-row bands per image
+    ((32, 200, 1), 1, [48, 16], 150),        # short, wide maps; more work items than SMs
+])
+def test_fused_conv_kernel_forced(monkeypatch, shape, pad, hidden, B):
+    """The fused two-block kernel on small calls too (by default it takes over once a call has >= one work item per SM)."""
+    monkeypatch.setenv("BCAD_FUSED_CONV", "1")
+    cfg = ocnn.NetConfig(shape, 2, [(32, 3), (64, 3)], hidden, 0.01, 0.01, pad, "chw", "first", "logits")
+    p = ocnn.init_params(cfg, seed=17, bias_std=0.05)
+    x = ocnn.synth_images(B, shape, seed=6)
+    eng = engine_from(cfg, p, precision="fp16", max_batch=max(8, B))
+    _check(cfg, p, x, eng, B)
+    eng.close()
 
 
 def test_tensor_path_valid_conv_odd_sizes():

@@ -243,8 +243,12 @@ int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const in
     const ConvLayer& c1 = m.conv[1];
     // both conv blocks in one persistent kernel when the shape allows (0.52 vs 0.25 + 0.35 ms at 512 x 256x256x1);
     // BCAD_TWO_CONV_KERNELS=1 forces the two-kernel path (profiling comparisons)
+    // The choice is a property of the HANDLE (max_batch), not of the call, so that chunked == un-chunked and host call == device
+    // call stay bit-identical: handles sized for fewer work items than SMs keep the two kernels, where the first block spreads
+    // better on its own (0.216 vs 0.244 ms for a single image end to end).
+    const int fuse_bands = cdiv(c1.Ho, c1.Ho < 64 ? cdiv(c1.Ho, 2) * 2 : 64);
     const bool fuse = !t.wide && t.d_w0_img != nullptr && conv_fused_supported(c0.Cin, c0.Cout, c1.Cout, c1.W, c1.Wo, t.x3) &&
-                      getenv("BCAD_TWO_CONV_KERNELS") == nullptr;
+                      (m.cfg.max_batch * fuse_bands >= t.sms || getenv("BCAD_FUSED_CONV") != nullptr) && getenv("BCAD_TWO_CONV_KERNELS") == nullptr;
     if (fuse) {
         FusedArgs f;
         f.x = x; f.w0_img = t.d_w0_img; f.w1_img = t.d_w1_img; f.act = t.act; f.pool_fc = t.fc_a;
