@@ -284,10 +284,13 @@ int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const in
     IgemmArgs a;
     a.in = t.p1; a.w_img = t.d_w1_img; a.act = t.act; a.pool_fc = t.fc_a; a.pool_c8 = nullptr;
     a.B = n; a.H = c1.H; a.W = c1.W; a.Ho = c1.Ho; a.Wo = c1.Wo; a.Hp = c1.Hp; a.Wp = c1.Wp; a.pad = m.cfg.pad;
+    a.xsegs = cdiv(c1.Wo, 128);
+    // rows per work item: 64 for big calls (2 halo rows per 64), fewer when the call would otherwise leave SMs idle (a single
+    // image is 2 items at 64 rows, 64 items at 2) -- the banding does not change any result
     a.band_rows = 64;
+    while (a.band_rows > 2 && (long long)n * cdiv(c1.Ho, a.band_rows) * a.xsegs < t.sms) a.band_rows -= 2;
     if (a.band_rows > c1.Ho) a.band_rows = cdiv(c1.Ho, 2) * 2;
     a.bands = cdiv(c1.Ho, a.band_rows);
-    a.xsegs = cdiv(c1.Wo, 128);
     a.alpha = m.cfg.alpha_conv;
     a.debug = 0;
     if (const char* dbg = getenv("BCAD_DEBUG_SKIP_STORES")) {      // timing experiments only (results are garbage)
