@@ -814,7 +814,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_splitk_kernel(FcArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const int split = blockIdx.x, mt = blockIdx.y;
+    const int split = blockIdx.x, mt = blockIdx.y, cb = blockIdx.z;
     const int kb0 = split * a.kb_per_split, kb1 = min(a.nkb, kb0 + a.kb_per_split);
     const int nk = kb1 - kb0;
 
@@ -827,7 +827,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_splitk_kernel(FcArgs a) {
                 uint8_t* sa = smem + st * stage_bytes;
                 const uint8_t* asrc = a.a_tiles + ((size_t)mt * a.nkb + kb0 + i) * (size_t)(nparts * a_tile);
                 for (int off = 0; off < nparts * a_tile; off += 16384) bulk_g2s(sa + off, asrc + off, 16384, &full[st]);
-                const uint8_t* wsrc = a.w_tiles + (size_t)(kb0 + i) * (size_t)(nparts * w_tile);
+                const uint8_t* wsrc = a.w_tiles + ((size_t)cb * a.nkb + kb0 + i) * (size_t)(nparts * w_tile);
                 for (int off = 0; off < nparts * w_tile; off += 16384)
                     bulk_g2s(sa + nparts * a_tile + off, wsrc + off, min(16384, nparts * w_tile - off), &full[st]);
             }
@@ -858,7 +858,9 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_splitk_kernel(FcArgs a) {
     } else {
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
-        float* dst = a.partials + ((size_t)split * a.m_pad + (size_t)mt * 128 + row) * a.N;
+        const size_t ld = a.ld_out > 0 ? (size_t)a.ld_out : (size_t)a.N;
+        float* dst = a.partials + ((size_t)split * a.m_pad + (size_t)mt * 128 + row) * ld + (size_t)cb * a.N;
+        const bool store = (a.m_valid <= 0) || (mt * 128 + row < a.m_valid);
         if (nk > 0) {
             mbar_wait(done, 0);
             tc_fence_after();
@@ -868,11 +870,11 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_splitk_kernel(FcArgs a) {
                 tmem_ld_wait();
 #pragma unroll
                 for (int q = 0; q < 32; q += 4)
-                    if (c0 + q < a.N)   // N is a multiple of 16, not necessarily of 32
+                    if (c0 + q < a.N && store)   // N is a multiple of 16, not necessarily of 32
                         *reinterpret_cast<float4*>(dst + c0 + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
             }
         } else {
-            for (int c0 = 0; c0 < a.N; c0 += 4) *reinterpret_cast<float4*>(dst + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int c0 = 0; c0 < a.N && store; c0 += 4) *reinterpret_cast<float4*>(dst + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
     tc_fence_before();
@@ -885,8 +887,45 @@ int launch_fc_splitk(const FcArgs& a, cudaStream_t s) {
     const int stage_bytes = (a.x3 ? 2 : 1) * (128 * 128 + a.N * 128);
     const int smem = (a.x3 ? 2 : FC_STAGES) * stage_bytes + 256;
     BCAD_CUDA_CHECK(cudaFuncSetAttribute(fc_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    dim3 grid(a.splits, a.m_tiles);
+    BCAD_REQUIRE(a.ncb <= 1 || a.splits == 1, "fc_splitk: column blocks need splits == 1");
+    dim3 grid(a.splits, a.m_tiles, a.ncb > 1 ? a.ncb : 1);
     fc_splitk_kernel<<<grid, FC_THREADS, smem, s>>>(a);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+// fp32 rows [B][K] (K % 64 == 0) -> split fp16 SW128 A tiles [b/128][K/64][(hi|lo)][128][128 B]; rows >= B are zero
+__global__ void rows_to_fc_tiles_x3_kernel(const float* __restrict__ src, uint8_t* __restrict__ tiles, int B, int K, int m_pad) {
+    const int nkb = K / 64;
+    const size_t total = (size_t)m_pad * nkb * 8;                 // (row, k-block, 16-byte chunk)
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i & 7);
+        const size_t r = i >> 3;
+        const int kb = (int)(r % nkb);
+        const int row = (int)(r / nkb);
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = (row < B) ? src[(size_t)row * K + kb * 64 + ch * 8 + e] : 0.f;
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+            const float2 f = __half22float2(h);
+            hi[e] = h2u(h);
+            lo[e] = pack_f16(v[2 * e] - f.x, v[2 * e + 1] - f.y);
+        }
+        const int rr = row & 127;
+        uint8_t* tile = tiles + (((size_t)(row >> 7) * nkb + kb) * 2) * (128 * 128);
+        const int sw = (ch ^ (rr & 7)) * 16;
+        *reinterpret_cast<uint4*>(tile + rr * 128 + sw) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(tile + 128 * 128 + rr * 128 + sw) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+int launch_rows_to_fc_tiles_x3(const float* src, uint8_t* tiles, int B, int K, int m_pad, cudaStream_t s) {
+    BCAD_REQUIRE(K % 64 == 0 && m_pad % 128 == 0, "rows_to_fc_tiles: K=%d m_pad=%d", K, m_pad);
+    const size_t total = (size_t)m_pad * (K / 64) * 8;
+    rows_to_fc_tiles_x3_kernel<<<(int)std::min<size_t>(148 * 4, (total + 255) / 256), 256, 0, s>>>(src, tiles, B, K, m_pad);
     BCAD_CUDA_CHECK(cudaGetLastError());
     return BCAD_OK;
 }

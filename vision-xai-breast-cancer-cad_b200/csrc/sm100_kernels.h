@@ -66,7 +66,12 @@ struct FcArgs {
     float* partials;              // [splits][m_pad][N]
     int N, nkb, kb_per_split, splits, m_tiles, m_pad;
     int x3;                       // fp16x3: tiles come as [hi][lo] pairs; A_hi.W_hi + A_lo.W_hi + A_hi.W_lo
+    int ncb;                      // column blocks (grid.z): block cb reads w_tiles + cb * nkb tiles and writes columns [cb*N, +N); 0/1 = one
+    long long ld_out;             // row stride of the output in floats; 0 = N (the split-K partial layout)
+    int m_valid;                  // rows >= m_valid are not stored (0 = store all m_pad rows: the partial buffer is padded)
 };
+// dz1 fp32 [B][K] -> fp16x3 A tiles [b/128][K/64][(hi|lo)][128][128 B, chunks XOR (row&7)] for the fc1 input-gradient GEMM
+int launch_rows_to_fc_tiles_x3(const float* src, uint8_t* tiles, int B, int K, int m_pad, cudaStream_t s);
 int launch_fc_splitk(const FcArgs& a, cudaStream_t s);
 int launch_fc_reduce(const float* part, int splits, size_t ld_split, const float* bias, float* z, float* h, float alpha,
                      int M, int N, cudaStream_t s);

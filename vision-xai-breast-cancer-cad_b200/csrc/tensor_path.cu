@@ -41,6 +41,8 @@ struct TensorPath {
     float* alpha_raw = nullptr;     // [B][Cout] = dz1 . S
     int fc_splits = 1, kb_per_split = 1, m_pad = 128;
     bool x3 = false;                // fp16x3: hi/lo split operands everywhere (fp32-grade)
+    uint8_t* d_fc_wT = nullptr;     // tie-duplicating mode: fc1 transposed as W tiles of the input-gradient GEMM [col block][k-block][hi|lo][256][128 B]
+    uint8_t* dz_tiles = nullptr;    // dz1 as split A tiles [m_pad/128][units/64][hi|lo][128][128 B]
     bool p1_valid = true;           // the last forward wrote the pooled first-block map to HBM (the fused kernel only does with keep_all_activations)
     bool wide = false;              // first block has Cin > 1: nhwc_to_c8 + conv_wide (sm100_wide.cu)
     int cin_pad = 0, kc = 0, groups = 0;
@@ -212,6 +214,31 @@ int tensor_path_commit(Model& m) {
         BCAD_CUDA_CHECK(cudaMemcpy(t.d_fc_w, tiles.data(), tiles.size() * 2, cudaMemcpyHostToDevice));
         BCAD_CUDA_CHECK(cudaMemcpy(t.d_S, Sf.data(), Sf.size() * 4, cudaMemcpyHostToDevice));
     }
+    // ---- tie-duplicating mode: fc1 transposed, as the W operand of the input-gradient GEMM g = dz1 . W1 on the tensor core
+    //      (column block cb = 256 consecutive flat positions, K = units in blocks of 64; split hi/lo like every x3 operand)
+    if (m.cfg.pool_ties != BCAD_TIES_FIRST && d0.in % 256 == 0 && d0.out % 64 == 0) {
+        const int ncb = (int)(d0.in / 256), nkb = d0.out / 64;
+        std::vector<uint16_t> tiles((size_t)ncb * nkb * 2 * 256 * 64);
+        for (int cb = 0; cb < ncb; ++cb)
+            for (int kb = 0; kb < nkb; ++kb) {
+                uint16_t* hi = tiles.data() + (((size_t)cb * nkb + kb) * 2) * (256 * 64);
+                uint16_t* lo = hi + 256 * 64;
+                for (int c = 0; c < 256; ++c)
+                    for (int j = 0; j < 64; ++j) {
+                        const float v = d0.h_w[(size_t)(kb * 64 + j) * d0.in + (size_t)cb * 256 + c];
+                        const uint16_t q = f2h(v);
+                        const int pos = c * 64 + (((j >> 3) ^ (c & 7)) << 3) + (j & 7);
+                        hi[pos] = q;
+                        lo[pos] = f2h(v - h2f(q));
+                    }
+            }
+        if (!t.d_fc_wT) TP_TRY(m.alloc((void**)&t.d_fc_wT, tiles.size() * 2));
+        BCAD_CUDA_CHECK(cudaMemcpy(t.d_fc_wT, tiles.data(), tiles.size() * 2, cudaMemcpyHostToDevice));
+        if (!t.dz_tiles) {
+            const int m_pad = cdiv(mb, 128) * 128;
+            TP_TRY(m.alloc((void**)&t.dz_tiles, (size_t)m_pad * d0.out * 2 * 2));
+        }
+    }
     // ---- workspace
     if (t.p1 == nullptr) {
         t.m_pad = cdiv(mb, 128) * 128;
@@ -305,7 +332,7 @@ int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const in
     FcArgs f;
     f.a_tiles = t.fc_a; f.w_tiles = t.d_fc_w; f.partials = t.fc_part;
     f.N = d0.out; f.nkb = c1.Hp * c1.Wp; f.kb_per_split = t.kb_per_split; f.splits = t.fc_splits;
-    f.m_tiles = cdiv(n, 128); f.m_pad = t.m_pad; f.x3 = t.x3 ? 1 : 0;
+    f.m_tiles = cdiv(n, 128); f.m_pad = t.m_pad; f.x3 = t.x3 ? 1 : 0; f.ncb = 1; f.ld_out = 0; f.m_valid = 0;
     TP_LAUNCH(m, "fc1_splitk_tcgen05", launch_fc_splitk(f, s));
     if (m.fused_head) {
         // reduce + dense tail + class + (explain) backward to dz1 + alpha shortcut, one launch
@@ -339,7 +366,17 @@ int tensor_explain_chunk(Model& m, int n, const int32_t* class_idx, int grad_mod
         // weights) -> alpha with per-window tie counts read from the split activations; alpha_raw then feeds the usual tail
         if (!m.fused_head) TP_TRY(dense_backward(&m, n, class_idx, grad_mode, nullptr, s));          // leaves dz1 in dense[0].h
         DenseLayer& D0 = m.dense[0];
-        TP_LAUNCH(m, "fc1_dgrad_sgemm", launch_sgemm(D0.h, D0.d_w, m.g_flat, n, D0.in, D0.out, false, 1, s));
+        if (t.d_fc_wT != nullptr) {
+            // g[b][col] = sum_u dz1[b][u] W1[u][col] on tcgen05: split operands, one CTA per (256-column block, 128-image tile)
+            TP_LAUNCH(m, "dz1_to_tiles", launch_rows_to_fc_tiles_x3(D0.h, t.dz_tiles, n, D0.out, t.m_pad, s));
+            FcArgs f;
+            f.a_tiles = t.dz_tiles; f.w_tiles = t.d_fc_wT; f.partials = m.g_flat;
+            f.N = 256; f.nkb = D0.out / 64; f.kb_per_split = f.nkb; f.splits = 1;
+            f.m_tiles = cdiv(n, 128); f.m_pad = 0; f.x3 = 1; f.ncb = (int)(D0.in / 256); f.ld_out = (long long)D0.in; f.m_valid = n;
+            TP_LAUNCH(m, "fc1_dgrad_tcgen05", launch_fc_splitk(f, s));
+        } else {
+            TP_LAUNCH(m, "fc1_dgrad_sgemm", launch_sgemm(D0.h, D0.d_w, m.g_flat, n, D0.in, D0.out, false, 1, s));
+        }
         TP_LAUNCH(m, "alpha_ties_c8", launch_alpha_ties_c8(t.act, m.g_flat, t.alpha_raw, n, T.Ho, T.Wo, T.Cout, s));
     } else
     if (!m.fused_head) {
