@@ -2,7 +2,7 @@
 import time
 import torch
 dev = torch.device("cuda", 0)
-for mb in (32, 128):
+for mb in (4, 16, 32, 128):
     n = mb * 1024 * 1024 // 4
     h_in = torch.empty(n, dtype=torch.float32).pin_memory()
     h_out = torch.empty(n, dtype=torch.float32).pin_memory()
