@@ -14,6 +14,8 @@
 // classes each (2 x 32 accumulator columns; the running maximum stays in registers as packed halves): four teams are what
 // it takes to hide a tile's dependent build -> MMA -> TMEM-load chain, and four 128-column teams would not fit in TMEM.
 // Reference semantics: Conv2d/valid conv + bias + LeakyReLU + MaxPool2d(2), twice (ADCNNM.py:48,76; Classes/CNNModel.py:227-261).
+#include <stdlib.h>
+
 #include "../../include/bcad.h"
 #include "common.cuh"
 #include "sm100.cuh"
@@ -48,6 +50,7 @@ struct FusedSmem {
     static constexpr int TOTAL = OFF_BAR + 256;
 };
 
+template <bool PLAIN>      // PLAIN (experiment): first-block operands as plain fp16 (no hi/lo split): one K-step per class
 __global__ void __launch_bounds__(FZ_THREADS, 1) conv_fused_kernel(FusedArgs a) {
     using L = FusedSmem;
     constexpr int S = FZ_STAGES, COUT = FZ_C1, CIN = FZ_C0;
@@ -153,6 +156,14 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) conv_fused_kernel(FusedArgs a) 
                 uint32_t wd[16];
                 wd[0] = pack_f16(xt[0], xt[1]); wd[1] = pack_f16(xt[2], xt[3]); wd[2] = pack_f16(xt[4], xt[5]); wd[3] = pack_f16(xt[6], xt[7]);
                 wd[4] = pack_f16(xt[8], 1.f);
+                if constexpr (PLAIN) {
+                    wd[5] = wd[6] = wd[7] = 0u;
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch)
+                        *reinterpret_cast<uint4*>(s_a + qc * 8192 + ch * 2048 + ttid * 16) =
+                            make_uint4(wd[ch * 4], wd[ch * 4 + 1], wd[ch * 4 + 2], wd[ch * 4 + 3]);
+                    continue;
+                }
                 wd[5] = pack_f16(lt[0], lt[1]); wd[6] = pack_f16(lt[2], lt[3]); wd[7] = pack_f16(lt[4], lt[5]); wd[8] = pack_f16(lt[6], lt[7]);
                 wd[9] = pack_f16(lt[8], 1.f);
                 wd[10] = wd[0]; wd[11] = wd[1]; wd[12] = wd[2]; wd[13] = wd[3];
@@ -270,7 +281,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) conv_fused_kernel(FusedArgs a) 
 #pragma unroll
                     for (int qc = 0; qc < 2; ++qc)
 #pragma unroll
-                        for (int ks = 0; ks < 2; ++ks)
+                        for (int ks = 0; ks < (PLAIN ? 1 : 2); ++ks)
                             umma_f16_if(leader, tmem + 256 + t * 64 + qc * FZ_C0, im_desc0 + (uint64_t)((t * 16384 + qc * 8192 + ks * 4096) >> 4),
                                         w0_desc0 + (uint64_t)((ks * 2 * FZ_C0 * 16) >> 4), idesc0, ks);
                     umma_commit_if(leader, &tbar[t]);
@@ -415,10 +426,16 @@ int launch_conv_fused(const FusedArgs& a, int sms, cudaStream_t s) {
     static_assert(FusedSmem::TOTAL <= 227 * 1024, "conv_fused: shared memory budget");
     BCAD_REQUIRE(a.band_rows % 2 == 0 && a.bands == cdiv(a.Ho, a.band_rows), "conv_fused: bad banding");
     BCAD_REQUIRE(a.W1 <= 128 && a.Wo <= 128, "conv_fused: second-block map wider than 128");
-    BCAD_CUDA_CHECK(cudaFuncSetAttribute(conv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedSmem::TOTAL));
     const int items = a.B * a.bands;
     const int grid = items < sms ? items : sms;
-    conv_fused_kernel<<<grid, FZ_THREADS, FusedSmem::TOTAL, s>>>(a);
+    if (getenv("BCAD_CONV0_PLAIN") != nullptr) {                      // experiment: no hi/lo split in the first block
+        BCAD_CUDA_CHECK(cudaFuncSetAttribute(conv_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedSmem::TOTAL));
+        conv_fused_kernel<true><<<grid, FZ_THREADS, FusedSmem::TOTAL, s>>>(a);
+        BCAD_CUDA_CHECK(cudaGetLastError());
+        return BCAD_OK;
+    }
+    BCAD_CUDA_CHECK(cudaFuncSetAttribute(conv_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedSmem::TOTAL));
+    conv_fused_kernel<false><<<grid, FZ_THREADS, FusedSmem::TOTAL, s>>>(a);
     BCAD_CUDA_CHECK(cudaGetLastError());
     return BCAD_OK;
 }
