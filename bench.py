@@ -326,6 +326,11 @@ def run_ours(args, rank, world, local_rank):
     def step_host_u8():      # same call, heat-maps as heatmap_uint8 (GRADCAM.py:70): informational, NOT the headline e2e
         return eng.predict_explain_host(x_host.numpy(), None, GRAD, heat_out=heat8_host.numpy(), heat_dtype=np.uint8)
 
+    x8_host = torch.from_numpy(np.clip(np.rint(x_host.numpy() * 255.0), 0, 255).astype(np.uint8)).pin_memory()
+
+    def step_host_u8io():    # 8-bit pixels in (normalised /255 on the device, app.py:71), heatmap_uint8 out: informational as well
+        return eng.predict_explain_host(x8_host.numpy(), None, GRAD, heat_out=heat8_host.numpy(), heat_dtype=np.uint8)
+
     # ---- device-resident throughput (value)
     for _ in range(args.warmup):
         step_dev()
@@ -362,11 +367,19 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize(dev)
     e2e_u8_s = time.perf_counter() - t0
     barrier()
+    step_host_u8io()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host_u8io()
+    torch.cuda.synchronize(dev)
+    e2e_u8io_s = time.perf_counter() - t0
+    barrier()
 
-    tt = torch.tensor([ms_total, e2e_s * 1e3, e2e_u8_s * 1e3], device=dev, dtype=torch.float64)
+    tt = torch.tensor([ms_total, e2e_s * 1e3, e2e_u8_s * 1e3, e2e_u8io_s * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, e2e_u8_ms = float(tt[0]), float(tt[1]), float(tt[2])
+    ms_total, e2e_ms, e2e_u8_ms, e2e_u8io_ms = float(tt[0]), float(tt[1]), float(tt[2]), float(tt[3])
 
     # ---- per-kernel device times (CUDA events before every kernel, separate profiled steps)
     eng.set_profiling(True)
@@ -450,7 +463,7 @@ def run_ours(args, rank, world, local_rank):
                                           "measured": "same run, BCAD_TWO_CONV_KERNELS=1, CUDA events"}
         if name.startswith("conv01"):
             roof["note"] = ("both conv blocks in ONE kernel: FLOPs of block 1 (K = 9 taps, CUDA-core-bound im2col) + block 2 over the kernel's "
-                            "time; `two_kernel_variant` has the stand-alone kernels of the same run (block 2 alone ~0.64 of peak, both ~0.40)")
+                            "time; `two_kernel_variant` has the stand-alone kernels of the same run (block 2 alone ~0.64 of peak, both ~0.43)")
     elif "sgemm" in name or "fc" in name:
         flops = 2.0 * (INPUT_SHAPE[0] // 4) * (INPUT_SHAPE[1] // 4) * CONV_LAYERS[-1][0] * HIDDEN[0] * B
         peak = pk["bf16_tflops_sustained"]
@@ -488,15 +501,15 @@ def run_ours(args, rank, world, local_rank):
                                       "equivalent_GBps": dense_bytes / max(1e-9, tail_ms * 1e-3) / 1e9,
                                       "note": "SURVEY 8d dense figure (read A, read dA, write fp32 map); this path derives alpha "
                                               "from dz1 and never materialises dA, so it moves fewer bytes than that"}}
-    traffic_file = os.path.join(ROOT, "profiles", "r01c_traffic.json")
+    traffic_file = os.path.join(ROOT, "profiles", "r01d_traffic.json")
     if roof is not None and os.path.exists(traffic_file) and B == 512 and INPUT_SHAPE == (256, 256, 1):
         tr = json.load(open(traffic_file))
         x3 = precision == "fp16x3"                       # the committed capture is of the fp16 mode
-        ncu_name = None if x3 else {"conv1_igemm_tcgen05": "conv_igemm_kernel<32, 64, 0>", "conv01_fused_tcgen05": "conv_fused_kernel",
+        ncu_name = None if x3 else {"conv1_igemm_tcgen05": "conv_igemm_kernel<32, 64, 0>", "conv01_fused_tcgen05": "conv_fused_kernel<1>",
                                     "conv0_first_tcgen05": "conv_first_tc_kernel<32, 0, 0>"}.get(roof["kernel"])
         if ncu_name in tr:
             roof["traffic"] = tr[ncu_name]
-            roof["traffic_source"] = (f"profiles/r01c_traffic.json [{ncu_name}] (ncu --set full, dram__bytes_read.sum + "
+            roof["traffic_source"] = (f"profiles/r01d_traffic.json [{ncu_name}] (ncu --set full, dram__bytes_read.sum + "
                                       "dram__bytes_write.sum, per launch)")
 
     cpu = None
@@ -517,6 +530,11 @@ def run_ours(args, rank, world, local_rank):
                             "d2h_bytes_per_step": int(heat8_host.numel() + B * (2 * NUM_CLASSES * 4 + 4)),
                             "api": "bcad_predict_explain_host_u8: same call, heat-maps as heatmap_uint8 (GRADCAM.py:70) -- informational, "
                                    "the headline e2e above returns float32 maps"},
+        "e2e_u8_in_out": {"value": world * B * args.steps / (e2e_u8io_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_u8io_ms / args.steps,
+                          "h2d_bytes_per_step": int(x8_host.numel()),
+                          "d2h_bytes_per_step": int(heat8_host.numel() + B * (2 * NUM_CLASSES * 4 + 4)),
+                          "api": "bcad_predict_explain_host_u8in: 8-bit pixels in (x = u8 / 255 on the device, app.py:71), heatmap_uint8 "
+                                 "out -- what the reference's callers hold and write; informational"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,

@@ -144,6 +144,13 @@ BCAD_API int bcad_predict_explain_host(bcad_model* m, const float* x_host, int B
 BCAD_API int bcad_predict_explain_host_u8(bcad_model* m, const float* x_host, int B, const int32_t* class_idx_host_or_null,
                                  int grad_mode, float* logits_host, float* probs_host, int32_t* cls_host,
                                  uint8_t* heat_u8_host);
+/* 8-bit images in: x_u8_host uint8 [B,H,W,C] (a decoded PNG / the 0-255 grey image the callers hold, app.py:629-639),
+ * normalised on the device as x = float32(u8) / 255.0f (app.py:71, GRADCAM.py:46) -- a quarter of the host->device
+ * bytes, results bit-identical to passing that float32 array.  Heat-maps as float32 (heatmap_host) or uint8
+ * (heat_u8_host); exactly one of the two may be non-NULL, both NULL = predict only. */
+BCAD_API int bcad_predict_explain_host_u8in(bcad_model* m, const uint8_t* x_u8_host, int B, const int32_t* class_idx_host_or_null,
+                                   int grad_mode, float* logits_host, float* probs_host, int32_t* cls_host,
+                                   float* heatmap_host, uint8_t* heat_u8_host);
 
 /* ---- stand-alone Grad-CAM tail (pytorch_grad_cam BaseCAM.forward / scale_cam_image) ------------ */
 /* A, dA: [B,h,w,K] NHWC device, dtype 0 = fp32, 1 = bf16; out: fp32 [B,H,W].

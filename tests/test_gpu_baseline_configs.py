@@ -58,7 +58,7 @@ def test_cfg1_245_images_in_batches_of_32(precision, tol):
 
 
 def test_cfg4_8192_images_chunked_host_call():
-    """8192 images through the host-buffer call (64-image transfer chunks, max_batch 512): 128 copies of 64 distinct images --
+    """8192 images through the host-buffer call (128-image transfer chunks, max_batch 512): 128 copies of 64 distinct images --
     every copy must reproduce the first bit for bit, whatever chunk / position it lands in, and match a 64-image call."""
     cfg, p = _canonical()
     base = ocnn.synth_images(64, (256, 256, 1), seed=99)

@@ -186,6 +186,28 @@ def test_host_call_u8_heatmaps_are_truncated_float_maps():
         eng.close()
 
 
+def test_host_call_u8_pixels_equal_the_normalised_float_call():
+    """bcad_predict_explain_host_u8in: uint8 pixels, x = float32(u8) / 255 on the device (app.py:71 `torch.tensor(.., float32) / 255.0`;
+    the float64 `img / 255.0` of GRADCAM.py:46 rounds to the same float32) -- bit-identical to passing that float32 array."""
+    cfg = ocnn.NetConfig.torch_flavour((64, 48, 1), 2, [(32, 3), (64, 3)], [32, 16], 0.01)
+    p = ocnn.init_params(cfg, seed=3, bias_std=0.05)
+    rng = np.random.default_rng(8)
+    x8 = rng.integers(0, 256, size=(70, 64, 48, 1), dtype=np.uint8)     # > one 64-image host chunk; every pixel value occurs
+    xf = (torch.tensor(x8, dtype=torch.float32) / 255.0).numpy()
+    assert np.array_equal(xf, (x8 / 255.0).astype(np.float32))
+    for precision in ("fp16", "fp32"):
+        eng = engine_from(cfg, p, precision=precision, max_batch=64)
+        cf, pf, lf, hf = eng.predict_explain_host(xf, None, "logit")
+        c8, p8, l8, h8 = eng.predict_explain_host(x8, None, "logit")
+        assert h8.dtype == np.float32
+        assert np.array_equal(c8, cf) and np.array_equal(l8, lf) and np.array_equal(p8, pf) and np.array_equal(h8, hf)
+        c8, p8, l8, h8u = eng.predict_explain_host(x8, None, "logit", heat_dtype=np.uint8)
+        assert h8u.dtype == np.uint8 and np.array_equal(h8u, (hf * np.float32(255)).astype(np.uint8)) and np.array_equal(l8, lf)
+        c8, p8, l8, none = eng.predict_explain_host(x8[:3], np.array([1, 0, 1]), "logit", want_heat=False)     # predict only, ragged
+        assert none is None and np.array_equal(l8, lf[:3])
+        eng.close()
+
+
 @pytest.mark.parametrize("shape,pad,hidden,B", [
     ((64, 64, 1), 1, [64, 32], 5),
     ((61, 61, 1), 0, [32], 4),               # valid conv, odd maps: 61 -> 59 -> 29 -> 27 -> 13

@@ -43,7 +43,7 @@ def main():
     out = [f"# ncu launch list ({os.path.basename(launches)}): gpu__time_duration.sum per kernel\n\n",
            "Cold-cache, serialised launches under ncu: compare SHARES with bench.py's `kernels[].share`, not absolutes.\n",
            (f"Only the first {first} launches = the device-resident batch-512 steps (warm-up + timed); the rest of the CSV are the "
-            "64-image chunk launches of the host-buffer (e2e) pipeline, whose proportions differ.\n\n" if first else "\n"),
+            "chunk launches of the host-buffer (e2e) pipeline, whose proportions differ.\n\n" if first else "\n"),
            "| kernel | launches | avg us | share of all profiled time |\n|---|---|---|---|\n"]
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         out.append(f"| {k} | {len(v)} | {sum(v) / len(v) / 1e3:.1f} | {sum(v) / tot:.3f} |\n")

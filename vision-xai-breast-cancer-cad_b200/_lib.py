@@ -55,6 +55,7 @@ _SIGNATURES = {
     "bcad_tensor_elems": (C.c_int64, [_P, C.c_int, C.c_int]),
     "bcad_predict_explain_host": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, _P, _P, _P]),
     "bcad_predict_explain_host_u8": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, _P, _P, _P]),
+    "bcad_predict_explain_host_u8in": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P]),
     "bcad_gradcam_tail": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "bcad_overlay": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "bcad_conv_block": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float,

@@ -625,10 +625,11 @@ int bcad_get_tensor(bcad_model* mm, int kind, int index, int B, float* dst, void
 // -----------------------------------------------------------------------------------------------------
 // host-buffer end-to-end call: H2D / compute / D2H in chunks on three streams, double-buffered
 // -----------------------------------------------------------------------------------------------------
-static int predict_explain_host_impl(bcad_model* mm, const float* x_host, int B, const int32_t* class_idx_host, int grad_mode,
-                                     float* logits_host, float* probs_host, int32_t* cls_host, float* heat_host, uint8_t* heat_u8_host) {
+static int predict_explain_host_impl(bcad_model* mm, const float* x_host, const uint8_t* x8_host, int B, const int32_t* class_idx_host,
+                                     int grad_mode, float* logits_host, float* probs_host, int32_t* cls_host, float* heat_host,
+                                     uint8_t* heat_u8_host) {
     Model* m = reinterpret_cast<Model*>(mm);
-    BCAD_REQUIRE(m && x_host, "predict_explain_host: null argument");
+    BCAD_REQUIRE(m && (x_host || x8_host), "predict_explain_host: null argument");
     BCAD_REQUIRE(B >= 1, "batch must be >= 1, got %d", B);
     if (!m->committed) { set_error("weights not committed: call bcad_commit first"); return BCAD_ERR_STATE; }
     DeviceGuard g(m->cfg.device);
@@ -637,7 +638,9 @@ static int predict_explain_host_impl(bcad_model* mm, const float* x_host, int B,
     const size_t img = (size_t)m->cfg.in_h * m->cfg.in_w * m->cfg.in_c, hm = (size_t)m->cfg.in_h * m->cfg.in_w;
     // transfer/compute chunk: small enough that the PCIe pipeline fills quickly (the link, ~52 GB/s per direction, is the
     // end-to-end bound), large enough to keep the kernels efficient.  BCAD_HOST_CHUNK overrides (tuning).
-    int chunk = std::min(m->cfg.max_batch, 64);
+    // Buffers are sized for 128 images; a call uses about a quarter of its batch per chunk (32..128 images: measured at 512
+    // images, float32 in/out 3.73 ms with 64 or 128, 8-bit in/out 2.11 ms with 64, 1.73 ms with 128, 1.80 ms with 256).
+    int chunk = std::min(m->cfg.max_batch, 128);
     if (const char* e = getenv("BCAD_HOST_CHUNK")) chunk = std::max(1, std::min(m->cfg.max_batch, atoi(e)));
     {
         std::lock_guard<std::mutex> lock(m->mu);
@@ -661,6 +664,8 @@ static int predict_explain_host_impl(bcad_model* mm, const float* x_host, int B,
         }
         if (heat_u8_host != nullptr && X.heat8[0] == nullptr)
             for (int i = 0; i < 2; ++i) BCAD_TRY(m->alloc((void**)&X.heat8[i], (size_t)X.chunk * hm));
+        if (x8_host != nullptr && X.x8[0] == nullptr)
+            for (int i = 0; i < 2; ++i) BCAD_TRY(m->alloc((void**)&X.x8[i], (size_t)X.chunk * img));
     }
     // small outputs go through pinned staging sized for the whole call
     const size_t per_img = (size_t)(2 * nc) * sizeof(float) + sizeof(int32_t);
@@ -678,7 +683,8 @@ static int predict_explain_host_impl(bcad_model* mm, const float* x_host, int B,
     // tail (last D2H) of the pipeline are short; the steady state runs H2D, compute and D2H of three chunks concurrently
     std::vector<int> sizes;
     {
-        const int C0 = X.chunk;
+        int C0 = X.chunk;
+        if (getenv("BCAD_HOST_CHUNK") == nullptr) C0 = std::min(X.chunk, std::max(32, ((B + 3) / 4 + 31) / 32 * 32));
         int left = B;
         std::vector<int> head, tail;
         // measured on the bench workload (512 images): uniform 64-image chunks 3.62 ms, ramped 3.93 ms -- the small
@@ -705,13 +711,15 @@ static int predict_explain_host_impl(bcad_model* mm, const float* x_host, int B,
             BCAD_CUDA_CHECK(cudaStreamWaitEvent(X.s_in, X.compute_done[slot], 0));
             BCAD_CUDA_CHECK(cudaStreamWaitEvent(X.s_compute, X.out_done[slot], 0));
         }
-        BCAD_CUDA_CHECK(cudaMemcpyAsync(X.x[slot], x_host + (size_t)b0 * img, (size_t)n * img * sizeof(float), cudaMemcpyHostToDevice, X.s_in));
+        if (x8_host) BCAD_CUDA_CHECK(cudaMemcpyAsync(X.x8[slot], x8_host + (size_t)b0 * img, (size_t)n * img, cudaMemcpyHostToDevice, X.s_in));
+        else BCAD_CUDA_CHECK(cudaMemcpyAsync(X.x[slot], x_host + (size_t)b0 * img, (size_t)n * img * sizeof(float), cudaMemcpyHostToDevice, X.s_in));
         if (class_idx_host)
             BCAD_CUDA_CHECK(cudaMemcpyAsync(X.cidx[slot], class_idx_host + b0, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, X.s_in));
         BCAD_CUDA_CHECK(cudaEventRecord(X.in_done[slot], X.s_in));
         BCAD_CUDA_CHECK(cudaStreamWaitEvent(X.s_compute, X.in_done[slot], 0));
         const bool want_heat = (heat_host != nullptr || heat_u8_host != nullptr);
-        int rc = run(m, X.x[slot], n, class_idx_host ? X.cidx[slot] : nullptr, grad_mode, want_heat, X.logits[slot],
+        int rc = x8_host ? launch_u8_to_unit(X.x8[slot], X.x[slot], (size_t)n * img, X.s_compute) : BCAD_OK;
+        if (rc == BCAD_OK) rc = run(m, X.x[slot], n, class_idx_host ? X.cidx[slot] : nullptr, grad_mode, want_heat, X.logits[slot],
                      X.probs[slot], X.cls[slot], X.heat[slot], X.s_compute);
         if (rc == BCAD_OK && heat_u8_host != nullptr) rc = launch_heat_to_u8(X.heat[slot], X.heat8[slot], (size_t)n * hm, X.s_compute);
         if (rc != BCAD_OK) { cudaDeviceSynchronize(); return rc; }
@@ -734,13 +742,20 @@ static int predict_explain_host_impl(bcad_model* mm, const float* x_host, int B,
 
 int bcad_predict_explain_host(bcad_model* mm, const float* x_host, int B, const int32_t* class_idx_host, int grad_mode,
                               float* logits_host, float* probs_host, int32_t* cls_host, float* heat_host) {
-    return predict_explain_host_impl(mm, x_host, B, class_idx_host, grad_mode, logits_host, probs_host, cls_host, heat_host, nullptr);
+    return predict_explain_host_impl(mm, x_host, nullptr, B, class_idx_host, grad_mode, logits_host, probs_host, cls_host, heat_host, nullptr);
 }
 
 int bcad_predict_explain_host_u8(bcad_model* mm, const float* x_host, int B, const int32_t* class_idx_host, int grad_mode,
                                  float* logits_host, float* probs_host, int32_t* cls_host, uint8_t* heat_u8_host) {
     BCAD_REQUIRE(heat_u8_host, "predict_explain_host_u8: null heat-map pointer");
-    return predict_explain_host_impl(mm, x_host, B, class_idx_host, grad_mode, logits_host, probs_host, cls_host, nullptr, heat_u8_host);
+    return predict_explain_host_impl(mm, x_host, nullptr, B, class_idx_host, grad_mode, logits_host, probs_host, cls_host, nullptr, heat_u8_host);
+}
+
+int bcad_predict_explain_host_u8in(bcad_model* mm, const uint8_t* x_u8_host, int B, const int32_t* class_idx_host, int grad_mode,
+                                   float* logits_host, float* probs_host, int32_t* cls_host, float* heat_host, uint8_t* heat_u8_host) {
+    BCAD_REQUIRE(x_u8_host, "predict_explain_host_u8in: null image pointer");
+    BCAD_REQUIRE(!(heat_host && heat_u8_host), "predict_explain_host_u8in: pass one heat-map pointer (float32 or uint8), not both");
+    return predict_explain_host_impl(mm, nullptr, x_u8_host, B, class_idx_host, grad_mode, logits_host, probs_host, cls_host, heat_host, heat_u8_host);
 }
 
 // -----------------------------------------------------------------------------------------------------

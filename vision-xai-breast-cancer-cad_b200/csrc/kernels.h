@@ -59,6 +59,7 @@ int launch_overlay(const float* img01, const float* cam, int B, int H, int W, ui
 // ---------------------------------------------------------------- training step (kernels_train.cu)
 int launch_ce_loss_topgrad(const float* probs, const int32_t* labels, float* loss, float* dz, int B, int nc, cudaStream_t s);
 int launch_heat_to_u8(const float* cam, uint8_t* out, size_t n, cudaStream_t s);
+int launch_u8_to_unit(const uint8_t* src, float* dst, size_t n, cudaStream_t s);
 int launch_bottleneck_resize(const float* src, float* dst, int B, int C, int H, int W, int chw, int oh, int ow, cudaStream_t s);
 int launch_leaky_from_z(const float* z, float* h, float alpha, int64_t n, cudaStream_t s);
 int launch_mul_mask(float* h, const float* mask, int B, int units, int ld, cudaStream_t s);

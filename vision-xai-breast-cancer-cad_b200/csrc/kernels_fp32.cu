@@ -994,6 +994,32 @@ int launch_heat_to_u8(const float* cam, uint8_t* out, size_t n, cudaStream_t s) 
     return BCAD_OK;
 }
 
+// 8-bit pixels -> the unit-range float32 image the CNN takes: x = float32(u8) / 255.0f, IEEE division (app.py:71
+// `torch.tensor(resized, dtype=torch.float32) / 255.0`; GRADCAM.py:46 `img / 255.0`), 16 pixels per thread
+__global__ void __launch_bounds__(256) u8_to_unit_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, size_t n) {
+    const size_t n16 = n / 16;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = ldg_stream_u4(reinterpret_cast<const uint4*>(src) + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float4 o;
+            o.x = __fdiv_rn((float)(w[j] & 0xffu), 255.f);         o.y = __fdiv_rn((float)((w[j] >> 8) & 0xffu), 255.f);
+            o.z = __fdiv_rn((float)((w[j] >> 16) & 0xffu), 255.f); o.w = __fdiv_rn((float)(w[j] >> 24), 255.f);
+            reinterpret_cast<float4*>(dst)[i * 4 + j] = o;
+        }
+    }
+    for (size_t i = n16 * 16 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = __fdiv_rn((float)src[i], 255.f);
+}
+
+int launch_u8_to_unit(const uint8_t* src, float* dst, size_t n, cudaStream_t s) {
+    const int blocks = (int)std::min<size_t>((size_t)148 * 8, (n / 16 + 255) / 256 + 1);
+    u8_to_unit_kernel<<<blocks, 256, 0, s>>>(src, dst, n);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
 int launch_overlay(const float* img01, const float* cam, int B, int H, int W, uint8_t* overlay_rgb, uint8_t* heat_u8,
                    cudaStream_t s) {
     overlay_kernel<<<B, 1024, 0, s>>>(img01, cam, H, W, overlay_rgb, heat_u8);

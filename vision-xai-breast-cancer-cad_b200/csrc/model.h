@@ -53,6 +53,7 @@ struct Xfer {                          // host-buffer pipeline (bcad_predict_exp
     float* x[2] = {nullptr, nullptr};
     float* heat[2] = {nullptr, nullptr};
     uint8_t* heat8[2] = {nullptr, nullptr};   // u8 heat-maps of a chunk (bcad_predict_explain_host_u8), allocated on first use
+    uint8_t* x8[2] = {nullptr, nullptr};      // 8-bit input pixels of a chunk (bcad_predict_explain_host_u8in), allocated on first use
     float* logits[2] = {nullptr, nullptr};
     float* probs[2] = {nullptr, nullptr};
     int32_t* cls[2] = {nullptr, nullptr};

@@ -14,8 +14,6 @@
 // classes each (2 x 32 accumulator columns; the running maximum stays in registers as packed halves): four teams are what
 // it takes to hide a tile's dependent build -> MMA -> TMEM-load chain, and four 128-column teams would not fit in TMEM.
 // Reference semantics: Conv2d/valid conv + bias + LeakyReLU + MaxPool2d(2), twice (ADCNNM.py:48,76; Classes/CNNModel.py:227-261).
-#include <stdlib.h>
-
 #include "../../include/bcad.h"
 #include "common.cuh"
 #include "sm100.cuh"
@@ -50,7 +48,9 @@ struct FusedSmem {
     static constexpr int TOTAL = OFF_BAR + 256;
 };
 
-template <bool PLAIN>      // PLAIN (experiment): first-block operands as plain fp16 (no hi/lo split): one K-step per class
+// PLAIN: first-block operands as plain fp16 (the fp16 mode): K slots [x(9) 1 1 0..] against [w(9) b_hi b_lo 0..], one K-step
+// per pool class and two 16-byte im2col stores per row; !PLAIN: the hi/lo split image (three stores, two K-steps)
+template <bool PLAIN>
 __global__ void __launch_bounds__(FZ_THREADS, 1) conv_fused_kernel(FusedArgs a) {
     using L = FusedSmem;
     constexpr int S = FZ_STAGES, COUT = FZ_C1, CIN = FZ_C0;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) conv_fused_kernel(FusedArgs a) 
         reinterpret_cast<uint4*>(s_zero)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < L::ONES_TILE / 16; i += FZ_THREADS)
         reinterpret_cast<uint4*>(s_ones)[i] = (i < 128) ? make_uint4(0x3C003C00u, 0, 0, 0) : make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < (4 * FZ_C0 * 16) / 16; i += FZ_THREADS)
+    for (int i = tid; i < ((PLAIN ? 2 : 4) * FZ_C0 * 16) / 16; i += FZ_THREADS)
         reinterpret_cast<uint4*>(s_w0)[i] = reinterpret_cast<const uint4*>(a.w0_img)[i];
     if (tid == 0) {
         for (int i = 0; i < S; ++i) { mbar_init(&full[i], 8); mbar_init(&empty[i], 1); }
@@ -157,7 +157,8 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) conv_fused_kernel(FusedArgs a) 
                 wd[0] = pack_f16(xt[0], xt[1]); wd[1] = pack_f16(xt[2], xt[3]); wd[2] = pack_f16(xt[4], xt[5]); wd[3] = pack_f16(xt[6], xt[7]);
                 wd[4] = pack_f16(xt[8], 1.f);
                 if constexpr (PLAIN) {
-                    wd[5] = wd[6] = wd[7] = 0u;
+                    wd[5] = 0x00003C00u;                      // (1, 0): the b_lo slot
+                    wd[6] = wd[7] = 0u;
 #pragma unroll
                     for (int ch = 0; ch < 2; ++ch)
                         *reinterpret_cast<uint4*>(s_a + qc * 8192 + ch * 2048 + ttid * 16) =
@@ -428,7 +429,7 @@ int launch_conv_fused(const FusedArgs& a, int sms, cudaStream_t s) {
     BCAD_REQUIRE(a.W1 <= 128 && a.Wo <= 128, "conv_fused: second-block map wider than 128");
     const int items = a.B * a.bands;
     const int grid = items < sms ? items : sms;
-    if (getenv("BCAD_CONV0_PLAIN") != nullptr) {                      // experiment: no hi/lo split in the first block
+    if (a.plain0) {
         BCAD_CUDA_CHECK(cudaFuncSetAttribute(conv_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedSmem::TOTAL));
         conv_fused_kernel<true><<<grid, FZ_THREADS, FusedSmem::TOTAL, s>>>(a);
         BCAD_CUDA_CHECK(cudaGetLastError());

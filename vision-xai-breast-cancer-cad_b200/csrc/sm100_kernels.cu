@@ -113,9 +113,10 @@ int launch_conv_first_pool(const float* x, const float* w9c, const float* bias, 
 // instructions than 1152 FFMAs per pooled pixel.  128-thread CTAs; DBUF: im2col image double-buffered, 3 CTAs per SM;
 // !DBUF: one image, 4 CTAs per SM.
 // =====================================================================================================
-template <int COUT, bool SPLIT, bool DBUF>
+// PLAIN (the fp16 mode): operands as plain fp16 -- A row = [x(9) 1 1 0 0 0 0 0], B row = [w(9) b_hi b_lo 0 0 0 0 0], one K-step.
+template <int COUT, bool SPLIT, bool DBUF, bool PLAIN>
 __global__ void __launch_bounds__(128, DBUF ? 3 : 4)
-conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_img /*[4][COUT][16 B]*/,
+conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_img /*[4 or 2][COUT][16 B]*/,
                      __half* __restrict__ out, int B, int H, int W, int pad, int Hp, int Wp, float alpha) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_a = smem;                          // (DBUF ? 2 : 1) buffers x 4 classes x [4 chunks][128 rows][16 B] = 32 KB each
@@ -123,7 +124,8 @@ conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
-    for (int i = tid; i < (4 * COUT * 16) / 16; i += 128) reinterpret_cast<uint4*>(s_b)[i] = reinterpret_cast<const uint4*>(w_img)[i];
+    static_assert(!(PLAIN && SPLIT), "the fp16x3 mode keeps the hi/lo split");
+    for (int i = tid; i < ((PLAIN ? 2 : 4) * COUT * 16) / 16; i += 128) reinterpret_cast<uint4*>(s_b)[i] = reinterpret_cast<const uint4*>(w_img)[i];
     if (tid == 0) {
         mbar_init(&bar, 1);
         fence_barrier_init();
@@ -188,7 +190,7 @@ conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_
         //      [x(9) 1 | x_lo(9) 1 | x(9) 0 0 0]  -- cvt.rn.f16x2 turns an fp32 pair straight into one packed word
         float lo[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) lo[e] = patch[e] - __half2float(__float2half_rn(patch[e]));
+        for (int e = 0; e < 16; ++e) lo[e] = PLAIN ? 0.f : patch[e] - __half2float(__float2half_rn(patch[e]));
 #pragma unroll
         for (int q = 0; q < 4; ++q) {               // class q = (row parity, col parity) of the pool window
             const int qr = q >> 1, qc = q & 1;
@@ -202,6 +204,15 @@ conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_
             uint32_t wd[16];
             wd[0] = pack_f16(xt[0], xt[1]); wd[1] = pack_f16(xt[2], xt[3]); wd[2] = pack_f16(xt[4], xt[5]); wd[3] = pack_f16(xt[6], xt[7]);
             wd[4] = pack_f16(xt[8], 1.f);
+            if constexpr (PLAIN) {
+                wd[5] = 0x00003C00u;                // (1, 0): the b_lo slot
+                wd[6] = wd[7] = 0u;
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch)
+                    *reinterpret_cast<uint4*>(s_a + buf * 32768 + q * 8192 + ch * 2048 + tid * 16) =
+                        make_uint4(wd[ch * 4], wd[ch * 4 + 1], wd[ch * 4 + 2], wd[ch * 4 + 3]);
+                continue;
+            }
             wd[5] = pack_f16(lt[0], lt[1]); wd[6] = pack_f16(lt[2], lt[3]); wd[7] = pack_f16(lt[4], lt[5]); wd[8] = pack_f16(lt[6], lt[7]);
             wd[9] = pack_f16(lt[8], 1.f);
             wd[10] = wd[0]; wd[11] = wd[1]; wd[12] = wd[2]; wd[13] = wd[3];
@@ -220,7 +231,7 @@ conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks)
+                for (int ks = 0; ks < (PLAIN ? 1 : 2); ++ks)
                     umma_f16_if(leader, tmem + q * COUT, a_desc0 + (uint64_t)((buf * 32768 + q * 8192 + ks * 4096) >> 4),
                                 b_desc0 + (uint64_t)((ks * 2 * COUT * 16) >> 4), idesc, ks);
             umma_commit_if(leader, &bar);
@@ -328,17 +339,18 @@ conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_
     if (warp == 0) tmem_dealloc(tmem, 4 * COUT);
 }
 
-template <int COUT, bool SPLIT, bool DBUF = true>
+template <int COUT, bool SPLIT, bool DBUF = true, bool PLAIN = false>
 static int launch_conv_first_tc_t(const float* x, const uint8_t* w_img, __half* out, int B, int H, int W, int pad, int Hp,
                                   int Wp, float alpha, int grid, int smem, cudaStream_t s) {
-    BCAD_CUDA_CHECK(cudaFuncSetAttribute(conv_first_tc_kernel<COUT, SPLIT, DBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    conv_first_tc_kernel<COUT, SPLIT, DBUF><<<grid, 128, smem, s>>>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha);
+    BCAD_CUDA_CHECK(cudaFuncSetAttribute(conv_first_tc_kernel<COUT, SPLIT, DBUF, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    conv_first_tc_kernel<COUT, SPLIT, DBUF, PLAIN><<<grid, 128, smem, s>>>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha);
     BCAD_CUDA_CHECK(cudaGetLastError());
     return BCAD_OK;
 }
 
 int launch_conv_first_tc(const float* x, const uint8_t* w_img, __half* out, int B, int H, int W, int pad, int Cout,
-                         float alpha, bool split_hi_lo, int sms, cudaStream_t s) {
+                         float alpha, bool split_hi_lo, bool plain, int sms, cudaStream_t s) {
+    BCAD_REQUIRE(!(plain && split_hi_lo), "conv_first_tc: the hi/lo output split needs hi/lo operands");
     const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2, Hp = Ho / 2, Wp = Wo / 2;
     const int n_tiles = B * Hp * cdiv(Wp, 128);
     // 32 filters, fp16 mode: ONE im2col buffer and a 4th CTA per SM (TMEM allows 4 x 128 columns) measured 2.6 % faster than
@@ -347,8 +359,10 @@ int launch_conv_first_tc(const float* x, const uint8_t* w_img, __half* out, int 
     const int smem = (single ? 1 : 2) * 32768 + 4 * Cout * 16;
     const int per_sm = Cout <= 32 ? (single ? 4 : 3) : 2;          // smem: 66 KB per CTA; TMEM: 4*Cout columns per CTA
     const int grid = n_tiles < sms * per_sm ? n_tiles : sms * per_sm;
+    if (single && plain) return launch_conv_first_tc_t<32, false, false, true>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s);
     if (single) return launch_conv_first_tc_t<32, false, false>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s);
     if (Cout == 32 && split_hi_lo) return launch_conv_first_tc_t<32, true>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s);
+    if (Cout == 64 && plain) return launch_conv_first_tc_t<64, false, true, true>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s);
     if (Cout == 64 && !split_hi_lo) return launch_conv_first_tc_t<64, false>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s);
     set_error("conv_first_tc: Cout %d (split=%d) not supported", Cout, (int)split_hi_lo);
     return BCAD_ERR_INVALID;

@@ -9,9 +9,10 @@ namespace bcad {
 int launch_conv_first_pool(const float* x, const float* w9c, const float* bias, __half* out, int B, int H, int W,
                            int pad, int Cout, float alpha, cudaStream_t s);
 
-// tensor-core first conv: w_img = [4 chunks][Cout][8 halves] rows [w_hi(9) b_hi | w_hi(9) b_lo | w_lo(9) 0 0 0]
+// tensor-core first conv: w_img = [4 chunks][Cout][8 halves] rows [w_hi(9) b_hi | w_hi(9) b_lo | w_lo(9) 0 0 0], or, with
+// plain_operands (fp16 mode: no hi/lo split of image and weights), [2 chunks][Cout][8 halves] rows [w(9) b_hi b_lo 0 0 0 0 0]
 int launch_conv_first_tc(const float* x, const uint8_t* w_img, __half* out, int B, int H, int W, int pad, int Cout,
-                         float alpha, bool split_hi_lo, int sms, cudaStream_t s);
+                         float alpha, bool split_hi_lo, bool plain_operands, int sms, cudaStream_t s);
 
 struct IgemmArgs {
     const __half* in;      // C8 planar [B][H][Cin/8][W][8]
@@ -45,7 +46,8 @@ int launch_nhwc_to_c8(const float* x, __half* out, int B, int H, int W, int C, i
 // both conv blocks in one persistent kernel (sm100_fused.cu): Cin = 1 -> 32 -> 64 filters, fp16 mode, maps up to 128 px wide
 struct FusedArgs {
     const float* x;               // fp32 [B][H][W]
-    const uint8_t* w0_img;        // first-block image [4 chunks][32][16 B] (as launch_conv_first_tc)
+    const uint8_t* w0_img;        // first-block image [4 chunks][32][16 B], or [2 chunks][32][16 B] with plain0 (as launch_conv_first_tc)
+    int plain0;                   // first-block operands as plain fp16 (the fp16 mode) instead of hi/lo pairs
     const uint8_t* w1_img;        // second-block weight image + bias tile (as IgemmArgs::w_img)
     __half* act;                  // second-block activations, C8 planar, or nullptr
     uint8_t* pool_fc;             // pooled second-block output as fc1 A tiles, or nullptr

@@ -30,6 +30,8 @@ struct TensorPath {
     float* d_w0 = nullptr;          // first conv weights [9][Cout0] fp32
     float* d_b0 = nullptr;
     uint8_t* d_w0_img = nullptr;    // tensor-core first conv: [4][Cout0][8] fp16 (hi/lo split weights + bias)
+    uint8_t* d_w0_plain = nullptr;  // the same without the split (fp16 mode): [2][Cout0][8] fp16 rows [w(9) b_hi b_lo 0..]
+    bool plain0 = false;            // fp16 mode: plain fp16 operands in the first block too (BCAD_CONV0_SPLIT=1 keeps the split)
     uint8_t* d_w1_img = nullptr;    // igemm weight image (fp16)
     float* d_b1 = nullptr;
     uint8_t* d_fc_w = nullptr;      // fc1 W tiles
@@ -160,6 +162,18 @@ int tensor_path_commit(Model& m) {
         }
         if (!t.d_w0_img) TP_TRY(m.alloc((void**)&t.d_w0_img, img.size() * 2));
         BCAD_CUDA_CHECK(cudaMemcpy(t.d_w0_img, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+        // fp16 mode: one K-step of plain fp16 weights; the bias stays an exact hi + lo pair (two slots against two ones)
+        std::vector<uint16_t> pl((size_t)2 * c0.Cout * 8, 0);
+        auto putp = [&](int f, int k, float v) { pl[((size_t)(k >> 3) * c0.Cout + f) * 8 + (k & 7)] = f2h(v); };
+        for (int f = 0; f < c0.Cout; ++f) {
+            for (int tap = 0; tap < 9; ++tap) putp(f, tap, c0.h_w[(size_t)f * 9 + tap]);
+            const float bhi = h2f(f2h(c0.h_b[f]));
+            putp(f, 9, bhi);
+            putp(f, 10, c0.h_b[f] - bhi);
+        }
+        if (!t.d_w0_plain) TP_TRY(m.alloc((void**)&t.d_w0_plain, pl.size() * 2));
+        BCAD_CUDA_CHECK(cudaMemcpy(t.d_w0_plain, pl.data(), pl.size() * 2, cudaMemcpyHostToDevice));
+        t.plain0 = !t.x3 && getenv("BCAD_CONV0_SPLIT") == nullptr;
     }
     // ---- conv1 weight image: [tap*(Cin/8)+chunk][cout][8] fp16
     {
@@ -278,7 +292,7 @@ int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const in
                       (m.cfg.max_batch * fuse_bands >= t.sms || getenv("BCAD_FUSED_CONV") != nullptr) && getenv("BCAD_TWO_CONV_KERNELS") == nullptr;
     if (fuse) {
         FusedArgs f;
-        f.x = x; f.w0_img = t.d_w0_img; f.w1_img = t.d_w1_img; f.act = t.act; f.pool_fc = t.fc_a;
+        f.x = x; f.w0_img = t.plain0 ? t.d_w0_plain : t.d_w0_img; f.plain0 = t.plain0 ? 1 : 0; f.w1_img = t.d_w1_img; f.act = t.act; f.pool_fc = t.fc_a;
         f.p1_out = m.cfg.keep_all_activations ? t.p1 : nullptr;          // the pooled first-block map normally never leaves the SM
         t.p1_valid = (f.p1_out != nullptr);
         f.B = n; f.H = c0.H; f.W = c0.W; f.H1 = c1.H; f.W1 = c1.W; f.Ho = c1.Ho; f.Wo = c1.Wo; f.Hp = c1.Hp; f.Wp = c1.Wp;
@@ -305,7 +319,7 @@ int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const in
         w.alpha = m.cfg.alpha_conv;
         TP_LAUNCH(m, "conv0_wide_tcgen05", launch_conv_wide(w, t.cin_pad, c0.Cout, t.sms, s));
     } else if (t.d_w0_img != nullptr && (t.x3 || getenv("BCAD_CONV0_CUDA_CORES") == nullptr))
-        TP_LAUNCH(m, "conv0_first_tcgen05", launch_conv_first_tc(x, t.d_w0_img, t.p1, n, c0.H, c0.W, m.cfg.pad, c0.Cout, m.cfg.alpha_conv, t.x3, t.sms, s));
+        TP_LAUNCH(m, "conv0_first_tcgen05", launch_conv_first_tc(x, t.plain0 ? t.d_w0_plain : t.d_w0_img, t.p1, n, c0.H, c0.W, m.cfg.pad, c0.Cout, m.cfg.alpha_conv, t.x3, t.plain0, t.sms, s));
     else
         TP_LAUNCH(m, "conv0_first_pool", launch_conv_first_pool(x, t.d_w0, t.d_b0, t.p1, n, c0.H, c0.W, m.cfg.pad, c0.Cout, m.cfg.alpha_conv, s));
     IgemmArgs a;

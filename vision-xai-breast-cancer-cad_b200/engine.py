@@ -337,13 +337,17 @@ class Engine:
     # ------------------------------------------------------------------ hot path, host buffers (end to end)
     def predict_explain_host(self, x: np.ndarray, class_idx: Optional[np.ndarray] = None, grad_mode: str = "logit",
                              heat_out: Optional[np.ndarray] = None, want_heat: bool = True, heat_dtype=np.float32):
-        """x: float32 [B,H,W,C] host array (pinned memory makes the copies asynchronous).
+        """x: float32 [B,H,W,C] host array (pinned memory makes the copies asynchronous), or uint8 [B,H,W,C] 0-255 pixels,
+        which the device normalises as ``float32(x) / 255`` (app.py:71, GRADCAM.py:46): a quarter of the host->device bytes.
         -> (cls int32 [B], probs [B,nc], logits [B,nc], heat [B,H,W]) as host arrays.
         heat_dtype=np.uint8 returns ``heatmap_uint8 = (cam * 255).astype(uint8)`` (GRADCAM.py:70) instead of the float32 map:
         a quarter of the device->host bytes of a PCIe-bound call."""
         u8 = np.dtype(heat_dtype) == np.uint8
         h, w, c = self.spec.input_shape
-        if x.dtype != np.float32 or not x.flags["C_CONTIGUOUS"]:
+        x8 = x.dtype == np.uint8
+        if x8:
+            x = np.ascontiguousarray(x)
+        elif x.dtype != np.float32 or not x.flags["C_CONTIGUOUS"]:
             x = np.ascontiguousarray(x, dtype=np.float32)
         if x.ndim == 3:
             x = x[None]
@@ -361,6 +365,11 @@ class Engine:
         ci = None
         if class_idx is not None:
             ci = np.ascontiguousarray(np.broadcast_to(np.asarray(class_idx, dtype=np.int32).reshape(-1), (B,)))
+        if x8:
+            hf, h8 = (None, heat) if u8 else (heat, None)
+            _lib.check(self.lib.bcad_predict_explain_host_u8in(self._h, _ptr(x), B, _ptr(ci), _lib.GRAD_MODE[grad_mode], _ptr(logits),
+                                                               _ptr(probs), _ptr(cls), _ptr(hf), _ptr(h8)))
+            return cls, probs, logits, heat
         fn = self.lib.bcad_predict_explain_host_u8 if (u8 and want_heat) else self.lib.bcad_predict_explain_host
         _lib.check(fn(self._h, _ptr(x), B, _ptr(ci), _lib.GRAD_MODE[grad_mode], _ptr(logits), _ptr(probs), _ptr(cls), _ptr(heat)))
         return cls, probs, logits, heat
