@@ -639,7 +639,7 @@ static int predict_explain_host_impl(bcad_model* mm, const float* x_host, const 
     // transfer/compute chunk: small enough that the PCIe pipeline fills quickly (the link, ~52 GB/s per direction, is the
     // end-to-end bound), large enough to keep the kernels efficient.  BCAD_HOST_CHUNK overrides (tuning).
     // Buffers are sized for 128 images; a call uses about a quarter of its batch per chunk (32..128 images: measured at 512
-    // images, float32 in/out 3.73 ms with 64 or 128, 8-bit in/out 2.11 ms with 64, 1.73 ms with 128, 1.80 ms with 256).
+    // images, float32 in/out 3.6-3.7 ms with 64, 3.7-3.8 with 128; 8-bit in/out 2.11 ms with 64, 1.73 ms with 128, 1.80 ms with 256).
     int chunk = std::min(m->cfg.max_batch, 128);
     if (const char* e = getenv("BCAD_HOST_CHUNK")) chunk = std::max(1, std::min(m->cfg.max_batch, atoi(e)));
     {
@@ -684,7 +684,10 @@ static int predict_explain_host_impl(bcad_model* mm, const float* x_host, const 
     std::vector<int> sizes;
     {
         int C0 = X.chunk;
-        if (getenv("BCAD_HOST_CHUNK") == nullptr) C0 = std::min(X.chunk, std::max(32, ((B + 3) / 4 + 31) / 32 * 32));
+        // float32 images: the link is the bound and 64-image chunks fill the pipeline sooner; 8-bit images: compute is the bound
+        // and 128-image chunks run the kernels more efficiently
+        if (getenv("BCAD_HOST_CHUNK") == nullptr)
+            C0 = std::min(std::min(X.chunk, x8_host ? 128 : 64), std::max(32, ((B + 3) / 4 + 31) / 32 * 32));
         int left = B;
         std::vector<int> head, tail;
         // measured on the bench workload (512 images): uniform 64-image chunks 3.62 ms, ramped 3.93 ms -- the small
