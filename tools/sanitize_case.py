@@ -13,6 +13,15 @@ for prec in ("fp16", "fp16x3", "fp32"):
     e.set_weights(p.conv_w, p.conv_b, p.dense_w, p.dense_b)
     cls, probs, logits, heat = e.predict_explain(x, None, "logit")
     h = e.predict_explain_host(x, None, "logit")
-    print(prec, cls.tolist(), float(heat.max()), h[0].tolist())
+    x8 = np.clip(np.rint(x * 255.0), 0, 255).astype(np.uint8)
+    h8 = e.predict_explain_host(x8, None, "logit", heat_dtype=np.uint8)       # 8-bit pixels in, heatmap_uint8 out
+    print(prec, cls.tolist(), float(heat.max()), h[0].tolist(), int(h8[3].max()))
     e.close()
+    if prec == "fp16":                                                       # the fused two-block kernel on a small case
+        os.environ["BCAD_FUSED_CONV"] = "1"
+        e = bcad_b200.Engine(spec, precision=prec, max_batch=4)
+        e.set_weights(p.conv_w, p.conv_b, p.dense_w, p.dense_b)
+        print("fused", e.predict_explain(x, None, "logit")[0].tolist())
+        e.close()
+        del os.environ["BCAD_FUSED_CONV"]
 print("done")
