@@ -443,8 +443,10 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
         mbar_init(wbar, 1);
         fence_barrier_init();
     }
+    // accumulator columns per output row: COUT, or 2*COUT in the fp16x3 mode ([x.w_hi sums | x_hi.w_lo sums], added in the epilogue)
+    constexpr int ACC = X3 ? 2 * COUT : COUT;
     if (warp == 0) {
-        tmem_alloc(tmem_slot, 256);
+        tmem_alloc(tmem_slot, 4 * ACC);
         tmem_relinquish();
     }
     fence_proxy_async();
@@ -541,9 +543,11 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
                     const uint32_t ones_lo = ((uint32_t)((128 * 16) >> 4) << 16) | ((smem_u32(s_ones) & 0x3FFFFu) >> 4);
                     for (int r = 0; r < 2; ++r) {
                         if (2 * p + r >= nrows || (a.debug & 8)) break;     // debug bit 3: timing experiment without MMAs
-                        const uint32_t d_tmem = tmem + j * (2 * COUT) + r * COUT;
-                        // bias K-step: D = ones x {b_hi, b_lo} (initialises the accumulator with the fp32-exact bias)
-                        umma_f16_if(leader, d_tmem, desc64(ones_lo, d_hi), desc64(b_lo0 + (uint32_t)(L::WBYTES >> 4), d_hi), idesc, 0u);
+                        const uint32_t d_tmem = tmem + j * (2 * ACC) + r * ACC;
+                        // bias K-step: D = ones x {b_hi, b_lo} (initialises the accumulator with the fp32-exact bias); in the fp16x3
+                        // mode the first N = 128 MMA initialises both column halves and the bias is accumulated last
+                        if constexpr (!X3)
+                            umma_f16_if(leader, d_tmem, desc64(ones_lo, d_hi), desc64(b_lo0 + (uint32_t)(L::WBYTES >> 4), d_hi), idesc, 0u);
 #pragma unroll
                         for (int dy = 0; dy < 3; ++dy) {
                             const int i = 2 * p + r + dy;                    // band-local input row
@@ -563,20 +567,26 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
                                 } else {
                                     // fp16x3: input octets [x_hi (H) | x_lo (H)], weight octets per tap [w_hi (H) | w_lo (H)], H = CIN/16:
                                     //   x_hi.w_hi + x_lo.w_hi + x_hi.w_lo   (x_lo.w_lo ~ 2^-22 is dropped)
+                                    // The weight image interleaves the halves per octet, [w_hi(c) | w_lo(c)] = 128 B-operand columns, so
+                                    // x_hi takes both in ONE N = 128 MMA (columns [0, COUT) += x_hi.w_hi, [COUT, 2 COUT) += x_hi.w_lo:
+                                    // 64 cycles instead of 2 x 48) and x_lo.w_hi is an N = 64 MMA over the first half of the same block.
                                     constexpr int HP = CIN / 32;               // octet PAIRS per half
+                                    constexpr uint32_t idesc2 = make_idesc_f16(128, 2 * COUT);
+                                    constexpr uint32_t b2_lo_t = (uint32_t)((2 * COUT * 16) >> 4) << 16;      // LBO: [hi | lo] blocks of consecutive octets
+                                    const uint32_t b2_lo0 = b2_lo_t | ((w_base & 0x3FFFFu) >> 4);
 #pragma unroll
-                                    for (int g3 = 0; g3 < 3; ++g3)
-#pragma unroll
-                                        for (int kp = 0; kp < HP; ++kp) {
-                                            const int a_pair = (g3 == 1 ? HP : 0) + kp;         // x_hi, x_lo, x_hi
-                                            const int b_pair = (g3 == 2 ? HP : 0) + kp;         // w_hi, w_hi, w_lo
-                                            umma_f16_if(leader, d_tmem, desc64(a_lo0 + (uint32_t)((a_pair * 2 * L::LBO + dx * 16) >> 4), d_hi),
-                                                      desc64(b_lo0 + (uint32_t)((((dy * 3 + dx) * L::CHUNKS + 2 * b_pair) * (COUT * 16)) >> 4), d_hi),
-                                                      idesc, 1u);
-                                        }
+                                    for (int kp = 0; kp < HP; ++kp) {
+                                        const uint32_t boff = (uint32_t)(((((dy * 3 + dx) * (L::CHUNKS / 2) + 2 * kp) * 2) * (COUT * 16)) >> 4);
+                                        umma_f16_if(leader, d_tmem, desc64(a_lo0 + (uint32_t)((kp * 2 * L::LBO + dx * 16) >> 4), d_hi),
+                                                    desc64(b2_lo0 + boff, d_hi), idesc2, (dy | dx | kp) ? 1u : 0u);
+                                        umma_f16_if(leader, d_tmem, desc64(a_lo0 + (uint32_t)(((HP + kp) * 2 * L::LBO + dx * 16) >> 4), d_hi),
+                                                    desc64(b2_lo0 + boff, d_hi), idesc, 1u);
+                                    }
                                 }
                             }
                         }
+                        if constexpr (X3)
+                            umma_f16_if(leader, d_tmem, desc64(ones_lo, d_hi), desc64(b_lo0 + (uint32_t)(L::WBYTES >> 4), d_hi), idesc, 1u);
                     }
                     umma_commit_if(leader, &empty[g % IG_STAGES]);      // stage p is dead once these MMAs retire
                     umma_commit_if(leader, &tfull[j]);
@@ -620,12 +630,16 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
 #pragma unroll 1
                         for (int sub = 0; sub < 2; ++sub) {                  // 16 channels at a time (register budget)
                             const int cbase = half * 32 + sub * 16;
-                            float v0[16], v1[16];
-                            tmem_ld16(tmem + lane_off + j * (2 * COUT) + cbase, v0);
-                            tmem_ld16(tmem + lane_off + j * (2 * COUT) + COUT + cbase, v1);
+                            float v0[16], v1[16], w0[16], w1[16];
+                            tmem_ld16(tmem + lane_off + j * (2 * ACC) + cbase, v0);
+                            tmem_ld16(tmem + lane_off + j * (2 * ACC) + COUT + cbase, w0);           // the x_hi.w_lo sums
+                            tmem_ld16(tmem + lane_off + j * (2 * ACC) + ACC + cbase, v1);
+                            tmem_ld16(tmem + lane_off + j * (2 * ACC) + ACC + COUT + cbase, w1);
                             tmem_ld_wait();
 #pragma unroll
                             for (int q = 0; q < 16; ++q) {
+                                v0[q] += w0[q];
+                                v1[q] += w1[q];
                                 v0[q] = fmaxf(v0[q], a.alpha * v0[q]);
                                 v1[q] = fmaxf(v1[q], a.alpha * v1[q]);
                             }
@@ -765,7 +779,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
     if (STAGED && tid == 64) bulk_wait<0>();         // staged rows must be read out before the CTA's smem goes away
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 256);
+    if (warp == 0) tmem_dealloc(tmem, 4 * ACC);
 }
 
 template <int CIN, int COUT, bool X3>

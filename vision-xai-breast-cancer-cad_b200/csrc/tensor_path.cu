@@ -178,7 +178,7 @@ int tensor_path_commit(Model& m) {
     // ---- conv1 weight image: [tap*(Cin/8)+chunk][cout][8] fp16
     {
         const int chunks = c1.Cin / 8;
-        const int vch = t.x3 ? 2 * chunks : chunks;                          // x3: octets [w_hi | w_lo] per tap
+        const int vch = t.x3 ? 2 * chunks : chunks;                          // x3: octets [w_hi(0) w_lo(0) w_hi(1) w_lo(1) ...] per tap
         const size_t wel = (size_t)9 * vch * c1.Cout * 8;
         std::vector<uint16_t> img(wel + (size_t)2 * c1.Cout * 8, 0);         // + bias tile [2 chunks][Cout][8]
         for (int tap = 0; tap < 9; ++tap)
@@ -187,8 +187,11 @@ int tensor_path_commit(Model& m) {
                     for (int e = 0; e < 8; ++e) {
                         const float w = c1.h_w[((size_t)f * 9 + tap) * c1.Cin + ch * 8 + e];
                         const uint16_t q = f2h(w);
-                        img[(((size_t)tap * vch + ch) * c1.Cout + f) * 8 + e] = q;
-                        if (t.x3) img[(((size_t)tap * vch + chunks + ch) * c1.Cout + f) * 8 + e] = f2h(w - h2f(q));
+                        if (!t.x3) img[(((size_t)tap * vch + ch) * c1.Cout + f) * 8 + e] = q;
+                        else {                                   // halves interleaved per octet: one N = 2*Cout operand block [w_hi(ch) | w_lo(ch)]
+                            img[(((size_t)tap * vch + 2 * ch) * c1.Cout + f) * 8 + e] = q;
+                            img[(((size_t)tap * vch + 2 * ch + 1) * c1.Cout + f) * 8 + e] = f2h(w - h2f(q));
+                        }
                     }
         for (int f = 0; f < c1.Cout; ++f) {                                 // bias K-step rows: {b_hi, b_lo, 0 ...}
             const float bhi = h2f(f2h(c1.h_b[f]));
