@@ -14,6 +14,8 @@
 // classes each (2 x 32 accumulator columns; the running maximum stays in registers as packed halves): four teams are what
 // it takes to hide a tile's dependent build -> MMA -> TMEM-load chain, and four 128-column teams would not fit in TMEM.
 // Reference semantics: Conv2d/valid conv + bias + LeakyReLU + MaxPool2d(2), twice (ADCNNM.py:48,76; Classes/CNNModel.py:227-261).
+#include <stdio.h>
+
 #include "../../include/bcad.h"
 #include "common.cuh"
 #include "sm100.cuh"
@@ -50,6 +52,13 @@ struct FusedSmem {
 
 // PLAIN: first-block operands as plain fp16 (the fp16 mode): K slots [x(9) 1 1 0..] against [w(9) b_hi b_lo 0..], one K-step
 // per pool class and two 16-byte im2col stores per row; !PLAIN: the hi/lo split image (three stores, two K-steps)
+#ifdef FZ_TRACE
+__device__ long long g_fz_trace[8];
+#define FZ_T(x) x
+#else
+#define FZ_T(x)
+#endif
+
 template <bool PLAIN>
 __global__ void __launch_bounds__(FZ_THREADS, 1) conv_fused_kernel(FusedArgs a) {
     using L = FusedSmem;
@@ -273,10 +282,14 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) conv_fused_kernel(FusedArgs a) 
         const uint64_t im_desc0 = a_tmpl | (uint64_t)((smem_u32(smem + L::OFF_IM) & 0x3FFFFu) >> 4);
         const uint64_t w0_desc0 = b_tmpl | (uint64_t)((smem_u32(s_w0) & 0x3FFFFu) >> 4);
         uint32_t rphase = 0;                                  // bit t = parity team t's `ready` barrier is expected to complete next
+        FZ_T(long long tr_full = 0; long long tr_tempty = 0; long long tr_issue = 0; long long tr_serv = 0; long long tr_nserv = 0;)
+        FZ_T(const long long tr_begin = clock64();)
         auto service_teams = [&]() {
 #pragma unroll
             for (int t = 0; t < FZ_TEAMS; ++t) {
                 if (mbar_test_wait(&ready[t], (rphase >> t) & 1)) {
+                    FZ_T(const long long s0 = clock64();)
+                    FZ_T(tr_nserv += 1;)
                     rphase ^= 1u << t;
                     tc_fence_after();
 #pragma unroll
@@ -286,6 +299,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) conv_fused_kernel(FusedArgs a) 
                             umma_f16_if(leader, tmem + 256 + t * 64 + qc * FZ_C0, im_desc0 + (uint64_t)((t * 16384 + qc * 8192 + ks * 4096) >> 4),
                                         w0_desc0 + (uint64_t)((ks * 2 * FZ_C0 * 16) >> 4), idesc0, ks);
                     umma_commit_if(leader, &tbar[t]);
+                    FZ_T(tr_serv += clock64() - s0;)
                 }
             }
         };
@@ -301,10 +315,13 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) conv_fused_kernel(FusedArgs a) 
             const int nrows = min(a.band_rows, a.Ho - y0);
             const int npairs = (nrows + 1) / 2;
             for (int p = 0; p < npairs; ++p, ++g, ++acc_it) {
+                FZ_T(const long long w0 = clock64(); const long long sv0 = tr_serv;)
                 if (p == 0) wait_serving(&full[g % S], (g / S) & 1);
                 wait_serving(&full[(g + 1) % S], ((g + 1) / S) & 1);
+                FZ_T(const long long w1 = clock64(); const long long sv1 = tr_serv; tr_full += (w1 - w0) - (sv1 - sv0);)
                 const uint32_t j = acc_it & 1;
                 if (acc_it >= 2) wait_serving(&tempty[j], ((acc_it >> 1) - 1) & 1);
+                FZ_T(const long long w2 = clock64(); const long long sv2 = tr_serv; tr_tempty += (w2 - w1) - (sv2 - sv1);)
                 tc_fence_after();
                 constexpr uint32_t d_hi = (uint32_t)(128 >> 4) | (1u << 14);
                 constexpr uint32_t a_lo_t = (uint32_t)(L::LBO >> 4) << 16;
@@ -335,10 +352,13 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) conv_fused_kernel(FusedArgs a) 
                 }
                 umma_commit_if(leader, &empty[g % S]);
                 umma_commit_if(leader, &tfull[j]);
+                FZ_T(tr_issue += (clock64() - w2) - (tr_serv - sv2);)
             }
             umma_commit_if(leader, &empty[g % S]);
             ++g;
         }
+        FZ_T(if (blockIdx.x == 0 && lane == 0) { g_fz_trace[0] = clock64() - tr_begin; g_fz_trace[1] = tr_full; g_fz_trace[2] = tr_tempty;
+                                                 g_fz_trace[3] = tr_issue; g_fz_trace[4] = tr_serv; g_fz_trace[5] = tr_nserv; g_fz_trace[6] = acc_it; })
     } else {
         // ================================ second-block epilogue (4 warps, one per TMEM lane quadrant) ================================
         const int quad = warp & 3;
@@ -432,12 +452,20 @@ int launch_conv_fused(const FusedArgs& a, int sms, cudaStream_t s) {
     if (a.plain0) {
         BCAD_CUDA_CHECK(cudaFuncSetAttribute(conv_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedSmem::TOTAL));
         conv_fused_kernel<true><<<grid, FZ_THREADS, FusedSmem::TOTAL, s>>>(a);
-        BCAD_CUDA_CHECK(cudaGetLastError());
-        return BCAD_OK;
+    } else {
+        BCAD_CUDA_CHECK(cudaFuncSetAttribute(conv_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedSmem::TOTAL));
+        conv_fused_kernel<false><<<grid, FZ_THREADS, FusedSmem::TOTAL, s>>>(a);
     }
-    BCAD_CUDA_CHECK(cudaFuncSetAttribute(conv_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedSmem::TOTAL));
-    conv_fused_kernel<false><<<grid, FZ_THREADS, FusedSmem::TOTAL, s>>>(a);
     BCAD_CUDA_CHECK(cudaGetLastError());
+#ifdef FZ_TRACE
+    if (a.debug & 64) {
+        long long h[8];
+        cudaDeviceSynchronize();
+        cudaMemcpyFromSymbol(h, g_fz_trace, sizeof(h));
+        fprintf(stderr, "fz_trace: total %lld | wait full %lld | wait tempty %lld | issue second block %lld | serve teams %lld (%lld requests) | pairs %lld\n",
+                h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
+    }
+#endif
     return BCAD_OK;
 }
 
