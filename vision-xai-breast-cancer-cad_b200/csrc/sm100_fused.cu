@@ -328,11 +328,12 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) conv_fused_kernel(FusedArgs a) 
                 constexpr uint32_t b_lo_t = (uint32_t)((COUT * 16) >> 4) << 16;
                 const uint32_t b_lo0 = b_lo_t | ((w_base & 0x3FFFFu) >> 4);
                 const uint32_t ones_lo = ((uint32_t)((128 * 16) >> 4) << 16) | ((smem_u32(s_ones) & 0x3FFFFu) >> 4);
+                const bool lead2 = leader && !(a.debug & 128);       // debug bit 7: the second block's MMA instructions run predicated off
                 for (int r = 0; r < 2; ++r) {
                     if (2 * p + r >= nrows || (a.debug & 8)) break;     // debug bit 3: no second-block MMAs (timing experiment)
                     service_teams();                          // between rows: a ready team waits for at most one row (19 MMAs)
                     const uint32_t d_tmem = tmem + j * (2 * COUT) + r * COUT;
-                    umma_f16_if(leader, d_tmem, desc64(ones_lo, d_hi), desc64(b_lo0 + (uint32_t)(L::WBYTES >> 4), d_hi), idesc, 0u);
+                    umma_f16_if(lead2, d_tmem, desc64(ones_lo, d_hi), desc64(b_lo0 + (uint32_t)(L::WBYTES >> 4), d_hi), idesc, 0u);
 #pragma unroll
                     for (int dy = 0; dy < 3; ++dy) {
                         const int i = 2 * p + r + dy;
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) conv_fused_kernel(FusedArgs a) 
                         for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
                             for (int ks = 0; ks < CIN / 16; ++ks)
-                                umma_f16_if(leader, d_tmem, desc64(a_lo0 + (uint32_t)((ks * 2 * L::LBO + dx * 16) >> 4), d_hi),
+                                umma_f16_if(lead2, d_tmem, desc64(a_lo0 + (uint32_t)((ks * 2 * L::LBO + dx * 16) >> 4), d_hi),
                                             desc64(b_lo0 + (uint32_t)((((dy * 3 + dx) * L::CHUNKS + 2 * ks) * (COUT * 16)) >> 4), d_hi),
                                             idesc, 1u);
                     }
