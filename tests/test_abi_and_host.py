@@ -145,3 +145,15 @@ def test_explainability_rejects_non_onehot():
     with pytest.raises(ValueError):
         E._class_of([0.5, 0.5], 2)
     assert E._class_of([0, 1], 2) == 1
+
+
+def test_u8_pixel_normalisation_is_one_rounding_whichever_way_the_reference_divides():
+    """bcad_predict_explain_host_u8in computes x = float32(u8) / 255.0f with IEEE division.  The reference's callers divide in
+    float32 (app.py:71 `torch.tensor(resized, dtype=torch.float32) / 255.0`) or in float64 followed by a float32 cast
+    (GRADCAM.py:46 `img / 255.0` -> the float32 input tensor): for all 256 pixel values both give the same float32."""
+    import torch
+    px = np.arange(256, dtype=np.uint8)
+    f32 = px.astype(np.float32) / np.float32(255.0)
+    assert np.array_equal(f32, (px / 255.0).astype(np.float32))
+    assert np.array_equal(f32, (torch.tensor(px, dtype=torch.float32) / 255.0).numpy())
+    assert f32[0] == 0.0 and f32[255] == 1.0
