@@ -81,6 +81,12 @@ typedef struct bcad_config {
                                              *    on the 16-bit path: also write out the pooled first-block map, which the fused
                                              *    conv kernel otherwise keeps on chip (bcad_get_tensor(BCAD_T_POOL_OUT, 0)) */
     int32_t device;                         /* CUDA device ordinal */
+    float refine_margin;                    /* BCAD_PREC_F16 only, 0 = off: an image whose two largest logits are closer than this is
+                                             * re-run through the split-operand (fp32-grade) kernels inside the same call, so that the
+                                             * predicted class is the fp32-grade one (north_star: classes bit-exact; the 16-bit logit
+                                             * error is ~3e-3, ADCNNM.py:72-78 + app.py:589 torch.max).  Needs a shape BCAD_PREC_F16X3 covers. */
+    int32_t refine_capacity;                /* images per chunk the refinement pass is sized for; 0 = max(8, max_batch/32).  Flagged images
+                                             * beyond it keep their 16-bit result and are counted (bcad_refine_stats). */
 } bcad_config;
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
@@ -209,6 +215,9 @@ BCAD_API int bcad_get_conv_weights(bcad_model* m, int conv_idx, float* filters_f
 BCAD_API int bcad_get_dense_weights(bcad_model* m, int dense_idx, float* w_units_in_host, float* bias_host);
 
 /* ---- introspection ---------------------------------------------------------------------------- */
+/* refinement counters since creation (cfg.refine_margin > 0): images re-run at fp32 grade, flagged images that did not fit
+ * cfg.refine_capacity (kept their 16-bit result).  Synchronises the device.  Both 0 when refinement is off. */
+BCAD_API int bcad_refine_stats(bcad_model* m, int64_t* refined, int64_t* overflowed);
 /* kernels launched by this handle since creation (bench.py reports the delta as gpu_launches) */
 BCAD_API int64_t bcad_launch_count(bcad_model* m);
 /* 1 when the handle runs the tcgen05 fast path for its conv/fc stack, 0 when it runs fp32 CUDA cores */
@@ -228,7 +237,8 @@ BCAD_API int bcad_selftest_umma(const void* a_img_dev, int a_bytes, const void* 
                        const int32_t* params_host, float* d_dev, void* stream);
 
 /* Micro-benchmark behind DESIGN.md's operand-layout choices: cycles of `reps` back-to-back 128xNx16 UMMAs and of
- * `reps` TMEM loads.  p = {N, a_layout, b_layout, a_lbo, a_sbo, b_lbo, b_sbo, reps, ld_warps, ld_x16, a_off, alternate}; out_dev: int64[3]. */
+ * `reps` TMEM loads.  p = {N, a_layout, b_layout, a_lbo, a_sbo, b_lbo, b_sbo, reps, ld_warps, ld_x16, a_off, alternate, grid,
+ * concurrent, st_warps}; out_dev: int64[6] = {MMA cycles of CTA 0, TMEM-load cycles, -, slowest CTA's MMA cycles, loads done, stores done}. */
 BCAD_API int bcad_selftest_umma_bench(const int32_t* p, long long* out_dev, void* stream);
 
 #ifdef __cplusplus

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from util import engine_from, oracle_heatmaps, ocnn
+from util import compare_all_images, engine_from, oracle_heatmaps, ocnn
 
 pytestmark = pytest.mark.gpu
 
@@ -41,20 +41,51 @@ def test_cfg1_245_images_in_batches_of_32(precision, tol):
     c2, p2, l2, h2 = eng_big.predict_explain(x, None, "logit")
     rnd = 2e-3 if precision == "fp16" else 2e-5
     assert np.abs(logits - l2.cpu().numpy()).max() <= rnd * max(1.0, np.abs(logits).max())
-    big_err = np.abs(heat - h2.cpu().numpy()).reshape(245, -1).max(axis=1)
-    assert np.sort(big_err)[:-3].max() <= 5 * rnd, np.sort(big_err)[-5:]    # (a rounding-level logit change can flip a LeakyReLU kink)
-    # the ragged tail against the oracle (images 224..244 live in the 21-image batch)
-    idx = np.array([0, 31, 32, 224, 244])
-    o_cls, cache, A, dA, o_heat = oracle_heatmaps(cfg, p, x[idx], None, "logit")
-    lg = cache.logits.numpy()
-    assert np.abs(logits[idx] - lg).max() <= tol * max(1.0, np.abs(lg).max())
-    margin = np.abs(lg[:, 0] - lg[:, 1])
-    safe = margin > 4 * tol * max(1.0, np.abs(lg).max())
-    assert np.array_equal(cls[idx][safe], o_cls[safe])
-    err = np.abs(heat[idx] - o_heat).reshape(len(idx), -1).max(axis=1)
-    assert np.sort(err)[:-1].max() <= tol, err                              # at most one LeakyReLU-kink image (DESIGN: 16-bit caveat)
+    assert np.array_equal(cls, c2.cpu().numpy())
+    # every image of both handles against the oracle (heat-maps of two handles are compared through the oracle, not with each
+    # other: a rounding-level change of a hidden pre-activation near 0 legitimately picks the other LeakyReLU branch)
+    tau = 1.5e-2 if precision == "fp16" else 1e-4
+    for eng in (eng32, eng_big):
+        (r,) = compare_all_images(cfg, p, x, eng, [(None, "logit")], tau=tau)
+        assert r["mask_violations"] == 0
+        assert r["cls_equal"].all(), np.flatnonzero(~r["cls_equal"])
+        assert r["logit_err"].max() <= tol * max(1.0, r["logit_absmax"].max())
+        assert r["heat_err"].max() <= tol, np.sort(r["heat_err"])[-5:]
     eng32.close()
     eng_big.close()
+
+
+def test_2048_images_every_one_against_the_oracle():
+    """North-star gate on the benchmarked configuration (cfg 2 network, 256x256x1): 2048 distinct images, BOTH top-gradient
+    modes, BOTH tensor-core modes (fp16 with small-margin refinement = the benchmarked path; fp16x3 = the fp32-grade default of
+    the drop-in mirrors), every image compared with the float64 oracle -- classes identical on all of them, logits and
+    heat-maps within the mode's tolerance on all of them.  No image is dropped, no flip allowance: the only latitude is the
+    LeakyReLU' branch of hidden units whose oracle |z| is below the path's stated pre-activation error bound
+    (util.compare_all_images), and the number of images that needed it is printed."""
+    cfg, p = _canonical()
+    n = 2048
+    x = ocnn.synth_images(n, (256, 256, 1), seed=424242)
+    e16 = engine_from(cfg, p, precision="fp16", max_batch=512)
+    ex3 = engine_from(cfg, p, precision="fp16x3", max_batch=512)
+    assert e16.refine_margin > 0
+    bounds = {"fp16": (1e-2, 1e-2, 1.5e-2), "fp16x3": (2e-4, 5e-4, 5e-4)}       # logits, heat-maps, tau
+    res = compare_all_images(cfg, p, x, [(e16, bounds["fp16"][2]), (ex3, bounds["fp16x3"][2])],
+                             [(None, "logit"), (np.arange(n) % 2, "softmax_ce")], tau=None)
+    refined, overflow = e16.refine_stats()
+    for precision, per_mode in zip(("fp16", "fp16x3"), res):
+        tol_l, tol_h, _ = bounds[precision]
+        for name, r in zip(("predicted class / logit", "alternating class / softmax-CE"), per_mode):
+            print(f"[{precision}] {name}: class mismatches {int((~r['cls_equal']).sum())}/{n}, max logit err {r['logit_err'].max():.3e}, "
+                  f"max heat err {r['heat_err'].max():.3e}, images with a near-kink branch override {int(r['overridden'].sum())}, "
+                  f"smallest margin {r['margin'].min():.3e}")
+            assert r["mask_violations"] == 0
+            assert np.array_equal(r["cls_equal"], np.ones(n, bool))
+            assert r["logit_err"].max() <= tol_l * max(1.0, r["logit_absmax"].max())
+            assert r["heat_err"].max() <= tol_h
+    print(f"[fp16] images re-run at fp32 grade (top-2 logit gap < {e16.refine_margin}): {refined} of {2 * n} forwarded, overflowed {overflow}")
+    assert overflow == 0 and refined > 0        # ~1 % of random-init images have a top-2 gap below the margin
+    e16.close()
+    ex3.close()
 
 
 def test_cfg4_8192_images_chunked_host_call():

@@ -1,54 +1,55 @@
 """16-bit (fp16 operand) tcgen05 path vs the float64 oracle.  Tolerance (north_star): logits / normalised heat-maps
-max-abs <= 1e-2; classes identical wherever the oracle's logit margin exceeds the 16-bit error bound; heat-maps compared
-on the images whose hidden-unit LeakyReLU masks agree with the oracle's (see _kink_flips)."""
+max-abs <= 1e-2 on EVERY image; classes identical on every image (the engine re-runs small-margin images at fp32 grade:
+``refine_margin``); the LeakyReLU kink of the hidden dense units is handled by ``util.compare_all_images`` (the oracle takes
+the device's branch for units whose |z| is below the path's stated pre-activation error, and nothing else)."""
 import numpy as np
 import pytest
 import torch
 
-from util import engine_from, oracle_heatmaps, ocnn
+from util import compare_all_images, engine_from, oracle_heatmaps, ocnn
 
 pytestmark = pytest.mark.gpu
 
 F16_TOL = 1e-2
+F16_TAU = 1.5e-2         # bound on the 16-bit path's hidden pre-activation error (largest seen on the canonical network: 6e-3)
 X3_LOGIT_TOL = 2e-4      # fp16x3: hi+lo split operands, fp32 accumulation -> fp32-grade
 X3_HEAT_TOL = 5e-4
+X3_TAU = 5e-4
 
 
 def _np(t):
     return t.detach().cpu().numpy()
 
 
-def _kink_flips(eng, cache, B):
-    """Images where the 16-bit forward lands on the other side of a LeakyReLU kink of a hidden dense unit than the
-    float64 oracle (|z| below the 16-bit error).  Grad-CAM is discontinuous there (the mask 1 vs alpha changes dz),
-    exactly like a class flip at a zero logit margin -- such images are counted, not compared."""
-    from bcad_b200 import _lib
-    flipped = np.zeros(B, bool)
-    for j in range(len(cache.z) - 1):
-        z_dev = _np(eng.get_tensor(_lib.T_DENSE_Z, j, B))
-        flipped |= ((z_dev > 0) != (cache.z[j].numpy() > 0)).any(axis=1)
-    return flipped
-
-
-def _check(cfg, p, x, eng, B, max_flip_frac=0.25):
+def _check(cfg, p, x, eng, B):
+    """Every image, both top-gradient modes: logits and heat-maps within 1e-2, classes equal (all images when the engine
+    refines small margins; otherwise wherever the oracle's margin exceeds the 16-bit logit error bound)."""
     assert eng.uses_tensor_path
-    for class_idx, mode in ((None, "logit"), (np.arange(B) % 2, "softmax_ce")):
-        cls, probs, logits, heat = eng.predict_explain(x, class_idx, mode)
-        o_cls, cache, A, dA, o_heat = oracle_heatmaps(cfg, p, x, class_idx, mode)
-        lg = cache.logits.numpy()
-        err_l = np.abs(_np(logits) - lg).max()
-        scale = max(1.0, np.abs(lg).max())
-        assert err_l <= F16_TOL * scale, f"logits err {err_l} (scale {scale})"
-        margin = np.abs(lg[:, 0] - lg[:, 1])
-        safe = margin > 4 * F16_TOL * scale
-        assert np.array_equal(_np(cls)[safe], o_cls[safe])
-        err_h = np.abs(_np(heat) - o_heat).max(axis=(1, 2))
-        flipped = _kink_flips(eng, cache, B) if B <= eng.max_batch else np.zeros(B, bool)
-        if class_idx is None:
-            flipped |= ~safe                      # predicted-class target: a class flip changes the target itself
-        assert flipped.sum() <= max(1, int(max_flip_frac * B)), f"{flipped.sum()} of {B} images crossed a LeakyReLU kink"
-        assert err_h[~flipped].max(initial=0.0) <= F16_TOL, f"heatmap err per image {err_h[~flipped]}"
-    return err_l, err_h
+    res = compare_all_images(cfg, p, x, eng, [(None, "logit"), (np.arange(B) % 2, "softmax_ce")], tau=F16_TAU)
+    for r, predicted_target in zip(res, (True, False)):
+        scale = max(1.0, r["logit_absmax"].max())
+        assert r["mask_violations"] == 0, "a hidden unit with |z| > tau took the other LeakyReLU branch"
+        assert r["logit_err"].max() <= F16_TOL * scale, f"logits err {r['logit_err'].max()} (scale {scale})"
+        if eng.refine_margin > 0:
+            assert r["cls_equal"].all(), f"classes differ on images {np.flatnonzero(~r['cls_equal'])}"
+            ok = np.ones(B, bool)
+        else:                                   # shapes the split-operand twin does not cover: no refinement available
+            ok = r["cls_equal"] | (r["margin"] < 2 * F16_TOL * scale)
+            assert ok.all()
+            ok = r["cls_equal"] | (not predicted_target)       # a flipped predicted class changes the Grad-CAM target itself
+        assert r["heat_err"][ok].max(initial=0.0) <= F16_TOL, f"heatmap err per image {r['heat_err']}"
+    return res
+
+
+def _check_x3(cfg, p, x, eng, modes):
+    res = compare_all_images(cfg, p, x, eng, modes, tau=X3_TAU)
+    for r in res:
+        scale = max(1.0, r["logit_absmax"].max())
+        assert r["mask_violations"] == 0
+        assert r["logit_err"].max() <= X3_LOGIT_TOL * scale, f"logits err {r['logit_err'].max()}"
+        assert r["cls_equal"].all()
+        assert r["heat_err"].max() <= X3_HEAT_TOL, f"heatmap err {r['heat_err']}"
+    return res
 
 
 def test_tensor_path_intermediates_small():
@@ -103,13 +104,7 @@ def test_tensor_path_wide_maps(shape, pad, precision):
     if precision == "fp16":
         _check(cfg, p, x, eng, 6)
     else:
-        cls, probs, logits, heat = eng.predict_explain(x, None, "logit")
-        o_cls, cache, A, dA, o_heat = oracle_heatmaps(cfg, p, x, None, "logit")
-        lg = cache.logits.numpy()
-        assert np.abs(_np(logits) - lg).max() <= X3_LOGIT_TOL * max(1.0, np.abs(lg).max())
-        flipped = _kink_flips(eng, cache, 6)
-        assert flipped.sum() <= 1
-        assert np.abs(_np(heat) - o_heat).max(axis=(1, 2))[~flipped].max(initial=0.0) <= X3_HEAT_TOL
+        _check_x3(cfg, p, x, eng, [(None, "logit")])
     eng.close()
 
 
@@ -291,21 +286,13 @@ def test_fp16x3_path_is_fp32_grade(shape, hidden, B, mb, pad):
     x = ocnn.synth_images(B, shape, seed=21)
     eng = engine_from(cfg, p, precision="fp16x3", max_batch=mb)
     assert eng.uses_tensor_path
-    cls, probs, logits, heat = eng.predict_explain(x, None, "logit")
-    o_cls, cache, A, dA, o_heat = oracle_heatmaps(cfg, p, x, None, "logit")
-    lg = cache.logits.numpy()
-    scale = max(1.0, np.abs(lg).max())
-    err_l = np.abs(_np(logits) - lg).max()
-    assert err_l <= X3_LOGIT_TOL * scale, f"logits err {err_l}"
-    assert np.array_equal(_np(cls), o_cls)
+    _check_x3(cfg, p, x, eng, [(None, "logit"), (np.arange(B) % 2, "softmax_ce")])
     if B <= mb:
+        cls, probs, logits, heat = eng.predict_explain(x, None, "logit")
+        o_cls, cache, A, dA, o_heat = oracle_heatmaps(cfg, p, x, None, "logit")
         last = len(cfg.conv_layers) - 1
         A_dev = _np(eng.get_tensor(_lib.T_CONV_OUT, last, B)).reshape(A.shape)
         assert np.abs(A_dev - A).max() <= 1e-4 * max(1.0, np.abs(A).max()), "conv1 activations"
-    flipped = _kink_flips(eng, cache, B) if B <= mb else np.zeros(B, bool)
-    err_h = np.abs(_np(heat) - o_heat).max(axis=(1, 2))
-    assert flipped.sum() <= max(1, B // 50)
-    assert err_h[~flipped].max(initial=0.0) <= X3_HEAT_TOL, f"heatmap err {err_h}"
     eng.close()
 
 
@@ -339,7 +326,7 @@ def test_numpy_flavour_on_the_split_operand_tensor_path(shape, hidden, B, kind):
         assert np.array_equal(_np(cls), o_cls)
         assert np.abs(_np(logits) - lg).max() <= X3_LOGIT_TOL * max(1.0, np.abs(lg).max())
         assert np.abs(_np(probs) - cache.probs.numpy()).max() <= X3_LOGIT_TOL
-        flipped = _kink_flips(eng, cache, B)
-        assert flipped.sum() <= 1
-        assert np.abs(_np(heat) - o_heat).max(axis=(1, 2))[~flipped].max(initial=0.0) <= X3_HEAT_TOL
+        for j in range(len(cfg.hidden_units)):            # no hidden unit on the other side of its LeakyReLU kink (would need |z| < 5e-4)
+            assert np.array_equal(_np(eng.get_tensor(_lib.T_DENSE_Z, j, B)) > 0, cache.z[j].numpy() > 0)
+        assert np.abs(_np(heat) - o_heat).max() <= X3_HEAT_TOL
     eng.close()

@@ -53,3 +53,48 @@ def test_leaky_relu_at_exactly_zero():
     # every element of a constant window ties: the duplicated gradient is g_pool at all four positions
     want = np.repeat(np.repeat(c["g_pool"].reshape(1, 1, 2, 1), 2, axis=1), 2, axis=2)
     np.testing.assert_allclose(cag[0].numpy(), want, atol=1e-12)
+
+
+def test_every_image_comparison_helper_with_a_float32_stand_in_engine():
+    """oracle/compare.py (the helper behind the 2048-image GPU gate and bench.py's `check`) on the CPU: an engine stand-in that
+    evaluates the oracle in float32 passes at float32-grade bounds on every image; one that perturbs a hidden pre-activation
+    across 0 by more than tau is reported as a mask violation, and a flipped class as a class mismatch."""
+    import torch
+    from oracle import cnn as ocnn, gradcam as ogc
+    from oracle.compare import compare_all_images
+    cfg = ocnn.NetConfig.torch_flavour((24, 24, 1), 2, [(4, 3), (8, 3)], [12, 6], 0.01)
+    p = ocnn.init_params(cfg, seed=5, bias_std=0.05)
+    x = ocnn.synth_images(9, (24, 24, 1), seed=3)
+
+    class Stand:
+        max_batch = 4
+
+        def __init__(self, bump=0.0, flip=False):
+            self.bump, self.flip = bump, flip
+
+        def predict_explain(self, xs, class_idx, mode):
+            c = ocnn.forward(cfg, p, xs, dtype=torch.float32)
+            if self.bump:
+                z = c.z[0].clone()
+                z[0, 0] = -z[0, 0] + (self.bump if z[0, 0] < 0 else -self.bump)      # unit 0 of image 0 lands on the other side
+                c.z[0] = z
+            cls = c.logits.argmax(dim=-1)
+            if self.flip:
+                cls = 1 - cls
+            ci = cls.numpy() if class_idx is None else class_idx
+            cag, _, _ = ocnn.backward(cfg, p, c, ocnn.top_gradient(c, ci, mode), through_input=False)
+            heat = ogc.gradcam_tail_nhwc(c.conv_out[1].numpy(), cag[1].numpy(), (24, 24))
+            self._z = [z.clone() for z in c.z]
+            return cls.int(), c.probs, c.logits, torch.from_numpy(heat)
+
+        def get_tensor(self, kind, j, B):
+            return self._z[j]
+
+    modes = [(None, "logit"), (np.arange(9) % 2, "softmax_ce")]
+    for r in compare_all_images(cfg, p, x, Stand(), modes, tau=1e-5):
+        assert r["mask_violations"] == 0 and r["cls_equal"].all() and not r["overridden"].any()
+        assert r["logit_err"].max() < 1e-5 and r["heat_err"].max() < 1e-4
+    r = compare_all_images(cfg, p, x, Stand(bump=0.5), modes, tau=1e-5)[0]
+    assert r["mask_violations"] >= 1 and r["overridden"][0]
+    r = compare_all_images(cfg, p, x, Stand(flip=True), modes, tau=1e-5)[0]
+    assert not r["cls_equal"].any()

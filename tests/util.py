@@ -90,3 +90,6 @@ def oracle_heatmaps(cfg, params, x, class_idx, grad_mode, A_for_ties=None):
     dA = cag[last].numpy().astype(np.float32)
     heat = ogc.gradcam_tail_nhwc(A, dA, cfg.input_shape[:2])
     return cls, cache, A, dA, heat
+
+
+from oracle.compare import compare_all_images  # noqa: E402,F401  (shared with bench.py's untimed `check` leg)

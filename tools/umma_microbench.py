@@ -1,16 +1,18 @@
-"""Diagnostic (GPU): UMMA throughput per operand layout / N, and TMEM load throughput (one CTA, one SM)."""
+"""Diagnostic (GPU): UMMA throughput per operand layout / N on ONE SM and on ALL SMs at once, alone and with concurrent TMEM
+loads / shared-memory stores (the fused conv kernel's situation); TMEM load throughput.  Evidence for DESIGN.md section 4."""
 import ctypes as C, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bcad_b200
 lib = bcad_b200._lib.load()
-out = torch.zeros(3, dtype=torch.int64, device="cuda")
-def run(N, al, bl, albo, asbo, blbo, bsbo, reps=2000, ldw=4, x16=0, a_off=0, alt=0):
-    p = np.array([N, al, bl, albo, asbo, blbo, bsbo, reps, ldw, x16, a_off, alt], np.int32)
+out = torch.zeros(6, dtype=torch.int64, device="cuda")
+SMS = torch.cuda.get_device_properties(0).multi_processor_count
+def run(N, al, bl, albo, asbo, blbo, bsbo, reps=2000, ldw=4, x16=0, a_off=0, alt=0, grid=1, conc=0, stw=0):
+    p = np.array([N, al, bl, albo, asbo, blbo, bsbo, reps, ldw, x16, a_off, alt, grid, conc, stw], np.int32)
     bcad_b200._lib.check(lib.bcad_selftest_umma_bench(C.c_void_p(p.ctypes.data), C.c_void_p(out.data_ptr()), None))
     torch.cuda.synchronize()
     o = out.cpu().numpy()
-    return o[0] / reps, o[1] / reps
+    return o[0] / reps, o[1] / reps, o[3] / reps, o[4], o[5]
 for N in (64, 128, 256):
     a = run(N, 0, 0, 2176, 128, N * 16, 128)
     b = run(N, 2, 2, 16, 1024, 16, 1024)
@@ -25,3 +27,13 @@ for ldw in (1,):
     for x16 in (0, 1):
         r = run(64, 2, 2, 16, 1024, 16, 1024, 2000, ldw, x16)
         print(f"tmem ld: {ldw} warps, x{16 if x16 else 32}: {r[1]:.1f} cycles per load per warp")
+# one SM vs the whole chip, and the MMA stream beside the traffic the fused kernel's other warps generate
+for N in (64, 128, 256):
+    for grid in (1, 2, SMS // 2, SMS, 2 * SMS):
+        r = run(N, 0, 0, 2176, 128, N * 16, 128, reps=20000, grid=grid, alt=1)
+        print(f"N={N} grid={grid}: {r[0]:.1f} cycles/MMA on CTA 0, {r[2]:.1f} on the slowest CTA")
+for grid in (1, SMS):
+    for ldw, stw in ((0, 0), (4, 0), (0, 3), (4, 3)):
+        r = run(64, 0, 0, 2176, 128, 1024, 128, reps=20000, ldw=ldw, grid=grid, alt=1, conc=1, stw=stw)
+        print(f"N=64 grid={grid} concurrent: {ldw} TMEM-load warps, {stw * 32} storing threads: {r[0]:.1f} cycles/MMA (slowest CTA {r[2]:.1f}); "
+              f"{r[3]} loads/warp, {r[4]} store rounds in that time")

@@ -35,6 +35,7 @@ class Config(C.Structure):
         ("pad", C.c_int32), ("flatten_order", C.c_int32), ("pool_ties", C.c_int32),
         ("head", C.c_int32), ("precision", C.c_int32), ("max_batch", C.c_int32),
         ("keep_all_activations", C.c_int32), ("device", C.c_int32),
+        ("refine_margin", C.c_float), ("refine_capacity", C.c_int32),
     ]
 
 
@@ -70,6 +71,7 @@ _SIGNATURES = {
     "bcad_apply_update": (C.c_int, [_P, _P, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _P]),
     "bcad_get_conv_weights": (C.c_int, [_P, C.c_int, _P, _P]),
     "bcad_get_dense_weights": (C.c_int, [_P, C.c_int, _P, _P]),
+    "bcad_refine_stats": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "bcad_launch_count": (C.c_int64, [_P]),
     "bcad_uses_tensor_path": (C.c_int, [_P]),
     "bcad_set_profiling": (C.c_int, [_P, C.c_int]),

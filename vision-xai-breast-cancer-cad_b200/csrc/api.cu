@@ -99,6 +99,9 @@ static int validate(const bcad_config& c) {
     BCAD_REQUIRE(c.precision == BCAD_PREC_FP32 || c.precision == BCAD_PREC_F16 || c.precision == BCAD_PREC_F16X3, "bad precision %d", c.precision);
     BCAD_REQUIRE(c.max_batch >= 1 && c.max_batch <= 65535, "max_batch %d out of range 1..65535", c.max_batch);
     BCAD_REQUIRE(c.alpha_conv >= 0.f && c.alpha_dense >= 0.f, "negative LeakyReLU slope is not supported (pool/activation fusion assumes a monotone activation)");
+    BCAD_REQUIRE(c.refine_margin >= 0.f && c.refine_margin == c.refine_margin, "refine_margin must be >= 0");
+    BCAD_REQUIRE(c.refine_margin == 0.f || c.precision == BCAD_PREC_F16, "refine_margin applies to BCAD_PREC_F16 only (the other paths are fp32-grade already)");
+    BCAD_REQUIRE(c.refine_capacity >= 0, "refine_capacity must be >= 0");
     return BCAD_OK;
 }
 
@@ -171,6 +174,25 @@ int bcad_create(const bcad_config* cfg, bcad_model** out) {
         }
         m->tensor_path = true;
     }
+    if (cfg->refine_margin > 0.f) {
+        // the fp32-grade twin the small-margin images are re-run on (refine.cu)
+        bcad_config c2 = *cfg;
+        c2.precision = BCAD_PREC_F16X3;
+        c2.refine_margin = 0.f;
+        c2.refine_capacity = 0;
+        c2.keep_all_activations = 0;
+        int cap = cfg->refine_capacity > 0 ? cfg->refine_capacity : std::max(8, cfg->max_batch / 32);
+        cap = std::min(cap, cfg->max_batch);
+        c2.max_batch = cap;
+        bcad_model* tw = nullptr;
+        int rc = bcad_create(&c2, &tw);
+        if (rc != BCAD_OK) {                       // (the twin's message says which shape limit was hit)
+            delete m;
+            return rc;
+        }
+        m->refine.twin = reinterpret_cast<Model*>(tw);
+        m->refine.cap = cap;
+    }
     *out = reinterpret_cast<bcad_model*>(m);
     return BCAD_OK;
 }
@@ -178,6 +200,8 @@ int bcad_create(const bcad_config* cfg, bcad_model** out) {
 void bcad_destroy(bcad_model* mm) {
     if (!mm) return;
     Model* m = reinterpret_cast<Model*>(mm);
+    if (m->refine.twin) bcad_destroy(reinterpret_cast<bcad_model*>(m->refine.twin));
+    m->refine.twin = nullptr;
     {
         DeviceGuard g(m->cfg.device);
         cudaDeviceSynchronize();
@@ -191,12 +215,14 @@ int bcad_set_conv_weights(bcad_model* mm, int i, const float* filters, const flo
     Model* m = reinterpret_cast<Model*>(mm);
     BCAD_REQUIRE(m && filters, "set_conv_weights: null argument");
     BCAD_REQUIRE(i >= 0 && i < (int)m->conv.size(), "conv index %d out of range", i);
+    std::lock_guard<std::mutex> lock(m->mu);
     ConvLayer& L = m->conv[i];
     const size_t n = (size_t)L.Cout * L.k * L.k * L.Cin;
     L.h_w.assign(filters, filters + n);
     if (bias) L.h_b.assign(bias, bias + L.Cout);
     else L.h_b.assign(L.Cout, 0.f);
     m->committed = false;
+    if (m->refine.twin) return bcad_set_conv_weights(reinterpret_cast<bcad_model*>(m->refine.twin), i, filters, bias);
     return BCAD_OK;
 }
 
@@ -204,6 +230,7 @@ int bcad_set_dense_weights(bcad_model* mm, int j, const float* w, const float* b
     Model* m = reinterpret_cast<Model*>(mm);
     BCAD_REQUIRE(m && w, "set_dense_weights: null argument");
     BCAD_REQUIRE(j >= 0 && j < (int)m->dense.size(), "dense index %d out of range", j);
+    std::lock_guard<std::mutex> lock(m->mu);
     DenseLayer& D = m->dense[j];
     const size_t n = (size_t)D.out * D.in;
     D.h_w.resize(n);
@@ -224,6 +251,7 @@ int bcad_set_dense_weights(bcad_model* mm, int j, const float* w, const float* b
     if (bias) D.h_b.assign(bias, bias + D.out);
     else D.h_b.assign(D.out, 0.f);
     m->committed = false;
+    if (m->refine.twin) return bcad_set_dense_weights(reinterpret_cast<bcad_model*>(m->refine.twin), j, w, bias);
     return BCAD_OK;
 }
 
@@ -232,6 +260,7 @@ int bcad_fold_batchnorm(bcad_model* mm, int i, const float* gamma, const float* 
     Model* m = reinterpret_cast<Model*>(mm);
     BCAD_REQUIRE(m && gamma && beta && mean && var, "fold_batchnorm: null argument");
     BCAD_REQUIRE(i >= 0 && i < (int)m->conv.size(), "conv index %d out of range", i);
+    std::lock_guard<std::mutex> lock(m->mu);
     ConvLayer& L = m->conv[i];
     BCAD_REQUIRE(!L.h_w.empty(), "fold_batchnorm: conv %d has no staged weights", i);
     const size_t per = (size_t)L.k * L.k * L.Cin;
@@ -241,6 +270,7 @@ int bcad_fold_batchnorm(bcad_model* mm, int i, const float* gamma, const float* 
         L.h_b[f] = (L.h_b[f] - mean[f]) * sc + beta[f];
     }
     m->committed = false;
+    if (m->refine.twin) return bcad_fold_batchnorm(reinterpret_cast<bcad_model*>(m->refine.twin), i, gamma, beta, mean, var, eps);
     return BCAD_OK;
 }
 
@@ -332,6 +362,20 @@ int bcad_commit(bcad_model* mm) {
         m->ws_ready = true;
     }
     if (m->tensor_path) BCAD_TRY(tensor_path_commit(*m));
+    if (m->refine.twin) {
+        Refine& R = m->refine;
+        BCAD_TRY(bcad_commit(reinterpret_cast<bcad_model*>(R.twin)));
+        if (R.idx == nullptr) {
+            const size_t img = (size_t)m->cfg.in_h * m->cfg.in_w * m->cfg.in_c, hm = (size_t)m->cfg.in_h * m->cfg.in_w;
+            BCAD_TRY(m->alloc((void**)&R.idx, (size_t)R.cap * sizeof(int32_t)));
+            BCAD_TRY(m->alloc((void**)&R.counters, 4 * sizeof(int32_t)));
+            BCAD_TRY(m->alloc((void**)&R.x, (size_t)R.cap * img * sizeof(float)));
+            BCAD_TRY(m->alloc((void**)&R.cidx, (size_t)R.cap * sizeof(int32_t)));
+            BCAD_TRY(m->alloc((void**)&R.heat, (size_t)R.cap * hm * sizeof(float)));
+            BCAD_CUDA_CHECK(cudaMemset(R.counters, 0, 4 * sizeof(int32_t)));
+            BCAD_CUDA_CHECK(cudaMemset(R.idx, 0, (size_t)R.cap * sizeof(int32_t)));
+        }
+    }
     BCAD_CUDA_CHECK(cudaDeviceSynchronize());
     m->committed = true;
     m->cached_B = 0;
@@ -463,6 +507,37 @@ static int explain_chunk_fp32(Model* m, int n, const int32_t* class_idx, int gra
 }
 
 static int run(Model* m, const float* x, int B, const int32_t* class_idx, int grad_mode, bool explain, float* logits,
+               float* probs, int32_t* cls, float* heat, cudaStream_t s);
+
+// cfg.refine_margin: re-run the chunk's small-margin images on the fp32-grade twin and write their results over the 16-bit ones
+// (refine.cu).  Stream-ordered: the twin always runs min(cap, n) slots, the device-side count selects what is written back.
+static int refine_chunk(Model* m, const float* xc, int n, const int32_t* ci, int grad_mode, bool explain, float* heat, cudaStream_t s) {
+    Refine& R = m->refine;
+    Model* t = R.twin;
+    const int nc = m->cfg.num_classes, slots = std::min(R.cap, n);
+    const size_t img = (size_t)m->cfg.in_h * m->cfg.in_w * m->cfg.in_c, hm = (size_t)m->cfg.in_h * m->cfg.in_w;
+    BCAD_LAUNCH(m, "refine_flag", launch_refine_flag(m->dense.back().z, n, nc, m->cfg.refine_margin, slots, R.idx, R.counters, s));
+    BCAD_LAUNCH(m, "refine_gather", launch_refine_gather(xc, img, ci, R.idx, R.counters, slots, R.x, R.cidx, s));
+    BCAD_TRY(m->mark("refine_twin_fp16x3", s));
+    const int64_t l0 = t->launches;
+    BCAD_TRY(run(t, R.x, slots, ci ? R.cidx : nullptr, grad_mode, explain, nullptr, nullptr, nullptr, explain ? R.heat : nullptr, s));
+    m->launches += t->launches - l0;
+    RefineScatter a;
+    memset(&a, 0, sizeof(a));
+    a.n_dense = (int)m->dense.size();
+    for (int j = 0; j < a.n_dense; ++j) {
+        a.sizes[j] = m->dense[j].out;
+        a.src_z[j] = t->dense[j].z;
+        a.dst_z[j] = m->dense[j].z;
+    }
+    a.src_probs = t->probs; a.dst_probs = m->probs; a.src_cls = t->cls; a.dst_cls = m->cls;
+    a.src_heat = explain ? R.heat : nullptr; a.dst_heat = explain ? heat : nullptr;
+    a.hm = hm; a.nc = nc;
+    BCAD_LAUNCH(m, "refine_scatter", launch_refine_scatter(a, R.idx, R.counters, slots, s));
+    return BCAD_OK;
+}
+
+static int run(Model* m, const float* x, int B, const int32_t* class_idx, int grad_mode, bool explain, float* logits,
                float* probs, int32_t* cls, float* heat, cudaStream_t s) {
     BCAD_REQUIRE(m && x, "null model or input");
     BCAD_REQUIRE(B >= 1, "batch must be >= 1, got %d", B);
@@ -483,13 +558,14 @@ static int run(Model* m, const float* x, int B, const int32_t* class_idx, int gr
         const int32_t* ci = (explain && class_idx) ? class_idx + b0 : nullptr;
         if (m->tensor_path) BCAD_TRY(tensor_forward_chunk(*m, xc, n, explain, ci, grad_mode, s));
         else BCAD_TRY(forward_chunk_fp32(m, xc, n, explain, ci, grad_mode, s));
-        if (logits) BCAD_CUDA_CHECK(cudaMemcpyAsync(logits + (size_t)b0 * nc, m->dense.back().z, (size_t)n * nc * sizeof(float), cudaMemcpyDeviceToDevice, s));
-        if (probs) BCAD_CUDA_CHECK(cudaMemcpyAsync(probs + (size_t)b0 * nc, m->probs, (size_t)n * nc * sizeof(float), cudaMemcpyDeviceToDevice, s));
-        if (cls) BCAD_CUDA_CHECK(cudaMemcpyAsync(cls + b0, m->cls, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
         if (explain) {
             if (m->tensor_path) BCAD_TRY(tensor_explain_chunk(*m, n, ci, grad_mode, heat + (size_t)b0 * hm, s));
             else BCAD_TRY(explain_chunk_fp32(m, n, ci, grad_mode, heat + (size_t)b0 * hm, s));
         }
+        if (m->refine.twin) BCAD_TRY(refine_chunk(m, xc, n, ci, grad_mode, explain, explain ? heat + (size_t)b0 * hm : nullptr, s));
+        if (logits) BCAD_CUDA_CHECK(cudaMemcpyAsync(logits + (size_t)b0 * nc, m->dense.back().z, (size_t)n * nc * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        if (probs) BCAD_CUDA_CHECK(cudaMemcpyAsync(probs + (size_t)b0 * nc, m->probs, (size_t)n * nc * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        if (cls) BCAD_CUDA_CHECK(cudaMemcpyAsync(cls + b0, m->cls, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
         m->cached_B = n;
     }
     if (B > mb) m->cached_B = 0;   // the cache only describes whole calls
@@ -632,7 +708,15 @@ static int predict_explain_host_impl(bcad_model* mm, const float* x_host, const 
     BCAD_REQUIRE(m && (x_host || x8_host), "predict_explain_host: null argument");
     BCAD_REQUIRE(B >= 1, "batch must be >= 1, got %d", B);
     if (!m->committed) { set_error("weights not committed: call bcad_commit first"); return BCAD_ERR_STATE; }
+    BCAD_REQUIRE(grad_mode == BCAD_GRAD_LOGIT || grad_mode == BCAD_GRAD_SOFTMAX_CE, "bad grad_mode %d", grad_mode);
+    if (class_idx_host != nullptr)
+        for (int b = 0; b < B; ++b)
+            BCAD_REQUIRE(class_idx_host[b] >= 0 && class_idx_host[b] < m->cfg.num_classes, "class_idx[%d] = %d is outside [0, %d)", b,
+                         class_idx_host[b], m->cfg.num_classes);
     DeviceGuard g(m->cfg.device);
+    // one host-buffer call at a time per handle: the three streams, the double-buffered device slots, the events and the pinned
+    // staging are shared (threaded callers -- a Flask app with one model -- queue here; separate handles run concurrently)
+    std::lock_guard<std::mutex> host_lock(m->host_mu);
     Xfer& X = m->xfer;
     const int nc = m->cfg.num_classes;
     const size_t img = (size_t)m->cfg.in_h * m->cfg.in_w * m->cfg.in_c, hm = (size_t)m->cfg.in_h * m->cfg.in_w;
@@ -851,6 +935,21 @@ int bcad_bottleneck_resize(const float* feat_dev, int B, int C, int H, int W, in
 int bcad_avg_pool(const float* x, int B, int H, int W, int C, int pool, float* out, void* stream) {
     BCAD_REQUIRE(x && out && B >= 1 && H >= 1 && W >= 1 && C >= 1 && pool >= 1, "avg_pool: bad argument");
     return launch_avg_pool(x, out, B, H, W, C, pool, (cudaStream_t)stream);
+}
+
+int bcad_refine_stats(bcad_model* mm, int64_t* refined, int64_t* overflowed) {
+    Model* m = reinterpret_cast<Model*>(mm);
+    BCAD_REQUIRE(m && refined && overflowed, "refine_stats: null argument");
+    *refined = 0;
+    *overflowed = 0;
+    if (m->refine.twin == nullptr || m->refine.counters == nullptr) return BCAD_OK;
+    DeviceGuard g(m->cfg.device);
+    int32_t h[4] = {0, 0, 0, 0};
+    BCAD_CUDA_CHECK(cudaDeviceSynchronize());
+    BCAD_CUDA_CHECK(cudaMemcpy(h, m->refine.counters, sizeof(h), cudaMemcpyDeviceToHost));
+    *refined = h[1];
+    *overflowed = h[2];
+    return BCAD_OK;
 }
 
 int64_t bcad_launch_count(bcad_model* mm) {

@@ -74,6 +74,29 @@ int launch_sgd_clip_update(float* w, const float* g, const float* norm, float lr
 int launch_adam_update(float* w, const float* g, float* m1, float* m2, float lr, float b1, float b2, float eps, int step, size_t n,
                        cudaStream_t s);
 
+// ---------------------------------------------------------------- small-margin refinement (refine.cu)
+// idx[0..count) = images of the chunk whose two largest logits differ by less than `margin`, ascending; counters = {count
+// clamped to cap, running total refined, running total overflowed}
+int launch_refine_flag(const float* logits, int n, int nc, float margin, int cap, int32_t* idx, int32_t* counters, cudaStream_t s);
+// slots [0,slots): image idx[slot] (slots >= count replicate image 0 of the chunk: finite inputs, results dropped)
+int launch_refine_gather(const float* x, size_t img_elems, const int32_t* class_idx, const int32_t* idx, const int32_t* counters,
+                         int slots, float* rx, int32_t* rcidx, cudaStream_t s);
+struct RefineScatter {
+    int n_dense;
+    int sizes[8];
+    const float* src_z[8];        // twin pre-activations [slots][size]
+    float* dst_z[8];              // chunk pre-activations [n][size]
+    const float* src_probs;
+    float* dst_probs;
+    const int32_t* src_cls;
+    int32_t* dst_cls;
+    const float* src_heat;        // [slots][hm] or nullptr
+    float* dst_heat;              // [n][hm] or nullptr
+    size_t hm;
+    int nc;
+};
+int launch_refine_scatter(const RefineScatter& a, const int32_t* idx, const int32_t* counters, int slots, cudaStream_t s);
+
 // fused dense head: fc1 split-K reduce -> remaining dense layers -> probs/class -> (explain) backward to dz1 + alpha
 struct HeadArgs {
     int n_dense;                  // dense layers incl. the output layer; layer 0 comes as split-K partials

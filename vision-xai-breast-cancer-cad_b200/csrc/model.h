@@ -85,6 +85,17 @@ struct TrainState {                     // row f4: buffers of the training step 
 
 struct TensorPath;                     // tensor_path.cu
 
+struct Model;
+struct Refine {                         // cfg.refine_margin > 0: small-margin images are re-run through a split-operand twin handle
+    Model* twin = nullptr;              // BCAD_PREC_F16X3 handle of the same network, max_batch = cap
+    int cap = 0;
+    int32_t* idx = nullptr;             // [cap] chunk-local indices of the flagged images, in ascending order
+    int32_t* counters = nullptr;        // {flagged in this chunk (clamped to cap), total refined, total overflowed}
+    float* x = nullptr;                 // [cap] gathered inputs
+    int32_t* cidx = nullptr;            // [cap] gathered target classes
+    float* heat = nullptr;              // [cap] heat-maps of the twin (its other outputs are read from its own workspace)
+};
+
 struct Model {
     bcad_config cfg;
     std::vector<ConvLayer> conv;
@@ -95,6 +106,8 @@ struct Model {
     int64_t launches = 0;
     size_t ws_bytes = 0;
     std::mutex mu;
+    std::mutex host_mu;                 // serialises the host-buffer calls of one handle (shared staging, streams, events)
+    Refine refine;
     std::vector<void*> allocs;
     // shared workspace
     float* partials = nullptr;

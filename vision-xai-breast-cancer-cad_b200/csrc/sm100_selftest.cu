@@ -64,19 +64,24 @@ umma_selftest_kernel(const uint4* __restrict__ a_img, int a_bytes, const uint4* 
 }
 
 // ---- micro-benchmarks (design evidence, not product): cycles for `reps` back-to-back UMMAs on fixed smem operands,
-// and for `reps` TMEM->register loads by `nwarps` warps.  out[0] = MMA cycles, out[1] = TMEM-load cycles.
+// and for `reps` TMEM->register loads by `nwarps` warps.  out[0] = MMA cycles (CTA 0), out[1] = TMEM-load cycles, out[3] = slowest
+// CTA's MMA cycles.  `grid` CTAs run the same loop (one per SM: is the per-MMA time a property of the SM or of the loaded
+// chip?); with `concurrent` the TMEM loads (warps 1..ld_warps) and `st_warps` warps of 16-byte shared-memory stores run WHILE
+// thread 0 issues the MMAs (the fused conv kernel's situation) instead of after them.
 __global__ void __launch_bounds__(256, 1)
 umma_bench_kernel(int N, int a_layout, int b_layout, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int reps, int ld_warps,
-                  int ld_x16, int a_off, int alternate, long long* __restrict__ out) {
+                  int ld_x16, int a_off, int alternate, int concurrent, int st_warps, long long* __restrict__ out) {
     using namespace sm100;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base;
+    __shared__ volatile int done;
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < (64 * 1024) / 16; i += 256) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x3C003C00u, 0x3C003C00u, 0, 0);
     if (tid == 0) {
         mbar_init(&bar, 1);
         fence_barrier_init();
+        done = 0;
     }
     if (warp == 0) {
         tmem_alloc(&tmem_base, 512);
@@ -100,30 +105,42 @@ umma_bench_kernel(int N, int a_layout, int b_layout, int a_lbo, int a_sbo, int b
         }
         umma_commit(&bar);
         mbar_wait(&bar, 0);
-        out[0] = clock64() - t0;
+        const long long dt = clock64() - t0;
+        if (blockIdx.x == 0) out[0] = dt;
+        atomicMax(reinterpret_cast<unsigned long long*>(out + 3), (unsigned long long)dt);
+        done = 1;
     }
-    __syncthreads();
-    tc_fence_after();
-    if (warp < ld_warps) {
+    if (!concurrent) {
+        __syncthreads();
+        tc_fence_after();
+    }
+    if (warp >= 1 && warp <= ld_warps) {
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
         float acc = 0.f;
         const long long t0 = clock64();
-        for (int k = 0; k < reps; ++k) {
+        long long n = 0;
+        for (int k = 0; concurrent ? !done : k < reps; ++k, ++n) {
             if (ld_x16) {
                 float v[16];
-                tmem_ld16(tmem + lane_off + ((k * 16) & 255), v);
+                tmem_ld16(tmem + lane_off + 256 + ((k * 16) & 255), v);
                 tmem_ld_wait();
                 acc += v[0] + v[15];
             } else {
                 float v[32];
-                tmem_ld32(tmem + lane_off + ((k * 32) & 255), v);
+                tmem_ld32(tmem + lane_off + 256 + ((k * 32) & 255), v);
                 tmem_ld_wait();
                 acc += v[0] + v[31];
             }
         }
         const long long dt = clock64() - t0;
-        if (tid == 0) out[1] = dt;
+        if (tid == 32 && blockIdx.x == 0) { out[1] = dt; out[4] = n; }
         if (acc == 123.456f) out[2] = 1;      // keep the loads alive
+    } else if (concurrent && warp >= 5 && warp < 5 + st_warps) {
+        // 16-byte stores into a scratch area of shared memory (an im2col build's traffic) until the MMAs are done
+        uint4* dst = reinterpret_cast<uint4*>(smem + 49152) + (tid & 127);
+        long long n = 0;
+        for (int k = 0; !done; ++k, ++n) dst[(k & 7) * 128] = make_uint4(k, k, k, k);
+        if ((tid & 31) == 0 && warp == 5 && blockIdx.x == 0) out[5] = n;
     }
     tc_fence_before();
     __syncthreads();
@@ -132,12 +149,14 @@ umma_bench_kernel(int N, int a_layout, int b_layout, int a_lbo, int a_sbo, int b
 
 }  // namespace bcad
 
-extern "C" int bcad_selftest_umma_bench(const int32_t* p /*N,a_layout,b_layout,a_lbo,a_sbo,b_lbo,b_sbo,reps,ld_warps,ld_x16,a_off,alternate*/,
+extern "C" int bcad_selftest_umma_bench(const int32_t* p /*N,a_layout,b_layout,a_lbo,a_sbo,b_lbo,b_sbo,reps,ld_warps,ld_x16,a_off,alternate,grid,concurrent,st_warps*/,
                                         long long* out_dev, void* stream) {
     using namespace bcad;
     BCAD_REQUIRE(p && out_dev, "selftest bench: null argument");
+    BCAD_REQUIRE(p[12] >= 1 && p[12] <= 1024 && p[8] >= 0 && p[8] <= 4 && p[14] >= 0 && p[14] <= 3, "selftest bench: bad grid / warp counts");
     BCAD_CUDA_CHECK(cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    umma_bench_kernel<<<1, 256, 64 * 1024, (cudaStream_t)stream>>>(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8], p[9], p[10], p[11], out_dev);
+    BCAD_CUDA_CHECK(cudaMemsetAsync(out_dev, 0, 6 * sizeof(long long), (cudaStream_t)stream));
+    umma_bench_kernel<<<p[12], 256, 64 * 1024, (cudaStream_t)stream>>>(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8], p[9], p[10], p[11], p[13], p[14], out_dev);
     BCAD_CUDA_CHECK(cudaGetLastError());
     return BCAD_OK;
 }

@@ -69,8 +69,16 @@ def _f32c(a) -> np.ndarray:
 class Engine:
     """One libbcad handle on one GPU."""
 
+    #: default of ``refine_margin`` on the fp16 path: ~3x the largest 16-bit logit-gap error seen on the canonical network
+    #: (tools/kink_stats.py); about 1 % of random-init images fall below it
+    DEFAULT_REFINE_MARGIN = 1e-2
+
     def __init__(self, spec: NetSpec, precision: str = "fp32", max_batch: int = 64,
-                 keep_all_activations: bool = False, device: int = 0):
+                 keep_all_activations: bool = False, device: int = 0, refine_margin: Optional[float] = None,
+                 refine_capacity: int = 0):
+        """precision "fp16": ``refine_margin`` (None = DEFAULT_REFINE_MARGIN where the shape allows, 0 = off) re-runs images
+        whose two largest logits are closer than the margin through the fp32-grade split-operand kernels inside the same call,
+        so the predicted classes are the fp32-grade ones (include/bcad.h ``refine_margin``)."""
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("libbcad needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -99,8 +107,17 @@ class Engine:
         cfg.max_batch = self.max_batch
         cfg.keep_all_activations = 1 if keep_all_activations else 0
         cfg.device = self.device
+        cfg.refine_capacity = int(refine_capacity)
         self._h = C.c_void_p()
-        _lib.check(self.lib.bcad_create(C.byref(cfg), C.byref(self._h)))
+        if precision == "fp16" and refine_margin is None:
+            cfg.refine_margin = self.DEFAULT_REFINE_MARGIN
+            if self.lib.bcad_create(C.byref(cfg), C.byref(self._h)) != _lib.OK:     # shape outside the split-operand path
+                cfg.refine_margin = 0.0
+                _lib.check(self.lib.bcad_create(C.byref(cfg), C.byref(self._h)))
+        else:
+            cfg.refine_margin = float(refine_margin or 0.0)
+            _lib.check(self.lib.bcad_create(C.byref(cfg), C.byref(self._h)))
+        self.refine_margin = float(cfg.refine_margin)
         self._committed = False
         self.tdev = torch.device("cuda", self.device)
 
@@ -165,6 +182,12 @@ class Engine:
     @property
     def launch_count(self) -> int:
         return int(self.lib.bcad_launch_count(self._h))
+
+    def refine_stats(self):
+        """(images re-run at fp32 grade, flagged images beyond ``refine_capacity``) since creation; synchronises."""
+        a, b = C.c_int64(), C.c_int64()
+        _lib.check(self.lib.bcad_refine_stats(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def set_profiling(self, on: bool):
         _lib.check(self.lib.bcad_set_profiling(self._h, 1 if on else 0))
