@@ -127,6 +127,13 @@ BCAD_API int bcad_predict_explain(bcad_model* m, const float* x_dev, int B, cons
                          int grad_mode, float* logits_dev, float* probs_dev, int32_t* cls_dev,
                          float* heatmap_dev, void* stream);
 
+/* Same call with the heat-map bilinearly resized to out_h x out_w instead of the model's input size: pytorch_grad_cam scales the
+ * low-resolution cam to the size of the image it was asked about, and the reference asks about a 512x512 image whatever its CNN
+ * was fed (app.py:649-657 -> GRADCAM.py:46-64).  heatmap_dev: fp32 [B,out_h,out_w]. */
+BCAD_API int bcad_predict_explain_sized(bcad_model* m, const float* x_dev, int B, const int32_t* class_idx_dev, int grad_mode,
+                               float* logits_dev, float* probs_dev, int32_t* cls_dev, int out_h, int out_w, float* heatmap_dev,
+                               void* stream);
+
 /* compute_backprops_for_explainability (explainability.py:13-68), activation-gradient part:
  * uses the activations cached by the preceding bcad_predict of the SAME B (<= max_batch,
  * keep_all_activations=1 when gradients below the last conv block are wanted).
@@ -157,6 +164,15 @@ BCAD_API int bcad_predict_explain_host_u8(bcad_model* m, const float* x_host, in
 BCAD_API int bcad_predict_explain_host_u8in(bcad_model* m, const uint8_t* x_u8_host, int B, const int32_t* class_idx_host_or_null,
                                    int grad_mode, float* logits_host, float* probs_host, int32_t* cls_host,
                                    float* heatmap_host, uint8_t* heat_u8_host);
+
+/* generate_dual_class_gradcam_overlays_pytorch (GRADCAM.py:31-81) for a BATCH of 8-bit grey images, end to end: gray_u8_host uint8
+ * [B,H,W] (model input size) -> img01 = u8 / 255 (GRADCAM.py:46) -> CNN input (standardise = 1: (img01 - mean) / (std + 1e-8) per
+ * image as app.py:179-182 prepares CNN inputs, 0: img01 itself; replicated over in_c channels) -> predict + Grad-CAM ->
+ * overlay_rgb_host uint8 [B,H,W,3] = show_cam_on_image(img_rgb, cam, use_rgb=True) (GRADCAM.py:67) and heat_u8_host uint8 [B,H,W] =
+ * (cam * 255).astype(uint8) (GRADCAM.py:70); either may be NULL.  Same chunked three-stream pipeline as above. */
+BCAD_API int bcad_gradcam_overlays_host(bcad_model* m, const uint8_t* gray_u8_host, int B, const int32_t* class_idx_host_or_null,
+                               int grad_mode, int standardise, float* logits_host, float* probs_host, int32_t* cls_host,
+                               uint8_t* overlay_rgb_host, uint8_t* heat_u8_host);
 
 /* ---- stand-alone Grad-CAM tail (pytorch_grad_cam BaseCAM.forward / scale_cam_image) ------------ */
 /* A, dA: [B,h,w,K] NHWC device, dtype 0 = fp32, 1 = bf16; out: fp32 [B,H,W].
@@ -238,7 +254,7 @@ BCAD_API int bcad_selftest_umma(const void* a_img_dev, int a_bytes, const void* 
 
 /* Micro-benchmark behind DESIGN.md's operand-layout choices: cycles of `reps` back-to-back 128xNx16 UMMAs and of
  * `reps` TMEM loads.  p = {N, a_layout, b_layout, a_lbo, a_sbo, b_lbo, b_sbo, reps, ld_warps, ld_x16, a_off, alternate, grid,
- * concurrent, st_warps}; out_dev: int64[6] = {MMA cycles of CTA 0, TMEM-load cycles, -, slowest CTA's MMA cycles, loads done, stores done}. */
+ * concurrent, st_warps, stores_to_hbm}; out_dev: int64[6] = {MMA cycles of CTA 0, TMEM-load cycles, -, slowest CTA's MMA cycles, loads done, stores done}. */
 BCAD_API int bcad_selftest_umma_bench(const int32_t* p, long long* out_dev, void* stream);
 
 #ifdef __cplusplus

@@ -175,6 +175,46 @@ def train_case(name, input_shape, conv_layers, hidden, seed, n=3, lr=0.05, dropo
     print("wrote", name, "losses", losses)
 
 
+def forward_train_case(name, input_shape, conv_layers, hidden, seed, dropout_rate=0.3):
+    """The reference's DEFAULT call ``model.forward(x)`` (training=True, dropout_rate=0.3: Classes/CNNModel.py:68,162,186-188)
+    under a seeded global np.random stream: probs, every layer cache, and the explainability backward of that forward."""
+    ref = ref_loader.load_numpy_cnn()
+    xai = ref_loader.load_explainability()
+    rng = np.random.default_rng(seed)
+    np.random.seed(seed)
+    with ref_loader.silenced():
+        m = ref.CNNModel(input_shape, 2, conv_layers=conv_layers, hidden_units=hidden, dropout_rate=dropout_rate, leaky_alpha=0.01)
+    for layer in m.layers:
+        if "biases" in layer:
+            layer["biases"] = rng.normal(0, 0.1, layer["biases"].shape)
+    x = rng.standard_normal(input_shape)
+    out = {"x": x, "alpha": 0.01, "input_shape": np.array(input_shape), "conv_layers": np.array(conv_layers), "hidden": np.array(hidden),
+           "dropout_rate": dropout_rate, "forward_seed": seed + 1000}
+    for i, layer in enumerate(m.layers):
+        if layer["type"] == "conv":
+            out[f"W{i}"], out[f"b{i}"] = layer["filters"].copy(), layer["biases"].copy()
+        elif layer["type"] in ("dense", "output"):
+            out[f"W{i}"], out[f"b{i}"] = layer["weights"].copy(), layer["biases"].copy()
+    np.random.seed(seed + 1000)
+    with ref_loader.silenced():
+        probs = m.forward(x)                                  # the reference's default: training=True
+    out["probs"] = probs
+    for i, layer in enumerate(m.layers):
+        if layer["type"] in ("dense", "output"):
+            out[f"z{i}"], out[f"dense_in{i}"] = layer["z"], layer["input"]
+    y = np.zeros(2)
+    y[1] = 1.0
+    with ref_loader.silenced():
+        grads, d_input, cag = xai.compute_backprops_for_explainability(m, y)
+    out["d_input_c1"] = d_input
+    for i, g in enumerate(grads):
+        if g is not None:
+            for kk, vv in g.items():
+                out[f"grad{i}_{kk}_c1"] = vv
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote", name, "probs", probs)
+
+
 def unet_case(name, shape, batch, seed):
     """Classes/unet.py functions (exec-loaded without the script part and its missing imports)."""
     import types
@@ -252,6 +292,7 @@ if __name__ == "__main__":
     torch_case("ref_torch_odd", (13, 18, 3), [(5, 3), (6, 3)], [9], batch=2, seed=22, alpha=0.2)
     train_case("ref_numpy_train", (12, 12, 2), [(3, 3), (4, 3)], [6, 5], seed=41)
     train_case("ref_numpy_train_dropout", (12, 12, 2), [(3, 3), (4, 3)], [8, 6], seed=42, n=4, dropout_rate=0.4)
+    forward_train_case("ref_numpy_forward_train", (12, 12, 2), [(3, 3), (4, 3)], [8, 6], seed=43)
     unet_case("ref_unet_small", (16, 16, 1), 2, seed=31)
     unet_case("ref_unet_odd", (21, 18, 2), 1, seed=32)
     bottleneck_case()

@@ -96,8 +96,9 @@ def test_numpy_mirror_layers_structure(tmp_path):
         for k in ("filters", "weights", "biases"):
             if k in a:
                 assert np.array_equal(a[k], b[k])
-    with pytest.raises(NotImplementedError):
-        m.forward(np.zeros((12, 12, 2)), training=True)       # dropout/training is not this hot path
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            m.forward(np.zeros((12, 12, 2)))                  # every forward runs on the device; there is nothing to fall back to
 
 
 def test_golden_npz_loads_through_mirror_load_weights(tmp_path):

@@ -7,8 +7,8 @@ import bcad_b200
 lib = bcad_b200._lib.load()
 out = torch.zeros(6, dtype=torch.int64, device="cuda")
 SMS = torch.cuda.get_device_properties(0).multi_processor_count
-def run(N, al, bl, albo, asbo, blbo, bsbo, reps=2000, ldw=4, x16=0, a_off=0, alt=0, grid=1, conc=0, stw=0):
-    p = np.array([N, al, bl, albo, asbo, blbo, bsbo, reps, ldw, x16, a_off, alt, grid, conc, stw], np.int32)
+def run(N, al, bl, albo, asbo, blbo, bsbo, reps=2000, ldw=4, x16=0, a_off=0, alt=0, grid=1, conc=0, stw=0, hbm=0):
+    p = np.array([N, al, bl, albo, asbo, blbo, bsbo, reps, ldw, x16, a_off, alt, grid, conc, stw, hbm], np.int32)
     bcad_b200._lib.check(lib.bcad_selftest_umma_bench(C.c_void_p(p.ctypes.data), C.c_void_p(out.data_ptr()), None))
     torch.cuda.synchronize()
     o = out.cpu().numpy()
@@ -37,3 +37,24 @@ for grid in (1, SMS):
         r = run(64, 0, 0, 2176, 128, 1024, 128, reps=20000, ldw=ldw, grid=grid, alt=1, conc=1, stw=stw)
         print(f"N=64 grid={grid} concurrent: {ldw} TMEM-load warps, {stw * 32} storing threads: {r[0]:.1f} cycles/MMA (slowest CTA {r[2]:.1f}); "
               f"{r[3]} loads/warp, {r[4]} store rounds in that time")
+
+# the same MMA stream beside HBM store traffic (the conv epilogue writes 2.8 TB/s while the MMAs run)
+for grid in (1, SMS):
+    r = run(64, 0, 0, 2176, 128, 1024, 128, reps=20000, ldw=4, grid=grid, alt=1, conc=1, stw=3, hbm=1)
+    print(f"N=64 grid={grid} concurrent: 4 TMEM-load warps, 96 threads storing to HBM: {r[0]:.1f} cycles/MMA (slowest CTA {r[2]:.1f}); "
+          f"{r[4]} store rounds = {r[4] * 96 * 16 * grid / (r[0] * 20000) :.0f} B/clk chip-wide")
+# sustained: does the per-MMA time (in SM cycles) stay at 48 once the chip runs into its power cap?
+import subprocess, time
+def smi():
+    try:
+        return subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw,clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-i", "0"],
+                              capture_output=True, text=True, timeout=5).stdout.strip()
+    except Exception as e:
+        return str(e)
+for N, hbm in ((64, 0), (64, 1), (256, 0)):
+    t0, i = time.time(), 0
+    while time.time() - t0 < 4.0:
+        r = run(N, 0, 0, 2176, 128, N * 16, 128, reps=200000, ldw=4, grid=SMS, alt=1, conc=1, stw=3, hbm=hbm)
+        if i % 40 == 0:
+            print(f"sustained N={N} hbm_stores={hbm} t={time.time() - t0:.2f}s: {r[0]:.1f} cycles/MMA (slowest CTA {r[2]:.1f}) | sm MHz, W, power cap: {smi()}")
+        i += 1

@@ -7,6 +7,12 @@ The modules only HOLD the parameters; ``forward`` runs in libbcad (Conv2d(paddin
 MaxPool2d(2), CHW flatten handled by permuting fc1's columns at load time, Linear + LeakyReLU(alpha)).
 ``forward`` returns logits without an autograd graph; training goes through ``train_model`` (forward, backward and
 Adam all on the device).
+
+``precision="auto"`` (default) picks the fastest path that is fp32-grade for the network's shape: the split-operand tensor-core
+path ``fp16x3`` where it is covered (single-channel inputs, conv 32/64: logits within 2e-4 of float64), else the 16-bit tensor
+path ``fp16`` (multi-channel inputs such as the deployed [64,256,256] model, app.py:584: logits within 1e-2), else the fp32
+CUDA-core path.  A model in train mode (the reference's state after construction) runs ``forward`` with dropout, like
+``nn.Dropout`` (ADCNNM.py:62): the multipliers are drawn with ``torch.rand`` on the device.
 """
 from __future__ import annotations
 
@@ -21,7 +27,7 @@ from .engine import Engine, NetSpec
 
 class CNNModel(nn.Module):
     def __init__(self, input_shape, num_classes, conv_layers=[(32, 3), (64, 3)], hidden_units=[256, 128],
-                 dropout_rate=0.3, leaky_alpha=0.01, *, precision="fp32", max_batch=64, device_index=0):
+                 dropout_rate=0.3, leaky_alpha=0.01, *, precision="auto", max_batch=64, device_index=0):
         super().__init__()
         H, W, C = input_shape                      # ADCNNM.py:42
         self._spec = NetSpec.torch_flavour((H, W, C), num_classes, conv_layers, hidden_units, leaky_alpha)
@@ -43,23 +49,36 @@ class CNNModel(nn.Module):
         self._precision, self._max_batch, self._device_index = precision, max_batch, device_index
         self._engine = None
         self._versions = None
+        self._train_eng = None           # fp32 handle of the train-mode forward (dropout lives on the fp32 path)
+        self._train_versions = None
 
     # ------------------------------------------------------------------ engine plumbing
+    def _make_engine(self):
+        if self._precision != "auto":
+            return Engine(self._spec, precision=self._precision, max_batch=self._max_batch, device=self._device_index)
+        for prec in ("fp16x3", "fp16"):
+            try:
+                return Engine(self._spec, precision=prec, max_batch=self._max_batch, device=self._device_index)
+            except ValueError:
+                continue
+        return Engine(self._spec, precision="fp32", max_batch=self._max_batch, device=self._device_index)
+
+    def _host_weights(self):
+        conv_w = [c.weight.detach().cpu().numpy().transpose(0, 2, 3, 1) for c in self.convs]   # (F,C,k,k)->(F,k,k,C)
+        conv_b = [c.bias.detach().cpu().numpy() for c in self.convs]
+        lin = [m for m in self.fc if isinstance(m, nn.Linear)]
+        return conv_w, conv_b, [l.weight.detach().cpu().numpy() for l in lin], [l.bias.detach().cpu().numpy() for l in lin]
+
     def _param_versions(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def sync_weights(self, force=True):
         ver = self._param_versions()
         if self._engine is None:
-            self._engine = Engine(self._spec, precision=self._precision, max_batch=self._max_batch,
-                                  device=self._device_index)
+            self._engine = self._make_engine()
             force = True
         if force or ver != self._versions:
-            conv_w = [c.weight.detach().cpu().numpy().transpose(0, 2, 3, 1) for c in self.convs]   # (F,C,k,k)->(F,k,k,C)
-            conv_b = [c.bias.detach().cpu().numpy() for c in self.convs]
-            lin = [m for m in self.fc if isinstance(m, nn.Linear)]
-            self._engine.set_weights(conv_w, conv_b, [l.weight.detach().cpu().numpy() for l in lin],
-                                     [l.bias.detach().cpu().numpy() for l in lin])
+            self._engine.set_weights(*self._host_weights())
             self._versions = ver
         return self._engine
 
@@ -69,11 +88,44 @@ class CNNModel(nn.Module):
 
     # ------------------------------------------------------------------ forward (ADCNNM.py:72-78)
     def forward(self, x):
-        if self.training and any(isinstance(m, nn.Dropout) and m.p > 0 for m in self.fc):
-            raise NotImplementedError("train-mode forward (dropout, autograd graph) is not offered: train with train_model(), "
-                                      "or call .eval() first")
-        cls, probs, logits = self.engine.predict(x)
+        rates = [m.p for m in self.fc if isinstance(m, nn.Dropout)]
+        if self.training and any(r > 0 for r in rates):
+            logits = self._forward_train(x, rates)
+        else:
+            cls, probs, logits = self.engine.predict(x)
         return logits.to(x.device) if isinstance(x, torch.Tensor) else logits
+
+    def _forward_train(self, x, rates, masks=None):
+        """ADCNNM.py:72-78 with the module in train mode: nn.Dropout(p) after every hidden LeakyReLU (ADCNNM.py:62).  ``masks``
+        [B, sum(hidden_units)] (0 or 1/(1-p)) may be injected; by default they are drawn with torch.rand on the device."""
+        eng = self._engine
+        if eng is None or eng.uses_tensor_path:
+            ver = self._param_versions()
+            if self._train_eng is None:
+                self._train_eng = Engine(self._spec, precision="fp32", max_batch=self._max_batch, device=self._device_index)
+                self._train_versions = None
+            if ver != self._train_versions:
+                self._train_eng.set_weights(*self._host_weights())
+                self._train_versions = ver
+            eng = self._train_eng
+        else:
+            eng = self.engine
+        n = int(x.shape[0]) if hasattr(x, "shape") and len(x.shape) == 4 else 1
+        units = list(self._spec.hidden_units)
+        out = []
+        for s0 in range(0, n, eng.max_batch):                   # masks are per forward of exactly B images
+            s1 = min(n, s0 + eng.max_batch)
+            if masks is None:
+                mk = torch.cat([(torch.rand(s1 - s0, u, device=eng.tdev) >= r).float() / (1.0 - r) if r < 1.0 else
+                                torch.zeros(s1 - s0, u, device=eng.tdev) for u, r in zip(units, rates)], dim=1)
+            else:
+                mk = torch.as_tensor(masks)[s0:s1]
+            eng.set_dropout_masks(mk, mask_backward=True)
+            try:
+                out.append(eng.predict(x[s0:s1] if n > 1 or (hasattr(x, "shape") and len(x.shape) == 4) else x)[2])
+            finally:
+                eng.set_dropout_masks(None)
+        return out[0] if len(out) == 1 else torch.cat(out, dim=0)
 
     # ------------------------------------------------------------------ batched entry points (new)
     def predict_batch(self, x):
@@ -87,9 +139,9 @@ class CNNModel(nn.Module):
         return cls.long(), logits, heat
 
 
-def _pull_into_modules(model):
-    """Device weights -> the nn.Parameters (state_dict layout), without triggering a re-upload."""
-    cw, cb, dw, db = model._engine.get_weights()
+def _pull_into_modules(model, eng):
+    """Weights of the training handle -> the nn.Parameters (state_dict layout); the inference handle re-uploads on its next use."""
+    cw, cb, dw, db = eng.get_weights()
     lin = [m for m in model.fc if isinstance(m, nn.Linear)]
     with torch.no_grad():
         for c, w, b in zip(model.convs, cw, cb):
@@ -98,7 +150,7 @@ def _pull_into_modules(model):
         for l, w, b in zip(lin, dw, db):
             l.weight.copy_(torch.from_numpy(w))
             l.bias.copy_(torch.from_numpy(b))
-    model._versions = model._param_versions()
+    model._train_versions = model._param_versions()
 
 
 def train_model(model, train_loader, test_loader, epochs=10, lr=0.001, device="cuda",
@@ -113,14 +165,16 @@ def train_model(model, train_loader, test_loader, epochs=10, lr=0.001, device="c
     from .training import DataParallelTrainer
     first = next(iter(train_loader))[0]
     bs = int(first.shape[0])
-    eng = model._engine
-    if eng is None or eng.uses_tensor_path or not eng.keep_all_activations or eng.max_batch < bs:
+    eng = model._train_eng
+    if eng is None or not eng.keep_all_activations or eng.max_batch < bs:
         if eng is not None:
             eng.close()
-        model._engine = Engine(model._spec, precision="fp32", max_batch=max(bs, model._max_batch), keep_all_activations=True,
-                               device=model._device_index)
-        model._versions = None
-    eng = model.sync_weights(force=False)
+        eng = model._train_eng = Engine(model._spec, precision="fp32", max_batch=max(bs, model._max_batch), keep_all_activations=True,
+                                        device=model._device_index)
+        model._train_versions = None
+    if model._param_versions() != model._train_versions:
+        eng.set_weights(*model._host_weights())
+        model._train_versions = model._param_versions()
     trainer = DataParallelTrainer(eng, opt="adam", lr=lr)
     rates = [m.p for m in model.fc if isinstance(m, nn.Dropout)]
     units = list(model._spec.hidden_units)
@@ -155,13 +209,13 @@ def train_model(model, train_loader, test_loader, epochs=10, lr=0.001, device="c
         history.append({"epoch": epoch + 1, "loss": avg_loss, "val_acc": val_acc})
         if val_acc > best_val_acc:
             best_val_acc = val_acc
-            _pull_into_modules(model)
+            _pull_into_modules(model, eng)
             d = os.path.dirname(save_path)
             if d:
                 os.makedirs(d, exist_ok=True)
             torch.save(model.state_dict(), save_path)
             print(f" Saved best model at epoch {epoch+1} with val_acc={val_acc:.4f}")
-    _pull_into_modules(model)
+    _pull_into_modules(model, eng)
     return history, best_val_acc
 
 

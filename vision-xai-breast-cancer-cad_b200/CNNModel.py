@@ -65,8 +65,16 @@ def load_weights(cls, path="trained_model/cnn_model.npz"):
 
 
 class CNNModel:
+    """Two handles behind one model (created on first use):
+
+    * the COMPAT handle -- fp32 CUDA-core path, every activation kept -- serves ``forward`` / ``predict`` (single sample, with the
+      reference's ``layers[*]`` caches), ``compute_backprops_for_explainability`` and training;
+    * the FAST handle serves the batched entry points ``predict_batch`` / ``predict_explain_batch``: ``precision="auto"``
+      (default) takes the fp32-grade split-operand tensor-core path (``fp16x3``) where the network's shape allows and the
+      compat handle otherwise; ``"fp32"`` forces the compat handle, ``"fp16x3"`` raises if the shape is not covered."""
+
     def __init__(self, input_shape, num_classes, conv_layers=[(8, 3), (16, 3)], hidden_units=[128, 64],
-                 dropout_rate=0.3, leaky_alpha=0.01, *, precision="fp32", max_batch=32, device=0,
+                 dropout_rate=0.3, leaky_alpha=0.01, *, precision="auto", max_batch=32, device=0,
                  keep_all_activations=True):
         self.input_shape = input_shape
         self.num_classes = num_classes
@@ -78,8 +86,14 @@ class CNNModel:
         self.epoch_accuracy = []
         self._precision, self._max_batch, self._device = precision, max_batch, device
         self._keep_all = keep_all_activations
-        self._engine = None
+        self._engine = None             # compat handle
         self._weights_key = None
+        self._fast = None               # fast handle (None: not created yet; the compat handle itself when the shape is not covered)
+        self._fast_key = None
+        self._gen = 0                   # forward() generation: the lazy layer caches and the explain backward check it
+        self._last_x = None
+        self._last_masks = None
+        self._dirty = False             # a training step moved the compat handle's weights ahead of ``layers`` (until _pull_weights)
         self._build_model()
 
     # ------------------------------------------------------------------ build (Classes/CNNModel.py:88-157)
@@ -123,65 +137,123 @@ class CNNModel:
     def _dense_layers(self):
         return [l for l in self.layers if l["type"] in ("dense", "output")]
 
+    def _key(self):
+        convs, denses = self._conv_layers(), self._dense_layers()
+        return tuple(id(dict.__getitem__(l, k)) for l in convs for k in ("filters", "biases")) + \
+            tuple(id(dict.__getitem__(l, k)) for l in denses for k in ("weights", "biases"))
+
+    def _upload(self, eng):
+        convs, denses = self._conv_layers(), self._dense_layers()
+        eng.set_weights([l["filters"] for l in convs], [l["biases"] for l in convs],
+                        [l["weights"] for l in denses], [l["biases"] for l in denses])
+
     def sync_weights(self, force=True):
         """Upload ``layers[*]['filters'|'weights'|'biases']`` to the device.  Called automatically when a
         weight array OBJECT is replaced (as ``load_weights`` does); call it yourself after in-place edits."""
-        convs, denses = self._conv_layers(), self._dense_layers()
-        key = tuple(id(dict.__getitem__(l, k)) for l in convs for k in ("filters", "biases")) + \
-            tuple(id(dict.__getitem__(l, k)) for l in denses for k in ("weights", "biases"))
+        key = self._key()
         if self._engine is None:
-            self._engine = Engine(self._spec(), precision=self._precision, max_batch=self._max_batch,
+            self._engine = Engine(self._spec(), precision="fp32", max_batch=self._max_batch,
                                   keep_all_activations=self._keep_all, device=self._device)
             force = True
         if force or key != self._weights_key:
-            self._engine.set_weights([l["filters"] for l in convs], [l["biases"] for l in convs],
-                                     [l["weights"] for l in denses], [l["biases"] for l in denses])
+            self._upload(self._engine)
             self._weights_key = key
+            if force:
+                self._fast_key = None
         return self._engine
 
     @property
     def engine(self) -> Engine:
+        """The compat handle (fp32, every activation kept)."""
         return self.sync_weights(force=False)
+
+    @property
+    def fast_engine(self) -> Engine:
+        """The handle of the batched entry points (see the class docstring)."""
+        if self._fast is None:
+            if self._precision in ("auto", "fp16x3"):
+                try:
+                    self._fast = Engine(self._spec(), precision="fp16x3", max_batch=self._max_batch, device=self._device)
+                except ValueError:
+                    if self._precision != "auto":
+                        raise
+            if self._fast is None:
+                self._fast = self.engine
+        if self._fast is self._engine:
+            return self.engine
+        key = self._key()
+        if key != self._fast_key:
+            self._upload(self._fast)
+            self._fast_key = key
+        return self._fast
 
     # ------------------------------------------------------------------ forward / predict
     def forward(self, x, training=True):
         """Classes/CNNModel.py:162-198 (single sample (H,W,C) -> probs (num_classes,) float64).
 
         Caches ``layer['input'|'output'|'switches'|'z']`` like the reference (fetched lazily from the device).
-        Training-mode dropout (:186-188) is applied inside ``train_batch`` (masks drawn from np.random in the reference's order)."""
-        if training and self.dropout_rate > 0.0:
-            raise NotImplementedError(
-                "forward(training=True) with dropout is part of the device training step: use train() / train_batch(); "
-                "for inference call forward(x, training=False) / predict(x)")
+        ``training=True`` (the reference's default) applies inverted dropout after every hidden dense layer (:186-188); the
+        multipliers are drawn from the global ``np.random`` stream exactly as the reference draws them (one ``rand(units)`` per
+        hidden layer, in layer order), so a seeded call follows the reference's random numbers."""
         x = np.asarray(x)
         eng = self.engine
-        cls, probs, logits = eng.predict(x[None].astype(np.float32))
+        masks = None
+        if training and self.dropout_rate > 0.0 and len(self.hidden_units) > 0:
+            masks = self._draw_dropout(1)
+            eng.set_dropout_masks(masks, mask_backward=False)
+        try:
+            cls, probs, logits = eng.predict(x[None].astype(np.float32))
+        finally:
+            if masks is not None:
+                eng.set_dropout_masks(None)
+        self._gen += 1
+        eng.cache_tag = (id(self), self._gen)
+        self._last_x, self._last_masks = np.array(x, dtype=np.float32), masks
         self._fill_caches(x)
         self._last_logits = logits
         return probs[0].double().cpu().numpy()
 
+    def _cache_ready(self):
+        """The compat handle still holds the activations of THIS model's latest forward(); anything run on it since (predict,
+        a batched call, another model sharing nothing but the device...) has reset the tag -> the forward is repeated."""
+        eng = self.engine
+        if self._last_x is None:
+            raise RuntimeError("no forward() has been run on this model yet")
+        if eng.cache_tag != (id(self), self._gen):
+            if self._last_masks is not None:
+                eng.set_dropout_masks(self._last_masks, mask_backward=False)
+            try:
+                eng.predict(self._last_x[None])
+            finally:
+                if self._last_masks is not None:
+                    eng.set_dropout_masks(None)
+            eng.cache_tag = (id(self), self._gen)
+        return eng
+
     def _fill_caches(self, x):
-        eng = self._engine
+        gen = self._gen
         ci = di = 0
-        prev_key = None
         for idx, layer in enumerate(self.layers):
             t = layer["type"]
             if t == "conv":
-                layer["input"] = x if ci == 0 else _Lazy(self._getter(_lib.T_POOL_OUT, ci - 1, self.layers[idx - 1]["output_shape"]))
-                layer["output"] = _Lazy(self._getter(_lib.T_CONV_OUT, ci, layer["output_shape"]))
+                layer["input"] = x if ci == 0 else _Lazy(self._getter(_lib.T_POOL_OUT, ci - 1, self.layers[idx - 1]["output_shape"], gen))
+                layer["output"] = _Lazy(self._getter(_lib.T_CONV_OUT, ci, layer["output_shape"], gen))
             elif t == "pool":
-                layer["input"] = _Lazy(self._getter(_lib.T_CONV_OUT, ci, layer["input_shape"]))
-                layer["output"] = _Lazy(self._getter(_lib.T_POOL_OUT, ci, layer["output_shape"]))
+                layer["input"] = _Lazy(self._getter(_lib.T_CONV_OUT, ci, layer["input_shape"], gen))
+                layer["output"] = _Lazy(self._getter(_lib.T_POOL_OUT, ci, layer["output_shape"], gen))
                 layer["switches"] = _Lazy(self._switch_getter(idx))
                 ci += 1
             else:
-                layer["z"] = _Lazy(self._getter(_lib.T_DENSE_Z, di, layer["output_shape"]))
+                layer["z"] = _Lazy(self._getter(_lib.T_DENSE_Z, di, layer["output_shape"], gen))
                 layer["input"] = _Lazy(self._dense_input_getter(idx, di))
                 di += 1
 
-    def _getter(self, kind, index, shape):
-        eng = self._engine
-        return lambda: eng.get_tensor(kind, index, 1)[0].double().cpu().numpy().reshape(shape)
+    def _getter(self, kind, index, shape, gen):
+        def fn():
+            if gen != self._gen:
+                raise RuntimeError("this layer cache belongs to an earlier forward(); read model.layers[...] again")
+            return self._cache_ready().get_tensor(kind, index, 1)[0].double().cpu().numpy().reshape(shape)
+        return fn
 
     def _switch_getter(self, idx):
         def fn():                                              # Classes/CNNModel.py:260 (every tie marked)
@@ -199,7 +271,11 @@ class CNNModel:
             if prev["type"] == "pool":
                 return prev["output"].flatten()
             z = prev["z"]
-            return np.where(z > 0, z, self.leaky_alpha * z)
+            h = np.where(z > 0, z, self.leaky_alpha * z)
+            if self._last_masks is not None:                  # training forward: the dropped activations (Classes/CNNModel.py:186-188)
+                off = sum(self.hidden_units[:di - 1])
+                h = h * self._last_masks[0, off:off + h.shape[0]].astype(np.float64)
+            return h
         return fn
 
     def _softmax(self, z):
@@ -219,14 +295,21 @@ class CNNModel:
         return np.argmax(probs), probs
 
     # ------------------------------------------------------------------ batched entry points (new)
+    def _batch_engine(self):
+        # between a training step and the next _pull_weights() only the compat handle has the current weights
+        return self.engine if self._dirty else self.fast_engine
+
     def predict_batch(self, X):
         """X [B,H,W,C] -> (classes int64 [B], probs float32 [B,nc])."""
-        cls, probs, _ = self.engine.predict(np.asarray(X, dtype=np.float32))
+        cls, probs, _ = self._batch_engine().predict(np.asarray(X, dtype=np.float32))
         return cls.cpu().numpy().astype(np.int64), probs.cpu().numpy()
 
     def predict_explain_batch(self, X, class_idx=None, grad_mode="softmax_ce"):
         """X [B,H,W,C] -> (classes [B], probs [B,nc], Grad-CAM heatmaps float32 [B,H,W] in [0,1])."""
-        cls, probs, _, heat = self.engine.predict_explain_host(np.asarray(X, dtype=np.float32), class_idx, grad_mode)
+        X = np.asarray(X)
+        if X.dtype != np.uint8:
+            X = np.asarray(X, dtype=np.float32)
+        cls, probs, _, heat = self._batch_engine().predict_explain_host(X, class_idx, grad_mode)
         return cls.astype(np.int64), probs, heat
 
     # ------------------------------------------------------------------ persistence (Classes/CNNModel.py:530-555)
@@ -250,10 +333,12 @@ class CNNModel:
     def _training_engine(self, batch_size):
         """The handle the training step runs on: fp32, every activation kept, max_batch >= batch_size."""
         eng = self._engine
-        if eng is None or eng.uses_tensor_path or not eng.keep_all_activations or eng.max_batch < batch_size:
+        if eng is None or not eng.keep_all_activations or eng.max_batch < batch_size:
             if eng is not None:
+                if self._fast is eng:
+                    self._fast = None
                 eng.close()
-            self._engine, self._precision, self._keep_all = None, "fp32", True
+            self._engine, self._keep_all = None, True
             self._max_batch = max(self._max_batch, int(batch_size))
         return self.sync_weights(force=False)
 
@@ -264,9 +349,8 @@ class CNNModel:
             l["filters"], l["biases"] = w.astype(np.float64), b.astype(np.float64)
         for l, w, b in zip(self._dense_layers(), dw, db):
             l["weights"], l["biases"] = w.astype(np.float64), b.astype(np.float64)
-        convs, denses = self._conv_layers(), self._dense_layers()
-        self._weights_key = tuple(id(dict.__getitem__(l, k)) for l in convs for k in ("filters", "biases")) + \
-            tuple(id(dict.__getitem__(l, k)) for l in denses for k in ("weights", "biases"))
+        self._weights_key = self._key()
+        self._dirty = False
 
     def _draw_dropout(self, n_samples):
         """The multipliers the reference would draw for n samples: np.random.rand(units) per hidden layer, sample by
@@ -296,6 +380,7 @@ class CNNModel:
                 eng.set_dropout_masks(None)
         allreduce_mean_(grads)
         eng.apply_update(grads, "sgd_clip", lr=lr, max_norm=5.0)
+        self._dirty = True
         return float(loss.sum())
 
     def train(self, X, y_onehot, X_test, y_test, epochs=10, lr=0.01, batch_size=8, eval_every_batch=True):

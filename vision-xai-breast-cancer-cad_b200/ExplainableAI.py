@@ -16,7 +16,7 @@ class ExplainableAI:
 
     def generate_heatmap(self, model, image, class_index, grad_mode="logit"):
         """image: (H,W,C) model input (or [B,H,W,C]); -> float32 heatmap (H,W) (or [B,H,W]) in [0,1]."""
-        eng = model.engine
+        eng = getattr(model, "fast_engine", None) or model.engine
         x = np.asarray(image, dtype=np.float32)
         single = x.ndim == 3
         xb = x[None] if single else x

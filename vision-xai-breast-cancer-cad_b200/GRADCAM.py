@@ -32,26 +32,34 @@ def generate_dual_class_gradcam_overlays_pytorch(img, classes_to_test=[0, 1], sa
                                                  model=None, preprocess=default_preprocess, write_png=True):
     """GRADCAM.py:31-81 -> ``{class_idx: (overlay_rgb_u8 (H,W,3), heatmap_u8 (H,W))}`` and the four PNGs.
 
-    ``img``: grayscale (H,W) scaled 0-255.  ``classes_to_test=None`` uses the predicted class (:60-61)."""
+    ``img``: grayscale (H,W) scaled 0-255, of ANY size: like pytorch_grad_cam, the heat-map is the low-resolution cam scaled to
+    the size of ``img`` (the reference hands a 512x512 image over whatever its CNN was fed, app.py:649-657); when ``img`` is not
+    the model's input size the CNN sees ``cv2.resize(img / 255, model size)``.  ``classes_to_test=None`` uses the predicted
+    class (:60-61)."""
     mdl = model if model is not None else globals()["model"]
     if mdl is None:
         raise RuntimeError("GRADCAM.model is not set: assign a CNNModel (bcad_b200.CNNModel / ADCNNM) first")
-    eng = mdl.engine
+    eng = getattr(mdl, "fast_engine", None) or mdl.engine     # NumPy mirror: the batched (tensor-core) handle
     os.makedirs(save_folder, exist_ok=True)
     overlays = {}
     img = np.asarray(img)
+    if img.ndim != 2:
+        raise ValueError(f"img must be a grayscale (H,W) array, got shape {img.shape}")
     H, W, _ = eng.spec.input_shape
-    if img.shape != (H, W):
-        raise ValueError(f"img shape {img.shape} does not match the model input ({H},{W})")
     img01 = (img / 255.0).astype(np.float32)                       # GRADCAM.py:46
-    x = preprocess(img01, eng.spec.input_shape)
+    net01 = img01
+    if img.shape != (H, W):
+        import cv2
+        net01 = cv2.resize(img01, (W, H), interpolation=cv2.INTER_LINEAR)
+    x = preprocess(net01, eng.spec.input_shape)
     if classes_to_test is None:
         cls, _, _ = eng.predict(x[None])
         classes_to_test = [int(cls[0])]                            # GRADCAM.py:56-61
     n = len(classes_to_test)
     xb = np.repeat(x[None], n, axis=0)
-    _, _, _, heat = eng.predict_explain(xb, np.asarray(classes_to_test, dtype=np.int32), "logit")   # :64
-    img_dev = torch.from_numpy(img01).to(heat.device)[None].expand(n, H, W)
+    _, _, _, heat = eng.predict_explain(xb, np.asarray(classes_to_test, dtype=np.int32), "logit",
+                                        out_hw=None if img.shape == (H, W) else img.shape)               # :64
+    img_dev = torch.from_numpy(img01).to(heat.device)[None].expand(n, *img.shape)
     ov, hu = _engine.overlay(img_dev, heat)                        # :67, :70
     ov, hu = ov.cpu().numpy(), hu.cpu().numpy()
     for i, class_idx in enumerate(classes_to_test):
@@ -63,3 +71,16 @@ def generate_dual_class_gradcam_overlays_pytorch(img, classes_to_test=[0, 1], sa
         overlays[class_idx] = (ov[i], hu[i])
         print(f"Saved Grad-CAM overlay and heatmap for class {class_idx} in {save_folder}")
     return overlays
+
+
+def generate_gradcam_overlays_batch(imgs_u8, class_idx=None, model=None, standardise=True, overlay_out=None, heat_out=None):
+    """The same outputs for a BATCH of 8-bit grey images [B,H,W] at the model's input size, through ONE host-buffer C-ABI call
+    (``bcad_gradcam_overlays_host``: uint8 in, uint8 RGB overlays + ``heatmap_uint8`` out; normalisation, CNN, Grad-CAM, JET
+    overlay all on the device).  ``class_idx``: None = each image's predicted class (GRADCAM.py:60-61), an int, or one per image.
+    -> (classes int64 [B], probs [B,nc], overlays uint8 [B,H,W,3], heatmaps uint8 [B,H,W])."""
+    mdl = model if model is not None else globals()["model"]
+    if mdl is None:
+        raise RuntimeError("GRADCAM.model is not set: assign a CNNModel (bcad_b200.CNNModel / ADCNNM) first")
+    eng = getattr(mdl, "fast_engine", None) or mdl.engine
+    cls, probs, _, ov, hu = eng.gradcam_overlays_host(imgs_u8, class_idx, "logit", standardise, overlay_out, heat_out)
+    return cls.astype(np.int64), probs, ov, hu

@@ -51,6 +51,8 @@ _SIGNATURES = {
     "bcad_commit": (C.c_int, [_P]),
     "bcad_predict": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P]),
     "bcad_predict_explain": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P]),
+    "bcad_predict_explain_sized": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
+    "bcad_gradcam_overlays_host": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "bcad_explain_backward": (C.c_int, [_P, C.c_int, _P, C.c_int, C.POINTER(_P), _P, _P]),
     "bcad_get_tensor": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "bcad_tensor_elems": (C.c_int64, [_P, C.c_int, C.c_int]),

@@ -372,8 +372,10 @@ int bcad_commit(bcad_model* mm) {
             BCAD_TRY(m->alloc((void**)&R.x, (size_t)R.cap * img * sizeof(float)));
             BCAD_TRY(m->alloc((void**)&R.cidx, (size_t)R.cap * sizeof(int32_t)));
             BCAD_TRY(m->alloc((void**)&R.heat, (size_t)R.cap * hm * sizeof(float)));
+            R.heat_elems = hm;
             BCAD_CUDA_CHECK(cudaMemset(R.counters, 0, 4 * sizeof(int32_t)));
             BCAD_CUDA_CHECK(cudaMemset(R.idx, 0, (size_t)R.cap * sizeof(int32_t)));
+            R.twin->n_dev = R.counters;          // counters[0]: images flagged in the current chunk
         }
     }
     BCAD_CUDA_CHECK(cudaDeviceSynchronize());
@@ -412,7 +414,7 @@ int launch_fused_head(Model* m, int n, const float* fc1_part, int splits, size_t
     a.fc1_part = fc1_part; a.fc1_splits = splits; a.fc1_ld = ld;
     a.alpha = m->cfg.alpha_dense; a.head = m->cfg.head; a.probs = m->probs; a.cls = m->cls;
     a.explain = explain ? 1 : 0; a.class_idx = class_idx; a.grad_mode = grad_mode;
-    a.dz1 = dz1; a.S = S; a.C = C; a.alpha_raw = alpha_raw;
+    a.dz1 = dz1; a.S = S; a.C = C; a.alpha_raw = alpha_raw; a.n_dev = m->n_dev;
     BCAD_LAUNCH(m, "dense_head_fused", launch_dense_head(a, n, s));
     return BCAD_OK;
 }
@@ -486,7 +488,7 @@ static int tail_chunk(Model* m, const void* A, int a_dtype, int n, float* heat, 
     const float inv_hw = 1.0f / ((float)T.Ho * (float)T.Wo);
     BCAD_LAUNCH(m, "cam", launch_cam(A, a_dtype, m->alpha_part, m->alpha_splits, inv_hw, m->alpha, m->cam_lo, m->mm, n, T.Ho,
                               T.Wo, T.Cout, m->cam_splits, s));
-    BCAD_LAUNCH(m, "upsample_norm", launch_upsample_norm(m->cam_lo, m->mm, m->cam_splits, heat, n, T.Ho, T.Wo, m->cfg.in_h, m->cfg.in_w, s));
+    BCAD_LAUNCH(m, "upsample_norm", launch_upsample_norm(m->cam_lo, m->mm, m->cam_splits, heat, n, T.Ho, T.Wo, m->heat_h, m->heat_w, s));
     return BCAD_OK;
 }
 
@@ -507,7 +509,7 @@ static int explain_chunk_fp32(Model* m, int n, const int32_t* class_idx, int gra
 }
 
 static int run(Model* m, const float* x, int B, const int32_t* class_idx, int grad_mode, bool explain, float* logits,
-               float* probs, int32_t* cls, float* heat, cudaStream_t s);
+               float* probs, int32_t* cls, float* heat, cudaStream_t s, int out_h = 0, int out_w = 0);
 
 // cfg.refine_margin: re-run the chunk's small-margin images on the fp32-grade twin and write their results over the 16-bit ones
 // (refine.cu).  Stream-ordered: the twin always runs min(cap, n) slots, the device-side count selects what is written back.
@@ -515,12 +517,17 @@ static int refine_chunk(Model* m, const float* xc, int n, const int32_t* ci, int
     Refine& R = m->refine;
     Model* t = R.twin;
     const int nc = m->cfg.num_classes, slots = std::min(R.cap, n);
-    const size_t img = (size_t)m->cfg.in_h * m->cfg.in_w * m->cfg.in_c, hm = (size_t)m->cfg.in_h * m->cfg.in_w;
+    const size_t img = (size_t)m->cfg.in_h * m->cfg.in_w * m->cfg.in_c, hm = (size_t)m->heat_h * m->heat_w;
+    if (explain && hm > R.heat_elems) {               // first call with a larger heat-map (bcad_predict_explain_sized): grow the twin's buffer
+        BCAD_CUDA_CHECK(cudaStreamSynchronize(s));
+        BCAD_TRY(m->alloc((void**)&R.heat, (size_t)R.cap * hm * sizeof(float)));
+        R.heat_elems = hm;
+    }
     BCAD_LAUNCH(m, "refine_flag", launch_refine_flag(m->dense.back().z, n, nc, m->cfg.refine_margin, slots, R.idx, R.counters, s));
     BCAD_LAUNCH(m, "refine_gather", launch_refine_gather(xc, img, ci, R.idx, R.counters, slots, R.x, R.cidx, s));
     BCAD_TRY(m->mark("refine_twin_fp16x3", s));
     const int64_t l0 = t->launches;
-    BCAD_TRY(run(t, R.x, slots, ci ? R.cidx : nullptr, grad_mode, explain, nullptr, nullptr, nullptr, explain ? R.heat : nullptr, s));
+    BCAD_TRY(run(t, R.x, slots, ci ? R.cidx : nullptr, grad_mode, explain, nullptr, nullptr, nullptr, explain ? R.heat : nullptr, s, m->heat_h, m->heat_w));
     m->launches += t->launches - l0;
     RefineScatter a;
     memset(&a, 0, sizeof(a));
@@ -538,8 +545,9 @@ static int refine_chunk(Model* m, const float* xc, int n, const int32_t* ci, int
 }
 
 static int run(Model* m, const float* x, int B, const int32_t* class_idx, int grad_mode, bool explain, float* logits,
-               float* probs, int32_t* cls, float* heat, cudaStream_t s) {
+               float* probs, int32_t* cls, float* heat, cudaStream_t s, int out_h, int out_w) {
     BCAD_REQUIRE(m && x, "null model or input");
+    BCAD_REQUIRE(out_h >= 0 && out_w >= 0 && out_h <= 16384 && out_w <= 16384 && (out_h == 0) == (out_w == 0), "bad heat-map size %dx%d", out_h, out_w);
     BCAD_REQUIRE(B >= 1, "batch must be >= 1, got %d", B);
     BCAD_REQUIRE(grad_mode == BCAD_GRAD_LOGIT || grad_mode == BCAD_GRAD_SOFTMAX_CE, "bad grad_mode %d", grad_mode);
     BCAD_REQUIRE(!explain || heat, "heatmap output pointer is null");
@@ -550,7 +558,9 @@ static int run(Model* m, const float* x, int B, const int32_t* class_idx, int gr
     // the workspace is shared: order this call after the previous one even when it ran on another stream
     BCAD_CUDA_CHECK(cudaStreamWaitEvent(s, m->call_done, 0));
     const int mb = m->cfg.max_batch, nc = m->cfg.num_classes;
-    const size_t img = (size_t)m->cfg.in_h * m->cfg.in_w * m->cfg.in_c, hm = (size_t)m->cfg.in_h * m->cfg.in_w;
+    m->heat_h = out_h ? out_h : m->cfg.in_h;
+    m->heat_w = out_w ? out_w : m->cfg.in_w;
+    const size_t img = (size_t)m->cfg.in_h * m->cfg.in_w * m->cfg.in_c, hm = (size_t)m->heat_h * m->heat_w;
     m->prof_n = 0;
     for (int b0 = 0; b0 < B; b0 += mb) {
         const int n = std::min(mb, B - b0);
@@ -587,6 +597,12 @@ int bcad_predict_explain(bcad_model* mm, const float* x, int B, const int32_t* c
                          float* probs, int32_t* cls, float* heat, void* stream) {
     return run(reinterpret_cast<Model*>(mm), x, B, class_idx, grad_mode, true, logits, probs, cls, heat,
                (cudaStream_t)stream);
+}
+
+int bcad_predict_explain_sized(bcad_model* mm, const float* x, int B, const int32_t* class_idx, int grad_mode, float* logits,
+                               float* probs, int32_t* cls, int out_h, int out_w, float* heat, void* stream) {
+    BCAD_REQUIRE(out_h >= 1 && out_w >= 1, "predict_explain_sized: bad heat-map size %dx%d", out_h, out_w);
+    return run(reinterpret_cast<Model*>(mm), x, B, class_idx, grad_mode, true, logits, probs, cls, heat, (cudaStream_t)stream, out_h, out_w);
 }
 
 int bcad_explain_backward(bcad_model* mm, int B, const int32_t* class_idx, int grad_mode,
@@ -703,9 +719,10 @@ int bcad_get_tensor(bcad_model* mm, int kind, int index, int B, float* dst, void
 // -----------------------------------------------------------------------------------------------------
 static int predict_explain_host_impl(bcad_model* mm, const float* x_host, const uint8_t* x8_host, int B, const int32_t* class_idx_host,
                                      int grad_mode, float* logits_host, float* probs_host, int32_t* cls_host, float* heat_host,
-                                     uint8_t* heat_u8_host) {
+                                     uint8_t* heat_u8_host, const uint8_t* gray8_host = nullptr, int standardise = 0,
+                                     uint8_t* overlay_host = nullptr) {
     Model* m = reinterpret_cast<Model*>(mm);
-    BCAD_REQUIRE(m && (x_host || x8_host), "predict_explain_host: null argument");
+    BCAD_REQUIRE(m && (x_host || x8_host || gray8_host), "predict_explain_host: null argument");
     BCAD_REQUIRE(B >= 1, "batch must be >= 1, got %d", B);
     if (!m->committed) { set_error("weights not committed: call bcad_commit first"); return BCAD_ERR_STATE; }
     BCAD_REQUIRE(grad_mode == BCAD_GRAD_LOGIT || grad_mode == BCAD_GRAD_SOFTMAX_CE, "bad grad_mode %d", grad_mode);
@@ -748,8 +765,13 @@ static int predict_explain_host_impl(bcad_model* mm, const float* x_host, const 
         }
         if (heat_u8_host != nullptr && X.heat8[0] == nullptr)
             for (int i = 0; i < 2; ++i) BCAD_TRY(m->alloc((void**)&X.heat8[i], (size_t)X.chunk * hm));
-        if (x8_host != nullptr && X.x8[0] == nullptr)
+        if ((x8_host != nullptr || gray8_host != nullptr) && X.x8[0] == nullptr)
             for (int i = 0; i < 2; ++i) BCAD_TRY(m->alloc((void**)&X.x8[i], (size_t)X.chunk * img));
+        if (gray8_host != nullptr && X.img01[0] == nullptr)
+            for (int i = 0; i < 2; ++i) {
+                BCAD_TRY(m->alloc((void**)&X.img01[i], (size_t)X.chunk * hm * sizeof(float)));
+                BCAD_TRY(m->alloc((void**)&X.ov8[i], (size_t)X.chunk * hm * 3));
+            }
     }
     // small outputs go through pinned staging sized for the whole call
     const size_t per_img = (size_t)(2 * nc) * sizeof(float) + sizeof(int32_t);
@@ -771,7 +793,7 @@ static int predict_explain_host_impl(bcad_model* mm, const float* x_host, const 
         // float32 images: the link is the bound and 64-image chunks fill the pipeline sooner; 8-bit images: compute is the bound
         // and 128-image chunks run the kernels more efficiently
         if (getenv("BCAD_HOST_CHUNK") == nullptr)
-            C0 = std::min(std::min(X.chunk, x8_host ? 128 : 64), std::max(32, ((B + 3) / 4 + 31) / 32 * 32));
+            C0 = std::min(std::min(X.chunk, (x8_host || gray8_host) ? 128 : 64), std::max(32, ((B + 3) / 4 + 31) / 32 * 32));
         int left = B;
         std::vector<int> head, tail;
         // measured on the bench workload (512 images): uniform 64-image chunks 3.62 ms, ramped 3.93 ms -- the small
@@ -813,22 +835,28 @@ static int predict_explain_host_impl(bcad_model* mm, const float* x_host, const 
             BCAD_CUDA_CHECK(cudaStreamWaitEvent(X.s_in, X.compute_done[slot], 0));
             BCAD_CUDA_CHECK(cudaStreamWaitEvent(X.s_compute, X.out_done[slot], 0));
         }
-        if (x8_host) BCAD_CUDA_CHECK(cudaMemcpyAsync(X.x8[slot], x8_host + (size_t)b0 * img, (size_t)n * img, cudaMemcpyHostToDevice, X.s_in));
+        if (gray8_host) BCAD_CUDA_CHECK(cudaMemcpyAsync(X.x8[slot], gray8_host + (size_t)b0 * hm, (size_t)n * hm, cudaMemcpyHostToDevice, X.s_in));
+        else if (x8_host) BCAD_CUDA_CHECK(cudaMemcpyAsync(X.x8[slot], x8_host + (size_t)b0 * img, (size_t)n * img, cudaMemcpyHostToDevice, X.s_in));
         else BCAD_CUDA_CHECK(cudaMemcpyAsync(X.x[slot], x_host + (size_t)b0 * img, (size_t)n * img * sizeof(float), cudaMemcpyHostToDevice, X.s_in));
         if (class_idx_host)
             BCAD_CUDA_CHECK(cudaMemcpyAsync(X.cidx[slot], class_idx_host + b0, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, X.s_in));
         BCAD_CUDA_CHECK(cudaEventRecord(X.in_done[slot], X.s_in));
         BCAD_CUDA_CHECK(cudaStreamWaitEvent(X.s_compute, X.in_done[slot], 0));
-        const bool want_heat = (heat_host != nullptr || heat_u8_host != nullptr);
-        int rc = x8_host ? launch_u8_to_unit(X.x8[slot], X.x[slot], (size_t)n * img, X.s_compute) : BCAD_OK;
+        const bool want_heat = (heat_host != nullptr || heat_u8_host != nullptr || overlay_host != nullptr);
+        int rc = BCAD_OK;
+        if (gray8_host) rc = launch_gray_preprocess(X.x8[slot], X.img01[slot], X.x[slot], n, (int)hm, m->cfg.in_c, standardise, X.s_compute);
+        else if (x8_host) rc = launch_u8_to_unit(X.x8[slot], X.x[slot], (size_t)n * img, X.s_compute);
         if (rc == BCAD_OK) rc = run(m, X.x[slot], n, class_idx_host ? X.cidx[slot] : nullptr, grad_mode, want_heat, X.logits[slot],
                      X.probs[slot], X.cls[slot], X.heat[slot], X.s_compute);
-        if (rc == BCAD_OK && heat_u8_host != nullptr) rc = launch_heat_to_u8(X.heat[slot], X.heat8[slot], (size_t)n * hm, X.s_compute);
+        if (rc == BCAD_OK && overlay_host != nullptr)             // show_cam_on_image + heatmap_uint8 in one pass (GRADCAM.py:67,70)
+            rc = launch_overlay(X.img01[slot], X.heat[slot], n, m->cfg.in_h, m->cfg.in_w, X.ov8[slot], heat_u8_host ? X.heat8[slot] : nullptr, X.s_compute);
+        else if (rc == BCAD_OK && heat_u8_host != nullptr) rc = launch_heat_to_u8(X.heat[slot], X.heat8[slot], (size_t)n * hm, X.s_compute);
         if (rc != BCAD_OK) { cudaDeviceSynchronize(); return rc; }
         BCAD_CUDA_CHECK(cudaEventRecord(X.compute_done[slot], X.s_compute));
         BCAD_CUDA_CHECK(cudaStreamWaitEvent(X.s_out, X.compute_done[slot], 0));
         if (heat_host) BCAD_CUDA_CHECK(cudaMemcpyAsync(heat_host + (size_t)b0 * hm, X.heat[slot], (size_t)n * hm * sizeof(float), cudaMemcpyDeviceToHost, X.s_out));
         if (heat_u8_host) BCAD_CUDA_CHECK(cudaMemcpyAsync(heat_u8_host + (size_t)b0 * hm, X.heat8[slot], (size_t)n * hm, cudaMemcpyDeviceToHost, X.s_out));
+        if (overlay_host) BCAD_CUDA_CHECK(cudaMemcpyAsync(overlay_host + (size_t)b0 * hm * 3, X.ov8[slot], (size_t)n * hm * 3, cudaMemcpyDeviceToHost, X.s_out));
         BCAD_CUDA_CHECK(cudaMemcpyAsync(st_logits + (size_t)b0 * nc, X.logits[slot], (size_t)n * nc * sizeof(float), cudaMemcpyDeviceToHost, X.s_out));
         BCAD_CUDA_CHECK(cudaMemcpyAsync(st_probs + (size_t)b0 * nc, X.probs[slot], (size_t)n * nc * sizeof(float), cudaMemcpyDeviceToHost, X.s_out));
         BCAD_CUDA_CHECK(cudaMemcpyAsync(st_cls + b0, X.cls[slot], (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, X.s_out));
@@ -858,6 +886,15 @@ int bcad_predict_explain_host_u8in(bcad_model* mm, const uint8_t* x_u8_host, int
     BCAD_REQUIRE(x_u8_host, "predict_explain_host_u8in: null image pointer");
     BCAD_REQUIRE(!(heat_host && heat_u8_host), "predict_explain_host_u8in: pass one heat-map pointer (float32 or uint8), not both");
     return predict_explain_host_impl(mm, nullptr, x_u8_host, B, class_idx_host, grad_mode, logits_host, probs_host, cls_host, heat_host, heat_u8_host);
+}
+
+int bcad_gradcam_overlays_host(bcad_model* mm, const uint8_t* gray_u8_host, int B, const int32_t* class_idx_host, int grad_mode,
+                               int standardise, float* logits_host, float* probs_host, int32_t* cls_host, uint8_t* overlay_rgb_host,
+                               uint8_t* heat_u8_host) {
+    BCAD_REQUIRE(gray_u8_host && (overlay_rgb_host || heat_u8_host), "gradcam_overlays_host: null image / output pointer");
+    BCAD_REQUIRE(standardise == 0 || standardise == 1, "gradcam_overlays_host: standardise must be 0 or 1");
+    return predict_explain_host_impl(mm, nullptr, nullptr, B, class_idx_host, grad_mode, logits_host, probs_host, cls_host, nullptr,
+                                     heat_u8_host, gray_u8_host, standardise, overlay_rgb_host);
 }
 
 // -----------------------------------------------------------------------------------------------------

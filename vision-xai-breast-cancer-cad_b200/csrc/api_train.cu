@@ -1,8 +1,9 @@
 // C-ABI of the training step (BASELINE config 5): gradients of the mean softmax cross-entropy over a
 // batch w.r.t. every weight and bias, optimiser updates on the device weights, weight read-back.
 // Reference: Classes/CNNModel.py:282-355 (_compute_sample_grads), :372-394 (_apply_grads), :399-512 (train);
-// ADCNNM.py:86-153 (Adam + CrossEntropyLoss).  fp32 path only; dropout is not applied (train with dropout_rate=0 or
-// accept eval-mode activations).
+// ADCNNM.py:86-153 (Adam + CrossEntropyLoss).  fp32 path only.  Dropout: the caller draws the multipliers and hands them over with
+// bcad_set_dropout_masks; the forward applies them after every hidden layer and the backward uses the dropped activations
+// (and, for autograd semantics, masks the gradient too).
 #include <string.h>
 
 #include <mutex>

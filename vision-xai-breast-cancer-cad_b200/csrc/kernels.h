@@ -60,6 +60,8 @@ int launch_overlay(const float* img01, const float* cam, int B, int H, int W, ui
 int launch_ce_loss_topgrad(const float* probs, const int32_t* labels, float* loss, float* dz, int B, int nc, cudaStream_t s);
 int launch_heat_to_u8(const float* cam, uint8_t* out, size_t n, cudaStream_t s);
 int launch_u8_to_unit(const uint8_t* src, float* dst, size_t n, cudaStream_t s);
+// GRADCAM.py:46 + the CNN-input normalisation of app.py:179-182: img01 = u8 / 255; x[.., c] = standardise ? (img01 - mean) / (std + 1e-8) : img01
+int launch_gray_preprocess(const uint8_t* g8, float* img01, float* x, int B, int npix, int C, int standardise, cudaStream_t s);
 int launch_bottleneck_resize(const float* src, float* dst, int B, int C, int H, int W, int chw, int oh, int ow, cudaStream_t s);
 int launch_leaky_from_z(const float* z, float* h, float alpha, int64_t n, cudaStream_t s);
 int launch_mul_mask(float* h, const float* mask, int B, int units, int ld, cudaStream_t s);
@@ -78,7 +80,7 @@ int launch_adam_update(float* w, const float* g, float* m1, float* m2, float lr,
 // idx[0..count) = images of the chunk whose two largest logits differ by less than `margin`, ascending; counters = {count
 // clamped to cap, running total refined, running total overflowed}
 int launch_refine_flag(const float* logits, int n, int nc, float margin, int cap, int32_t* idx, int32_t* counters, cudaStream_t s);
-// slots [0,slots): image idx[slot] (slots >= count replicate image 0 of the chunk: finite inputs, results dropped)
+// slots [0,count): image idx[slot] (the twin's kernels read the same device-side count and skip the other slots)
 int launch_refine_gather(const float* x, size_t img_elems, const int32_t* class_idx, const int32_t* idx, const int32_t* counters,
                          int slots, float* rx, int32_t* rcidx, cudaStream_t s);
 struct RefineScatter {
@@ -119,6 +121,7 @@ struct HeadArgs {
     const float* S;               // [sizes[0]][C] fp32, nullable
     int C;
     float* alpha_raw;             // [B][C]
+    const int* n_dev;             // nullable DEVICE pointer: only the first *n_dev images are live (refinement twin)
 };
 int launch_dense_head(const HeadArgs& a, int B, cudaStream_t s);
 

@@ -1020,6 +1020,45 @@ int launch_u8_to_unit(const uint8_t* src, float* dst, size_t n, cudaStream_t s) 
     return BCAD_OK;
 }
 
+// 8-bit grey image -> img01 = u8 / 255 (GRADCAM.py:46) and the CNN input: per-image standardisation (x - mean) / (std + 1e-8) as the
+// reference prepares its CNN inputs (app.py:179-182), the single channel replicated to C.  mean / std from exact integer sums.
+__global__ void __launch_bounds__(512) gray_preprocess_kernel(const uint8_t* __restrict__ g8, float* __restrict__ img01, float* __restrict__ x,
+                                                              int npix, int C, int standardise) {
+    __shared__ unsigned long long s_sum[16], s_sq[16];
+    __shared__ float s_mean, s_den;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const uint8_t* src = g8 + (size_t)b * npix;
+    if (standardise) {
+        unsigned long long sum = 0, sq = 0;
+        for (int i = tid; i < npix; i += 512) { const unsigned v = src[i]; sum += v; sq += v * v; }
+        for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+        if ((tid & 31) == 0) { s_sum[tid >> 5] = sum; s_sq[tid >> 5] = sq; }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long ts = 0, tq = 0;
+            for (int w = 0; w < 16; ++w) { ts += s_sum[w]; tq += s_sq[w]; }
+            const double mean = (double)ts / (255.0 * npix);
+            const double var = (double)tq / (65025.0 * npix) - mean * mean;
+            s_mean = (float)mean;
+            s_den = (float)sqrt(var > 0.0 ? var : 0.0) + 1e-8f;
+        }
+        __syncthreads();
+    }
+    const float mean = standardise ? s_mean : 0.f, den = standardise ? s_den : 1.f;
+    for (int i = tid; i < npix; i += 512) {
+        const float v = (float)src[i] / 255.0f;
+        img01[(size_t)b * npix + i] = v;
+        const float xv = standardise ? (v - mean) / den : v;
+        for (int c = 0; c < C; ++c) x[((size_t)b * npix + i) * C + c] = xv;
+    }
+}
+
+int launch_gray_preprocess(const uint8_t* g8, float* img01, float* x, int B, int npix, int C, int standardise, cudaStream_t s) {
+    gray_preprocess_kernel<<<B, 512, 0, s>>>(g8, img01, x, npix, C, standardise);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
 int launch_overlay(const float* img01, const float* cam, int B, int H, int W, uint8_t* overlay_rgb, uint8_t* heat_u8,
                    cudaStream_t s) {
     overlay_kernel<<<B, 1024, 0, s>>>(img01, cam, H, W, overlay_rgb, heat_u8);
@@ -1090,6 +1129,7 @@ __global__ void __launch_bounds__(256) dense_head_kernel(HeadArgs a) {
     extern __shared__ __align__(16) float sh[];   // z of every layer, then activations / gradients scratch
     __shared__ int s_cls;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (a.n_dev != nullptr && b >= *a.n_dev) return;      // refinement twin: only the flagged images are live
     int off[BCAD_MAX_DENSE + 1];
     off[0] = 0;
     for (int j = 0; j < a.n_dense; ++j) off[j + 1] = off[j] + a.sizes[j];

@@ -54,6 +54,8 @@ struct Xfer {                          // host-buffer pipeline (bcad_predict_exp
     float* heat[2] = {nullptr, nullptr};
     uint8_t* heat8[2] = {nullptr, nullptr};   // u8 heat-maps of a chunk (bcad_predict_explain_host_u8), allocated on first use
     uint8_t* x8[2] = {nullptr, nullptr};      // 8-bit input pixels of a chunk (bcad_predict_explain_host_u8in), allocated on first use
+    float* img01[2] = {nullptr, nullptr};     // grey image / 255 of a chunk and its RGB overlays (bcad_gradcam_overlays_host), first use
+    uint8_t* ov8[2] = {nullptr, nullptr};
     float* logits[2] = {nullptr, nullptr};
     float* probs[2] = {nullptr, nullptr};
     int32_t* cls[2] = {nullptr, nullptr};
@@ -94,6 +96,7 @@ struct Refine {                         // cfg.refine_margin > 0: small-margin i
     float* x = nullptr;                 // [cap] gathered inputs
     int32_t* cidx = nullptr;            // [cap] gathered target classes
     float* heat = nullptr;              // [cap] heat-maps of the twin (its other outputs are read from its own workspace)
+    size_t heat_elems = 0;              // per-image capacity of `heat` (grows on the first larger bcad_predict_explain_sized call)
 };
 
 struct Model {
@@ -108,6 +111,8 @@ struct Model {
     std::mutex mu;
     std::mutex host_mu;                 // serialises the host-buffer calls of one handle (shared staging, streams, events)
     Refine refine;
+    int heat_h = 0, heat_w = 0;         // heat-map size of the call in flight (in_h x in_w unless bcad_predict_explain_sized asks otherwise)
+    const int32_t* n_dev = nullptr;     // refinement TWIN only: device pointer to the live image count of its launches
     std::vector<void*> allocs;
     // shared workspace
     float* partials = nullptr;

@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(256)
 refine_gather_kernel(const float* __restrict__ x, size_t img_elems, const int32_t* __restrict__ class_idx, const int32_t* __restrict__ idx,
                      const int32_t* __restrict__ counters, float* __restrict__ rx, int32_t* __restrict__ rcidx) {
     const int slot = blockIdx.x;
-    const int src = slot < counters[0] ? idx[slot] : 0;
+    if (slot >= counters[0]) return;              // the twin's kernels only touch the first counters[0] slots
+    const int src = idx[slot];
     const float* in = x + (size_t)src * img_elems;
     float* out = rx + (size_t)slot * img_elems;
     if (blockIdx.y == 0 && threadIdx.x == 0 && class_idx != nullptr) rcidx[slot] = class_idx[src];

@@ -117,7 +117,12 @@ int launch_conv_first_pool(const float* x, const float* w9c, const float* bias, 
 template <int COUT, bool SPLIT, bool DBUF, bool PLAIN>
 __global__ void __launch_bounds__(128, DBUF ? 3 : 4)
 conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_img /*[4 or 2][COUT][16 B]*/,
-                     __half* __restrict__ out, int B, int H, int W, int pad, int Hp, int Wp, float alpha) {
+                     __half* __restrict__ out, int B, int H, int W, int pad, int Hp, int Wp, float alpha, const int* __restrict__ n_dev) {
+    if (n_dev != nullptr) {                       // live image count decided on the device (refine.cu)
+        const int nd = *n_dev;
+        if (nd <= 0) return;
+        if (nd < B) B = nd;
+    }
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_a = smem;                          // (DBUF ? 2 : 1) buffers x 4 classes x [4 chunks][128 rows][16 B] = 32 KB each
     uint8_t* s_b = smem + (DBUF ? 2 : 1) * 32768;  // [4 chunks][COUT][16 B]
@@ -341,15 +346,15 @@ conv_first_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_
 
 template <int COUT, bool SPLIT, bool DBUF = true, bool PLAIN = false>
 static int launch_conv_first_tc_t(const float* x, const uint8_t* w_img, __half* out, int B, int H, int W, int pad, int Hp,
-                                  int Wp, float alpha, int grid, int smem, cudaStream_t s) {
+                                  int Wp, float alpha, int grid, int smem, cudaStream_t s, const int* n_dev) {
     BCAD_CUDA_CHECK(cudaFuncSetAttribute(conv_first_tc_kernel<COUT, SPLIT, DBUF, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    conv_first_tc_kernel<COUT, SPLIT, DBUF, PLAIN><<<grid, 128, smem, s>>>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha);
+    conv_first_tc_kernel<COUT, SPLIT, DBUF, PLAIN><<<grid, 128, smem, s>>>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, n_dev);
     BCAD_CUDA_CHECK(cudaGetLastError());
     return BCAD_OK;
 }
 
 int launch_conv_first_tc(const float* x, const uint8_t* w_img, __half* out, int B, int H, int W, int pad, int Cout,
-                         float alpha, bool split_hi_lo, bool plain, int sms, cudaStream_t s) {
+                         float alpha, bool split_hi_lo, bool plain, int sms, cudaStream_t s, const int* n_dev) {
     BCAD_REQUIRE(!(plain && split_hi_lo), "conv_first_tc: the hi/lo output split needs hi/lo operands");
     const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2, Hp = Ho / 2, Wp = Wo / 2;
     const int n_tiles = B * Hp * cdiv(Wp, 128);
@@ -359,11 +364,11 @@ int launch_conv_first_tc(const float* x, const uint8_t* w_img, __half* out, int 
     const int smem = (single ? 1 : 2) * 32768 + 4 * Cout * 16;
     const int per_sm = Cout <= 32 ? (single ? 4 : 3) : 2;          // smem: 66 KB per CTA; TMEM: 4*Cout columns per CTA
     const int grid = n_tiles < sms * per_sm ? n_tiles : sms * per_sm;
-    if (single && plain) return launch_conv_first_tc_t<32, false, false, true>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s);
-    if (single) return launch_conv_first_tc_t<32, false, false>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s);
-    if (Cout == 32 && split_hi_lo) return launch_conv_first_tc_t<32, true>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s);
-    if (Cout == 64 && plain) return launch_conv_first_tc_t<64, false, true, true>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s);
-    if (Cout == 64 && !split_hi_lo) return launch_conv_first_tc_t<64, false>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s);
+    if (single && plain) return launch_conv_first_tc_t<32, false, false, true>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s, n_dev);
+    if (single) return launch_conv_first_tc_t<32, false, false>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s, n_dev);
+    if (Cout == 32 && split_hi_lo) return launch_conv_first_tc_t<32, true>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s, n_dev);
+    if (Cout == 64 && plain) return launch_conv_first_tc_t<64, false, true, true>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s, n_dev);
+    if (Cout == 64 && !split_hi_lo) return launch_conv_first_tc_t<64, false>(x, w_img, out, B, H, W, pad, Hp, Wp, alpha, grid, smem, s, n_dev);
     set_error("conv_first_tc: Cout %d (split=%d) not supported", Cout, (int)split_hi_lo);
     return BCAD_ERR_INVALID;
 }
@@ -412,6 +417,12 @@ struct IgemmSmem {
 
 template <int CIN, int COUT, bool X3>
 __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) {
+    int n_live = a.B;
+    if (a.n_dev != nullptr) {                     // live image count decided on the device (refine.cu)
+        const int nd = *a.n_dev;
+        if (nd <= 0) return;
+        if (nd < n_live) n_live = nd;
+    }
     using L = IgemmSmem<CIN, COUT>;
     constexpr int IG_STAGES = L::STAGES;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -456,7 +467,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_igemm_kernel(IgemmArgs a) 
     const uint32_t tmem = *tmem_slot;
 
     const int per_img = a.bands * a.xsegs;
-    const int n_items = a.B * per_img;
+    const int n_items = n_live * per_img;
     const int in_row_elems = L::CHUNKS * a.W * 8;          // fp16 elements per input row (all channel octets)
 
     if (warp == 0) {
@@ -816,6 +827,7 @@ constexpr int FC_STAGES = 4;
 constexpr int FC_THREADS = 192;
 
 __global__ void __launch_bounds__(FC_THREADS, 1) fc_splitk_kernel(FcArgs a) {
+    if (a.n_dev != nullptr && *a.n_dev <= 0) return;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem base is 1024-aligned by declaration; SW128 tiles need it
     uint8_t* smem = smem_raw;

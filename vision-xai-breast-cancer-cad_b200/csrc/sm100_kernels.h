@@ -11,8 +11,11 @@ int launch_conv_first_pool(const float* x, const float* w9c, const float* bias, 
 
 // tensor-core first conv: w_img = [4 chunks][Cout][8 halves] rows [w_hi(9) b_hi | w_hi(9) b_lo | w_lo(9) 0 0 0], or, with
 // plain_operands (fp16 mode: no hi/lo split of image and weights), [2 chunks][Cout][8 halves] rows [w(9) b_hi b_lo 0 0 0 0 0]
+// n_dev (nullable, also in the argument structs below): DEVICE pointer to the live image count of this launch -- the kernel works
+// on min(B, *n_dev) images and returns at once when that is 0 (the refinement twin, refine.cu: the host does not know how many
+// images were flagged)
 int launch_conv_first_tc(const float* x, const uint8_t* w_img, __half* out, int B, int H, int W, int pad, int Cout,
-                         float alpha, bool split_hi_lo, bool plain_operands, int sms, cudaStream_t s);
+                         float alpha, bool split_hi_lo, bool plain_operands, int sms, cudaStream_t s, const int* n_dev = nullptr);
 
 struct IgemmArgs {
     const __half* in;      // C8 planar [B][H][Cin/8][W][8]
@@ -25,6 +28,7 @@ struct IgemmArgs {
     int xsegs;                    // 128-pixel segments per row: work item = (image, band, segment)
     float alpha;
     int debug;                    // timing experiments only: 1 no act store, 2 no pool store, 4 empty epilogue, 8 no MMA
+    const int* n_dev = nullptr;
 };
 int launch_conv_igemm(const IgemmArgs& a, int Cin, int Cout, bool x3, int sms, cudaStream_t s);
 
@@ -71,6 +75,7 @@ struct FcArgs {
     int ncb;                      // column blocks (grid.z): block cb reads w_tiles + cb * nkb tiles and writes columns [cb*N, +N); 0/1 = one
     long long ld_out;             // row stride of the output in floats; 0 = N (the split-K partial layout)
     int m_valid;                  // rows >= m_valid are not stored (0 = store all m_pad rows: the partial buffer is padded)
+    const int* n_dev = nullptr;   // *n_dev == 0: nothing to do
 };
 // dz1 fp32 [B][K] -> fp16x3 A tiles [b/128][K/64][(hi|lo)][128][128 B, chunks XOR (row&7)] for the fc1 input-gradient GEMM
 int launch_rows_to_fc_tiles_x3(const float* src, uint8_t* tiles, int B, int K, int m_pad, cudaStream_t s);
@@ -83,7 +88,7 @@ int launch_cam_c8(const __half* A, const float* alpha_raw, float scale, float* a
 // fused tail (sm100_tail.cu): cam + min-max + bilinear + min-max, a 2-CTA cluster per image
 bool tail_fused_supported(int h, int w, int H, int W, int C);
 int launch_tail_fused(const __half* A, const float* alpha_raw, float scale, float* alpha_out, float* out, int B, int h, int w,
-                      int H, int W, int C, bool x3, cudaStream_t s);
+                      int H, int W, int C, bool x3, cudaStream_t s, const int* n_dev = nullptr);
 // tie-duplicating rule on the fp16x3 path: alpha_raw[b][k] = sum_windows g * (#maxima in the window), A = split C8-planar activations
 int launch_alpha_ties_c8(const __half* A, const float* g_pool, float* alpha_raw, int B, int h, int w, int C, cudaStream_t s);
 int launch_c8_to_nhwc(const __half* src, float* dst, int B, int h, int w, int C, bool x3, cudaStream_t s);

@@ -70,7 +70,7 @@ umma_selftest_kernel(const uint4* __restrict__ a_img, int a_bytes, const uint4* 
 // thread 0 issues the MMAs (the fused conv kernel's situation) instead of after them.
 __global__ void __launch_bounds__(256, 1)
 umma_bench_kernel(int N, int a_layout, int b_layout, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int reps, int ld_warps,
-                  int ld_x16, int a_off, int alternate, int concurrent, int st_warps, long long* __restrict__ out) {
+                  int ld_x16, int a_off, int alternate, int concurrent, int st_warps, uint4* __restrict__ gscratch, long long* __restrict__ out) {
     using namespace sm100;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
@@ -137,9 +137,14 @@ umma_bench_kernel(int N, int a_layout, int b_layout, int a_lbo, int a_sbo, int b
         if (acc == 123.456f) out[2] = 1;      // keep the loads alive
     } else if (concurrent && warp >= 5 && warp < 5 + st_warps) {
         // 16-byte stores into a scratch area of shared memory (an im2col build's traffic) until the MMAs are done
-        uint4* dst = reinterpret_cast<uint4*>(smem + 49152) + (tid & 127);
         long long n = 0;
-        for (int k = 0; !done; ++k, ++n) dst[(k & 7) * 128] = make_uint4(k, k, k, k);
+        if (gscratch != nullptr) {                        // ... or coalesced 16-byte stores to HBM (the conv epilogue's traffic: 1 MB per CTA, revisited)
+            uint4* dst = gscratch + (size_t)blockIdx.x * 65536 + (tid & 127);
+            for (int k = 0; !done; ++k, ++n) dst[(size_t)(k & 511) * 128] = make_uint4(k, k, k, k);
+        } else {
+            uint4* dst = reinterpret_cast<uint4*>(smem + 49152) + (tid & 127);
+            for (int k = 0; !done; ++k, ++n) dst[(k & 7) * 128] = make_uint4(k, k, k, k);
+        }
         if ((tid & 31) == 0 && warp == 5 && blockIdx.x == 0) out[5] = n;
     }
     tc_fence_before();
@@ -149,14 +154,17 @@ umma_bench_kernel(int N, int a_layout, int b_layout, int a_lbo, int a_sbo, int b
 
 }  // namespace bcad
 
-extern "C" int bcad_selftest_umma_bench(const int32_t* p /*N,a_layout,b_layout,a_lbo,a_sbo,b_lbo,b_sbo,reps,ld_warps,ld_x16,a_off,alternate,grid,concurrent,st_warps*/,
+extern "C" int bcad_selftest_umma_bench(const int32_t* p /*N,a_layout,b_layout,a_lbo,a_sbo,b_lbo,b_sbo,reps,ld_warps,ld_x16,a_off,alternate,grid,concurrent,st_warps,stores_to_hbm*/,
                                         long long* out_dev, void* stream) {
     using namespace bcad;
     BCAD_REQUIRE(p && out_dev, "selftest bench: null argument");
     BCAD_REQUIRE(p[12] >= 1 && p[12] <= 1024 && p[8] >= 0 && p[8] <= 4 && p[14] >= 0 && p[14] <= 3, "selftest bench: bad grid / warp counts");
     BCAD_CUDA_CHECK(cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     BCAD_CUDA_CHECK(cudaMemsetAsync(out_dev, 0, 6 * sizeof(long long), (cudaStream_t)stream));
-    umma_bench_kernel<<<p[12], 256, 64 * 1024, (cudaStream_t)stream>>>(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8], p[9], p[10], p[11], p[13], p[14], out_dev);
+    static uint4* gscratch = nullptr;                     // 1 MB per CTA for the stores-to-HBM variant (diagnostic tool: kept for the process)
+    if (p[15] && gscratch == nullptr) BCAD_CUDA_CHECK(cudaMalloc((void**)&gscratch, (size_t)1024 * 65536 * sizeof(uint4)));
+    umma_bench_kernel<<<p[12], 256, 64 * 1024, (cudaStream_t)stream>>>(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8], p[9], p[10], p[11], p[13], p[14],
+                                                                        p[15] ? gscratch : nullptr, out_dev);
     BCAD_CUDA_CHECK(cudaGetLastError());
     return BCAD_OK;
 }

@@ -35,10 +35,11 @@ __device__ __forceinline__ void tf_block_minmax(float& vmin, float& vmax, float*
 template <bool X3, int CL, int NT>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1024 / NT)
 tail_fused_kernel(const __half* __restrict__ A, const float* __restrict__ alpha_raw, float scale, float* __restrict__ alpha_out,
-                  float* __restrict__ out, int h, int w, int H, int W, int C) {
+                  float* __restrict__ out, int h, int w, int H, int W, int C, const int* __restrict__ n_dev) {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int b = blockIdx.x / CL;
+    if (n_dev != nullptr && b >= *n_dev) return;          // (every CTA of the image's cluster leaves together)
     constexpr int TF_THREADS = NT;
     extern __shared__ __align__(16) float sm[];
     __shared__ float s_red[64];
@@ -190,15 +191,15 @@ bool tail_fused_supported(int h, int w, int H, int W, int C) {
 }
 
 int launch_tail_fused(const __half* A, const float* alpha_raw, float scale, float* alpha_out, float* out, int B, int h, int w,
-                      int H, int W, int C, bool x3, cudaStream_t s) {
+                      int H, int W, int C, bool x3, cudaStream_t s, const int* n_dev) {
     const size_t smem = tail_fused_smem(h, w, H, W, C);
     BCAD_REQUIRE(tail_fused_supported(h, w, H, W, C), "tail_fused: map %dx%d -> %dx%d does not fit in shared memory", h, w, H, W);
     if (x3) {
         BCAD_CUDA_CHECK(cudaFuncSetAttribute(tail_fused_kernel<true, TF_CL, TF_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tail_fused_kernel<true, TF_CL, TF_NT><<<TF_CL * B, TF_NT, smem, s>>>(A, alpha_raw, scale, alpha_out, out, h, w, H, W, C);
+        tail_fused_kernel<true, TF_CL, TF_NT><<<TF_CL * B, TF_NT, smem, s>>>(A, alpha_raw, scale, alpha_out, out, h, w, H, W, C, n_dev);
     } else {
         BCAD_CUDA_CHECK(cudaFuncSetAttribute(tail_fused_kernel<false, TF_CL, TF_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tail_fused_kernel<false, TF_CL, TF_NT><<<TF_CL * B, TF_NT, smem, s>>>(A, alpha_raw, scale, alpha_out, out, h, w, H, W, C);
+        tail_fused_kernel<false, TF_CL, TF_NT><<<TF_CL * B, TF_NT, smem, s>>>(A, alpha_raw, scale, alpha_out, out, h, w, H, W, C, n_dev);
     }
     BCAD_CUDA_CHECK(cudaGetLastError());
     return BCAD_OK;

@@ -322,7 +322,7 @@ int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const in
         w.alpha = m.cfg.alpha_conv;
         TP_LAUNCH(m, "conv0_wide_tcgen05", launch_conv_wide(w, t.cin_pad, c0.Cout, t.sms, s));
     } else if (t.d_w0_img != nullptr && (t.x3 || getenv("BCAD_CONV0_CUDA_CORES") == nullptr))
-        TP_LAUNCH(m, "conv0_first_tcgen05", launch_conv_first_tc(x, t.plain0 ? t.d_w0_plain : t.d_w0_img, t.p1, n, c0.H, c0.W, m.cfg.pad, c0.Cout, m.cfg.alpha_conv, t.x3, t.plain0, t.sms, s));
+        TP_LAUNCH(m, "conv0_first_tcgen05", launch_conv_first_tc(x, t.plain0 ? t.d_w0_plain : t.d_w0_img, t.p1, n, c0.H, c0.W, m.cfg.pad, c0.Cout, m.cfg.alpha_conv, t.x3, t.plain0, t.sms, s, m.n_dev));
     else
         TP_LAUNCH(m, "conv0_first_pool", launch_conv_first_pool(x, t.d_w0, t.d_b0, t.p1, n, c0.H, c0.W, m.cfg.pad, c0.Cout, m.cfg.alpha_conv, s));
     IgemmArgs a;
@@ -336,6 +336,7 @@ int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const in
     if (a.band_rows > c1.Ho) a.band_rows = cdiv(c1.Ho, 2) * 2;
     a.bands = cdiv(c1.Ho, a.band_rows);
     a.alpha = m.cfg.alpha_conv;
+    a.n_dev = m.n_dev;
     a.debug = 0;
     if (const char* dbg = getenv("BCAD_DEBUG_SKIP_STORES")) {      // timing experiments only (results are garbage)
         a.debug = atoi(dbg);
@@ -349,7 +350,7 @@ int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const in
     FcArgs f;
     f.a_tiles = t.fc_a; f.w_tiles = t.d_fc_w; f.partials = t.fc_part;
     f.N = d0.out; f.nkb = c1.Hp * c1.Wp; f.kb_per_split = t.kb_per_split; f.splits = t.fc_splits;
-    f.m_tiles = cdiv(n, 128); f.m_pad = t.m_pad; f.x3 = t.x3 ? 1 : 0; f.ncb = 1; f.ld_out = 0; f.m_valid = 0;
+    f.m_tiles = cdiv(n, 128); f.m_pad = t.m_pad; f.x3 = t.x3 ? 1 : 0; f.ncb = 1; f.ld_out = 0; f.m_valid = 0; f.n_dev = m.n_dev;
     TP_LAUNCH(m, "fc1_splitk_tcgen05", launch_fc_splitk(f, s));
     if (m.fused_head) {
         // reduce + dense tail + class + (explain) backward to dz1 + alpha shortcut, one launch
@@ -403,12 +404,12 @@ int tensor_explain_chunk(Model& m, int n, const int32_t* class_idx, int grad_mod
         TP_LAUNCH(m, "alpha_shortcut_sgemm", launch_sgemm(dz1, t.d_S, t.alpha_raw, n, T.Cout, m.dense[0].out, false, 1, s));
     }
     const float inv_hw = 1.0f / ((float)T.Ho * (float)T.Wo);
-    if (tail_fused_supported(T.Ho, T.Wo, m.cfg.in_h, m.cfg.in_w, T.Cout) && getenv("BCAD_TAIL_TWO_KERNELS") == nullptr) {
-        TP_LAUNCH(m, "tail_fused", launch_tail_fused(t.act, t.alpha_raw, inv_hw, m.alpha, heat, n, T.Ho, T.Wo, m.cfg.in_h, m.cfg.in_w, T.Cout, t.x3, s));
+    if (tail_fused_supported(T.Ho, T.Wo, m.heat_h, m.heat_w, T.Cout) && getenv("BCAD_TAIL_TWO_KERNELS") == nullptr) {
+        TP_LAUNCH(m, "tail_fused", launch_tail_fused(t.act, t.alpha_raw, inv_hw, m.alpha, heat, n, T.Ho, T.Wo, m.heat_h, m.heat_w, T.Cout, t.x3, s, m.n_dev));
         return BCAD_OK;
     }
     TP_LAUNCH(m, "cam_c8", launch_cam_c8(t.act, t.alpha_raw, inv_hw, m.alpha, m.cam_lo, m.mm, n, T.Ho, T.Wo, T.Cout, m.cam_splits, t.x3, s));
-    TP_LAUNCH(m, "upsample_norm", launch_upsample_norm(m.cam_lo, m.mm, m.cam_splits, heat, n, T.Ho, T.Wo, m.cfg.in_h, m.cfg.in_w, s));
+    TP_LAUNCH(m, "upsample_norm", launch_upsample_norm(m.cam_lo, m.mm, m.cam_splits, heat, n, T.Ho, T.Wo, m.heat_h, m.heat_w, s));
     return BCAD_OK;
 }
 

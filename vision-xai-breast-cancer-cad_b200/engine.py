@@ -120,6 +120,9 @@ class Engine:
         self.refine_margin = float(cfg.refine_margin)
         self._committed = False
         self.tdev = torch.device("cuda", self.device)
+        #: whoever fills the handle's activation cache for later reads (the mirrors' lazy ``layers[*]`` getters, explain_backward)
+        #: stamps it here; every forward of this engine resets it, so a stale read is detectable instead of silently wrong
+        self.cache_tag = None
 
     # ------------------------------------------------------------------ lifetime / weights
     def close(self):
@@ -206,6 +209,7 @@ class Engine:
     # ------------------------------------------------------------------ hot path, device tensors
     def predict(self, x):
         """-> (cls int32 [B], probs fp32 [B,nc], logits fp32 [B,nc]) as CUDA tensors."""
+        self.cache_tag = None
         x = self._as_device_input(x)
         B, nc = x.shape[0], self.spec.num_classes
         with torch.cuda.device(self.tdev):
@@ -215,19 +219,31 @@ class Engine:
             _lib.check(self.lib.bcad_predict(self._h, _ptr(x), B, _ptr(logits), _ptr(probs), _ptr(cls), self._stream()))
         return cls, probs, logits
 
-    def predict_explain(self, x, class_idx=None, grad_mode: str = "logit", out_heat: Optional[torch.Tensor] = None):
-        """-> (cls, probs, logits, heatmaps fp32 [B,H,W]) as CUDA tensors."""
+    def predict_explain(self, x, class_idx=None, grad_mode: str = "logit", out_heat: Optional[torch.Tensor] = None,
+                        out_hw: Optional[Tuple[int, int]] = None):
+        """-> (cls, probs, logits, heatmaps fp32 [B,H,W]) as CUDA tensors.  ``out_hw``: heat-maps resized to that size instead
+        of the model's input size (pytorch_grad_cam scales the cam to the image it explains: GRADCAM.py:46-64 with a 512x512
+        image, app.py:649-657)."""
+        self.cache_tag = None
         x = self._as_device_input(x)
         B, nc = x.shape[0], self.spec.num_classes
         h, w, _ = self.spec.input_shape
+        if out_hw is not None:
+            h, w = int(out_hw[0]), int(out_hw[1])
         with torch.cuda.device(self.tdev):
             logits = torch.empty((B, nc), device=self.tdev, dtype=torch.float32)
             probs = torch.empty((B, nc), device=self.tdev, dtype=torch.float32)
             cls = torch.empty((B,), device=self.tdev, dtype=torch.int32)
             heat = out_heat if out_heat is not None else torch.empty((B, h, w), device=self.tdev, dtype=torch.float32)
+            if tuple(heat.shape) != (B, h, w) or heat.dtype != torch.float32 or not heat.is_contiguous():
+                raise ValueError(f"out_heat must be a contiguous float32 [{B},{h},{w}] tensor")
             ci = self._class_idx(class_idx, B)
-            _lib.check(self.lib.bcad_predict_explain(self._h, _ptr(x), B, _ptr(ci), _lib.GRAD_MODE[grad_mode],
-                                                     _ptr(logits), _ptr(probs), _ptr(cls), _ptr(heat), self._stream()))
+            if out_hw is None:
+                _lib.check(self.lib.bcad_predict_explain(self._h, _ptr(x), B, _ptr(ci), _lib.GRAD_MODE[grad_mode],
+                                                         _ptr(logits), _ptr(probs), _ptr(cls), _ptr(heat), self._stream()))
+            else:
+                _lib.check(self.lib.bcad_predict_explain_sized(self._h, _ptr(x), B, _ptr(ci), _lib.GRAD_MODE[grad_mode],
+                                                               _ptr(logits), _ptr(probs), _ptr(cls), h, w, _ptr(heat), self._stream()))
         return cls, probs, logits, heat
 
     def _class_idx(self, class_idx, B):
@@ -365,6 +381,7 @@ class Engine:
         -> (cls int32 [B], probs [B,nc], logits [B,nc], heat [B,H,W]) as host arrays.
         heat_dtype=np.uint8 returns ``heatmap_uint8 = (cam * 255).astype(uint8)`` (GRADCAM.py:70) instead of the float32 map:
         a quarter of the device->host bytes of a PCIe-bound call."""
+        self.cache_tag = None
         u8 = np.dtype(heat_dtype) == np.uint8
         h, w, c = self.spec.input_shape
         x8 = x.dtype == np.uint8
@@ -388,6 +405,8 @@ class Engine:
         ci = None
         if class_idx is not None:
             ci = np.ascontiguousarray(np.broadcast_to(np.asarray(class_idx, dtype=np.int32).reshape(-1), (B,)))
+            if ci.min() < 0 or ci.max() >= nc:
+                raise ValueError("class_idx out of range")
         if x8:
             hf, h8 = (None, heat) if u8 else (heat, None)
             _lib.check(self.lib.bcad_predict_explain_host_u8in(self._h, _ptr(x), B, _ptr(ci), _lib.GRAD_MODE[grad_mode], _ptr(logits),
@@ -396,6 +415,45 @@ class Engine:
         fn = self.lib.bcad_predict_explain_host_u8 if (u8 and want_heat) else self.lib.bcad_predict_explain_host
         _lib.check(fn(self._h, _ptr(x), B, _ptr(ci), _lib.GRAD_MODE[grad_mode], _ptr(logits), _ptr(probs), _ptr(cls), _ptr(heat)))
         return cls, probs, logits, heat
+
+
+def _gradcam_overlays_host(self, gray_u8: np.ndarray, class_idx=None, grad_mode: str = "logit", standardise: bool = True,
+                           overlay_out: Optional[np.ndarray] = None, heat_out: Optional[np.ndarray] = None,
+                           want_overlay: bool = True, want_heat: bool = True):
+    """The GRADCAM.py call surface for a batch, end to end through one C-ABI call (bcad_gradcam_overlays_host): uint8 grey
+    images [B,H,W] (model input size) -> (cls int32 [B], probs [B,nc], logits [B,nc], overlay uint8 RGB [B,H,W,3] =
+    show_cam_on_image, heatmap_uint8 [B,H,W]).  ``standardise``: the CNN input is the per-image standardised img/255 (the
+    reference's CNN-input normalisation, app.py:179-182), else img/255 itself.  Pinned host arrays make the copies asynchronous."""
+    self.cache_tag = None
+    h, w, c = self.spec.input_shape
+    g = np.ascontiguousarray(gray_u8)
+    if g.dtype != np.uint8:
+        raise ValueError("gray_u8 must be uint8 (0-255 grey levels)")
+    if g.ndim == 2:
+        g = g[None]
+    if g.shape[1:] != (h, w):
+        raise ValueError(f"image shape {g.shape} does not match [B,{h},{w}]")
+    B, nc = g.shape[0], self.spec.num_classes
+    logits, probs, cls = np.empty((B, nc), np.float32), np.empty((B, nc), np.float32), np.empty((B,), np.int32)
+    ov = hu = None
+    if want_overlay:
+        ov = overlay_out if overlay_out is not None else np.empty((B, h, w, 3), np.uint8)
+    if want_heat:
+        hu = heat_out if heat_out is not None else np.empty((B, h, w), np.uint8)
+    for a, shp in ((ov, (B, h, w, 3)), (hu, (B, h, w))):
+        if a is not None and (a.dtype != np.uint8 or a.shape != shp or not a.flags["C_CONTIGUOUS"]):
+            raise ValueError("output arrays must be C-contiguous uint8 of the documented shape")
+    ci = None
+    if class_idx is not None:
+        ci = np.ascontiguousarray(np.broadcast_to(np.asarray(class_idx, dtype=np.int32).reshape(-1), (B,)))
+        if ci.min() < 0 or ci.max() >= nc:
+            raise ValueError("class_idx out of range")
+    _lib.check(self.lib.bcad_gradcam_overlays_host(self._h, _ptr(g), B, _ptr(ci), _lib.GRAD_MODE[grad_mode], 1 if standardise else 0,
+                                                   _ptr(logits), _ptr(probs), _ptr(cls), _ptr(ov), _ptr(hu)))
+    return cls, probs, logits, ov, hu
+
+
+Engine.gradcam_overlays_host = _gradcam_overlays_host
 
 
 def gradcam_tail(A: torch.Tensor, dA: torch.Tensor, out_hw: Tuple[int, int]) -> torch.Tensor:

@@ -2,9 +2,11 @@
 
 ``compute_backprops_for_explainability(model, y_true)`` returns ``(grads, d_input, conv_act_grads)`` like
 the reference (explainability.py:13-68); the activation-gradient chain (dense W^T dz with the LeakyReLU'
-mask, tie-duplicating un-pool, conv input gradients) runs in libbcad.  ``grads`` (the WEIGHT gradients
-dW/db/dF) are training quantities that nothing on the explain path reads (explainability.py:94 drops
-them): the list is returned with ``None`` entries -- weight gradients are SURVEY 8 row f4.
+mask, tie-duplicating un-pool, conv input gradients) runs in libbcad.  ``grads`` holds the weight gradients of
+the same backward pass -- ``{'dW','db'}`` per dense / output layer (explainability.py:25,33), ``{'dF','db_conv'}``
+per conv layer (:63), ``None`` for pool layers (:42) -- from ``bcad_train_backward`` (the cross-entropy gradient of one
+sample with label c IS the reference's ``probs - y_true`` backward); ``want_weight_grads=False`` skips them, as
+``generate_dual_class_overlays`` does (explainability.py:94 drops them).
 """
 from __future__ import annotations
 
@@ -23,15 +25,30 @@ def _class_of(y_true, num_classes):
     return int(np.argmax(y))
 
 
-def compute_backprops_for_explainability(model, y_true):
-    """Assumes ``model.forward(x, training=False)`` was just called (as the reference does)."""
-    eng = model.engine
+def compute_backprops_for_explainability(model, y_true, want_weight_grads=True):
+    """Differentiates the model's latest ``forward(x, ...)`` (the reference reads that forward's caches out of ``model.layers``);
+    if something else has used the handle since, the forward is repeated first (never a silently different image)."""
+    eng = model._cache_ready()
     c = _class_of(y_true, model.num_classes)
     conv_idx = [i for i, l in enumerate(model.layers) if l["type"] == "conv"]
     outs, d_in = eng.explain_backward(1, c, "softmax_ce", want_conv=range(len(conv_idx)), want_input=True)
     conv_act_grads = {li: outs[bi][0].double().cpu().numpy() for bi, li in enumerate(conv_idx)}
     d_input = d_in[0].double().cpu().numpy()
     grads = [None] * len(model.layers)
+    if want_weight_grads:
+        if model._last_masks is not None:
+            eng.set_dropout_masks(model._last_masks, mask_backward=False)
+        try:
+            flat, _ = eng.train_backward(model._last_x[None], [c])
+        finally:
+            if model._last_masks is not None:
+                eng.set_dropout_masks(None)
+        g = eng.unpack_grads(flat)
+        dense_idx = [i for i, l in enumerate(model.layers) if l["type"] in ("dense", "output")]
+        for bi, li in enumerate(conv_idx):
+            grads[li] = {"dF": g["conv_w"][bi].astype(np.float64), "db_conv": g["conv_b"][bi].astype(np.float64)}
+        for di, li in enumerate(dense_idx):
+            grads[li] = {"dW": g["dense_w"][di].astype(np.float64), "db": g["dense_b"][di].astype(np.float64)}
     return grads, d_input, conv_act_grads
 
 
@@ -61,7 +78,7 @@ def generate_dual_class_overlays(model, img, classes_to_test=[0, 1], save_folder
     for class_idx in classes_to_test:
         y_true = np.zeros(model.layers[-1]["biases"].shape, dtype=np.float32)
         y_true[class_idx] = 1.0
-        grads, d_input, conv_act_grads = compute_backprops_for_explainability(model, y_true)
+        grads, d_input, conv_act_grads = compute_backprops_for_explainability(model, y_true, want_weight_grads=False)
         vis = img if img.shape[-1] == 3 else np.repeat(img[..., :1], 3, axis=-1)
         overlay, heatmap = generate_saliency_overlay(vis, d_input)
         cv2.imwrite(os.path.join(save_folder, f"overlay_class_{class_idx}.png"), overlay)
