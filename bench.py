@@ -440,7 +440,74 @@ def run_ours(args, rank, world, local_rank):
         r["ms_total"], r["e2e_ms"], r["e2e_u8_ms"], r["e2e_u8io_ms"] = (float(v) for v in tt)
         return r
 
+    def host_copy_probe(iters=8):
+        """The ceiling of the e2e leg on this box: every rank moves the step's bytes (pinned H2D of the input batch and pinned D2H
+        of the heat-maps, two streams, both directions at once) with NO compute in between -> aggregate GB/s over all ranks."""
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        def once():
+            with torch.cuda.stream(s_in):
+                x_dev.copy_(x_host, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                heat_host.copy_(heat_dev, non_blocking=True)
+        once()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            once()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        nbytes = (x_host.numel() + heat_host.numel()) * 4 * iters * world
+        return nbytes / float(tt[0]) / 1e9, float(tt[0]) / iters * 1e3
+
+    def measure_api():
+        """End to end through the reference-shaped Python surface: GRADCAM.generate_gradcam_overlays_batch on a drop-in
+        ADCNNM.CNNModel with DEFAULT settings (precision auto): uint8 grey images in pinned host memory in, uint8 RGB overlays
+        (show_cam_on_image) + heatmap_uint8 out (GRADCAM.py:31-81), everything in between on the device."""
+        from bcad_b200 import ADCNNM as A, GRADCAM as G
+        model = A.CNNModel(INPUT_SHAPE, NUM_CLASSES, conv_layers=CONV_LAYERS, hidden_units=HIDDEN, max_batch=MB, device_index=local_rank).eval()
+        sd = {}
+        for i, (w, b) in enumerate(zip(conv_w, conv_b)):
+            sd[f"convs.{i}.weight"] = torch.tensor(np.ascontiguousarray(w.transpose(0, 3, 1, 2)), dtype=torch.float32)
+            sd[f"convs.{i}.bias"] = torch.tensor(b, dtype=torch.float32)
+        for j, (w, b) in enumerate(zip(dense_w, dense_b)):
+            sd[f"fc.{3 * j}.weight"] = torch.tensor(w, dtype=torch.float32)
+            sd[f"fc.{3 * j}.bias"] = torch.tensor(b, dtype=torch.float32)
+        model.load_state_dict(sd)
+        g8 = x8_host.numpy().reshape(B, INPUT_SHAPE[0], INPUT_SHAPE[1])
+        ov_host = torch.empty((B, INPUT_SHAPE[0], INPUT_SHAPE[1], 3), dtype=torch.uint8).pin_memory()
+        def step():
+            return G.generate_gradcam_overlays_batch(g8, None, model=model, overlay_out=ov_host.numpy(), heat_out=heat8_host.numpy())
+        for _ in range(3):
+            step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        prec = model.engine.precision
+        model.engine.close()
+        return {"value": world * B * args.steps / float(tt[0]), "unit": UNIT, "ms_per_step": float(tt[0]) / args.steps * 1e3,
+                "h2d_bytes_per_step": int(g8.size), "d2h_bytes_per_step": int(ov_host.numel() + heat8_host.numel() + B * (2 * NUM_CLASSES * 4 + 4)),
+                "precision_path": prec,
+                "api": "GRADCAM.generate_gradcam_overlays_batch(uint8 [B,H,W], model=ADCNNM.CNNModel(...)) with the mirror's DEFAULT precision: "
+                       "uint8 grey images in -> uint8 RGB show_cam_on_image overlays + heatmap_uint8 out (GRADCAM.py:31-81), one "
+                       "bcad_gradcam_overlays_host call per step"}
+
     main = measure(eng)
+    ceiling_gbs, ceiling_ms = host_copy_probe()
+    api = None
+    if FLAVOUR == "torch" and INPUT_SHAPE[2] == 1 and not args.no_api:
+        try:
+            api = measure_api()
+        except Exception as e:                                      # the API leg must not take the headline down with it
+            log(f"[bench] e2e_api leg failed: {e!r}")
     # ---- the same workload at fp32 grade (hi+lo split operands, 3 MMAs per product): the mode the drop-in mirrors default to
     eng3, grade = None, None
     if precision == "fp16" and not args.no_fp32_grade:
@@ -587,7 +654,12 @@ def run_ours(args, rank, world, local_rank):
         "config": workload_config(B, precision, args.total_batch, eng.refine_margin),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
                 "d2h_bytes_per_step": int(heat_host.numel() * 4 + B * (2 * NUM_CLASSES * 4 + 4)),
-                "ms_per_step": e2e_ms / args.steps, "api": "bcad_predict_explain_host (pinned host buffers)"},
+                "ms_per_step": e2e_ms / args.steps, "api": "bcad_predict_explain_host (pinned host buffers)",
+                "host_ceiling_gbs": ceiling_gbs, "host_ceiling_ms_per_step": ceiling_ms,
+                "achieved_gbs": world * (x_host.numel() + heat_host.numel()) * 4 / (e2e_ms / args.steps * 1e-3) / 1e9,
+                "host_ceiling_note": "all ranks copying the step's bytes both ways at once with no compute (same pinned buffers): what the "
+                                     "host side of this box can move; the e2e leg is bound by it when achieved_gbs is close"},
+        "e2e_api": api,
         "e2e_u8_heatmaps": {"value": world * B * args.steps / (e2e_u8_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_u8_ms / args.steps,
                             "d2h_bytes_per_step": int(heat8_host.numel() + B * (2 * NUM_CLASSES * 4 + 4)),
                             "api": "bcad_predict_explain_host_u8: same call, heat-maps as heatmap_uint8 (GRADCAM.py:70) -- informational, "
@@ -622,6 +694,41 @@ def run_ours(args, rank, world, local_rank):
             "roofline": roofline_of(grade["prof"], {}, "fp16x3"), "roofline_tail": tail_roofline(grade["prof"], "fp16x3"),
             "kernels": kernel_table(grade["prof"]), "check": check3}
     emit(out_json)
+
+
+def run_sharded(args):
+    """Secondary line: the in-process batch-sharded driver (bcad_b200.ShardedEngine: one handle + one host thread per GPU, no
+    torchrun, no collective) -- end-to-end images/s from ONE pinned host batch to pinned host heat-maps over --gpus GPUs."""
+    import torch
+    import bcad_b200
+    n = min(args.gpus, torch.cuda.device_count())
+    B = args.total_batch if args.total_batch else args.batch * n
+    spec = bcad_b200.NetSpec.torch_flavour(INPUT_SHAPE, NUM_CLASSES, CONV_LAYERS, HIDDEN, 0.01)
+    prec = "fp16" if args.precision == "auto" else args.precision
+    sh = bcad_b200.ShardedEngine(spec, list(range(n)), precision=prec, max_batch=min(512, max(1, B // n)))
+    sh.set_weights(*synth_weights())
+    out = {}
+    for name, dt in (("float32", np.float32), ("uint8", np.uint8)):
+        if dt == np.uint8:
+            x = torch.from_numpy(np.clip(np.rint(synth_images(B, INPUT_SHAPE, seed=5) * 255.0), 0, 255).astype(np.uint8)).pin_memory().numpy()
+        else:
+            x = torch.from_numpy(synth_images(B, INPUT_SHAPE, seed=5)).pin_memory().numpy()
+        for _ in range(3):
+            sh.predict_explain_host(x, None, "logit", heat_dtype=dt)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            sh.predict_explain_host(x, None, "logit", heat_dtype=dt)
+        dt_s = time.perf_counter() - t0
+        out[name] = {"value": B * args.steps / dt_s, "unit": UNIT, "ms_per_step": dt_s / args.steps * 1e3}
+    emit({"metric": METRIC + " (in-process ShardedEngine, end to end)", "value": out["float32"]["value"], "unit": UNIT, "n_gpus": n,
+          "steps": args.steps, "warmup": 3, "ms_per_step": out["float32"]["ms_per_step"], "higher_is_better": True,
+          "scaling": "strong" if args.total_batch else "weak", "vs_baseline": None, "dtype": "f16" if prec == "fp16" else prec, "data": "synthetic",
+          "config": {"workload": f"ShardedEngine.predict_explain_host: {B} images per step split over {n} GPUs by one process "
+                                 f"(one handle + one host thread per GPU), pinned host buffers both ways", "images_per_step": B},
+          "e2e": dict(out["float32"], h2d_bytes_per_step=B * INPUT_SHAPE[0] * INPUT_SHAPE[1] * INPUT_SHAPE[2] * 4,
+                      d2h_bytes_per_step=B * INPUT_SHAPE[0] * INPUT_SHAPE[1] * 4),
+          "e2e_u8_in_out": out["uint8"]})
+    sh.close()
 
 
 def run_train(args, rank, world, local_rank):
@@ -747,7 +854,7 @@ def main():
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "fp16", "fp16x3"])
     ap.add_argument("--cpu-images", type=int, default=1024, help="bounded CPU-baseline sample (~10 s of CPU work on 16 cores)")
     ap.add_argument("--ref-images", type=int, default=64, help="images per step of the --impl reference arm")
-    ap.add_argument("--workload", default="explain", choices=["explain", "train"],
+    ap.add_argument("--workload", default="explain", choices=["explain", "train", "sharded"],
                     help="explain = the headline path (predict + Grad-CAM); train = the secondary training-step line")
     ap.add_argument("--train-batch", type=int, default=64, help="images per GPU per training step")
     ap.add_argument("--flavour", default="torch", choices=["torch", "numpy"],
@@ -758,6 +865,7 @@ def main():
                                                                "split evenly; 0 = weak scaling with --batch images per GPU")
     ap.add_argument("--preheat", type=float, default=2.0, help="seconds of untimed full-duty steps before each timed region")
     ap.add_argument("--check-images", type=int, default=256, help="images of the batch compared one by one with the oracle (untimed)")
+    ap.add_argument("--no-api", action="store_true", help="skip the e2e_api leg (the mirrors' Python surface)")
     ap.add_argument("--no-fp32-grade", action="store_true", help="skip the second measurement of the workload in fp16x3 mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the (untimed) oracle check of the first images")
@@ -774,6 +882,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "sharded":
+        if rank == 0:
+            run_sharded(args)
         return
     if world > 1:
         import torch.distributed as dist

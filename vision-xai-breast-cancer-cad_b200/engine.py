@@ -502,32 +502,45 @@ def shard_bounds(n: int, world: int) -> List[Tuple[int, int]]:
 
 
 class ShardedEngine:
-    """Single-process driver over several GPUs of one box: one Engine + one host thread per GPU."""
+    """Single-process driver over several GPUs of one box (north_star (d)): one Engine + one host thread per GPU, contiguous
+    batch split, replicated weights, NO collective.  Results land in PINNED host arrays owned by the driver (reused from call to
+    call while the batch size stays the same), so every shard's device->host copies are asynchronous and overlap the other
+    shards' work; pass a pinned ``x`` (``torch.Tensor.pin_memory().numpy()``) for the same on the way in."""
 
     def __init__(self, spec: NetSpec, devices: Sequence[int], **kw):
         self.engines = [Engine(spec, device=d, **kw) for d in devices]
         self.spec = spec
+        self._out = None
 
     def set_weights(self, *a, **k):
         for e in self.engines:
             e.set_weights(*a, **k)
 
-    def predict_explain_host(self, x: np.ndarray, class_idx=None, grad_mode="logit"):
-        B = x.shape[0]
+    def _outputs(self, B, heat_dtype):
         h, w, _ = self.spec.input_shape
         nc = self.spec.num_classes
-        cls = np.empty((B,), np.int32)
-        probs = np.empty((B, nc), np.float32)
-        logits = np.empty((B, nc), np.float32)
-        heat = np.empty((B, h, w), np.float32)
+        key = (B, np.dtype(heat_dtype).str)
+        if self._out is None or self._out[0] != key:
+            tdt = torch.uint8 if np.dtype(heat_dtype) == np.uint8 else torch.float32
+            bufs = (torch.empty((B,), dtype=torch.int32).pin_memory(), torch.empty((B, nc), dtype=torch.float32).pin_memory(),
+                    torch.empty((B, nc), dtype=torch.float32).pin_memory(), torch.empty((B, h, w), dtype=tdt).pin_memory())
+            self._out = (key, bufs)
+        return tuple(t.numpy() for t in self._out[1])
+
+    def predict_explain_host(self, x: np.ndarray, class_idx=None, grad_mode="logit", heat_dtype=np.float32):
+        """-> (cls, probs, logits, heat) host arrays over the whole batch.  The arrays are the driver's pinned buffers: they are
+        overwritten by the next call with the same batch size (copy what must outlive it)."""
+        B = x.shape[0]
+        cls, probs, logits, heat = self._outputs(B, heat_dtype)
         errs = []
+        ci_all = None if class_idx is None else np.ascontiguousarray(np.broadcast_to(np.asarray(class_idx, np.int32).reshape(-1), (B,)))
 
         def work(e, s, t):
             try:
                 if t <= s:
                     return
-                ci = None if class_idx is None else np.broadcast_to(np.asarray(class_idx, np.int32).reshape(-1), (B,))[s:t]
-                c, p, l, hm = e.predict_explain_host(x[s:t], ci, grad_mode, heat_out=heat[s:t])
+                c, p, l, hm = e.predict_explain_host(x[s:t], None if ci_all is None else ci_all[s:t], grad_mode, heat_out=heat[s:t],
+                                                     heat_dtype=heat_dtype)
                 cls[s:t], probs[s:t], logits[s:t] = c, p, l
             except Exception as ex:  # surfaced after join
                 errs.append(ex)
