@@ -305,7 +305,7 @@ def run_ours(args, rank, world, local_rank):
     if precision in ("auto", "fp16", "fp16x3"):
         want = ("fp16x3" if FLAVOUR == "numpy" else "fp16") if precision == "auto" else precision
         try:
-            eng = bcad_b200.Engine(spec, precision=want, max_batch=MB, device=local_rank)
+            eng = bcad_b200.Engine(spec, precision=want, max_batch=MB, device=local_rank, refine_margin=args.refine_margin)
             precision = want
         except ValueError as e:
             if args.precision != "auto":
@@ -731,6 +731,198 @@ def run_sharded(args):
     sh.close()
 
 
+def run_pipeline(args, rank, world, local_rank):
+    """Secondary line, BASELINE config 3: FULL pipeline at batch 256 per GPU -- 8-bit grey image -> per-image standardisation ->
+    tiny U-Net encoder (Classes/unet.py:61-73: the "ROI" front) -> average_pool(3) (Classes/ImageSegmentation.py:182) -> CNN classify on
+    the (22,22,64) features -> Grad-CAM (last conv block) scaled to the 256x256 image (GRADCAM.py:46-64) -> show_cam_on_image
+    overlay + heatmap_uint8 (GRADCAM.py:67,70).  U-Net conv2/conv3 and the CNN's convs / fc1 on tcgen05 (fp16 operands)."""
+    import torch
+    import torch.distributed as dist
+    import bcad_b200
+    from bcad_b200 import unet as U
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B = args.batch if args.batch != 512 else 256
+    H, W = INPUT_SHAPE[0], INPUT_SHAPE[1]
+    rng = np.random.default_rng(11)
+    # the reference draws randn(std 1) kernels inside tiny_unet_numpy; scaled here so the features stay O(1) for the random-init CNN
+    ks = [rng.standard_normal(shp) * sc for shp, sc in (((3, 3, 1, 16), 0.3), ((3, 3, 16, 32), 0.08), ((3, 3, 32, 64), 0.06))]
+    front = U.UnetFront(H, W, ks, max_batch=B, device=local_rank)
+    fh, fw, fc = front.out_shape(3)
+    cnn_shape = (fh, fw, fc)
+    spec = bcad_b200.NetSpec.torch_flavour(cnn_shape, NUM_CLASSES, CONV_LAYERS, HIDDEN, 0.01)
+    eng = bcad_b200.Engine(spec, precision="fp16" if args.precision == "auto" else args.precision, max_batch=B, device=local_rank)
+    cw, cb, dw, db = synth_weights_for(cnn_shape)
+    eng.set_weights(cw, cb, dw, db)
+    g8_host = torch.from_numpy(np.clip(synth_images(B, (H, W, 1), seed=31 + rank)[..., 0] * 48 + 128, 0, 255).astype(np.uint8)).pin_memory()
+    ov_host = torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory()
+    hu_host = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
+    g8_dev = g8_host.to(dev)
+    heat = torch.empty((B, H, W), device=dev, dtype=torch.float32)
+    feat = torch.empty((B, fh, fw, fc), device=dev, dtype=torch.float32)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_dev(g8):
+        img01, x = bcad_b200.gray_preprocess(g8, 1, True)
+        front.forward(x, 3, out=feat)
+        cls, probs, logits, _ = eng.predict_explain(feat, None, "logit", out_heat=heat, out_hw=(H, W))
+        ov, hu = bcad_b200.overlay(img01, heat)
+        return cls, logits, ov, hu
+
+    def step_e2e():
+        cls, logits, ov, hu = step_dev(g8_host.to(dev, non_blocking=True))
+        ov_host.copy_(ov, non_blocking=True)
+        hu_host.copy_(hu, non_blocking=True)
+        return cls.cpu()
+
+    for _ in range(max(3, args.warmup)):
+        step_dev(g8_dev)
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < args.preheat:
+        for _ in range(10):
+            step_dev(g8_dev)
+        torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count + front.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step_dev(g8_dev)
+    ev1.record()
+    barrier()
+    launches = eng.launch_count + front.launch_count - l0 + 2 * args.steps          # + gray_preprocess and overlay per step
+    ms_total = ev0.elapsed_time(ev1)
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize(dev)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    tt = torch.tensor([ms_total, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(tt[0]), float(tt[1])
+    # per-kernel times under load: the two handles' own marks, torch events around the two stand-alone stages
+    front.set_profiling(True)
+    eng.set_profiling(True)
+    prof = {}
+    nprof = 3
+    for _ in range(nprof):
+        for _ in range(5):
+            step_dev(g8_dev)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e[0].record()
+        img01, x = bcad_b200.gray_preprocess(g8_dev, 1, True)
+        e[1].record()
+        front.forward(x, 3, out=feat)
+        eng.predict_explain(feat, None, "logit", out_heat=heat, out_hw=(H, W))
+        e[2].record()
+        bcad_b200.overlay(img01, heat)
+        e[3].record()
+        torch.cuda.synchronize(dev)
+        items = [("gray_preprocess", e[0].elapsed_time(e[1]))] + front.last_profile() + [("cnn_" + n, ms) for n, ms in eng.last_profile()] + \
+                [("overlay", e[2].elapsed_time(e[3]))]
+        for i, (name, ms) in enumerate(items):
+            key = f"{i:02d}:{name}"
+            prof[key] = prof.get(key, 0.0) + ms / nprof
+    front.set_profiling(False)
+    eng.set_profiling(False)
+    if rank != 0:
+        return
+    pk = peaks()
+    # algorithmic work of the front per image (true conv areas; quirk rows are zeros, not work)
+    H1, W1, H2, W2 = H // 2, W // 2, H // 4 + 1, W // 4 + 1
+    flops = {"unet_conv2_igemm_tcgen05": 2.0 * H1 * W1 * 32 * 9 * 16, "unet_conv3_igemm_tcgen05": 2.0 * H2 * W2 * 64 * 9 * 32,
+             "cnn_conv0_wide_tcgen05": 2.0 * fh * fw * 32 * 9 * fc, "cnn_conv1_igemm_tcgen05": 2.0 * (fh // 2) * (fw // 2) * 64 * 9 * 32}
+    nbytes = {"gray_preprocess": H * W * (1 + 4 + 4.0), "unet_conv1_first_pool": H * W * 4 + H1 * W1 * 16 * 2.0,
+              "unet_out_avgpool": H2 * W2 * 64 * 2 + fh * fw * fc * 4.0, "overlay": H * W * (4 + 4 + 3 + 1.0),
+              "cnn_upsample_norm": (fh // 2) * (fw // 2) * 4 + H * W * 4.0, "cnn_tail_fused": (fh // 2) * (fw // 2) * 64 * 2 + H * W * 4.0}
+    dom_key = max(prof, key=prof.get)
+    dom = dom_key.split(":", 1)[1]
+    dom_ms = prof[dom_key]
+    if dom in flops:
+        ach = flops[dom] * B / (dom_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": dom, "ms": dom_ms, "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": ach / pk["bf16_tflops_sustained"], "frac_burst": ach / pk["bf16_tflops"], "traffic": None,
+                "algorithmic_flops_per_launch": flops[dom] * B, "peak_source": pk["source"]}
+    else:
+        nb = nbytes.get(dom, 0.0) * B
+        ach = nb / (dom_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "ms": dom_ms, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                "traffic": None, "algorithmic_bytes_per_launch": nb, "peak_source": pk["source"]}
+    tot = max(1e-9, sum(prof.values()))
+    kernels = [{"kernel": k, "ms": round(v, 4), "share": round(v / tot, 4)} for k, v in sorted(prof.items())]
+    for kr in kernels:
+        n = kr["kernel"].split(":", 1)[1]
+        if n in flops:
+            kr["tflops"] = round(flops[n] * B / (kr["ms"] * 1e-3) / 1e12, 1)
+        elif n in nbytes:
+            kr["GBps"] = round(nbytes[n] * B / (kr["ms"] * 1e-3) / 1e9, 1)
+    # untimed check of the first images against the float64 oracle of the whole pipeline
+    check = None
+    if not args.no_check:
+        from oracle import cnn as ocnn, gradcam as ogc, unet as ou
+        k = min(B, 16)
+        g8 = g8_host[:k].numpy()
+        img01 = (g8 / 255.0).astype(np.float32)
+        xs = np.stack([((im - im.mean()) / (im.std() + 1e-8)).astype(np.float32) for im in img01])[..., None]
+        f64 = ou.average_pool(ou.tiny_unet(xs.astype(np.float64), ks), 3)
+        cfg = ocnn.NetConfig.torch_flavour(cnn_shape, NUM_CLASSES, CONV_LAYERS, HIDDEN, 0.01)
+        params = ocnn.Params(cw, cb, dw, db)
+        cache = ocnn.forward(cfg, params, f64)
+        o_cls = cache.logits.argmax(dim=-1).numpy()
+        cag, _, _ = ocnn.backward(cfg, params, cache, ocnn.top_gradient(cache, o_cls, "logit"), through_input=False)
+        o_heat = ogc.gradcam_tail_nhwc(cache.conv_out[-1].numpy().astype(np.float32), cag[1].numpy().astype(np.float32), (H, W))
+        cls, logits, ov, hu = out
+        d_feat = feat[:k].cpu().numpy()
+        lg = cache.logits.numpy()
+        want_hu = np.stack([ogc.heatmap_u8(o_heat[i]) for i in range(k)]).astype(np.int32)
+        want_ov = np.stack([ogc.show_cam_on_image(np.stack([img01[i]] * 3, -1), o_heat[i]) for i in range(k)]).astype(np.int32)
+        margin = np.abs(lg[:, 0] - lg[:, 1])
+        check = {"images": k, "vs": "float64 oracle of the whole pipeline (oracle/unet.py + oracle/cnn.py + oracle/gradcam.py)",
+                 "feature_rel_err": float(np.abs(d_feat - f64).max() / max(1.0, np.abs(f64).max())),
+                 "class_mismatches": int((cls[:k].cpu().numpy() != o_cls).sum()), "smallest_logit_margin": float(margin.min()),
+                 "max_logit_err": float(np.abs(logits[:k].cpu().numpy() - lg).max()), "logit_scale": float(np.abs(lg).max()),
+                 "heatmap_u8_max_abs_diff": int(np.abs(hu[:k].cpu().numpy().astype(np.int32) - want_hu).max()),
+                 "overlay_u8_frac_pixels_off_by_more_than_1": float((np.abs(ov[:k].cpu().numpy().astype(np.int32) - want_ov) > 1).mean())}
+    emit({"metric": "full pipeline (U-Net front -> CNN classify -> Grad-CAM overlay) images/sec at 256x256", "value": world * B * args.steps / (ms_total * 1e-3),
+          "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps,
+          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+          "config": {"workload": f"cfg3: uint8 grey {H}x{W} images -> standardise -> tiny U-Net encoder (1->16->32->64, ReLU, pools; conv2d 'same' "
+                                 f"quirk kept) -> average_pool(3) -> ADCNNM-flavour CNN on ({fh},{fw},{fc}) (conv 32,64 k3 pad1; fc 256,128; random "
+                                 f"init) -> Grad-CAM(last conv, predicted class) scaled to {H}x{W} -> JET overlay + heatmap_uint8; batch {B} per GPU",
+                     "batch_per_gpu": B, "l2_policy": "image batch + intermediate maps per step (> 300 MB) exceed the 126 MB L2"},
+          "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                  "h2d_bytes_per_step": int(g8_host.numel()), "d2h_bytes_per_step": int(ov_host.numel() + hu_host.numel() + B * 4),
+                  "api": "uint8 images in pinned host memory -> bcad_gray_preprocess, bcad_unet_forward, bcad_predict_explain_sized, bcad_overlay -> "
+                         "uint8 overlays + heat-maps in pinned host memory + classes"},
+          "gpu_launches": int(launches), "clocks": clocks, "preheat": {"seconds": args.preheat}, "roofline": roof, "kernels": kernels, "check": check})
+    front.close()
+    eng.close()
+
+
+def synth_weights_for(shape):
+    """synth_weights() for another input shape (the pipeline's CNN sees the U-Net features)."""
+    global INPUT_SHAPE
+    keep = INPUT_SHAPE
+    INPUT_SHAPE = tuple(shape)
+    try:
+        return synth_weights()
+    finally:
+        INPUT_SHAPE = keep
+
+
 def run_train(args, rank, world, local_rank):
     """Secondary line (SURVEY 8 row f4 / BASELINE config 5): data-parallel training step, images/s.  fp32 forward +
     backward + weight gradients in libbcad, ONE bucketed NCCL all-reduce of the flat gradient, Adam on the device."""
@@ -854,7 +1046,7 @@ def main():
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "fp16", "fp16x3"])
     ap.add_argument("--cpu-images", type=int, default=1024, help="bounded CPU-baseline sample (~10 s of CPU work on 16 cores)")
     ap.add_argument("--ref-images", type=int, default=64, help="images per step of the --impl reference arm")
-    ap.add_argument("--workload", default="explain", choices=["explain", "train", "sharded"],
+    ap.add_argument("--workload", default="explain", choices=["explain", "train", "sharded", "pipeline"],
                     help="explain = the headline path (predict + Grad-CAM); train = the secondary training-step line")
     ap.add_argument("--train-batch", type=int, default=64, help="images per GPU per training step")
     ap.add_argument("--flavour", default="torch", choices=["torch", "numpy"],
@@ -865,6 +1057,8 @@ def main():
                                                                "split evenly; 0 = weak scaling with --batch images per GPU")
     ap.add_argument("--preheat", type=float, default=2.0, help="seconds of untimed full-duty steps before each timed region")
     ap.add_argument("--check-images", type=int, default=256, help="images of the batch compared one by one with the oracle (untimed)")
+    ap.add_argument("--refine-margin", type=float, default=None, help="fp16 path: top-2 logit gap below which an image is re-run at fp32 "
+                                                                    "grade (default: the engine's; 0 switches the refinement off)")
     ap.add_argument("--no-api", action="store_true", help="skip the e2e_api leg (the mirrors' Python surface)")
     ap.add_argument("--no-fp32-grade", action="store_true", help="skip the second measurement of the workload in fp16x3 mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -896,7 +1090,7 @@ def main():
     elif args.gpus > 1:
         log(f"[bench] --gpus {args.gpus} without torchrun: launch with torch.distributed.run; running 1 rank")
     try:
-        (run_train if args.workload == "train" else run_ours)(args, rank, world, local_rank)
+        {"train": run_train, "pipeline": run_pipeline}.get(args.workload, run_ours)(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

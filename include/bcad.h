@@ -60,6 +60,7 @@ extern "C" {
 #endif
 
 typedef struct bcad_model bcad_model;
+typedef struct bcad_unet bcad_unet;     /* tiny U-Net encoder front on the tensor cores (below) */
 
 typedef struct bcad_config {
     int32_t in_h, in_w, in_c;               /* input_shape (H,W,C): Classes/CNNModel.py:68, ADCNNM.py:42 */
@@ -180,6 +181,12 @@ BCAD_API int bcad_gradcam_overlays_host(bcad_model* m, const uint8_t* gray_u8_ho
 BCAD_API int bcad_gradcam_tail(const void* A_dev, const void* dA_dev, int B, int K, int h, int w, int H, int W,
                       int dtype, float* out_dev, void* stream);
 
+/* ---- input stage of the GRADCAM.py surface, DEVICE buffers: gray_u8_dev uint8 [B,H,W] -> img01_dev fp32 [B,H,W] = u8 / 255
+ * (GRADCAM.py:46) and the CNN input x_dev fp32 [B,H,W,C]: standardise = 1: (img01 - mean) / (std + 1e-8) per image (the reference's
+ * CNN-input normalisation, app.py:179-182; mean / std from exact integer sums), 0: img01; the channel replicated C times. */
+BCAD_API int bcad_gray_preprocess(const uint8_t* gray_u8_dev, int B, int H, int W, int C, int standardise, float* img01_dev,
+                         float* x_dev, void* stream);
+
 /* ---- overlay stage (show_cam_on_image GRADCAM.py:67, heatmap_uint8 GRADCAM.py:70) -------------- */
 /* img01_dev: fp32 [B,H,W] grayscale in [0,1]; cam_dev: fp32 [B,H,W]; overlay_rgb_dev: u8 [B,H,W,3]
  * (NULL to skip); heat_u8_dev: u8 [B,H,W] (NULL to skip). */
@@ -196,6 +203,26 @@ BCAD_API int bcad_conv_block(const float* x_dev, int B, int H, int W, int Cin, c
                     float* y_dev, float* pooled_dev, void* stream);
 /* non-overlapping mean pool, floor dims (Classes/ImageSegmentation.py:145-163): [B,H,W,C] -> [B,H/pool,W/pool,C] */
 BCAD_API int bcad_avg_pool(const float* x_dev, int B, int H, int W, int C, int pool, float* out_dev, void* stream);
+
+/* The same front as ONE tensor-core pipeline behind a handle (BASELINE config 3: U-Net -> CNN -> Grad-CAM at batch 256), for
+ * single-channel images with H, W multiples of 4: tiny_unet_numpy (Classes/unet.py:61-73: conv(1->16)+ReLU+pool, conv(16->32)+ReLU+
+ * pool, conv(32->64)+ReLU, every conv with the padded-size-output quirk of unet.py:19-27) followed by average_pool
+ * (Classes/ImageSegmentation.py:145-163).  conv1 on CUDA cores (K = 9), conv2 / conv3 as tcgen05 implicit GEMMs with fp16 operands
+ * and fp32 accumulation (results within 1e-2 of the map's scale; bcad_conv_block above is the fp32 route for every other shape).
+ * The handle owns the weight images and the intermediate maps: no allocation on the forward path. */
+BCAD_API int bcad_unet_create(int H, int W, int max_batch, int device, bcad_unet** out);
+BCAD_API void bcad_unet_destroy(bcad_unet* u);
+/* kernels as unet.py holds them, HOST fp32: k1 (3,3,1,16), k2 (3,3,16,32), k3 (3,3,32,64) */
+BCAD_API int bcad_unet_set_kernels(bcad_unet* u, const float* k1_host, const float* k2_host, const float* k3_host);
+/* output shape per image: avg_pool = 0 -> the reference's bn tensor (H/4+3, W/4+3, 64) incl. its two zero rows / columns;
+ * avg_pool = p > 0 -> average_pool(bn, p): floor((H/4+3)/p) x floor((W/4+3)/p) x 64 (256x256, p = 3: 22 x 22 x 64) */
+BCAD_API int bcad_unet_out_shape(bcad_unet* u, int avg_pool, int* out_h, int* out_w, int* out_c);
+/* x_dev: fp32 [B,H,W] (single channel); out_dev: fp32 NHWC [B,out_h,out_w,64] */
+BCAD_API int bcad_unet_forward(bcad_unet* u, const float* x_dev, int B, int avg_pool, float* out_dev, void* stream);
+BCAD_API int64_t bcad_unet_launch_count(bcad_unet* u);
+/* per-stage device times of the last forward's last chunk (CUDA events before every launch), stages 0..4 */
+BCAD_API int bcad_unet_set_profiling(bcad_unet* u, int on);
+BCAD_API int bcad_unet_profile_get(bcad_unet* u, int i, char* name_buf, int name_cap, float* ms);
 
 /* ---- feeding producer of the basic classifier (app.py:466-489 process_bottleneck_features) ----------------------------- */
 /* feat_dev: fp32 [B][C][H][W] (layout 0) or [B][H][W][C] (layout 1) -> cv2.resize(.., (out_w, out_h), INTER_LINEAR) ->

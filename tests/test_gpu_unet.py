@@ -80,3 +80,52 @@ def test_process_bottleneck_features_matches_reference():
     fb = rng.standard_normal((2, 64, 256, 256)).astype(np.float32)
     out = bn.resize_batch(fb, (32, 32)).cpu().numpy()
     assert np.array_equal(out[1], ogc.process_bottleneck_features(fb[1], (32, 32)))
+
+
+def test_unet_front_on_tensor_cores_vs_reference_fixture():
+    """bcad_unet_* (conv2 / conv3 as tcgen05 implicit GEMMs, fp16 operands) against the reference's own tiny_unet_numpy output
+    and average_pool (fixture made by running Classes/unet.py): 16-bit tolerance, quirk rows / columns exactly zero."""
+    from bcad_b200 import unet as U
+    from oracle import unet as ou
+    g = np.load(os.path.join(GOLDEN, "ref_unet_small.npz"))
+    ks = ou.draw_kernels(1, int(g["seed"]))
+    front = U.UnetFront(16, 16, ks, max_batch=2)
+    bn = front.forward(g["x"], avg_pool=0).cpu().numpy()
+    assert bn.shape == g["bn"].shape == (2, 7, 7, 64) and front.out_shape(0) == (7, 7, 64)
+    assert np.all(bn[:, -2:] == 0) and np.all(bn[:, :, -2:] == 0)
+    assert _rel(bn, g["bn"]) <= 1e-2
+    avg = front.forward(g["x"], avg_pool=3).cpu().numpy()
+    assert avg.shape == g["avg3"].shape and _rel(avg, g["avg3"]) <= 1e-2
+    assert front.launch_count == 10
+    front.close()
+    with pytest.raises(ValueError, match="multiples of 4"):
+        U.UnetFront(18, 16)
+
+
+@pytest.mark.parametrize("H,W,B,scales", [(256, 256, 5, (0.3, 0.08, 0.06)),      # BASELINE cfg 3 shape, activations O(1)
+                                          (256, 256, 3, (1.0, 1.0, 1.0)),         # the reference's raw randn kernels: values in the 1000s
+                                          (64, 48, 7, (0.3, 0.08, 0.06)),
+                                          (8, 12, 3, (0.3, 0.1, 0.1)),            # smallest maps: 4x6 -> 3x4
+                                          (40, 520, 2, (0.3, 0.08, 0.06))])       # 260-pixel rows: conv2 walks three 128-pixel segments
+def test_unet_front_on_tensor_cores_vs_oracle(H, W, B, scales):
+    import torch
+    from bcad_b200 import unet as U
+    from oracle import unet as ou
+    from oracle import cnn as ocnn
+    x = ocnn.synth_images(B, (H, W, 1), seed=5)
+    ks = [k * s for k, s in zip(ou.draw_kernels(1, 7), scales)]
+    front = U.UnetFront(H, W, ks, max_batch=4)                                   # B > max_batch: chunked
+    want = ou.tiny_unet(x.astype(np.float64), ks)
+    bn = front.forward(torch.from_numpy(x).cuda(), avg_pool=0).cpu().numpy()
+    assert bn.shape == want.shape == (B, H // 4 + 3, W // 4 + 3, 64)
+    assert np.isfinite(bn).all() and _rel(bn, want) <= 1e-2
+    assert np.all(bn[:, -2:] == 0) and np.all(bn[:, :, -2:] == 0)
+    # the border row / column of the pooled second map is the part computed outside the tensor-core kernel: check it on its own
+    h3, w3 = H // 4 + 1, W // 4 + 1
+    assert _rel(bn[:, h3 - 2:h3, :w3], want[:, h3 - 2:h3, :w3]) <= 1e-2 and _rel(bn[:, :h3, w3 - 2:w3], want[:, :h3, w3 - 2:w3]) <= 1e-2
+    for pool in (3, 5):
+        if min(h3 + 2, w3 + 2) >= pool:
+            got = front.forward(x, avg_pool=pool).cpu().numpy()
+            ref = ou.average_pool(want, pool)
+            assert got.shape == ref.shape and _rel(got, ref) <= 1e-2
+    front.close()

@@ -21,6 +21,6 @@ Everything computes inside ``libbcad.so`` (hand-written sm_100a CUDA).  There is
 PyTorch-op fallback: importing works anywhere, calling needs the built library and a B200.
 """
 from . import _lib  # noqa: F401
-from .engine import Engine, NetSpec, ShardedEngine, gradcam_tail, overlay, shard_bounds  # noqa: F401
+from .engine import Engine, NetSpec, ShardedEngine, gradcam_tail, gray_preprocess, overlay, shard_bounds  # noqa: F401
 
-__all__ = ["Engine", "NetSpec", "ShardedEngine", "gradcam_tail", "overlay", "shard_bounds"]
+__all__ = ["Engine", "NetSpec", "ShardedEngine", "gradcam_tail", "gray_preprocess", "overlay", "shard_bounds"]

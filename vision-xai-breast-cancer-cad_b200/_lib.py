@@ -64,6 +64,15 @@ _SIGNATURES = {
     "bcad_conv_block": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float,
                                   C.c_int, _P, _P, _P]),
     "bcad_avg_pool": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "bcad_unet_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "bcad_unet_destroy": (None, [_P]),
+    "bcad_unet_set_kernels": (C.c_int, [_P, _P, _P, _P]),
+    "bcad_unet_out_shape": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "bcad_unet_forward": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
+    "bcad_unet_launch_count": (C.c_int64, [_P]),
+    "bcad_unet_set_profiling": (C.c_int, [_P, C.c_int]),
+    "bcad_unet_profile_get": (C.c_int, [_P, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_float)]),
+    "bcad_gray_preprocess": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "bcad_bottleneck_resize": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "bcad_grad_elems": (C.c_int64, [_P]),
     "bcad_grad_layout": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),

@@ -921,6 +921,12 @@ int bcad_gradcam_tail(const void* A, const void* dA, int B, int K, int h, int w,
     return rc;
 }
 
+int bcad_gray_preprocess(const uint8_t* gray_u8, int B, int H, int W, int C, int standardise, float* img01, float* x, void* stream) {
+    BCAD_REQUIRE(gray_u8 && img01 && x, "gray_preprocess: null argument");
+    BCAD_REQUIRE(B >= 1 && H >= 1 && W >= 1 && C >= 1 && (standardise == 0 || standardise == 1), "gray_preprocess: bad argument");
+    return launch_gray_preprocess(gray_u8, img01, x, B, H * W, C, standardise, (cudaStream_t)stream);
+}
+
 int bcad_overlay(const float* img01, const float* cam, int B, int H, int W, uint8_t* overlay_rgb, uint8_t* heat_u8,
                  void* stream) {
     BCAD_REQUIRE(img01 && cam, "overlay: null argument");

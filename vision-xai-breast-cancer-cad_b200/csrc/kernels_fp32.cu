@@ -941,37 +941,64 @@ __constant__ uint8_t c_jet_bgr[256 * 3] = {
 #include "jet_lut.inc"
 };
 
+// One CTA per image.  The JET table sits in shared memory as the float heat values (the colour index differs from lane to lane, so
+// constant memory would serialise every lookup); a thread handles 4 consecutive pixels: 16-byte loads of cam and image, one
+// 12-byte store of RGB.  Pass 1: per-image maximum of the blend (+ heatmap_uint8); pass 2 (inputs come back from L2): scale, store.
 __global__ void __launch_bounds__(1024)
 overlay_kernel(const float* __restrict__ img01, const float* __restrict__ cam, int H, int W,
                uint8_t* __restrict__ overlay_rgb, uint8_t* __restrict__ heat_u8) {
     __shared__ float s_red[64];
+    __shared__ float s_lut[256 * 3];                                       // RGB order, already / 255
     const int b = blockIdx.x, npix = H * W;
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = (float)c_jet_bgr[(i / 3) * 3 + (2 - i % 3)] / 255.f;   // BGR -> RGB
+    __syncthreads();
     const float* ib = img01 + (size_t)b * npix;
     const float* cb = cam + (size_t)b * npix;
+    const bool vec = (npix % 4 == 0) && ((reinterpret_cast<uintptr_t>(ib) | reinterpret_cast<uintptr_t>(cb)) % 16 == 0);
+    const int n4 = vec ? npix / 4 : 0;
     float vmax = -3.4e38f, vmin = 0.f;
-    for (int i = threadIdx.x; i < npix; i += blockDim.x) {
-        const float cv = cb[i];
-        const int li = (int)(uint8_t)(int)(255.f * cv);          // np.uint8(255*cam): truncation
-        if (heat_u8 != nullptr) heat_u8[(size_t)b * npix + i] = (uint8_t)(int)(cv * 255.f);
-        const float g = ib[i];
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const float heat = (float)c_jet_bgr[li * 3 + (2 - ch)] / 255.f;     // BGR -> RGB
-            vmax = fmaxf(vmax, 0.5f * heat + 0.5f * g);
+    auto blend_max = [&](float cv, float g) {
+        const int li = (int)(uint8_t)(int)(255.f * cv);                   // np.uint8(255*cam): truncation
+        const float* l = s_lut + li * 3;
+        vmax = fmaxf(vmax, fmaxf(fmaxf(0.5f * l[0] + 0.5f * g, 0.5f * l[1] + 0.5f * g), 0.5f * l[2] + 0.5f * g));
+    };
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+        const float4 c4 = __ldg(reinterpret_cast<const float4*>(cb) + i), g4 = __ldg(reinterpret_cast<const float4*>(ib) + i);
+        blend_max(c4.x, g4.x); blend_max(c4.y, g4.y); blend_max(c4.z, g4.z); blend_max(c4.w, g4.w);
+        if (heat_u8 != nullptr) {
+            uchar4 o;
+            o.x = (uint8_t)(int)(c4.x * 255.f); o.y = (uint8_t)(int)(c4.y * 255.f); o.z = (uint8_t)(int)(c4.z * 255.f); o.w = (uint8_t)(int)(c4.w * 255.f);
+            reinterpret_cast<uchar4*>(heat_u8 + (size_t)b * npix)[i] = o;
         }
+    }
+    for (int i = n4 * 4 + threadIdx.x; i < npix; i += blockDim.x) {
+        blend_max(cb[i], ib[i]);
+        if (heat_u8 != nullptr) heat_u8[(size_t)b * npix + i] = (uint8_t)(int)(cb[i] * 255.f);
     }
     if (overlay_rgb == nullptr) return;
     block_minmax(vmin, vmax, s_red);
-    for (int i = threadIdx.x; i < npix; i += blockDim.x) {
-        const int li = (int)(uint8_t)(int)(255.f * cb[i]);
-        const float g = ib[i];
+    auto rgb = [&](float cv, float g, uint8_t* o) {
+        const int li = (int)(uint8_t)(int)(255.f * cv);
+        const float* l = s_lut + li * 3;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const float heat = (float)c_jet_bgr[li * 3 + (2 - ch)] / 255.f;
-            const float o = (0.5f * heat + 0.5f * g) / vmax;
-            overlay_rgb[((size_t)b * npix + i) * 3 + ch] = (uint8_t)(int)(255.f * o);
+        for (int ch = 0; ch < 3; ++ch) o[ch] = (uint8_t)(int)(255.f * ((0.5f * l[ch] + 0.5f * g) / vmax));
+    };
+    uint8_t* ob = overlay_rgb + (size_t)b * npix * 3;
+    const bool vst = vec && (reinterpret_cast<uintptr_t>(ob) % 4 == 0);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+        const float4 c4 = __ldg(reinterpret_cast<const float4*>(cb) + i), g4 = __ldg(reinterpret_cast<const float4*>(ib) + i);
+        uint8_t o[12];
+        rgb(c4.x, g4.x, o); rgb(c4.y, g4.y, o + 3); rgb(c4.z, g4.z, o + 6); rgb(c4.w, g4.w, o + 9);
+        if (vst) {
+            uint32_t* d = reinterpret_cast<uint32_t*>(ob + (size_t)i * 12);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) d[q] = (uint32_t)o[4 * q] | ((uint32_t)o[4 * q + 1] << 8) | ((uint32_t)o[4 * q + 2] << 16) | ((uint32_t)o[4 * q + 3] << 24);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 12; ++q) ob[(size_t)i * 12 + q] = o[q];
         }
     }
+    for (int i = n4 * 4 + threadIdx.x; i < npix; i += blockDim.x) rgb(cb[i], ib[i], ob + (size_t)i * 3);
 }
 
 // heatmap_uint8 = (cam * 255).astype(np.uint8)  (GRADCAM.py:70: truncation), 4 pixels per thread

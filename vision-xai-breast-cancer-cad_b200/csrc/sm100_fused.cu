@@ -9,7 +9,7 @@
 // block's CUDA-core work (instruction-issue bound) now overlaps the second block's HBM-bound stores on the same SM.
 //
 // Warp roles (22 warps): 0-15 four first-block teams (team t produces ring row t&1 of the stages with parity t>>1),
-// 16 second-block MMA issuer, 17 weight loader, 18-21 second-block epilogue.  TMEM (512 columns): [0,256) second block
+// 16 second-block MMA issuer, 17 weight loader + issuer of the teams' (first-block) MMAs, 18-21 second-block epilogue.  TMEM (512 columns): [0,256) second block
 // (2 buffers x 2 rows x 64), [256 + 64 t, +64) team t.  A team's tile (128 pooled pixels) runs in TWO passes of two pool
 // classes each (2 x 32 accumulator columns; the running maximum stays in registers as packed halves): four teams are what
 // it takes to hide a tile's dependent build -> MMA -> TMEM-load chain, and four 128-column teams would not fit in TMEM.
@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) conv_fused_kernel(FusedArgs a) 
     uint64_t* tbar = bars + 2 * S + 5;           // [4] a team's first-block MMAs have retired
     uint64_t* ready = bars + 2 * S + 5 + FZ_TEAMS;   // [4] a team's im2col image is built and its accumulator columns are drained (count 4)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 5 + 2 * FZ_TEAMS);
+    uint32_t* fz_stop = tmem_slot + 1;           // set by the second block's issuer when its last item is done
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) conv_fused_kernel(FusedArgs a) 
     for (int i = tid; i < ((PLAIN ? 2 : 4) * FZ_C0 * 16) / 16; i += FZ_THREADS)
         reinterpret_cast<uint4*>(s_w0)[i] = reinterpret_cast<const uint4*>(a.w0_img)[i];
     if (tid == 0) {
+        *fz_stop = 0u;
         for (int i = 0; i < S; ++i) { mbar_init(&full[i], 8); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
         for (int i = 0; i < FZ_TEAMS; ++i) { mbar_init(&tbar[i], 1); mbar_init(&ready[i], 4); }
@@ -265,31 +267,29 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) conv_fused_kernel(FusedArgs a) 
             c = n;
         }
     } else if (warp == 4 * FZ_TEAMS + 1) {
-        // ================================ second-block weights ================================
+        // ================================ second-block weights, then the teams' MMA issuer ================================
         if (lane == 0) {
             constexpr int WB = L::WBYTES + L::BIAS_TILE;
             mbar_arrive_expect_tx(wbar, WB);
             for (int off = 0; off < WB; off += 16384) bulk_g2s(s_w + off, a.w1_img + off, min(16384, WB - off), wbar);
         }
-    } else if (warp == 4 * FZ_TEAMS) {
-        // ================================ second-block MMA issuer ================================
+        // The first block's MMAs are issued HERE, on behalf of the teams, not by the second block's issuer: polling four `ready`
+        // barriers costs ~600 cycles a round (mbarrier.test_wait), and inside the second block's issue loop those rounds (two per
+        // row pair + every wait) kept its single thread from feeding the tensor pipe: 79 cycles per 128x64x16 MMA with the teams
+        // idle against the pipe's own 48 (tools/fz_decompose.sh, tools/umma_microbench.py).  Any thread of the CTA may issue
+        // tcgen05.mma; the two issuers' instructions interleave in the pipe's queue exactly as they did before.
         const bool leader = elect_one();
-        constexpr uint32_t idesc = make_idesc_f16(128, COUT);
-        // ---- first-block MMAs on behalf of the teams
         constexpr uint32_t idesc0 = make_idesc_f16(128, FZ_C0);
         constexpr uint64_t a_tmpl = ((uint64_t)(2048 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
         constexpr uint64_t b_tmpl = ((uint64_t)((FZ_C0 * 16) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
         const uint64_t im_desc0 = a_tmpl | (uint64_t)((smem_u32(smem + L::OFF_IM) & 0x3FFFFu) >> 4);
         const uint64_t w0_desc0 = b_tmpl | (uint64_t)((smem_u32(s_w0) & 0x3FFFFu) >> 4);
         uint32_t rphase = 0;                                  // bit t = parity team t's `ready` barrier is expected to complete next
-        FZ_T(long long tr_full = 0; long long tr_tempty = 0; long long tr_issue = 0; long long tr_serv = 0; long long tr_nserv = 0;)
-        FZ_T(const long long tr_begin = clock64();)
-        auto service_teams = [&]() {
+        const volatile uint32_t* stop = fz_stop;
+        while (!*stop) {
 #pragma unroll
             for (int t = 0; t < FZ_TEAMS; ++t) {
                 if (mbar_test_wait(&ready[t], (rphase >> t) & 1)) {
-                    FZ_T(const long long s0 = clock64();)
-                    FZ_T(tr_nserv += 1;)
                     rphase ^= 1u << t;
                     tc_fence_after();
 #pragma unroll
@@ -299,13 +299,16 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) conv_fused_kernel(FusedArgs a) 
                             umma_f16_if(leader, tmem + 256 + t * 64 + qc * FZ_C0, im_desc0 + (uint64_t)((t * 16384 + qc * 8192 + ks * 4096) >> 4),
                                         w0_desc0 + (uint64_t)((ks * 2 * FZ_C0 * 16) >> 4), idesc0, ks);
                     umma_commit_if(leader, &tbar[t]);
-                    FZ_T(tr_serv += clock64() - s0;)
                 }
             }
-        };
-        auto wait_serving = [&](uint64_t* bar, uint32_t parity) {      // never block: the teams need this warp to make progress
-            while (!mbar_test_wait(bar, parity)) service_teams();
-        };
+        }
+    } else if (warp == 4 * FZ_TEAMS) {
+        // ================================ second-block MMA issuer ================================
+        const bool leader = elect_one();
+        constexpr uint32_t idesc = make_idesc_f16(128, COUT);
+        FZ_T(long long tr_full = 0; long long tr_tempty = 0; long long tr_issue = 0; long long tr_serv = 0; long long tr_nserv = 0;)
+        FZ_T(const long long tr_begin = clock64();)
+        auto wait_serving = [&](uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); };    // (the loader warp serves the teams now)
         mbar_wait(wbar, 0);
         uint32_t g = 0, acc_it = 0;
         const uint32_t w_base = smem_u32(s_w), zero_base = smem_u32(s_zero), ring_base = smem_u32(s_ring);
@@ -331,7 +334,6 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) conv_fused_kernel(FusedArgs a) 
                 const bool lead2 = leader && !(a.debug & 128);       // debug bit 7: the second block's MMA instructions run predicated off
                 for (int r = 0; r < 2; ++r) {
                     if (2 * p + r >= nrows || (a.debug & 8)) break;     // debug bit 3: no second-block MMAs (timing experiment)
-                    service_teams();                          // between rows: a ready team waits for at most one row (19 MMAs)
                     const uint32_t d_tmem = tmem + j * (2 * COUT) + r * COUT;
                     umma_f16_if(lead2, d_tmem, desc64(ones_lo, d_hi), desc64(b_lo0 + (uint32_t)(L::WBYTES >> 4), d_hi), idesc, 0u);
 #pragma unroll
@@ -358,6 +360,9 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) conv_fused_kernel(FusedArgs a) 
             umma_commit_if(leader, &empty[g % S]);
             ++g;
         }
+        // every team MMA has retired by now (the second block consumed their rows): release the loader warp's service loop
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(fz_stop) = 1u;
         FZ_T(if (blockIdx.x == 0 && lane == 0) { g_fz_trace[0] = clock64() - tr_begin; g_fz_trace[1] = tr_full; g_fz_trace[2] = tr_tempty;
                                                  g_fz_trace[3] = tr_issue; g_fz_trace[4] = tr_serv; g_fz_trace[5] = tr_nserv; g_fz_trace[6] = acc_it; })
     } else {

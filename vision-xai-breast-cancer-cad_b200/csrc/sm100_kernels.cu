@@ -814,6 +814,7 @@ int launch_conv_igemm(const IgemmArgs& a, int Cin, int Cout, bool x3, int sms, c
         if (Cin == 64) return launch_igemm_t<64, 64, false>(a, sms, s);
     }
     if (Cout == 64 && x3 && Cin == 64) return launch_igemm_t<64, 64, true>(a, sms, s);
+    if (Cout == 32 && !x3 && Cin == 16) return launch_igemm_t<16, 32, false>(a, sms, s);      // tiny U-Net front, second conv (sm100_unet.cu)
     set_error("conv_igemm: Cin=%d Cout=%d x3=%d not supported", Cin, Cout, (int)x3);
     return BCAD_ERR_INVALID;
 }

@@ -473,6 +473,21 @@ def gradcam_tail(A: torch.Tensor, dA: torch.Tensor, out_hw: Tuple[int, int]) -> 
     return out
 
 
+def gray_preprocess(gray_u8: torch.Tensor, channels: int = 1, standardise: bool = True):
+    """uint8 grey images [B,H,W] on the GPU -> (img01 fp32 [B,H,W] = u8 / 255, x fp32 [B,H,W,channels] = the CNN input)."""
+    lib = _lib.load()
+    g = gray_u8.contiguous()
+    if g.dtype != torch.uint8 or g.dim() != 3 or not g.is_cuda:
+        raise ValueError("gray_u8 must be a CUDA uint8 tensor [B,H,W]")
+    B, H, W = g.shape
+    img01 = torch.empty((B, H, W), device=g.device, dtype=torch.float32)
+    x = torch.empty((B, H, W, channels), device=g.device, dtype=torch.float32)
+    with torch.cuda.device(g.device):
+        _lib.check(lib.bcad_gray_preprocess(_ptr(g), B, H, W, int(channels), 1 if standardise else 0, _ptr(img01), _ptr(x),
+                                            C.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)))
+    return img01, x
+
+
 def overlay(img01: torch.Tensor, cam: torch.Tensor, want_overlay=True, want_heat_u8=True):
     """show_cam_on_image + heatmap_uint8 (GRADCAM.py:67,70) on CUDA tensors [B,H,W] -> (u8 [B,H,W,3], u8 [B,H,W])."""
     lib = _lib.load()

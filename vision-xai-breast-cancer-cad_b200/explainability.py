@@ -28,27 +28,37 @@ def _class_of(y_true, num_classes):
 def compute_backprops_for_explainability(model, y_true, want_weight_grads=True):
     """Differentiates the model's latest ``forward(x, ...)`` (the reference reads that forward's caches out of ``model.layers``);
     if something else has used the handle since, the forward is repeated first (never a silently different image)."""
-    eng = model._cache_ready()
     c = _class_of(y_true, model.num_classes)
     conv_idx = [i for i, l in enumerate(model.layers) if l["type"] == "conv"]
-    outs, d_in = eng.explain_backward(1, c, "softmax_ce", want_conv=range(len(conv_idx)), want_input=True)
-    conv_act_grads = {li: outs[bi][0].double().cpu().numpy() for bi, li in enumerate(conv_idx)}
-    d_input = d_in[0].double().cpu().numpy()
-    grads = [None] * len(model.layers)
-    if want_weight_grads:
-        if model._last_masks is not None:
-            eng.set_dropout_masks(model._last_masks, mask_backward=False)
-        try:
+    masks = model._last_masks
+    if masks is None:
+        eng = model._cache_ready()
+    else:
+        # a training forward: its dropout multipliers stay set on the handle for the whole backward (the weight gradients see the
+        # dropped activations, Classes/CNNModel.py:186-188), so the forward is replayed under them first
+        if model._last_x is None:
+            raise RuntimeError("no forward() has been run on this model yet")
+        eng = model.engine
+        eng.set_dropout_masks(masks, mask_backward=False)
+    try:
+        if masks is not None:
+            eng.predict(model._last_x[None])
+        outs, d_in = eng.explain_backward(1, c, "softmax_ce", want_conv=range(len(conv_idx)), want_input=True)
+        conv_act_grads = {li: outs[bi][0].double().cpu().numpy() for bi, li in enumerate(conv_idx)}
+        d_input = d_in[0].double().cpu().numpy()
+        grads = [None] * len(model.layers)
+        if want_weight_grads:
             flat, _ = eng.train_backward(model._last_x[None], [c])
-        finally:
-            if model._last_masks is not None:
-                eng.set_dropout_masks(None)
-        g = eng.unpack_grads(flat)
-        dense_idx = [i for i, l in enumerate(model.layers) if l["type"] in ("dense", "output")]
-        for bi, li in enumerate(conv_idx):
-            grads[li] = {"dF": g["conv_w"][bi].astype(np.float64), "db_conv": g["conv_b"][bi].astype(np.float64)}
-        for di, li in enumerate(dense_idx):
-            grads[li] = {"dW": g["dense_w"][di].astype(np.float64), "db": g["dense_b"][di].astype(np.float64)}
+            g = eng.unpack_grads(flat)
+            dense_idx = [i for i, l in enumerate(model.layers) if l["type"] in ("dense", "output")]
+            for bi, li in enumerate(conv_idx):
+                grads[li] = {"dF": g["conv_w"][bi].astype(np.float64), "db_conv": g["conv_b"][bi].astype(np.float64)}
+            for di, li in enumerate(dense_idx):
+                grads[li] = {"dW": g["dense_w"][di].astype(np.float64), "db": g["dense_b"][di].astype(np.float64)}
+    finally:
+        if masks is not None:
+            eng.set_dropout_masks(None)
+            eng.cache_tag = None
     return grads, d_input, conv_act_grads
 
 

@@ -92,3 +92,78 @@ def average_pool(input, pool_size=5, as_numpy=True):
     with torch.cuda.device(x.device):
         _lib.check(lib.bcad_avg_pool(C.c_void_p(x.data_ptr()), B, H, W, Cc, int(pool_size), C.c_void_p(out.data_ptr()), _stream(x)))
     return out.double().cpu().numpy() if as_numpy else out
+
+
+class UnetFront:
+    """``tiny_unet`` + ``average_pool`` as ONE tensor-core pipeline (libbcad ``bcad_unet_*``: conv2 / conv3 as tcgen05 implicit
+    GEMMs, fp16 operands, fp32 accumulation) for batches of single-channel images whose H and W are multiples of 4 -- BASELINE
+    config 3's front at batch 256.  Results agree with the reference functions to the 16-bit mode's tolerance (1e-2 of the
+    map's scale); ``tiny_unet`` / ``average_pool`` above are the fp32 route for every other shape."""
+
+    def __init__(self, H, W, kernels=None, max_batch=256, device=0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("libbcad needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.H, self.W, self.device = int(H), int(W), int(device)
+        self.tdev = torch.device("cuda", self.device)
+        self._h = C.c_void_p()
+        _lib.check(self.lib.bcad_unet_create(self.H, self.W, int(max_batch), self.device, C.byref(self._h)))
+        if kernels is not None:
+            self.set_kernels(kernels)
+
+    def set_kernels(self, kernels):
+        """kernels: the three arrays ``tiny_unet_numpy`` draws -- (3,3,1,16), (3,3,16,32), (3,3,32,64)."""
+        ks = [np.ascontiguousarray(k, dtype=np.float32) for k in kernels]
+        if [k.shape for k in ks] != [(3, 3, 1, 16), (3, 3, 16, 32), (3, 3, 32, 64)]:
+            raise ValueError(f"kernel shapes {[k.shape for k in ks]} are not the tiny U-Net's")
+        _lib.check(self.lib.bcad_unet_set_kernels(self._h, *[C.c_void_p(k.ctypes.data) for k in ks]))
+
+    def out_shape(self, avg_pool=3):
+        h, w, c = C.c_int(), C.c_int(), C.c_int()
+        _lib.check(self.lib.bcad_unet_out_shape(self._h, int(avg_pool), C.byref(h), C.byref(w), C.byref(c)))
+        return h.value, w.value, c.value
+
+    def forward(self, x, avg_pool=3, out=None):
+        """x: [B,H,W] or [B,H,W,1] (CUDA tensor or array) -> fp32 CUDA tensor [B,h,w,64]: ``average_pool(tiny_unet(x), avg_pool)``,
+        or the ``bn`` tensor itself with ``avg_pool=0``."""
+        x = x.to(device=self.tdev, dtype=torch.float32) if isinstance(x, torch.Tensor) else \
+            torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.tdev)
+        if x.dim() == 4 and x.shape[-1] == 1:
+            x = x[..., 0]
+        if x.dim() != 3 or tuple(x.shape[1:]) != (self.H, self.W):
+            raise ValueError(f"input shape {tuple(x.shape)} does not match [B,{self.H},{self.W}(,1)]")
+        x = x.contiguous()
+        h, w, c = self.out_shape(avg_pool)
+        if out is None:
+            out = torch.empty((x.shape[0], h, w, c), device=self.tdev, dtype=torch.float32)
+        with torch.cuda.device(self.tdev):
+            _lib.check(self.lib.bcad_unet_forward(self._h, C.c_void_p(x.data_ptr()), int(x.shape[0]), int(avg_pool),
+                                                  C.c_void_p(out.data_ptr()), _stream(x)))
+        return out
+
+    @property
+    def launch_count(self):
+        return int(self.lib.bcad_unet_launch_count(self._h))
+
+    def set_profiling(self, on: bool):
+        _lib.check(self.lib.bcad_unet_set_profiling(self._h, 1 if on else 0))
+
+    def last_profile(self):
+        """[(stage, ms)] of the last forward's last chunk (needs set_profiling(True) before it)."""
+        out = []
+        for i in range(5):
+            buf, ms = C.create_string_buffer(64), C.c_float()
+            _lib.check(self.lib.bcad_unet_profile_get(self._h, i, buf, 64, C.byref(ms)))
+            out.append((buf.value.decode(), float(ms.value)))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.bcad_unet_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
