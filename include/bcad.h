@@ -242,6 +242,10 @@ BCAD_API int bcad_grad_layout(bcad_model* m, int is_dense, int index, int64_t* w
  * ADCNNM.py:89).  labels_dev: int32 [B]; grads_dev: fp32 [bcad_grad_elems]; loss_dev: fp32 [B] per-sample loss or NULL. */
 BCAD_API int bcad_train_backward(bcad_model* m, const float* x_dev, const int32_t* labels_dev, int B, float* grads_dev,
                         float* loss_dev, void* stream);
+/* The same in two parts, for a data-parallel step that overlaps communication with the backward: part 1 = loss + dense layers
+ * (their gradients -- 99.9 % of the bytes, fc1 -- are final when it returns), part 2 = the conv blocks; part 0 = both. */
+BCAD_API int bcad_train_backward_part(bcad_model* m, const float* x_dev, const int32_t* labels_dev, int B, float* grads_dev,
+                             float* loss_dev, int part, void* stream);
 /* Dropout multipliers for the next forwards of exactly B images (B <= max_batch): masks[b][sum of hidden units] (host or
  * device pointer), hidden layers in order, each value 0 or 1/(1-rate) -- Classes/CNNModel.py:186-188, nn.Dropout of
  * ADCNNM.py:62.  The caller draws them.  NULL or B = 0 switches dropout off.  bcad_train_backward feeds the dropped

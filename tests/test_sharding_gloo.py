@@ -79,3 +79,66 @@ def test_gradient_allreduce_mean_world2(tmp_path):
     mp.spawn(_ar_worker, args=(2, 29500 + (os.getpid() % 2000) + 17, out), nprocs=2, join=True)
     got = torch.load(out)
     assert torch.allclose(got["avg"], got["want"], atol=1e-6)
+
+
+class _FakeEngine:
+    """Host stand-in for bcad_b200.Engine in the trainer's N>1 logic: the 'gradient' of a shard is the mean of per-sample
+    vectors, the dense slice written by part 1 and the conv slice by part 2 (like bcad_train_backward_part)."""
+    uses_tensor_path = False
+    tdev = torch.device("cpu")
+    N, DENSE0 = 64, 16                                   # flat vector: [conv 0..16 | dense 16..64], fc1 bucket = 24..56
+
+    def __init__(self):
+        self.applied = None
+
+    def grad_layout(self, is_dense, index):
+        return (24, 32, 56, 8)
+
+    def _as_device_input(self, x):
+        return torch.as_tensor(x)
+
+    def predict(self, x):
+        return torch.zeros(x.shape[0], dtype=torch.int32), None, None
+
+    @staticmethod
+    def sample_grad(i):
+        return torch.arange(_FakeEngine.N, dtype=torch.float32) * 0.01 + float(i)
+
+    def train_backward(self, x, labels, grads=None, part=0, loss=None):
+        g = torch.zeros(self.N) if grads is None else grads
+        mean = torch.stack([self.sample_grad(int(v)) for v in x[:, 0]]).mean(dim=0)
+        if part in (0, 1):
+            g[self.DENSE0:] = mean[self.DENSE0:]
+        if part in (0, 2):
+            g[:self.DENSE0] = mean[:self.DENSE0]
+        return g, torch.zeros(x.shape[0])
+
+    def apply_update(self, grads, *a, **k):
+        self.applied = grads.clone()
+
+
+def _trainer_worker(rank, world, port, out_path, overlap, equal):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from bcad_b200.training import DataParallelTrainer
+    ids = [[0, 1, 2], [3, 4, 5]] if equal else [[0, 1, 2], [3]]              # sample ids per rank; unequal: 3 + 1
+    eng = _FakeEngine()
+    tr = DataParallelTrainer(eng, overlap=overlap, equal_shards=equal)
+    tr.step(torch.tensor(ids[rank], dtype=torch.float32)[:, None], None)
+    if rank == 0:
+        n = sum(len(v) for v in ids)
+        want = torch.stack([_FakeEngine.sample_grad(i) for v in ids for i in v]).mean(dim=0)
+        torch.save({"got": eng.applied, "want": want, "n": n}, out_path)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("overlap,equal", [(True, True), (True, False), (False, False)])
+def test_data_parallel_trainer_step_is_the_global_batch_mean(tmp_path, overlap, equal):
+    """DataParallelTrainer over 2 gloo ranks: two-part backward with the dense bucket all-reduced before the conv part runs, and
+    shard-size weighting -- the update every rank applies is the mean gradient of the GLOBAL batch (Classes/CNNModel.py:459-464),
+    also when the shards differ in size."""
+    out = str(tmp_path / "tr.pt")
+    mp.spawn(_trainer_worker, args=(2, 29500 + (os.getpid() % 2000) + 31 + 2 * overlap + equal, out, overlap, equal), nprocs=2, join=True)
+    got = torch.load(out)
+    assert torch.allclose(got["got"], got["want"], atol=1e-5)

@@ -78,6 +78,7 @@ _SIGNATURES = {
     "bcad_grad_layout": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                    C.POINTER(C.c_int64)]),
     "bcad_train_backward": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P]),
+    "bcad_train_backward_part": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, C.c_int, _P]),
     "bcad_set_dropout_masks": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
     "bcad_apply_update": (C.c_int, [_P, _P, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _P]),
     "bcad_get_conv_weights": (C.c_int, [_P, C.c_int, _P, _P]),

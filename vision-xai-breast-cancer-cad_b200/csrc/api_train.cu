@@ -101,8 +101,15 @@ int bcad_grad_layout(bcad_model* mm, int is_dense, int index, int64_t* w_off, in
 // Gradients of the MEAN cross-entropy over the B images of the preceding bcad_predict (same x, same B, fp32 path,
 // keep_all_activations=1).  grads_dev: fp32 [bcad_grad_elems]; loss_dev: fp32 [B] per-sample losses (may be NULL).
 int bcad_train_backward(bcad_model* mm, const float* x, const int32_t* labels, int B, float* grads, float* loss, void* stream) {
+    return bcad_train_backward_part(mm, x, labels, B, grads, loss, 0, stream);
+}
+
+// part 0: everything; part 1: loss + dense layers only (their gradients are final when it returns: a data-parallel caller can start
+// all-reducing them -- 99.9 % of the bytes -- while part 2 runs); part 2: the conv blocks (needs part 1 of the same batch before it).
+int bcad_train_backward_part(bcad_model* mm, const float* x, const int32_t* labels, int B, float* grads, float* loss, int part, void* stream) {
     Model* m = reinterpret_cast<Model*>(mm);
     BCAD_REQUIRE(m && x && labels && grads, "train_backward: null argument");
+    BCAD_REQUIRE(part >= 0 && part <= 2, "train_backward: part must be 0 (all), 1 (dense) or 2 (conv)");
     cudaStream_t s = (cudaStream_t)stream;
     if (m->tensor_path) { set_error("training runs on the fp32 path: create the model with BCAD_PREC_FP32"); return BCAD_ERR_INVALID; }
     if (!m->committed || m->cached_B != B) {
@@ -118,6 +125,7 @@ int bcad_train_backward(bcad_model* mm, const float* x, const int32_t* labels, i
     BCAD_CUDA_CHECK(cudaStreamWaitEvent(s, m->call_done, 0));
     const int nc = m->cfg.num_classes, nd = (int)m->dense.size(), nconv = (int)m->conv.size();
     m->prof_n = 0;
+    if (part != 2) {
     float* loss_buf = loss ? loss : T.hbuf;                  // scratch when the caller does not want the losses
     TR_LAUNCH(m, "ce_loss_topgrad", launch_ce_loss_topgrad(m->probs, labels, loss_buf, T.dense_dz[nd - 1], B, nc, s));
     // ---- dense layers, last to first
@@ -136,6 +144,12 @@ int bcad_train_backward(bcad_model* mm, const float* x, const int32_t* labels, i
         TR_LAUNCH(m, "dense_dgrad", launch_sgemm(T.dense_dz[j], D.d_w, dst, B, D.in, D.out, false, 1, s));
         if (j > 0 && T.drop_B && T.drop_backward) TR_LAUNCH(m, "dropout", launch_mul_mask(dst, T.drop + T.drop_off[j - 1], B, m->dense[j - 1].out, T.drop_ld, s));
         if (j > 0) TR_LAUNCH(m, "leaky_mask_mul", launch_leaky_mask_mul(dst, m->dense[j - 1].z, m->cfg.alpha_dense, (int64_t)B * m->dense[j - 1].out, s));
+    }
+    }
+    if (part == 1) {
+        TR_TRY(m->mark("end", s));
+        BCAD_CUDA_CHECK(cudaEventRecord(m->call_done, s));
+        return BCAD_OK;
     }
     // ---- conv blocks, last to first
     const float* gp = m->g_flat;

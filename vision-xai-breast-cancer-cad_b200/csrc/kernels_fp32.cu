@@ -1057,6 +1057,15 @@ __global__ void __launch_bounds__(512) gray_preprocess_kernel(const uint8_t* __r
     const uint8_t* src = g8 + (size_t)b * npix;
     if (standardise) {
         unsigned long long sum = 0, sq = 0;
+        if (npix % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+            unsigned s32 = 0, q32 = 0;                       // per thread <= npix / 512 * 255^2: fits 32 bits up to 33 M pixels
+            for (int i = tid; i < npix / 4; i += 512) {
+                const uchar4 q = reinterpret_cast<const uchar4*>(src)[i];
+                s32 += q.x + q.y + q.z + q.w;
+                q32 += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+            }
+            sum = s32; sq = q32;
+        } else
         for (int i = tid; i < npix; i += 512) { const unsigned v = src[i]; sum += v; sq += v * v; }
         for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
         if ((tid & 31) == 0) { s_sum[tid >> 5] = sum; s_sq[tid >> 5] = sq; }
@@ -1072,11 +1081,22 @@ __global__ void __launch_bounds__(512) gray_preprocess_kernel(const uint8_t* __r
         __syncthreads();
     }
     const float mean = standardise ? s_mean : 0.f, den = standardise ? s_den : 1.f;
+    float* ib = img01 + (size_t)b * npix;
+    float* xb = x + (size_t)b * npix * C;
+    if (C == 1 && npix % 4 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(ib) | reinterpret_cast<uintptr_t>(xb)) & 15) == 0) {
+        for (int i = tid; i < npix / 4; i += 512) {           // 4 pixels per thread: one 4-byte load, two 16-byte stores
+            const uchar4 q = reinterpret_cast<const uchar4*>(src)[i];
+            const float4 v = make_float4((float)q.x / 255.0f, (float)q.y / 255.0f, (float)q.z / 255.0f, (float)q.w / 255.0f);
+            reinterpret_cast<float4*>(ib)[i] = v;
+            reinterpret_cast<float4*>(xb)[i] = standardise ? make_float4((v.x - mean) / den, (v.y - mean) / den, (v.z - mean) / den, (v.w - mean) / den) : v;
+        }
+        return;
+    }
     for (int i = tid; i < npix; i += 512) {
         const float v = (float)src[i] / 255.0f;
-        img01[(size_t)b * npix + i] = v;
+        ib[i] = v;
         const float xv = standardise ? (v - mean) / den : v;
-        for (int c = 0; c < C; ++c) x[((size_t)b * npix + i) * C + c] = xv;
+        for (int c = 0; c < C; ++c) xb[(size_t)i * C + c] = xv;
     }
 }
 

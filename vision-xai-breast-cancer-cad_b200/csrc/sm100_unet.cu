@@ -78,7 +78,7 @@ unet_conv2_border_kernel(const __half* __restrict__ p1, const float* __restrict_
     };
     __half* ob = p2 + (size_t)b * H2 * 4 * W2 * 8;
     const int n_row = W2, n_col = H2 - 1;
-    for (int i = threadIdx.x; i < (n_row + n_col) * 32; i += 256) {
+    for (int i = blockIdx.y * 256 + threadIdx.x; i < (n_row + n_col) * 32; i += 256 * gridDim.y) {
         const int f = i & 31, pos = i >> 5;
         float v;
         int py, px;
@@ -95,27 +95,32 @@ unet_conv2_border_kernel(const __half* __restrict__ p1, const float* __restrict_
 
 // conv3 map (C8-planar fp16, true size h x w) -> fp32 NHWC output: pool = 0: the reference's `bn` tensor (h+2, w+2, C) with its two
 // quirk-zero rows / columns; pool > 0: average_pool(pool) of that tensor (floor dims; the zero rows count in the mean).
+// One thread per (output pixel, channel octet): 16-byte loads of 8 channels per source pixel, two 16-byte stores.
 __global__ void __launch_bounds__(256)
-unet_out_kernel(const __half* __restrict__ a3, float* __restrict__ out, int h, int w, int C, int pool, int Hn, int Wn, size_t total) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        size_t r = i / C;
+unet_out_kernel(const __half* __restrict__ a3, float* __restrict__ out, int h, int w, int C, int pool, int Hn, int Wn, size_t total8) {
+    const int oct = C / 8;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total8; i += (size_t)gridDim.x * blockDim.x) {
+        const int o = (int)(i % oct);
+        size_t r = i / oct;
         const int ox = (int)(r % Wn);
         r /= Wn;
         const int oy = (int)(r % Hn);
         const size_t b = r / Hn;
-        const __half* ab = a3 + b * (size_t)h * (C / 8) * w * 8;
-        auto at = [&](int y, int x) -> float {
-            return (y < h && x < w) ? __half2float(ab[(((size_t)y * (C / 8) + (c >> 3)) * w + x) * 8 + (c & 7)]) : 0.f;
-        };
-        if (pool <= 0) {
-            out[i] = at(oy, ox);
-        } else {
-            float s = 0.f;
-            for (int u = 0; u < pool; ++u)
-                for (int v = 0; v < pool; ++v) s += at(oy * pool + u, ox * pool + v);
-            out[i] = s / (float)(pool * pool);
-        }
+        const uint4* ab = reinterpret_cast<const uint4*>(a3) + b * (size_t)h * oct * w;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const int p = pool > 0 ? pool : 1;
+        for (int u = 0; u < p; ++u)
+            for (int v = 0; v < p; ++v) {
+                const int y = oy * p + u, x = ox * p + v;
+                if (y >= h || x >= w) continue;               // the quirk's zero rows / columns
+                const uint4 q = __ldg(ab + ((size_t)y * oct + o) * w + x);
+                const float2 f0 = unpack_f16(q.x), f1 = unpack_f16(q.y), f2 = unpack_f16(q.z), f3 = unpack_f16(q.w);
+                acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y; acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
+            }
+        const float inv = 1.f / (float)(p * p);
+        float4* dst = reinterpret_cast<float4*>(out + ((b * Hn + oy) * (size_t)Wn + ox) * C + o * 8);
+        dst[0] = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+        dst[1] = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
     }
 }
 
@@ -127,6 +132,21 @@ static int ualloc(UnetFront* u, void** p, size_t bytes) {
     }
     u->allocs.push_back(*p);
     return BCAD_OK;
+}
+
+// rows per work item of a persistent conv kernel: the even band height that minimises the busiest SM's row count
+// (waves x band rows), e.g. 256 images of a 65-row map on 148 SMs: 22-row bands (6 waves x 22) instead of 64 + 1 (2 waves x 64)
+static int pick_band_rows(int n, int Ho, int xsegs, int sms) {
+    int best = 2;
+    long long best_cost = -1;
+    for (int br = 2; br <= 64; br += 2) {
+        const int bands = cdiv(Ho, br);
+        const long long items = (long long)n * bands * xsegs;
+        const long long cost = ((items + sms - 1) / sms) * (br + 2);      // + 2: the halo rows every band re-reads
+        if (best_cost < 0 || cost < best_cost || (cost == best_cost && br > best)) { best_cost = cost; best = br; }
+    }
+    if (best > Ho) best = cdiv(Ho, 2) * 2;
+    return best;
 }
 
 static uint16_t f2h_bits(float f) {
@@ -267,16 +287,14 @@ int bcad_unet_forward(bcad_unet* uu, const float* x_dev, int B, int avg_pool, fl
             a.in = u->p1; a.w_img = u->d_w2_img; a.act = nullptr; a.pool_fc = nullptr; a.pool_c8 = u->p2;
             a.B = n; a.H = u->H1; a.W = u->W1; a.Ho = u->H1; a.Wo = u->W1; a.Hp = u->H2; a.Wp = u->W2; a.pad = 1;
             a.xsegs = cdiv(a.Wo, 128);
-            a.band_rows = 64;
-            while (a.band_rows > 2 && (long long)n * cdiv(a.Ho, a.band_rows) * a.xsegs < u->sms) a.band_rows -= 2;
-            if (a.band_rows > a.Ho) a.band_rows = cdiv(a.Ho, 2) * 2;
+            a.band_rows = pick_band_rows(n, a.Ho, a.xsegs, u->sms);
             a.bands = cdiv(a.Ho, a.band_rows);
             a.alpha = 0.f; a.debug = 0;
             rc = launch_conv_igemm(a, 16, 32, false, u->sms, s);
         }
         mark(2);
         if (rc == BCAD_OK) {
-            unet_conv2_border_kernel<<<n, 256, 0, s>>>(u->p1, u->d_w2_f32, u->p2, u->H1, u->W1, u->H2, u->W2);
+            unet_conv2_border_kernel<<<dim3(n, 8), 256, 0, s>>>(u->p1, u->d_w2_f32, u->p2, u->H1, u->W1, u->H2, u->W2);
             if (cudaGetLastError() != cudaSuccess) { set_error("unet border kernel launch failed"); rc = BCAD_ERR_CUDA; }
         }
         mark(3);
@@ -286,18 +304,16 @@ int bcad_unet_forward(bcad_unet* uu, const float* x_dev, int B, int avg_pool, fl
             a.in = u->p2; a.w_img = u->d_w3_img; a.act = u->a3; a.pool_fc = nullptr; a.pool_c8 = nullptr;
             a.B = n; a.H = u->H2; a.W = u->W2; a.Ho = u->H2; a.Wo = u->W2; a.Hp = u->H2 / 2; a.Wp = u->W2 / 2; a.pad = 1;
             a.xsegs = cdiv(a.Wo, 128);
-            a.band_rows = 64;
-            while (a.band_rows > 2 && (long long)n * cdiv(a.Ho, a.band_rows) * a.xsegs < u->sms) a.band_rows -= 2;
-            if (a.band_rows > a.Ho) a.band_rows = cdiv(a.Ho, 2) * 2;
+            a.band_rows = pick_band_rows(n, a.Ho, a.xsegs, u->sms);
             a.bands = cdiv(a.Ho, a.band_rows);
             a.alpha = 0.f; a.debug = 0;
             rc = launch_conv_igemm(a, 32, 64, false, u->sms, s);
         }
         mark(4);
         if (rc == BCAD_OK) {
-            const size_t total = (size_t)n * oh * ow * 64;
-            const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)u->sms * 16);
-            unet_out_kernel<<<grid, 256, 0, s>>>(u->a3, out_dev + (size_t)b0 * oh * ow * 64, u->H2, u->W2, 64, avg_pool, oh, ow, total);
+            const size_t total8 = (size_t)n * oh * ow * 8;
+            const int grid = (int)std::min<size_t>((total8 + 255) / 256, (size_t)u->sms * 16);
+            unet_out_kernel<<<grid, 256, 0, s>>>(u->a3, out_dev + (size_t)b0 * oh * ow * 64, u->H2, u->W2, 64, avg_pool, oh, ow, total8);
             if (cudaGetLastError() != cudaSuccess) { set_error("unet output kernel launch failed"); rc = BCAD_ERR_CUDA; }
         }
         mark(5);

@@ -296,9 +296,12 @@ class Engine:
         _lib.check(self.lib.bcad_grad_layout(self._h, 1 if is_dense else 0, index, *[C.byref(v) for v in vals]))
         return tuple(int(v.value) for v in vals)          # (w_off, w_elems, b_off, b_elems)
 
-    def train_backward(self, x: torch.Tensor, labels, grads: Optional[torch.Tensor] = None):
+    def train_backward(self, x: torch.Tensor, labels, grads: Optional[torch.Tensor] = None, part: int = 0,
+                       loss: Optional[torch.Tensor] = None):
         """After ``predict(x)`` of the same batch (fp32 engine, keep_all_activations=True):
-        -> (flat gradient of the MEAN cross-entropy [grad_elems], per-sample loss [B]) as CUDA tensors."""
+        -> (flat gradient of the MEAN cross-entropy [grad_elems], per-sample loss [B]) as CUDA tensors.
+        ``part``: 0 everything; 1 the loss + dense layers only (their slice of ``grads`` is final afterwards); 2 the conv blocks
+        (after part 1 of the same batch) -- the split a data-parallel step uses to all-reduce fc1 while the convs run."""
         x = self._as_device_input(x)
         B = x.shape[0]
         lab = torch.as_tensor(labels, dtype=torch.int32).reshape(-1).to(self.tdev).contiguous()
@@ -307,8 +310,9 @@ class Engine:
         with torch.cuda.device(self.tdev):
             if grads is None:
                 grads = torch.zeros((self.grad_elems(),), device=self.tdev, dtype=torch.float32)   # gaps between tensors stay 0
-            loss = torch.empty((B,), device=self.tdev, dtype=torch.float32)
-            _lib.check(self.lib.bcad_train_backward(self._h, _ptr(x), _ptr(lab), B, _ptr(grads), _ptr(loss), self._stream()))
+            if loss is None:
+                loss = torch.empty((B,), device=self.tdev, dtype=torch.float32)
+            _lib.check(self.lib.bcad_train_backward_part(self._h, _ptr(x), _ptr(lab), B, _ptr(grads), _ptr(loss), int(part), self._stream()))
         return grads, loss
 
     def set_dropout_masks(self, masks, mask_backward: bool = True):
