@@ -963,6 +963,34 @@ def run_train(args, rank, world, local_rank):
     barrier()
     launches = eng.launch_count - l0
     ms_total = ev0.elapsed_time(ev1)
+    # what the overlap buys: the same steps with the all-reduce AFTER the whole backward, and the all-reduce of the flat gradient alone
+    ms_serial, ar_ms = None, None
+    if world > 1:
+        tr.overlap = False
+        for _ in range(2):
+            tr.step(x_dev, y_dev)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            tr.step(x_dev, y_dev)
+        e1.record()
+        barrier()
+        ms_serial = e0.elapsed_time(e1) / args.steps
+        tr.overlap = True
+        gbuf = torch.zeros((eng.grad_elems(),), device=dev, dtype=torch.float32)
+        for _ in range(2):
+            dist.all_reduce(gbuf)
+        barrier()
+        e0.record()
+        for _ in range(10):
+            dist.all_reduce(gbuf)
+        e1.record()
+        barrier()
+        ar_ms = e0.elapsed_time(e1) / 10
+        t2 = torch.tensor([ms_serial, ar_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        ms_serial, ar_ms = float(t2[0]), float(t2[1])
     # end to end: inputs and labels from pinned host memory, the step's mean loss read back (2 untimed steps first: torch
     # loads its reduction kernel lazily)
     def step_e2e():
@@ -1011,6 +1039,11 @@ def run_train(args, rank, world, local_rank):
         "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + B * 4),
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "last_mean_loss": mean_loss},
         "gpu_launches": int(launches), "clocks": clocks, "kernels": kernels, "grad_bytes": grad_bytes,
+        "comm": None if world == 1 else {
+            "allreduce_alone_ms": ar_ms, "allreduce_busbw_GBps": grad_bytes * 2 * (world - 1) / world / (ar_ms * 1e-3) / 1e9,
+            "ms_per_step_overlapped": ms_total / args.steps, "ms_per_step_allreduce_after_backward": ms_serial,
+            "allreduce_share_of_step_if_serial": ar_ms / ms_serial,
+            "note": "overlapped = the dense (fc1) bucket is all-reduced while the conv blocks' backward runs (bcad_train_backward_part)"},
     })
 
 
