@@ -46,6 +46,10 @@ extern "C" {
 /* grad_mode: gradient injected at the network output for the explanation */
 #define BCAD_GRAD_LOGIT 0          /* d(logit_c): pytorch_grad_cam ClassifierOutputTarget, GRADCAM.py:64 */
 #define BCAD_GRAD_SOFTMAX_CE 1     /* probs - onehot(c): explainability.py:21-22 */
+/* explain target (bcad_set_explain_target): which tensor of the last conv block Grad-CAM explains */
+#define BCAD_TARGET_CONV_ACT 0     /* post-LeakyReLU, pre-pool output = layer['output'] / conv_act_grads (explainability.py:64): default */
+#define BCAD_TARGET_CONV_PREACT 1  /* the nn.Conv2d module's own output, before F.leaky_relu: what pytorch_grad_cam captures when it hooks
+                                    * model.convs[-1] of ADCNNM.CNNModel (the activation there is functional, ADCNNM.py:76) */
 /* bcad_get_tensor kinds (cached by the most recent forward of <= max_batch images) */
 #define BCAD_T_CONV_OUT 0          /* layer['output'] of conv block i, NHWC fp32 (Classes/CNNModel.py:169) */
 #define BCAD_T_POOL_OUT 1          /* layer['output'] of pool block i, NHWC fp32 (:174) */
@@ -262,6 +266,8 @@ BCAD_API int bcad_get_conv_weights(bcad_model* m, int conv_idx, float* filters_f
 BCAD_API int bcad_get_dense_weights(bcad_model* m, int dense_idx, float* w_units_in_host, float* bias_host);
 
 /* ---- introspection ---------------------------------------------------------------------------- */
+/* Grad-CAM target tensor for the following explain calls of this handle (BCAD_TARGET_*; fp32 path only for CONV_PREACT) */
+BCAD_API int bcad_set_explain_target(bcad_model* m, int target);
 /* refinement counters since creation (cfg.refine_margin > 0): images re-run at fp32 grade, flagged images that did not fit
  * cfg.refine_capacity (kept their 16-bit result).  Synchronises the device.  Both 0 when refinement is off. */
 BCAD_API int bcad_refine_stats(bcad_model* m, int64_t* refined, int64_t* overflowed);

@@ -234,3 +234,40 @@ def test_sharded_engine_equals_single_gpu():
     np.testing.assert_allclose(heat, h1, rtol=0, atol=1e-5)
     sh.close()
     one.close()
+
+
+@pytest.mark.parametrize("flavour,kind", [("torch", "gauss"), ("numpy", "mammo")])
+def test_gradcam_on_the_pre_activation_conv_output(flavour, kind):
+    """target="conv_preact": what pytorch_grad_cam captures when it hooks ``model.convs[-1]`` of the reference's torch CNN -- the
+    nn.Conv2d output BEFORE the functional F.leaky_relu (ADCNNM.py:76).  Oracle: z = a > 0 ? a : a / slope recovered from the
+    post-activation map, dz = dA * LeakyReLU'(z), same tail.  fp32 engine, both pool-tie rules."""
+    import bcad_b200
+    from oracle import gradcam as ogc
+    mk = ocnn.NetConfig.numpy_flavour if flavour == "numpy" else ocnn.NetConfig.torch_flavour
+    cfg = mk((40, 36, 1), 2, [(8, 3), (16, 3)], [24, 12], 0.05)
+    p = ocnn.init_params(cfg, seed=12, bias_std=0.05)
+    x = ocnn.synth_images(5, (40, 36, 1), seed=9, kind=kind)
+    eng = engine_from(cfg, p, max_batch=8)
+    eng.set_explain_target("conv_preact")
+    ci = np.array([0, 1, 1, 0, 1])
+    cls, probs, logits, heat = eng.predict_explain(x, ci, "logit")
+    cache = ocnn.forward(cfg, p, x)
+    cag, _, _ = ocnn.backward(cfg, p, cache, ocnn.top_gradient(cache, ci, "logit"), through_input=False)
+    A = cache.conv_out[1].numpy()
+    slope = cfg.alpha_conv
+    Z = np.where(A > 0, A, A / slope).astype(np.float32)
+    dZ = (cag[1].numpy() * np.where(A > 0, 1.0, slope)).astype(np.float32)
+    want = ogc.gradcam_tail_nhwc(Z, dZ, (40, 36))
+    np.testing.assert_allclose(_np(heat), want, rtol=0, atol=FP32_TOL)
+    eng.set_explain_target("conv")
+    _, _, _, heat_act = eng.predict_explain(x, ci, "logit")
+    _, _, _, _, o_heat = oracle_heatmaps(cfg, p, x, ci, "logit")
+    np.testing.assert_allclose(_np(heat_act), o_heat, rtol=0, atol=FP32_TOL)
+    assert np.abs(_np(heat_act) - want).max() > 1e-3                     # the two targets really differ
+    eng.close()
+    from util import spec_from_cfg
+    if flavour == "torch":
+        t = bcad_b200.Engine(spec_from_cfg(ocnn.NetConfig.torch_flavour((32, 32, 1), 2, [(32, 3), (64, 3)], [32], 0.01)), precision="fp16")
+        with pytest.raises(ValueError, match="fp32 path"):
+            t.set_explain_target("conv_preact")
+        t.close()

@@ -133,9 +133,29 @@ class CNNModel(nn.Module):
         cls, probs, _ = self.engine.predict(x)
         return cls.long(), probs
 
-    def predict_explain_batch(self, x, class_idx=None, grad_mode="logit"):
-        """-> (classes [B], logits [B,nc], Grad-CAM heatmaps fp32 [B,H,W]) on the GPU."""
-        cls, probs, logits, heat = self.engine.predict_explain(x, class_idx, grad_mode)
+    def predict_explain_batch(self, x, class_idx=None, grad_mode="logit", target="conv"):
+        """-> (classes [B], logits [B,nc], Grad-CAM heatmaps fp32 [B,H,W]) on the GPU.
+        ``target="conv"``: the last block's post-LeakyReLU map (default).  ``target="conv_preact"``: the ``nn.Conv2d`` module's own
+        output -- what ``GradCAM(model, target_layers=[model.convs[-1]])`` of pytorch_grad_cam would hook on the reference model,
+        whose activation is functional (ADCNNM.py:76); runs on an fp32 handle (it needs the dense pooled gradient)."""
+        if target == "conv":
+            cls, probs, logits, heat = self.engine.predict_explain(x, class_idx, grad_mode)
+            return cls.long(), logits, heat
+        if target != "conv_preact":
+            raise ValueError(f"unknown target {target!r} (conv | conv_preact)")
+        ver = self._param_versions()
+        if self._train_eng is None:
+            self._train_eng = Engine(self._spec, precision="fp32", max_batch=self._max_batch, device=self._device_index)
+            self._train_versions = None
+        if ver != self._train_versions:
+            self._train_eng.set_weights(*self._host_weights())
+            self._train_versions = ver
+        eng = self._train_eng
+        eng.set_explain_target("conv_preact")
+        try:
+            cls, probs, logits, heat = eng.predict_explain(x, class_idx, grad_mode)
+        finally:
+            eng.set_explain_target("conv")
         return cls.long(), logits, heat
 
 

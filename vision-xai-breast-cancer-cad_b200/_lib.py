@@ -19,6 +19,7 @@ TIES = {"dup": 0, "all": 0, "first": 1}
 HEAD = {"softmax": 0, "logits": 1}
 PRECISION = {"fp32": 0, "fp16": 1, "fp16x3": 2}
 GRAD_MODE = {"logit": 0, "softmax_ce": 1}
+TARGET = {"conv": 0, "conv_act": 0, "conv_preact": 1}
 T_CONV_OUT, T_POOL_OUT, T_DENSE_Z, T_ALPHA, T_CAM_LOWRES = 0, 1, 2, 3, 4
 
 
@@ -83,6 +84,7 @@ _SIGNATURES = {
     "bcad_apply_update": (C.c_int, [_P, _P, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _P]),
     "bcad_get_conv_weights": (C.c_int, [_P, C.c_int, _P, _P]),
     "bcad_get_dense_weights": (C.c_int, [_P, C.c_int, _P, _P]),
+    "bcad_set_explain_target": (C.c_int, [_P, C.c_int]),
     "bcad_refine_stats": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "bcad_launch_count": (C.c_int64, [_P]),
     "bcad_uses_tensor_path": (C.c_int, [_P]),

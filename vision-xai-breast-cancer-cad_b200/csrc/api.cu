@@ -486,8 +486,9 @@ int dense_backward(Model* m, int n, const int32_t* class_idx, int grad_mode, flo
 static int tail_chunk(Model* m, const void* A, int a_dtype, int n, float* heat, cudaStream_t s) {
     const ConvLayer& T = m->conv.back();
     const float inv_hw = 1.0f / ((float)T.Ho * (float)T.Wo);
+    const float inv_slope = (m->target == BCAD_TARGET_CONV_PREACT) ? 1.0f / m->cfg.alpha_conv : 0.f;
     BCAD_LAUNCH(m, "cam", launch_cam(A, a_dtype, m->alpha_part, m->alpha_splits, inv_hw, m->alpha, m->cam_lo, m->mm, n, T.Ho,
-                              T.Wo, T.Cout, m->cam_splits, s));
+                              T.Wo, T.Cout, m->cam_splits, s, inv_slope));
     BCAD_LAUNCH(m, "upsample_norm", launch_upsample_norm(m->cam_lo, m->mm, m->cam_splits, heat, n, T.Ho, T.Wo, m->heat_h, m->heat_w, s));
     return BCAD_OK;
 }
@@ -503,7 +504,7 @@ static int explain_chunk_fp32(Model* m, int n, const int32_t* class_idx, int gra
         BCAD_TRY(dense_backward(m, n, class_idx, grad_mode, m->g_flat, s));
     }
     BCAD_LAUNCH(m, "alpha_from_pool_grad", launch_alpha_from_pool_grad(m->g_flat, T.y, m->alpha_part, n, T.Ho, T.Wo, T.Cout, m->cfg.pool_ties,
-                                               m->alpha_splits, s));
+                                               m->alpha_splits, s, m->target == BCAD_TARGET_CONV_PREACT ? m->cfg.alpha_conv : -1.f));
     BCAD_TRY(tail_chunk(m, T.y, 0, n, heat, s));
     return BCAD_OK;
 }
@@ -978,6 +979,20 @@ int bcad_bottleneck_resize(const float* feat_dev, int B, int C, int H, int W, in
 int bcad_avg_pool(const float* x, int B, int H, int W, int C, int pool, float* out, void* stream) {
     BCAD_REQUIRE(x && out && B >= 1 && H >= 1 && W >= 1 && C >= 1 && pool >= 1, "avg_pool: bad argument");
     return launch_avg_pool(x, out, B, H, W, C, pool, (cudaStream_t)stream);
+}
+
+int bcad_set_explain_target(bcad_model* mm, int target) {
+    Model* m = reinterpret_cast<Model*>(mm);
+    BCAD_REQUIRE(m, "null model");
+    BCAD_REQUIRE(target == BCAD_TARGET_CONV_ACT || target == BCAD_TARGET_CONV_PREACT, "bad explain target %d", target);
+    if (target == BCAD_TARGET_CONV_PREACT) {
+        BCAD_REQUIRE(!m->tensor_path, "the pre-activation target needs the dense pooled gradient, which only the fp32 path forms: create the model "
+                                      "with BCAD_PREC_FP32 (the tensor paths derive the channel weights from dz1 and never build it)");
+        BCAD_REQUIRE(m->cfg.alpha_conv > 0.f, "the pre-activation map is recovered from the stored post-LeakyReLU map: needs alpha_conv > 0");
+    }
+    std::lock_guard<std::mutex> lock(m->mu);
+    m->target = target;
+    return BCAD_OK;
 }
 
 int bcad_refine_stats(bcad_model* mm, int64_t* refined, int64_t* overflowed) {

@@ -36,8 +36,9 @@ int launch_unpool(const float* g, const float* y, float* dy, int B, int Ho, int 
                   cudaStream_t s);
 // alpha partials from the pooled gradient (+ tie counts from y when ties==ALL): [B][splits][C]
 int alpha_pool_splits(int Hp);
+// pre_slope >= 0: gradients w.r.t. the PRE-activation map (routed gradient x LeakyReLU' at the window maximum)
 int launch_alpha_from_pool_grad(const float* g, const float* y, float* alpha_part, int B, int Ho, int Wo,
-                                int C, int ties, int splits, cudaStream_t s);
+                                int C, int ties, int splits, cudaStream_t s, float pre_slope = -1.f);
 // alpha partials from a dense gradient map (fp32 or bf16 NHWC): [B][splits][C]
 int launch_alpha_from_dense_grad(const void* dA, int dtype, float* alpha_part, int B, int h, int w, int C,
                                  int splits, cudaStream_t s);
@@ -46,7 +47,7 @@ int launch_alpha_from_dense_grad(const void* dA, int dtype, float* alpha_part, i
 int cam_splits(int h);
 int launch_cam(const void* A, int dtype, const float* alpha_part, int alpha_splits, float inv_hw,
                float* alpha_out, float* cam_lo, float* mm, int B, int h, int w, int C, int splits,
-               cudaStream_t s);
+               cudaStream_t s, float inv_slope = 0.f);       // inv_slope > 0 (fp32 A): undo the LeakyReLU first (pre-activation target)
 int launch_upsample_norm(const float* cam_lo, const float* mm, int mm_splits, float* out, int B, int h,
                          int w, int H, int W, cudaStream_t s);
 // non-overlapping mean pool, floor dims (Classes/ImageSegmentation.py:145-163)

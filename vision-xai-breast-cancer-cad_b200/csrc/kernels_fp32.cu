@@ -462,9 +462,11 @@ int launch_unpool(const float* g, const float* y, float* dy, int B, int Ho, int 
 //   (#routed = 1 for TIES_FIRST, number of maxima for TIES_ALL)
 // grid (splits, B); block 256 = CL channel lanes x (256/CL) pixel lanes
 // =====================================================================================================
+// pre_slope >= 0: the target is the conv block's PRE-activation output (what a hook on the nn.Conv2d module captures,
+// ADCNNM.py:76): the routed gradient is also multiplied by LeakyReLU'(z) at the maximum = (max > 0 ? 1 : pre_slope).
 __global__ void alpha_from_pool_grad_kernel(const float* __restrict__ g, const float* __restrict__ y,
                                             float* __restrict__ alpha_part, int Ho, int Wo, int C, int ties,
-                                            int CL) {
+                                            int CL, float pre_slope) {
     extern __shared__ float red[];                     // [256/CL][CL]
     const int Hp = Ho / 2, Wp = Wo / 2;
     const int b = blockIdx.y, split = blockIdx.x, splits = gridDim.x;
@@ -477,12 +479,12 @@ __global__ void alpha_from_pool_grad_kernel(const float* __restrict__ g, const f
         for (int wy = r0; wy < r1 && c < C; ++wy)
             for (int wx = pl; wx < Wp; wx += PL) {
                 float gv = g[(((size_t)b * Hp + wy) * Wp + wx) * C + c];
-                if (ties == BCAD_TIES_ALL) {
+                if (ties == BCAD_TIES_ALL || pre_slope >= 0.f) {
                     const float* yp = y + (((size_t)b * Ho + 2 * wy) * Wo + 2 * wx) * C + c;
                     const float v0 = yp[0], v1 = yp[C], v2 = yp[(size_t)Wo * C], v3 = yp[(size_t)Wo * C + C];
                     const float m = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
-                    const int cnt = (v0 == m) + (v1 == m) + (v2 == m) + (v3 == m);
-                    gv *= (float)cnt;
+                    if (ties == BCAD_TIES_ALL) gv *= (float)((v0 == m) + (v1 == m) + (v2 == m) + (v3 == m));
+                    if (pre_slope >= 0.f && !(m > 0.f)) gv *= pre_slope;
                 }
                 acc += gv;
             }
@@ -506,10 +508,10 @@ static int pick_channel_lanes(int C) {
 }
 
 int launch_alpha_from_pool_grad(const float* g, const float* y, float* alpha_part, int B, int Ho, int Wo, int C,
-                                int ties, int splits, cudaStream_t s) {
+                                int ties, int splits, cudaStream_t s, float pre_slope) {
     const int CL = pick_channel_lanes(C);
     dim3 grid(splits, B);
-    alpha_from_pool_grad_kernel<<<grid, 256, 256 * sizeof(float), s>>>(g, y, alpha_part, Ho, Wo, C, ties, CL);
+    alpha_from_pool_grad_kernel<<<grid, 256, 256 * sizeof(float), s>>>(g, y, alpha_part, Ho, Wo, C, ties, CL, pre_slope);
     BCAD_CUDA_CHECK(cudaGetLastError());
     return BCAD_OK;
 }
@@ -611,7 +613,8 @@ template <bool BF16>
 __global__ void __launch_bounds__(256)
 cam_kernel(const void* __restrict__ A, const float* __restrict__ alpha_part, int alpha_splits, float inv_hw,
            float* __restrict__ alpha_out, float* __restrict__ cam_lo, float* __restrict__ mm, int h, int w, int C,
-           int LP, int vec) {
+           int LP, int vec, float inv_slope) {
+    // inv_slope > 0 (fp32 maps only): A holds post-LeakyReLU values and the target is the PRE-activation map: z = a > 0 ? a : a / slope
     extern __shared__ float s_alpha[];                 // [C] then [16] reduction scratch
     __shared__ float s_min[8], s_max[8];
     const int b = blockIdx.y, split = blockIdx.x, splits = gridDim.x;
@@ -647,8 +650,13 @@ cam_kernel(const void* __restrict__ A, const float* __restrict__ alpha_part, int
                         acc = fmaf(bf16lo(q.z), al[4], acc); acc = fmaf(bf16hi(q.z), al[5], acc);
                         acc = fmaf(bf16lo(q.w), al[6], acc); acc = fmaf(bf16hi(q.w), al[7], acc);
                     } else {
-                        acc = fmaf(__uint_as_float(q.x), al[0], acc); acc = fmaf(__uint_as_float(q.y), al[1], acc);
-                        acc = fmaf(__uint_as_float(q.z), al[2], acc); acc = fmaf(__uint_as_float(q.w), al[3], acc);
+                        float a0 = __uint_as_float(q.x), a1 = __uint_as_float(q.y), a2 = __uint_as_float(q.z), a3 = __uint_as_float(q.w);
+                        if (inv_slope > 0.f) {
+                            a0 = a0 > 0.f ? a0 : a0 * inv_slope; a1 = a1 > 0.f ? a1 : a1 * inv_slope;
+                            a2 = a2 > 0.f ? a2 : a2 * inv_slope; a3 = a3 > 0.f ? a3 : a3 * inv_slope;
+                        }
+                        acc = fmaf(a0, al[0], acc); acc = fmaf(a1, al[1], acc);
+                        acc = fmaf(a2, al[2], acc); acc = fmaf(a3, al[3], acc);
                     }
                 }
             for (int o = LP >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -666,6 +674,7 @@ cam_kernel(const void* __restrict__ A, const float* __restrict__ alpha_part, int
                 float a;
                 if (BF16) a = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(A)[((size_t)b * npix + p) * C + c]);
                 else a = reinterpret_cast<const float*>(A)[((size_t)b * npix + p) * C + c];
+                if (!BF16 && inv_slope > 0.f && !(a > 0.f)) a *= inv_slope;
                 acc = fmaf(a, s_alpha[c], acc);
             }
             acc = fmaxf(acc, 0.f);
@@ -688,15 +697,15 @@ cam_kernel(const void* __restrict__ A, const float* __restrict__ alpha_part, int
 int cam_splits(int h) { return h >= 64 ? 8 : (h >= 16 ? 2 : 1); }
 
 int launch_cam(const void* A, int dtype, const float* alpha_part, int alpha_splits, float inv_hw, float* alpha_out,
-               float* cam_lo, float* mm, int B, int h, int w, int C, int splits, cudaStream_t s) {
+               float* cam_lo, float* mm, int B, int h, int w, int C, int splits, cudaStream_t s, float inv_slope) {
     const int epv = dtype == 1 ? 8 : 4;
     const int vec = (C % epv == 0) ? 1 : 0;
     int LP = 1;
     if (vec) { while (LP < C / epv && LP < 32) LP <<= 1; }
     dim3 grid(splits, B);
     const size_t smem = (size_t)C * sizeof(float);
-    if (dtype == 1) cam_kernel<true><<<grid, 256, smem, s>>>(A, alpha_part, alpha_splits, inv_hw, alpha_out, cam_lo, mm, h, w, C, LP, vec);
-    else cam_kernel<false><<<grid, 256, smem, s>>>(A, alpha_part, alpha_splits, inv_hw, alpha_out, cam_lo, mm, h, w, C, LP, vec);
+    if (dtype == 1) cam_kernel<true><<<grid, 256, smem, s>>>(A, alpha_part, alpha_splits, inv_hw, alpha_out, cam_lo, mm, h, w, C, LP, vec, 0.f);
+    else cam_kernel<false><<<grid, 256, smem, s>>>(A, alpha_part, alpha_splits, inv_hw, alpha_out, cam_lo, mm, h, w, C, LP, vec, inv_slope);
     BCAD_CUDA_CHECK(cudaGetLastError());
     return BCAD_OK;
 }

@@ -111,6 +111,7 @@ struct Model {
     std::mutex mu;
     std::mutex host_mu;                 // serialises the host-buffer calls of one handle (shared staging, streams, events)
     Refine refine;
+    int target = BCAD_TARGET_CONV_ACT;  // bcad_set_explain_target
     int heat_h = 0, heat_w = 0;         // heat-map size of the call in flight (in_h x in_w unless bcad_predict_explain_sized asks otherwise)
     const int32_t* n_dev = nullptr;     // refinement TWIN only: device pointer to the live image count of its launches
     std::vector<void*> allocs;

@@ -123,6 +123,7 @@ class Engine:
         #: whoever fills the handle's activation cache for later reads (the mirrors' lazy ``layers[*]`` getters, explain_backward)
         #: stamps it here; every forward of this engine resets it, so a stale read is detectable instead of silently wrong
         self.cache_tag = None
+        self.explain_target = "conv"
 
     # ------------------------------------------------------------------ lifetime / weights
     def close(self):
@@ -185,6 +186,13 @@ class Engine:
     @property
     def launch_count(self) -> int:
         return int(self.lib.bcad_launch_count(self._h))
+
+    def set_explain_target(self, target: str = "conv"):
+        """"conv": the last conv block's post-LeakyReLU output (default; explainability.py:64).  "conv_preact": the conv module's own
+        output before the activation -- what pytorch_grad_cam sees when it hooks ``model.convs[-1]`` of ADCNNM.CNNModel (ADCNNM.py:76);
+        fp32 engines only."""
+        _lib.check(self.lib.bcad_set_explain_target(self._h, _lib.TARGET[target]))
+        self.explain_target = target
 
     def refine_stats(self):
         """(images re-run at fp32 grade, flagged images beyond ``refine_capacity``) since creation; synchronises."""
