@@ -394,7 +394,7 @@ def run_ours(args, rank, world, local_rank):
         # the same step with the two conv blocks as separate kernels (the fused kernel is the production default because the
         # whole step is faster; the stand-alone second block is the cleaner tensor-core roofline point)
         prof2 = {}
-        if rank == 0 and any("conv01" in k for k in prof) and "BCAD_TWO_CONV_KERNELS" not in os.environ:
+        if rank == 0 and any("conv01" in k for k in prof) and "BCAD_TWO_CONV_KERNELS" not in os.environ and not args.only_value:
             os.environ["BCAD_TWO_CONV_KERNELS"] = "1"
             try:
                 for _ in range(nprof):
@@ -407,6 +407,10 @@ def run_ours(args, rank, world, local_rank):
                 del os.environ["BCAD_TWO_CONV_KERNELS"]
         e.set_profiling(False)
         r["prof"], r["prof2"] = prof, prof2
+        if args.only_value:                       # profiling runs (ncu): the device-resident leg only
+            r["clocks"] = sampler.stop() if rank == 0 else None
+            r["e2e_ms"] = r["e2e_u8_ms"] = r["e2e_u8io_ms"] = float("nan")
+            return r
         # ---- end to end through the host-buffer C-ABI call (e2e)
         for _ in range(max(1, min(args.warmup, 3))):
             step_host()
@@ -501,9 +505,9 @@ def run_ours(args, rank, world, local_rank):
                        "bcad_gradcam_overlays_host call per step"}
 
     main = measure(eng)
-    ceiling_gbs, ceiling_ms = host_copy_probe()
+    ceiling_gbs, ceiling_ms = (float("nan"), float("nan")) if args.only_value else host_copy_probe()
     api = None
-    if FLAVOUR == "torch" and INPUT_SHAPE[2] == 1 and not args.no_api:
+    if FLAVOUR == "torch" and INPUT_SHAPE[2] == 1 and not args.no_api and not args.only_value:
         try:
             api = measure_api()
         except Exception as e:                                      # the API leg must not take the headline down with it
@@ -1092,6 +1096,7 @@ def main():
     ap.add_argument("--check-images", type=int, default=256, help="images of the batch compared one by one with the oracle (untimed)")
     ap.add_argument("--refine-margin", type=float, default=None, help="fp16 path: top-2 logit gap below which an image is re-run at fp32 "
                                                                     "grade (default: the engine's; 0 switches the refinement off)")
+    ap.add_argument("--only-value", action="store_true", help="device-resident leg only (for runs under ncu)")
     ap.add_argument("--no-api", action="store_true", help="skip the e2e_api leg (the mirrors' Python surface)")
     ap.add_argument("--no-fp32-grade", action="store_true", help="skip the second measurement of the workload in fp16x3 mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
