@@ -285,7 +285,8 @@ BCAD_API int bcad_profile_get(bcad_model* m, int i, char* name_buf, int name_cap
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 /* One 128 x N x (16*steps) tcgen05 UMMA problem on caller-provided shared-memory operand images and descriptor
  * fields; used by tests/test_gpu_sm100.py to pin the descriptor conventions the tensor path relies on.
- * params_host: int32 {N, steps, a_lbo, a_sbo, a_layout, b_lbo, b_sbo, b_layout, a_koff[64], b_koff[64]}. */
+ * params_host: int32 {N, steps, a_lbo, a_sbo, a_layout, b_lbo, b_sbo, b_layout, a_koff[64], b_koff[64], mode}; mode 0: bf16
+ * operands, d_dev fp32 [128][N]; mode 1: fp16 operands, FP16 accumulators, d_dev = the raw 32-bit TMEM cells [128][N/2]. */
 BCAD_API int bcad_selftest_umma(const void* a_img_dev, int a_bytes, const void* b_img_dev, int b_bytes,
                        const int32_t* params_host, float* d_dev, void* stream);
 

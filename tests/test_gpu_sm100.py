@@ -32,16 +32,17 @@ def image_sw128(X: torch.Tensor) -> np.ndarray:
     return np.ascontiguousarray(out)
 
 
-def run_umma(a_img, b_img, N, steps, a_lbo, a_sbo, a_layout, b_lbo, b_sbo, b_layout, a_koff, b_koff):
+def run_umma(a_img, b_img, N, steps, a_lbo, a_sbo, a_layout, b_lbo, b_sbo, b_layout, a_koff, b_koff, mode=0):
     import bcad_b200
     lib = bcad_b200._lib.load()
-    params = np.zeros(8 + 128, np.int32)
+    params = np.zeros(8 + 128 + 1, np.int32)
     params[:8] = [N, steps, a_lbo, a_sbo, a_layout, b_lbo, b_sbo, b_layout]
     params[8:8 + steps] = a_koff
     params[72:72 + steps] = b_koff
+    params[136] = mode
     a_dev = torch.from_numpy(a_img.view(np.int16).reshape(-1).copy()).cuda()
     b_dev = torch.from_numpy(b_img.view(np.int16).reshape(-1).copy()).cuda()
-    d = torch.full((128, N), float("nan"), device="cuda")
+    d = torch.full((128, N if mode == 0 else N // 2), float("nan"), device="cuda")
     rc = lib.bcad_selftest_umma(C.c_void_p(a_dev.data_ptr()), a_dev.numel() * 2, C.c_void_p(b_dev.data_ptr()),
                                 b_dev.numel() * 2, C.c_void_p(params.ctypes.data), C.c_void_p(d.data_ptr()), None)
     bcad_b200._lib.check(rc)
@@ -84,3 +85,24 @@ def test_sw128_kmajor_k_advance(N, K):
     want = A.float() @ B.float().T
     err = (got - want).abs().max().item()
     assert err <= 1e-3 * max(1.0, want.abs().max().item()), f"max err {err}"
+
+
+@pytest.mark.parametrize("N", [32, 64, 128])
+def test_fp16_accumulators_still_take_one_tmem_column_each(N):
+    """kind::f16 with D format F16: measured here because a packed layout (two accumulators per 32-bit TMEM cell) would have let the
+    fused conv kernel's first block run all four pool classes in one pass.  It is NOT packed: accumulator n sits alone in the low
+    half of column n, so half-precision accumulators save no tensor memory.  Values = the fp32 product sum
+    rounded to fp16."""
+    g = torch.Generator().manual_seed(N)
+    A = torch.randn(128, 16, generator=g).to(torch.float16)
+    B = torch.randn(N, 16, generator=g).to(torch.float16)
+
+    def img(X):
+        R, K = X.shape
+        return np.ascontiguousarray(X.view(torch.int16).numpy().astype(np.uint16).reshape(R, K // 8, 8).transpose(1, 0, 2))
+    got = run_umma(img(A), img(B), N, 1, 128 * 16, 128, LAYOUT_NONE, N * 16, 128, LAYOUT_NONE, [0], [0], mode=1)
+    cells = got.numpy().view(np.uint32)                                   # the first N/2 columns, raw
+    lo = (cells & 0xFFFF).astype(np.uint16).view(np.float16).astype(np.float32)
+    want = (A.float() @ B.float().T).numpy().astype(np.float16).astype(np.float32)[:, :N // 2]
+    ulp = np.maximum(np.abs(want), 2.0 ** -14) * 2.0 ** -10
+    assert np.all(np.abs(lo - want) <= ulp)

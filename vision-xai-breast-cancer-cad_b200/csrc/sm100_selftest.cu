@@ -11,6 +11,8 @@ struct SelftestParams {
     int N, steps;
     int a_lbo, a_sbo, a_layout, b_lbo, b_sbo, b_layout;
     int a_koff[64], b_koff[64];
+    int mode;      // 0: bf16 operands, fp32 accumulators -> D fp32 [128][N];  1: fp16 operands, FP16 accumulators -> the raw 32-bit TMEM
+                   //    cells [128][N/2] (pins how tcgen05 packs half-precision accumulators: two per column)
 };
 
 __global__ void __launch_bounds__(128, 1)
@@ -39,7 +41,7 @@ umma_selftest_kernel(const uint4* __restrict__ a_img, int a_bytes, const uint4* 
     tc_fence_after();
     const uint32_t tmem = tmem_base;
     if (tid == 0) {
-        const uint32_t idesc = make_idesc_bf16(128, p.N);
+        const uint32_t idesc = p.mode == 1 ? (make_idesc_f16(128, p.N) & ~(1u << 4)) : make_idesc_bf16(128, p.N);     // D format 0 = F16
         for (int k = 0; k < p.steps; ++k) {
             const uint64_t ad = make_smem_desc(smem_u32(sa) + p.a_koff[k], p.a_lbo, p.a_sbo, p.a_layout);
             const uint64_t bd = make_smem_desc(smem_u32(sb) + p.b_koff[k], p.b_lbo, p.b_sbo, p.b_layout);
@@ -49,6 +51,17 @@ umma_selftest_kernel(const uint4* __restrict__ a_img, int a_bytes, const uint4* 
     }
     mbar_wait(&bar, 0);
     tc_fence_after();
+    if (p.mode == 1) {
+        for (int c0 = 0; c0 < p.N / 2; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+            tmem_ld_wait();
+            const int row = warp * 32 + (tid & 31);
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (c0 + j < p.N / 2) D[(size_t)row * (p.N / 2) + c0 + j] = v[j];
+        }
+    } else
     for (int c0 = 0; c0 < p.N; c0 += 32) {
         float v[32];
         tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
@@ -177,6 +190,7 @@ extern "C" int bcad_selftest_umma(const void* a_img_dev, int a_bytes, const void
     SelftestParams p;
     memcpy(&p, params_host, sizeof(p));
     BCAD_REQUIRE(p.N >= 16 && p.N <= 256 && p.N % 16 == 0 && p.steps >= 1 && p.steps <= 64, "selftest: bad N/steps");
+    BCAD_REQUIRE(p.mode == 0 || (p.mode == 1 && p.N % 32 == 0), "selftest: mode must be 0, or 1 with N a multiple of 32");
     const size_t smem = ((size_t)(a_bytes + 1023) / 1024) * 1024 + b_bytes + 1024;
     BCAD_REQUIRE(smem <= 200 * 1024, "selftest: operand images too large");
     BCAD_CUDA_CHECK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
