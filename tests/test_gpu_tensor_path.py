@@ -137,6 +137,41 @@ def test_tensor_path_multichannel_first_block(shape, convs, pad, B):
     eng.close()
 
 
+@pytest.mark.parametrize("shape,pad,B", [
+    ((32, 40, 3), 1, 5),          # RGB-like: 3 channels padded to one 16-channel group, x 3 virtual passes
+    ((24, 24, 64), 1, 4),         # "(H,W,64)" bottleneck features
+    ((16, 48, 256), 1, 3),        # the deployed model's literal shape family: 256 channels = 8 groups x 3 passes in TMEM
+    ((20, 20, 48), 1, 4),
+    ((12, 300, 32), 1, 3),        # wide map: 3 segments in the first block
+    ((21, 23, 16), 0, 4),         # valid conv, odd sizes
+    ((38, 20, 64), 1, 150),       # more work items than SMs
+])
+def test_fp16x3_multichannel_first_block_is_fp32_grade(shape, pad, B):
+    """fp16x3 for multi-channel inputs (the deployed [64,256,256] classifier, app.py:584): the first block runs the plain
+    channel-grouped kernel over 3 x Cin virtual channels -- inputs [x_hi | x_lo | x_hi] against weights [w_hi | w_hi | w_lo] -- and
+    writes its pooled map as hi + lo halves for the split-operand second block.  fp32-grade: logits 2e-4, heat-maps 5e-4."""
+    from bcad_b200 import _lib
+    cfg = ocnn.NetConfig(shape, 2, [(32, 3), (64, 3)], [32, 16], 0.01, 0.01, pad, "chw", "first", "logits")
+    p = ocnn.init_params(cfg, seed=13, bias_std=0.05)
+    x = ocnn.synth_images(B, shape, seed=8)
+    eng = engine_from(cfg, p, precision="fp16x3", max_batch=max(8, B))
+    assert eng.uses_tensor_path
+    k = min(4, B)
+    cache = ocnn.forward(cfg, p, x[:k])
+    eng.predict(x[:k])
+    h1, w1 = cache.pool_out[0].shape[1:3]
+    p1 = _np(eng.get_tensor(_lib.T_POOL_OUT, 0, k)).reshape(k, h1, w1, 32)
+    want = cache.pool_out[0].numpy()
+    assert np.abs(p1 - want).max() <= 1e-4 * max(1.0, np.abs(want).max()), "first block (split operands)"
+    _check_x3(cfg, p, x, eng, [(None, "logit"), (np.arange(B) % 2, "softmax_ce")])
+    eng.close()
+    # and the 16-bit engine of the same network now refines small-margin images through this twin
+    e16 = engine_from(cfg, p, precision="fp16", max_batch=max(8, B))
+    assert e16.refine_margin > 0
+    _check(cfg, p, x, e16, B)
+    e16.close()
+
+
 def test_fused_and_two_kernel_conv_paths_agree(monkeypatch):
     """The fused two-block kernel (default) and the conv0 + conv1 kernels compute the same network: logits and heat-maps agree
     to fp16 rounding of the pooled first-block map (max-then-round vs round-then-max, LeakyReLU in half2), and the fused
@@ -236,8 +271,8 @@ def test_tensor_path_rejects_unsupported_shapes():
     cfg = ocnn.NetConfig.numpy_flavour((32, 32, 1), 2, [(32, 3), (64, 3)], [32])        # tie-duplicating pool: fp16x3 or fp32 only
     with pytest.raises(ValueError, match="TIES_FIRST"):
         bcad_b200.Engine(spec_from_cfg(cfg), precision="fp16")
-    cfg = ocnn.NetConfig.torch_flavour((32, 32, 3), 2, [(32, 3), (64, 3)], [32])
-    with pytest.raises(ValueError, match="single-channel"):
+    cfg = ocnn.NetConfig.torch_flavour((32, 32, 3), 2, [(64, 3), (64, 3)], [32])
+    with pytest.raises(ValueError, match="32 first-block filters"):
         bcad_b200.Engine(spec_from_cfg(cfg), precision="fp16x3")
     cfg = ocnn.NetConfig.torch_flavour((32, 32, 3), 2, [(16, 3), (64, 3)], [32])
     with pytest.raises(ValueError, match="32 or 64 filters"):

@@ -41,11 +41,15 @@ struct WideArgs {
     int G;                        // channel groups of KC = conv_wide_group_channels(CinPad, Cout) channels
     int ybands, xsegs;            // bands of 256/Cout output rows, 128-pixel segments: work item = (image, band, segment)
     float alpha;
+    int split_out = 0;            // fp16x3: the pooled fp32 value goes out as hi + lo halves, octets [hi 0..Cout/8) | lo 0..Cout/8)
 };
 int conv_wide_group_channels(int CinPad, int Cout);
 int conv_wide_rows_per_band(int Cout);
 int launch_conv_wide(const WideArgs& a, int CinPad, int Cout, int sms, cudaStream_t s);
 int launch_nhwc_to_c8(const float* x, __half* out, int B, int H, int W, int C, int CinPad, cudaStream_t s);
+// fp16x3: 3 * CinPad "virtual" channels, octets [x_hi | x_lo | x_hi]; against weight groups [w_hi | w_hi | w_lo] the plain kernel's
+// fp32 accumulators then hold x_hi.w_hi + x_lo.w_hi + x_hi.w_lo
+int launch_nhwc_to_c8_x3(const float* x, __half* out, int B, int H, int W, int C, int CinPad, cudaStream_t s);
 
 // both conv blocks in one persistent kernel (sm100_fused.cu): Cin = 1 -> 32 -> 64 filters, fp16 mode, maps up to 128 px wide
 struct FusedArgs {

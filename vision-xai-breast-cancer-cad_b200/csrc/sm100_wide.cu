@@ -48,6 +48,49 @@ __global__ void __launch_bounds__(256) nhwc_to_c8_kernel(const float* __restrict
     }
 }
 
+// fp16x3 form: thread = (pixel, REAL channel octet); writes the hi halves to octets o and 2*octets + o, the lo halves to octets + o
+__global__ void __launch_bounds__(256) nhwc_to_c8_x3_kernel(const float* __restrict__ x, __half* __restrict__ out, int W, int C,
+                                                            int octets, size_t rows) {
+    const size_t per_row = (size_t)octets * W;
+    const size_t total = rows * per_row;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t row = i / per_row;
+        const int rem = (int)(i - row * per_row);
+        const int o = rem / W, px = rem - o * W;
+        const float* src = x + (row * W + px) * C + o * 8;
+        float v[8];
+        if (o * 8 + 8 <= C && (C & 3) == 0) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = (o * 8 + e < C) ? __ldg(src + e) : 0.f;
+        }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+            const __half2 h = __floats2half2_rn(v[e], v[e + 1]);
+            const float2 hf = __half22float2(h);
+            hi[e >> 1] = wh2u(h);
+            lo[e >> 1] = pack_f16(v[e] - hf.x, v[e + 1] - hf.y);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out) + (row * 3 * octets + o) * W + px;
+        const uint4 vh = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        dst[0] = vh;
+        dst[(size_t)octets * W] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        dst[(size_t)2 * octets * W] = vh;
+    }
+}
+
+int launch_nhwc_to_c8_x3(const float* x, __half* out, int B, int H, int W, int C, int CinPad, cudaStream_t s) {
+    BCAD_REQUIRE(CinPad % 8 == 0 && CinPad >= C, "nhwc_to_c8_x3: bad channel padding %d for %d", CinPad, C);
+    const size_t total = (size_t)B * H * (CinPad / 8) * W;
+    const int blocks = (int)std::min<size_t>((size_t)148 * 16, (total + 255) / 256);
+    nhwc_to_c8_x3_kernel<<<blocks, 256, 0, s>>>(x, out, W, C, CinPad / 8, (size_t)B * H);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
 int launch_nhwc_to_c8(const float* x, __half* out, int B, int H, int W, int C, int CinPad, cudaStream_t s) {
     BCAD_REQUIRE(CinPad % 8 == 0 && CinPad >= C, "nhwc_to_c8: bad channel padding %d for %d", CinPad, C);
     const size_t total = (size_t)B * H * (CinPad / 8) * W;
@@ -283,6 +326,33 @@ __global__ void __launch_bounds__(WD_THREADS, 1) conv_wide_kernel(WideArgs a) {
                 tmem_ld32(tmem + lane_off + half * 256 + (2 * pair) * COUT + ch * 32, v0);
                 tmem_ld32(tmem + lane_off + half * 256 + (2 * pair + 1) * COUT + ch * 32, v1);
                 tmem_ld_wait();
+                if (a.split_out) {
+                    // fp16x3: LeakyReLU and the pool in fp32, then the pooled value as hi + lo halves (2*COUT virtual channels)
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        const float a0 = fmaxf(v0[q], a.alpha * v0[q]), a1 = fmaxf(v1[q], a.alpha * v1[q]);
+                        const float mv = fmaxf(a0, a1);
+                        v0[q] = fmaxf(mv, __shfl_xor_sync(0xffffffffu, mv, 1));
+                    }
+                    if (pool_ok) {
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {
+                            uint32_t ph[4], pl[4];
+#pragma unroll
+                            for (int e = 0; e < 8; e += 2) {
+                                const float m0 = v0[cc * 8 + e], m1 = v0[cc * 8 + e + 1];
+                                const __half2 h = __floats2half2_rn(m0, m1);
+                                const float2 hf = __half22float2(h);
+                                ph[e >> 1] = wh2u(h);
+                                pl[e >> 1] = pack_f16(m0 - hf.x, m1 - hf.y);
+                            }
+                            uint4* dh = reinterpret_cast<uint4*>(a.pool_c8) + (((size_t)b * a.Hp + py) * (2 * COUT / 8) + ch * 4 + cc) * a.Wp + px;
+                            *dh = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                            *(dh + (size_t)(COUT / 8) * a.Wp) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                        }
+                    }
+                    continue;
+                }
                 __half2 m[16];
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {

@@ -77,7 +77,7 @@ int tensor_path_supported(const Model& m) {
     if (c0.Cin > 1) {
         BCAD_REQUIRE(c0.Cout == 32 || c0.Cout == 64, "precision=F16: a multi-channel first conv block needs 32 or 64 filters (got %d)", c0.Cout);
         BCAD_REQUIRE(c0.Cin <= 1024, "precision=F16: first conv block with %d input channels (max 1024)", c0.Cin);
-        BCAD_REQUIRE(c.precision != BCAD_PREC_F16X3, "precision=F16X3 covers single-channel inputs; use BCAD_PREC_F16 or BCAD_PREC_FP32 for %d channels", c0.Cin);
+        BCAD_REQUIRE(c.precision != BCAD_PREC_F16X3 || c0.Cin <= 512, "precision=F16X3: first conv block with %d input channels (max 512)", c0.Cin);
     }
     BCAD_REQUIRE(c1.k == 3 && c1.Cout == 64, "precision=F16: second conv block must be 3x3 with 64 filters (got k=%d, %d)", c1.k, c1.Cout);
     BCAD_REQUIRE(c.pad == 0 || c.pad == 1, "precision=F16: pad must be 0 or 1");
@@ -90,7 +90,7 @@ int tensor_path_supported(const Model& m) {
     BCAD_REQUIRE(c.pool_ties == BCAD_TIES_FIRST || m.dense.size() > 1,
                  "precision=F16X3 with the tie-duplicating rule needs at least one hidden dense layer");
     if (c.precision == BCAD_PREC_F16X3)
-        BCAD_REQUIRE(c0.Cin == 1 && c0.Cout == 32, "precision=F16X3: the split-operand path needs 32 first-block filters (got %d)", c0.Cout);
+        BCAD_REQUIRE(c0.Cout == 32, "precision=F16X3: the split-operand path needs 32 first-block filters (got %d)", c0.Cout);
     const int units = m.dense[0].out;
     BCAD_REQUIRE(units % 16 == 0 && units <= 256, "precision=F16: first dense layer must have a multiple of 16 units <= 256 (got %d)", units);
     return BCAD_OK;
@@ -115,24 +115,31 @@ int tensor_path_commit(Model& m) {
         t.groups = t.cin_pad / t.kc;
         const int chunks = t.kc / 8;
         const size_t wg = (size_t)9 * chunks * c0.Cout * 8;                   // halves per group
-        std::vector<uint16_t> img(wg * t.groups + (size_t)2 * c0.Cout * 8, 0);
-        for (int g = 0; g < t.groups; ++g)
-            for (int tap = 0; tap < 9; ++tap)
-                for (int ch = 0; ch < chunks; ++ch)
-                    for (int f = 0; f < c0.Cout; ++f)
-                        for (int e = 0; e < 8; ++e) {
-                            const int cidx = g * t.kc + ch * 8 + e;
-                            if (cidx < c0.Cin)
-                                img[g * wg + (((size_t)tap * chunks + ch) * c0.Cout + f) * 8 + e] = f2h(c0.h_w[((size_t)f * 9 + tap) * c0.Cin + cidx]);
-                        }
+        // fp16x3: three passes over the channel groups -- inputs [x_hi | x_lo | x_hi] (launch_nhwc_to_c8_x3) against weights
+        // [w_hi | w_hi | w_lo]: the plain kernel's fp32 accumulators then hold x_hi.w_hi + x_lo.w_hi + x_hi.w_lo
+        const int parts = t.x3 ? 3 : 1;
+        std::vector<uint16_t> img(wg * t.groups * parts + (size_t)2 * c0.Cout * 8, 0);
+        for (int part = 0; part < parts; ++part)
+            for (int g = 0; g < t.groups; ++g)
+                for (int tap = 0; tap < 9; ++tap)
+                    for (int ch = 0; ch < chunks; ++ch)
+                        for (int f = 0; f < c0.Cout; ++f)
+                            for (int e = 0; e < 8; ++e) {
+                                const int cidx = g * t.kc + ch * 8 + e;
+                                if (cidx >= c0.Cin) continue;
+                                const float w = c0.h_w[((size_t)f * 9 + tap) * c0.Cin + cidx];
+                                const uint16_t q = f2h(w);
+                                img[((size_t)part * t.groups + g) * wg + (((size_t)tap * chunks + ch) * c0.Cout + f) * 8 + e] =
+                                    (part == 2) ? f2h(w - h2f(q)) : q;
+                            }
         for (int f = 0; f < c0.Cout; ++f) {
             const float bhi = h2f(f2h(c0.h_b[f]));
-            img[wg * t.groups + (size_t)f * 8 + 0] = f2h(bhi);
-            img[wg * t.groups + (size_t)f * 8 + 1] = f2h(c0.h_b[f] - bhi);
+            img[wg * t.groups * parts + (size_t)f * 8 + 0] = f2h(bhi);
+            img[wg * t.groups * parts + (size_t)f * 8 + 1] = f2h(c0.h_b[f] - bhi);
         }
         if (!t.d_w0_wide) TP_TRY(m.alloc((void**)&t.d_w0_wide, img.size() * 2));
         BCAD_CUDA_CHECK(cudaMemcpy(t.d_w0_wide, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
-        if (!t.x_c8) TP_TRY(m.alloc((void**)&t.x_c8, (size_t)mb * c0.H * c0.W * t.cin_pad * 2));
+        if (!t.x_c8) TP_TRY(m.alloc((void**)&t.x_c8, (size_t)parts * mb * c0.H * c0.W * t.cin_pad * 2));
     }
     // ---- conv0: [9][Cout] fp32
     if (!t.wide) {
@@ -314,13 +321,16 @@ int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const in
     } else {
     t.p1_valid = true;
     if (t.wide) {
-        TP_LAUNCH(m, "input_to_c8", launch_nhwc_to_c8(x, t.x_c8, n, c0.H, c0.W, c0.Cin, t.cin_pad, s));
+        if (t.x3) TP_LAUNCH(m, "input_to_c8_hi_lo", launch_nhwc_to_c8_x3(x, t.x_c8, n, c0.H, c0.W, c0.Cin, t.cin_pad, s));
+        else TP_LAUNCH(m, "input_to_c8", launch_nhwc_to_c8(x, t.x_c8, n, c0.H, c0.W, c0.Cin, t.cin_pad, s));
+        const int parts = t.x3 ? 3 : 1;
         WideArgs w;
         w.in = t.x_c8; w.w_img = t.d_w0_wide; w.pool_c8 = t.p1;
         w.B = n; w.H = c0.H; w.W = c0.W; w.Ho = c0.Ho; w.Wo = c0.Wo; w.Hp = c0.Hp; w.Wp = c0.Wp; w.pad = m.cfg.pad;
-        w.G = t.groups; w.ybands = cdiv(c0.Ho, conv_wide_rows_per_band(c0.Cout)); w.xsegs = cdiv(c0.Wo, 128);
+        w.G = parts * t.groups; w.ybands = cdiv(c0.Ho, conv_wide_rows_per_band(c0.Cout)); w.xsegs = cdiv(c0.Wo, 128);
         w.alpha = m.cfg.alpha_conv;
-        TP_LAUNCH(m, "conv0_wide_tcgen05", launch_conv_wide(w, t.cin_pad, c0.Cout, t.sms, s));
+        w.split_out = t.x3 ? 1 : 0;
+        TP_LAUNCH(m, "conv0_wide_tcgen05", launch_conv_wide(w, parts * t.cin_pad, c0.Cout, t.sms, s));
     } else if (t.d_w0_img != nullptr && (t.x3 || getenv("BCAD_CONV0_CUDA_CORES") == nullptr))
         TP_LAUNCH(m, "conv0_first_tcgen05", launch_conv_first_tc(x, t.plain0 ? t.d_w0_plain : t.d_w0_img, t.p1, n, c0.H, c0.W, m.cfg.pad, c0.Cout, m.cfg.alpha_conv, t.x3, t.plain0, t.sms, s, m.n_dev));
     else
