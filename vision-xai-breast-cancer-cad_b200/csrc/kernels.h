@@ -49,7 +49,7 @@ int launch_cam(const void* A, int dtype, const float* alpha_part, int alpha_spli
                float* alpha_out, float* cam_lo, float* mm, int B, int h, int w, int C, int splits,
                cudaStream_t s, float inv_slope = 0.f);       // inv_slope > 0 (fp32 A): undo the LeakyReLU first (pre-activation target)
 int launch_upsample_norm(const float* cam_lo, const float* mm, int mm_splits, float* out, int B, int h,
-                         int w, int H, int W, cudaStream_t s);
+                         int w, int H, int W, cudaStream_t s, const int* n_dev = nullptr);   // n_dev: live image count on the device (refine.cu)
 // non-overlapping mean pool, floor dims (Classes/ImageSegmentation.py:145-163)
 int launch_avg_pool(const float* x, float* out, int B, int H, int W, int C, int pool, cudaStream_t s);
 // [k][k][Cin][Cout] -> [k*k][Cin][CoutPad] (zero padded)

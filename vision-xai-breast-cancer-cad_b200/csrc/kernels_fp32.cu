@@ -800,7 +800,8 @@ upsample_norm_kernel(const float* __restrict__ cam_lo, const float* __restrict__
 // shared-memory reads and one lerp; both min-max passes run over that.
 __global__ void __launch_bounds__(UP_THREADS)
 upsample_norm_sep_kernel(const float* __restrict__ cam_lo, const float* __restrict__ mm, int mm_splits,
-                         float* __restrict__ out, int h, int w, int H, int W) {
+                         float* __restrict__ out, int h, int w, int H, int W, const int* __restrict__ n_dev) {
+    if (n_dev != nullptr && (int)blockIdx.x >= *n_dev) return;
     extern __shared__ float sm[];
     __shared__ float s_red[64];
     int* s_x0 = reinterpret_cast<int*>(sm);
@@ -877,14 +878,14 @@ upsample_norm_sep_kernel(const float* __restrict__ cam_lo, const float* __restri
 }
 
 int launch_upsample_norm(const float* cam_lo, const float* mm, int mm_splits, float* out, int B, int h, int w, int H,
-                         int W, cudaStream_t s) {
+                         int W, cudaStream_t s, const int* n_dev) {
     const size_t tables = (size_t)(3 * W + 3 * H) * sizeof(float);
     const size_t lo_bytes = (size_t)h * w * sizeof(float), hr_bytes = (size_t)h * W * sizeof(float);
     if (tables + lo_bytes + hr_bytes <= 220 * 1024) {
         const size_t smem = tables + lo_bytes + hr_bytes;
         if (smem > 48 * 1024)
             BCAD_CUDA_CHECK(cudaFuncSetAttribute(upsample_norm_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        upsample_norm_sep_kernel<<<B, UP_THREADS, smem, s>>>(cam_lo, mm, mm_splits, out, h, w, H, W);
+        upsample_norm_sep_kernel<<<B, UP_THREADS, smem, s>>>(cam_lo, mm, mm_splits, out, h, w, H, W, n_dev);
         BCAD_CUDA_CHECK(cudaGetLastError());
         return BCAD_OK;
     }

@@ -1000,10 +1000,12 @@ int launch_fc_reduce(const float* part, int splits, size_t ld_split, const float
 template <bool X3>
 __global__ void __launch_bounds__(256)
 cam_c8_kernel(const __half* __restrict__ A, const float* __restrict__ alpha_raw, float scale,
-              float* __restrict__ alpha_out, float* __restrict__ cam_lo, float* __restrict__ mm, int h, int w, int C) {
+              float* __restrict__ alpha_out, float* __restrict__ cam_lo, float* __restrict__ mm, int h, int w, int C,
+              const int* __restrict__ n_dev) {
     extern __shared__ float s_alpha[];
     __shared__ float s_min[8], s_max[8];
     const int b = blockIdx.y, split = blockIdx.x, splits = gridDim.x;
+    if (n_dev != nullptr && b >= *n_dev) return;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const float t = alpha_raw[(size_t)b * C + c] * scale;
         s_alpha[c] = t;
@@ -1052,10 +1054,10 @@ cam_c8_kernel(const __half* __restrict__ A, const float* __restrict__ alpha_raw,
 }
 
 int launch_cam_c8(const __half* A, const float* alpha_raw, float scale, float* alpha_out, float* cam_lo, float* mm,
-                  int B, int h, int w, int C, int splits, bool x3, cudaStream_t s) {
+                  int B, int h, int w, int C, int splits, bool x3, cudaStream_t s, const int* n_dev) {
     dim3 grid(splits, B);
-    if (x3) cam_c8_kernel<true><<<grid, 256, C * sizeof(float), s>>>(A, alpha_raw, scale, alpha_out, cam_lo, mm, h, w, C);
-    else cam_c8_kernel<false><<<grid, 256, C * sizeof(float), s>>>(A, alpha_raw, scale, alpha_out, cam_lo, mm, h, w, C);
+    if (x3) cam_c8_kernel<true><<<grid, 256, C * sizeof(float), s>>>(A, alpha_raw, scale, alpha_out, cam_lo, mm, h, w, C, n_dev);
+    else cam_c8_kernel<false><<<grid, 256, C * sizeof(float), s>>>(A, alpha_raw, scale, alpha_out, cam_lo, mm, h, w, C, n_dev);
     BCAD_CUDA_CHECK(cudaGetLastError());
     return BCAD_OK;
 }

@@ -88,7 +88,7 @@ int launch_fc_reduce(const float* part, int splits, size_t ld_split, const float
                      int M, int N, cudaStream_t s);
 
 int launch_cam_c8(const __half* A, const float* alpha_raw, float scale, float* alpha_out, float* cam_lo, float* mm,
-                  int B, int h, int w, int C, int splits, bool x3, cudaStream_t s);
+                  int B, int h, int w, int C, int splits, bool x3, cudaStream_t s, const int* n_dev = nullptr);
 // fused tail (sm100_tail.cu): cam + min-max + bilinear + min-max, a 2-CTA cluster per image
 bool tail_fused_supported(int h, int w, int H, int W, int C);
 int launch_tail_fused(const __half* A, const float* alpha_raw, float scale, float* alpha_out, float* out, int B, int h, int w,

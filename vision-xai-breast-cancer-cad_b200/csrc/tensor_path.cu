@@ -343,6 +343,7 @@ int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const in
     // image is 2 items at 64 rows, 64 items at 2) -- the banding does not change any result
     a.band_rows = 64;
     while (a.band_rows > 2 && (long long)n * cdiv(c1.Ho, a.band_rows) * a.xsegs < t.sms) a.band_rows -= 2;
+    if (m.n_dev != nullptr && a.band_rows > 4) a.band_rows = 4;     // refinement twin: usually 1-3 of its slots are live -- spread each image
     if (a.band_rows > c1.Ho) a.band_rows = cdiv(c1.Ho, 2) * 2;
     a.bands = cdiv(c1.Ho, a.band_rows);
     a.alpha = m.cfg.alpha_conv;
@@ -414,12 +415,17 @@ int tensor_explain_chunk(Model& m, int n, const int32_t* class_idx, int grad_mod
         TP_LAUNCH(m, "alpha_shortcut_sgemm", launch_sgemm(dz1, t.d_S, t.alpha_raw, n, T.Cout, m.dense[0].out, false, 1, s));
     }
     const float inv_hw = 1.0f / ((float)T.Ho * (float)T.Wo);
-    if (tail_fused_supported(T.Ho, T.Wo, m.heat_h, m.heat_w, T.Cout) && getenv("BCAD_TAIL_TWO_KERNELS") == nullptr) {
+    // The one-launch cluster tail needs about a CTA pair per SM to pay (one image's pair streams its 2-4 MB map at a single SM
+    // pair's bandwidth: 73 us whatever the batch); handles sized for a few images (single requests, the refinement twin) take the
+    // two-launch form, whose channel reduction spreads one image over 8 CTAs (16 images: 30 instead of 72 us).  A property of the
+    // HANDLE, so that a given handle's results do not depend on how a batch is chunked.
+    const bool small_handle = m.cfg.max_batch <= 32;
+    if (!small_handle && tail_fused_supported(T.Ho, T.Wo, m.heat_h, m.heat_w, T.Cout) && getenv("BCAD_TAIL_TWO_KERNELS") == nullptr) {
         TP_LAUNCH(m, "tail_fused", launch_tail_fused(t.act, t.alpha_raw, inv_hw, m.alpha, heat, n, T.Ho, T.Wo, m.heat_h, m.heat_w, T.Cout, t.x3, s, m.n_dev));
         return BCAD_OK;
     }
-    TP_LAUNCH(m, "cam_c8", launch_cam_c8(t.act, t.alpha_raw, inv_hw, m.alpha, m.cam_lo, m.mm, n, T.Ho, T.Wo, T.Cout, m.cam_splits, t.x3, s));
-    TP_LAUNCH(m, "upsample_norm", launch_upsample_norm(m.cam_lo, m.mm, m.cam_splits, heat, n, T.Ho, T.Wo, m.heat_h, m.heat_w, s));
+    TP_LAUNCH(m, "cam_c8", launch_cam_c8(t.act, t.alpha_raw, inv_hw, m.alpha, m.cam_lo, m.mm, n, T.Ho, T.Wo, T.Cout, m.cam_splits, t.x3, s, m.n_dev));
+    TP_LAUNCH(m, "upsample_norm", launch_upsample_norm(m.cam_lo, m.mm, m.cam_splits, heat, n, T.Ho, T.Wo, m.heat_h, m.heat_w, s, m.n_dev));
     return BCAD_OK;
 }
 
