@@ -57,6 +57,7 @@ struct FusedArgs {
     const uint8_t* w0_img;        // first-block image [4 chunks][32][16 B], or [2 chunks][32][16 B] with plain0 (as launch_conv_first_tc)
     int plain0;                   // first-block operands as plain fp16 (the fp16 mode) instead of hi/lo pairs
     const uint8_t* w1_img;        // second-block weight image + bias tile (as IgemmArgs::w_img)
+    const float* b0 = nullptr;    // conv_fused2 only: first-block bias fp32 [32]; w0_img is then the patch-union image [2 chunks][4 classes x 32][16 B]
     __half* act;                  // second-block activations, C8 planar, or nullptr
     uint8_t* pool_fc;             // pooled second-block output as fc1 A tiles, or nullptr
     __half* p1_out;               // optional copy of the pooled first-block output (C8 planar), nullptr = stays on chip
@@ -66,9 +67,13 @@ struct FusedArgs {
     int bands, band_rows;
     float alpha;
     int debug;                    // timing experiments only: 1 no activation store, 2 no fc1-tile store, 16 first-block teams idle
+    int xoff = 0;                 // conv_fused2 only: the input boxes start xoff columns left of -pad (16-byte aligned box starts)
 };
 bool conv_fused_supported(int Cin, int C0, int C1, int W1, int Wo1, bool x3);
 int launch_conv_fused(const FusedArgs& a, int sms, cudaStream_t s);
+// second generation (sm100_fused2.cu): patch-union first block (one MMA per tile), tensor-map TMA input boxes, three pipelined teams
+bool conv_fused2_supported(const float* x, int H, int W);
+int launch_conv_fused2(const FusedArgs& a, int sms, cudaStream_t s);
 
 struct FcArgs {
     const uint8_t* a_tiles;       // [m_tiles][nkb][128][128 B] SW128

@@ -31,6 +31,7 @@ struct TensorPath {
     float* d_b0 = nullptr;
     uint8_t* d_w0_img = nullptr;    // tensor-core first conv: [4][Cout0][8] fp16 (hi/lo split weights + bias)
     uint8_t* d_w0_plain = nullptr;  // the same without the split (fp16 mode): [2][Cout0][8] fp16 rows [w(9) b_hi b_lo 0..]
+    uint8_t* d_w0_union = nullptr;  // fp16 mode, conv_fused2: patch-union image [2 chunks][4 pool classes x Cout0][8] fp16 (K slot r*4+c of the 4x4 patch)
     bool plain0 = false;            // fp16 mode: plain fp16 operands in the first block too (BCAD_CONV0_SPLIT=1 keeps the split)
     uint8_t* d_w1_img = nullptr;    // igemm weight image (fp16)
     float* d_b1 = nullptr;
@@ -181,6 +182,20 @@ int tensor_path_commit(Model& m) {
         if (!t.d_w0_plain) TP_TRY(m.alloc((void**)&t.d_w0_plain, pl.size() * 2));
         BCAD_CUDA_CHECK(cudaMemcpy(t.d_w0_plain, pl.data(), pl.size() * 2, cudaMemcpyHostToDevice));
         t.plain0 = !t.x3 && getenv("BCAD_CONV0_SPLIT") == nullptr;
+        // patch-union form (sm100_fused2.cu): the filter of pool class (qr, qc) sits at offset (qr, qc) inside the 4x4 input patch
+        if (c0.Cout == 32) {
+            std::vector<uint16_t> un((size_t)2 * 4 * c0.Cout * 8, 0);
+            for (int qr = 0; qr < 2; ++qr)
+                for (int qc = 0; qc < 2; ++qc)
+                    for (int f = 0; f < c0.Cout; ++f)
+                        for (int ty = 0; ty < 3; ++ty)
+                            for (int tx = 0; tx < 3; ++tx) {
+                                const int k = (qr + ty) * 4 + (qc + tx), n = (qr * 2 + qc) * c0.Cout + f;
+                                un[((size_t)(k >> 3) * 4 * c0.Cout + n) * 8 + (k & 7)] = f2h(c0.h_w[(size_t)f * 9 + ty * 3 + tx]);
+                            }
+            if (!t.d_w0_union) TP_TRY(m.alloc((void**)&t.d_w0_union, un.size() * 2));
+            BCAD_CUDA_CHECK(cudaMemcpy(t.d_w0_union, un.data(), un.size() * 2, cudaMemcpyHostToDevice));
+        }
     }
     // ---- conv1 weight image: [tap*(Cin/8)+chunk][cout][8] fp16
     {
@@ -317,6 +332,14 @@ int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const in
             if (f.debug & 1) f.act = nullptr;
             if (f.debug & 2) f.pool_fc = nullptr;
         }
+        // second-generation kernel (patch-union first block, TMA input boxes) where its extra conditions hold; BCAD_FUSED_V1=1 keeps the first
+        if (t.plain0 && t.d_w0_union != nullptr && getenv("BCAD_FUSED_V1") == nullptr && conv_fused2_supported(x, c0.H, c0.W)) {
+            f.w0_img = t.d_w0_union;
+            f.b0 = t.d_b0;
+            f.xoff = (4 - m.cfg.pad % 4) % 4;                       // box start column -pad - xoff = a multiple of 4 floats
+            if (const char* e = getenv("BCAD_F2_XOFF")) f.xoff = atoi(e);
+            TP_LAUNCH(m, "conv01_fused_tcgen05", launch_conv_fused2(f, t.sms, s));
+        } else
         TP_LAUNCH(m, "conv01_fused_tcgen05", launch_conv_fused(f, t.sms, s));
     } else {
     t.p1_valid = true;
