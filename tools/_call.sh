@@ -1,7 +1,9 @@
 cd /root/repo
-D=$PWD/vision-xai-breast-cancer-cad_b200
-for at in 3 300 1500; do
-echo "== t4e4 trace lib, bench mode, trace of launch $at"
-BCAD_F2_TRACE_AT=$at BCAD_LIB=$D/libbcad_t4e4tr.so timeout 200 python bench.py --steps 50 --warmup 5 --preheat 2 --no-check --no-cpu-baseline --no-fp32-grade --only-value --refine-margin 0 2>&1 >/dev/null | grep "f2_trace issuer\|f2_trace team\|per-CTA issuer"
-done > gpurun_out/r02q_clock.log 2>&1
-cat gpurun_out/r02q_clock.log | cut -c1-400
+CMD="python bench.py --steps 3 --warmup 3 --preheat 0 --no-check --no-cpu-baseline --no-fp32-grade --only-value"
+$CMD > gpurun_out/r02t_plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/r02_launches.csv $CMD > gpurun_out/r02t_ncu1.log 2>&1
+echo "launch list rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:"conv_fused2|tail_fused|fc_splitk|dense_head" -s 16 -c 4 -o gpurun_out/r02_all -f $CMD > gpurun_out/r02t_ncu2.log 2>&1
+echo "full rc=$?"
+tail -3 gpurun_out/r02t_ncu2.log
+ls -la gpurun_out/r02_all.ncu-rep gpurun_out/r02_launches.csv

@@ -69,7 +69,7 @@ struct F2Smem {
     static constexpr int LBO = F2_XP * 16;
     static constexpr int ROWB = CHUNKS * LBO;
     static constexpr int WBYTES = 9 * CHUNKS * F2_C1 * 16;
-    static constexpr int BIAS_TILE = 2 * F2_C1 * 16;
+    static constexpr int BIAS_TILE = 2 * 2 * F2_C1 * 16;               // [2 chunks][2 x 64 rows][16 B]: the bias rows twice (N = 128 bias MMA)
     static constexpr int ONES_TILE = 2 * 128 * 16;
     static constexpr int OFF_W1 = 0;
     static constexpr int OFF_ONES = OFF_W1 + WBYTES + BIAS_TILE;
@@ -327,6 +327,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_fused2_kernel(FusedArgs a,
         }
         const volatile uint32_t* stop = f2_stop;
         while (!*stop) {
+            if (a.debug & 2048) __nanosleep(64);                  // back off between polling rounds: the chip is power-capped, a hot spin costs clock
 #pragma unroll
             for (int t = 0; t < F2_TEAMS; ++t) {
                 const uint32_t par = served[t] & 1u;
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_fused2_kernel(FusedArgs a,
     } else if (warp == F2_TW * F2_TEAMS) {
         // ================================ second-block MMA issuer (as conv_fused_kernel) ================================
         const bool leader = elect_one();
-        constexpr uint32_t idesc = make_idesc_f16(128, COUT);
+        constexpr uint32_t idesc = make_idesc_f16(128, COUT), idesc2 = make_idesc_f16(128, 2 * COUT);
         F2_T(long long tr_full = 0; long long tr_tempty = 0; long long tr_issue = 0;)
         F2_T(const long long tr_begin = clock64(); unsigned long long tr_ns0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_ns0));)
         mbar_wait(wbar, 0);
@@ -351,8 +352,9 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_fused2_kernel(FusedArgs a,
         const uint32_t w_base = smem_u32(s_w), zero_base = smem_u32(s_zero), ring_base = smem_u32(s_ring);
         constexpr uint32_t d_hi = (uint32_t)(128 >> 4) | (1u << 14);
         constexpr uint32_t a_lo_t = (uint32_t)(L::LBO >> 4) << 16;
-        constexpr uint32_t b_lo_t = (uint32_t)((COUT * 16) >> 4) << 16;
+        constexpr uint32_t b_lo_t = (uint32_t)((3 * COUT * 16) >> 4) << 16;      // K chunks of one (dx, k-step) are 3 taps apart
         const uint32_t b_lo0 = b_lo_t | ((w_base & 0x3FFFFu) >> 4);
+        const uint32_t bias_lo = ((uint32_t)((2 * COUT * 16) >> 4) << 16) | (((w_base + L::WBYTES) & 0x3FFFFu) >> 4);   // [2 chunks][128 rows][16 B]
         const uint32_t ones_lo = ((uint32_t)((128 * 16) >> 4) << 16) | ((smem_u32(s_ones) & 0x3FFFFu) >> 4);
         const bool lead2 = leader && !(a.debug & 128);           // debug bit 7: the second block's MMA instructions run predicated off
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -369,25 +371,51 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_fused2_kernel(FusedArgs a,
                 if (acc_it >= 2) mbar_wait(&tempty[j], ((acc_it >> 1) - 1) & 1);
                 F2_T(const long long w2 = clock64(); tr_tempty += w2 - w1;)
                 tc_fence_after();
-                for (int r = 0; r < 2; ++r) {
-                    if (2 * p + r >= nrows || (a.debug & 8)) break;     // debug bit 3: no second-block MMAs (timing experiment)
-                    const uint32_t d_tmem = tmem + j * (2 * COUT) + r * COUT;
-                    umma_f16_if(lead2, d_tmem, desc64(ones_lo, d_hi), desc64(b_lo0 + (uint32_t)(L::WBYTES >> 4), d_hi), idesc, 0u);
+                // Weight image (pair layout): per (dx, 8-channel chunk) the three dy taps are contiguous, [w(dy=2) | w(1) | w(0)], 64 rows x 16 B each,
+                // so [w(2) | w(1)] and [w(1) | w(0)] are valid N = 128 operands.  Input row i of the pair (i = 0..3 below the pair's first output
+                // row) feeds output row 0 with tap dy = i and output row 1 with dy = i - 1: rows 1 and 2 do both with ONE N = 128 MMA into the two
+                // adjacent accumulators (the A operand is read once instead of twice); rows 0 and 3 are N = 64.  25 MMAs per pair instead of 38,
+                // same products in the same order per accumulator.
+                auto row_desc = [&](int i_abs) -> uint32_t {
+                    const int in_row = y0 - a.pad + i_abs;
+                    uint32_t row_base;
+                    if (in_row < 0 || in_row >= a.H1) row_base = zero_base;
+                    else row_base = ring_base + ((((g + (i_abs >> 1) - p) % S) << 1) + (i_abs & 1)) * L::ROWB;
+                    return a_lo_t | ((row_base & 0x3FFFFu) >> 4);
+                };
+                auto w_off = [&](int dy, int dx, int ks) -> uint32_t { return (uint32_t)((((dx * L::CHUNKS + 2 * ks) * 3 + (2 - dy)) * (COUT * 16)) >> 4); };
+                const uint32_t d_tmem = tmem + j * (2 * COUT);
+                const bool pair = (2 * p + 1 < nrows) && !(a.debug & 1024);      // debug bit 10: no paired taps (A/B timing)
+                if (a.debug & 8) {                                               // debug bit 3: no second-block MMAs (timing experiment)
+                } else if (pair) {
+                    umma_f16_if(lead2, d_tmem, desc64(ones_lo, d_hi), desc64(bias_lo, d_hi), idesc2, 0u);
 #pragma unroll
-                    for (int dy = 0; dy < 3; ++dy) {
-                        const int i = 2 * p + r + dy;
-                        const int in_row = y0 - a.pad + i;
-                        uint32_t row_base;
-                        if (in_row < 0 || in_row >= a.H1) row_base = zero_base;
-                        else row_base = ring_base + ((((g + (i >> 1) - p) % S) << 1) + (i & 1)) * L::ROWB;
-                        const uint32_t a_lo0 = a_lo_t | ((row_base & 0x3FFFFu) >> 4);
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t a_lo0 = row_desc(2 * p + i);
 #pragma unroll
                         for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
-                            for (int ks = 0; ks < CIN / 16; ++ks)
-                                umma_f16_if(lead2, d_tmem, desc64(a_lo0 + (uint32_t)((ks * 2 * L::LBO + dx * 16) >> 4), d_hi),
-                                            desc64(b_lo0 + (uint32_t)((((dy * 3 + dx) * L::CHUNKS + 2 * ks) * (COUT * 16)) >> 4), d_hi),
-                                            idesc, 1u);
+                            for (int ks = 0; ks < CIN / 16; ++ks) {
+                                const uint64_t ad = desc64(a_lo0 + (uint32_t)((ks * 2 * L::LBO + dx * 16) >> 4), d_hi);
+                                if (i == 0) umma_f16_if(lead2, d_tmem, ad, desc64(b_lo0 + w_off(0, dx, ks), d_hi), idesc, 1u);
+                                else if (i == 3) umma_f16_if(lead2, d_tmem + COUT, ad, desc64(b_lo0 + w_off(2, dx, ks), d_hi), idesc, 1u);
+                                else umma_f16_if(lead2, d_tmem, ad, desc64(b_lo0 + w_off(i, dx, ks), d_hi), idesc2, 1u);     // [w(i) | w(i-1)]
+                            }
+                    }
+                } else {
+                    for (int r = 0; r < 2; ++r) {
+                        if (2 * p + r >= nrows) break;
+                        umma_f16_if(lead2, d_tmem + r * COUT, desc64(ones_lo, d_hi), desc64(bias_lo, d_hi), idesc, 0u);
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy) {
+                            const uint32_t a_lo0 = row_desc(2 * p + r + dy);
+#pragma unroll
+                            for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                                for (int ks = 0; ks < CIN / 16; ++ks)
+                                    umma_f16_if(lead2, d_tmem + r * COUT, desc64(a_lo0 + (uint32_t)((ks * 2 * L::LBO + dx * 16) >> 4), d_hi),
+                                                desc64(b_lo0 + w_off(dy, dx, ks), d_hi), idesc, 1u);
+                        }
                     }
                 }
                 umma_commit_if(leader, &empty[g % S]);

@@ -56,7 +56,7 @@ struct FusedArgs {
     const float* x;               // fp32 [B][H][W]
     const uint8_t* w0_img;        // first-block image [4 chunks][32][16 B], or [2 chunks][32][16 B] with plain0 (as launch_conv_first_tc)
     int plain0;                   // first-block operands as plain fp16 (the fp16 mode) instead of hi/lo pairs
-    const uint8_t* w1_img;        // second-block weight image + bias tile (as IgemmArgs::w_img)
+    const uint8_t* w1_img;        // second-block weight image + bias tile (as IgemmArgs::w_img; conv_fused2: the pair layout, see tensor_path.cu)
     const float* b0 = nullptr;    // conv_fused2 only: first-block bias fp32 [32]; w0_img is then the patch-union image [2 chunks][4 classes x 32][16 B]
     __half* act;                  // second-block activations, C8 planar, or nullptr
     uint8_t* pool_fc;             // pooled second-block output as fc1 A tiles, or nullptr

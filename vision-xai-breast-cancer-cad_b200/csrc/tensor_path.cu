@@ -32,6 +32,7 @@ struct TensorPath {
     uint8_t* d_w0_img = nullptr;    // tensor-core first conv: [4][Cout0][8] fp16 (hi/lo split weights + bias)
     uint8_t* d_w0_plain = nullptr;  // the same without the split (fp16 mode): [2][Cout0][8] fp16 rows [w(9) b_hi b_lo 0..]
     uint8_t* d_w0_union = nullptr;  // fp16 mode, conv_fused2: patch-union image [2 chunks][4 pool classes x Cout0][8] fp16 (K slot r*4+c of the 4x4 patch)
+    uint8_t* d_w1_pair = nullptr;   // conv_fused2: second-block weights [dx][Cin/8][dy = 2,1,0][Cout][8] fp16 (adjacent dy taps = N = 128 operands) + bias tile [2][2 x Cout][8]
     bool plain0 = false;            // fp16 mode: plain fp16 operands in the first block too (BCAD_CONV0_SPLIT=1 keeps the split)
     uint8_t* d_w1_img = nullptr;    // igemm weight image (fp16)
     float* d_b1 = nullptr;
@@ -222,6 +223,26 @@ int tensor_path_commit(Model& m) {
         }
         if (!t.d_w1_img) TP_TRY(m.alloc((void**)&t.d_w1_img, img.size() * 2));
         BCAD_CUDA_CHECK(cudaMemcpy(t.d_w1_img, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+        if (!t.x3 && c1.Cin == 32 && c1.Cout == 64) {
+            // pair layout for conv_fused2 (sm100_fused2.cu): the three dy taps of a (dx, chunk) are contiguous, highest dy first
+            std::vector<uint16_t> pr((size_t)9 * chunks * c1.Cout * 8 + (size_t)2 * 2 * c1.Cout * 8, 0);
+            for (int dx = 0; dx < 3; ++dx)
+                for (int ch = 0; ch < chunks; ++ch)
+                    for (int dy = 0; dy < 3; ++dy)
+                        for (int f = 0; f < c1.Cout; ++f)
+                            for (int e = 0; e < 8; ++e)
+                                pr[((((size_t)dx * chunks + ch) * 3 + (2 - dy)) * c1.Cout + f) * 8 + e] =
+                                    f2h(c1.h_w[((size_t)f * 9 + dy * 3 + dx) * c1.Cin + ch * 8 + e]);
+            const size_t boff = (size_t)9 * chunks * c1.Cout * 8;
+            for (int n = 0; n < 2 * c1.Cout; ++n) {                          // bias rows twice: rows n and n + Cout of an N = 128 operand
+                const int f = n % c1.Cout;
+                const float bhi = h2f(f2h(c1.h_b[f]));
+                pr[boff + (size_t)n * 8 + 0] = f2h(bhi);
+                pr[boff + (size_t)n * 8 + 1] = f2h(c1.h_b[f] - bhi);
+            }
+            if (!t.d_w1_pair) TP_TRY(m.alloc((void**)&t.d_w1_pair, pr.size() * 2));
+            BCAD_CUDA_CHECK(cudaMemcpy(t.d_w1_pair, pr.data(), pr.size() * 2, cudaMemcpyHostToDevice));
+        }
     }
     // ---- fc1: SW128 tiles [pixel][unit][128 B]; K index inside a tile = channel; S = per-channel column sums
     {
@@ -333,10 +354,16 @@ int tensor_forward_chunk(Model& m, const float* x, int n, bool explain, const in
             if (f.debug & 2) f.pool_fc = nullptr;
         }
         // second-generation kernel (patch-union first block, TMA input boxes) where its extra conditions hold; BCAD_FUSED_V1=1 keeps the first
-        if (t.plain0 && t.d_w0_union != nullptr && getenv("BCAD_FUSED_V1") == nullptr && conv_fused2_supported(x, c0.H, c0.W)) {
+        if (t.plain0 && t.d_w0_union != nullptr && t.d_w1_pair != nullptr && getenv("BCAD_FUSED_V1") == nullptr && conv_fused2_supported(x, c0.H, c0.W)) {
             f.w0_img = t.d_w0_union;
+            f.w1_img = t.d_w1_pair;
             f.b0 = t.d_b0;
             f.xoff = (4 - m.cfg.pad % 4) % 4;                       // box start column -pad - xoff = a multiple of 4 floats
+            // paired taps (N = 128 MMAs, 25 instead of 38 per row pair): 17 % faster second block on its own (0.233 vs 0.281 ms), but the whole
+            // kernel is then bound by the teams / epilogue and, power-capped, measured 3 % SLOWER under sustained load (0.485 vs 0.469 ms,
+            // profiles/r02_fused2_variants.md): opt-in
+            if (getenv("BCAD_F2_PAIRED") == nullptr) f.debug |= 1024;
+            if (getenv("BCAD_F2_NOSLEEP") == nullptr) f.debug |= 2048;      // loader warp backs off 64 ns between polling rounds (0.444-0.465 vs 0.469-0.470 ms sustained)
             if (const char* e = getenv("BCAD_F2_XOFF")) f.xoff = atoi(e);
             TP_LAUNCH(m, "conv01_fused_tcgen05", launch_conv_fused2(f, t.sms, s));
         } else
