@@ -956,6 +956,8 @@ def run_train(args, rank, world, local_rank):
     spec = bcad_b200.NetSpec.torch_flavour(INPUT_SHAPE, NUM_CLASSES, CONV_LAYERS, HIDDEN, 0.01)
     eng = bcad_b200.Engine(spec, precision="fp32", max_batch=B, keep_all_activations=True, device=local_rank)
     eng.set_weights(*synth_weights())
+    if args.train_kernels == "tensor":
+        eng.set_fast_training(True)          # second conv block: forward / dgrad / wgrad as split-operand tcgen05 GEMMs (sm100_train.cu)
     tr = DataParallelTrainer(eng, opt="adam", lr=1e-4)
     x_host = torch.from_numpy(synth_images(B, INPUT_SHAPE, seed=777 + rank)).pin_memory()
     y_host = torch.from_numpy((np.arange(B) % 2).astype(np.int32)).pin_memory()
@@ -1057,10 +1059,11 @@ def run_train(args, rank, world, local_rank):
     emit({
         "metric": "training throughput (forward + backward + gradient all-reduce + Adam), images/s", "value": world * B * args.steps / (ms_total * 1e-3),
         "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (second conv block: split-operand tcgen05, fp32 in/out)" if args.train_kernels == "tensor" else "f32", "data": "synthetic",
         "config": {"workload": f"train: ADCNNM-flavour CNN {INPUT_SHAPE} conv{CONV_LAYERS} fc{HIDDEN}, {B} images/GPU/step, Adam, "
                                f"one {grad_bytes / 1e6:.0f} MB gradient all-reduce per step (secondary line, BASELINE config 5)",
-                   "images_per_gpu": B, "l2": "activations >> 126 MB L2 per step"},
+                   "images_per_gpu": B, "l2": "activations >> 126 MB L2 per step", "train_kernels": args.train_kernels},
         "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + B * 4),
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "last_mean_loss": mean_loss},
         "gpu_launches": int(launches), "clocks": clocks, "kernels": kernels, "grad_bytes": grad_bytes,
@@ -1113,6 +1116,8 @@ def main():
                                                         "the headline line uses the default 256,256,1")
     ap.add_argument("--total-batch", type=int, default=0, help="STRONG scaling (BASELINE cfg 4: 8192): images per step over ALL GPUs, "
                                                                "split evenly; 0 = weak scaling with --batch images per GPU")
+    ap.add_argument("--train-kernels", default="tensor", choices=["tensor", "fp32"], help="--workload train: the second conv block on the tensor "
+                                                                                         "cores (bcad_set_fast_training) or every kernel fp32")
     ap.add_argument("--preheat", type=float, default=2.0, help="seconds of untimed full-duty steps before each timed region")
     ap.add_argument("--check-images", type=int, default=256, help="images of the batch compared one by one with the oracle (untimed)")
     ap.add_argument("--refine-margin", type=float, default=None, help="fp16 path: top-2 logit gap below which an image is re-run at fp32 "

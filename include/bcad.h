@@ -256,6 +256,11 @@ BCAD_API int bcad_train_backward_part(bcad_model* m, const float* x_dev, const i
  * activations to the weight gradients; mask_backward = 1 also masks the back-propagated gradient (autograd, ADCNNM.py),
  * 0 leaves it unmasked as the NumPy reference's backward does (Classes/CNNModel.py:307-316). */
 BCAD_API int bcad_set_dropout_masks(bcad_model* m, const float* masks, int B, int mask_backward, void* stream);
+/* Fast training (off by default): eligible conv blocks (3x3, 32 -> 64 filters, maps <= 128 px wide) run forward / input gradient / weight
+ * gradient on tcgen05 with split (hi + lo) operands; fp32 tensors in and out.  Replaces the per-block work of
+ * Classes/CNNModel.py:227-240, 320-355 / torch autograd (ADCNNM.py:100-118) at ~1e-4 relative instead of fp32 rounding.
+ * BCAD_ERR_INVALID when no block of the network is eligible or the handle is not BCAD_PREC_FP32. */
+BCAD_API int bcad_set_fast_training(bcad_model* m, int on);
 
 /* opt 0: w -= lr * clip(g), per-tensor L2-norm clipping at max_norm (Classes/CNNModel.py:217-222, 372-394; 0 = no clip);
  * opt 1: Adam(lr, b1, b2, eps) as torch.optim.Adam (ADCNNM.py:88).  grads_dev usually comes back from an all-reduce. */

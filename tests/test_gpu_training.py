@@ -240,3 +240,47 @@ def test_nccl_data_parallel_step_matches_full_batch():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29611", os.path.join(root, "tools", "train_dp_check.py")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "DP-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("shape,pad,B", [
+    ((64, 64, 1), 1, 6),        # second block on 32x32 maps
+    ((61, 61, 1), 0, 5),        # valid conv, odd maps: 29x29 -> 27x27 (a last row without a partner, "full" dgrad padding of 2)
+    ((40, 200, 1), 1, 4),       # 100-pixel rows: two 64-pixel halves in the weight gradient
+])
+def test_fast_training_matches_the_fp32_kernels(shape, pad, B):
+    """bcad_set_fast_training: the 32 -> 64 conv block's forward, input gradient and weight gradient on tcgen05 (split operands) against
+    the reference-pinned fp32 kernels of the same handle: logits, loss and every gradient tensor to 1e-3 of the tensor's largest entry
+    (measured ~1e-5), then two Adam steps stay together."""
+    cfg = ocnn.NetConfig(shape, 2, [(32, 3), (64, 3)], [32, 16], 0.01, 0.01, pad, "chw", "first", "logits")
+    p = ocnn.init_params(cfg, seed=3, bias_std=0.05)
+    x = torch.from_numpy(ocnn.synth_images(B, shape, seed=9)).cuda()
+    labels = np.arange(B) % 2
+    ref = engine_from(cfg, p, max_batch=8, keep_all_activations=True)
+    fast = engine_from(cfg, p, max_batch=8, keep_all_activations=True)
+    fast.set_fast_training(True)
+    for step in range(2):
+        _, _, l_ref = ref.predict(x)
+        _, _, l_fast = fast.predict(x)
+        _cmp(l_fast.cpu().numpy(), l_ref.cpu().numpy(), 1e-3, f"step {step} logits")
+        g_ref, loss_ref = ref.train_backward(x, labels)
+        g_fast, loss_fast = fast.train_backward(x, labels)
+        _cmp(loss_fast.cpu().numpy(), loss_ref.cpu().numpy(), 1e-3, "loss")
+        u_ref, u_fast = ref.unpack_grads(g_ref), fast.unpack_grads(g_fast)
+        for k in ("conv_w", "conv_b", "dense_w", "dense_b"):
+            for i, (a, b) in enumerate(zip(u_fast[k], u_ref[k])):
+                err = np.abs(a - b).max()
+                assert err <= 1e-3 * max(1e-12, np.abs(b).max()), f"step {step} {k}[{i}]: err {err} vs max {np.abs(b).max()}"
+        ref.apply_update(g_ref, "adam", lr=1e-3)
+        fast.apply_update(g_fast, "adam", lr=1e-3)
+    names = [n for n, _ in fast.last_profile()] if hasattr(fast, "last_profile") else []
+    ref.close()
+    fast.close()
+
+
+def test_fast_training_rejects_networks_without_an_eligible_block():
+    cfg = ocnn.NetConfig.torch_flavour((20, 24, 1), 2, [(8, 3), (16, 3)], [12], 0.01)
+    p = ocnn.init_params(cfg, seed=3)
+    eng = engine_from(cfg, p, max_batch=4, keep_all_activations=True)
+    with pytest.raises(ValueError, match="no conv block"):
+        eng.set_fast_training(True)
+    eng.close()

@@ -50,6 +50,7 @@ _SIGNATURES = {
     "bcad_set_dense_weights": (C.c_int, [_P, C.c_int, _P, _P]),
     "bcad_fold_batchnorm": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_float]),
     "bcad_commit": (C.c_int, [_P]),
+    "bcad_set_fast_training": (C.c_int, [_P, C.c_int]),
     "bcad_predict": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P]),
     "bcad_predict_explain": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P]),
     "bcad_predict_explain_sized": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, _P]),

@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "model.h"
+#include "sm100_train.h"
 
 namespace bcad {
 
@@ -381,6 +382,7 @@ int bcad_commit(bcad_model* mm) {
     BCAD_CUDA_CHECK(cudaDeviceSynchronize());
     m->committed = true;
     m->cached_B = 0;
+    m->train.tc_dirty = true;
     return BCAD_OK;
 }
 
@@ -422,8 +424,19 @@ int launch_fused_head(Model* m, int n, const float* fc1_part, int splits, size_t
 static int forward_chunk_fp32(Model* m, const float* x, int n, bool explain, const int32_t* class_idx, int grad_mode,
                               cudaStream_t s) {
     const float* in = x;
+    if (m->fast_train) BCAD_TRY(tc_train_refresh(m, s));
     for (size_t i = 0; i < m->conv.size(); ++i) {
         ConvLayer& L = m->conv[i];
+        if (m->fast_train && tc_train_eligible(m, i) && L.y != nullptr) {
+            // the block as a split-operand tcgen05 implicit GEMM on the fp32 NHWC tensors (sm100_train.cu), then the 2x2 pool
+            TcConvArgs t;
+            t.x = in; t.w_img = L.tc_w; t.bias = L.d_b; t.y = L.y; t.B = n; t.H = L.H; t.W = L.W; t.Ho = L.Ho; t.Wo = L.Wo;
+            t.pad = m->cfg.pad; t.alpha = m->cfg.alpha_conv; t.a_bf16 = 0;
+            BCAD_LAUNCH(m, "conv1_fwd_tcgen05_x3", launch_conv3x3_x3(t, L.Cin, L.Cout, m->sms, s));
+            BCAD_LAUNCH(m, "maxpool2x2", launch_maxpool2x2_nhwc(L.y, L.p, n, L.Ho, L.Wo, L.Cout, s));
+            in = L.p;
+            continue;
+        }
         ConvArgs a;
         a.x = in; a.w = L.d_w; a.bias = L.d_b; a.y = L.y; a.p = L.p;
         a.B = n; a.H = L.H; a.W = L.W; a.Cin = L.Cin; a.Cout = L.Cout; a.CoutPad = L.CoutPad;
@@ -756,9 +769,6 @@ static int predict_explain_host_impl(bcad_model* mm, const float* x_host, const 
                 BCAD_CUDA_CHECK(cudaEventCreateWithFlags(&X.out_done[i], cudaEventDisableTiming));
                 BCAD_TRY(m->alloc((void**)&X.x[i], (size_t)chunk * img * sizeof(float)));
                 BCAD_TRY(m->alloc((void**)&X.heat[i], (size_t)chunk * hm * sizeof(float)));
-                BCAD_TRY(m->alloc((void**)&X.logits[i], (size_t)chunk * nc * sizeof(float)));
-                BCAD_TRY(m->alloc((void**)&X.probs[i], (size_t)chunk * nc * sizeof(float)));
-                BCAD_TRY(m->alloc((void**)&X.cls[i], (size_t)chunk * sizeof(int32_t)));
                 BCAD_TRY(m->alloc((void**)&X.cidx[i], (size_t)chunk * sizeof(int32_t)));
             }
             X.chunk = chunk;
@@ -783,9 +793,19 @@ static int predict_explain_host_impl(bcad_model* mm, const float* x_host, const 
         BCAD_CUDA_CHECK(cudaMallocHost(&X.h_small, per_img * B));
         X.h_small_bytes = per_img * B;
     }
+    if (X.d_small_bytes < per_img * B) {
+        std::lock_guard<std::mutex> lock(m->mu);             // grows only when a call is larger than every call before it; the handle
+        X.d_small = nullptr;                                 // owns (and frees at destroy) the smaller ones it replaces: tens of bytes per image
+        X.d_small_bytes = 0;
+        BCAD_TRY(m->alloc(&X.d_small, per_img * B));
+        X.d_small_bytes = per_img * B;
+    }
     float* st_logits = reinterpret_cast<float*>(X.h_small);
     float* st_probs = st_logits + (size_t)B * nc;
     int32_t* st_cls = reinterpret_cast<int32_t*>(st_probs + (size_t)B * nc);
+    float* dv_logits = reinterpret_cast<float*>(X.d_small);
+    float* dv_probs = dv_logits + (size_t)B * nc;
+    int32_t* dv_cls = reinterpret_cast<int32_t*>(dv_probs + (size_t)B * nc);
     // chunk schedule: ramp up and down (C/4, C/2, C, ..., C, C/2, C/4) so the un-overlapped head (first H2D + compute) and
     // tail (last D2H) of the pipeline are short; the steady state runs H2D, compute and D2H of three chunks concurrently
     std::vector<int> sizes;
@@ -847,8 +867,8 @@ static int predict_explain_host_impl(bcad_model* mm, const float* x_host, const 
         int rc = BCAD_OK;
         if (gray8_host) rc = launch_gray_preprocess(X.x8[slot], X.img01[slot], X.x[slot], n, (int)hm, m->cfg.in_c, standardise, X.s_compute);
         else if (x8_host) rc = launch_u8_to_unit(X.x8[slot], X.x[slot], (size_t)n * img, X.s_compute);
-        if (rc == BCAD_OK) rc = run(m, X.x[slot], n, class_idx_host ? X.cidx[slot] : nullptr, grad_mode, want_heat, X.logits[slot],
-                     X.probs[slot], X.cls[slot], X.heat[slot], X.s_compute);
+        if (rc == BCAD_OK) rc = run(m, X.x[slot], n, class_idx_host ? X.cidx[slot] : nullptr, grad_mode, want_heat, dv_logits + (size_t)b0 * nc,
+                     dv_probs + (size_t)b0 * nc, dv_cls + b0, X.heat[slot], X.s_compute);
         if (rc == BCAD_OK && overlay_host != nullptr)             // show_cam_on_image + heatmap_uint8 in one pass (GRADCAM.py:67,70)
             rc = launch_overlay(X.img01[slot], X.heat[slot], n, m->cfg.in_h, m->cfg.in_w, X.ov8[slot], heat_u8_host ? X.heat8[slot] : nullptr, X.s_compute);
         else if (rc == BCAD_OK && heat_u8_host != nullptr) rc = launch_heat_to_u8(X.heat[slot], X.heat8[slot], (size_t)n * hm, X.s_compute);
@@ -858,9 +878,8 @@ static int predict_explain_host_impl(bcad_model* mm, const float* x_host, const 
         if (heat_host) BCAD_CUDA_CHECK(cudaMemcpyAsync(heat_host + (size_t)b0 * hm, X.heat[slot], (size_t)n * hm * sizeof(float), cudaMemcpyDeviceToHost, X.s_out));
         if (heat_u8_host) BCAD_CUDA_CHECK(cudaMemcpyAsync(heat_u8_host + (size_t)b0 * hm, X.heat8[slot], (size_t)n * hm, cudaMemcpyDeviceToHost, X.s_out));
         if (overlay_host) BCAD_CUDA_CHECK(cudaMemcpyAsync(overlay_host + (size_t)b0 * hm * 3, X.ov8[slot], (size_t)n * hm * 3, cudaMemcpyDeviceToHost, X.s_out));
-        BCAD_CUDA_CHECK(cudaMemcpyAsync(st_logits + (size_t)b0 * nc, X.logits[slot], (size_t)n * nc * sizeof(float), cudaMemcpyDeviceToHost, X.s_out));
-        BCAD_CUDA_CHECK(cudaMemcpyAsync(st_probs + (size_t)b0 * nc, X.probs[slot], (size_t)n * nc * sizeof(float), cudaMemcpyDeviceToHost, X.s_out));
-        BCAD_CUDA_CHECK(cudaMemcpyAsync(st_cls + b0, X.cls[slot], (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, X.s_out));
+        if (c + 1 == (int)sizes.size())                       // the small outputs of the whole call, once, behind the last chunk
+            BCAD_CUDA_CHECK(cudaMemcpyAsync(X.h_small, X.d_small, per_img * B, cudaMemcpyDeviceToHost, X.s_out));
         BCAD_CUDA_CHECK(cudaEventRecord(X.out_done[slot], X.s_out));
     }
     BCAD_CUDA_CHECK(cudaStreamSynchronize(X.s_out));

@@ -4,6 +4,7 @@
 // ADCNNM.py:86-153 (Adam + CrossEntropyLoss).  fp32 path only.  Dropout: the caller draws the multipliers and hands them over with
 // bcad_set_dropout_masks; the forward applies them after every hidden layer and the backward uses the dropped activations
 // (and, for autograd semantics, masks the gradient too).
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -13,6 +14,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "model.h"
+#include "sm100_train.h"
 
 namespace bcad {
 
@@ -63,6 +65,31 @@ static int ensure_train_state(Model* m) {
     TR_TRY(m->alloc((void**)&T.part_b, pb * sizeof(float)));
     TR_TRY(m->alloc((void**)&T.norms, 2 * (m->conv.size() + m->dense.size()) * sizeof(float)));
     T.ready = true;
+    return BCAD_OK;
+}
+
+// fast training (bcad_set_fast_training): conv blocks i >= 1 of the 32 -> 64 shape run forward / dgrad / wgrad on the tensor cores
+bool tc_train_eligible(const Model* m, size_t i) {
+    if (i == 0 || i >= m->conv.size()) return false;
+    const ConvLayer& L = m->conv[i];
+    return L.Cin == 32 && L.Cout == 64 && L.CoutPad == 64 && conv3x3_x3_supported(L.Cin, L.Cout, L.k, L.W, L.Wo, m->cfg.pad) &&
+           conv3x3_x3_supported(L.Cout, L.Cin, L.k, L.Wo, L.W, L.k - 1 - m->cfg.pad) && wgrad3x3_x3_supported(L.Cin, L.Cout, L.k, L.W, L.Wo, m->cfg.pad);
+}
+
+int tc_train_refresh(Model* m, cudaStream_t s) {
+    if (!m->fast_train || !m->train.tc_dirty) return BCAD_OK;
+    for (size_t i = 0; i < m->conv.size(); ++i) {
+        if (!tc_train_eligible(m, i)) continue;
+        ConvLayer& L = m->conv[i];
+        if (L.tc_w == nullptr) {
+            TR_TRY(m->alloc((void**)&L.tc_w, conv3x3_x3_weight_bytes(L.Cin, L.Cout)));
+            TR_TRY(m->alloc((void**)&L.tc_wd, conv3x3_x3_weight_bytes(L.Cout, L.Cin)));
+        }
+        TR_TRY(launch_pack_w_x3(L.d_w, L.tc_w, L.Cin, L.Cout, L.CoutPad, false, s));
+        TR_TRY(launch_pack_w_x3(L.d_w_dgrad, L.tc_wd, L.Cout, L.Cin, cdiv(L.Cin, 32) * 32, true, s));     // bf16: multiplies the bf16-split gradient
+        m->launches += 2;
+    }
+    m->train.tc_dirty = false;
     return BCAD_OK;
 }
 
@@ -160,10 +187,35 @@ int bcad_train_backward_part(bcad_model* mm, const float* x, const int32_t* labe
         TR_LAUNCH(m, "unpool", launch_unpool(gp, L.y, L.dz, B, L.Ho, L.Wo, L.Cout, m->cfg.pool_ties, s));
         TR_LAUNCH(m, "leaky_mask_mul", launch_leaky_mask_mul(L.dz, L.y, m->cfg.alpha_conv, (int64_t)elems, s));
         const float* in_i = (i == 0) ? x : m->conv[i - 1].p;
+        const bool tc = m->fast_train && tc_train_eligible(m, (size_t)i);
+        const bool tc_w = tc && getenv("BCAD_TC_NO_WGRAD") == nullptr, tc_d = tc && getenv("BCAD_TC_NO_DGRAD") == nullptr;   // (fault isolation)
+        if (tc_w) {
+            // weight gradient as a pixel-contracting tcgen05 GEMM, bias gradient as a slab column sum (sm100_train.cu)
+            TR_TRY(tc_train_refresh(m, s));
+            if (T.wg_part == nullptr) {
+                TR_TRY(m->alloc((void**)&T.wg_part, wgrad3x3_x3_partial_floats(m->sms) * sizeof(float)));
+                TR_TRY(m->alloc((void**)&T.cs_part, (size_t)4096 * 64 * sizeof(float)));
+            }
+            TcWgradArgs w;
+            w.x = in_i; w.dy = L.dz; w.partials = T.wg_part; w.B = B; w.H = L.H; w.W = L.W; w.Ho = L.Ho; w.Wo = L.Wo; w.pad = m->cfg.pad;
+            TR_LAUNCH(m, "conv_wgrad_tcgen05_x3", launch_wgrad3x3_x3(w, grads + T.conv_w_off[i], L.CoutPad, m->sms, s));
+            TR_LAUNCH(m, "conv_bgrad", launch_colsum64(L.dz, T.cs_part, grads + T.conv_b_off[i], (size_t)B * L.Ho * L.Wo, s));
+            m->launches += 2;                                // the two reductions
+        } else {
         const int rows = conv_wgrad_band_rows(B, L.Ho, T.max_ctas);
         TR_LAUNCH(m, "conv_wgrad", launch_conv_wgrad(L.dz, in_i, T.part_w, T.part_b, grads + T.conv_w_off[i], grads + T.conv_b_off[i], B, L.H, L.W,
                                                     L.Cin, L.Cout, L.CoutPad, L.k, m->cfg.pad, L.Ho, L.Wo, rows, s));
         m->launches += 2;                                    // the two partial reductions
+        }
+        if (i > 0 && tc_d) {
+            ConvLayer& P = m->conv[i - 1];
+            if (P.gp == nullptr) TR_TRY(m->alloc((void**)&P.gp, (size_t)m->cfg.max_batch * P.Hp * P.Wp * P.Cout * sizeof(float)));
+            TcConvArgs t;
+            t.x = L.dz; t.w_img = L.tc_wd; t.bias = nullptr; t.y = P.gp; t.B = B; t.H = L.Ho; t.W = L.Wo; t.Ho = L.H; t.Wo = L.W;
+            t.pad = L.k - 1 - m->cfg.pad; t.alpha = 1.f; t.a_bf16 = 1;
+            TR_LAUNCH(m, "conv_dgrad_tcgen05_x3", launch_conv3x3_x3(t, L.Cout, L.Cin, m->sms, s));
+            gp = P.gp;
+        } else
         if (i > 0) {
             ConvLayer& P = m->conv[i - 1];
             if (P.gp == nullptr) TR_TRY(m->alloc((void**)&P.gp, (size_t)m->cfg.max_batch * P.Hp * P.Wp * P.Cout * sizeof(float)));
@@ -207,6 +259,29 @@ int bcad_set_dropout_masks(bcad_model* mm, const float* masks, int B, int mask_b
     BCAD_CUDA_CHECK(cudaEventRecord(m->call_done, s));
     T.drop_B = B;
     T.drop_backward = (mask_backward != 0);
+    m->cached_B = 0;
+    return BCAD_OK;
+}
+
+// Fast training: the eligible conv blocks (3x3, 32 -> 64 filters, maps up to 128 px wide) run their forward, input gradient and weight
+// gradient as split-operand tcgen05 GEMMs (fp32 in / out, products from fp16 / bf16 hi + lo pairs: gradients agree with the fp32 kernels to
+// ~1e-4 relative instead of 1e-6).  Off by default: the reference-pinned fp32 kernels stay the parity anchor.
+int bcad_set_fast_training(bcad_model* mm, int on) {
+    Model* m = reinterpret_cast<Model*>(mm);
+    BCAD_REQUIRE(m, "null model");
+    if (m->tensor_path) { set_error("training runs on the fp32 path: create the model with BCAD_PREC_FP32"); return BCAD_ERR_INVALID; }
+    std::lock_guard<std::mutex> lock(m->mu);
+    if (on) {
+        bool any = false;
+        for (size_t i = 0; i < m->conv.size(); ++i) any = any || tc_train_eligible(m, i);
+        BCAD_REQUIRE(any, "fast training: no conv block of this network has the tensor-core shape (3x3, 32 -> 64 filters, maps <= 128 px wide)");
+        if (m->sms == 0) {
+            DeviceGuard g(m->cfg.device);
+            BCAD_CUDA_CHECK(cudaDeviceGetAttribute(&m->sms, cudaDevAttrMultiProcessorCount, m->cfg.device));
+        }
+    }
+    m->fast_train = (on != 0);
+    m->train.tc_dirty = true;
     m->cached_B = 0;
     return BCAD_OK;
 }
@@ -256,6 +331,7 @@ int bcad_apply_update(bcad_model* mm, const float* grads, int opt, float lr, flo
         TR_TRY(step(D.d_b, T.dense_b_off[j], (size_t)D.out));
     }
     m->cached_B = 0;                                         // cached activations no longer match the weights
+    T.tc_dirty = true;
     TR_TRY(m->mark("end", s));
     BCAD_CUDA_CHECK(cudaEventRecord(m->call_done, s));
     return BCAD_OK;

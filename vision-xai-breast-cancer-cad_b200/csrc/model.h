@@ -34,6 +34,8 @@ struct ConvLayer {
     float* p = nullptr;               // cached pooled output (fp32 path), NHWC
     float* dz = nullptr;              // explain_backward scratch
     float* gp = nullptr;              // gradient w.r.t. this block's pooled output (explain_backward)
+    uint8_t* tc_w = nullptr;          // fast training (sm100_train.cu): fp16 hi / lo image of d_w, and of d_w_dgrad
+    uint8_t* tc_wd = nullptr;
 };
 
 struct DenseLayer {
@@ -56,14 +58,15 @@ struct Xfer {                          // host-buffer pipeline (bcad_predict_exp
     uint8_t* x8[2] = {nullptr, nullptr};      // 8-bit input pixels of a chunk (bcad_predict_explain_host_u8in), allocated on first use
     float* img01[2] = {nullptr, nullptr};     // grey image / 255 of a chunk and its RGB overlays (bcad_gradcam_overlays_host), first use
     uint8_t* ov8[2] = {nullptr, nullptr};
-    float* logits[2] = {nullptr, nullptr};
-    float* probs[2] = {nullptr, nullptr};
-    int32_t* cls[2] = {nullptr, nullptr};
     int32_t* cidx[2] = {nullptr, nullptr};
     // pinned host staging for the small per-image outputs (user arrays may be pageable: a pageable D2H would
     // block the host and serialise the chunk pipeline)
     void* h_small = nullptr;
     size_t h_small_bytes = 0;
+    // device staging of the same outputs for a WHOLE call: every chunk writes its logits / probabilities / classes here and ONE copy at
+    // the end brings them back (three tiny D2H copies per chunk sat between the heat-map copies of the link-bound output stream)
+    void* d_small = nullptr;
+    size_t d_small_bytes = 0;
 };
 
 struct TrainState {                     // row f4: buffers of the training step (allocated on first use)
@@ -83,6 +86,9 @@ struct TrainState {                     // row f4: buffers of the training step 
     bool drop_backward = true;          // mask the gradient too (autograd); false = the NumPy reference's backward
     std::vector<int> drop_off;          // column offset of every hidden layer in a mask row
     int max_ctas = 2048;
+    float* wg_part = nullptr;           // fast training: per-CTA accumulator dumps of the tensor-core weight gradient
+    float* cs_part = nullptr;           //                slab partials of the bias gradient
+    bool tc_dirty = true;               //                the fp16 weight images are older than the fp32 weights
 };
 
 struct TensorPath;                     // tensor_path.cu
@@ -111,6 +117,8 @@ struct Model {
     std::mutex mu;
     std::mutex host_mu;                 // serialises the host-buffer calls of one handle (shared staging, streams, events)
     Refine refine;
+    bool fast_train = false;            // bcad_set_fast_training: tensor-core (split-operand) kernels for the eligible conv blocks of the training step
+    int sms = 0;
     int target = BCAD_TARGET_CONV_ACT;  // bcad_set_explain_target
     int heat_h = 0, heat_w = 0;         // heat-map size of the call in flight (in_h x in_w unless bcad_predict_explain_sized asks otherwise)
     const int32_t* n_dev = nullptr;     // refinement TWIN only: device pointer to the live image count of its launches
@@ -141,6 +149,10 @@ struct Model {
 
 // dense backward shared by both paths: d_top -> ... -> dz of dense[0] (left in dense[0].h) and, when
 // g_flat != nullptr, on to the flattened pool output
+// fast training: which conv blocks run on the tensor-core kernels, and keeping their fp16 weight images current
+bool tc_train_eligible(const Model* m, size_t i);
+int tc_train_refresh(Model* m, cudaStream_t s);
+
 int dense_backward(Model* m, int n, const int32_t* class_idx, int grad_mode, float* g_flat, cudaStream_t s);
 
 bool fused_head_ok(const Model* m);

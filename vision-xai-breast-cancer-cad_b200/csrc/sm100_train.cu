@@ -1,0 +1,565 @@
+// Tensor-core kernels of the training step: the second conv block's forward, input gradient and weight gradient as
+// split-operand ("x3") tcgen05 implicit GEMMs that read and write the fp32 NHWC tensors of the fp32 path directly.
+//
+// Every fp32 value v is split on the fly into hi = round16(v) and lo = round16(v - hi); a product is a_hi b_hi + a_lo b_hi + a_hi b_lo
+// with fp32 accumulation in TMEM.  The forward splits into fp16 pairs (2^-22 relative); the two gradient kernels split BOTH operands into
+// bf16 pairs (2^-16, but fp32's exponent range: no loss scaling; one MMA takes one 16-bit type -- mixing fp16 and bf16 operands raises
+// "illegal instruction").  Reference: Classes/CNNModel.py:227-240 (conv forward), :320-355 (dX, dF of a conv block),
+// ADCNNM.py:72-78 / autograd.
+//
+//   conv3x3_x3_kernel<CIN, COUT, ABF>   y[b, oy, ox, :] = act(sum_taps x[b, oy+dy-pad, ox+dx-pad, :] . w[tap] + bias)      (fwd: 32 -> 64, dgrad: 64 -> 32)
+//   wgrad3x3_x3_kernel                   dW[tap][ci][co] = sum_{b, y, x} X[b, y+dy-pad, x+dx-pad, ci] dY[b, y, x, co]           (32 -> 64)
+//
+// Common structure (as the second block of conv_fused_kernel): a persistent CTA walks (image, row band) items; producer warps convert
+// input rows into a shared-memory ring of "C8-planar" rows [plane hi|lo][channel octet][pixel slot][8 x 16 bit] -- a tap's column shift is a
+// +16-byte descriptor offset, a row is loaded once per band --; one thread issues the MMAs; four epilogue warps drain TMEM.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdio.h>
+
+#include "../../include/bcad.h"
+#include "common.cuh"
+#include "sm100.cuh"
+#include "sm100_train.h"
+
+namespace bcad {
+
+using namespace sm100;
+
+namespace {
+
+constexpr int TC_XP = 130;                    // pixel slots per ring row (128 + 2 halo): LBO = 2080 B keeps the producers' 16-byte stores conflict-free
+constexpr int TC_PW = 8;                      // producer warps
+constexpr int TC_THREADS = 32 * (TC_PW + 1 + 4);
+constexpr int TC_NB = 4;                      // accumulator buffers (output rows in flight between the issuer and the epilogue)
+
+__device__ __forceinline__ uint32_t split_hi_lo(float a, float b, uint32_t& lo, bool bf) {
+    if (bf) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        const float2 hf = __bfloat1622float2(h);
+        const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+        lo = *reinterpret_cast<const uint32_t*>(&l);
+        return *reinterpret_cast<const uint32_t*>(&h);
+    }
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// instruction descriptor, kind::f16, fp32 accumulate; formats 0 = fp16, 1 = bf16; major bits 15 (A) / 16 (B): 1 = MN-major
+__host__ __device__ constexpr uint32_t tc_idesc(int M, int N, int a_fmt, int b_fmt, int a_mn, int b_mn) {
+    return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int CIN, int COUT>
+struct TcSmem {
+    static constexpr int CHUNKS = CIN / 8;
+    static constexpr int LBO = TC_XP * 16;
+    static constexpr int PLANEB = CHUNKS * LBO;
+    static constexpr int ROWB = 2 * PLANEB;
+    static constexpr int R = (CIN <= 32) ? 6 : 4;
+    static constexpr int WPL = 9 * CHUNKS * COUT * 16;                 // one weight plane [tap][octet][COUT][16 B]
+    static constexpr int OFF_W = 0;
+    static constexpr int OFF_RING = 2 * WPL;
+    static constexpr int OFF_BIAS = OFF_RING + R * ROWB;
+    static constexpr int OFF_BAR = OFF_BIAS + COUT * 4;
+    static constexpr int TOTAL = OFF_BAR + 256;
+};
+
+// row of `n8` items of 8 fp32 values -> hi / lo 16-byte items of a ring row (256 producer threads)
+template <int CIN>
+__device__ __forceinline__ void produce_row(const float* __restrict__ src, int W, uint8_t* row, int planeb, int pad, int ptid, bool bf) {
+    constexpr int CHUNKS = CIN / 8;
+    for (int it = ptid; it < W * CHUNKS; it += 32 * TC_PW) {
+        const int px = it / CHUNKS, ch = it % CHUNKS;
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + (size_t)px * CIN + ch * 8));
+        const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + (size_t)px * CIN + ch * 8 + 4));
+        uint4 hi, lo;
+        hi.x = split_hi_lo(v0.x, v0.y, lo.x, bf);
+        hi.y = split_hi_lo(v0.z, v0.w, lo.y, bf);
+        hi.z = split_hi_lo(v1.x, v1.y, lo.z, bf);
+        hi.w = split_hi_lo(v1.z, v1.w, lo.w, bf);
+        uint8_t* dst = row + ch * (TC_XP * 16) + (px + pad) * 16;
+        *reinterpret_cast<uint4*>(dst) = hi;
+        *reinterpret_cast<uint4*>(dst + planeb) = lo;
+    }
+}
+
+template <int CIN, int COUT, bool ABF>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_x3_kernel(TcConvArgs a) {
+    using L = TcSmem<CIN, COUT>;
+    constexpr int R = L::R, NB = TC_NB;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* s_w = smem + L::OFF_W;
+    uint8_t* s_ring = smem + L::OFF_RING;
+    float* s_bias = reinterpret_cast<float*>(smem + L::OFF_BIAS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+    uint64_t* full = bars;                 // [R] producers -> MMA (count TC_PW)
+    uint64_t* empty = bars + R;            // [R] MMA -> producers
+    uint64_t* tfull = bars + 2 * R;        // [NB] MMA -> epilogue
+    uint64_t* tempty = bars + 2 * R + NB;  // [NB] epilogue -> MMA (count 4)
+    uint64_t* wbar = bars + 2 * R + 2 * NB;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * R + 2 * NB + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < (R * L::ROWB) / 16; i += TC_THREADS) reinterpret_cast<uint4*>(s_ring)[i] = make_uint4(0, 0, 0, 0);   // halo slots stay zero
+    if (tid < COUT) s_bias[tid] = a.bias ? a.bias[tid] : 0.f;
+    if (tid == 0) {
+        for (int i = 0; i < R; ++i) { mbar_init(&full[i], TC_PW); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < NB; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        mbar_init(wbar, 1);
+        fence_barrier_init();
+    }
+    constexpr uint32_t TCOLS = (NB * COUT <= 128) ? 128 : 256;
+    if (warp == 0) {
+        tmem_alloc(tmem_slot, TCOLS);
+        tmem_relinquish();
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int n_items = a.B * a.bands;
+
+    if (warp < TC_PW) {
+        // ================================ producers: fp32 NHWC rows -> hi / lo ring rows ================================
+        uint32_t g = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int b = item / a.bands, y0 = (item % a.bands) * a.band_rows;
+            const int nrows = min(a.band_rows, a.Ho - y0);
+            for (int i = 0; i < nrows + 2; ++i, ++g) {
+                const uint32_t slot = g % R;
+                if (g >= (uint32_t)R) mbar_wait(&empty[slot], ((g / R) - 1) & 1);
+                const int in_row = y0 - a.pad + i;
+                if (in_row >= 0 && in_row < a.H) {
+                    produce_row<CIN>(a.x + ((size_t)b * a.H + in_row) * a.W * CIN, a.W, s_ring + slot * L::ROWB, L::PLANEB, a.pad, tid, ABF);
+                    fence_proxy_async();
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[slot]);
+            }
+        }
+    } else if (warp == TC_PW) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            constexpr int WB = 2 * L::WPL;
+            mbar_arrive_expect_tx(wbar, WB);
+            for (int off = 0; off < WB; off += 16384) bulk_g2s(s_w + off, a.w_img + off, min(16384, WB - off), wbar);
+        }
+        const bool leader = elect_one();
+        constexpr uint32_t idesc = tc_idesc(128, COUT, ABF ? 1 : 0, ABF ? 1 : 0, 0, 0);     // kind::f16 wants A and B of ONE 16-bit type
+        constexpr uint32_t d_hi = (uint32_t)(128 >> 4) | (1u << 14);                 // SBO 128, descriptor version 1
+        constexpr uint32_t a_lo_t = (uint32_t)(L::LBO >> 4) << 16;
+        constexpr uint32_t b_lo_t = (uint32_t)((COUT * 16) >> 4) << 16;
+        const uint32_t w_base = smem_u32(s_w), ring_base = smem_u32(s_ring);
+        mbar_wait(wbar, 0);
+        uint32_t gbase = 0, acc_it = 0;
+        auto wait_full = [&](uint32_t gs) { mbar_wait(&full[gs % R], (gs / R) & 1u); };
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int y0 = (item % a.bands) * a.band_rows;
+            const int nrows = min(a.band_rows, a.Ho - y0);
+            for (int r = 0; r < nrows; ++r, ++acc_it) {
+                if (r == 0) { wait_full(gbase); wait_full(gbase + 1); }
+                wait_full(gbase + r + 2);
+                const uint32_t j = acc_it % NB;
+                if (acc_it >= (uint32_t)NB) mbar_wait(&tempty[j], ((acc_it / NB) - 1) & 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem + j * COUT;
+                uint32_t acc = 0;
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    const int in_row = y0 - a.pad + r + dy;
+                    if (in_row < 0 || in_row >= a.H) continue;                      // padding row: contributes nothing
+                    const uint32_t row_base = ring_base + ((gbase + (uint32_t)(r + dy)) % R) * L::ROWB;
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                        for (int ks = 0; ks < CIN / 16; ++ks)
+#pragma unroll
+                            for (int combo = 0; combo < 3; ++combo) {           // a_hi w_hi, a_lo w_hi, a_hi w_lo
+                                const uint32_t a_addr = row_base + (combo == 1 ? L::PLANEB : 0) + ks * 2 * L::LBO + dx * 16;
+                                const uint32_t b_addr = w_base + (combo == 2 ? L::WPL : 0) + ((dy * 3 + dx) * L::CHUNKS + 2 * ks) * (COUT * 16);
+                                umma_f16_if(leader, d_tmem, desc64(a_lo_t | ((a_addr & 0x3FFFFu) >> 4), d_hi), desc64(b_lo_t | ((b_addr & 0x3FFFFu) >> 4), d_hi),
+                                            idesc, acc);
+                                acc = 1u;
+                            }
+                }
+                umma_commit_if(leader, &empty[(gbase + (uint32_t)r) % R]);
+                umma_commit_if(leader, &tfull[j]);
+            }
+            umma_commit_if(leader, &empty[(gbase + (uint32_t)nrows) % R]);
+            umma_commit_if(leader, &empty[(gbase + (uint32_t)nrows + 1) % R]);
+            gbase += (uint32_t)nrows + 2;
+        }
+    } else {
+        // ================================ epilogue: TMEM -> (+ bias, LeakyReLU) -> fp32 NHWC ================================
+        const int quad = warp & 3;
+        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+        const int x = quad * 32 + lane;
+        uint32_t acc_it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int b = item / a.bands, y0 = (item % a.bands) * a.band_rows;
+            const int nrows = min(a.band_rows, a.Ho - y0);
+            for (int r = 0; r < nrows; ++r, ++acc_it) {
+                const uint32_t j = acc_it % NB;
+                mbar_wait(&tfull[j], (acc_it / NB) & 1);
+                tc_fence_after();
+                float* dst = a.y + (((size_t)b * a.Ho + (y0 + r)) * a.Wo + x) * COUT;
+#pragma unroll
+                for (int half = 0; half < COUT / 32; ++half) {
+                    float v[32];
+                    tmem_ld32(tmem + lane_off + j * COUT + half * 32, v);
+                    tmem_ld_wait();
+                    if (half == COUT / 32 - 1) {                    // the row is in registers: hand the buffer back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[j]);
+                    }
+                    if (x < a.Wo) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float4 o;
+                            o.x = v[4 * q] + s_bias[half * 32 + 4 * q];
+                            o.y = v[4 * q + 1] + s_bias[half * 32 + 4 * q + 1];
+                            o.z = v[4 * q + 2] + s_bias[half * 32 + 4 * q + 2];
+                            o.w = v[4 * q + 3] + s_bias[half * 32 + 4 * q + 3];
+                            o.x = o.x > 0.f ? o.x : a.alpha * o.x;
+                            o.y = o.y > 0.f ? o.y : a.alpha * o.y;
+                            o.z = o.z > 0.f ? o.z : a.alpha * o.z;
+                            o.w = o.w > 0.f ? o.w : a.alpha * o.w;
+                            *reinterpret_cast<float4*>(dst + half * 32 + 4 * q) = o;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, TCOLS);
+}
+
+// fp32 [9][CIN][CoutPad] (the fp32 path's packed filters) -> fp16 hi / lo planes [plane][tap][CIN/8][COUT][8]
+__global__ void pack_w_x3_kernel(const float* __restrict__ w, uint8_t* __restrict__ img, int CIN, int COUT, int CoutPad, int bf) {
+    const int n = 9 * CIN * COUT;
+    const size_t wpl = (size_t)9 * (CIN / 8) * COUT * 16;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int co = i % COUT, ci = (i / COUT) % CIN, tap = i / (COUT * CIN);
+        const float v = w[((size_t)tap * CIN + ci) * CoutPad + co];
+        const size_t off = (((size_t)tap * (CIN / 8) + ci / 8) * COUT + co) * 16 + (ci % 8) * 2;
+        if (bf) {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            *reinterpret_cast<__nv_bfloat16*>(img + off) = hi;
+            *reinterpret_cast<__nv_bfloat16*>(img + wpl + off) = __float2bfloat16_rn(v - __bfloat162float(hi));
+        } else {
+            const __half hi = __float2half_rn(v);
+            *reinterpret_cast<__half*>(img + off) = hi;
+            *reinterpret_cast<__half*>(img + wpl + off) = __float2half_rn(v - __half2float(hi));
+        }
+    }
+}
+
+// 2x2 / 2 max pool of an NHWC fp32 map (floor: Classes/CNNModel.py:245-261, nn.MaxPool2d(2)); C % 4 == 0
+__global__ void maxpool2x2_nhwc_kernel(const float* __restrict__ y, float* __restrict__ p, int Ho, int Wo, int Hp, int Wp, int C4, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4);
+        size_t t = i / C4;
+        const int px = (int)(t % Wp);
+        t /= Wp;
+        const int py = (int)(t % Hp);
+        const size_t b = t / Hp;
+        const float4* r0 = reinterpret_cast<const float4*>(y) + ((b * Ho + 2 * py) * Wo + 2 * px) * C4 + c;
+        const float4* r1 = r0 + (size_t)Wo * C4;
+        const float4 a0 = r0[0], a1 = r0[C4], a2 = r1[0], a3 = r1[C4];
+        float4 o;
+        o.x = fmaxf(fmaxf(a0.x, a1.x), fmaxf(a2.x, a3.x));
+        o.y = fmaxf(fmaxf(a0.y, a1.y), fmaxf(a2.y, a3.y));
+        o.z = fmaxf(fmaxf(a0.z, a1.z), fmaxf(a2.z, a3.z));
+        o.w = fmaxf(fmaxf(a0.w, a1.w), fmaxf(a2.w, a3.w));
+        reinterpret_cast<float4*>(p)[i] = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Weight gradient of a 3x3 conv block, 32 -> 64 channels:  dW[dy][dx][ci][co] = sum_{b, y, x} X[b, y+dy-pad, x+dx-pad, ci] dY[b, y, x, co].
+// The pixel index is the GEMM's K: both operands are read MN-major (8 channels = one 16-byte item, consecutive pixels 16 bytes apart --
+// exactly the C8-planar rows above), so a tap's column shift is again a descriptor offset.  A work unit is (image, output row pair, 64-pixel
+// half): the A operand stacks the two dY rows (M = 2 x 64 filters), the B operand is one of the four X rows y'-pad .. y'-pad+3 (N = 32).
+// X row k feeds tap dy = k of the first dY row (accumulator lanes 0-63) and tap dy = k - 1 of the second (lanes 64-127), so twelve 32-column
+// accumulators T[dx][k] collect everything; they stay in TMEM for the CTA's whole life and are dumped once (partials[cta][dx][k][lane][ci]).
+// ---------------------------------------------------------------------------------------------------------------------------------
+constexpr int WG_STAGES = 3;
+constexpr int WG_XS = 66;                                       // X pixel slots per half row (64 + 2 halo)
+constexpr int WG_XROWB = 2 * 4 * WG_XS * 16;                    // [plane][4 octets][66][16 B]
+constexpr int WG_XPLANE = 4 * WG_XS * 16;
+constexpr int WG_YPLANE = 2 * 8 * 64 * 16;                      // [row r][8 octets][64 px][16 B]
+constexpr int WG_YB = 2 * WG_YPLANE;
+constexpr int WG_STAGEB = 4 * WG_XROWB + WG_YB;
+constexpr int WG_OFF_BAR = WG_STAGES * WG_STAGEB;
+constexpr int WG_TOTAL = WG_OFF_BAR + 128;
+constexpr int WG_THREADS = 32 * (TC_PW + 1 + 4);
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad3x3_x3_kernel(TcWgradArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_OFF_BAR);
+    uint64_t* full = bars;                       // [S] producers -> MMA (count TC_PW)
+    uint64_t* empty = bars + WG_STAGES;          // [S] MMA -> producers
+    uint64_t* done = bars + 2 * WG_STAGES;       // all MMAs retired -> epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_STAGES + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], TC_PW); mbar_init(&empty[i], 1); }
+        mbar_init(done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int npairs = (a.Ho + 1) / 2, nhalf = (a.Wo + 63) / 64;
+    const int n_units = a.B * npairs * nhalf;
+
+    if (warp < TC_PW) {
+        // ================================ producers ================================
+        uint32_t g = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++g) {
+            const int h = u % nhalf, p = (u / nhalf) % npairs, b = u / (nhalf * npairs);
+            const int x0 = h * 64;
+            const uint32_t st = g % WG_STAGES;
+            if (g >= (uint32_t)WG_STAGES) mbar_wait(&empty[st], ((g / WG_STAGES) - 1) & 1);
+            uint8_t* sx = smem + st * WG_STAGEB;
+            uint8_t* sy = sx + 4 * WG_XROWB;
+            // X rows (bf16 pairs, like dY: one MMA takes one 16-bit type): slot s = pixel x0 + s - pad, zero outside the map
+            for (int it = tid; it < 4 * WG_XS * 4; it += 32 * TC_PW) {
+                const int ch = it & 3, sl = (it >> 2) % WG_XS, k = it / (4 * WG_XS);
+                const int in_row = 2 * p - a.pad + k, px = x0 + sl - a.pad;
+                if (in_row < 0 || in_row >= a.H) continue;                       // the issuer skips this row
+                uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+                if (px >= 0 && px < a.W) {
+                    const float* src = a.x + (((size_t)b * a.H + in_row) * a.W + px) * 32 + ch * 8;
+                    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src)), v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+                    hi.x = split_hi_lo(v0.x, v0.y, lo.x, true);
+                    hi.y = split_hi_lo(v0.z, v0.w, lo.y, true);
+                    hi.z = split_hi_lo(v1.x, v1.y, lo.z, true);
+                    hi.w = split_hi_lo(v1.z, v1.w, lo.w, true);
+                }
+                uint8_t* dst = sx + k * WG_XROWB + ch * (WG_XS * 16) + sl * 16;
+                *reinterpret_cast<uint4*>(dst) = hi;
+                *reinterpret_cast<uint4*>(dst + WG_XPLANE) = lo;
+            }
+            // dY rows (bf16 pairs): slot s = pixel x0 + s, zero outside the map / below the last row
+            for (int it = tid; it < 2 * 64 * 8; it += 32 * TC_PW) {
+                const int ch = it & 7, sl = (it >> 3) & 63, r = it >> 9;
+                const int y = 2 * p + r, px = x0 + sl;
+                uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+                if (y < a.Ho && px < a.Wo) {
+                    const float* src = a.dy + (((size_t)b * a.Ho + y) * a.Wo + px) * 64 + ch * 8;
+                    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src)), v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+                    hi.x = split_hi_lo(v0.x, v0.y, lo.x, true);
+                    hi.y = split_hi_lo(v0.z, v0.w, lo.y, true);
+                    hi.z = split_hi_lo(v1.x, v1.y, lo.z, true);
+                    hi.w = split_hi_lo(v1.z, v1.w, lo.w, true);
+                }
+                uint8_t* dst = sy + (r * 8 + ch) * (64 * 16) + sl * 16;
+                *reinterpret_cast<uint4*>(dst) = hi;
+                *reinterpret_cast<uint4*>(dst + WG_YPLANE) = lo;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[st]);
+        }
+    } else if (warp == TC_PW) {
+        // ================================ MMA issuer ================================
+        const bool leader = elect_one();
+        constexpr uint32_t idesc = tc_idesc(128, 32, 1, 1, 1, 1);              // A = dY, B = X: bf16, both MN-major
+        // MN-major, no swizzle: LBO = byte distance between 8-pixel (K) groups = 128, SBO = byte distance between channel octets
+        constexpr uint32_t a_hi = (uint32_t)((64 * 16) >> 4) | (1u << 14);
+        constexpr uint32_t b_hi = (uint32_t)((WG_XS * 16) >> 4) | (1u << 14);
+        constexpr uint32_t lbo_t = (uint32_t)(128 >> 4) << 16;
+        uint32_t started = 0;                                                    // bit dx * 4 + k: accumulator T[dx][k] has been written
+        uint32_t g = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++g) {
+            const int p = (u / nhalf) % npairs;
+            const uint32_t st = g % WG_STAGES;
+            mbar_wait(&full[st], (g / WG_STAGES) & 1);
+            tc_fence_after();
+            const uint32_t sx = smem_u32(smem + st * WG_STAGEB), sy = sx + 4 * WG_XROWB;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int in_row = 2 * p - a.pad + k;
+                if (in_row < 0 || in_row >= a.H) continue;
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const uint32_t bit = 1u << (dx * 4 + k);
+                    uint32_t acc = (started & bit) ? 1u : 0u;
+                    started |= bit;
+                    const uint32_t d_tmem = tmem + (dx * 4 + k) * 32;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+                        for (int combo = 0; combo < 3; ++combo) {               // dY_hi X_hi, dY_lo X_hi, dY_hi X_lo
+                            const uint32_t a_addr = sy + (combo == 1 ? WG_YPLANE : 0) + ks * 256;
+                            const uint32_t b_addr = sx + k * WG_XROWB + (combo == 2 ? WG_XPLANE : 0) + (ks * 16 + dx) * 16;
+                            umma_f16_if(leader, d_tmem, desc64(lbo_t | ((a_addr & 0x3FFFFu) >> 4), a_hi), desc64(lbo_t | ((b_addr & 0x3FFFFu) >> 4), b_hi), idesc, acc);
+                            acc = 1u;
+                        }
+                }
+            }
+            umma_commit_if(leader, &empty[st]);
+        }
+        // accumulators that never received an MMA hold garbage: tell the epilogue which ones are live (before the commit it waits on)
+        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(tmem_slot + 1) = started;
+        __threadfence_block();
+        __syncwarp();
+        umma_commit_if(leader, done);
+    } else {
+        // ================================ epilogue: dump the accumulators once ================================
+        const int quad = warp & 3;
+        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+        const int row = quad * 32 + lane;
+        mbar_wait(done, 0);
+        tc_fence_after();
+        __syncwarp();
+        const uint32_t started = *reinterpret_cast<volatile uint32_t*>(tmem_slot + 1);
+        float* dst = a.partials + (size_t)blockIdx.x * (12 * 128 * 32);
+#pragma unroll 1
+        for (int t = 0; t < 12; ++t) {
+            float v[32];
+            tmem_ld32(tmem + lane_off + t * 32, v);
+            tmem_ld_wait();
+            const bool live = (started >> t) & 1u;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<float4*>(dst + ((size_t)t * 128 + row) * 32 + 4 * q) =
+                    live ? make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// dW[(dy, dx)][ci][co] = sum over CTAs of T[dx][dy][lane co][ci] + T[dx][dy + 1][lane 64 + co][ci], into the fp32 path's [9][32][CoutPad] layout
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int nparts, float* __restrict__ dw, int CoutPad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;          // over 9 * 32 * 64
+    if (i >= 9 * 32 * 64) return;
+    const int co = i & 63, ci = (i >> 6) & 31, tap = i >> 11;
+    const int dy = tap / 3, dx = tap % 3;
+    const size_t o0 = ((size_t)(dx * 4 + dy) * 128 + co) * 32 + ci, o1 = ((size_t)(dx * 4 + dy + 1) * 128 + 64 + co) * 32 + ci;
+    float s0 = 0.f, s1 = 0.f;
+    for (int c = 0; c < nparts; ++c) {
+        s0 += part[(size_t)c * (12 * 128 * 32) + o0];
+        s1 += part[(size_t)c * (12 * 128 * 32) + o1];
+    }
+    dw[((size_t)tap * 32 + ci) * CoutPad + co] = s0 + s1;
+}
+
+// out[n] = sum_k A[k][64] over a tall matrix (bias gradient of the 64-filter block): fixed slabs of rows per CTA, fixed-order second pass
+__global__ void __launch_bounds__(256) colsum64_part_kernel(const float* __restrict__ A, float* __restrict__ part, size_t K, int slab) {
+    __shared__ float sm[4][64];
+    const int n = threadIdx.x & 63, q = threadIdx.x >> 6;
+    const size_t k0 = (size_t)blockIdx.x * slab, k1 = k0 + slab < K ? k0 + slab : K;
+    float acc = 0.f;
+    for (size_t k = k0 + q; k < k1; k += 4) acc += A[k * 64 + n];
+    sm[q][n] = acc;
+    __syncthreads();
+    if (q == 0) part[(size_t)blockIdx.x * 64 + n] = (sm[0][n] + sm[1][n]) + (sm[2][n] + sm[3][n]);
+}
+__global__ void colsum64_final_kernel(const float* __restrict__ part, int nparts, float* __restrict__ out) {
+    const int n = threadIdx.x;
+    float acc = 0.f;
+    for (int c = 0; c < nparts; ++c) acc += part[(size_t)c * 64 + n];
+    out[n] = acc;
+}
+
+template <int CIN, int COUT, bool ABF>
+int launch_conv_t(const TcConvArgs& a, int grid, cudaStream_t s) {
+    using L = TcSmem<CIN, COUT>;
+    static_assert(L::TOTAL <= 227 * 1024, "conv3x3_x3: shared memory budget");
+    BCAD_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_x3_kernel<CIN, COUT, ABF>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    conv3x3_x3_kernel<CIN, COUT, ABF><<<grid, TC_THREADS, L::TOTAL, s>>>(a);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+}  // namespace
+
+bool conv3x3_x3_supported(int Cin, int Cout, int k, int W, int Wo, int pad) {
+    return k == 3 && ((Cin == 32 && Cout == 64) || (Cin == 64 && Cout == 32)) && Wo <= 128 && W + 2 * pad <= TC_XP && pad >= 0 && pad <= 2;
+}
+
+size_t conv3x3_x3_weight_bytes(int Cin, int Cout) { return (size_t)2 * 9 * (Cin / 8) * Cout * 16; }
+
+int launch_pack_w_x3(const float* w, uint8_t* img, int Cin, int Cout, int CoutPad, bool bf16, cudaStream_t s) {
+    pack_w_x3_kernel<<<cdiv(9 * Cin * Cout, 256), 256, 0, s>>>(w, img, Cin, Cout, CoutPad, bf16 ? 1 : 0);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+int launch_maxpool2x2_nhwc(const float* y, float* p, int B, int Ho, int Wo, int C, cudaStream_t s) {
+    BCAD_REQUIRE(C % 4 == 0, "maxpool2x2_nhwc: channels must be a multiple of 4");
+    const int Hp = Ho / 2, Wp = Wo / 2;
+    const size_t n = (size_t)B * Hp * Wp * (C / 4);
+    if (n == 0) return BCAD_OK;
+    const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    maxpool2x2_nhwc_kernel<<<grid, 256, 0, s>>>(y, p, Ho, Wo, Hp, Wp, C / 4, n);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+bool wgrad3x3_x3_supported(int Cin, int Cout, int k, int W, int Wo, int pad) {
+    return k == 3 && Cin == 32 && Cout == 64 && Wo <= 128 && W <= 128 && pad >= 0 && pad <= 1;
+}
+
+size_t wgrad3x3_x3_partial_floats(int sms) { return (size_t)sms * 12 * 128 * 32; }
+
+int launch_wgrad3x3_x3(const TcWgradArgs& a, float* dw, int CoutPad, int sms, cudaStream_t s) {
+    static_assert(WG_TOTAL <= 227 * 1024, "wgrad3x3_x3: shared memory budget");
+    BCAD_REQUIRE(wgrad3x3_x3_supported(32, 64, 3, a.W, a.Wo, a.pad), "wgrad3x3_x3: unsupported shape (W %d, Wo %d, pad %d)", a.W, a.Wo, a.pad);
+    const int units = a.B * ((a.Ho + 1) / 2) * ((a.Wo + 63) / 64);
+    const int grid = units < sms ? units : sms;
+    BCAD_CUDA_CHECK(cudaFuncSetAttribute(wgrad3x3_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_TOTAL));
+    wgrad3x3_x3_kernel<<<grid, WG_THREADS, WG_TOTAL, s>>>(a);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    wgrad_reduce_kernel<<<cdiv(9 * 32 * 64, 256), 256, 0, s>>>(a.partials, grid, dw, CoutPad);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+int launch_colsum64(const float* A, float* scratch, float* out, size_t K, cudaStream_t s) {
+    const int slab = 2048;
+    const int nparts = (int)((K + slab - 1) / slab);
+    BCAD_REQUIRE(nparts <= 4096, "colsum64: %zu rows exceed the scratch (4096 slabs)", K);
+    colsum64_part_kernel<<<nparts, 256, 0, s>>>(A, scratch, K, slab);
+    colsum64_final_kernel<<<1, 64, 0, s>>>(scratch, nparts, out);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+int launch_conv3x3_x3(const TcConvArgs& a0, int Cin, int Cout, int sms, cudaStream_t s) {
+    BCAD_REQUIRE(conv3x3_x3_supported(Cin, Cout, 3, a0.W, a0.Wo, a0.pad), "conv3x3_x3: unsupported shape %d -> %d, W %d", Cin, Cout, a0.W);
+    TcConvArgs a = a0;
+    // rows per work item: the split that minimises the busiest CTA's rows (+ 2 halo rows of producer work per item)
+    int best = 8, best_cost = 1 << 30;
+    for (int br = 4; br <= 64; br *= 2) {
+        const int items = a.B * cdiv(a.Ho, br);
+        const int cost = cdiv(items, sms) * (br + 1);
+        if (cost < best_cost) { best_cost = cost; best = br; }
+    }
+    a.band_rows = best;
+    a.bands = cdiv(a.Ho, a.band_rows);
+    const int items = a.B * a.bands;
+    const int grid = items < sms ? items : sms;
+    if (Cin == 32 && Cout == 64) return a.a_bf16 ? launch_conv_t<32, 64, true>(a, grid, s) : launch_conv_t<32, 64, false>(a, grid, s);
+    return a.a_bf16 ? launch_conv_t<64, 32, true>(a, grid, s) : launch_conv_t<64, 32, false>(a, grid, s);
+}
+
+}  // namespace bcad

@@ -1,0 +1,37 @@
+// Launchers of the training step's tensor-core kernels (sm100_train.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bcad {
+
+struct TcConvArgs {
+    const float* x;        // fp32 NHWC [B][H][W][Cin]
+    const uint8_t* w_img;  // launch_pack_w_x3 image: hi / lo planes [plane][tap][Cin/8][Cout][8], fp16 -- or bf16 when a_bf16 (same type as the input)
+    const float* bias;     // fp32 [Cout] or nullptr
+    float* y;              // fp32 NHWC [B][Ho][Wo][Cout]
+    int B, H, W, Ho, Wo, pad;
+    float alpha;           // LeakyReLU slope (1 = identity)
+    int a_bf16;            // the input splits into bf16 pairs (gradients: fp32's range) instead of fp16 pairs
+    int bands = 0, band_rows = 0;   // set by the launcher
+};
+bool conv3x3_x3_supported(int Cin, int Cout, int k, int W, int Wo, int pad);
+size_t conv3x3_x3_weight_bytes(int Cin, int Cout);
+// w: the fp32 path's packed filters [9][Cin][CoutPad]
+int launch_pack_w_x3(const float* w, uint8_t* img, int Cin, int Cout, int CoutPad, bool bf16, cudaStream_t s);
+int launch_conv3x3_x3(const TcConvArgs& a, int Cin, int Cout, int sms, cudaStream_t s);
+struct TcWgradArgs {
+    const float* x;        // the block's input, fp32 NHWC [B][H][W][32]
+    const float* dy;       // gradient w.r.t. the block's pre-activation, fp32 NHWC [B][Ho][Wo][64]
+    float* partials;       // [grid][12][128][32] fp32 scratch (wgrad3x3_x3_partial_floats)
+    int B, H, W, Ho, Wo, pad;
+};
+bool wgrad3x3_x3_supported(int Cin, int Cout, int k, int W, int Wo, int pad);
+size_t wgrad3x3_x3_partial_floats(int sms);
+// dw: [9][32][CoutPad] fp32 (the fp32 path's gradient layout), overwritten
+int launch_wgrad3x3_x3(const TcWgradArgs& a, float* dw, int CoutPad, int sms, cudaStream_t s);
+// out[64] = column sums of A[K][64]; scratch: 4096 * 64 floats
+int launch_colsum64(const float* A, float* scratch, float* out, size_t K, cudaStream_t s);
+int launch_maxpool2x2_nhwc(const float* y, float* p, int B, int Ho, int Wo, int C, cudaStream_t s);
+
+}  // namespace bcad

@@ -323,6 +323,11 @@ class Engine:
             _lib.check(self.lib.bcad_train_backward_part(self._h, _ptr(x), _ptr(lab), B, _ptr(grads), _ptr(loss), int(part), self._stream()))
         return grads, loss
 
+    def set_fast_training(self, on: bool = True):
+        """Training step on the tensor cores where the shape allows (bcad_set_fast_training): the 32 -> 64 conv block's forward, input
+        gradient and weight gradient as split-operand tcgen05 GEMMs (~1e-4 relative against the fp32 kernels).  fp32 handles only."""
+        _lib.check(self.lib.bcad_set_fast_training(self._h, 1 if on else 0))
+
     def set_dropout_masks(self, masks, mask_backward: bool = True):
         """masks [B, sum(hidden_units)] multipliers (0 or 1/(1-rate)) for the next forwards of exactly B images; None = off.
         mask_backward=False restates the NumPy reference, whose backward ignores the mask (Classes/CNNModel.py:307-316)."""
