@@ -242,16 +242,18 @@ def test_nccl_data_parallel_step_matches_full_batch():
     assert r.returncode == 0 and "DP-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize("shape,pad,B", [
-    ((64, 64, 1), 1, 6),        # second block on 32x32 maps
-    ((61, 61, 1), 0, 5),        # valid conv, odd maps: 29x29 -> 27x27 (a last row without a partner, "full" dgrad padding of 2)
-    ((40, 200, 1), 1, 4),       # 100-pixel rows: two 64-pixel halves in the weight gradient
+@pytest.mark.parametrize("shape,pad,B,hidden", [
+    ((64, 64, 1), 1, 6, [32, 16]),        # second block on 32x32 maps
+    ((61, 61, 1), 0, 5, [32, 16]),        # valid conv, odd maps: 29x29 -> 27x27 (a last row without a partner, "full" dgrad padding of 2)
+    ((40, 200, 1), 1, 4, [32, 16]),       # 100-pixel rows: two 64-pixel halves in the weight gradient
+    ((64, 64, 1), 1, 6, [128, 16]),       # + the first dense layer's weight / input gradient GEMMs on tcgen05 (128 units: one half)
+    ((64, 64, 1), 1, 5, [256, 32]),       #   256 units (the canonical width): two halves, four streamed stages per tile
 ])
-def test_fast_training_matches_the_fp32_kernels(shape, pad, B):
+def test_fast_training_matches_the_fp32_kernels(shape, pad, B, hidden):
     """bcad_set_fast_training: the 32 -> 64 conv block's forward, input gradient and weight gradient on tcgen05 (split operands) against
     the reference-pinned fp32 kernels of the same handle: logits, loss and every gradient tensor to 1e-3 of the tensor's largest entry
     (measured ~1e-5), then two Adam steps stay together."""
-    cfg = ocnn.NetConfig(shape, 2, [(32, 3), (64, 3)], [32, 16], 0.01, 0.01, pad, "chw", "first", "logits")
+    cfg = ocnn.NetConfig(shape, 2, [(32, 3), (64, 3)], hidden, 0.01, 0.01, pad, "chw", "first", "logits")
     p = ocnn.init_params(cfg, seed=3, bias_std=0.05)
     x = torch.from_numpy(ocnn.synth_images(B, shape, seed=9)).cuda()
     labels = np.arange(B) % 2

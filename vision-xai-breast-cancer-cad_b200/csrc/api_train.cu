@@ -165,10 +165,22 @@ int bcad_train_backward_part(bcad_model* mm, const float* x, const int32_t* labe
             if (T.drop_B) TR_LAUNCH(m, "dropout", launch_mul_mask(T.hbuf, T.drop + T.drop_off[j - 1], B, m->dense[j - 1].out, T.drop_ld, s));
             in_j = T.hbuf;
         }
+        // fast training: the first dense layer's two GEMMs against the big weight matrix as split-operand tcgen05 GEMMs (sm100_train.cu)
+        const bool tcd = m->fast_train && j == 0 && dense_bwd_x3_supported(B, D.out, D.in) && getenv("BCAD_TC_NO_DENSE") == nullptr;
+        float* dst = (j > 0) ? T.dense_dz[j - 1] : m->g_flat;
+        if (tcd) {
+            DenseBwdArgs dw;
+            dw.dz = T.dense_dz[j]; dw.src = in_j; dw.out = grads + T.dense_w_off[j]; dw.B = B; dw.units = D.out; dw.flat = D.in;
+            TR_LAUNCH(m, "dense_wgrad_tcgen05_x3", launch_dense_bwd_x3(dw, 0, m->sms, s));
+            TR_LAUNCH(m, "dense_bgrad", launch_colsum(T.dense_dz[j], grads + T.dense_b_off[j], B, D.out, s));
+            DenseBwdArgs dg;
+            dg.dz = T.dense_dz[j]; dg.src = D.d_w; dg.out = dst; dg.B = B; dg.units = D.out; dg.flat = D.in;
+            TR_LAUNCH(m, "dense_dgrad_tcgen05_x3", launch_dense_bwd_x3(dg, 1, m->sms, s));
+        } else {
         TR_LAUNCH(m, "dense_wgrad", launch_sgemm_tn(T.dense_dz[j], in_j, grads + T.dense_w_off[j], D.out, D.in, B, s));
         TR_LAUNCH(m, "dense_bgrad", launch_colsum(T.dense_dz[j], grads + T.dense_b_off[j], B, D.out, s));
-        float* dst = (j > 0) ? T.dense_dz[j - 1] : m->g_flat;
         TR_LAUNCH(m, "dense_dgrad", launch_sgemm(T.dense_dz[j], D.d_w, dst, B, D.in, D.out, false, 1, s));
+        }
         if (j > 0 && T.drop_B && T.drop_backward) TR_LAUNCH(m, "dropout", launch_mul_mask(dst, T.drop + T.drop_off[j - 1], B, m->dense[j - 1].out, T.drop_ld, s));
         if (j > 0) TR_LAUNCH(m, "leaky_mask_mul", launch_leaky_mask_mul(dst, m->dense[j - 1].z, m->cfg.alpha_dense, (int64_t)B * m->dense[j - 1].out, s));
     }
@@ -183,9 +195,22 @@ int bcad_train_backward_part(bcad_model* mm, const float* x, const int32_t* labe
     for (int i = nconv - 1; i >= 0; --i) {
         ConvLayer& L = m->conv[i];
         const size_t elems = (size_t)B * L.Ho * L.Wo * L.Cout;
+        const int first_only = (m->cfg.pool_ties == BCAD_TIES_FIRST) ? 1 : 0;
+        if (m->fast_train && i == 0 && L.Cin == 1 && L.Cout == 32 && L.CoutPad == 32 && L.k == 3 && getenv("BCAD_TC_NO_CONV0") == nullptr) {
+            // first block, one input channel: pool backward + LeakyReLU' + dF / db in one pass, the full-resolution gradient is never written
+            if (T.c0_part == nullptr) TR_TRY(m->alloc((void**)&T.c0_part, (size_t)conv0_bwd_fused_parts(m->sms) * 320 * sizeof(float)));
+            TR_LAUNCH(m, "conv0_bwd_fused", launch_conv0_bwd_fused(gp, L.y, x, T.c0_part, grads + T.conv_w_off[i], grads + T.conv_b_off[i], B, L.H, L.W,
+                                                                  L.Ho, L.Wo, m->cfg.pad, first_only, m->cfg.alpha_conv, m->sms, s));
+            m->launches += 1;
+            continue;
+        }
         if (L.dz == nullptr) TR_TRY(m->alloc((void**)&L.dz, (size_t)m->cfg.max_batch * L.Ho * L.Wo * L.Cout * sizeof(float)));
+        if (m->fast_train && L.Cout % 4 == 0) {
+            TR_LAUNCH(m, "unpool_mask", launch_unpool_mask(gp, L.y, L.dz, B, L.Ho, L.Wo, L.Cout, first_only, m->cfg.alpha_conv, s));
+        } else {
         TR_LAUNCH(m, "unpool", launch_unpool(gp, L.y, L.dz, B, L.Ho, L.Wo, L.Cout, m->cfg.pool_ties, s));
         TR_LAUNCH(m, "leaky_mask_mul", launch_leaky_mask_mul(L.dz, L.y, m->cfg.alpha_conv, (int64_t)elems, s));
+        }
         const float* in_i = (i == 0) ? x : m->conv[i - 1].p;
         const bool tc = m->fast_train && tc_train_eligible(m, (size_t)i);
         const bool tc_w = tc && getenv("BCAD_TC_NO_WGRAD") == nullptr, tc_d = tc && getenv("BCAD_TC_NO_DGRAD") == nullptr;   // (fault isolation)

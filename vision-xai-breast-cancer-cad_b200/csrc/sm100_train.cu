@@ -480,6 +480,345 @@ __global__ void colsum64_final_kernel(const float* __restrict__ part, int nparts
     out[n] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// CUDA-core pieces of the fast backward.
+// unpool_mask: dz = (pool switch ? g : 0) * LeakyReLU'(y) in ONE pass over y (Classes/CNNModel.py:263-280 + :300-304; the two-kernel
+// form reads and writes the full-resolution gradient twice).  Same arithmetic, same results.
+// ---------------------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) unpool_mask_kernel(const float4* __restrict__ g, const float4* __restrict__ y, float4* __restrict__ dz,
+                                                          int B, int Ho, int Wo, int C4, int first_only, float alpha) {
+    const int Hp = Ho / 2, Wp = Wo / 2, Hc = (Ho + 1) / 2, Wc = (Wo + 1) / 2;
+    const size_t total = (size_t)B * Hc * Wc * C4;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4);
+        size_t r = i / C4;
+        const int wx = (int)(r % Wc); r /= Wc;
+        const int wy = (int)(r % Hc);
+        const size_t b = r / Hc;
+        const size_t ybase = (b * Ho) * Wo * C4 + c;
+        if (wy < Hp && wx < Wp) {
+            const float4 gv = g[((b * Hp + wy) * Wp + wx) * C4 + c];
+            float4 v[4];
+            size_t idx[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                idx[q] = ybase + ((size_t)(2 * wy + (q >> 1)) * Wo + (2 * wx + (q & 1))) * C4;
+                v[q] = y[idx[q]];
+            }
+            float4 o[4];
+            auto lane = [&](float g1, float a0, float a1, float a2, float a3, float& o0, float& o1, float& o2, float& o3) {
+                const float m = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+                bool s0 = (a0 == m), s1 = (a1 == m), s2 = (a2 == m), s3 = (a3 == m);
+                if (first_only) { s1 = s1 && !s0; s2 = s2 && !(s0 || s1); s3 = s3 && !(s0 || s1 || s2); }
+                o0 = (s0 ? g1 : 0.f) * (a0 > 0.f ? 1.f : alpha);
+                o1 = (s1 ? g1 : 0.f) * (a1 > 0.f ? 1.f : alpha);
+                o2 = (s2 ? g1 : 0.f) * (a2 > 0.f ? 1.f : alpha);
+                o3 = (s3 ? g1 : 0.f) * (a3 > 0.f ? 1.f : alpha);
+            };
+            lane(gv.x, v[0].x, v[1].x, v[2].x, v[3].x, o[0].x, o[1].x, o[2].x, o[3].x);
+            lane(gv.y, v[0].y, v[1].y, v[2].y, v[3].y, o[0].y, o[1].y, o[2].y, o[3].y);
+            lane(gv.z, v[0].z, v[1].z, v[2].z, v[3].z, o[0].z, o[1].z, o[2].z, o[3].z);
+            lane(gv.w, v[0].w, v[1].w, v[2].w, v[3].w, o[0].w, o[1].w, o[2].w, o[3].w);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dz[idx[q]] = o[q];
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int yy = 2 * wy + (q >> 1), xx = 2 * wx + (q & 1);
+                if (yy < Ho && xx < Wo) dz[ybase + ((size_t)yy * Wo + xx) * C4] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// First conv block (one input channel, 32 filters, 3x3): max-pool backward, LeakyReLU' and the weight / bias gradients in ONE pass --
+// the 32-channel full-resolution gradient (0.5 GB per 64 images at 256x256) is never written: a warp (lane = filter) walks the pool
+// windows of a row pair, routes g to the window's maximum, and accumulates dF[tap][lane] += dz * x[tap] from a 4x4 patch of the input row
+// strip staged in shared memory.  Per-CTA partials, fixed-order final sum (deterministic).
+// dF[ky][kx][f] = sum dz[b,y,x,f] x[b, y+ky-pad, x+kx-pad]   (explainability.py:58-59 / Classes/CNNModel.py:340-352 for C = 1), db[f] = sum dz.
+// ---------------------------------------------------------------------------------------------------------------------------------
+constexpr int C0B_WARPS = 8;
+__global__ void __launch_bounds__(32 * C0B_WARPS) conv0_bwd_fused_kernel(const float* __restrict__ g, const float* __restrict__ y, const float* __restrict__ x,
+                                                                        float* __restrict__ part, int B, int H, int W, int Ho, int Wo, int pad,
+                                                                        int first_only, float alpha) {
+    extern __shared__ float s_x[];                              // [4 rows][pitch]: column j = input column j - pad, zero outside the image
+    __shared__ float s_red[C0B_WARPS][10][32];
+    const int Hp = Ho / 2, Wp = Wo / 2;
+    const int pitch = (W + 2 * pad + 4 + 1) & ~1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float acc[9], accb = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+    const int units = B * Hp;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int b = u / Hp, wy = u % Hp;
+        __syncthreads();                                        // the previous unit's patch reads are done
+        for (int i = threadIdx.x; i < 4 * pitch; i += blockDim.x) {
+            const int r = i / pitch, j = i % pitch;
+            const int row = 2 * wy - pad + r, col = j - pad;
+            s_x[i] = (row >= 0 && row < H && col >= 0 && col < W) ? __ldg(x + ((size_t)b * H + row) * W + col) : 0.f;
+        }
+        __syncthreads();
+        const float* y0 = y + (((size_t)b * Ho + 2 * wy) * Wo) * 32 + lane;
+        const float* y1 = y0 + (size_t)Wo * 32;
+        const float* gr = g + (((size_t)b * Hp + wy) * Wp) * 32 + lane;
+        for (int wx = warp; wx < Wp; wx += C0B_WARPS) {
+            const float gv = __ldg(gr + (size_t)wx * 32);
+            const float a0 = __ldg(y0 + (size_t)(2 * wx) * 32), a1 = __ldg(y0 + (size_t)(2 * wx + 1) * 32);
+            const float a2 = __ldg(y1 + (size_t)(2 * wx) * 32), a3 = __ldg(y1 + (size_t)(2 * wx + 1) * 32);
+            const float m = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+            bool s0 = (a0 == m), s1 = (a1 == m), s2 = (a2 == m), s3 = (a3 == m);
+            if (first_only) { s1 = s1 && !s0; s2 = s2 && !(s0 || s1); s3 = s3 && !(s0 || s1 || s2); }
+            float d[4];
+            d[0] = (s0 ? gv : 0.f) * (a0 > 0.f ? 1.f : alpha);
+            d[1] = (s1 ? gv : 0.f) * (a1 > 0.f ? 1.f : alpha);
+            d[2] = (s2 ? gv : 0.f) * (a2 > 0.f ? 1.f : alpha);
+            d[3] = (s3 ? gv : 0.f) * (a3 > 0.f ? 1.f : alpha);
+            accb += (d[0] + d[1]) + (d[2] + d[3]);
+            float p[4][4];                                      // input patch: rows 2 wy - pad + r, columns 2 wx - pad + c (broadcast reads)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float2 lo = *reinterpret_cast<const float2*>(s_x + r * pitch + 2 * wx);
+                const float2 hi = *reinterpret_cast<const float2*>(s_x + r * pitch + 2 * wx + 2);
+                p[r][0] = lo.x; p[r][1] = lo.y; p[r][2] = hi.x; p[r][3] = hi.y;
+            }
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    float t = acc[ky * 3 + kx];
+                    t = fmaf(d[0], p[ky][kx], t);
+                    t = fmaf(d[1], p[ky][kx + 1], t);
+                    t = fmaf(d[2], p[ky + 1][kx], t);
+                    t = fmaf(d[3], p[ky + 1][kx + 1], t);
+                    acc[ky * 3 + kx] = t;
+                }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) s_red[warp][t][lane] = acc[t];
+    s_red[warp][9][lane] = accb;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 320; i += blockDim.x) {
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < C0B_WARPS; ++w) sum += s_red[w][i / 32][i % 32];
+        part[(size_t)blockIdx.x * 320 + i] = sum;
+    }
+}
+__global__ void conv0_bwd_final_kernel(const float* __restrict__ part, int nparts, float* __restrict__ dw, float* __restrict__ db) {
+    const int i = threadIdx.x + blockIdx.x * blockDim.x;
+    if (i >= 320) return;
+    float sum = 0.f;
+    for (int c = 0; c < nparts; ++c) sum += part[(size_t)c * 320 + i];
+    if (i < 288) dw[i] = sum;
+    else db[i - 288] = sum;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// The first dense layer's two backward GEMMs against the big (units x flat, 268 MB at the canonical shape) weight matrix:
+//   MODE 0 (weight gradient)  dW[u][k] = sum_b dz[b][u] p[b][k]      M = units (halves of 128), N = 128 columns per tile, K = batch (<= 64)
+//   MODE 1 (input gradient)   g[b][k]  = sum_u dz[b][u] W[u][k]      M = 128 columns per tile, N = batch (64), K = units in four stages of 64
+// Both stream fp32 tiles of 64 rows x 128 contiguous columns (rows of p, resp. of W) that enter the MMA MN-major: the producers split them
+// into bf16 hi / lo 16-byte items (8 columns of one row) at [column octet][row / 8][row % 8] -- the no-swizzle MN-major canonical layout
+// (LBO = 128 B between 8-row groups, SBO = the octet pitch, padded to 1040 B so the producers' stores do not collide).  dz is resident.
+// Reference: Classes/CNNModel.py:307-318 (dW = d_out^T . input, d_input = d_out . W), torch autograd of nn.Linear (ADCNNM.py:57-66).
+// ---------------------------------------------------------------------------------------------------------------------------------
+constexpr int DG_NST = 4;                               // streamed stages
+constexpr int DG_OCT = 1040;                            // pitch of a column octet: 8 row groups x 128 B, + 16 B
+constexpr int DG_SPLANE = 16 * DG_OCT;                  // one plane of a streamed tile (128 columns)
+constexpr int DG_STAGEB = 2 * DG_SPLANE;
+constexpr int DG_RPLANE = 32 * DG_OCT;                  // resident dz plane: 32 octets (256 units MN-major, or 256 units as 32 K-chunks K-major)
+constexpr int DG_OFF_R = DG_NST * DG_STAGEB;
+constexpr int DG_OFF_BAR = DG_OFF_R + 2 * DG_RPLANE;
+constexpr int DG_TOTAL = DG_OFF_BAR + 256;
+constexpr int DG_THREADS = 32 * (TC_PW + 1 + 4);
+
+template <int MODE>
+__global__ void __launch_bounds__(DG_THREADS, 1) dense_bwd_x3_kernel(DenseBwdArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* s_res = smem + DG_OFF_R;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DG_OFF_BAR);
+    uint64_t* full = bars;                       // [NST] producers -> MMA (count TC_PW)
+    uint64_t* empty = bars + DG_NST;             // [NST] MMA -> producers
+    uint64_t* tfull = bars + 2 * DG_NST;         // [2] MMA -> epilogue
+    uint64_t* tempty = bars + 2 * DG_NST + 2;    // [2] epilogue -> MMA (count 4)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * DG_NST + 4);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr uint32_t TCOLS = (MODE == 0) ? 512 : 128;
+    if (tid == 0) {
+        for (int i = 0; i < DG_NST; ++i) { mbar_init(&full[i], TC_PW); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(tmem_slot, TCOLS);
+        tmem_relinquish();
+    }
+    // resident dz (bf16 hi / lo): 16-byte item = 8 consecutive units of one image, MODE 0: MN-major [unit octet][b / 8][b % 8],
+    // MODE 1: K-major [unit octet = K chunk][b]; rows b >= B and units >= a.units are zero
+    for (int it = tid; it < 32 * 64; it += DG_THREADS) {
+        const int oct = it & 31, b = it >> 5;
+        uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+        if (b < a.B && oct * 8 < a.units) {
+            const float* src = a.dz + (size_t)b * a.units + oct * 8;
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(src)), v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+            hi.x = split_hi_lo(v0.x, v0.y, lo.x, true);
+            hi.y = split_hi_lo(v0.z, v0.w, lo.y, true);
+            hi.z = split_hi_lo(v1.x, v1.y, lo.z, true);
+            hi.w = split_hi_lo(v1.z, v1.w, lo.w, true);
+        }
+        uint8_t* dst = s_res + oct * DG_OCT + ((MODE == 0) ? ((b >> 3) * 128 + (b & 7) * 16) : (b * 16));
+        *reinterpret_cast<uint4*>(dst) = hi;
+        *reinterpret_cast<uint4*>(dst + DG_RPLANE) = lo;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int n_tiles = (int)(a.flat / 128);
+    constexpr int SPT = (MODE == 0) ? 1 : 4;                     // streamed stages per output tile
+    const int kq = (MODE == 0) ? 1 : a.units / 64;              // ... of which carry data (MODE 1: units / 64 row groups of W)
+
+    if (warp < TC_PW) {
+        // ================================ producers ================================
+        uint32_t g = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
+            for (int q = 0; q < SPT; ++q) {
+                if (MODE == 1 && q >= kq) break;
+                const uint32_t st = g % DG_NST;
+                if (g >= (uint32_t)DG_NST) mbar_wait(&empty[st], ((g / DG_NST) - 1) & 1);
+                uint8_t* dstb = smem + st * DG_STAGEB;
+                const int nrows = (MODE == 0) ? a.B : 64;
+                const float* base = a.src + (size_t)(MODE == 0 ? 0 : q * 64) * a.flat + (size_t)t * 128;
+                for (int it = tid; it < 16 * 64; it += 32 * TC_PW) {
+                    const int oct = it & 15, k = it >> 4;
+                    uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+                    if (k < nrows) {
+                        const float* src = base + (size_t)k * a.flat + oct * 8;
+                        const float4 v0 = __ldg(reinterpret_cast<const float4*>(src)), v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+                        hi.x = split_hi_lo(v0.x, v0.y, lo.x, true);
+                        hi.y = split_hi_lo(v0.z, v0.w, lo.y, true);
+                        hi.z = split_hi_lo(v1.x, v1.y, lo.z, true);
+                        hi.w = split_hi_lo(v1.z, v1.w, lo.w, true);
+                    }
+                    uint8_t* dst = dstb + oct * DG_OCT + (k >> 3) * 128 + (k & 7) * 16;
+                    *reinterpret_cast<uint4*>(dst) = hi;
+                    *reinterpret_cast<uint4*>(dst + DG_SPLANE) = lo;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[st]);
+                ++g;
+            }
+    } else if (warp == TC_PW) {
+        // ================================ MMA issuer ================================
+        const bool leader = elect_one();
+        const uint32_t res = smem_u32(s_res);
+        constexpr uint32_t mn_hi = (uint32_t)(DG_OCT >> 4) | (1u << 14);             // MN-major: SBO = octet pitch
+        constexpr uint32_t mn_lo = (uint32_t)(128 >> 4) << 16;                      //           LBO = 128 B between 8-row (K) groups
+        constexpr uint32_t k_hi = (uint32_t)(128 >> 4) | (1u << 14);                // K-major resident dz: SBO = 128 B (8 images)
+        constexpr uint32_t k_lo = (uint32_t)(DG_OCT >> 4) << 16;                    //           LBO = chunk pitch
+        uint32_t g = 0, acc_it = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++acc_it) {
+            const uint32_t j = acc_it & 1;
+            if (acc_it >= 2) mbar_wait(&tempty[j], ((acc_it >> 1) - 1) & 1);
+            if (MODE == 0) {
+                constexpr uint32_t idesc = tc_idesc(128, 128, 1, 1, 1, 1);
+                const uint32_t st = g % DG_NST;
+                mbar_wait(&full[st], (g / DG_NST) & 1);
+                tc_fence_after();
+                const uint32_t sb = smem_u32(smem + st * DG_STAGEB);
+                const int halves = a.units / 128;
+                for (int h = 0; h < halves; ++h) {
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+                        for (int combo = 0; combo < 3; ++combo) {           // dz_hi p_hi, dz_lo p_hi, dz_hi p_lo
+                            const uint32_t a_addr = res + (combo == 1 ? DG_RPLANE : 0) + h * 16 * DG_OCT + ks * 256;
+                            const uint32_t b_addr = sb + (combo == 2 ? DG_SPLANE : 0) + ks * 256;
+                            umma_f16_if(leader, tmem + j * 256 + h * 128, desc64(mn_lo | ((a_addr & 0x3FFFFu) >> 4), mn_hi),
+                                        desc64(mn_lo | ((b_addr & 0x3FFFFu) >> 4), mn_hi), idesc, acc);
+                            acc = 1u;
+                        }
+                }
+                umma_commit_if(leader, &empty[st]);
+                ++g;
+            } else {
+                constexpr uint32_t idesc = tc_idesc(128, 64, 1, 1, 1, 0);
+                uint32_t acc = 0;
+                for (int q = 0; q < kq; ++q, ++g) {
+                    const uint32_t st = g % DG_NST;
+                    mbar_wait(&full[st], (g / DG_NST) & 1);
+                    tc_fence_after();
+                    const uint32_t sb = smem_u32(smem + st * DG_STAGEB);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+                        for (int combo = 0; combo < 3; ++combo) {           // W_hi dz_hi, W_lo dz_hi, W_hi dz_lo
+                            const uint32_t a_addr = sb + (combo == 1 ? DG_SPLANE : 0) + ks * 256;
+                            const uint32_t b_addr = res + (combo == 2 ? DG_RPLANE : 0) + (q * 8 + ks * 2) * DG_OCT;
+                            umma_f16_if(leader, tmem + j * 64, desc64(mn_lo | ((a_addr & 0x3FFFFu) >> 4), mn_hi),
+                                        desc64(k_lo | ((b_addr & 0x3FFFFu) >> 4), k_hi), idesc, acc);
+                            acc = 1u;
+                        }
+                    umma_commit_if(leader, &empty[st]);
+                }
+            }
+            umma_commit_if(leader, &tfull[j]);
+        }
+    } else {
+        // ================================ epilogue ================================
+        const int quad = warp & 3;
+        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+        const int row = quad * 32 + lane;
+        uint32_t acc_it = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++acc_it) {
+            const uint32_t j = acc_it & 1;
+            mbar_wait(&tfull[j], (acc_it >> 1) & 1);
+            tc_fence_after();
+            if (MODE == 0) {
+                const int halves = a.units / 128;
+                for (int h = 0; h < halves; ++h) {
+                    float* dst = a.out + (size_t)(h * 128 + row) * a.flat + (size_t)t * 128;
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        float v[32];
+                        tmem_ld32(tmem + lane_off + j * 256 + h * 128 + c * 32, v);
+                        tmem_ld_wait();
+                        if (h == halves - 1 && c == 3) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tempty[j]);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *reinterpret_cast<float4*>(dst + c * 32 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    }
+                }
+            } else {
+                float v[64];
+                tmem_ld32(tmem + lane_off + j * 64, *reinterpret_cast<float(*)[32]>(v));
+                tmem_ld32(tmem + lane_off + j * 64 + 32, *reinterpret_cast<float(*)[32]>(v + 32));
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[j]);
+                float* dst = a.out + (size_t)t * 128 + row;
+#pragma unroll
+                for (int b = 0; b < 64; ++b)
+                    if (b < a.B) dst[(size_t)b * a.flat] = v[b];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, TCOLS);
+}
+
 template <int CIN, int COUT, bool ABF>
 int launch_conv_t(const TcConvArgs& a, int grid, cudaStream_t s) {
     using L = TcSmem<CIN, COUT>;
@@ -530,6 +869,49 @@ int launch_wgrad3x3_x3(const TcWgradArgs& a, float* dw, int CoutPad, int sms, cu
     wgrad3x3_x3_kernel<<<grid, WG_THREADS, WG_TOTAL, s>>>(a);
     BCAD_CUDA_CHECK(cudaGetLastError());
     wgrad_reduce_kernel<<<cdiv(9 * 32 * 64, 256), 256, 0, s>>>(a.partials, grid, dw, CoutPad);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+int launch_unpool_mask(const float* g, const float* y, float* dz, int B, int Ho, int Wo, int C, int first_only, float alpha, cudaStream_t s) {
+    BCAD_REQUIRE(C % 4 == 0, "unpool_mask: channels must be a multiple of 4");
+    const size_t total = (size_t)B * ((Ho + 1) / 2) * ((Wo + 1) / 2) * (C / 4);
+    const int blocks = (int)std::min<size_t>((size_t)148 * 16, (total + 255) / 256);
+    unpool_mask_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(y), reinterpret_cast<float4*>(dz), B, Ho, Wo, C / 4,
+                                              first_only, alpha);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+// scratch: conv0_bwd_fused_parts() * 320 floats; dw: [9][32] (tap-major, filters innermost), db: [32]
+int conv0_bwd_fused_parts(int sms) { return sms * 4; }
+int launch_conv0_bwd_fused(const float* g, const float* y, const float* x, float* scratch, float* dw, float* db, int B, int H, int W, int Ho, int Wo,
+                           int pad, int first_only, float alpha, int sms, cudaStream_t s) {
+    const int units = B * (Ho / 2);
+    if (units == 0) return BCAD_OK;
+    const int grid = std::min(units, conv0_bwd_fused_parts(sms));
+    const int pitch = (W + 2 * pad + 4 + 1) & ~1;
+    conv0_bwd_fused_kernel<<<grid, 32 * C0B_WARPS, (size_t)4 * pitch * sizeof(float), s>>>(g, y, x, scratch, B, H, W, Ho, Wo, pad, first_only, alpha);
+    conv0_bwd_final_kernel<<<2, 160, 0, s>>>(scratch, grid, dw, db);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+bool dense_bwd_x3_supported(int B, int units, long long flat) { return B >= 1 && B <= 64 && (units == 128 || units == 256) && flat % 128 == 0; }
+
+// mode 0: out = dW [units][flat] from dz [B][units] and src = p [B][flat]; mode 1: out = g [B][flat] from dz and src = W [units][flat]
+int launch_dense_bwd_x3(const DenseBwdArgs& a, int mode, int sms, cudaStream_t s) {
+    static_assert(DG_TOTAL <= 227 * 1024, "dense_bwd_x3: shared memory budget");
+    BCAD_REQUIRE(dense_bwd_x3_supported(a.B, a.units, a.flat), "dense_bwd_x3: unsupported shape (B %d, units %d, flat %lld)", a.B, a.units, a.flat);
+    const int tiles = (int)(a.flat / 128);
+    const int grid = tiles < sms ? tiles : sms;
+    if (mode == 0) {
+        BCAD_CUDA_CHECK(cudaFuncSetAttribute(dense_bwd_x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_TOTAL));
+        dense_bwd_x3_kernel<0><<<grid, DG_THREADS, DG_TOTAL, s>>>(a);
+    } else {
+        BCAD_CUDA_CHECK(cudaFuncSetAttribute(dense_bwd_x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_TOTAL));
+        dense_bwd_x3_kernel<1><<<grid, DG_THREADS, DG_TOTAL, s>>>(a);
+    }
     BCAD_CUDA_CHECK(cudaGetLastError());
     return BCAD_OK;
 }

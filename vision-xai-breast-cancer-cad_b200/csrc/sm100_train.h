@@ -30,6 +30,21 @@ bool wgrad3x3_x3_supported(int Cin, int Cout, int k, int W, int Wo, int pad);
 size_t wgrad3x3_x3_partial_floats(int sms);
 // dw: [9][32][CoutPad] fp32 (the fp32 path's gradient layout), overwritten
 int launch_wgrad3x3_x3(const TcWgradArgs& a, float* dw, int CoutPad, int sms, cudaStream_t s);
+struct DenseBwdArgs {
+    const float* dz;       // [B][units] fp32: gradient w.r.t. the layer's pre-activation
+    const float* src;      // mode 0: the layer's input p [B][flat]; mode 1: its weights W [units][flat]
+    float* out;            // mode 0: dW [units][flat]; mode 1: g [B][flat]
+    int B, units;
+    long long flat;
+};
+bool dense_bwd_x3_supported(int B, int units, long long flat);
+int launch_dense_bwd_x3(const DenseBwdArgs& a, int mode, int sms, cudaStream_t s);
+// dz = (pool switch ? g : 0) * (y > 0 ? 1 : alpha): max-pool backward + LeakyReLU' in one pass (NHWC fp32, C % 4 == 0)
+int launch_unpool_mask(const float* g, const float* y, float* dz, int B, int Ho, int Wo, int C, int first_only, float alpha, cudaStream_t s);
+// first conv block with ONE input channel and 32 filters: pool backward + LeakyReLU' + weight / bias gradients without writing dz
+int conv0_bwd_fused_parts(int sms);
+int launch_conv0_bwd_fused(const float* g, const float* y, const float* x, float* scratch, float* dw, float* db, int B, int H, int W, int Ho, int Wo,
+                           int pad, int first_only, float alpha, int sms, cudaStream_t s);
 // out[64] = column sums of A[K][64]; scratch: 4096 * 64 floats
 int launch_colsum64(const float* A, float* scratch, float* out, size_t K, cudaStream_t s);
 int launch_maxpool2x2_nhwc(const float* y, float* p, int B, int Ho, int Wo, int C, cudaStream_t s);
