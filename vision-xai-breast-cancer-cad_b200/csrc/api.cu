@@ -447,7 +447,17 @@ static int forward_chunk_fp32(Model* m, const float* x, int n, bool explain, con
     }
     // fc1 as a split-K SGEMM, then either the fused head or the layer-by-layer chain
     DenseLayer& D0 = m->dense[0];
-    const int splits0 = std::min(D0.splits, sgemm_pick_splits(n, D0.out, D0.in));
+    int splits0 = std::min(D0.splits, sgemm_pick_splits(n, D0.out, D0.in));
+    float* fc_part = m->partials;
+    if (m->fast_train && dense_fwd_x3_supported(n, D0.out, D0.in) && getenv("BCAD_TC_NO_DENSE") == nullptr) {
+        // fast training: fc1 as a split-K, split-operand tcgen05 GEMM on the fp32 tensors (sm100_train.cu)
+        splits0 = dense_fwd_x3_splits(D0.in, m->sms);
+        if (m->train.fc_part == nullptr) BCAD_TRY(m->alloc((void**)&m->train.fc_part, (size_t)splits0 * 64 * D0.out * sizeof(float)));
+        fc_part = m->train.fc_part;
+        DenseFwdArgs f;
+        f.p = in; f.w = D0.d_w; f.partials = fc_part; f.B = n; f.units = D0.out; f.flat = D0.in;
+        BCAD_LAUNCH(m, "fc1_fwd_tcgen05_x3", launch_dense_fwd_x3(f, m->sms, s));
+    } else
     BCAD_LAUNCH(m, "fc1_sgemm", launch_sgemm(in, D0.d_w, m->partials, n, D0.out, D0.in, true, splits0, s));
     const float* drop = m->train.drop_B ? m->train.drop : nullptr;   // training forward: dropout after every hidden layer
     if (drop && m->train.drop_B != n) {
@@ -455,12 +465,12 @@ static int forward_chunk_fp32(Model* m, const float* x, int n, bool explain, con
         return BCAD_ERR_STATE;
     }
     if (m->fused_head && !drop) {
-        BCAD_TRY(launch_fused_head(m, n, m->partials, splits0, (size_t)n * D0.out, explain, class_idx, grad_mode,
+        BCAD_TRY(launch_fused_head(m, n, fc_part, splits0, (size_t)n * D0.out, explain, class_idx, grad_mode,
                                    explain ? D0.h : nullptr, nullptr, 0, nullptr, s));
         return BCAD_OK;
     }
     const bool only = (m->dense.size() == 1);
-    BCAD_LAUNCH(m, "splitk_reduce", launch_splitk_reduce(m->partials, splits0, D0.d_b, D0.z, only ? nullptr : D0.h, m->cfg.alpha_dense, n, D0.out, s));
+    BCAD_LAUNCH(m, "splitk_reduce", launch_splitk_reduce(fc_part, splits0, D0.d_b, D0.z, only ? nullptr : D0.h, m->cfg.alpha_dense, n, D0.out, s));
     if (drop && !only) BCAD_LAUNCH(m, "dropout", launch_mul_mask(D0.h, drop + m->train.drop_off[0], n, D0.out, m->train.drop_ld, s));
     in = D0.h;
     for (size_t j = 1; j < m->dense.size(); ++j) {

@@ -88,6 +88,7 @@ struct TrainState {                     // row f4: buffers of the training step 
     int max_ctas = 2048;
     float* wg_part = nullptr;           // fast training: per-CTA accumulator dumps of the tensor-core weight gradient
     float* cs_part = nullptr;           //                slab partials of the bias gradient
+    float* fc_part = nullptr;           //                split-K partials of the tensor-core fc1 forward
     float* c0_part = nullptr;           //                per-CTA partials of the fused first-block backward
     bool tc_dirty = true;               //                the fp16 weight images are older than the fp32 weights
 };

@@ -819,6 +819,137 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dense_bwd_x3_kernel(DenseBwdArg
     if (warp == 0) tmem_dealloc(tmem, TCOLS);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// The first dense layer's forward against the same big matrix:  z[b][u] = sum_k p[b][k] W[u][k], split-K over the CTAs.
+// Both operands are K-major (k contiguous in memory): D[u][b] with A = W rows (M = 128-unit halves), B = p rows (N = 64 images), fp16 hi / lo
+// pairs; 64 columns of k per stage.  The two (or one) 64-column accumulators live in TMEM for the CTA's whole k range and are written once
+// as split-K partials [cta][b][u] -- the layout the fp32 path's reduction / fused head already consume.
+// Reference: Classes/CNNModel.py:177-189 (z = input . W^T + b), nn.Linear (ADCNNM.py:77).
+// ---------------------------------------------------------------------------------------------------------------------------------
+constexpr int DF_NST = 2;
+constexpr int DF_ALBO = 256 * 16 + 16;                  // pitch of a K chunk (8 columns) of the W tile: 256 unit rows x 16 B, + 16 B
+constexpr int DF_APLANE = 8 * DF_ALBO;
+constexpr int DF_BLBO = 64 * 16 + 16;
+constexpr int DF_BPLANE = 8 * DF_BLBO;
+constexpr int DF_STAGEB = 2 * DF_APLANE + 2 * DF_BPLANE;
+constexpr int DF_OFF_BAR = DF_NST * DF_STAGEB;
+constexpr int DF_TOTAL = DF_OFF_BAR + 128;
+
+__global__ void __launch_bounds__(DG_THREADS, 1) dense_fwd_x3_kernel(DenseFwdArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DF_OFF_BAR);
+    uint64_t* full = bars;                       // [NST] producers -> MMA (count TC_PW)
+    uint64_t* empty = bars + DF_NST;             // [NST] MMA -> producers
+    uint64_t* done = bars + 2 * DF_NST;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * DF_NST + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < DF_NST; ++i) { mbar_init(&full[i], TC_PW); mbar_init(&empty[i], 1); }
+        mbar_init(done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(tmem_slot, 128);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int n_chunks = (int)(a.flat / 64);
+    const int per = (n_chunks + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int c0 = blockIdx.x * per, c1 = min(n_chunks, c0 + per);
+    const int halves = a.units / 128;
+
+    if (warp < TC_PW) {
+        uint32_t g = 0;
+        for (int c = c0; c < c1; ++c, ++g) {
+            const uint32_t st = g % DF_NST;
+            if (g >= (uint32_t)DF_NST) mbar_wait(&empty[st], ((g / DF_NST) - 1) & 1);
+            uint8_t* sa = smem + st * DF_STAGEB;
+            uint8_t* sb = sa + 2 * DF_APLANE;
+            // W tile: item (unit row m, chunk k8) = 8 consecutive k of row m
+            for (int it = tid; it < a.units * 8; it += 32 * TC_PW) {
+                const int k8 = it & 7, mrow = it >> 3;
+                const float* src = a.w + (size_t)mrow * a.flat + (size_t)c * 64 + k8 * 8;
+                const float4 v0 = __ldg(reinterpret_cast<const float4*>(src)), v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+                uint4 hi, lo;
+                hi.x = split_hi_lo(v0.x, v0.y, lo.x, false);
+                hi.y = split_hi_lo(v0.z, v0.w, lo.y, false);
+                hi.z = split_hi_lo(v1.x, v1.y, lo.z, false);
+                hi.w = split_hi_lo(v1.z, v1.w, lo.w, false);
+                uint8_t* dst = sa + k8 * DF_ALBO + mrow * 16;
+                *reinterpret_cast<uint4*>(dst) = hi;
+                *reinterpret_cast<uint4*>(dst + DF_APLANE) = lo;
+            }
+            // p tile: item (image b, chunk k8); images >= B are zero
+            for (int it = tid; it < 64 * 8; it += 32 * TC_PW) {
+                const int k8 = it & 7, b = it >> 3;
+                uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+                if (b < a.B) {
+                    const float* src = a.p + (size_t)b * a.flat + (size_t)c * 64 + k8 * 8;
+                    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src)), v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+                    hi.x = split_hi_lo(v0.x, v0.y, lo.x, false);
+                    hi.y = split_hi_lo(v0.z, v0.w, lo.y, false);
+                    hi.z = split_hi_lo(v1.x, v1.y, lo.z, false);
+                    hi.w = split_hi_lo(v1.z, v1.w, lo.w, false);
+                }
+                uint8_t* dst = sb + k8 * DF_BLBO + b * 16;
+                *reinterpret_cast<uint4*>(dst) = hi;
+                *reinterpret_cast<uint4*>(dst + DF_BPLANE) = lo;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[st]);
+        }
+    } else if (warp == TC_PW) {
+        const bool leader = elect_one();
+        constexpr uint32_t idesc = tc_idesc(128, 64, 0, 0, 0, 0);
+        constexpr uint32_t sbo_hi = (uint32_t)(128 >> 4) | (1u << 14);
+        constexpr uint32_t a_lo_t = (uint32_t)(DF_ALBO >> 4) << 16, b_lo_t = (uint32_t)(DF_BLBO >> 4) << 16;
+        uint32_t g = 0, acc = 0;
+        for (int c = c0; c < c1; ++c, ++g) {
+            const uint32_t st = g % DF_NST;
+            mbar_wait(&full[st], (g / DF_NST) & 1);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + st * DF_STAGEB), sb = sa + 2 * DF_APLANE;
+            for (int h = 0; h < halves; ++h)
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+                    for (int combo = 0; combo < 3; ++combo) {               // W_hi p_hi, W_lo p_hi, W_hi p_lo
+                        const uint32_t a_addr = sa + (combo == 1 ? DF_APLANE : 0) + ks * 2 * DF_ALBO + h * 128 * 16;
+                        const uint32_t b_addr = sb + (combo == 2 ? DF_BPLANE : 0) + ks * 2 * DF_BLBO;
+                        umma_f16_if(leader, tmem + h * 64, desc64(a_lo_t | ((a_addr & 0x3FFFFu) >> 4), sbo_hi), desc64(b_lo_t | ((b_addr & 0x3FFFFu) >> 4), sbo_hi),
+                                    idesc, (acc || ks || combo) ? 1u : 0u);
+                    }
+            acc = 1u;
+            umma_commit_if(leader, &empty[st]);
+        }
+        umma_commit_if(leader, done);
+    } else {
+        const int quad = warp & 3;
+        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+        const int row = quad * 32 + lane;
+        mbar_wait(done, 0);
+        tc_fence_after();
+        float* dst = a.partials + (size_t)blockIdx.x * a.B * a.units;
+        for (int h = 0; h < halves; ++h) {
+            float v[64];
+            tmem_ld32(tmem + lane_off + h * 64, *reinterpret_cast<float(*)[32]>(v));
+            tmem_ld32(tmem + lane_off + h * 64 + 32, *reinterpret_cast<float(*)[32]>(v + 32));
+            tmem_ld_wait();
+            const bool live = c1 > c0;                                      // a CTA without chunks contributes zeros
+#pragma unroll
+            for (int b = 0; b < 64; ++b)
+                if (b < a.B) dst[(size_t)b * a.units + h * 128 + row] = live ? v[b] : 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
 template <int CIN, int COUT, bool ABF>
 int launch_conv_t(const TcConvArgs& a, int grid, cudaStream_t s) {
     using L = TcSmem<CIN, COUT>;
@@ -912,6 +1043,24 @@ int launch_dense_bwd_x3(const DenseBwdArgs& a, int mode, int sms, cudaStream_t s
         BCAD_CUDA_CHECK(cudaFuncSetAttribute(dense_bwd_x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_TOTAL));
         dense_bwd_x3_kernel<1><<<grid, DG_THREADS, DG_TOTAL, s>>>(a);
     }
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+bool dense_fwd_x3_supported(int B, int units, long long flat) { return B >= 1 && B <= 64 && (units == 128 || units == 256) && flat % 64 == 0; }
+int dense_fwd_x3_splits(long long flat, int sms) {
+    const int chunks = (int)(flat / 64);
+    const int grid = chunks < sms ? chunks : sms;
+    const int per = (chunks + grid - 1) / grid;
+    return (chunks + per - 1) / per;                          // every launched CTA owns at least one chunk
+}
+// partials: [dense_fwd_x3_splits][B][units] fp32
+int launch_dense_fwd_x3(const DenseFwdArgs& a, int sms, cudaStream_t s) {
+    static_assert(DF_TOTAL <= 227 * 1024, "dense_fwd_x3: shared memory budget");
+    BCAD_REQUIRE(dense_fwd_x3_supported(a.B, a.units, a.flat), "dense_fwd_x3: unsupported shape (B %d, units %d, flat %lld)", a.B, a.units, a.flat);
+    const int grid = dense_fwd_x3_splits(a.flat, sms);
+    BCAD_CUDA_CHECK(cudaFuncSetAttribute(dense_fwd_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_TOTAL));
+    dense_fwd_x3_kernel<<<grid, DG_THREADS, DF_TOTAL, s>>>(a);
     BCAD_CUDA_CHECK(cudaGetLastError());
     return BCAD_OK;
 }

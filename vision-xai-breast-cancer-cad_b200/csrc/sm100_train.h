@@ -39,6 +39,16 @@ struct DenseBwdArgs {
 };
 bool dense_bwd_x3_supported(int B, int units, long long flat);
 int launch_dense_bwd_x3(const DenseBwdArgs& a, int mode, int sms, cudaStream_t s);
+struct DenseFwdArgs {
+    const float* p;        // the layer's input [B][flat] fp32
+    const float* w;        // its weights [units][flat] fp32
+    float* partials;       // split-K partials [dense_fwd_x3_splits(flat, sms)][B][units]
+    int B, units;
+    long long flat;
+};
+bool dense_fwd_x3_supported(int B, int units, long long flat);
+int dense_fwd_x3_splits(long long flat, int sms);
+int launch_dense_fwd_x3(const DenseFwdArgs& a, int sms, cudaStream_t s);
 // dz = (pool switch ? g : 0) * (y > 0 ? 1 : alpha): max-pool backward + LeakyReLU' in one pass (NHWC fp32, C % 4 == 0)
 int launch_unpool_mask(const float* g, const float* y, float* dz, int B, int Ho, int Wo, int C, int first_only, float alpha, cudaStream_t s);
 // first conv block with ONE input channel and 32 filters: pool backward + LeakyReLU' + weight / bias gradients without writing dz
