@@ -255,6 +255,33 @@ def test_fused_conv_kernel_forced(monkeypatch, shape, pad, hidden, B):
     eng.close()
 
 
+def test_second_generation_fused_kernel_against_the_first_and_its_paired_tap_form(monkeypatch):
+    """conv_fused2_kernel (patch-union first block, tensor-map TMA input boxes; the default wherever image rows are 16-byte aligned) against
+    conv_fused_kernel (BCAD_FUSED_V1=1) on the same handle: the same network to fp16 rounding of the pooled first-block map; and its opt-in
+    paired-tap form (N = 128 MMAs, BCAD_F2_PAIRED=1) gives bit-identical logits / heat-maps (same products, same order per accumulator)."""
+    monkeypatch.setenv("BCAD_FUSED_CONV", "1")
+    cfg = ocnn.NetConfig.torch_flavour((96, 80, 1), 2, [(32, 3), (64, 3)], [64, 32], 0.01)
+    p = ocnn.init_params(cfg, seed=21, bias_std=0.05)
+    x = ocnn.synth_images(9, (96, 80, 1), seed=2)
+    eng = engine_from(cfg, p, precision="fp16", max_batch=16, refine_margin=0.0)
+    c2, p2, l2, h2 = eng.predict_explain(x, None, "logit")
+    monkeypatch.setenv("BCAD_F2_PAIRED", "1")
+    c3, p3, l3, h3 = eng.predict_explain(x, None, "logit")
+    monkeypatch.delenv("BCAD_F2_PAIRED")
+    assert torch.equal(l2, l3) and torch.equal(h2, h3)
+    monkeypatch.setenv("BCAD_FUSED_V1", "1")
+    c1, p1, l1, h1 = eng.predict_explain(x, None, "logit")
+    monkeypatch.delenv("BCAD_FUSED_V1")
+    assert np.abs(_np(l1) - _np(l2)).max() <= 2e-3 * max(1.0, float(l1.abs().max()))
+    assert np.abs(_np(h1) - _np(h2)).max() <= 5e-3
+    eng.close()
+    # both against the oracle, every image
+    monkeypatch.setenv("BCAD_F2_PAIRED", "1")
+    e2 = engine_from(cfg, p, precision="fp16", max_batch=16)
+    _check(cfg, p, x, e2, 9)
+    e2.close()
+
+
 def test_tensor_path_valid_conv_odd_sizes():
     """pad=0 (valid) with odd maps: 61 -> 59 -> 29 -> 27 -> 13; first-index pooling, softmax head, HWC flatten."""
     cfg = ocnn.NetConfig((61, 61, 1), 2, [(32, 3), (64, 3)], [32], 0.01, 0.01, 0, "hwc", "first", "softmax")

@@ -230,6 +230,24 @@ def test_torch_mirror_train_model(tmp_path):
     assert float((m2(Xt).argmax(1).cpu() == yt).float().mean()) >= 0.9
 
 
+def test_torch_mirror_train_model_on_tensor_cores(tmp_path):
+    """train_model(..., tensor_cores=True): the mirror's training loop with the tcgen05 kernels (dropout on) learns the toy problem too,
+    and refuses a network without an eligible block."""
+    from bcad_b200 import ADCNNM as A
+    shape = (32, 32, 1)
+    X, y = _toy_dataset(32, shape, 2)
+    Xt, yt = torch.from_numpy(X), torch.from_numpy(y).long()
+    loader = [(Xt[i:i + 8], yt[i:i + 8]) for i in range(0, 32, 8)]
+    torch.manual_seed(0)
+    m = A.CNNModel(shape, 2, conv_layers=[(32, 3), (64, 3)], hidden_units=[128, 16], dropout_rate=0.2)
+    hist, best = A.train_model(m, loader, loader, epochs=12, lr=2e-3, save_path=str(tmp_path / "best.pth"), tensor_cores=True)
+    assert len(hist) == 12 and hist[-1]["loss"] < hist[0]["loss"] and best >= 0.9
+    small = A.CNNModel((16, 16, 1), 2, conv_layers=[(4, 3), (8, 3)], hidden_units=[16, 8], dropout_rate=0.2)
+    Xs = torch.zeros((8, 16, 16, 1))
+    with pytest.raises(ValueError, match="no conv block"):
+        A.train_model(small, [(Xs, yt[:8])], [(Xs, yt[:8])], epochs=1, tensor_cores=True)
+
+
 def test_nccl_data_parallel_step_matches_full_batch():
     """2 ranks over NCCL (needs 2 GPUs; the driver's 1-GPU run skips it -- the gloo test covers the collective on CPU)."""
     import subprocess
@@ -274,7 +292,6 @@ def test_fast_training_matches_the_fp32_kernels(shape, pad, B, hidden):
                 assert err <= 1e-3 * max(1e-12, np.abs(b).max()), f"step {step} {k}[{i}]: err {err} vs max {np.abs(b).max()}"
         ref.apply_update(g_ref, "adam", lr=1e-3)
         fast.apply_update(g_fast, "adam", lr=1e-3)
-    names = [n for n, _ in fast.last_profile()] if hasattr(fast, "last_profile") else []
     ref.close()
     fast.close()
 
