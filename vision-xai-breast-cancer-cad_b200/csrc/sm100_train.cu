@@ -70,21 +70,43 @@ struct TcSmem {
 };
 
 // row of `n8` items of 8 fp32 values -> hi / lo 16-byte items of a ring row (256 producer threads)
+// 8 fp32 values -> one hi and one lo 16-byte item
+__device__ __forceinline__ void split8(const float4& v0, const float4& v1, uint4& hi, uint4& lo, bool bf) {
+    hi.x = split_hi_lo(v0.x, v0.y, lo.x, bf);
+    hi.y = split_hi_lo(v0.z, v0.w, lo.y, bf);
+    hi.z = split_hi_lo(v1.x, v1.y, lo.z, bf);
+    hi.w = split_hi_lo(v1.z, v1.w, lo.w, bf);
+}
+
+constexpr int TC_U = 4;                       // producer items in flight per thread: all loads of a group are issued before the first conversion
+
+// row of W * CIN fp32 values -> hi / lo 16-byte items of a ring row (256 producer threads)
 template <int CIN>
 __device__ __forceinline__ void produce_row(const float* __restrict__ src, int W, uint8_t* row, int planeb, int pad, int ptid, bool bf) {
     constexpr int CHUNKS = CIN / 8;
-    for (int it = ptid; it < W * CHUNKS; it += 32 * TC_PW) {
-        const int px = it / CHUNKS, ch = it % CHUNKS;
-        const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + (size_t)px * CIN + ch * 8));
-        const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + (size_t)px * CIN + ch * 8 + 4));
-        uint4 hi, lo;
-        hi.x = split_hi_lo(v0.x, v0.y, lo.x, bf);
-        hi.y = split_hi_lo(v0.z, v0.w, lo.y, bf);
-        hi.z = split_hi_lo(v1.x, v1.y, lo.z, bf);
-        hi.w = split_hi_lo(v1.z, v1.w, lo.w, bf);
-        uint8_t* dst = row + ch * (TC_XP * 16) + (px + pad) * 16;
-        *reinterpret_cast<uint4*>(dst) = hi;
-        *reinterpret_cast<uint4*>(dst + planeb) = lo;
+    const int n = W * CHUNKS;
+    for (int it0 = ptid; it0 < n; it0 += 32 * TC_PW * TC_U) {
+        float4 v0[TC_U], v1[TC_U];
+#pragma unroll
+        for (int u = 0; u < TC_U; ++u) {
+            const int it = it0 + u * 32 * TC_PW;
+            if (it < n) {
+                v0[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)it * 8));           // item (px, ch) = 8 consecutive floats of the row
+                v1[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)it * 8 + 4));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < TC_U; ++u) {
+            const int it = it0 + u * 32 * TC_PW;
+            if (it < n) {
+                const int px = it / CHUNKS, ch = it % CHUNKS;
+                uint4 hi, lo;
+                split8(v0[u], v1[u], hi, lo, bf);
+                uint8_t* dst = row + ch * (TC_XP * 16) + (px + pad) * 16;
+                *reinterpret_cast<uint4*>(dst) = hi;
+                *reinterpret_cast<uint4*>(dst + planeb) = lo;
+            }
+        }
     }
 }
 
@@ -338,39 +360,61 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad3x3_x3_kernel(TcWgradArgs 
             uint8_t* sx = smem + st * WG_STAGEB;
             uint8_t* sy = sx + 4 * WG_XROWB;
             // X rows (bf16 pairs, like dY: one MMA takes one 16-bit type): slot s = pixel x0 + s - pad, zero outside the map
-            for (int it = tid; it < 4 * WG_XS * 4; it += 32 * TC_PW) {
-                const int ch = it & 3, sl = (it >> 2) % WG_XS, k = it / (4 * WG_XS);
-                const int in_row = 2 * p - a.pad + k, px = x0 + sl - a.pad;
-                if (in_row < 0 || in_row >= a.H) continue;                       // the issuer skips this row
-                uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
-                if (px >= 0 && px < a.W) {
-                    const float* src = a.x + (((size_t)b * a.H + in_row) * a.W + px) * 32 + ch * 8;
-                    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src)), v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
-                    hi.x = split_hi_lo(v0.x, v0.y, lo.x, true);
-                    hi.y = split_hi_lo(v0.z, v0.w, lo.y, true);
-                    hi.z = split_hi_lo(v1.x, v1.y, lo.z, true);
-                    hi.w = split_hi_lo(v1.z, v1.w, lo.w, true);
+            for (int it0 = tid; it0 < 4 * WG_XS * 4; it0 += 32 * TC_PW * TC_U) {
+                float4 v0[TC_U], v1[TC_U];
+                bool ok[TC_U];
+#pragma unroll
+                for (int u = 0; u < TC_U; ++u) {
+                    const int it = it0 + u * 32 * TC_PW;
+                    const int ch = it & 3, sl = (it >> 2) % WG_XS, k = it / (4 * WG_XS);
+                    const int in_row = 2 * p - a.pad + k, px = x0 + sl - a.pad;
+                    ok[u] = it < 4 * WG_XS * 4 && in_row >= 0 && in_row < a.H && px >= 0 && px < a.W;
+                    if (ok[u]) {
+                        const float* src = a.x + (((size_t)b * a.H + in_row) * a.W + px) * 32 + ch * 8;
+                        v0[u] = __ldg(reinterpret_cast<const float4*>(src));
+                        v1[u] = __ldg(reinterpret_cast<const float4*>(src + 4));
+                    }
                 }
-                uint8_t* dst = sx + k * WG_XROWB + ch * (WG_XS * 16) + sl * 16;
-                *reinterpret_cast<uint4*>(dst) = hi;
-                *reinterpret_cast<uint4*>(dst + WG_XPLANE) = lo;
+#pragma unroll
+                for (int u = 0; u < TC_U; ++u) {
+                    const int it = it0 + u * 32 * TC_PW;
+                    if (it >= 4 * WG_XS * 4) continue;
+                    const int ch = it & 3, sl = (it >> 2) % WG_XS, k = it / (4 * WG_XS);
+                    const int in_row = 2 * p - a.pad + k;
+                    if (in_row < 0 || in_row >= a.H) continue;                   // the issuer skips this row
+                    uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+                    if (ok[u]) split8(v0[u], v1[u], hi, lo, true);
+                    uint8_t* dst = sx + k * WG_XROWB + ch * (WG_XS * 16) + sl * 16;
+                    *reinterpret_cast<uint4*>(dst) = hi;
+                    *reinterpret_cast<uint4*>(dst + WG_XPLANE) = lo;
+                }
             }
             // dY rows (bf16 pairs): slot s = pixel x0 + s, zero outside the map / below the last row
-            for (int it = tid; it < 2 * 64 * 8; it += 32 * TC_PW) {
-                const int ch = it & 7, sl = (it >> 3) & 63, r = it >> 9;
-                const int y = 2 * p + r, px = x0 + sl;
-                uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
-                if (y < a.Ho && px < a.Wo) {
-                    const float* src = a.dy + (((size_t)b * a.Ho + y) * a.Wo + px) * 64 + ch * 8;
-                    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src)), v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
-                    hi.x = split_hi_lo(v0.x, v0.y, lo.x, true);
-                    hi.y = split_hi_lo(v0.z, v0.w, lo.y, true);
-                    hi.z = split_hi_lo(v1.x, v1.y, lo.z, true);
-                    hi.w = split_hi_lo(v1.z, v1.w, lo.w, true);
+            for (int it0 = tid; it0 < 2 * 64 * 8; it0 += 32 * TC_PW * TC_U) {
+                float4 v0[TC_U], v1[TC_U];
+                bool ok[TC_U];
+#pragma unroll
+                for (int u = 0; u < TC_U; ++u) {
+                    const int it = it0 + u * 32 * TC_PW;
+                    const int ch = it & 7, sl = (it >> 3) & 63, r = it >> 9;
+                    const int y = 2 * p + r, px = x0 + sl;
+                    ok[u] = y < a.Ho && px < a.Wo;
+                    if (ok[u]) {
+                        const float* src = a.dy + (((size_t)b * a.Ho + y) * a.Wo + px) * 64 + ch * 8;
+                        v0[u] = __ldg(reinterpret_cast<const float4*>(src));
+                        v1[u] = __ldg(reinterpret_cast<const float4*>(src + 4));
+                    }
                 }
-                uint8_t* dst = sy + (r * 8 + ch) * (64 * 16) + sl * 16;
-                *reinterpret_cast<uint4*>(dst) = hi;
-                *reinterpret_cast<uint4*>(dst + WG_YPLANE) = lo;
+#pragma unroll
+                for (int u = 0; u < TC_U; ++u) {
+                    const int it = it0 + u * 32 * TC_PW;
+                    const int ch = it & 7, sl = (it >> 3) & 63, r = it >> 9;
+                    uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+                    if (ok[u]) split8(v0[u], v1[u], hi, lo, true);
+                    uint8_t* dst = sy + (r * 8 + ch) * (64 * 16) + sl * 16;
+                    *reinterpret_cast<uint4*>(dst) = hi;
+                    *reinterpret_cast<uint4*>(dst + WG_YPLANE) = lo;
+                }
             }
             fence_proxy_async();
             __syncwarp();
@@ -631,7 +675,8 @@ constexpr int DG_SPLANE = 16 * DG_OCT;                  // one plane of a stream
 constexpr int DG_STAGEB = 2 * DG_SPLANE;
 constexpr int DG_RPLANE = 32 * DG_OCT;                  // resident dz plane: 32 octets (256 units MN-major, or 256 units as 32 K-chunks K-major)
 constexpr int DG_OFF_R = DG_NST * DG_STAGEB;
-constexpr int DG_OFF_BAR = DG_OFF_R + 2 * DG_RPLANE;
+constexpr int DG_OFF_STG = DG_OFF_R + 2 * DG_RPLANE;     // 4 epilogue warps x [32 rows][33] floats: accumulator rows -> row-contiguous stores
+constexpr int DG_OFF_BAR = DG_OFF_STG + 4 * 32 * 33 * 4;
 constexpr int DG_TOTAL = DG_OFF_BAR + 256;
 constexpr int DG_THREADS = 32 * (TC_PW + 1 + 4);
 
@@ -693,20 +738,28 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dense_bwd_x3_kernel(DenseBwdArg
                 uint8_t* dstb = smem + st * DG_STAGEB;
                 const int nrows = (MODE == 0) ? a.B : 64;
                 const float* base = a.src + (size_t)(MODE == 0 ? 0 : q * 64) * a.flat + (size_t)t * 128;
-                for (int it = tid; it < 16 * 64; it += 32 * TC_PW) {
-                    const int oct = it & 15, k = it >> 4;
-                    uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
-                    if (k < nrows) {
-                        const float* src = base + (size_t)k * a.flat + oct * 8;
-                        const float4 v0 = __ldg(reinterpret_cast<const float4*>(src)), v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
-                        hi.x = split_hi_lo(v0.x, v0.y, lo.x, true);
-                        hi.y = split_hi_lo(v0.z, v0.w, lo.y, true);
-                        hi.z = split_hi_lo(v1.x, v1.y, lo.z, true);
-                        hi.w = split_hi_lo(v1.z, v1.w, lo.w, true);
+                for (int it0 = tid; it0 < 16 * 64; it0 += 32 * TC_PW * TC_U) {          // all loads of a group first: DRAM latency paid once
+                    float4 v0[TC_U], v1[TC_U];
+#pragma unroll
+                    for (int u = 0; u < TC_U; ++u) {
+                        const int it = it0 + u * 32 * TC_PW;
+                        const int oct = it & 15, k = it >> 4;
+                        if (k < nrows) {
+                            const float* src = base + (size_t)k * a.flat + oct * 8;
+                            v0[u] = __ldg(reinterpret_cast<const float4*>(src));
+                            v1[u] = __ldg(reinterpret_cast<const float4*>(src + 4));
+                        }
                     }
-                    uint8_t* dst = dstb + oct * DG_OCT + (k >> 3) * 128 + (k & 7) * 16;
-                    *reinterpret_cast<uint4*>(dst) = hi;
-                    *reinterpret_cast<uint4*>(dst + DG_SPLANE) = lo;
+#pragma unroll
+                    for (int u = 0; u < TC_U; ++u) {
+                        const int it = it0 + u * 32 * TC_PW;
+                        const int oct = it & 15, k = it >> 4;
+                        uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+                        if (k < nrows) split8(v0[u], v1[u], hi, lo, true);
+                        uint8_t* dst = dstb + oct * DG_OCT + (k >> 3) * 128 + (k & 7) * 16;
+                        *reinterpret_cast<uint4*>(dst) = hi;
+                        *reinterpret_cast<uint4*>(dst + DG_SPLANE) = lo;
+                    }
                 }
                 fence_proxy_async();
                 __syncwarp();
@@ -782,8 +835,11 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dense_bwd_x3_kernel(DenseBwdArg
             tc_fence_after();
             if (MODE == 0) {
                 const int halves = a.units / 128;
+                // a lane holds 32 consecutive columns of ITS row (rows are `flat` floats apart): through a padded per-warp tile so that a
+                // warp's store instruction writes four 128-byte row segments instead of thirty-two 16-byte pieces 1 MB apart
+                float* stg = reinterpret_cast<float*>(smem + DG_OFF_STG) + (warp - (TC_PW + 1)) * (32 * 33);
                 for (int h = 0; h < halves; ++h) {
-                    float* dst = a.out + (size_t)(h * 128 + row) * a.flat + (size_t)t * 128;
+                    float* dst = a.out + (size_t)(h * 128 + quad * 32) * a.flat + (size_t)t * 128;
 #pragma unroll 1
                     for (int c = 0; c < 4; ++c) {
                         float v[32];
@@ -795,8 +851,15 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dense_bwd_x3_kernel(DenseBwdArg
                             if (lane == 0) mbar_arrive(&tempty[j]);
                         }
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            *reinterpret_cast<float4*>(dst + c * 32 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        for (int q = 0; q < 32; ++q) stg[lane * 33 + q] = v[q];
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = i * 4 + (lane >> 3), c4 = lane & 7;
+                            const float* sp = stg + r * 33 + c4 * 4;
+                            *reinterpret_cast<float4*>(dst + (size_t)r * a.flat + c * 32 + c4 * 4) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                        }
+                        __syncwarp();
                     }
                 }
             } else {
@@ -868,19 +931,30 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dense_fwd_x3_kernel(DenseFwdArg
             if (g >= (uint32_t)DF_NST) mbar_wait(&empty[st], ((g / DF_NST) - 1) & 1);
             uint8_t* sa = smem + st * DF_STAGEB;
             uint8_t* sb = sa + 2 * DF_APLANE;
-            // W tile: item (unit row m, chunk k8) = 8 consecutive k of row m
-            for (int it = tid; it < a.units * 8; it += 32 * TC_PW) {
-                const int k8 = it & 7, mrow = it >> 3;
-                const float* src = a.w + (size_t)mrow * a.flat + (size_t)c * 64 + k8 * 8;
-                const float4 v0 = __ldg(reinterpret_cast<const float4*>(src)), v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
-                uint4 hi, lo;
-                hi.x = split_hi_lo(v0.x, v0.y, lo.x, false);
-                hi.y = split_hi_lo(v0.z, v0.w, lo.y, false);
-                hi.z = split_hi_lo(v1.x, v1.y, lo.z, false);
-                hi.w = split_hi_lo(v1.z, v1.w, lo.w, false);
-                uint8_t* dst = sa + k8 * DF_ALBO + mrow * 16;
-                *reinterpret_cast<uint4*>(dst) = hi;
-                *reinterpret_cast<uint4*>(dst + DF_APLANE) = lo;
+            // W tile: item (unit row m, chunk k8) = 8 consecutive k of row m; all loads of a group of TC_U items first
+            const int na = a.units * 8;
+            for (int it0 = tid; it0 < na; it0 += 32 * TC_PW * TC_U) {
+                float4 v0[TC_U], v1[TC_U];
+#pragma unroll
+                for (int u = 0; u < TC_U; ++u) {
+                    const int it = it0 + u * 32 * TC_PW;
+                    if (it < na) {
+                        const float* src = a.w + (size_t)(it >> 3) * a.flat + (size_t)c * 64 + (it & 7) * 8;
+                        v0[u] = __ldg(reinterpret_cast<const float4*>(src));
+                        v1[u] = __ldg(reinterpret_cast<const float4*>(src + 4));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < TC_U; ++u) {
+                    const int it = it0 + u * 32 * TC_PW;
+                    if (it < na) {
+                        uint4 hi, lo;
+                        split8(v0[u], v1[u], hi, lo, false);
+                        uint8_t* dst = sa + (it & 7) * DF_ALBO + (it >> 3) * 16;
+                        *reinterpret_cast<uint4*>(dst) = hi;
+                        *reinterpret_cast<uint4*>(dst + DF_APLANE) = lo;
+                    }
+                }
             }
             // p tile: item (image b, chunk k8); images >= B are zero
             for (int it = tid; it < 64 * 8; it += 32 * TC_PW) {
@@ -889,10 +963,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dense_fwd_x3_kernel(DenseFwdArg
                 if (b < a.B) {
                     const float* src = a.p + (size_t)b * a.flat + (size_t)c * 64 + k8 * 8;
                     const float4 v0 = __ldg(reinterpret_cast<const float4*>(src)), v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
-                    hi.x = split_hi_lo(v0.x, v0.y, lo.x, false);
-                    hi.y = split_hi_lo(v0.z, v0.w, lo.y, false);
-                    hi.z = split_hi_lo(v1.x, v1.y, lo.z, false);
-                    hi.w = split_hi_lo(v1.z, v1.w, lo.w, false);
+                    split8(v0, v1, hi, lo, false);
                 }
                 uint8_t* dst = sb + k8 * DF_BLBO + b * 16;
                 *reinterpret_cast<uint4*>(dst) = hi;
