@@ -604,8 +604,9 @@ def run_ours(args, rank, world, local_rank):
                                                   "conv1_frac": a1 / pk["bf16_tflops_sustained"], "conv1_frac_burst": a1 / pk["bf16_tflops"],
                                                   "both_frac": (fl["conv0"] + fl["conv1"]) * B / ((t0 + t1) * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
                                                   "measured": "same run, BCAD_TWO_CONV_KERNELS=1, CUDA events"}
-                roof["note"] = ("both conv blocks in ONE kernel: FLOPs of block 1 (K = 9 taps, CUDA-core-bound im2col) + block 2 over the kernel's "
-                                "time; `two_kernel_variant` has the stand-alone kernels of the same run")
+                roof["note"] = ("both conv blocks in ONE kernel (conv_fused2_kernel, sm100_fused2.cu: patch-union first block on tcgen05, tensor-map TMA input "
+                                "boxes; BCAD_FUSED_V1=1 = the first generation): algorithmic FLOPs of block 1 (9 taps) + block 2 over the kernel's time; "
+                                "`two_kernel_variant` has the stand-alone kernels of the same run")
             else:
                 li = 0 if "conv0" in name else 1
                 roof = tensor(fl[f"conv{li}"] * B)
