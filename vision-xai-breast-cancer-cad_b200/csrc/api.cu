@@ -427,6 +427,13 @@ static int forward_chunk_fp32(Model* m, const float* x, int n, bool explain, con
     if (m->fast_train) BCAD_TRY(tc_train_refresh(m, s));
     for (size_t i = 0; i < m->conv.size(); ++i) {
         ConvLayer& L = m->conv[i];
+        if (m->fast_train && i == 0 && L.Cin == 1 && L.Cout == 32 && L.CoutPad == 32 && L.k == 3 && L.y != nullptr && L.p != nullptr &&
+            getenv("BCAD_TC_NO_CONV0") == nullptr) {
+            // first block, one input channel: conv + bias + LeakyReLU + 2x2 pool in one pass, lane = filter (sm100_train.cu)
+            BCAD_LAUNCH(m, "conv0_fwd_fused", launch_conv0_fwd_fused(in, L.d_w, L.d_b, L.y, L.p, n, L.H, L.W, L.Ho, L.Wo, m->cfg.pad, m->cfg.alpha_conv, m->sms, s));
+            in = L.p;
+            continue;
+        }
         if (m->fast_train && tc_train_eligible(m, i) && L.y != nullptr) {
             // the block as a split-operand tcgen05 implicit GEMM on the fp32 NHWC tensors (sm100_train.cu), then the 2x2 pool
             TcConvArgs t;

@@ -582,6 +582,69 @@ __global__ void __launch_bounds__(256) unpool_mask_kernel(const float4* __restri
 // strip staged in shared memory.  Per-CTA partials, fixed-order final sum (deterministic).
 // dF[ky][kx][f] = sum dz[b,y,x,f] x[b, y+ky-pad, x+kx-pad]   (explainability.py:58-59 / Classes/CNNModel.py:340-352 for C = 1), db[f] = sum dz.
 // ---------------------------------------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------------------------------
+// First conv block forward for training (one input channel, 32 filters, 3x3): y = LeakyReLU(conv + b) and its 2x2 max pool in one pass,
+// lane = filter (a pixel's 32 outputs are one coalesced 128-byte store), the 4x4 input patch of a pool window broadcast from a shared-memory
+// row strip, the 9 weights + bias of the lane's filter in registers.  Same structure as conv0_bwd_fused_kernel below.
+// Reference: Classes/CNNModel.py:227-261 for C = 1 / nn.Conv2d(1, 32, 3) + LeakyReLU + MaxPool2d(2) (ADCNNM.py:48-53).
+// ---------------------------------------------------------------------------------------------------------------------------------
+constexpr int C0F_WARPS = 8;
+__global__ void __launch_bounds__(32 * C0F_WARPS) conv0_fwd_fused_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                                        float* __restrict__ y, float* __restrict__ p, int B, int H, int W, int Ho, int Wo,
+                                                                        int pad, float alpha) {
+    extern __shared__ float s_x[];                              // [4 rows][pitch]: column j = input column j - pad, zero outside the image
+    const int Hp = Ho / 2, Wp = Wo / 2, Hc = (Ho + 1) / 2, Wc = (Wo + 1) / 2;      // windows incl. the odd last row / column (computed, not pooled)
+    const int pitch = (W + 2 * pad + 4 + 1) & ~1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float wt[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wt[t] = __ldg(w + t * 32 + lane);              // packed [tap][Cin = 1][CoutPad = 32]
+    const float bl = __ldg(bias + lane);
+    const int units = B * Hc;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int b = u / Hc, wy = u % Hc;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 4 * pitch; i += blockDim.x) {
+            const int r = i / pitch, j = i % pitch;
+            const int row = 2 * wy - pad + r, col = j - pad;
+            s_x[i] = (row >= 0 && row < H && col >= 0 && col < W) ? __ldg(x + ((size_t)b * H + row) * W + col) : 0.f;
+        }
+        __syncthreads();
+        const bool row1 = 2 * wy + 1 < Ho;
+        float* y0 = y + (((size_t)b * Ho + 2 * wy) * Wo) * 32 + lane;
+        float* y1 = y0 + (size_t)Wo * 32;
+        for (int wx = warp; wx < Wc; wx += C0F_WARPS) {
+            float pt[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float2 lo = *reinterpret_cast<const float2*>(s_x + r * pitch + 2 * wx);
+                const float2 hi = *reinterpret_cast<const float2*>(s_x + r * pitch + 2 * wx + 2);
+                pt[r][0] = lo.x; pt[r][1] = lo.y; pt[r][2] = hi.x; pt[r][3] = hi.y;
+            }
+            float o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int qy = q >> 1, qx = q & 1;
+                float acc = 0.f;
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) acc = fmaf(pt[qy + ky][qx + kx], wt[ky * 3 + kx], acc);
+                acc += bl;
+                o[q] = acc > 0.f ? acc : alpha * acc;
+            }
+            const bool col1 = 2 * wx + 1 < Wo;
+            y0[(size_t)(2 * wx) * 32] = o[0];
+            if (col1) y0[(size_t)(2 * wx + 1) * 32] = o[1];
+            if (row1) {
+                y1[(size_t)(2 * wx) * 32] = o[2];
+                if (col1) y1[(size_t)(2 * wx + 1) * 32] = o[3];
+            }
+            if (wy < Hp && wx < Wp) p[(((size_t)b * Hp + wy) * Wp + wx) * 32 + lane] = fmaxf(fmaxf(o[0], o[1]), fmaxf(o[2], o[3]));
+        }
+    }
+}
+
 constexpr int C0B_WARPS = 8;
 __global__ void __launch_bounds__(32 * C0B_WARPS) conv0_bwd_fused_kernel(const float* __restrict__ g, const float* __restrict__ y, const float* __restrict__ x,
                                                                         float* __restrict__ part, int B, int H, int W, int Ho, int Wo, int pad,
@@ -1081,6 +1144,17 @@ int launch_unpool_mask(const float* g, const float* y, float* dz, int B, int Ho,
     const int blocks = (int)std::min<size_t>((size_t)148 * 16, (total + 255) / 256);
     unpool_mask_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(y), reinterpret_cast<float4*>(dz), B, Ho, Wo, C / 4,
                                               first_only, alpha);
+    BCAD_CUDA_CHECK(cudaGetLastError());
+    return BCAD_OK;
+}
+
+int launch_conv0_fwd_fused(const float* x, const float* w, const float* bias, float* y, float* p, int B, int H, int W, int Ho, int Wo, int pad, float alpha,
+                           int sms, cudaStream_t s) {
+    const int units = B * ((Ho + 1) / 2);
+    if (units == 0) return BCAD_OK;
+    const int grid = std::min(units, sms * 4);
+    const int pitch = (W + 2 * pad + 4 + 1) & ~1;
+    conv0_fwd_fused_kernel<<<grid, 32 * C0F_WARPS, (size_t)4 * pitch * sizeof(float), s>>>(x, w, bias, y, p, B, H, W, Ho, Wo, pad, alpha);
     BCAD_CUDA_CHECK(cudaGetLastError());
     return BCAD_OK;
 }

@@ -51,6 +51,9 @@ int dense_fwd_x3_splits(long long flat, int sms);
 int launch_dense_fwd_x3(const DenseFwdArgs& a, int sms, cudaStream_t s);
 // dz = (pool switch ? g : 0) * (y > 0 ? 1 : alpha): max-pool backward + LeakyReLU' in one pass (NHWC fp32, C % 4 == 0)
 int launch_unpool_mask(const float* g, const float* y, float* dz, int B, int Ho, int Wo, int C, int first_only, float alpha, cudaStream_t s);
+// first conv block with ONE input channel and 32 filters, forward: y (post-activation) and its 2x2 max pool in one pass; w = packed [9][1][32]
+int launch_conv0_fwd_fused(const float* x, const float* w, const float* bias, float* y, float* p, int B, int H, int W, int Ho, int Wo, int pad, float alpha,
+                           int sms, cudaStream_t s);
 // first conv block with ONE input channel and 32 filters: pool backward + LeakyReLU' + weight / bias gradients without writing dz
 int conv0_bwd_fused_parts(int sms);
 int launch_conv0_bwd_fused(const float* g, const float* y, const float* x, float* scratch, float* dw, float* db, int B, int H, int W, int Ho, int Wo,
