@@ -8,7 +8,11 @@
 // ADCNNM.py:72-78 / autograd.
 //
 //   conv3x3_x3_kernel<CIN, COUT, ABF>   y[b, oy, ox, :] = act(sum_taps x[b, oy+dy-pad, ox+dx-pad, :] . w[tap] + bias)      (fwd: 32 -> 64, dgrad: 64 -> 32)
-//   wgrad3x3_x3_kernel                   dW[tap][ci][co] = sum_{b, y, x} X[b, y+dy-pad, x+dx-pad, ci] dY[b, y, x, co]           (32 -> 64)
+//   wgrad3x3_x3_kernel                   dW[tap][ci][co] = sum_{b, y, x} X[b, y+dy-pad, x+dx-pad, ci] dY[b, y, x, co]           (32 -> 64; pixels = K, MN-major operands)
+//   dense_fwd_x3_kernel                  z[b][u] = sum_k p[b][k] W[u][k]                                                       (split-K over the CTAs)
+//   dense_bwd_x3_kernel<0 / 1>           dW[u][k] = sum_b dz[b][u] p[b][k]   /   g[b][k] = sum_u dz[b][u] W[u][k]               (streamed fp32 tiles, MN-major)
+//   CUDA-core helpers of the same step: conv0_fwd_fused / conv0_bwd_fused (first block, one input channel, lane = filter), unpool_mask,
+//   maxpool2x2_nhwc, colsum64, pack_w_x3.
 //
 // Common structure (as the second block of conv_fused_kernel): a persistent CTA walks (image, row band) items; producer warps convert
 // input rows into a shared-memory ring of "C8-planar" rows [plane hi|lo][channel octet][pixel slot][8 x 16 bit] -- a tap's column shift is a
